@@ -1,0 +1,559 @@
+// ORACLE / TEST INFRASTRUCTURE ONLY -- never linked into the product.
+//
+// Driver around the UNMODIFIED reference (stark + symx + tmcd, built from /root/reference by
+// oracle/Makefile.ref into oracle/_ref/).  Two jobs:
+//   1. `--dump DIR`: run a deterministic scene for a few steps through the reference's public API and
+//      write every input and every stage output of ONE Newton iteration (SURVEY.md section 8(c) parity
+//      protocol): per-potential connectivity + bound arrays, per-element [E | grad | Hessian] outputs,
+//      global E / grad, the assembled 3x3-BCSR (rows/cols/float vals), the PCG solution, the six
+//      proximity lists, the edge-triangle intersection list and the PD-projected element Hessians.
+//      tests/golden/make_golden.py packs these into the committed .npz fixtures.
+//   2. `--bench`: time `newton->solve()` over K time steps and print Newton-iterations/s as one JSON line
+//      (the CPU baseline / `bench.py --impl reference` arm).
+//
+// The `#define private public` below only widens access for *reading* internal state (contact tables,
+// compiled potentials); no reference source is modified or copied.
+#include <algorithm>
+#include <array>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <filesystem>
+#include <fstream>
+#include <functional>
+#include <iomanip>
+#include <iostream>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <sstream>
+#include <string>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+#include <omp.h>
+#include <Eigen/Dense>
+#include <Eigen/Sparse>
+
+#define private public
+#define protected public
+#include <stark>
+#undef private
+#undef protected
+
+namespace fs = std::filesystem;
+
+// ---------------------------------------------------------------------------------------------------
+// tiny dump helpers
+// ---------------------------------------------------------------------------------------------------
+struct Dumper
+{
+	std::string dir;
+	std::ostringstream meta;
+	bool first = true;
+
+	explicit Dumper(const std::string& d) : dir(d) { fs::create_directories(d); meta << "{\n"; }
+	void key(const std::string& k) { if (!first) meta << ",\n"; first = false; meta << "  \"" << k << "\": "; }
+	void num(const std::string& k, double v) { key(k); meta << std::setprecision(17) << v; }
+	void integer(const std::string& k, long long v) { key(k); meta << v; }
+	void str(const std::string& k, const std::string& v) { key(k); meta << "\"" << v << "\""; }
+	void raw(const std::string& k, const std::string& json) { key(k); meta << json; }
+	template<typename T> void bin(const std::string& name, const T* p, size_t n)
+	{
+		std::ofstream f(dir + "/" + name + ".bin", std::ios::binary);
+		if (n > 0) f.write(reinterpret_cast<const char*>(p), sizeof(T) * n);
+	}
+	void finish() { meta << "\n}\n"; std::ofstream f(dir + "/meta.json"); f << meta.str(); }
+};
+
+struct Args
+{
+	std::string scene = "tetdrop";
+	int n = 4;           // grid subdivisions (per axis, tetdrop) / nx (tetbar)
+	int ny = -1, nz = -1;
+	int steps = 3;       // time steps to run before the dump / to time in bench mode
+	int warmup = 1;      // bench: untimed time steps before timing (first step includes JIT/init)
+	int threads = -1;
+	std::string dump = "";
+	bool bench = false;
+	double drop = 0.003; // initial gap between body and floor contact surfaces' zero plane
+	double dt = 0.01;
+	std::string codegen = "";
+	bool verbose = false;
+	double vz = 0.0;     // initial downward speed (to reach contact quickly in small fixtures)
+	bool llt = false;
+};
+
+static Args parse(int argc, char** argv)
+{
+	Args a;
+	for (int i = 1; i < argc; i++) {
+		std::string s = argv[i];
+		auto next = [&]() { if (i + 1 >= argc) { std::cerr << "missing value for " << s << "\n"; exit(2); } return std::string(argv[++i]); };
+		if (s == "--scene") a.scene = next();
+		else if (s == "--n") a.n = std::stoi(next());
+		else if (s == "--ny") a.ny = std::stoi(next());
+		else if (s == "--nz") a.nz = std::stoi(next());
+		else if (s == "--steps") a.steps = std::stoi(next());
+		else if (s == "--warmup") a.warmup = std::stoi(next());
+		else if (s == "--threads") a.threads = std::stoi(next());
+		else if (s == "--dump") a.dump = next();
+		else if (s == "--bench") a.bench = true;
+		else if (s == "--drop") a.drop = std::stod(next());
+		else if (s == "--dt") a.dt = std::stod(next());
+		else if (s == "--vz") a.vz = std::stod(next());
+		else if (s == "--codegen") a.codegen = next();
+		else if (s == "--verbose") a.verbose = true;
+		else if (s == "--llt") a.llt = true;
+		else { std::cerr << "unknown arg " << s << "\n"; exit(2); }
+	}
+	return a;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// scenes (BASELINE.json configs, built only through the reference's public API)
+// ---------------------------------------------------------------------------------------------------
+struct Scene
+{
+	std::unique_ptr<stark::Simulation> sim;
+	std::function<void()> per_step = nullptr;
+};
+
+static stark::Settings base_settings(const Args& a, const std::string& name)
+{
+	stark::Settings settings;
+	settings.output.simulation_name = name;
+	settings.output.output_directory = "/tmp/stark_ref_out/" + name;
+	if (!a.codegen.empty()) settings.output.codegen_directory = a.codegen;
+	settings.output.enable_frame_writes = false;
+	settings.output.enable_output = false;
+	settings.output.console_verbosity = a.verbose ? symx::Verbosity::Full : symx::Verbosity::Minimal;
+	settings.output.file_verbosity = symx::Verbosity::Minimal;
+	settings.simulation.max_time_step_size = a.dt;
+	if (a.threads > 0) settings.execution.n_threads = a.threads;
+	else settings.execution.n_threads = omp_get_max_threads();
+	if (a.llt) settings.newton.linear_solver = symx::LinearSolver::DirectLLT;
+	return settings;
+}
+
+// C2: n^3 tet grid (Soft_Rubber) dropped onto a fixed rigid floor box, IPC contact + friction.
+static Scene scene_tetdrop(const Args& a)
+{
+	Scene sc;
+	stark::Settings settings = base_settings(a, "tetdrop");
+	sc.sim = std::make_unique<stark::Simulation>(settings);
+	auto& sim = *sc.sim;
+
+	stark::EnergyFrictionalContact::GlobalParams cp;
+	cp.default_contact_thickness = 0.001;
+	cp.min_contact_stiffness = 1e8;
+	sim.interactions->contact->set_global_params(cp);
+
+	auto material = stark::Volume::Params::Soft_Rubber();
+	auto [V, T, H] = sim.presets->deformables->add_volume_grid("body", { 1.0, 1.0, 1.0 }, { a.n, a.n, a.n }, material);
+	H.point_set.add_displacement({ 0.0, 0.0, 0.5 + a.drop });
+	if (a.vz != 0.0) {
+		for (int i = 0; i < H.point_set.size(); i++) H.point_set.set_velocity(i, { 0.0, 0.0, -a.vz });
+	}
+
+	auto [Vf, Cf, floor] = sim.presets->rigidbodies->add_box("floor", 1.0, { 4.0, 4.0, 0.1 });
+	floor.rigidbody.set_translation({ 0.0, 0.0, -0.05 });
+	sim.rigidbodies->add_constraint_fix(floor.rigidbody);
+	sim.interactions->contact->set_friction(floor.contact, H.contact, 0.5);
+	return sc;
+}
+
+// C5: tet bar, both end caps prescribed, one cap rotating 90 deg/s, no contact.
+static Scene scene_tetbar(const Args& a)
+{
+	Scene sc;
+	stark::Settings settings = base_settings(a, "tetbar");
+	settings.simulation.init_frictional_contact = false;
+	sc.sim = std::make_unique<stark::Simulation>(settings);
+	auto& sim = *sc.sim;
+	const int nx = a.n, ny = (a.ny > 0) ? a.ny : a.n, nz = (a.nz > 0) ? a.nz : 8 * a.n;
+	const double h = 1.0 / 22.0;  // element size of the 22x22x172 headline bar
+	const Eigen::Vector3d dim = { nx * h, ny * h, nz * h };
+	auto material = stark::Volume::Params::Soft_Rubber();
+	auto [V, T, H] = sim.presets->deformables->add_volume_grid("bar", dim, { nx, ny, nz }, material);
+	const double hz = 0.5 * dim[2];
+	auto bc0 = sim.deformables->prescribed_positions->add_inside_aabb(H.point_set, { 0.0, 0.0, -hz }, { dim[0], dim[1], 0.001 }, stark::EnergyPrescribedPositions::Params());
+	auto bc1 = sim.deformables->prescribed_positions->add_inside_aabb(H.point_set, { 0.0, 0.0, hz }, { dim[0], dim[1], 0.001 }, stark::EnergyPrescribedPositions::Params());
+	auto bc1p = std::make_shared<decltype(bc1)>(bc1);
+	sim.add_time_event(0.0, 1e9, [bc1p, hz](double t) { bc1p->set_transformation({ 0.0, 0.0, 0.0 }, 90.0 * t, { 0.0, 0.0, 1.0 }); });
+	return sc;
+}
+
+// C1 / C3: n x n cloth grid dropped over a fixed rigid box.
+static Scene scene_cloth(const Args& a, bool discrete_shells, double mu)
+{
+	Scene sc;
+	stark::Settings settings = base_settings(a, "cloth");
+	sc.sim = std::make_unique<stark::Simulation>(settings);
+	auto& sim = *sc.sim;
+	stark::EnergyFrictionalContact::GlobalParams cp;
+	cp.default_contact_thickness = 0.002;
+	sim.interactions->contact->set_global_params(cp);
+	auto material = stark::Surface::Params::Cotton_Fabric();
+	if (discrete_shells) material.bending.flat_rest_angle = false;
+	auto [V, T, cloth] = sim.presets->deformables->add_surface_grid("cloth", Eigen::Vector2d(0.4, 0.4), { a.n, a.n }, material);
+	if (a.drop != 0.003) cloth.point_set.add_displacement({ 0.0, 0.0, a.drop });
+	auto box = sim.presets->rigidbodies->add_box("box", 1.0, 0.08);
+	box.handler.rigidbody.add_translation({ 0.0, 0.0, -0.08 });
+	auto fix = sim.rigidbodies->add_constraint_fix(box.handler.rigidbody);
+	if (mu > 0.0) sim.interactions->contact->set_friction(box.handler.contact, cloth.contact, mu);
+	auto fixp = std::make_shared<decltype(fix)>(fix);
+	sim.add_time_event(0.0, 1e9, [fixp](double t) { fixp->set_transformation({ 0.0, 0.0, -0.08 - 0.1 * std::sin(t) }, 90.0 * t, { 0.0, 0.0, 1.0 }); });
+	return sc;
+}
+
+static Scene make_scene(const Args& a)
+{
+	if (a.scene == "tetdrop") return scene_tetdrop(a);
+	if (a.scene == "tetbar") return scene_tetbar(a);
+	if (a.scene == "cloth") return scene_cloth(a, false, 0.0);
+	if (a.scene == "cloth_shells") return scene_cloth(a, true, 0.3);
+	std::cerr << "unknown scene " << a.scene << "\n";
+	exit(2);
+}
+
+// One time step exactly as Simulation::run does it (script cycle, then the step).
+static void one_step(stark::Simulation& sim) { sim.run_one_time_step(); }
+
+// ---------------------------------------------------------------------------------------------------
+// dump of one Newton iteration on an injected state
+// ---------------------------------------------------------------------------------------------------
+static void dump_iteration(const Args& a, stark::Simulation& sim)
+{
+	stark::core::Stark& st = sim.get_stark();
+	auto gp = st.global_potential;
+	auto ctx = st.context;
+	const int n_threads = ctx->n_threads;
+	Dumper D(a.dump);
+	D.str("scene", a.scene);
+	D.integer("n", a.n);
+	D.integer("steps_before_dump", a.steps);
+	D.num("dt", st.dt);
+	D.num("time", st.current_time);
+	D.raw("gravity", "[" + std::to_string(st.gravity[0]) + "," + std::to_string(st.gravity[1]) + "," + std::to_string(st.gravity[2]) + "]");
+
+	// Script + before_time_step exactly as the next step would do, then inject v1 := v0 as the DoF state
+	// (the reference's own initial guess is v1 = 0; a non-zero state exercises every derivative term).
+	sim.get_script().run_a_cycle(st.current_time);
+	st.callbacks->run_before_time_step();
+	{
+		auto& dyn = *sim.deformables->point_sets;
+		for (int i = 0; i < dyn.size(); i++) dyn.v1[i] = dyn.v0[i];
+		auto& rb = *sim.rigidbodies->rb;
+		for (int i = 0; i < rb.get_n_bodies(); i++) { rb.v1[i] = rb.v0[i]; rb.w1[i] = rb.w0[i]; }
+		// small deterministic perturbation so that rigid DoFs and symmetric nodes are not exactly zero
+		for (int i = 0; i < dyn.size(); i++) {
+			dyn.v1[i] += 1e-3 * Eigen::Vector3d(std::sin(0.37 * i), std::cos(0.91 * i), std::sin(1.3 * i + 0.5));
+		}
+		for (int i = 0; i < rb.get_n_bodies(); i++) {
+			rb.v1[i] += 1e-4 * Eigen::Vector3d(0.3, -0.2, 0.5);
+			rb.w1[i] += 1e-4 * Eigen::Vector3d(-0.1, 0.4, 0.2);
+		}
+	}
+	st.callbacks->newton->run_before_energy_evaluation();
+
+	// ---- DoFs
+	const int ndofs = gp->get_total_n_dofs();
+	D.integer("ndofs", ndofs);
+	{
+		std::ostringstream s; s << "[";
+		const auto& offs = gp->get_dofs_offsets();
+		for (size_t i = 0; i < offs.size(); i++) { if (i) s << ","; s << offs[i]; }
+		s << "]";
+		D.raw("dof_offsets", s.str());
+		std::ostringstream ids; ids << "[";
+		const auto& maps = gp->get_dof_maps();
+		for (size_t i = 0; i < maps.size(); i++) { if (i) ids << ","; ids << "\"" << maps[i].id() << "\""; }
+		ids << "]";
+		D.raw("dof_array_ids", ids.str());
+		std::vector<double> u(ndofs);
+		gp->get_dofs(u.data());
+		D.bin("dofs", u.data(), u.size());
+	}
+
+	// ---- the compiled potentials NewtonsMethod itself holds (a second instance would re-hash and re-JIT)
+	symx::SecondOrderCompiledGlobal& compiled = *st.newton->compiled;
+
+	// ---- potentials: inputs
+	std::unordered_map<std::uintptr_t, int> array_index;
+	std::ostringstream arrays_json; arrays_json << "[";
+	std::ostringstream pots_json; pots_json << "[";
+	const auto& pots = gp->get_potentials();
+	bool first_array = true;
+	for (size_t p = 0; p < pots.size(); p++) {
+		const symx::Potential& pot = *pots[p];
+		auto mws = pot.get_mws();
+		const int n_elem = mws->conn.n_elements();
+		const int stride = mws->conn.stride;
+		if (p) pots_json << ",\n    ";
+		pots_json << "{\"name\": \"" << pot.get_name() << "\", \"n_elements\": " << n_elem << ", \"conn_stride\": " << stride
+			<< ", \"has_condition\": " << (pot.has_conditional() ? "true" : "false")
+			<< ", \"n_symbols\": " << mws->ws.get_n_symbols();
+		if (n_elem > 0) D.bin("pot" + std::to_string(p) + "_conn", mws->conn.data(), (size_t)n_elem * stride);
+		pots_json << ", \"maps\": [";
+		for (size_t m = 0; m < mws->maps.size(); m++) {
+			const auto& map = mws->maps[m];
+			const std::uintptr_t id = map.id();
+			auto it = array_index.find(id);
+			int aidx;
+			if (it == array_index.end()) {
+				aidx = (int)array_index.size();
+				array_index[id] = aidx;
+				const int n = map.n_elements();
+				if (!first_array) arrays_json << ","; first_array = false;
+				arrays_json << "{\"id\": \"" << id << "\", \"n_elements\": " << n << ", \"stride\": " << map.stride << "}";
+				D.bin("array" + std::to_string(aidx), map.data(), (size_t)n * map.stride);
+			} else {
+				aidx = it->second;
+			}
+			if (m) pots_json << ", ";
+			pots_json << "{\"array\": " << aidx << ", \"stride\": " << map.stride << ", \"conn_idx\": " << map.connectivity_index
+				<< ", \"first_symbol\": " << map.first_symbol_idx << "}";
+		}
+		pots_json << "]";
+
+		// DoF layout of the element (which conn column feeds each 3-block, and of which DoF set)
+		auto& cp = *compiled.compiled_potentials[p];
+		pots_json << ", \"n_dofs\": " << cp.n_dofs << ", \"dof_in_conn\": [";
+		for (size_t b = 0; b < cp.dof_in_conn.size(); b++) {
+			if (b) pots_json << ", ";
+			pots_json << "[" << cp.dof_in_conn[b].dof_set << ", " << cp.dof_in_conn[b].conn_idx << "]";
+		}
+		pots_json << "]";
+
+		// per-element outputs  [E | grad(n) | hess(n*n)]
+		const int n_out = 1 + cp.n_dofs + cp.n_dofs * cp.n_dofs;
+		if (n_elem > 0) {
+			std::vector<double> sol((size_t)n_elem * n_out, 0.0);
+			std::vector<uint8_t> active(n_elem, 1);
+			if (pot.has_conditional()) {
+				cp._evaluate_element_condition(n_threads);
+				active = cp.has_element_positive_condition;
+			}
+			cp.P__dP_du__d2P_du2.run(n_threads,
+				[&](const symx::View<double> s, int32_t e, int32_t tid, const symx::View<int32_t> conn) {
+					for (int k = 0; k < n_out; k++) sol[(size_t)e * n_out + k] = s[k];
+				}, cp.has_element_positive_condition);
+			D.bin("pot" + std::to_string(p) + "_sol", sol.data(), sol.size());
+			D.bin("pot" + std::to_string(p) + "_active", active.data(), active.size());
+		}
+		pots_json << ", \"n_out\": " << n_out << "}";
+	}
+	arrays_json << "]";
+	pots_json << "]";
+	D.raw("arrays", arrays_json.str());
+	D.raw("potentials", pots_json.str());
+
+	// ---- global evaluation
+	double E = 0.0, E_only = 0.0;
+	Eigen::VectorXd grad(ndofs);
+	compiled.evaluate_P(E_only);
+	auto eh = compiled.evaluate_P__dP_du__local_d2P_du2(E, grad);
+	D.num("E", E);
+	D.num("E_only", E_only);
+	D.num("residual_inf", grad.cwiseAbs().maxCoeff());
+	D.bin("grad", grad.data(), (size_t)ndofs);
+	D.integer("n_element_hessians", (long long)eh->size());
+
+	// ---- assembly (unprojected, as PPN does first)
+	auto hess = eh->assemble_global(n_threads, ndofs);
+	{
+		const auto& crs = *hess->crs_current;
+		D.integer("bcsr_n_block_rows", hess->n_block_rows);
+		D.integer("bcsr_nnzb", (long long)crs.cols.size());
+		D.bin("bcsr_rows", crs.rows.data(), crs.rows.size());
+		D.bin("bcsr_cols", crs.cols.data(), crs.cols.size());
+		D.bin("bcsr_vals", crs.vals.data(), crs.vals.size());
+	}
+
+	// ---- linear solve (BDPCG, same forcing tolerance as NewtonsMethod::_solve_linear_system)
+	{
+		const double residual_norm = grad.cwiseAbs().maxCoeff();
+		const double forcing = std::min(1e-2, residual_norm * std::min(0.5, std::sqrt(residual_norm)));
+		const double abs_tol = std::max(forcing, st.settings.newton.cg_abs_tolerance);
+		Eigen::VectorXd rhs = -grad, du = Eigen::VectorXd::Zero(ndofs);
+		hess->set_preconditioner(bsm::Preconditioner::BlockDiagonal);
+		hess->prepare_preconditioning(n_threads);
+		bsm::PCGContext pc;
+		bsm::PCGInfo info = bsm::solve_pcg(*hess, du.data(), rhs.data(), ndofs, abs_tol, st.settings.newton.cg_rel_tolerance,
+			st.settings.newton.cg_max_iterations, n_threads, st.settings.newton.cg_stop_on_indefiniteness, pc);
+		D.num("pcg_abs_tol", abs_tol);
+		D.num("pcg_rel_tol", st.settings.newton.cg_rel_tolerance);
+		D.integer("pcg_iterations", info.n_iterations);
+		D.integer("pcg_converged", info.converged ? 1 : 0);
+		D.num("du_dot_grad", du.dot(grad));
+		D.bin("pcg_du", du.data(), (size_t)ndofs);
+	}
+
+	// ---- PD projection of every element Hessian (clamp, eps from settings)
+	{
+		const double eps = st.settings.newton.projection_eps;
+		std::vector<double> proj;
+		std::vector<int32_t> sizes;
+		for (size_t i = 0; i < eh->hessians.size(); i++) {
+			auto& h = eh->hessians[i];
+			const int n = 3 * h.n_blocks_per_dim;
+			std::vector<double> m(h.values, h.values + n * n);
+			project_to_PD_inplace(m.data(), n, eps, false);
+			proj.insert(proj.end(), m.begin(), m.end());
+			sizes.push_back(n);
+		}
+		D.bin("projected_hessians", proj.data(), proj.size());
+		D.bin("projected_sizes", sizes.data(), sizes.size());
+		// element order of ElementHessians (block rows) so the fixtures can be matched up
+		std::vector<int32_t> rows;
+		for (size_t i = 0; i < eh->hessians.size(); i++) {
+			auto& h = eh->hessians[i];
+			for (int b = 0; b < h.n_blocks_per_dim; b++) rows.push_back(h.block_rows[b]);
+		}
+		D.bin("element_block_rows", rows.data(), rows.size());
+	}
+
+	// ---- collision detection
+	auto contact = sim.interactions->contact;
+	if (contact->is_initialized && !contact->is_empty()) {
+		std::ostringstream mj; mj << "[";
+		for (size_t g = 0; g < contact->meshes.size(); g++) {
+			auto& mesh = contact->meshes[g];
+			if (g) mj << ", ";
+			const bool dummy_tri = (mesh.loc_triangles.size() == 1 && mesh.loc_triangles[0][0] == -1);
+			mj << "{\"ps\": " << (mesh.ps == stark::PhysicalSystem::Deformable ? 0 : 1) << ", \"idx_in_ps\": " << mesh.idx_in_ps
+				<< ", \"n_vertices\": " << mesh.vertices.size() << ", \"n_triangles\": " << (dummy_tri ? 0 : mesh.loc_triangles.size())
+				<< ", \"n_edges\": " << mesh.loc_edges.size() << ", \"contact_thickness\": " << std::setprecision(17) << contact->contact_thicknesses[g] << "}";
+			D.bin("mesh" + std::to_string(g) + "_vertices", &mesh.vertices[0][0], mesh.vertices.size() * 3);
+			if (!dummy_tri) D.bin("mesh" + std::to_string(g) + "_triangles", &mesh.loc_triangles[0][0], mesh.loc_triangles.size() * 3);
+			D.bin("mesh" + std::to_string(g) + "_edges", &mesh.loc_edges[0][0], mesh.loc_edges.size() * 2);
+		}
+		mj << "]";
+		D.raw("meshes", mj.str());
+		std::ostringstream bl; bl << "[";
+		bool fb = true;
+		for (const auto& pr : contact->disabled_collision_pairs) { if (!fb) bl << ", "; fb = false; bl << "[" << pr[0] << ", " << pr[1] << "]"; }
+		bl << "]";
+		D.raw("blacklist", bl.str());
+		D.num("contact_stiffness", contact->contact_stiffness);
+
+		const double max_thickness = *std::max_element(contact->contact_thicknesses.begin(), contact->contact_thicknesses.end());
+		const double enl = 2.0 * max_thickness;
+		D.num("proximity_enlargement", enl);
+		const tmcd::ProximityResults& pr = contact->_run_proximity_detection(st, st.dt);
+		auto dump_list = [&](const std::string& name, const std::vector<std::vector<int32_t>>& rows, const std::vector<double>& dist) {
+			std::vector<int32_t> flat;
+			for (auto& r : rows) flat.insert(flat.end(), r.begin(), r.end());
+			D.bin("prox_" + name + "_ids", flat.data(), flat.size());
+			D.bin("prox_" + name + "_dist", dist.data(), dist.size());
+			D.integer("prox_" + name + "_n", (long long)rows.size());
+			D.integer("prox_" + name + "_width", rows.empty() ? 0 : (long long)rows[0].size());
+		};
+		{
+			std::vector<std::vector<int32_t>> r; std::vector<double> d;
+			for (auto& x : pr.point_triangle.point_point) { r.push_back({ x.first.set, x.first.idx, x.second.triangle.set, x.second.triangle.idx, x.second.point.idx }); d.push_back(x.distance); }
+			dump_list("pt_pp", r, d);
+		}
+		{
+			std::vector<std::vector<int32_t>> r; std::vector<double> d;
+			for (auto& x : pr.point_triangle.point_edge) { r.push_back({ x.first.set, x.first.idx, x.second.triangle.set, x.second.triangle.idx, x.second.edge.vertices[0], x.second.edge.vertices[1] }); d.push_back(x.distance); }
+			dump_list("pt_pe", r, d);
+		}
+		{
+			std::vector<std::vector<int32_t>> r; std::vector<double> d;
+			for (auto& x : pr.point_triangle.point_triangle) { r.push_back({ x.first.set, x.first.idx, x.second.set, x.second.idx }); d.push_back(x.distance); }
+			dump_list("pt_pt", r, d);
+		}
+		{
+			std::vector<std::vector<int32_t>> r; std::vector<double> d;
+			for (auto& x : pr.edge_edge.point_point) { r.push_back({ x.first.edge.set, x.first.edge.idx, x.first.point.idx, x.second.edge.set, x.second.edge.idx, x.second.point.idx }); d.push_back(x.distance); }
+			dump_list("ee_pp", r, d);
+		}
+		{
+			std::vector<std::vector<int32_t>> r; std::vector<double> d;
+			for (auto& x : pr.edge_edge.point_edge) { r.push_back({ x.first.edge.set, x.first.edge.idx, x.first.point.idx, x.second.set, x.second.idx }); d.push_back(x.distance); }
+			dump_list("ee_pe", r, d);
+		}
+		{
+			std::vector<std::vector<int32_t>> r; std::vector<double> d;
+			for (auto& x : pr.edge_edge.edge_edge) { r.push_back({ x.first.set, x.first.idx, x.second.set, x.second.idx }); d.push_back(x.distance); }
+			dump_list("ee_ee", r, d);
+		}
+		const tmcd::IntersectionResults& ir = contact->_run_intersection_detection(st, st.dt);
+		{
+			std::vector<int32_t> flat;
+			for (auto& x : ir.edge_triangle) { flat.push_back(x.first.set); flat.push_back(x.first.idx); flat.push_back(x.second.set); flat.push_back(x.second.idx); }
+			D.bin("intersections", flat.data(), flat.size());
+			D.integer("n_intersections", (long long)ir.edge_triangle.size());
+		}
+	}
+	D.finish();
+}
+
+// ---------------------------------------------------------------------------------------------------
+int main(int argc, char** argv)
+{
+	Args a = parse(argc, argv);
+	Scene sc = make_scene(a);
+	stark::Simulation& sim = *sc.sim;
+	stark::core::Stark& st = sim.get_stark();
+
+	if (!a.dump.empty()) {
+		for (int s = 0; s < a.steps; s++) one_step(sim);
+		dump_iteration(a, sim);
+
+		// residual trace of the next real step (for end-to-end comparison)
+		std::vector<double> residuals;
+		st.callbacks->newton->set_residual([&](Eigen::VectorXd& r) { const double v = r.cwiseAbs().maxCoeff(); residuals.push_back(v); return v; });
+		// restore v1 := 0 happens inside before_time_step of the next step
+		one_step(sim);
+		std::ofstream f(a.dump + "/next_step_residuals.txt");
+		f << std::setprecision(17);
+		for (double r : residuals) f << r << "\n";
+		auto stats = st.newton->get_last_solve_stats();
+		std::ofstream g(a.dump + "/next_step_stats.json");
+		g << "{\"newton_iterations\": " << stats.newton_iterations << ", \"cg_iterations\": " << stats.cg_iterations
+			<< ", \"ls_inv\": " << stats.ls_inv_iterations << ", \"ls_bt\": " << stats.ls_bt_iterations << "}\n";
+		return 0;
+	}
+
+	if (a.bench) {
+		// warm-up (includes JIT/initialization)
+		for (int s = 0; s < a.warmup; s++) one_step(sim);
+		auto& logger = sim.get_logger();
+		long long iters = 0, cg = 0, evals = 0;
+		int n_evals = 0;
+		st.callbacks->newton->set_residual([&](Eigen::VectorXd& r) { n_evals++; return r.cwiseAbs().maxCoeff(); });
+		const double t0 = omp_get_wtime();
+		double solve_time = 0.0;
+		int accepted = 0;
+		for (int s = 0; s < a.steps; s++) {
+			const double ta = omp_get_wtime();
+			const int step_before = st.current_time_step;
+			one_step(sim);
+			solve_time += omp_get_wtime() - ta;
+			auto stats = st.newton->get_last_solve_stats();
+			iters += stats.newton_iterations;
+			cg += stats.cg_iterations;
+			accepted += (st.current_time_step > step_before) ? 1 : 0;
+		}
+		const double wall = omp_get_wtime() - t0;
+		std::cout << std::setprecision(10)
+			<< "{\"impl\": \"reference\", \"scene\": \"" << a.scene << "\", \"n\": " << a.n
+			<< ", \"ndofs\": " << st.global_potential->get_total_n_dofs()
+			<< ", \"threads\": " << st.context->n_threads
+			<< ", \"steps\": " << a.steps << ", \"accepted_steps\": " << accepted
+			<< ", \"newton_iterations\": " << iters << ", \"evaluations\": " << n_evals << ", \"cg_iterations\": " << cg
+			<< ", \"wall_s\": " << wall
+			<< ", \"newton_it_per_s\": " << (wall > 0 ? iters / wall : 0.0)
+			<< ", \"time\": " << st.current_time << "}" << std::endl;
+		return 0;
+	}
+
+	std::cerr << "nothing to do: pass --dump DIR or --bench\n";
+	return 2;
+}
