@@ -1,0 +1,201 @@
+/*
+ * stark_b200 -- C-ABI of the B200-native Newton hot path of STARK.
+ *
+ * Plain pointers and sizes only; every function returns 0 on success or a negative sb_status and never throws.
+ * `sb_last_error()` gives the message of the last failure.  One context per Simulation, one host thread per
+ * context, calls are synchronous from the caller's view (SURVEY.md section 8(b) "Threading").
+ *
+ * Each group of entry points names the reference interface it replaces (paths relative to /root/reference;
+ * symx/ = stark/extern/symx/src/, tmcd/ = stark/extern/TriangleMeshCollisionDetection/src/, S/ = stark/src/).
+ */
+#ifndef STARK_B200_H
+#define STARK_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define SB_API __attribute__((visibility("default")))
+#else
+#define SB_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sb_context sb_context;
+
+enum sb_status {
+    SB_OK = 0,
+    SB_ERR_CUDA = -1,       /* a CUDA runtime call failed */
+    SB_ERR_ARG = -2,        /* invalid argument / unknown handle */
+    SB_ERR_LAYOUT = -3,     /* fetch table does not match the kernel's in[] layout */
+    SB_ERR_NO_KERNEL = -4,  /* no hand-written kernel for this potential name */
+    SB_ERR_STATE = -5       /* call made in the wrong order */
+};
+
+/* ---- context -------------------------------------------------------------------------------------------------
+ * replaces: symx::Context (symx/solver/Context.h:11-22) as far as execution resources go.
+ * `stream` is a cudaStream_t (0 = the library creates its own non-blocking stream). */
+SB_API int sb_create(sb_context** out, int device, void* stream);
+SB_API void sb_destroy(sb_context* ctx);
+SB_API const char* sb_last_error(const sb_context* ctx);
+SB_API void* sb_get_stream(sb_context* ctx);
+SB_API int sb_synchronize(sb_context* ctx);
+/* number of kernels launched by this context since creation (bench.py `gpu_launches`) */
+SB_API int64_t sb_launch_count(const sb_context* ctx);
+
+/* ---- arrays ----------------------------------------------------------------------------------------------------
+ * replaces: symx::DataMap<const double> (symx/compile/data_maps.h:86-105): an array of `n_rows` x `stride` doubles,
+ * row-major, identified by a small integer handle.  Host buffers are borrowed for the duration of the call only. */
+SB_API int sb_array_create(sb_context* ctx, const char* label, int stride, int* out_array);
+SB_API int sb_array_upload(sb_context* ctx, int array, const double* host, int n_rows);
+SB_API int sb_array_download(sb_context* ctx, int array, double* host, int n_rows);
+SB_API int sb_array_rows(sb_context* ctx, int array, int* out_rows);
+
+/* ---- degrees of freedom ---------------------------------------------------------------------------------------
+ * replaces: GlobalPotential::add_dof / get_dofs / set_dofs / get_dofs_offsets (symx/solver/GlobalPotential.cpp:86-144).
+ * DoF sets are concatenated in registration order (soft.v1, rigid.v1, rigid.w1 in STARK). */
+SB_API int sb_dof_add(sb_context* ctx, int array, int* out_set);
+SB_API int sb_dof_total(sb_context* ctx, int* out_ndofs);
+SB_API int sb_dofs_get(sb_context* ctx, double* host_u);       /* flat, length ndofs */
+SB_API int sb_dofs_set(sb_context* ctx, const double* host_u);
+
+/* ---- potentials --------------------------------------------------------------------------------------------------
+ * replaces: GlobalPotential::add_potential (symx/solver/GlobalPotential.cpp:22-84) + SecondOrderCompiledPotential
+ * (symx/solver/second_order/SecondOrderCompiledPotential.cpp:6-87) + the BlockFetch table of CompiledInLoop::run
+ * (symx/compile/CompiledInLoop_run.h:170-190).
+ * `kernel_name` is the reference's potential name ("EnergyTetStrain", "contact_rb_d_pt_tp_cubic", ...).
+ * `fetch[i]` binds in[first_slot .. first_slot+stride) to row conn[elem][conn_col] of `array` (conn_col = -1: row 0). */
+typedef struct sb_fetch {
+    int32_t array;
+    int32_t conn_col;
+    int32_t first_slot;
+    int32_t stride;
+} sb_fetch;
+SB_API int sb_potential_create(sb_context* ctx, const char* kernel_name, int conn_stride, const sb_fetch* fetch, int n_fetch, int* out_potential);
+SB_API int sb_potential_set_connectivity(sb_context* ctx, int potential, const int32_t* conn, int n_elements);
+SB_API int sb_potential_info(sb_context* ctx, int potential, int* n_in, int* n_dofs, int* n_elements);
+/* names of all built-in kernels, '\n' separated */
+SB_API const char* sb_kernel_names(void);
+
+/* ---- evaluation ---------------------------------------------------------------------------------------------------
+ * replaces: SecondOrderCompiledGlobal::{evaluate_P, evaluate_P__dP_du__local_d2P_du2}
+ * (symx/solver/second_order/SecondOrderCompiledGlobal.cpp:72-93, 119-142). */
+enum sb_eval_mode { SB_EVAL_P = 0, SB_EVAL_PGH = 2 };
+SB_API int sb_eval(sb_context* ctx, int mode, double* out_E, double* out_grad_inf);
+SB_API int sb_grad_get(sb_context* ctx, double* host_grad);   /* flat, length ndofs */
+/* per-element output of one potential as the reference lays it out: [E | grad(n) | hess(n*n) row-major] per element */
+SB_API int sb_potential_get_element_output(sb_context* ctx, int potential, double* host_sol);
+SB_API int sb_potential_get_block_rows(sb_context* ctx, int potential, int32_t* host_rows);
+
+/* ---- PD projection + assembly -----------------------------------------------------------------------------------
+ * replaces: ElementHessians::{project_to_PD_*, assemble_global, update_global}
+ * (symx/solver/second_order/ElementHessians.cpp:48-294), project_to_PD_inplace (project_to_PD.cpp:13-82) and
+ * BlockedSparseMatrix insertion (bsm/BlockedSparseMatrix.h:332-593, 782-895).
+ * project: grad_threshold < 0 projects nothing, 0 projects every element, > 0 projects elements touching a DoF block
+ * with |g|_inf >= threshold (PPN selection, NewtonsMethod.cpp:316-327).  Returns counts for the `ph` statistic. */
+SB_API int sb_project_to_pd(sb_context* ctx, double grad_threshold, double eps, int mirror, int64_t* out_n_projected, int64_t* out_n_hessians, int* out_all_projected);
+SB_API int sb_assemble(sb_context* ctx);
+SB_API int sb_bcsr_info(sb_context* ctx, int* n_block_rows, int64_t* nnzb);
+/* reference layout: rows u64[nbr+1], cols = first scalar column of the block, vals float[9*nnzb] column-major per block */
+SB_API int sb_bcsr_get(sb_context* ctx, int64_t* host_rows, int32_t* host_cols, float* host_vals);
+
+/* ---- linear solve ---------------------------------------------------------------------------------------------------
+ * replaces: NewtonsMethod::_solve_linear_system (symx/solver/NewtonsMethod.cpp:388-457), bsm::solve_pcg
+ * (bsm/solve_pcg.h:83-232) with the block-Jacobi preconditioner (bsm/BlockedSparseMatrix.h:1147-1361).
+ * Solves H du = -grad.  out_ok = 0 when p^T A p <= 0 was met (indefiniteness) or max_iterations was hit. */
+SB_API int sb_solve_pcg(sb_context* ctx, double abs_tol, double rel_tol, int max_iterations, int stop_on_indefiniteness,
+                 int* out_iterations, int* out_ok, double* out_du_dot_grad, double* out_du_inf);
+SB_API int sb_du_get(sb_context* ctx, double* host_du);
+
+/* ---- line search support ----------------------------------------------------------------------------------------------
+ * replaces: the apply_scaled_du lambda of NewtonsMethod::_line_search_inplace (symx/solver/NewtonsMethod.cpp:469-476).
+ * save: remember the current DoFs; apply: dofs = saved + step * scale * du. */
+SB_API int sb_dofs_save(sb_context* ctx);
+SB_API int sb_dofs_apply_step(sb_context* ctx, double step);
+SB_API int sb_du_scale(sb_context* ctx, double factor);
+
+/* ---- collision detection + contact lists ---------------------------------------------------------------------------------
+ * replaces: tmcd::ProximityDetection / IntersectionDetection (tmcd/ProximityDetection.cpp:74-220,
+ * tmcd/IntersectionDetection.cpp:54-108, tmcd/BroadPhasePTEEBase.cpp, tmcd/AABBs.cpp, tmcd/Octree.cpp) and the vertex
+ * update + list building of EnergyFrictionalContact (S/models/interactions/EnergyFrictionalContact.cpp:219-262, 368-799).
+ * Meshes are registered once; per-mesh vertex positions are produced on the device from the DoF arrays. */
+typedef struct sb_contact_mesh {
+    int32_t physical_system;   /* 0 = deformable, 1 = rigid body */
+    int32_t rigid_body;        /* body index when rigid */
+    int32_t n_vertices;
+    int32_t n_triangles;
+    int32_t n_edges;
+    const int32_t* vertex_global;   /* deformable: global node index of every collision vertex; rigid: NULL */
+    const double* vertices_local;   /* rigid: local coordinates (3 per vertex); deformable: NULL */
+    const int32_t* triangles;       /* 3 per triangle, local vertex ids */
+    const int32_t* edges;           /* 2 per edge, local vertex ids */
+    double contact_thickness;
+} sb_contact_mesh;
+typedef struct sb_contact_bindings {
+    /* arrays the contact module reads / binds into the contact + friction potentials */
+    int32_t soft_v1, soft_x0, soft_X;          /* deformable DoF, x0, rest positions */
+    int32_t rb_v1, rb_w1, rb_t0, rb_q0;        /* rigid DoFs and state (q0 as w,x,y,z) */
+    int32_t dt;                                /* 1x1 array holding the time step */
+} sb_contact_bindings;
+SB_API int sb_contact_init(sb_context* ctx, const sb_contact_bindings* bindings);
+SB_API int sb_contact_add_mesh(sb_context* ctx, const sb_contact_mesh* mesh, int* out_group);
+SB_API int sb_contact_blacklist(sb_context* ctx, int group_a, int group_b);
+SB_API int sb_contact_set_friction(sb_context* ctx, int group_a, int group_b, double mu);
+SB_API int sb_contact_set_params(sb_context* ctx, double contact_stiffness, double friction_stick_slide_threshold,
+                          int enable_point_triangle, int enable_edge_edge, int enable_friction);
+/* before_energy_evaluation: vertex update + proximity + the 21 contact tables (dt < 0: use the bound dt array) */
+SB_API int sb_contact_update(sb_context* ctx);
+/* before_time_step: proximity at dt = 0 + friction tables with T / bary / fn / mu */
+SB_API int sb_contact_update_friction(sb_context* ctx);
+/* is_intermediate_state_valid: number of edge-triangle intersections at the current DoFs */
+SB_API int sb_contact_count_intersections(sb_context* ctx, int* out_count);
+/* raw results for parity tests: kind 0..5 = pt_pp, pt_pe, pt_pt, ee_pp, ee_pe, ee_ee; 6 = intersections.
+ * ids rows as in tests/golden (see oracle/ref_driver.cpp); call with NULL buffers to query the count. */
+SB_API int sb_contact_get_proximity(sb_context* ctx, int kind, int32_t* host_ids, double* host_dist, int capacity, int* out_count, int* out_width);
+SB_API int sb_contact_get_vertices(sb_context* ctx, int group, double* host_xyz);
+/* feed externally computed vertex positions (tests of the detection stage alone) */
+SB_API int sb_contact_set_vertices(sb_context* ctx, int group, const double* host_xyz);
+SB_API int sb_contact_detect(sb_context* ctx, double enlargement, int with_intersections);
+/* contact / friction potential handle by reference name (e.g. "contact_rb_d_pt_tp_cubic"), -1 if absent */
+SB_API int sb_contact_potential(sb_context* ctx, const char* name, int* out_potential);
+
+/* ---- Newton driver -----------------------------------------------------------------------------------------------------------
+ * replaces: symx::NewtonsMethod::solve (symx/solver/NewtonsMethod.cpp:28-252) with NewtonSettings
+ * (symx/solver/solver_utils.h:170-258) and SolveStats (symx/solver/NewtonsMethod.h:32-43). */
+typedef struct sb_newton_settings {
+    int32_t max_iterations, min_iterations;
+    double residual_tolerance_abs, residual_tolerance_rel, step_tolerance;
+    int32_t max_iterations_as_success;
+    double step_cap;
+    int32_t enable_armijo_backtracking;
+    double line_search_armijo_beta;
+    int32_t max_backtracking_armijo_iterations, max_backtracking_invalid_state_iterations;
+    int32_t projection_mode;   /* 0 Newton, 1 ProjectedNewton, 2 ProjectOnDemand, 3 Progressive */
+    double projection_eps;
+    int32_t project_to_pd_use_mirroring, project_on_demand_countdown;
+    double ppn_tightening_factor, ppn_release_factor;
+    int32_t linear_solver;     /* 0 DirectLLT (not built yet), 1 BDPCG */
+    int32_t cg_max_iterations;
+    double cg_abs_tolerance, cg_rel_tolerance;
+    int32_t cg_stop_on_indefiniteness;
+    double bailout_residual;
+    int32_t contact_enabled;   /* run the built-in contact callbacks (update / intersection test) */
+} sb_newton_settings;
+typedef struct sb_newton_stats {
+    int32_t result;            /* symx::SolverReturn value (solver_utils.h:15-26) */
+    int32_t newton_iterations, cg_iterations;
+    int32_t ls_cap_iterations, ls_max_iterations, ls_inv_iterations, ls_bt_iterations;
+    int64_t n_hessians, n_projected_hessians;
+    int32_t n_evaluations;
+    double last_residual, last_energy;
+    double residuals[64];      /* residual of every evaluation (first 64) */
+} sb_newton_stats;
+SB_API void sb_newton_default_settings(sb_newton_settings* s);   /* STARK's defaults (S/core/Settings.cpp:40-54) */
+SB_API int sb_newton_solve(sb_context* ctx, const sb_newton_settings* settings, sb_newton_stats* stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STARK_B200_H */

@@ -1,0 +1,539 @@
+// Context, arrays, DoF sets, potentials and the evaluation driver behind the C-ABI (include/stark_b200.h).
+#include "internal.h"
+#include <algorithm>
+#include <cstring>
+
+namespace sb {
+
+int fail(sb_context* ctx, int code, const std::string& msg)
+{
+    if (ctx) ctx->error = msg;
+    return code;
+}
+int check_cuda(sb_context* ctx, cudaError_t e, const char* what)
+{
+    if (e == cudaSuccess) return 0;
+    return fail(ctx, SB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// deterministic reductions: fixed grid, fixed tree -> bitwise reproducible run to run
+// ---------------------------------------------------------------------------------------------------
+constexpr int RED_BLOCKS = 296;   // 2 CTAs per SM on a 148-SM B200
+constexpr int RED_THREADS = 256;
+
+template<bool ABSMAX>
+__global__ void __launch_bounds__(RED_THREADS) k_reduce_stage1(const double* __restrict__ in, size_t n, double* __restrict__ partial)
+{
+    __shared__ double s[RED_THREADS];
+    double acc = 0.0;
+    for (size_t i = (size_t)blockIdx.x * RED_THREADS + threadIdx.x; i < n; i += (size_t)RED_BLOCKS * RED_THREADS) {
+        const double v = in[i];
+        acc = ABSMAX ? fmax(acc, fabs(v)) : acc + v;
+    }
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int w = RED_THREADS / 2; w > 0; w >>= 1) {
+        if (threadIdx.x < w) s[threadIdx.x] = ABSMAX ? fmax(s[threadIdx.x], s[threadIdx.x + w]) : s[threadIdx.x] + s[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = s[0];
+}
+template<bool ABSMAX>
+__global__ void __launch_bounds__(512) k_reduce_stage2(const double* __restrict__ partial, double* __restrict__ out)
+{
+    __shared__ double s[512];
+    s[threadIdx.x] = (threadIdx.x < RED_BLOCKS) ? partial[threadIdx.x] : 0.0;
+    __syncthreads();
+    for (int w = 256; w > 0; w >>= 1) {
+        if (threadIdx.x < w) s[threadIdx.x] = ABSMAX ? fmax(s[threadIdx.x], s[threadIdx.x + w]) : s[threadIdx.x] + s[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = s[0];
+}
+void reduce_sum(sb_context* ctx, const double* d_in, size_t n, double* d_out)
+{
+    ctx->scratch.ensure(1024);
+    k_reduce_stage1<false><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(d_in, n, ctx->scratch.p);
+    k_reduce_stage2<false><<<1, 512, 0, ctx->stream>>>(ctx->scratch.p, d_out);
+    ctx->launches += 2;
+}
+void reduce_absmax(sb_context* ctx, const double* d_in, size_t n, double* d_out)
+{
+    ctx->scratch.ensure(1024);
+    k_reduce_stage1<true><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(d_in, n, ctx->scratch.p + 512);
+    k_reduce_stage2<true><<<1, 512, 0, ctx->stream>>>(ctx->scratch.p + 512, d_out);
+    ctx->launches += 2;
+}
+
+int recompute_dof_offsets(sb_context* ctx)
+{
+    int off = 0;
+    for (auto& s : ctx->dof_sets) {
+        s.offset = off;
+        const Array& a = ctx->arrays[s.array];
+        off += a.n_rows * a.stride;
+    }
+    ctx->ndofs = off;
+    return 0;
+}
+
+// Build the per-slot gather table of a potential from its fetch list (device pointers may have moved).
+int refresh_slots(sb_context* ctx, Potential& p)
+{
+    std::vector<FetchSlot> h(p.k->n_in);
+    for (auto& s : h) { s.base = nullptr; s.conn_col = -1; s.stride = 0; s.off = 0; s.pad = 0; }
+    for (const sb_fetch& f : p.fetch) {
+        const Array& a = ctx->arrays[f.array];
+        for (int c = 0; c < f.stride; c++) {
+            FetchSlot& s = h[f.first_slot + c];
+            s.base = a.d.p;
+            s.conn_col = f.conn_col;
+            s.stride = a.stride;
+            s.off = c;
+        }
+    }
+    p.slots.ensure(h.size());
+    SB_CUDA(ctx, cudaMemcpyAsync(p.slots.p, h.data(), h.size() * sizeof(FetchSlot), cudaMemcpyHostToDevice, ctx->stream));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // h is a stack-owned staging buffer
+    // DoF block offsets
+    for (int b = 0; b < p.k->nb; b++) p.blocks[b].dof_offset = ctx->dof_sets[p.block_set[b]].offset;
+    return 0;
+}
+
+int eval_internal(sb_context* ctx, int mode, double* out_E, double* out_grad_inf, bool sync_scalars)
+{
+    if (mode != SB_EVAL_P && mode != SB_EVAL_PGH) return fail(ctx, SB_ERR_ARG, "sb_eval: unknown mode");
+    recompute_dof_offsets(ctx);
+    if (ctx->ndofs <= 0) return fail(ctx, SB_ERR_STATE, "sb_eval: no degrees of freedom");
+    if (ctx->ndofs % 3 != 0) return fail(ctx, SB_ERR_STATE, "sb_eval: ndofs must be divisible by 3");
+
+    // layout of the shared element-output buffers
+    size_t H_total = 0, rows_total = 0, E_total = 0, n_blocks = 0;
+    for (auto& p : ctx->potentials) {
+        p.H_off = H_total; p.rows_off = rows_total; p.E_off = E_total;
+        const size_t n = p.k->n_dof;
+        H_total += (size_t)p.n_elem * n * n;
+        rows_total += (size_t)p.n_elem * p.k->nb;
+        E_total += (size_t)p.n_elem;
+        n_blocks += (size_t)p.n_elem * p.k->nb * p.k->nb;
+    }
+    ctx->E_elem.ensure(E_total + 1);
+    if (mode == SB_EVAL_PGH) {
+        ctx->H.ensure(H_total + 1);
+        ctx->rows.ensure(rows_total + 1);
+        ctx->grad.ensure(ctx->ndofs);
+        ctx->projected.ensure(E_total + 1);
+        SB_CUDA(ctx, cudaMemsetAsync(ctx->grad.p, 0, sizeof(double) * ctx->ndofs, ctx->stream));
+        SB_CUDA(ctx, cudaMemsetAsync(ctx->projected.p, 0, E_total + 1, ctx->stream));
+        ctx->n_hessians = E_total;
+        ctx->n_blocks_total = n_blocks;
+        ctx->n_rows_total = rows_total;
+        ctx->H_total = H_total;
+        ctx->n_projected = 0;
+    }
+
+    for (auto& p : ctx->potentials) {
+        if (p.n_elem == 0) continue;
+        int r = refresh_slots(ctx, p);
+        if (r) return r;
+        EvalArgs a;
+        a.slots = p.slots.p;
+        a.conn = p.conn_ext ? p.conn_ext : p.conn.p;
+        a.conn_stride = p.conn_stride;
+        a.n_elem = p.n_elem;
+        for (int b = 0; b < MAX_BLOCKS; b++) a.blocks[b] = p.blocks[b];
+        a.grad = ctx->grad.p;
+        a.H = ctx->H.p + p.H_off;
+        a.rows = ctx->rows.p + p.rows_off;
+        a.E_elem = ctx->E_elem.p + p.E_off;
+        a.g_elem = nullptr;
+        if (mode == SB_EVAL_PGH) p.k->launch_pgh(a, ctx->stream);
+        else p.k->launch_p(a, ctx->stream);
+        ctx->launches++;
+    }
+    SB_CUDA(ctx, cudaGetLastError());
+
+    reduce_sum(ctx, ctx->E_elem.p, E_total, ctx->d_scalars + 0);
+    if (mode == SB_EVAL_PGH) {
+        reduce_absmax(ctx, ctx->grad.p, ctx->ndofs, ctx->d_scalars + 1);
+        ctx->have_pgh = true;
+    }
+    if (sync_scalars) {
+        SB_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (out_E) *out_E = ctx->h_scalars[0];
+        if (out_grad_inf && mode == SB_EVAL_PGH) *out_grad_inf = ctx->h_scalars[1];
+    }
+    return 0;
+}
+
+// scatter / gather between the flat DoF vector and the DoF arrays
+__global__ void k_copy(double* __restrict__ dst, const double* __restrict__ src, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+__global__ void k_axpy_set(double* __restrict__ dst, const double* __restrict__ base, const double* __restrict__ d, double s, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = base[i] + s * d[i];
+}
+__global__ void k_scale(double* __restrict__ x, double s, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] *= s;
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+// =====================================================================================================
+// C-ABI
+// =====================================================================================================
+extern "C" {
+
+int sb_create(sb_context** out, int device, void* stream)
+{
+    if (!out) return SB_ERR_ARG;
+    *out = nullptr;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return SB_ERR_CUDA;  // no CPU fallback
+    if (device < 0 || device >= n_dev) return SB_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return SB_ERR_CUDA;
+    sb_context* ctx = new sb_context();
+    ctx->device = device;
+    if (stream) {
+        ctx->stream = (cudaStream_t)stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SB_ERR_CUDA; }
+        ctx->own_stream = true;
+    }
+    if (cudaMallocHost(&ctx->h_scalars, 64 * sizeof(double)) != cudaSuccess) { delete ctx; return SB_ERR_CUDA; }
+    if (cudaMalloc(&ctx->d_scalars, 64 * sizeof(double)) != cudaSuccess) { delete ctx; return SB_ERR_CUDA; }
+    cudaMemset(ctx->d_scalars, 0, 64 * sizeof(double));
+    *out = ctx;
+    return SB_OK;
+}
+
+void sb_destroy(sb_context* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    assembly_destroy(ctx);
+    pcg_destroy(ctx);
+    contact_destroy(ctx);
+    for (auto& a : ctx->arrays) a.d.release();
+    for (auto& p : ctx->potentials) { p.conn.release(); p.slots.release(); }
+    ctx->H.release(); ctx->rows.release(); ctx->E_elem.release(); ctx->grad.release(); ctx->du.release();
+    ctx->dofs_saved.release(); ctx->scratch.release(); ctx->projected.release();
+    if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
+    if (ctx->d_scalars) cudaFree(ctx->d_scalars);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* sb_last_error(const sb_context* ctx) { return ctx ? ctx->error.c_str() : "null context"; }
+void* sb_get_stream(sb_context* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int sb_synchronize(sb_context* ctx)
+{
+    if (!ctx) return SB_ERR_ARG;
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}
+int64_t sb_launch_count(const sb_context* ctx) { return ctx ? ctx->launches : 0; }
+
+int sb_array_create(sb_context* ctx, const char* label, int stride, int* out_array)
+{
+    if (!ctx || stride <= 0 || !out_array) return fail(ctx, SB_ERR_ARG, "sb_array_create: bad argument");
+    Array a;
+    a.label = label ? label : "";
+    a.stride = stride;
+    ctx->arrays.push_back(a);
+    *out_array = (int)ctx->arrays.size() - 1;
+    return SB_OK;
+}
+static int check_array(sb_context* ctx, int array, const char* where)
+{
+    if (!ctx) return SB_ERR_ARG;
+    if (array < 0 || array >= (int)ctx->arrays.size()) return fail(ctx, SB_ERR_ARG, std::string(where) + ": unknown array handle");
+    return 0;
+}
+int sb_array_upload(sb_context* ctx, int array, const double* host, int n_rows)
+{
+    int r = check_array(ctx, array, "sb_array_upload"); if (r) return r;
+    if (n_rows < 0 || (n_rows > 0 && !host)) return fail(ctx, SB_ERR_ARG, "sb_array_upload: bad argument");
+    Array& a = ctx->arrays[array];
+    a.d.ensure((size_t)std::max(n_rows, 1) * a.stride);
+    a.n_rows = n_rows;
+    if (n_rows > 0) {
+        SB_CUDA(ctx, cudaMemcpyAsync(a.d.p, host, sizeof(double) * (size_t)n_rows * a.stride, cudaMemcpyHostToDevice, ctx->stream));
+        SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host buffer is only borrowed for this call
+    }
+    return SB_OK;
+}
+int sb_array_download(sb_context* ctx, int array, double* host, int n_rows)
+{
+    int r = check_array(ctx, array, "sb_array_download"); if (r) return r;
+    Array& a = ctx->arrays[array];
+    if (n_rows < 0 || n_rows > a.n_rows || (n_rows > 0 && !host)) return fail(ctx, SB_ERR_ARG, "sb_array_download: bad size");
+    if (n_rows > 0) {
+        SB_CUDA(ctx, cudaMemcpyAsync(host, a.d.p, sizeof(double) * (size_t)n_rows * a.stride, cudaMemcpyDeviceToHost, ctx->stream));
+        SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return SB_OK;
+}
+int sb_array_rows(sb_context* ctx, int array, int* out_rows)
+{
+    int r = check_array(ctx, array, "sb_array_rows"); if (r) return r;
+    if (out_rows) *out_rows = ctx->arrays[array].n_rows;
+    return SB_OK;
+}
+
+int sb_dof_add(sb_context* ctx, int array, int* out_set)
+{
+    int r = check_array(ctx, array, "sb_dof_add"); if (r) return r;
+    if (ctx->arrays[array].stride != 3) return fail(ctx, SB_ERR_ARG, "sb_dof_add: expected DoF stride of 3");
+    ctx->dof_sets.push_back({array, 0});
+    if (out_set) *out_set = (int)ctx->dof_sets.size() - 1;
+    recompute_dof_offsets(ctx);
+    return SB_OK;
+}
+int sb_dof_total(sb_context* ctx, int* out_ndofs)
+{
+    if (!ctx) return SB_ERR_ARG;
+    recompute_dof_offsets(ctx);
+    if (out_ndofs) *out_ndofs = ctx->ndofs;
+    return SB_OK;
+}
+int sb_dofs_get(sb_context* ctx, double* host_u)
+{
+    if (!ctx || !host_u) return fail(ctx, SB_ERR_ARG, "sb_dofs_get: bad argument");
+    recompute_dof_offsets(ctx);
+    for (auto& s : ctx->dof_sets) {
+        Array& a = ctx->arrays[s.array];
+        const size_t n = (size_t)a.n_rows * a.stride;
+        if (n) SB_CUDA(ctx, cudaMemcpyAsync(host_u + s.offset, a.d.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}
+int sb_dofs_set(sb_context* ctx, const double* host_u)
+{
+    if (!ctx || !host_u) return fail(ctx, SB_ERR_ARG, "sb_dofs_set: bad argument");
+    recompute_dof_offsets(ctx);
+    for (auto& s : ctx->dof_sets) {
+        Array& a = ctx->arrays[s.array];
+        const size_t n = (size_t)a.n_rows * a.stride;
+        if (n) SB_CUDA(ctx, cudaMemcpyAsync(a.d.p, host_u + s.offset, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}
+
+const char* sb_kernel_names(void)
+{
+    static std::string names;
+    if (names.empty())
+        for (const auto& k : all_kernels()) { names += k.name; names += "\n"; }
+    return names.c_str();
+}
+
+int sb_potential_create(sb_context* ctx, const char* kernel_name, int conn_stride, const sb_fetch* fetch, int n_fetch, int* out_potential)
+{
+    if (!ctx || !kernel_name || !fetch || n_fetch <= 0 || conn_stride <= 0) return fail(ctx, SB_ERR_ARG, "sb_potential_create: bad argument");
+    const KernelInfo* k = find_kernel(kernel_name);
+    if (!k) return fail(ctx, SB_ERR_NO_KERNEL, std::string("sb_potential_create: no kernel named '") + kernel_name + "'");
+    Potential p;
+    p.k = k;
+    p.name = kernel_name;
+    p.conn_stride = conn_stride;
+    std::vector<int> covered(k->n_in, 0);
+    for (int i = 0; i < n_fetch; i++) {
+        const sb_fetch& f = fetch[i];
+        if (f.array < 0 || f.array >= (int)ctx->arrays.size()) return fail(ctx, SB_ERR_ARG, "sb_potential_create: unknown array in fetch table");
+        if (f.stride != ctx->arrays[f.array].stride) return fail(ctx, SB_ERR_LAYOUT, "sb_potential_create: fetch stride differs from the array stride");
+        if (f.conn_col < -1 || f.conn_col >= conn_stride) return fail(ctx, SB_ERR_LAYOUT, "sb_potential_create: connectivity column out of range");
+        if (f.first_slot < 0 || f.first_slot + f.stride > k->n_in) return fail(ctx, SB_ERR_LAYOUT, std::string("sb_potential_create: in[] slot out of range for ") + kernel_name);
+        for (int c = 0; c < f.stride; c++) covered[f.first_slot + c]++;
+        p.fetch.push_back(f);
+    }
+    for (int s = 0; s < k->n_in; s++)
+        if (covered[s] != 1) return fail(ctx, SB_ERR_LAYOUT, std::string("sb_potential_create: in[] slots of ") + kernel_name + " are not covered exactly once (expected " + std::to_string(k->n_in) + " inputs)");
+    // DoF blocks: the kernel's DOF_SLOT[b] must be bound to a DoF array, in DoF-set order then slot order
+    int prev_set = -1, prev_slot = -1;
+    for (int b = 0; b < k->nb; b++) {
+        const int slot = k->dof_slot[b];
+        const sb_fetch* src = nullptr;
+        for (const auto& f : p.fetch)
+            if (f.first_slot == slot && f.stride == 3) src = &f;
+        if (!src) return fail(ctx, SB_ERR_LAYOUT, std::string("sb_potential_create: DoF block slot not bound by a stride-3 fetch in ") + kernel_name);
+        int set = -1;
+        for (int s = 0; s < (int)ctx->dof_sets.size(); s++)
+            if (ctx->dof_sets[s].array == src->array) set = s;
+        if (set < 0) return fail(ctx, SB_ERR_LAYOUT, std::string("sb_potential_create: DoF slot of ") + kernel_name + " is bound to an array that is not a DoF set");
+        if (src->conn_col < 0) return fail(ctx, SB_ERR_LAYOUT, "sb_potential_create: DoF fetch must be connectivity-indexed");
+        if (set < prev_set || (set == prev_set && slot < prev_slot)) return fail(ctx, SB_ERR_LAYOUT, std::string("sb_potential_create: DoF block order of ") + kernel_name + " differs from the reference's (DoF set, then slot)");
+        prev_set = set; prev_slot = slot;
+        p.block_set[b] = set;
+        p.blocks[b].conn_col = src->conn_col;
+        p.blocks[b].dof_offset = 0;
+    }
+    // every other binding of a DoF array would be a DoF the kernel does not differentiate
+    for (const auto& f : p.fetch) {
+        bool is_dof_array = false;
+        for (const auto& s : ctx->dof_sets) if (s.array == f.array) is_dof_array = true;
+        if (!is_dof_array) continue;
+        bool known = false;
+        for (int b = 0; b < k->nb; b++) if (k->dof_slot[b] == f.first_slot) known = true;
+        if (!known) return fail(ctx, SB_ERR_LAYOUT, std::string("sb_potential_create: ") + kernel_name + " binds a DoF array at a slot the kernel treats as constant");
+    }
+    for (int b = k->nb; b < MAX_BLOCKS; b++) { p.blocks[b].conn_col = 0; p.blocks[b].dof_offset = 0; p.block_set[b] = 0; }
+    ctx->potentials.push_back(std::move(p));
+    if (out_potential) *out_potential = (int)ctx->potentials.size() - 1;
+    ctx->pattern_version++;
+    return SB_OK;
+}
+
+static int check_pot(sb_context* ctx, int pot, const char* where)
+{
+    if (!ctx) return SB_ERR_ARG;
+    if (pot < 0 || pot >= (int)ctx->potentials.size()) return fail(ctx, SB_ERR_ARG, std::string(where) + ": unknown potential handle");
+    return 0;
+}
+int sb_potential_set_connectivity(sb_context* ctx, int potential, const int32_t* conn, int n_elements)
+{
+    int r = check_pot(ctx, potential, "sb_potential_set_connectivity"); if (r) return r;
+    if (n_elements < 0 || (n_elements > 0 && !conn)) return fail(ctx, SB_ERR_ARG, "sb_potential_set_connectivity: bad argument");
+    Potential& p = ctx->potentials[potential];
+    if (p.conn_ext) return fail(ctx, SB_ERR_STATE, "sb_potential_set_connectivity: connectivity of this potential is owned by the contact module");
+    p.conn.ensure((size_t)std::max(n_elements, 1) * p.conn_stride);
+    p.n_elem = n_elements;
+    if (n_elements > 0) {
+        SB_CUDA(ctx, cudaMemcpyAsync(p.conn.p, conn, sizeof(int32_t) * (size_t)n_elements * p.conn_stride, cudaMemcpyHostToDevice, ctx->stream));
+        SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->pattern_version++;
+    ctx->have_pgh = false;
+    return SB_OK;
+}
+int sb_potential_info(sb_context* ctx, int potential, int* n_in, int* n_dofs, int* n_elements)
+{
+    int r = check_pot(ctx, potential, "sb_potential_info"); if (r) return r;
+    const Potential& p = ctx->potentials[potential];
+    if (n_in) *n_in = p.k->n_in;
+    if (n_dofs) *n_dofs = p.k->n_dof;
+    if (n_elements) *n_elements = p.n_elem;
+    return SB_OK;
+}
+
+int sb_eval(sb_context* ctx, int mode, double* out_E, double* out_grad_inf)
+{
+    if (!ctx) return SB_ERR_ARG;
+    return eval_internal(ctx, mode, out_E, out_grad_inf, true);
+}
+int sb_grad_get(sb_context* ctx, double* host_grad)
+{
+    if (!ctx || !host_grad) return fail(ctx, SB_ERR_ARG, "sb_grad_get: bad argument");
+    if (!ctx->have_pgh) return fail(ctx, SB_ERR_STATE, "sb_grad_get: no gradient evaluated yet");
+    SB_CUDA(ctx, cudaMemcpyAsync(host_grad, ctx->grad.p, sizeof(double) * ctx->ndofs, cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}
+
+// [E | grad | hess] per element, gradient recomputed from a dedicated pass so that it is the element's own share
+int sb_potential_get_element_output(sb_context* ctx, int potential, double* host_sol)
+{
+    int r = check_pot(ctx, potential, "sb_potential_get_element_output"); if (r) return r;
+    if (!ctx->have_pgh) return fail(ctx, SB_ERR_STATE, "sb_potential_get_element_output: call sb_eval(SB_EVAL_PGH) first");
+    Potential& p = ctx->potentials[potential];
+    if (p.n_elem == 0) return SB_OK;
+    const int n = p.k->n_dof, n_out = 1 + n + n * n;
+    // re-run this potential alone with a per-element gradient sink (values identical, the flat gradient gets a scratch copy)
+    DevBuf<double> g_elem, grad_tmp;
+    g_elem.ensure((size_t)p.n_elem * n);
+    grad_tmp.ensure(ctx->ndofs);
+    SB_CUDA(ctx, cudaMemsetAsync(grad_tmp.p, 0, sizeof(double) * ctx->ndofs, ctx->stream));
+    r = refresh_slots(ctx, p); if (r) return r;
+    EvalArgs a;
+    a.slots = p.slots.p;
+    a.conn = p.conn_ext ? p.conn_ext : p.conn.p;
+    a.conn_stride = p.conn_stride;
+    a.n_elem = p.n_elem;
+    for (int b = 0; b < MAX_BLOCKS; b++) a.blocks[b] = p.blocks[b];
+    a.grad = grad_tmp.p;
+    a.H = ctx->H.p + p.H_off;
+    a.rows = ctx->rows.p + p.rows_off;
+    a.E_elem = ctx->E_elem.p + p.E_off;
+    a.g_elem = g_elem.p;
+    p.k->launch_pgh(a, ctx->stream);
+    ctx->launches++;
+    std::vector<double> E(p.n_elem), g((size_t)p.n_elem * n), H((size_t)p.n_elem * n * n);
+    SB_CUDA(ctx, cudaMemcpyAsync(E.data(), ctx->E_elem.p + p.E_off, E.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(ctx, cudaMemcpyAsync(g.data(), g_elem.p, g.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(ctx, cudaMemcpyAsync(H.data(), ctx->H.p + p.H_off, H.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int e = 0; e < p.n_elem; e++) {
+        double* o = host_sol + (size_t)e * n_out;
+        o[0] = E[e];
+        std::memcpy(o + 1, g.data() + (size_t)e * n, n * sizeof(double));
+        std::memcpy(o + 1 + n, H.data() + (size_t)e * n * n, (size_t)n * n * sizeof(double));
+    }
+    g_elem.release(); grad_tmp.release();
+    return SB_OK;
+}
+int sb_potential_get_block_rows(sb_context* ctx, int potential, int32_t* host_rows)
+{
+    int r = check_pot(ctx, potential, "sb_potential_get_block_rows"); if (r) return r;
+    if (!ctx->have_pgh) return fail(ctx, SB_ERR_STATE, "sb_potential_get_block_rows: call sb_eval(SB_EVAL_PGH) first");
+    Potential& p = ctx->potentials[potential];
+    if (p.n_elem == 0) return SB_OK;
+    SB_CUDA(ctx, cudaMemcpyAsync(host_rows, ctx->rows.p + p.rows_off, sizeof(int32_t) * (size_t)p.n_elem * p.k->nb, cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}
+
+// ---- line-search support ----
+int sb_dofs_save(sb_context* ctx)
+{
+    if (!ctx) return SB_ERR_ARG;
+    recompute_dof_offsets(ctx);
+    ctx->dofs_saved.ensure(ctx->ndofs);
+    for (auto& s : ctx->dof_sets) {
+        Array& a = ctx->arrays[s.array];
+        const size_t n = (size_t)a.n_rows * a.stride;
+        if (n) SB_CUDA(ctx, cudaMemcpyAsync(ctx->dofs_saved.p + s.offset, a.d.p, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    return SB_OK;
+}
+int sb_dofs_apply_step(sb_context* ctx, double step)
+{
+    if (!ctx) return SB_ERR_ARG;
+    if (!ctx->du.p || !ctx->dofs_saved.p) return fail(ctx, SB_ERR_STATE, "sb_dofs_apply_step: no saved DoFs / direction");
+    for (auto& s : ctx->dof_sets) {
+        Array& a = ctx->arrays[s.array];
+        const int n = a.n_rows * a.stride;
+        if (n) { k_axpy_set<<<(n + 255) / 256, 256, 0, ctx->stream>>>(a.d.p, ctx->dofs_saved.p + s.offset, ctx->du.p + s.offset, step, n); ctx->launches++; }
+    }
+    SB_CUDA(ctx, cudaGetLastError());
+    return SB_OK;
+}
+int sb_du_scale(sb_context* ctx, double factor)
+{
+    if (!ctx || !ctx->du.p) return fail(ctx, SB_ERR_STATE, "sb_du_scale: no direction");
+    k_scale<<<(ctx->ndofs + 255) / 256, 256, 0, ctx->stream>>>(ctx->du.p, factor, ctx->ndofs);
+    ctx->launches++;
+    SB_CUDA(ctx, cudaGetLastError());
+    return SB_OK;
+}
+int sb_du_get(sb_context* ctx, double* host_du)
+{
+    if (!ctx || !host_du || !ctx->du.p) return fail(ctx, SB_ERR_STATE, "sb_du_get: no direction");
+    SB_CUDA(ctx, cudaMemcpyAsync(host_du, ctx->du.p, sizeof(double) * ctx->ndofs, cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,177 @@
+// Element evaluation kernels: gather -> energy / gradient / Hessian -> scatter.
+//
+// Replaces CompiledInLoop<double>::run (symx/compile/CompiledInLoop_run.h:66-472) and the per-element callbacks of
+// SecondOrderCompiledPotential (symx/solver/second_order/SecondOrderCompiledPotential.cpp:94-181):
+//   * gather: every element's in[] is staged ONCE in shared memory by the whole CTA (the reference memcpy-gathers
+//     8 elements at a time into a thread buffer, CompiledInLoop_run.h:262-282);
+//   * evaluate: n(n+1)/2 lanes per element, one Hessian entry each (ad.cuh);
+//   * scatter: dense row-major n x n element Hessian + global block rows (the ElementHessians contract,
+//     ElementHessians.cpp:20-41), gradient scatter-add into the flat gradient, per-element energy.
+#include "internal.h"
+#include "potentials.cuh"
+#include <cstring>
+
+namespace sb {
+
+template<class Pot> struct Geo {
+    static constexpr int N = Pot::N_DOF;
+    static constexpr int L = N * (N + 1) / 2;                       // lanes per element
+    static constexpr int BLOCK = (L <= EVAL_THREADS) ? EVAL_THREADS : ((L + 31) / 32) * 32;
+    static constexpr int G = BLOCK / L;                              // elements per CTA
+};
+
+__device__ __forceinline__ void pair_from_index(int p, int& i, int& j)
+{
+    int r = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
+    while ((r + 1) * (r + 2) / 2 <= p) r++;
+    while (r * (r + 1) / 2 > p) r--;
+    i = r;
+    j = p - r * (r + 1) / 2;
+}
+
+template<class Pot>
+__global__ void __launch_bounds__(Geo<Pot>::BLOCK) k_eval_pgh(const EvalArgs a)
+{
+    constexpr int N = Pot::N_DOF, L = Geo<Pot>::L, G = Geo<Pot>::G, NIN = Pot::N_IN, NB = Pot::NB, BLOCK = Geo<Pot>::BLOCK;
+    __shared__ double s_in[G * NIN];
+    const int tid = threadIdx.x;
+    const int e_base = blockIdx.x * G;
+
+    // cooperative gather of G elements' inputs
+    for (int idx = tid; idx < G * NIN; idx += BLOCK) {
+        const int el = idx / NIN, slot = idx - el * NIN;
+        const int e = e_base + el;
+        if (e < a.n_elem) {
+            const FetchSlot fs = a.slots[slot];
+            const int row = (fs.conn_col >= 0) ? a.conn[(size_t)e * a.conn_stride + fs.conn_col] : 0;
+            s_in[idx] = fs.base[(size_t)row * fs.stride + fs.off];
+        }
+    }
+    __syncthreads();
+
+    const int el = tid / L;
+    const int p = tid - el * L;
+    const int e = e_base + el;
+    if (el >= G || e >= a.n_elem) return;
+
+    sbad::Seed<sbad::D2> seed;
+    pair_from_index(p, seed.i, seed.j);
+    const sbad::D2 r = Pot::template energy<sbad::D2>(s_in + el * NIN, seed);
+
+    const int i = seed.i, j = seed.j;
+    double* He = a.H + (size_t)e * N * N;
+    He[i * N + j] = r.h;
+    if (i != j) He[j * N + i] = r.h;
+    const int32_t* ce = a.conn + (size_t)e * a.conn_stride;
+    if (j == 0) {
+        const DofBlock b = a.blocks[i / 3];
+        atomicAdd(a.grad + b.dof_offset + 3 * ce[b.conn_col] + (i % 3), r.gi);
+        if (a.g_elem) a.g_elem[(size_t)e * N + i] = r.gi;
+    }
+    if (p < NB) {
+        const DofBlock b = a.blocks[p];
+        a.rows[(size_t)e * NB + p] = b.dof_offset / 3 + ce[b.conn_col];
+    }
+    if (p == 0) a.E_elem[e] = r.v;
+}
+
+template<class Pot>
+__global__ void __launch_bounds__(128) k_eval_p(const EvalArgs a)
+{
+    constexpr int NIN = Pot::N_IN;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= a.n_elem) return;
+    double in[NIN];
+    const int32_t* ce = a.conn + (size_t)e * a.conn_stride;
+#pragma unroll 1
+    for (int slot = 0; slot < NIN; slot++) {
+        const FetchSlot fs = a.slots[slot];
+        const int row = (fs.conn_col >= 0) ? ce[fs.conn_col] : 0;
+        in[slot] = fs.base[(size_t)row * fs.stride + fs.off];
+    }
+    sbad::Seed<double> seed;
+    a.E_elem[e] = Pot::template energy<double>(in, seed);
+}
+
+template<class Pot> static void launch_pgh(const EvalArgs& a, cudaStream_t s)
+{
+    const int grid = (a.n_elem + Geo<Pot>::G - 1) / Geo<Pot>::G;
+    k_eval_pgh<Pot><<<grid, Geo<Pot>::BLOCK, 0, s>>>(a);
+}
+template<class Pot> static void launch_p(const EvalArgs& a, cudaStream_t s)
+{
+    const int grid = (a.n_elem + 127) / 128;
+    k_eval_p<Pot><<<grid, 128, 0, s>>>(a);
+}
+
+}  // namespace sb
+#include "tet_analytic.cuh"
+namespace sb {
+
+#define SB_KERNEL(STRUCT, NAME) \
+    KernelInfo { NAME, sbpot::STRUCT::N_IN, sbpot::STRUCT::N_DOF, sbpot::STRUCT::NB, sbpot::STRUCT::DOF_SLOT, &launch_pgh<sbpot::STRUCT>, &launch_p<sbpot::STRUCT> }
+
+const std::vector<KernelInfo>& all_kernels()
+{
+    static const std::vector<KernelInfo> k = {
+        SB_KERNEL(EnergyLumpedInertia, "EnergyLumpedInertia"),
+        SB_KERNEL(EnergyPrescribedPositions, "EnergyPrescribedPositions"),
+        SB_KERNEL(EnergySegmentStrain, "EnergySegmentStrain"),
+        SB_KERNEL(EnergySegmentStrain_Elasticity_Only, "EnergySegmentStrain_Elasticity_Only"),
+        SB_KERNEL(EnergyTriangleStrain, "EnergyTriangleStrain"),
+        SB_KERNEL(EnergyTriangleStrain_Elasticity_Only, "EnergyTriangleStrain_Elasticity_Only"),
+        SB_KERNEL(EnergyDiscreteShells, "EnergyDiscreteShells"),
+        SB_KERNEL(EnergyBendingFlat, "EnergyBendingFlat"),
+        // hand-derived analytic tet kernels (tet_analytic.cuh) are the product path; the AD ones stay as cross-checks
+        KernelInfo { "EnergyTetStrain", 43, 12, 4, sbpot::EnergyTetStrain::DOF_SLOT, &launch_tet_analytic_pgh<true>, &launch_p<sbpot::EnergyTetStrain> },
+        KernelInfo { "EnergyTetStrain_Elasticity_Only", 40, 12, 4, sbpot::EnergyTetStrain_Elasticity_Only::DOF_SLOT, &launch_tet_analytic_pgh<false>, &launch_p<sbpot::EnergyTetStrain_Elasticity_Only> },
+        SB_KERNEL(EnergyTetStrain, "EnergyTetStrain_AD"),
+        SB_KERNEL(EnergyTetStrain_Elasticity_Only, "EnergyTetStrain_Elasticity_Only_AD"),
+        SB_KERNEL(EnergyRigidBodyInertia_Linear, "EnergyRigidBodyInertia_Linear"),
+        SB_KERNEL(EnergyRigidBodyInertia_Angular, "EnergyRigidBodyInertia_Angular"),
+        SB_KERNEL(rb_constraint_global_points, "rb_constraint_global_points"),
+        SB_KERNEL(rb_constraint_global_directions, "rb_constraint_global_directions"),
+        SB_KERNEL(rb_constraint_points, "rb_constraint_points"),
+        SB_KERNEL(rb_constraint_point_on_axis, "rb_constraint_point_on_axis"),
+        SB_KERNEL(rb_constraint_distances, "rb_constraint_distances"),
+        SB_KERNEL(rb_constraint_distance_limits, "rb_constraint_distance_limits"),
+        SB_KERNEL(rb_constraint_directions, "rb_constraint_directions"),
+        SB_KERNEL(rb_constraint_angle_limits, "rb_constraint_angle_limits"),
+        SB_KERNEL(rb_constraint_damped_spring, "rb_constraint_damped_spring"),
+        SB_KERNEL(contact_d_d_pt_pp, "contact_d_d_pt_pp_cubic"),
+        SB_KERNEL(contact_d_d_pt_pe, "contact_d_d_pt_pe_cubic"),
+        SB_KERNEL(contact_d_d_pt_pt, "contact_d_d_pt_pt_cubic"),
+        SB_KERNEL(contact_d_d_ee_pp, "contact_d_d_ee_pp_cubic"),
+        SB_KERNEL(contact_d_d_ee_pe, "contact_d_d_ee_pe_cubic"),
+        SB_KERNEL(contact_d_d_ee_ee, "contact_d_d_ee_ee_cubic"),
+        SB_KERNEL(contact_rb_d_pt_pp, "contact_rb_d_pt_pp_cubic"),
+        SB_KERNEL(contact_rb_d_pt_pe, "contact_rb_d_pt_pe_cubic"),
+        SB_KERNEL(contact_rb_d_pt_pt, "contact_rb_d_pt_pt_cubic"),
+        SB_KERNEL(contact_rb_d_pt_ep, "contact_rb_d_pt_ep_cubic"),
+        SB_KERNEL(contact_rb_d_pt_tp, "contact_rb_d_pt_tp_cubic"),
+        SB_KERNEL(contact_rb_d_ee_pp, "contact_rb_d_ee_pp_cubic"),
+        SB_KERNEL(contact_rb_d_ee_pe, "contact_rb_d_ee_pe_cubic"),
+        SB_KERNEL(contact_rb_d_ee_ee, "contact_rb_d_ee_ee_cubic"),
+        SB_KERNEL(contact_rb_d_ee_ep, "contact_rb_d_ee_ep_cubic"),
+        SB_KERNEL(friction_d_d_pp, "friction_d_d_pp_C0"),
+        SB_KERNEL(friction_d_d_pe, "friction_d_d_pe_C0"),
+        SB_KERNEL(friction_d_d_pt, "friction_d_d_pt_C0"),
+        SB_KERNEL(friction_d_d_ee, "friction_d_d_ee_C0"),
+        SB_KERNEL(friction_rb_d_pp, "friction_rb_d_pp_C0"),
+        SB_KERNEL(friction_rb_d_pe, "friction_rb_d_pe_C0"),
+        SB_KERNEL(friction_rb_d_pt, "friction_rb_d_pt_C0"),
+        SB_KERNEL(friction_rb_d_ee, "friction_rb_d_ee_C0"),
+        SB_KERNEL(friction_rb_d_ep, "friction_rb_d_ep_C0"),
+        SB_KERNEL(friction_rb_d_tp, "friction_rb_d_tp_C0"),
+    };
+    return k;
+}
+
+const KernelInfo* find_kernel(const char* name)
+{
+    for (const auto& k : all_kernels())
+        if (std::strcmp(k.name, name) == 0) return &k;
+    return nullptr;
+}
+
+}  // namespace sb

@@ -1,0 +1,165 @@
+// Internal state of a stark_b200 context (not part of the C-ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include "../../include/stark_b200.h"
+
+namespace sb {
+
+constexpr int MAX_BLOCKS = 8;     // 3-DoF blocks per element (reference potentials use at most 8)
+constexpr int EVAL_THREADS = 256;
+
+// One in[] slot of a potential: value = base[row * stride + off], row = conn[e * conn_stride + conn_col] (or 0)
+struct FetchSlot {
+    const double* base;
+    int32_t conn_col;
+    int32_t stride;
+    int32_t off;
+    int32_t pad;
+};
+
+struct DofBlock {
+    int32_t dof_offset;  // offset of the DoF set in the flat DoF vector
+    int32_t conn_col;    // connectivity column that indexes the set
+};
+
+struct EvalArgs {
+    const FetchSlot* slots;
+    const int32_t* conn;
+    int32_t conn_stride;
+    int32_t n_elem;
+    DofBlock blocks[MAX_BLOCKS];
+    double* grad;      // flat gradient (atomic accumulation)
+    double* H;         // element Hessians of this potential, n*n per element, row-major
+    int32_t* rows;     // global block rows, NB per element
+    double* E_elem;    // per-element energy
+    double* g_elem;    // optional per-element gradient (n per element) for parity dumps, may be null
+};
+
+struct KernelInfo {
+    const char* name;
+    int n_in, n_dof, nb;
+    const int* dof_slot;
+    void (*launch_pgh)(const EvalArgs&, cudaStream_t);
+    void (*launch_p)(const EvalArgs&, cudaStream_t);
+};
+const KernelInfo* find_kernel(const char* name);
+const std::vector<KernelInfo>& all_kernels();
+
+template<class T> struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t n)
+    {
+        if (n <= cap) return;
+        size_t ncap = cap ? cap : 256;
+        while (ncap < n) ncap = ncap + ncap / 2 + 256;
+        T* np = nullptr;
+        cudaMalloc(&np, ncap * sizeof(T));
+        if (p) cudaFree(p);
+        p = np;
+        cap = ncap;
+    }
+    void ensure_keep(size_t n, size_t keep, cudaStream_t s)
+    {
+        if (n <= cap) return;
+        size_t ncap = cap ? cap : 256;
+        while (ncap < n) ncap = ncap + ncap / 2 + 256;
+        T* np = nullptr;
+        cudaMalloc(&np, ncap * sizeof(T));
+        if (p) {
+            if (keep) cudaMemcpyAsync(np, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, s);
+            cudaStreamSynchronize(s);
+            cudaFree(p);
+        }
+        p = np;
+        cap = ncap;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct Array {
+    std::string label;
+    int stride = 0;
+    int n_rows = 0;
+    DevBuf<double> d;
+};
+
+struct DofSet {
+    int array;
+    int offset;  // in the flat DoF vector (recomputed when sizes change)
+};
+
+struct Potential {
+    const KernelInfo* k = nullptr;
+    std::string name;
+    int conn_stride = 0;
+    std::vector<sb_fetch> fetch;
+    DofBlock blocks[MAX_BLOCKS];
+    int block_set[MAX_BLOCKS];  // DoF set of each block
+    int n_elem = 0;
+    DevBuf<int32_t> conn;       // owned connectivity (host-provided)
+    const int32_t* conn_ext = nullptr;  // or device-resident table owned by the contact module
+    const int32_t* n_elem_dev = nullptr;
+    DevBuf<FetchSlot> slots;
+    // offsets into the shared element-output buffers (recomputed each evaluation)
+    size_t H_off = 0, rows_off = 0, E_off = 0;
+};
+
+struct Assembly;   // assembly.cu
+struct Pcg;        // pcg.cu
+struct Contact;    // contact.cu
+
+}  // namespace sb
+
+struct sb_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string error;
+    int64_t launches = 0;
+
+    std::vector<sb::Array> arrays;
+    std::vector<sb::DofSet> dof_sets;
+    int ndofs = 0;
+    std::vector<sb::Potential> potentials;
+
+    // element outputs of the last PGH evaluation
+    sb::DevBuf<double> H;        // all element Hessians
+    sb::DevBuf<int32_t> rows;    // all element block rows
+    sb::DevBuf<double> E_elem;   // all element energies
+    sb::DevBuf<double> grad;     // flat gradient
+    sb::DevBuf<double> du;       // Newton direction
+    sb::DevBuf<double> dofs_saved;
+    sb::DevBuf<double> scratch;  // reductions
+    sb::DevBuf<uint8_t> projected;  // per element Hessian: already projected
+    size_t n_hessians = 0, n_blocks_total = 0, n_rows_total = 0, H_total = 0;
+    int64_t n_projected = 0;
+    uint64_t pattern_version = 1;   // bumped whenever any connectivity changes
+    bool have_pgh = false;
+
+    double* h_scalars = nullptr;    // pinned host scratch (16 doubles)
+    double* d_scalars = nullptr;    // device scratch (16 doubles)
+
+    sb::Assembly* assembly = nullptr;
+    sb::Pcg* pcg = nullptr;
+    sb::Contact* contact = nullptr;
+};
+
+namespace sb {
+int fail(sb_context* ctx, int code, const std::string& msg);
+int check_cuda(sb_context* ctx, cudaError_t e, const char* what);
+#define SB_CUDA(ctx, call) do { int _r = sb::check_cuda((ctx), (call), #call); if (_r) return _r; } while (0)
+int recompute_dof_offsets(sb_context* ctx);
+int refresh_slots(sb_context* ctx, Potential& p);
+// reductions (core.cu): deterministic sum / inf-norm into d_out[0]
+void reduce_sum(sb_context* ctx, const double* d_in, size_t n, double* d_out);
+void reduce_absmax(sb_context* ctx, const double* d_in, size_t n, double* d_out);
+void assembly_destroy(sb_context* ctx);
+void pcg_destroy(sb_context* ctx);
+void contact_destroy(sb_context* ctx);
+int eval_internal(sb_context* ctx, int mode, double* out_E, double* out_grad_inf, bool sync_scalars);
+}  // namespace sb

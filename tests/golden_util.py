@@ -1,0 +1,48 @@
+"""Load a golden fixture (tests/golden/*.npz, produced by the unmodified reference) and bind it to a context exactly
+the way a host walking `MappedWorkspace::maps` would: one device array per distinct bound container, DoF sets in
+registration order, one potential per reference potential with its fetch table."""
+import json
+import os
+
+import numpy as np
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+class Golden:
+    def __init__(self, name):
+        self.z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+        self.meta = json.loads(bytes(self.z["meta_json"]))
+        self.name = name
+
+    def __getitem__(self, k):
+        return self.z[k]
+
+    def potentials(self, only_nonempty=True):
+        for i, p in enumerate(self.meta["potentials"]):
+            if only_nonempty and p["n_elements"] == 0:
+                continue
+            yield i, p
+
+
+def bind(ctx, g, kernel_names, rename=None, skip=()):
+    """Returns {reference potential index: context potential handle}."""
+    rename = rename or {}
+    arrays = {}
+    for i, a in enumerate(g.meta["arrays"]):
+        arrays[i] = ctx.array(f"a{i}", a["stride"], g[f"array{i}"])
+    ids = [a["id"] for a in g.meta["arrays"]]
+    for did in g.meta["dof_array_ids"]:
+        ctx.dof_add(arrays[ids.index(did)])
+    handles = {}
+    for i, p in g.potentials():
+        name = rename.get(p["name"], p["name"])
+        if name not in kernel_names or p["name"] in skip:
+            continue
+        fetch = [(arrays[m["array"]], m["conn_idx"], m["first_symbol"], m["stride"]) for m in p["maps"]]
+        h = ctx.potential(name, p["conn_stride"], fetch)
+        conn = g[f"pot{i}_conn"]
+        active = g[f"pot{i}_active"].astype(bool)
+        ctx.set_connectivity(h, conn[active])
+        handles[i] = h
+    return handles
