@@ -88,6 +88,8 @@ SB_API int sb_grad_get(sb_context* ctx, double* host_grad);   /* flat, length nd
 /* per-element output of one potential as the reference lays it out: [E | grad(n) | hess(n*n) row-major] per element */
 SB_API int sb_potential_get_element_output(sb_context* ctx, int potential, double* host_sol);
 SB_API int sb_potential_get_block_rows(sb_context* ctx, int potential, int32_t* host_rows);
+/* the stored element Hessians of one potential (n*n per element, row-major) as they are now, i.e. after any projection */
+SB_API int sb_potential_get_hessians(sb_context* ctx, int potential, double* host_hessians);
 
 /* ---- PD projection + assembly -----------------------------------------------------------------------------------
  * replaces: ElementHessians::{project_to_PD_*, assemble_global, update_global}

@@ -71,7 +71,7 @@ SYMBOLS = [
     "sb_array_create", "sb_array_upload", "sb_array_download", "sb_array_rows",
     "sb_dof_add", "sb_dof_total", "sb_dofs_get", "sb_dofs_set",
     "sb_potential_create", "sb_potential_set_connectivity", "sb_potential_info", "sb_kernel_names",
-    "sb_eval", "sb_grad_get", "sb_potential_get_element_output", "sb_potential_get_block_rows",
+    "sb_eval", "sb_grad_get", "sb_potential_get_element_output", "sb_potential_get_block_rows", "sb_potential_get_hessians",
     "sb_project_to_pd", "sb_assemble", "sb_bcsr_info", "sb_bcsr_get",
     "sb_solve_pcg", "sb_du_get", "sb_dofs_save", "sb_dofs_apply_step", "sb_du_scale",
     "sb_contact_init", "sb_contact_add_mesh", "sb_contact_blacklist", "sb_contact_set_friction", "sb_contact_set_params",
@@ -220,6 +220,12 @@ class Context:
         n_in, n, ne = self.potential_info(pot)
         out = np.empty((ne, n // 3), dtype=np.int32)
         self._ck(self.lib.sb_potential_get_block_rows(self.h, int(pot), _p(out, C.c_int32)))
+        return out
+
+    def hessians(self, pot):
+        n_in, n, ne = self.potential_info(pot)
+        out = np.empty((ne, n, n), dtype=np.float64)
+        self._ck(self.lib.sb_potential_get_hessians(self.h, int(pot), _p(out, C.c_double)))
         return out
 
     # ---- projection / assembly / solve

@@ -225,6 +225,7 @@ void sb_destroy(sb_context* ctx)
     assembly_destroy(ctx);
     pcg_destroy(ctx);
     contact_destroy(ctx);
+    projector_destroy(ctx);
     for (auto& a : ctx->arrays) a.d.release();
     for (auto& p : ctx->potentials) { p.conn.release(); p.slots.release(); }
     ctx->H.release(); ctx->rows.release(); ctx->E_elem.release(); ctx->grad.release(); ctx->du.release();
@@ -491,6 +492,18 @@ int sb_potential_get_block_rows(sb_context* ctx, int potential, int32_t* host_ro
     Potential& p = ctx->potentials[potential];
     if (p.n_elem == 0) return SB_OK;
     SB_CUDA(ctx, cudaMemcpyAsync(host_rows, ctx->rows.p + p.rows_off, sizeof(int32_t) * (size_t)p.n_elem * p.k->nb, cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}
+
+int sb_potential_get_hessians(sb_context* ctx, int potential, double* host_hessians)
+{
+    int r = check_pot(ctx, potential, "sb_potential_get_hessians"); if (r) return r;
+    if (!ctx->have_pgh) return fail(ctx, SB_ERR_STATE, "sb_potential_get_hessians: call sb_eval(SB_EVAL_PGH) first");
+    Potential& p = ctx->potentials[potential];
+    if (p.n_elem == 0) return SB_OK;
+    const size_t n = p.k->n_dof;
+    SB_CUDA(ctx, cudaMemcpyAsync(host_hessians, ctx->H.p + p.H_off, sizeof(double) * (size_t)p.n_elem * n * n, cudaMemcpyDeviceToHost, ctx->stream));
     SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return SB_OK;
 }

@@ -112,6 +112,7 @@ struct Potential {
 struct Assembly;   // assembly.cu
 struct Pcg;        // pcg.cu
 struct Contact;    // contact.cu
+struct Projector;  // project.cu
 
 }  // namespace sb
 
@@ -147,6 +148,7 @@ struct sb_context {
     sb::Assembly* assembly = nullptr;
     sb::Pcg* pcg = nullptr;
     sb::Contact* contact = nullptr;
+    sb::Projector* projector = nullptr;
 };
 
 namespace sb {
@@ -161,5 +163,13 @@ void reduce_absmax(sb_context* ctx, const double* d_in, size_t n, double* d_out)
 void assembly_destroy(sb_context* ctx);
 void pcg_destroy(sb_context* ctx);
 void contact_destroy(sb_context* ctx);
+void projector_destroy(sb_context* ctx);
+int assemble_internal(sb_context* ctx);
+int project_internal(sb_context* ctx, double grad_threshold, double eps, int mirror, int64_t* out_n_projected, int64_t* out_n_hessians, int* out_all_projected);
+int solve_pcg_internal(sb_context* ctx, double abs_tol, double rel_tol, int max_iter, int stop_on_indef, int* out_iterations, int* out_ok, double* out_du_dot_grad, double* out_du_inf);
+// contact hooks used by the Newton driver (contact.cu)
+int contact_update_internal(sb_context* ctx);
+int contact_intersections_internal(sb_context* ctx, int* out_count);
+bool contact_active(sb_context* ctx);
 int eval_internal(sb_context* ctx, int mode, double* out_E, double* out_grad_inf, bool sync_scalars);
 }  // namespace sb

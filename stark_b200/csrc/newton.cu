@@ -1,0 +1,217 @@
+// Newton driver on device-resident state.
+//
+// Replaces symx::NewtonsMethod::solve and its helpers (symx/solver/NewtonsMethod.cpp:28-641): same control flow, same
+// projection policies (Newton / ProjectedNewton / ProjectOnDemand / Progressive), same Eisenstat-Walker forcing
+// tolerance for the PCG, same four-stage line search (cap / max / invalid-state halving / Armijo).  The host only sees
+// scalars (E, |g|_inf, du.g, |du|_inf, counts); DoFs, gradient, element Hessians, BCSR and contact tables stay on the GPU.
+// The model callbacks the reference runs on the host are the built-in contact stages here:
+//   before_energy_evaluation  -> contact_update_internal       (EnergyFrictionalContact.cpp:368-530)
+//   is_*_state_valid          -> contact_intersections_internal (EnergyFrictionalContact.cpp:774-799)
+#include "internal.h"
+#include <algorithm>
+#include <cmath>
+#include <limits>
+
+using namespace sb;
+
+namespace {
+// symx::SolverReturn (symx/solver/solver_utils.h:15-26)
+enum Ret { Successful = 0, Running, InvalidInitialState, TooManyIterations, TooManyArmijoIterations, LinearSystemSolveFailure,
+           TooManyInvalidIntermediateIterations, StepDoesNotDescend, InvalidConvergedState };
+enum Proj { PNewton = 0, PProjectedNewton = 1, PProjectOnDemand = 2, PProgressive = 3 };
+}
+
+extern "C" void sb_newton_default_settings(sb_newton_settings* s)
+{
+    if (!s) return;
+    // symx defaults (solver_utils.h:170-258) with STARK's overrides (S/core/Settings.cpp:45-49)
+    s->max_iterations = std::numeric_limits<int>::max();
+    s->min_iterations = 0;
+    s->residual_tolerance_abs = 1e-6;
+    s->residual_tolerance_rel = 0.0;
+    s->step_tolerance = 1e-3;
+    s->max_iterations_as_success = 0;
+    s->step_cap = std::numeric_limits<double>::infinity();
+    s->enable_armijo_backtracking = 1;
+    s->line_search_armijo_beta = 1e-4;
+    s->max_backtracking_armijo_iterations = 20;
+    s->max_backtracking_invalid_state_iterations = 8;
+    s->projection_mode = PProgressive;
+    s->projection_eps = 1e-10;
+    s->project_to_pd_use_mirroring = 0;
+    s->project_on_demand_countdown = 4;
+    s->ppn_tightening_factor = 0.5;
+    s->ppn_release_factor = 2.0;
+    s->linear_solver = 1;
+    s->cg_max_iterations = 10000;
+    s->cg_abs_tolerance = 1e-12;
+    s->cg_rel_tolerance = 1e-4;
+    s->cg_stop_on_indefiniteness = 1;
+    s->bailout_residual = 1e-10;
+    s->contact_enabled = 1;
+}
+
+extern "C" int sb_newton_solve(sb_context* ctx, const sb_newton_settings* S, sb_newton_stats* stats)
+{
+    if (!ctx || !S || !stats) return fail(ctx, SB_ERR_ARG, "sb_newton_solve: bad argument");
+    if (S->linear_solver != 1) return fail(ctx, SB_ERR_ARG, "sb_newton_solve: only BDPCG is built (DirectLLT is a later row)");
+    recompute_dof_offsets(ctx);
+    const int ndofs = ctx->ndofs;
+    if (ndofs <= 0) return fail(ctx, SB_ERR_STATE, "sb_newton_solve: no degrees of freedom");
+    if (ndofs % 3 != 0) return fail(ctx, SB_ERR_STATE, "sb_newton_solve: ndofs must be divisible by 3");
+    *stats = sb_newton_stats();
+    const bool contact = S->contact_enabled && contact_active(ctx);
+    int rc;
+    auto record = [&](double r) { if (stats->n_evaluations < 64) stats->residuals[stats->n_evaluations] = r; stats->n_evaluations++; };
+    auto state_valid = [&](bool& valid) -> int {
+        valid = true;
+        if (!contact) return 0;
+        int n = 0;
+        int r = contact_intersections_internal(ctx, &n);
+        if (r) return r;
+        valid = (n == 0);
+        return 0;
+    };
+
+    double E0 = 0.0, du_dot_grad = 0.0, res_0 = std::numeric_limits<double>::max();
+    int result = Running;
+    int pdn_countdown = 0;
+    double ppn_threshold = -1.0;
+
+    bool valid = true;
+    if ((rc = state_valid(valid))) return rc;
+    if (!valid) result = InvalidInitialState;
+
+    int it = -1;
+    while (result == Running) {
+        it++;
+        if (it == S->max_iterations) {
+            result = S->max_iterations_as_success ? Successful : TooManyIterations;
+            break;
+        }
+        if (contact && (rc = contact_update_internal(ctx))) return rc;
+        double residual = 0.0;
+        if ((rc = eval_internal(ctx, SB_EVAL_PGH, &E0, &residual, true))) return rc;
+        record(residual);
+        stats->last_residual = residual;
+        stats->last_energy = E0;
+        if (it == 0) res_0 = residual;
+        if (residual < S->bailout_residual) { result = Successful; break; }
+        if (it >= S->min_iterations) {
+            if (residual < S->residual_tolerance_abs) { result = Successful; break; }
+            if (it > 0 && residual / res_0 < S->residual_tolerance_rel) { result = Successful; break; }
+        }
+
+        // ---- project + assemble + solve until the direction descends (NewtonsMethod.cpp:137-182)
+        bool assembled = false;
+        bool solved = false;
+        double du_inf = 0.0;
+        int64_t n_proj = 0, n_hess = 0;
+        while (!solved) {
+            bool all_projected = false;
+            // _project_and_assemble (NewtonsMethod.cpp:254-352).  The reference assembles the unprojected matrix first and
+            // then adds (projected - original) blocks; here the projected Hessians replace the originals in the element
+            // store and one numeric assembly follows, so projection simply runs first.
+            bool projected_now = false;
+            int allp = 0;
+            switch (S->projection_mode) {
+            case PNewton: break;
+            case PProjectedNewton:
+                if ((rc = project_internal(ctx, 0.0, S->projection_eps, S->project_to_pd_use_mirroring, &n_proj, &n_hess, &allp))) return rc;
+                all_projected = true; projected_now = true;
+                break;
+            case PProjectOnDemand:
+                if (pdn_countdown > 0) {
+                    if ((rc = project_internal(ctx, 0.0, S->projection_eps, S->project_to_pd_use_mirroring, &n_proj, &n_hess, &allp))) return rc;
+                    all_projected = true; projected_now = true;
+                }
+                break;
+            case PProgressive:
+                if (ppn_threshold > 0.0) {
+                    if (ppn_threshold < 1e-12) ppn_threshold = 0.0;
+                    if ((rc = project_internal(ctx, ppn_threshold, S->projection_eps, S->project_to_pd_use_mirroring, &n_proj, &n_hess, &allp))) return rc;
+                    all_projected = (allp != 0); projected_now = true;
+                }
+                break;
+            default: return fail(ctx, SB_ERR_ARG, "sb_newton_solve: unknown projection mode");
+            }
+            if (!assembled || projected_now) {
+                if ((rc = assemble_internal(ctx))) return rc;
+                assembled = true;
+            }
+            // _solve_linear_system (NewtonsMethod.cpp:420-451): forcing sequence
+            const double forcing = std::min(1e-2, residual * std::min(0.5, std::sqrt(residual)));
+            const double abs_tol = std::max(forcing, S->cg_abs_tolerance);
+            int cg_it = 0, ok = 0;
+            if ((rc = solve_pcg_internal(ctx, abs_tol, S->cg_rel_tolerance, S->cg_max_iterations, S->cg_stop_on_indefiniteness, &cg_it, &ok, &du_dot_grad, &du_inf))) return rc;
+            stats->cg_iterations += cg_it;
+            const bool can_project_more = (S->projection_mode != PNewton) && !all_projected;
+            if (!ok) {
+                if (!can_project_more) { result = LinearSystemSolveFailure; break; }
+            } else {
+                if (du_dot_grad < 0.0) { solved = true; break; }
+                if (!can_project_more) { result = StepDoesNotDescend; break; }
+            }
+            // _increase_projection (NewtonsMethod.cpp:354-371)
+            if (S->projection_mode == PProjectOnDemand) pdn_countdown = S->project_on_demand_countdown;
+            else if (S->projection_mode == PProgressive) {
+                if (ppn_threshold < 0.0) ppn_threshold = residual;   // grad.cwiseAbs().maxCoeff()
+                ppn_threshold *= S->ppn_tightening_factor;
+            }
+        }
+        if (result != Running) break;
+        // _decrease_projection
+        if (S->projection_mode == PProjectOnDemand) pdn_countdown--;
+        else if (S->projection_mode == PProgressive) ppn_threshold *= S->ppn_release_factor;
+        stats->n_hessians += (int64_t)ctx->n_hessians;
+        stats->n_projected_hessians += ctx->n_projected;
+
+        if (it >= S->min_iterations && du_inf < S->step_tolerance) { result = Successful; break; }
+
+        // ---- line search (NewtonsMethod.cpp:459-641)
+        if ((rc = sb_dofs_save(ctx))) return rc;
+        double retraction = 1.0;
+        if (du_inf > S->step_cap) {
+            retraction *= S->step_cap / du_inf;
+            if ((rc = sb_du_scale(ctx, retraction))) return rc;
+            du_inf = S->step_cap;
+            stats->ls_cap_iterations++;
+        }
+        // [max] no max_allowed_step callback is registered by STARK
+        double step = 1.0;
+        if ((rc = sb_dofs_apply_step(ctx, step))) return rc;
+        int ls_inv = 0;
+        for (; ls_inv < S->max_backtracking_invalid_state_iterations; ++ls_inv) {
+            if ((rc = state_valid(valid))) return rc;
+            if (valid) break;
+            step *= 0.5;
+            if ((rc = sb_dofs_apply_step(ctx, step))) return rc;
+            stats->ls_inv_iterations++;
+        }
+        if (ls_inv == S->max_backtracking_invalid_state_iterations) { result = TooManyInvalidIntermediateIterations; break; }
+        if (S->enable_armijo_backtracking) {
+            const double expected = S->line_search_armijo_beta * du_dot_grad * retraction;
+            double E_threshold = E0 + expected * step;
+            double E1 = 0.0;
+            int k = 0;
+            for (; k < S->max_backtracking_armijo_iterations; ++k) {
+                if (contact && (rc = contact_update_internal(ctx))) return rc;
+                if ((rc = eval_internal(ctx, SB_EVAL_P, &E1, nullptr, true))) return rc;
+                if (E1 < E_threshold) break;
+                step *= 0.5;
+                if ((rc = sb_dofs_apply_step(ctx, step))) return rc;
+                E_threshold = E0 + expected * step;
+                stats->ls_bt_iterations++;
+            }
+            if (k == S->max_backtracking_armijo_iterations) { result = TooManyArmijoIterations; break; }
+        }
+    }
+
+    if (result == Successful) {
+        if ((rc = state_valid(valid))) return rc;
+        if (!valid) result = InvalidConvergedState;
+    }
+    stats->result = result;
+    stats->newton_iterations = it;
+    return SB_OK;
+}

@@ -1,6 +1,6 @@
 // Temporary: contact entry points until contact.cu lands.
 #include "internal.h"
-namespace sb { void contact_destroy(sb_context*) {} }
+namespace sb { void contact_destroy(sb_context*) {} int contact_update_internal(sb_context*) { return 0; } int contact_intersections_internal(sb_context*, int* c) { *c = 0; return 0; } bool contact_active(sb_context*) { return false; } }
 using namespace sb;
 extern "C" {
 #define NOT_YET(name) return fail(ctx, SB_ERR_STATE, name ": not built yet")

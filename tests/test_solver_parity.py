@@ -1,0 +1,150 @@
+"""GPU parity of assembly, PD projection, block-Jacobi PCG and the Newton driver (SURVEY.md 8(c) stages 2, 3, 5):
+CUDA path (through the C-ABI) vs the numpy oracle on the same inputs and vs the reference's golden outputs."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from golden_util import Golden, bind
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+import oracle  # noqa: E402
+
+FIXTURES = ["tetdrop_n3", "tetdrop_n5", "tetbar_n2", "cloth_n8", "cloth_shells_n8"]
+
+
+def setup(fixture):
+    from stark_b200 import capi
+    ctx = capi.Context(0)
+    g = Golden(fixture)
+    handles = bind(ctx, g, set(capi.kernel_names()))
+    return capi, ctx, g, handles
+
+
+def gpu_elements(ctx, handles):
+    Hs, rows = [], []
+    for i in sorted(handles):
+        H = ctx.hessians(handles[i])
+        r = ctx.block_rows(handles[i])
+        Hs += list(H)
+        rows += [list(x) for x in r]
+    return Hs, rows
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fixture", FIXTURES)
+def test_assembly(fixture):
+    capi, ctx, g, handles = setup(fixture)
+    ctx.eval("PGH")
+    ctx.assemble()
+    rows, cols, vals = ctx.bcsr()
+    # pattern: bit-exact against the reference
+    assert np.array_equal(rows, g["bcsr_rows"])
+    assert np.array_equal(cols, g["bcsr_cols"])
+    # values: bit-exact against the oracle's float64-accumulated, float-rounded sum of the SAME element Hessians
+    Hs, erows = gpu_elements(ctx, handles)
+    rp, oc, ov = oracle.assemble_bcsr(Hs, erows, len(rows) - 1)
+    assert np.array_equal(rp, rows) and np.array_equal(oc, cols)
+    diff = np.abs(ov.astype(np.float64) - vals.astype(np.float64)).reshape(-1, 9)
+    scale = np.abs(ov.astype(np.float64)).reshape(-1, 9).max(axis=1, keepdims=True) + 1e-30
+    assert (diff / scale).max() < 2e-7   # one float ulp (summation order inside float64 may differ)
+    # and within float-accumulation noise of the reference's values
+    ref = g["bcsr_vals"].astype(np.float64).reshape(-1, 9)
+    assert (np.abs(vals.astype(np.float64).reshape(-1, 9) - ref) / (np.abs(ref).max(axis=1, keepdims=True) + 1e-30)).max() < 5e-5
+    # second assembly with an unchanged pattern reuses the symbolic phase and gives identical values
+    ctx.assemble()
+    _, _, vals2 = ctx.bcsr()
+    assert np.array_equal(vals, vals2)
+    ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fixture", FIXTURES)
+def test_pcg(fixture):
+    capi, ctx, g, handles = setup(fixture)
+    ctx.eval("PGH")
+    ctx.assemble()
+    rows, cols, vals = ctx.bcsr()
+    grad = ctx.grad()
+    out = ctx.solve_pcg(g.meta["pcg_abs_tol"], g.meta["pcg_rel_tol"], 10000, True)
+    du = ctx.du()
+    # oracle on the same matrix / rhs
+    x, it, ok = oracle.solve_pcg(rows, cols, vals, -grad, g.meta["pcg_abs_tol"], g.meta["pcg_rel_tol"], 10000)
+    assert out["ok"] == ok == bool(g.meta["pcg_converged"])
+    assert out["iterations"] == it
+    assert abs(out["iterations"] - g.meta["pcg_iterations"]) <= 1
+    assert np.abs(du - x).max() <= 1e-7 * np.abs(x).max()
+    if out["iterations"] == g.meta["pcg_iterations"]:
+        assert np.abs(du - g["pcg_du"]).max() <= 1e-4 * np.abs(g["pcg_du"]).max()
+    # contract of the inexact solve: residual below the forcing tolerance, descent direction
+    r = oracle.bcsr_spmv(rows, cols, vals, du) + grad
+    assert np.linalg.norm(r) / np.linalg.norm(grad) < max(g.meta["pcg_abs_tol"], g.meta["pcg_rel_tol"]) * 1.0000001
+    assert out["du_dot_grad"] < 0
+    assert abs(out["du_dot_grad"] - du @ grad) <= 1e-12 * abs(du @ grad)
+    assert abs(out["du_inf"] - np.abs(du).max()) == 0.0
+    assert abs(out["du_dot_grad"] - g.meta["du_dot_grad"]) <= 1e-4 * abs(g.meta["du_dot_grad"])
+    ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fixture", ["tetdrop_n3", "cloth_n8", "cloth_shells_n8"])
+def test_projection_all(fixture):
+    capi, ctx, g, handles = setup(fixture)
+    ctx.eval("PGH")
+    before, _ = gpu_elements(ctx, handles)
+    n_proj, n_hess, all_proj = ctx.project_to_pd(0.0)
+    assert n_proj == n_hess == len(before) and all_proj
+    after, _ = gpu_elements(ctx, handles)
+    n_changed = 0
+    for H, P in zip(before, after):
+        ref, changed = oracle.project_to_pd(H)
+        n_changed += changed
+        assert np.abs(P - ref).max() <= 1e-9 * max(1.0, np.abs(ref).max())
+        if changed:
+            assert np.linalg.eigvalsh(0.5 * (P + P.T)).min() > -1e-9 * np.abs(P).max()
+    assert n_changed > 0
+    # projecting again is idempotent (everything is flagged as projected)
+    n_proj2, _, _ = ctx.project_to_pd(0.0)
+    assert n_proj2 == n_proj
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_projection_selective_ppn():
+    capi, ctx, g, handles = setup("tetdrop_n3")
+    E, res = ctx.eval("PGH")
+    grad = ctx.grad()
+    thr = 0.5 * res
+    before, rows = gpu_elements(ctx, handles)
+    n_proj, n_hess, all_proj = ctx.project_to_pd(thr)
+    active = np.abs(grad.reshape(-1, 3)).max(axis=1) >= thr
+    expect = sum(1 for r in rows if active[r].any())
+    assert n_proj == expect and not all_proj and 0 < n_proj < n_hess
+    after, _ = gpu_elements(ctx, handles)
+    for H, P, r in zip(before, after, rows):
+        if active[r].any():
+            ref, _ = oracle.project_to_pd(H)
+            assert np.abs(P - ref).max() <= 1e-9 * max(1.0, np.abs(ref).max())
+        else:
+            assert np.array_equal(H, P)
+    ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fixture", ["tetbar_n2", "tetdrop_n3"])
+def test_newton_converges_from_injected_state(fixture):
+    """Newton driver without the contact callbacks (fixed contact lists): residual history starts at the reference's
+    residual for this state and drops below the tolerance with a monotone energy decrease."""
+    capi, ctx, g, handles = setup(fixture)
+    s = ctx.newton_default_settings()
+    s.contact_enabled = 0
+    s.max_iterations = 50
+    E0 = ctx.eval("P")
+    st = ctx.newton_solve(s)
+    assert st.result == 0, st.result
+    assert abs(st.residuals[0] - g.meta["residual_inf"]) <= 1e-10 * g.meta["residual_inf"]
+    assert st.last_residual < 1e-6 or st.n_evaluations > 1
+    assert st.last_energy < E0
+    assert 1 <= st.newton_iterations <= 20
+    ctx.close()
