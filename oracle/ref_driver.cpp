@@ -431,6 +431,19 @@ static void dump_iteration(const Args& a, stark::Simulation& sim)
 			D.bin("mesh" + std::to_string(g) + "_vertices", &mesh.vertices[0][0], mesh.vertices.size() * 3);
 			if (!dummy_tri) D.bin("mesh" + std::to_string(g) + "_triangles", &mesh.loc_triangles[0][0], mesh.loc_triangles.size() * 3);
 			D.bin("mesh" + std::to_string(g) + "_edges", &mesh.loc_edges[0][0], mesh.loc_edges.size() * 2);
+			// index of every collision vertex in its physical system (deformable: global node, rigid: row of rigidbody_local_vertices)
+			std::vector<int32_t> ps_index(mesh.vertices.size());
+			for (int i = 0; i < (int)mesh.vertices.size(); i++) ps_index[i] = contact->_local_to_ps_global_indices<1>((int)g, { i })[0];
+			D.bin("mesh" + std::to_string(g) + "_ps_index", ps_index.data(), ps_index.size());
+		}
+		D.bin("rigidbody_local_vertices", &contact->rigidbody_local_vertices.data[0][0], contact->rigidbody_local_vertices.data.size() * 3);
+		{
+			std::ostringstream fj; fj << "[";
+			bool ff = true;
+			for (const auto& kv : contact->pair_coulombs_mu) { if (!ff) fj << ", "; ff = false; fj << "[" << kv.first[0] << ", " << kv.first[1] << ", " << std::setprecision(17) << kv.second << "]"; }
+			fj << "]";
+			D.raw("friction_pairs", fj.str());
+			D.num("friction_stick_slide_threshold", contact->global_params.friction_stick_slide_threshold);
 		}
 		mj << "]";
 		D.raw("meshes", mj.str());

@@ -1,0 +1,1083 @@
+// Collision detection and contact / friction list construction on the device.
+//
+// Replaces, for the Newton hot path:
+//   * tmcd::ProximityDetection::run  (tmcd/ProximityDetection.cpp:74-220): float AABBs enlarged by (enl + FLT_EPSILON)
+//     (tmcd/AABBs.cpp:22-180), candidate pairs = overlapping AABBs minus shared-vertex ("orphan") and blacklisted pairs
+//     (tmcd/BroadPhasePTEEBase.cpp:270-420), narrow phase = IPC-toolkit distance-type classification + squared distance
+//     (tmcd/ipc_toolkit_geometry_functions.cpp:42-306), kept if d^2 < enl^2;
+//   * tmcd::IntersectionDetection::run (tmcd/IntersectionDetection.cpp:54-108, geometry :565-585);
+//   * EnergyFrictionalContact::{_update_vertices, _before_energy_evaluation__update_contacts,
+//     _before_time_step__update_friction_contacts} (S/models/interactions/EnergyFrictionalContact.cpp:219-262, 368-773):
+//     the serial host loops that turn proximity pairs into the 21 connectivity tables and the friction data
+//     (T, bary, fn, mu -- S/models/interactions/friction_geometry.cpp).
+//
+// The reference's octree only de-duplicates and prunes; the candidate SET is "all overlapping AABB pairs", which is what
+// the tiled all-pairs kernels below enumerate directly (one CTA per 256 x 256 tile, AABBs staged in shared memory).
+// Candidates are compacted into a list and classified one pair per thread by a second kernel, so the long narrow-phase
+// code does not diverge inside the tile loop.  Compile this file with -fmad=false: the classification thresholds of the
+// narrow phase are decided by the last bit for grid-aligned scenes, and un-fused IEEE arithmetic in the reference's
+// operation order is the closest reproducible restatement.
+#include "internal.h"
+#include <algorithm>
+#include <cfloat>
+#include <cstring>
+
+namespace sb {
+
+enum Role { R_SOFT_V1, R_SOFT_X0, R_SOFT_X, R_RB_V1, R_RB_W1, R_RB_T0, R_RB_Q0, R_DT, R_THICKNESS, R_STIFFNESS, R_RB_LOCAL, R_EPSV,
+            R_F_T, R_F_BARY, R_F_MU, R_F_FN };
+struct LayoutEntry { int role, col, slot, stride; };
+struct Layout { const char* name; int conn_stride; int n; LayoutEntry e[32]; };
+static const Layout LAYOUTS[] = {
+#include "contact_layouts.inc"
+};
+constexpr int N_TABLES = 25;       // 15 contact + 10 friction, in the order of contact_layouts.inc
+constexpr int N_CONTACT_TABLES = 15;
+constexpr int N_FRICTION = 10;
+enum Table {
+    CT_DD_PT_PP, CT_DD_PT_PE, CT_DD_PT_PT, CT_DD_EE_PP, CT_DD_EE_PE, CT_DD_EE_EE,
+    CT_RD_PT_PP, CT_RD_PT_PE, CT_RD_PT_PT, CT_RD_PT_EP, CT_RD_PT_TP, CT_RD_EE_PP, CT_RD_EE_PE, CT_RD_EE_EE, CT_RD_EE_EP,
+    FT_DD_PP, FT_DD_PE, FT_DD_PT, FT_DD_EE, FT_RD_PP, FT_RD_PE, FT_RD_PT, FT_RD_EE, FT_RD_EP, FT_RD_TP
+};
+constexpr int N_LISTS = 7;         // pt_pp pt_pe pt_pt ee_pp ee_pe ee_ee intersections
+static const int LIST_WIDTH[N_LISTS] = {5, 6, 4, 6, 5, 4, 4};
+constexpr int MAX_GROUPS = 64;
+
+struct Group {
+    int ps, body, n_v, n_t, n_e;
+    int v_off, t_off, e_off;   // offsets in the concatenated collision vertex / triangle / edge arrays
+    double thickness;
+};
+
+// everything the device kernels need, passed by value
+struct Dev {
+    int n_v, n_t, n_e, n_groups;
+    double* x;                   // [n_v][3] current collision vertex positions
+    const int32_t* v_group;      // [n_v]
+    const int32_t* v_ps_index;   // [n_v] soft: global node; rigid: row in the rigid local-vertex array
+    const int32_t* tri;          // [n_t][3] global collision vertex ids
+    const int32_t* t_group;
+    const int32_t* edge;         // [n_e][2]
+    const int32_t* e_group;
+    float* bb_p; float* bb_t; float* bb_e;   // [n][6] bottom xyz, top xyz
+    const int32_t* g_ps; const int32_t* g_body; const int32_t* g_voff; const int32_t* g_toff; const int32_t* g_eoff;
+    const double* g_thickness;
+    const uint8_t* blacklist;    // [MAX_GROUPS * MAX_GROUPS]
+    const double* mu;            // [MAX_GROUPS * MAX_GROUPS]
+    // candidates
+    int2* cand_pt; int2* cand_ee; int2* cand_et;
+    int cand_cap;
+    int* counters;               // [0] pt cands [1] ee cands [2] et cands [3] overflow flag, [8 + l] list counts, [16 + t] table counts
+    // raw results
+    int32_t* list_ids[N_LISTS];
+    double* list_dist[N_LISTS];
+    int list_cap;
+    // contact / friction tables
+    int32_t* table[N_TABLES];
+    int table_stride[N_TABLES];
+    int table_cap;
+    double* fT[N_FRICTION]; double* fmu[N_FRICTION]; double* ffn[N_FRICTION]; double* fbary[N_FRICTION];
+};
+
+struct Contact {
+    sb_contact_bindings bind;
+    std::vector<Group> groups;
+    std::vector<int32_t> h_v_group, h_v_ps, h_tri, h_t_group, h_edge, h_e_group;
+    std::vector<double> h_rb_local;          // concatenated rigid local vertices
+    std::vector<uint8_t> h_blacklist;
+    std::vector<double> h_mu;
+    bool topology_dirty = true;
+    double stiffness = 1e3, epsv = 0.1;
+    int enable_pt = 1, enable_ee = 1, enable_friction = 1;
+    // ctx arrays owned by the module
+    int a_thickness = -1, a_stiffness = -1, a_rb_local = -1, a_epsv = -1;
+    int a_fT[N_FRICTION], a_fbary[N_FRICTION], a_fmu[N_FRICTION], a_ffn[N_FRICTION];
+    int pot[N_TABLES];
+    // device storage
+    DevBuf<double> x;
+    DevBuf<int32_t> v_group, v_ps, tri, t_group, edge, e_group, g_i32;
+    DevBuf<double> g_f64, mu;
+    DevBuf<uint8_t> blacklist;
+    DevBuf<float> bb_p, bb_t, bb_e;
+    DevBuf<int2> cand_pt, cand_ee, cand_et;
+    DevBuf<int> counters;
+    DevBuf<int32_t> list_ids[N_LISTS];
+    DevBuf<double> list_dist[N_LISTS];
+    DevBuf<int32_t> table[N_TABLES];
+    int cand_cap = 1 << 16, list_cap = 1 << 14, table_cap = 1 << 14;
+    int* h_counters = nullptr;
+    int h_list_count[N_LISTS] = {0};
+    int h_table_count[N_TABLES] = {0};
+    bool external_vertices = false;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// vertex update (EnergyFrictionalContact.cpp:219-250)
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_update_vertices(Dev d, const double* __restrict__ v1, const double* __restrict__ x0, const double* __restrict__ rb_v, const double* __restrict__ rb_w,
+                                  const double* __restrict__ rb_t0, const double* __restrict__ rb_q0, const double* __restrict__ rb_local, const double* __restrict__ dt_ptr, int zero_dt)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.n_v) return;
+    const double dt = zero_dt ? 0.0 : dt_ptr[0];
+    const int g = d.v_group[i];
+    const int k = d.v_ps_index[i];
+    if (d.g_ps[g] == 0) {
+        for (int c = 0; c < 3; c++) d.x[3 * i + c] = x0[3 * k + c] + dt * v1[3 * k + c];
+    } else {
+        const int b = d.g_body[g];
+        // quat_time_integration (rigidbody_transformations.cpp:33-40): q1 = normalize(q0 + dt/2 (0,w) * q0); q0 as (w,x,y,z)
+        const double qw = rb_q0[4 * b], qx = rb_q0[4 * b + 1], qy = rb_q0[4 * b + 2], qz = rb_q0[4 * b + 3];
+        const double wx = rb_w[3 * b], wy = rb_w[3 * b + 1], wz = rb_w[3 * b + 2];
+        const double pw = -wx * qx - wy * qy - wz * qz;
+        const double px = wx * qw + wy * qz - wz * qy;
+        const double py = wy * qw + wz * qx - wx * qz;
+        const double pz = wz * qw + wx * qy - wy * qx;
+        const double h = 0.5 * dt;
+        double ew = qw + h * pw, ex = qx + h * px, ey = qy + h * py, ez = qz + h * pz;
+        const double n = sqrt(ex * ex + ey * ey + ez * ez + ew * ew);
+        ew /= n; ex /= n; ey /= n; ez /= n;
+        const double tx = 2.0 * ex, ty = 2.0 * ey, tz = 2.0 * ez;
+        const double twx = tx * ew, twy = ty * ew, twz = tz * ew;
+        const double txx = tx * ex, txy = ty * ex, txz = tz * ex;
+        const double tyy = ty * ey, tyz = tz * ey, tzz = tz * ez;
+        const double R[9] = {1.0 - (tyy + tzz), txy - twz, txz + twy, txy + twz, 1.0 - (txx + tzz), tyz - twx, txz - twy, tyz + twx, 1.0 - (txx + tyy)};
+        const double X0 = rb_local[3 * k], X1 = rb_local[3 * k + 1], X2 = rb_local[3 * k + 2];
+        for (int c = 0; c < 3; c++) {
+            const double t1 = rb_t0[3 * b + c] + dt * rb_v[3 * b + c];
+            d.x[3 * i + c] = t1 + (R[3 * c] * X0 + R[3 * c + 1] * X1 + R[3 * c + 2] * X2);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// AABBs (tmcd/AABBs.cpp:22-140): float min / max of the vertices, enlarged by extra = (float)enl + FLT_EPSILON
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bb_init(float* b) { b[0] = b[1] = b[2] = FLT_MAX; b[3] = b[4] = b[5] = -FLT_MAX; }
+__device__ __forceinline__ void bb_expand(float* b, const double* x)
+{
+    for (int c = 0; c < 3; c++) { const float v = (float)x[c]; b[c] = fminf(b[c], v); b[3 + c] = fmaxf(b[3 + c], v); }
+}
+__global__ void k_aabbs(Dev d, float extra, int do_points)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float b[6];
+    if (do_points && i < d.n_v) {
+        bb_init(b); bb_expand(b, d.x + 3 * i);
+        for (int c = 0; c < 3; c++) { d.bb_p[6 * i + c] = b[c] - extra; d.bb_p[6 * i + 3 + c] = b[3 + c] + extra; }
+    }
+    if (i < d.n_t) {
+        bb_init(b);
+        for (int k = 0; k < 3; k++) bb_expand(b, d.x + 3 * d.tri[3 * i + k]);
+        for (int c = 0; c < 3; c++) { d.bb_t[6 * i + c] = b[c] - extra; d.bb_t[6 * i + 3 + c] = b[3 + c] + extra; }
+    }
+    if (i < d.n_e) {
+        bb_init(b);
+        for (int k = 0; k < 2; k++) bb_expand(b, d.x + 3 * d.edge[2 * i + k]);
+        for (int c = 0; c < 3; c++) { d.bb_e[6 * i + c] = b[c] - extra; d.bb_e[6 * i + 3 + c] = b[3 + c] + extra; }
+    }
+}
+
+// tmcd/helpers.h:35-44
+__device__ __forceinline__ bool bb_overlap(const float* a, const float* b)
+{
+    bool o = true;
+    for (int c = 0; c < 3; c++) if (a[c] > b[3 + c] || b[c] > a[3 + c]) o = false;
+    return o;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// broad phase: tiled all-pairs.  KIND 0: point(A) x triangle(B); 1: edge(A) x edge(B), A < B; 2: edge(A) x triangle(B)
+// ---------------------------------------------------------------------------------------------------
+constexpr int TILE = 256;
+template<int KIND>
+__global__ void __launch_bounds__(TILE) k_broad(Dev d)
+{
+    __shared__ float s_bb[TILE][6];
+    __shared__ int s_v[TILE][3];
+    __shared__ int s_g[TILE];
+    const int nA = (KIND == 0) ? d.n_v : d.n_e;
+    const int nB = (KIND == 1) ? d.n_e : d.n_t;
+    const float* bbA = (KIND == 0) ? d.bb_p : d.bb_e;
+    const float* bbB = (KIND == 1) ? d.bb_e : d.bb_t;
+    const int a = blockIdx.x * TILE + threadIdx.x;
+    const int b0 = blockIdx.y * TILE;
+    if (KIND == 1 && b0 + TILE - 1 <= blockIdx.x * TILE) return;   // whole tile has B <= A
+    {
+        const int b = b0 + threadIdx.x;
+        if (b < nB) {
+            for (int c = 0; c < 6; c++) s_bb[threadIdx.x][c] = bbB[6 * b + c];
+            if (KIND == 1) { s_v[threadIdx.x][0] = d.edge[2 * b]; s_v[threadIdx.x][1] = d.edge[2 * b + 1]; s_v[threadIdx.x][2] = -1; s_g[threadIdx.x] = d.e_group[b]; }
+            else { s_v[threadIdx.x][0] = d.tri[3 * b]; s_v[threadIdx.x][1] = d.tri[3 * b + 1]; s_v[threadIdx.x][2] = d.tri[3 * b + 2]; s_g[threadIdx.x] = d.t_group[b]; }
+        }
+    }
+    __syncthreads();
+    if (a >= nA) return;
+    float ba[6];
+    for (int c = 0; c < 6; c++) ba[c] = bbA[6 * a + c];
+    int va0, va1, ga;
+    if (KIND == 0) { va0 = a; va1 = -2; ga = d.v_group[a]; }
+    else { va0 = d.edge[2 * a]; va1 = d.edge[2 * a + 1]; ga = d.e_group[a]; }
+    const int nb = min(TILE, nB - b0);
+    for (int j = 0; j < nb; j++) {
+        const int b = b0 + j;
+        if (KIND == 1 && b <= a) continue;
+        if (!bb_overlap(ba, s_bb[j])) continue;
+        const int gb = s_g[j];
+        // shared-vertex ("orphan") discard: same set and a common vertex (collision vertex ids are global, so equality suffices)
+        const bool orphan = (va0 == s_v[j][0]) || (va0 == s_v[j][1]) || (va0 == s_v[j][2]) || (va1 == s_v[j][0]) || (va1 == s_v[j][1]) || (va1 == s_v[j][2]);
+        if (orphan) continue;
+        if (d.blacklist[ga * MAX_GROUPS + gb]) continue;
+        int2* out = (KIND == 0) ? d.cand_pt : (KIND == 1 ? d.cand_ee : d.cand_et);
+        const int slot = atomicAdd(d.counters + KIND, 1);
+        if (slot < d.cand_cap) out[slot] = make_int2(a, b); else d.counters[3] = 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// narrow phase geometry (tmcd/ipc_toolkit_geometry_functions.cpp), same operation order
+// ---------------------------------------------------------------------------------------------------
+struct V { double x, y, z; };
+__device__ __forceinline__ V ld(const double* p) { return {p[0], p[1], p[2]}; }
+__device__ __forceinline__ V operator-(V a, V b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ V operator+(V a, V b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ V operator*(double s, V a) { return {s * a.x, s * a.y, s * a.z}; }
+__device__ __forceinline__ double dotv(V a, V b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ V crossv(V a, V b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+__device__ __forceinline__ double sqn(V a) { return dotv(a, a); }
+__device__ __forceinline__ V normalizedv(V a) { const double n = sqrt(sqn(a)); return {a.x / n, a.y / n, a.z / n}; }
+
+__device__ __forceinline__ double pp_sq(V p0, V p1) { return sqn(p1 - p0); }
+__device__ __forceinline__ double pl_sq(V p, V e0, V e1) { return sqn(crossv(e0 - p, e1 - p)) / sqn(e1 - e0); }
+__device__ __forceinline__ double ll_sq(V ea0, V ea1, V eb0, V eb1)
+{
+    const V n = crossv(ea1 - ea0, eb1 - eb0);
+    const double l = dotv(eb0 - ea0, n);
+    return l * l / sqn(n);
+}
+__device__ __forceinline__ double ppl_sq(V p, V t0, V t1, V t2)
+{
+    const V n = crossv(t1 - t0, t2 - t0);
+    const double l = dotv(p - t0, n);
+    return l * l / sqn(n);
+}
+
+// sympy-unrolled edge parametrisation (:204-247)
+__device__ void edge_param(V p, V e0, V e1, V n, double& p0, double& p1)
+{
+    const double x0 = e0.x * e0.x, x1 = e0.y * e0.y, x2 = e0.z * e0.z;
+    const double x3 = e1.x * e1.x, x4 = e1.y * e1.y, x5 = e1.z * e1.z;
+    const double x6 = 2 * e0.x, x7 = e1.x * x6, x8 = 2 * e0.y, x9 = e1.y * x8, x10 = 2 * e1.z, x11 = e0.z * x10;
+    const double x12 = -e0.x + e1.x, x13 = -e0.x + p.x, x14 = -e0.y + e1.y, x15 = -e0.y + p.y, x16 = -e0.z + e1.z, x17 = -e0.z + p.z;
+    const double x18 = n.x * x6, x19 = n.y * x18, x20 = e0.z * n.z, x21 = e1.z * n.z, x22 = n.y * x8, x23 = e1.x * n.x, x24 = 2 * x23;
+    const double x25 = e1.y * n.y, x26 = n.z * x10, x27 = n.y * n.y, x28 = n.z * n.z, x29 = n.x * n.x;
+    p0 = (x12 * x13 + x14 * x15 + x16 * x17) / (x0 + x1 - x11 + x2 + x3 + x4 + x5 - x7 - x9);
+    p1 = (x13 * (-n.y * x16 + n.z * x14) + x15 * (n.x * x16 - n.z * x12) + x17 * (-n.x * x14 + n.y * x12))
+       / (-e0.y * x19 + e1.y * x19 + x0 * x27 + x0 * x28 + x1 * x28 + x1 * x29 - x11 * x27 - x11 * x29 - x18 * x20 + x18 * x21 + x2 * x27 + x2 * x29
+          - x20 * x22 + x20 * x24 + 2 * x20 * x25 + x21 * x22 + x22 * x23 - x23 * x26 - x24 * x25 - x25 * x26 + x27 * x3 + x27 * x5 - x27 * x7 + x28 * x3
+          + x28 * x4 - x28 * x7 - x28 * x9 + x29 * x4 + x29 * x5 - x29 * x9);
+}
+enum PT { P_T0, P_T1, P_T2, P_E0, P_E1, P_E2, P_T };
+__device__ int pt_type(V p, V t0, V t1, V t2)
+{
+    const V n = crossv(t1 - t0, t2 - t0);
+    double a0, a1, b0, b1, c0, c1;
+    edge_param(p, t0, t1, n, a0, a1);
+    if (a0 > 0.0 && a0 < 1.0 && a1 >= 0.0) return P_E0;
+    edge_param(p, t1, t2, n, b0, b1);
+    if (b0 > 0.0 && b0 < 1.0 && b1 >= 0.0) return P_E1;
+    edge_param(p, t2, t0, n, c0, c1);
+    if (c0 > 0.0 && c0 < 1.0 && c1 >= 0.0) return P_E2;
+    if (a0 <= 0.0 && c0 >= 1.0) return P_T0;
+    if (b0 <= 0.0 && a0 >= 1.0) return P_T1;
+    if (c0 <= 0.0 && b0 >= 1.0) return P_T2;
+    return P_T;
+}
+enum EE { EA0_EB0, EA0_EB1, EA1_EB0, EA1_EB1, EA_EB0, EA_EB1, EA0_EB, EA1_EB, EA_EB };
+__device__ int ee_parallel_type(V ea0, V ea1, V eb0, V eb1)
+{
+    const V ea = ea1 - ea0;
+    const double alpha = dotv(eb0 - ea0, ea) / sqn(ea);
+    const double beta = dotv(eb1 - ea0, ea) / sqn(ea);
+    int eac, ebc;
+    if (alpha < 0) { eac = (0 <= beta && beta <= 1) ? 2 : 0; ebc = (beta <= alpha) ? 0 : (beta <= 1 ? 1 : 2); }
+    else if (alpha > 1) { eac = (0 <= beta && beta <= 1) ? 2 : 1; ebc = (beta >= alpha) ? 0 : (0 <= beta ? 1 : 2); }
+    else { eac = 2; ebc = 0; }
+    return ebc < 2 ? (eac << 1 | ebc) : (6 + eac);
+}
+__device__ int ee_type(V ea0, V ea1, V eb0, V eb1, double tol)
+{
+    const V u = ea1 - ea0, v = eb1 - eb0, w = ea0 - eb0;
+    const double a = sqn(u), b = dotv(u, v), c = sqn(v), dd = dotv(u, w), e = dotv(v, w);
+    const double D = a * c - b * b;
+    if (a == 0.0 && c == 0.0) return EA0_EB0;
+    else if (a == 0.0) return EA0_EB;
+    else if (c == 0.0) return EA_EB0;
+    if (sqn(crossv(u, v)) < tol) return ee_parallel_type(ea0, ea1, eb0, eb1);
+    int def = EA_EB;
+    const double sN = (b * e - c * dd);
+    double tN, tD;
+    if (sN <= 0.0) { tN = e; tD = c; def = EA0_EB; }
+    else if (sN >= D) { tN = e + b; tD = c; def = EA1_EB; }
+    else {
+        tN = (a * e - b * dd); tD = D;
+        if (tN > 0.0 && tN < tD && sqn(crossv(u, v)) < tol) {
+            if (sN < D / 2) { tN = e; tD = c; def = EA0_EB; }
+            else { tN = e + b; tD = c; def = EA1_EB; }
+        }
+    }
+    if (tN <= 0.0) {
+        if (-dd <= 0.0) return EA0_EB0;
+        else if (-dd >= a) return EA1_EB0;
+        else return EA_EB0;
+    } else if (tN >= tD) {
+        if ((-dd + b) <= 0.0) return EA0_EB1;
+        else if ((-dd + b) >= a) return EA1_EB1;
+        else return EA_EB1;
+    }
+    return def;
+}
+// :565-585
+__device__ bool edge_hits_triangle(V Q1, V Q2, V A, V B, V C)
+{
+    const V E1 = B - A, E2 = C - A;
+    const V N = crossv(E1, E2);
+    const V Dir = Q2 - Q1;
+    const double det = -dotv(Dir, N);
+    const double invdet = 1.0 / det;
+    const V AO = Q1 - A;
+    const V DAO = crossv(AO, Dir);
+    const double u = dotv(E2, DAO) * invdet;
+    const double v = -dotv(E1, DAO) * invdet;
+    const double t = dotv(AO, N) * invdet;
+    return (fabs(det) >= 1e-14 && t >= 0.0 && t <= 1.0 && u >= 0.0 && v >= 0.0 && (u + v) <= 1.0);
+}
+
+// ---- friction geometry (S/models/interactions/friction_geometry.cpp) ----
+__device__ void proj_point_point(V p, V a, double* T)
+{
+    const V n = normalizedv(p - a);
+    const V e = (n.z < 0.99) ? V{0, 0, 1} : V{1, 0, 0};
+    const V u = normalizedv(crossv(e, n));
+    const V v = normalizedv(crossv(u, n));
+    T[0] = u.x; T[1] = u.y; T[2] = u.z; T[3] = v.x; T[4] = v.y; T[5] = v.z;
+}
+__device__ void proj_point_edge(V p, V a, V b, double* T)
+{
+    const V u = normalizedv(b - a);
+    const V v = normalizedv(crossv(u, p - a));
+    T[0] = u.x; T[1] = u.y; T[2] = u.z; T[3] = v.x; T[4] = v.y; T[5] = v.z;
+}
+__device__ void proj_triangle(V a, V b, V c, double* T)
+{
+    const V v01 = a - c, v02 = b - c;
+    const V u = normalizedv(v01);
+    const V v = normalizedv(crossv(crossv(v01, v02), u));
+    T[0] = u.x; T[1] = u.y; T[2] = u.z; T[3] = v.x; T[4] = v.y; T[5] = v.z;
+}
+__device__ void proj_edge_edge(V a, V b, V p, V q, double* T)
+{
+    const V u = normalizedv(b - a);
+    const V n = crossv(u, q - p);
+    const V v = normalizedv(crossv(u, n));
+    T[0] = u.x; T[1] = u.y; T[2] = u.z; T[3] = v.x; T[4] = v.y; T[5] = v.z;
+}
+__device__ void bary_point_edge(V p, V a, V b, double* o)
+{
+    const V ab = b - a;
+    const double alpha = dotv(p - a, ab) / sqn(ab);
+    o[0] = 1.0 - alpha; o[1] = alpha;
+}
+__device__ void bary_point_triangle(V p, V a, V b, V c, double* o)
+{
+    const V v0 = b - a, v1 = c - a, v2 = p - a;
+    const double d00 = dotv(v0, v0), d01 = dotv(v0, v1), d11 = dotv(v1, v1), d20 = dotv(v2, v0), d21 = dotv(v2, v1);
+    const double inv = 1.0 / (d00 * d11 - d01 * d01);
+    const double v = (d11 * d20 - d01 * d21) * inv, w = (d00 * d21 - d01 * d20) * inv;
+    o[0] = 1.0 - v - w; o[1] = v; o[2] = w;
+}
+__device__ void bary_edge_edge(V A, V B, V P, V Q, double* o)
+{
+    const V da = B - A, db = Q - P, r = A - P;
+    const double a = dotv(da, da), e = dotv(db, db), f = dotv(db, r), b = dotv(da, db), c = dotv(da, r);
+    const double denom = a * e - b * b;
+    if (denom < 1e-16) { o[0] = 0.5; o[1] = 0.5; return; }
+    const double s = (b * f - c * e) / denom;
+    o[0] = s; o[1] = (b * s + f) / e;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// list / table writers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int push_row(const Dev& d, int table, const int* row)
+{
+    const int slot = atomicAdd(d.counters + 16 + table, 1);
+    if (slot >= d.table_cap) { d.counters[3] = 1; return -1; }
+    int32_t* dst = d.table[table] + (size_t)slot * d.table_stride[table];
+    for (int k = 0; k < d.table_stride[table]; k++) dst[k] = row[k];
+    return slot;
+}
+__device__ __forceinline__ void push_list(const Dev& d, int list, int width, const int* ids, double dist)
+{
+    const int slot = atomicAdd(d.counters + 8 + list, 1);
+    if (slot >= d.list_cap) { d.counters[3] = 1; return; }
+    for (int k = 0; k < width; k++) d.list_ids[list][(size_t)slot * width + k] = ids[k];
+    d.list_dist[list][slot] = dist;
+}
+// friction rows carry their own index in column 0 (LabelledConnectivity::numbered_push_back)
+__device__ __forceinline__ int push_friction(const Dev& d, int table, int* row, const double* T, const double* bary, int nbary, double mu, double fn)
+{
+    const int slot = atomicAdd(d.counters + 16 + table, 1);
+    if (slot >= d.table_cap) { d.counters[3] = 1; return -1; }
+    row[0] = slot;
+    int32_t* dst = d.table[table] + (size_t)slot * d.table_stride[table];
+    for (int k = 0; k < d.table_stride[table]; k++) dst[k] = row[k];
+    const int f = table - N_CONTACT_TABLES;
+    for (int k = 0; k < 6; k++) d.fT[f][6 * (size_t)slot + k] = T[k];
+    for (int k = 0; k < nbary; k++) d.fbary[f][(size_t)nbary * slot + k] = bary[k];
+    d.fmu[f][slot] = mu;
+    d.ffn[f][slot] = fn;
+    return slot;
+}
+
+struct Side { int group, ps, body; };
+__device__ __forceinline__ Side side_of(const Dev& d, int g) { return {g, d.g_ps[g], d.g_body[g]}; }
+
+// One point (A) - primitive of a triangle (B) proximity pair.  nB = number of B vertices (1 point, 2 edge, 3 triangle).
+// mode 0: contact tables (EnergyFrictionalContact.cpp:381-455), mode 1: friction tables (:600-690)
+__device__ void emit_pt(const Dev& d, int mode, double dist, double stiffness, int nB, int pA, const int* vB, Side A, Side B)
+{
+    if (mode > 1) return;   // raw lists only
+    const double dhat = d.g_thickness[A.group] + d.g_thickness[B.group];
+    if (dist > dhat) return;
+    const int a = d.v_ps_index[pA];
+    int b[3];
+    for (int k = 0; k < nB; k++) b[k] = d.v_ps_index[vB[k]];
+    const bool A_soft = (A.ps == 0), B_soft = (B.ps == 0);
+    if (!A_soft && !B_soft) return;   // rigid-rigid pairs: potentials not built yet (rb_rb tables)
+    if (mode == 0) {
+        int row[8];
+        if (A_soft && B_soft) {
+            row[0] = A.group; row[1] = B.group; row[2] = a;
+            for (int k = 0; k < nB; k++) row[3 + k] = b[k];
+            push_row(d, nB == 1 ? CT_DD_PT_PP : (nB == 2 ? CT_DD_PT_PE : CT_DD_PT_PT), row);
+        } else if (!A_soft) {   // rigid point vs deformable primitive
+            row[0] = A.group; row[1] = B.group; row[2] = A.body; row[3] = a;
+            for (int k = 0; k < nB; k++) row[4 + k] = b[k];
+            push_row(d, nB == 1 ? CT_RD_PT_PP : (nB == 2 ? CT_RD_PT_PE : CT_RD_PT_PT), row);
+        } else {                // deformable point vs rigid primitive
+            row[0] = B.group; row[1] = A.group; row[2] = B.body;
+            for (int k = 0; k < nB; k++) row[3 + k] = b[k];
+            row[3 + nB] = a;
+            push_row(d, nB == 1 ? CT_RD_PT_PP : (nB == 2 ? CT_RD_PT_EP : CT_RD_PT_TP), row);
+        }
+    } else {
+        const double mu = d.mu[A.group * MAX_GROUPS + B.group];
+        if (mu == 0.0) return;
+        const double fn = stiffness * (dhat - dist) * (dhat - dist);   // _barrier_force, cubic (:1239-1243)
+        const V P = ld(d.x + 3 * pA);
+        double T[6], bary[3];
+        int row[8];
+        if (nB == 1) {
+            proj_point_point(P, ld(d.x + 3 * vB[0]), T);
+            if (A_soft && B_soft) { row[1] = a; row[2] = b[0]; push_friction(d, FT_DD_PP, row, T, bary, 0, mu, fn); }
+            else if (!A_soft) { row[1] = A.body; row[2] = a; row[3] = b[0]; push_friction(d, FT_RD_PP, row, T, bary, 0, mu, fn); }
+            else { row[1] = B.body; row[2] = b[0]; row[3] = a; push_friction(d, FT_RD_PP, row, T, bary, 0, mu, fn); }
+        } else if (nB == 2) {
+            const V E0 = ld(d.x + 3 * vB[0]), E1 = ld(d.x + 3 * vB[1]);
+            bary_point_edge(P, E0, E1, bary);
+            proj_point_edge(P, E0, E1, T);
+            if (A_soft && B_soft) { row[1] = a; row[2] = b[0]; row[3] = b[1]; push_friction(d, FT_DD_PE, row, T, bary, 2, mu, fn); }
+            else if (!A_soft) { row[1] = A.body; row[2] = a; row[3] = b[0]; row[4] = b[1]; push_friction(d, FT_RD_PE, row, T, bary, 2, mu, fn); }
+            else { row[1] = B.body; row[2] = b[0]; row[3] = b[1]; row[4] = a; push_friction(d, FT_RD_EP, row, T, bary, 2, mu, fn); }
+        } else {
+            const V T0 = ld(d.x + 3 * vB[0]), T1 = ld(d.x + 3 * vB[1]), T2 = ld(d.x + 3 * vB[2]);
+            bary_point_triangle(P, T0, T1, T2, bary);
+            proj_triangle(T0, T1, T2, T);
+            if (A_soft && B_soft) { row[1] = a; row[2] = b[0]; row[3] = b[1]; row[4] = b[2]; push_friction(d, FT_DD_PT, row, T, bary, 3, mu, fn); }
+            else if (!A_soft) { row[1] = A.body; row[2] = a; row[3] = b[0]; row[4] = b[1]; row[5] = b[2]; push_friction(d, FT_RD_PT, row, T, bary, 3, mu, fn); }
+            else { row[1] = B.body; row[2] = b[0]; row[3] = b[1]; row[4] = b[2]; row[5] = a; push_friction(d, FT_RD_TP, row, T, bary, 3, mu, fn); }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_narrow_pt(Dev d, double enl_sq, int mode, double stiffness)
+{
+    const int total = min(d.counters[0], d.cand_cap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int p = d.cand_pt[i].x, t = d.cand_pt[i].y;
+        const int v0 = d.tri[3 * t], v1 = d.tri[3 * t + 1], v2 = d.tri[3 * t + 2];
+        const V P = ld(d.x + 3 * p), A = ld(d.x + 3 * v0), B = ld(d.x + 3 * v1), C = ld(d.x + 3 * v2);
+        const int type = pt_type(P, A, B, C);
+        double d2;
+        switch (type) {
+        case P_T0: d2 = pp_sq(P, A); break;
+        case P_T1: d2 = pp_sq(P, B); break;
+        case P_T2: d2 = pp_sq(P, C); break;
+        case P_E0: d2 = pl_sq(P, A, B); break;
+        case P_E1: d2 = pl_sq(P, B, C); break;
+        case P_E2: d2 = pl_sq(P, C, A); break;
+        default: d2 = ppl_sq(P, A, B, C); break;
+        }
+        if (!(d2 < enl_sq)) continue;
+        const double dist = sqrt(d2);
+        const int gp = d.v_group[p], gt = d.t_group[t];
+        const int lp = p - d.g_voff[gp], lt = t - d.g_toff[gt], tvo = d.g_voff[gt];
+        const Side SA = side_of(d, gp), SB = side_of(d, gt);
+        int ids[6], vB[3];
+        if (type <= P_T2) {
+            vB[0] = (type == P_T0) ? v0 : (type == P_T1 ? v1 : v2);
+            ids[0] = gp; ids[1] = lp; ids[2] = gt; ids[3] = lt; ids[4] = vB[0] - tvo;
+            push_list(d, 0, 5, ids, dist);
+            emit_pt(d, mode, dist, stiffness, 1, p, vB, SA, SB);
+        } else if (type <= P_E2) {
+            vB[0] = (type == P_E0) ? v0 : (type == P_E1 ? v1 : v2);
+            vB[1] = (type == P_E0) ? v1 : (type == P_E1 ? v2 : v0);
+            ids[0] = gp; ids[1] = lp; ids[2] = gt; ids[3] = lt; ids[4] = vB[0] - tvo; ids[5] = vB[1] - tvo;
+            push_list(d, 1, 6, ids, dist);
+            emit_pt(d, mode, dist, stiffness, 2, p, vB, SA, SB);
+        } else {
+            vB[0] = v0; vB[1] = v1; vB[2] = v2;
+            ids[0] = gp; ids[1] = lp; ids[2] = gt; ids[3] = lt;
+            push_list(d, 2, 4, ids, dist);
+            emit_pt(d, mode, dist, stiffness, 3, p, vB, SA, SB);
+        }
+    }
+}
+
+// Edge-edge derived pairs.  kind 0: point(A edge-point) - point(B edge-point); 1: edge-point(A) - edge(B); 2: edge(A) - edge(B)
+// (EnergyFrictionalContact.cpp:457-529 contact, :692-772 friction).  eA / eB: the full edges (for the mollifier tables).
+__device__ void emit_ee(const Dev& d, int mode, double dist, double stiffness, int kind, const int* eA, int pA, const int* eB, int pB, Side A, Side B)
+{
+    if (mode > 1) return;   // raw lists only
+    const double dhat = d.g_thickness[A.group] + d.g_thickness[B.group];
+    if (dist > dhat) return;
+    const bool A_soft = (A.ps == 0), B_soft = (B.ps == 0);
+    if (!A_soft && !B_soft) return;
+    const int a0 = d.v_ps_index[eA[0]], a1 = d.v_ps_index[eA[1]], b0 = d.v_ps_index[eB[0]], b1 = d.v_ps_index[eB[1]];
+    const int ap = (pA >= 0) ? d.v_ps_index[pA] : -1, bp = (pB >= 0) ? d.v_ps_index[pB] : -1;
+    if (mode == 0) {
+        int row[10];
+        if (kind == 0) {
+            if (A_soft && B_soft) { const int r[8] = {A.group, B.group, a0, a1, ap, b0, b1, bp}; push_row(d, CT_DD_EE_PP, r); }
+            else if (!A_soft) { const int r[9] = {A.group, B.group, A.body, a0, a1, ap, b0, b1, bp}; push_row(d, CT_RD_EE_PP, r); }
+            else { const int r[9] = {B.group, A.group, B.body, b0, b1, bp, a0, a1, ap}; push_row(d, CT_RD_EE_PP, r); }
+        } else if (kind == 1) {
+            if (A_soft && B_soft) { const int r[7] = {A.group, B.group, a0, a1, ap, b0, b1}; push_row(d, CT_DD_EE_PE, r); }
+            else if (!A_soft) { const int r[8] = {A.group, B.group, A.body, a0, a1, ap, b0, b1}; push_row(d, CT_RD_EE_PE, r); }
+            else { const int r[8] = {B.group, A.group, B.body, b0, b1, a0, a1, ap}; push_row(d, CT_RD_EE_EP, r); }
+        } else {
+            if (A_soft && B_soft) { const int r[6] = {A.group, B.group, a0, a1, b0, b1}; push_row(d, CT_DD_EE_EE, r); }
+            else if (!A_soft) { const int r[7] = {A.group, B.group, A.body, a0, a1, b0, b1}; push_row(d, CT_RD_EE_EE, r); }
+            else { const int r[7] = {B.group, A.group, B.body, b0, b1, a0, a1}; push_row(d, CT_RD_EE_EE, r); }
+        }
+        (void)row;
+    } else {
+        const double mu = d.mu[A.group * MAX_GROUPS + B.group];
+        if (mu == 0.0) return;
+        const double fn = stiffness * (dhat - dist) * (dhat - dist);
+        double T[6], bary[3];
+        int row[8];
+        if (kind == 0) {
+            proj_point_point(ld(d.x + 3 * pA), ld(d.x + 3 * pB), T);
+            if (A_soft && B_soft) { row[1] = ap; row[2] = bp; push_friction(d, FT_DD_PP, row, T, bary, 0, mu, fn); }
+            else if (!A_soft) { row[1] = A.body; row[2] = ap; row[3] = bp; push_friction(d, FT_RD_PP, row, T, bary, 0, mu, fn); }
+            else { row[1] = B.body; row[2] = bp; row[3] = ap; push_friction(d, FT_RD_PP, row, T, bary, 0, mu, fn); }
+        } else if (kind == 1) {
+            const V P = ld(d.x + 3 * pA), E0 = ld(d.x + 3 * eB[0]), E1 = ld(d.x + 3 * eB[1]);
+            bary_point_edge(P, E0, E1, bary);
+            proj_point_edge(P, E0, E1, T);
+            if (A_soft && B_soft) { row[1] = ap; row[2] = b0; row[3] = b1; push_friction(d, FT_DD_PE, row, T, bary, 2, mu, fn); }
+            else if (!A_soft) { row[1] = A.body; row[2] = ap; row[3] = b0; row[4] = b1; push_friction(d, FT_RD_PE, row, T, bary, 2, mu, fn); }
+            else { row[1] = B.body; row[2] = b0; row[3] = b1; row[4] = ap; push_friction(d, FT_RD_EP, row, T, bary, 2, mu, fn); }
+        } else {
+            const V EA0 = ld(d.x + 3 * eA[0]), EA1 = ld(d.x + 3 * eA[1]), EB0 = ld(d.x + 3 * eB[0]), EB1 = ld(d.x + 3 * eB[1]);
+            bary_edge_edge(EA0, EA1, EB0, EB1, bary);     // in detection order, like the reference (even when the table swaps A and B)
+            proj_edge_edge(EA0, EA1, EB0, EB1, T);
+            if (A_soft && B_soft) { row[1] = a0; row[2] = a1; row[3] = b0; row[4] = b1; push_friction(d, FT_DD_EE, row, T, bary, 2, mu, fn); }
+            else if (!A_soft) { row[1] = A.body; row[2] = a0; row[3] = a1; row[4] = b0; row[5] = b1; push_friction(d, FT_RD_EE, row, T, bary, 2, mu, fn); }
+            else { row[1] = B.body; row[2] = b0; row[3] = b1; row[4] = a0; row[5] = a1; push_friction(d, FT_RD_EE, row, T, bary, 2, mu, fn); }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_narrow_ee(Dev d, double enl_sq, int mode, double stiffness, double parallel_tol)
+{
+    const int total = min(d.counters[1], d.cand_cap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int ea = d.cand_ee[i].x, eb = d.cand_ee[i].y;
+        const int eA[2] = {d.edge[2 * ea], d.edge[2 * ea + 1]}, eB[2] = {d.edge[2 * eb], d.edge[2 * eb + 1]};
+        const V a = ld(d.x + 3 * eA[0]), b = ld(d.x + 3 * eA[1]), p = ld(d.x + 3 * eB[0]), q = ld(d.x + 3 * eB[1]);
+        const int type = ee_type(a, b, p, q, parallel_tol);
+        double d2;
+        switch (type) {
+        case EA0_EB0: d2 = pp_sq(a, p); break;
+        case EA0_EB1: d2 = pp_sq(a, q); break;
+        case EA1_EB0: d2 = pp_sq(b, p); break;
+        case EA1_EB1: d2 = pp_sq(b, q); break;
+        case EA_EB0: d2 = pl_sq(p, a, b); break;
+        case EA_EB1: d2 = pl_sq(q, a, b); break;
+        case EA0_EB: d2 = pl_sq(a, p, q); break;
+        case EA1_EB: d2 = pl_sq(b, p, q); break;
+        default: d2 = ll_sq(a, b, p, q); break;
+        }
+        if (!(d2 < enl_sq)) continue;
+        if (sqn(crossv(b - a, q - p)) <= parallel_tol) continue;
+        const double dist = sqrt(d2);
+        const int ga = d.e_group[ea], gb = d.e_group[eb];
+        const int la = ea - d.g_eoff[ga], lb = eb - d.g_eoff[gb], vao = d.g_voff[ga], vbo = d.g_voff[gb];
+        const Side SA = side_of(d, ga), SB = side_of(d, gb);
+        int ids[6];
+        if (type <= EA1_EB1) {
+            const int pa = (type == EA0_EB0 || type == EA0_EB1) ? eA[0] : eA[1];
+            const int pb = (type == EA0_EB0 || type == EA1_EB0) ? eB[0] : eB[1];
+            ids[0] = ga; ids[1] = la; ids[2] = pa - vao; ids[3] = gb; ids[4] = lb; ids[5] = pb - vbo;
+            push_list(d, 3, 6, ids, dist);
+            emit_ee(d, mode, dist, stiffness, 0, eA, pa, eB, pb, SA, SB);
+        } else if (type == EA_EB0 || type == EA_EB1) {   // point of B vs edge A: the edge-point is on B
+            const int pb = (type == EA_EB0) ? eB[0] : eB[1];
+            ids[0] = gb; ids[1] = lb; ids[2] = pb - vbo; ids[3] = ga; ids[4] = la;
+            push_list(d, 4, 5, ids, dist);
+            emit_ee(d, mode, dist, stiffness, 1, eB, pb, eA, -1, SB, SA);
+        } else if (type == EA0_EB || type == EA1_EB) {
+            const int pa = (type == EA0_EB) ? eA[0] : eA[1];
+            ids[0] = ga; ids[1] = la; ids[2] = pa - vao; ids[3] = gb; ids[4] = lb;
+            push_list(d, 4, 5, ids, dist);
+            emit_ee(d, mode, dist, stiffness, 1, eA, pa, eB, -1, SA, SB);
+        } else {
+            ids[0] = ga; ids[1] = la; ids[2] = gb; ids[3] = lb;
+            push_list(d, 5, 4, ids, dist);
+            emit_ee(d, mode, dist, stiffness, 2, eA, -1, eB, -1, SA, SB);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_narrow_et(Dev d)
+{
+    const int total = min(d.counters[2], d.cand_cap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int e = d.cand_et[i].x, t = d.cand_et[i].y;
+        const V e0 = ld(d.x + 3 * d.edge[2 * e]), e1 = ld(d.x + 3 * d.edge[2 * e + 1]);
+        const V t0 = ld(d.x + 3 * d.tri[3 * t]), t1 = ld(d.x + 3 * d.tri[3 * t + 1]), t2 = ld(d.x + 3 * d.tri[3 * t + 2]);
+        if (edge_hits_triangle(e0, e1, t0, t1, t2)) {
+            const int ge = d.e_group[e], gt = d.t_group[t];
+            const int ids[4] = {ge, e - d.g_eoff[ge], gt, t - d.g_toff[gt]};
+            push_list(d, 6, 4, ids, 0.0);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+void contact_destroy(sb_context* ctx)
+{
+    Contact* C = ctx->contact;
+    if (!C) return;
+    C->x.release(); C->v_group.release(); C->v_ps.release(); C->tri.release(); C->t_group.release(); C->edge.release(); C->e_group.release();
+    C->g_i32.release(); C->g_f64.release(); C->mu.release(); C->blacklist.release(); C->bb_p.release(); C->bb_t.release(); C->bb_e.release();
+    C->cand_pt.release(); C->cand_ee.release(); C->cand_et.release(); C->counters.release();
+    for (int l = 0; l < N_LISTS; l++) { C->list_ids[l].release(); C->list_dist[l].release(); }
+    for (int t = 0; t < N_TABLES; t++) C->table[t].release();
+    if (C->h_counters) cudaFreeHost(C->h_counters);
+    delete C;
+    ctx->contact = nullptr;
+}
+bool contact_active(sb_context* ctx) { return ctx->contact && !ctx->contact->groups.empty(); }
+
+static int new_array(sb_context* ctx, const char* label, int stride)
+{
+    Array a;
+    a.label = label;
+    a.stride = stride;
+    ctx->arrays.push_back(a);
+    return (int)ctx->arrays.size() - 1;
+}
+
+static int upload_topology(sb_context* ctx, Contact* C)
+{
+    cudaStream_t st = ctx->stream;
+    const int nv = (int)C->h_v_group.size(), nt = (int)C->h_t_group.size(), ne = (int)C->h_e_group.size();
+    auto up = [&](auto& buf, const auto& h) {
+        buf.ensure(h.size() + 1);
+        if (!h.empty()) cudaMemcpyAsync(buf.p, h.data(), h.size() * sizeof(h[0]), cudaMemcpyHostToDevice, st);
+    };
+    up(C->v_group, C->h_v_group); up(C->v_ps, C->h_v_ps); up(C->tri, C->h_tri); up(C->t_group, C->h_t_group); up(C->edge, C->h_edge); up(C->e_group, C->h_e_group);
+    up(C->blacklist, C->h_blacklist); up(C->mu, C->h_mu);
+    const int G = (int)C->groups.size();
+    std::vector<int32_t> gi(5 * MAX_GROUPS, 0);
+    std::vector<double> gf(MAX_GROUPS, 0.0);
+    for (int g = 0; g < G; g++) {
+        gi[g] = C->groups[g].ps; gi[MAX_GROUPS + g] = C->groups[g].body; gi[2 * MAX_GROUPS + g] = C->groups[g].v_off;
+        gi[3 * MAX_GROUPS + g] = C->groups[g].t_off; gi[4 * MAX_GROUPS + g] = C->groups[g].e_off;
+        gf[g] = C->groups[g].thickness;
+    }
+    up(C->g_i32, gi); up(C->g_f64, gf);
+    C->x.ensure(3 * (size_t)nv + 3);
+    C->bb_p.ensure(6 * (size_t)nv + 6); C->bb_t.ensure(6 * (size_t)nt + 6); C->bb_e.ensure(6 * (size_t)ne + 6);
+    SB_CUDA(ctx, cudaStreamSynchronize(st));
+    // module-owned arrays seen by the potentials
+    Array& th = ctx->arrays[C->a_thickness];
+    th.d.ensure(MAX_GROUPS); th.n_rows = G;
+    SB_CUDA(ctx, cudaMemcpy(th.d.p, gf.data(), G * sizeof(double), cudaMemcpyHostToDevice));
+    Array& rl = ctx->arrays[C->a_rb_local];
+    rl.d.ensure(C->h_rb_local.size() + 3); rl.n_rows = (int)C->h_rb_local.size() / 3;
+    if (!C->h_rb_local.empty()) SB_CUDA(ctx, cudaMemcpy(rl.d.p, C->h_rb_local.data(), C->h_rb_local.size() * sizeof(double), cudaMemcpyHostToDevice));
+    C->topology_dirty = false;
+    return 0;
+}
+
+static void ensure_capacities(sb_context* ctx, Contact* C)
+{
+    C->cand_pt.ensure(C->cand_cap); C->cand_ee.ensure(C->cand_cap); C->cand_et.ensure(C->cand_cap);
+    C->counters.ensure(64);
+    for (int l = 0; l < N_LISTS; l++) { C->list_ids[l].ensure((size_t)C->list_cap * LIST_WIDTH[l]); C->list_dist[l].ensure(C->list_cap); }
+    for (int t = 0; t < N_TABLES; t++) C->table[t].ensure((size_t)C->table_cap * LAYOUTS[t].conn_stride);
+    for (int f = 0; f < N_FRICTION; f++) {
+        ctx->arrays[C->a_fT[f]].d.ensure(6 * (size_t)C->table_cap);
+        ctx->arrays[C->a_fmu[f]].d.ensure(C->table_cap);
+        ctx->arrays[C->a_ffn[f]].d.ensure(C->table_cap);
+        if (C->a_fbary[f] >= 0) ctx->arrays[C->a_fbary[f]].d.ensure((size_t)ctx->arrays[C->a_fbary[f]].stride * C->table_cap);
+    }
+}
+
+static Dev make_dev(sb_context* ctx, Contact* C)
+{
+    Dev d;
+    d.n_v = (int)C->h_v_group.size(); d.n_t = (int)C->h_t_group.size(); d.n_e = (int)C->h_e_group.size(); d.n_groups = (int)C->groups.size();
+    d.x = C->x.p; d.v_group = C->v_group.p; d.v_ps_index = C->v_ps.p; d.tri = C->tri.p; d.t_group = C->t_group.p; d.edge = C->edge.p; d.e_group = C->e_group.p;
+    d.bb_p = C->bb_p.p; d.bb_t = C->bb_t.p; d.bb_e = C->bb_e.p;
+    d.g_ps = C->g_i32.p; d.g_body = C->g_i32.p + MAX_GROUPS; d.g_voff = C->g_i32.p + 2 * MAX_GROUPS; d.g_toff = C->g_i32.p + 3 * MAX_GROUPS; d.g_eoff = C->g_i32.p + 4 * MAX_GROUPS;
+    d.g_thickness = C->g_f64.p; d.blacklist = C->blacklist.p; d.mu = C->mu.p;
+    d.cand_pt = C->cand_pt.p; d.cand_ee = C->cand_ee.p; d.cand_et = C->cand_et.p; d.cand_cap = C->cand_cap;
+    d.counters = C->counters.p;
+    for (int l = 0; l < N_LISTS; l++) { d.list_ids[l] = C->list_ids[l].p; d.list_dist[l] = C->list_dist[l].p; }
+    d.list_cap = C->list_cap;
+    for (int t = 0; t < N_TABLES; t++) { d.table[t] = C->table[t].p; d.table_stride[t] = LAYOUTS[t].conn_stride; }
+    d.table_cap = C->table_cap;
+    for (int f = 0; f < N_FRICTION; f++) {
+        d.fT[f] = ctx->arrays[C->a_fT[f]].d.p; d.fmu[f] = ctx->arrays[C->a_fmu[f]].d.p; d.ffn[f] = ctx->arrays[C->a_ffn[f]].d.p;
+        d.fbary[f] = (C->a_fbary[f] >= 0) ? ctx->arrays[C->a_fbary[f]].d.p : nullptr;
+    }
+    return d;
+}
+
+static int update_vertices(sb_context* ctx, Contact* C, bool zero_dt)
+{
+    if (C->external_vertices) return 0;
+    Dev d = make_dev(ctx, C);
+    const sb_contact_bindings& b = C->bind;
+    auto ptr = [&](int a) -> const double* { return (a >= 0) ? ctx->arrays[a].d.p : nullptr; };
+    k_update_vertices<<<(d.n_v + 255) / 256, 256, 0, ctx->stream>>>(d, ptr(b.soft_v1), ptr(b.soft_x0), ptr(b.rb_v1), ptr(b.rb_w1), ptr(b.rb_t0), ptr(b.rb_q0),
+                                                                      ctx->arrays[C->a_rb_local].d.p, ptr(b.dt), zero_dt ? 1 : 0);
+    ctx->launches++;
+    return 0;
+}
+
+// mode 0: proximity + contact tables; 1: proximity + friction tables; 2: intersections only; 3: proximity lists only + intersections
+static int detect(sb_context* ctx, Contact* C, int mode, double enlargement)
+{
+    cudaStream_t st = ctx->stream;
+    for (int attempt = 0; attempt < 8; attempt++) {
+        ensure_capacities(ctx, C);
+        Dev d = make_dev(ctx, C);
+        const int nmax = std::max(d.n_v, std::max(d.n_t, d.n_e));
+        // only the counters this mode rewrites are cleared (contact and friction tables live side by side)
+        SB_CUDA(ctx, cudaMemsetAsync(C->counters.p, 0, 4 * sizeof(int), st));
+        if (mode == 0 || mode == 3) { SB_CUDA(ctx, cudaMemsetAsync(C->counters.p + 8, 0, 6 * sizeof(int), st)); SB_CUDA(ctx, cudaMemsetAsync(C->counters.p + 16, 0, N_CONTACT_TABLES * sizeof(int), st)); }
+        if (mode == 1) { SB_CUDA(ctx, cudaMemsetAsync(C->counters.p + 8, 0, 6 * sizeof(int), st)); SB_CUDA(ctx, cudaMemsetAsync(C->counters.p + 16 + N_CONTACT_TABLES, 0, N_FRICTION * sizeof(int), st)); }
+        if (mode == 2 || mode == 3) SB_CUDA(ctx, cudaMemsetAsync(C->counters.p + 8 + 6, 0, sizeof(int), st));
+        const dim3 gpt((d.n_v + TILE - 1) / TILE, (d.n_t + TILE - 1) / TILE), gee((d.n_e + TILE - 1) / TILE, (d.n_e + TILE - 1) / TILE), get((d.n_e + TILE - 1) / TILE, (d.n_t + TILE - 1) / TILE);
+        if (mode != 2) {
+            const float extra = (float)enlargement + FLT_EPSILON;
+            k_aabbs<<<(nmax + 255) / 256, 256, 0, st>>>(d, extra, 1);
+            if (C->enable_pt && d.n_t > 0 && d.n_v > 0) k_broad<0><<<gpt, TILE, 0, st>>>(d);
+            if (C->enable_ee && d.n_e > 1) k_broad<1><<<gee, TILE, 0, st>>>(d);
+            const int emit_mode = (mode == 3) ? 2 : mode;   // 2 = lists only (no table matches mode 2 inside emit_*)
+            if (C->enable_pt) k_narrow_pt<<<148, 128, 0, st>>>(d, enlargement * enlargement, emit_mode, C->stiffness);
+            if (C->enable_ee) k_narrow_ee<<<148, 128, 0, st>>>(d, enlargement * enlargement, emit_mode, C->stiffness, 1e-30);
+            ctx->launches += 5;
+        }
+        if (mode == 2 || mode == 3) {
+            const float extra = 0.0f + FLT_EPSILON;   // IntersectionDetection uses non-enlarged AABBs (tmcd/BroadPhaseET.cpp:38)
+            k_aabbs<<<(nmax + 255) / 256, 256, 0, st>>>(d, extra, 0);
+            if (d.n_e > 0 && d.n_t > 0) k_broad<2><<<get, TILE, 0, st>>>(d);
+            k_narrow_et<<<148, 128, 0, st>>>(d);
+            ctx->launches += 3;
+        }
+        SB_CUDA(ctx, cudaMemcpyAsync(C->h_counters, C->counters.p, 64 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        SB_CUDA(ctx, cudaStreamSynchronize(st));
+        SB_CUDA(ctx, cudaGetLastError());
+        if (!C->h_counters[3]) break;
+        // overflow: grow whatever was too small and run again
+        const int mc = std::max(C->h_counters[0], std::max(C->h_counters[1], C->h_counters[2]));
+        if (mc > C->cand_cap) C->cand_cap = mc + mc / 2;
+        int ml = 0, mt = 0;
+        for (int l = 0; l < N_LISTS; l++) ml = std::max(ml, C->h_counters[8 + l]);
+        for (int t = 0; t < N_TABLES; t++) mt = std::max(mt, C->h_counters[16 + t]);
+        if (ml > C->list_cap) C->list_cap = ml + ml / 2;
+        if (mt > C->table_cap) C->table_cap = mt + mt / 2;
+        if (attempt == 7) return fail(ctx, SB_ERR_STATE, "contact detection: buffers keep overflowing");
+    }
+    for (int l = 0; l < N_LISTS; l++) C->h_list_count[l] = C->h_counters[8 + l];
+    // publish the table sizes to the potentials / friction arrays
+    const int t0 = (mode == 0) ? 0 : N_CONTACT_TABLES, t1 = (mode == 0) ? N_CONTACT_TABLES : N_TABLES;
+    if (mode == 0 || mode == 1) {
+        for (int t = t0; t < t1; t++) {
+            const int n = C->h_counters[16 + t];
+            C->h_table_count[t] = n;
+            Potential& p = ctx->potentials[C->pot[t]];
+            p.conn_ext = C->table[t].p;
+            p.n_elem = n;
+            if (t >= N_CONTACT_TABLES) {
+                const int f = t - N_CONTACT_TABLES;
+                ctx->arrays[C->a_fT[f]].n_rows = n; ctx->arrays[C->a_fmu[f]].n_rows = n; ctx->arrays[C->a_ffn[f]].n_rows = n;
+                if (C->a_fbary[f] >= 0) ctx->arrays[C->a_fbary[f]].n_rows = n;
+            }
+        }
+        ctx->pattern_version++;
+        ctx->have_pgh = false;
+    }
+    return 0;
+}
+
+static double max_thickness(Contact* C)
+{
+    double m = 0.0;
+    for (auto& g : C->groups) m = std::max(m, g.thickness);
+    return m;
+}
+static int refresh_params(sb_context* ctx, Contact* C)
+{
+    // contact stiffness / stick-slide threshold are tiny and may change between retries: re-upload every time
+    Array& ks = ctx->arrays[C->a_stiffness];
+    Array& ev = ctx->arrays[C->a_epsv];
+    ks.d.ensure(1); ks.n_rows = 1; ev.d.ensure(1); ev.n_rows = 1;
+    ctx->h_scalars[8] = C->stiffness; ctx->h_scalars[9] = C->epsv;
+    SB_CUDA(ctx, cudaMemcpyAsync(ks.d.p, ctx->h_scalars + 8, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    SB_CUDA(ctx, cudaMemcpyAsync(ev.d.p, ctx->h_scalars + 9, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+int contact_update_internal(sb_context* ctx)
+{
+    Contact* C = ctx->contact;
+    if (!C || C->groups.empty()) return 0;
+    int r;
+    if (C->topology_dirty && (r = upload_topology(ctx, C))) return r;
+    if ((r = refresh_params(ctx, C))) return r;
+    if ((r = update_vertices(ctx, C, false))) return r;
+    return detect(ctx, C, 0, 2.0 * max_thickness(C));
+}
+int contact_intersections_internal(sb_context* ctx, int* out_count)
+{
+    Contact* C = ctx->contact;
+    *out_count = 0;
+    if (!C || C->groups.empty()) return 0;
+    int r;
+    if (C->topology_dirty && (r = upload_topology(ctx, C))) return r;
+    if ((r = update_vertices(ctx, C, false))) return r;
+    if ((r = detect(ctx, C, 2, 0.0))) return r;
+    *out_count = C->h_list_count[6];
+    return 0;
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+extern "C" {
+
+int sb_contact_init(sb_context* ctx, const sb_contact_bindings* b)
+{
+    if (!ctx || !b) return fail(ctx, SB_ERR_ARG, "sb_contact_init: bad argument");
+    if (ctx->contact) return fail(ctx, SB_ERR_STATE, "sb_contact_init: already initialised");
+    const int ids[8] = {b->soft_v1, b->soft_x0, b->soft_X, b->rb_v1, b->rb_w1, b->rb_t0, b->rb_q0, b->dt};
+    for (int i = 0; i < 8; i++)
+        if (ids[i] < 0 || ids[i] >= (int)ctx->arrays.size()) return fail(ctx, SB_ERR_ARG, "sb_contact_init: unknown array handle in bindings");
+    Contact* C = new Contact();
+    C->bind = *b;
+    C->h_blacklist.assign(MAX_GROUPS * MAX_GROUPS, 0);
+    C->h_mu.assign(MAX_GROUPS * MAX_GROUPS, 0.0);
+    cudaMallocHost(&C->h_counters, 64 * sizeof(int));
+    C->a_thickness = new_array(ctx, "contact_thicknesses", 1);
+    C->a_stiffness = new_array(ctx, "contact_stiffness", 1);
+    C->a_rb_local = new_array(ctx, "rigidbody_local_vertices", 3);
+    C->a_epsv = new_array(ctx, "friction_stick_slide_threshold", 1);
+    ctx->contact = C;
+    // one potential per contact / friction table, bound exactly like the reference's lambdas bind their symbols
+    for (int t = 0; t < N_TABLES; t++) {
+        const Layout& L = LAYOUTS[t];
+        const int f = t - N_CONTACT_TABLES;
+        if (f >= 0) { C->a_fT[f] = C->a_fmu[f] = C->a_ffn[f] = C->a_fbary[f] = -1; }
+        std::vector<sb_fetch> fetch;
+        for (int k = 0; k < L.n; k++) {
+            const LayoutEntry& e = L.e[k];
+            int arr = -1;
+            switch (e.role) {
+            case R_SOFT_V1: arr = b->soft_v1; break;
+            case R_SOFT_X0: arr = b->soft_x0; break;
+            case R_SOFT_X: arr = b->soft_X; break;
+            case R_RB_V1: arr = b->rb_v1; break;
+            case R_RB_W1: arr = b->rb_w1; break;
+            case R_RB_T0: arr = b->rb_t0; break;
+            case R_RB_Q0: arr = b->rb_q0; break;
+            case R_DT: arr = b->dt; break;
+            case R_THICKNESS: arr = C->a_thickness; break;
+            case R_STIFFNESS: arr = C->a_stiffness; break;
+            case R_RB_LOCAL: arr = C->a_rb_local; break;
+            case R_EPSV: arr = C->a_epsv; break;
+            case R_F_T: arr = C->a_fT[f] = new_array(ctx, "friction_T", 6); break;
+            case R_F_BARY: arr = C->a_fbary[f] = new_array(ctx, "friction_bary", e.stride); break;
+            case R_F_MU: arr = C->a_fmu[f] = new_array(ctx, "friction_mu", 1); break;
+            case R_F_FN: arr = C->a_ffn[f] = new_array(ctx, "friction_fn", 1); break;
+            }
+            fetch.push_back({arr, e.col, e.slot, e.stride});
+        }
+        int pot = -1;
+        int r = sb_potential_create(ctx, L.name, L.conn_stride, fetch.data(), (int)fetch.size(), &pot);
+        if (r) return r;
+        C->pot[t] = pot;
+        ctx->potentials[pot].conn_ext = nullptr;
+    }
+    return SB_OK;
+}
+
+int sb_contact_add_mesh(sb_context* ctx, const sb_contact_mesh* m, int* out_group)
+{
+    if (!ctx || !m) return fail(ctx, SB_ERR_ARG, "sb_contact_add_mesh: bad argument");
+    Contact* C = ctx->contact;
+    if (!C) return fail(ctx, SB_ERR_STATE, "sb_contact_add_mesh: call sb_contact_init first");
+    if ((int)C->groups.size() >= MAX_GROUPS) return fail(ctx, SB_ERR_STATE, "sb_contact_add_mesh: too many contact groups");
+    if (m->n_vertices <= 0 || m->contact_thickness <= 0.0) return fail(ctx, SB_ERR_ARG, "sb_contact_add_mesh: contact thickness must be positive and the mesh non-empty");
+    Group g;
+    g.ps = m->physical_system; g.body = m->rigid_body; g.n_v = m->n_vertices; g.n_t = m->n_triangles; g.n_e = m->n_edges;
+    g.v_off = (int)C->h_v_group.size(); g.t_off = (int)C->h_t_group.size(); g.e_off = (int)C->h_e_group.size();
+    g.thickness = m->contact_thickness;
+    const int gi = (int)C->groups.size();
+    const int rb_off = (int)C->h_rb_local.size() / 3;
+    for (int i = 0; i < g.n_v; i++) {
+        C->h_v_group.push_back(gi);
+        if (g.ps == 0) {
+            if (!m->vertex_global) return fail(ctx, SB_ERR_ARG, "sb_contact_add_mesh: deformable mesh without vertex_global");
+            C->h_v_ps.push_back(m->vertex_global[i]);
+        } else {
+            if (!m->vertices_local) return fail(ctx, SB_ERR_ARG, "sb_contact_add_mesh: rigid mesh without vertices_local");
+            C->h_v_ps.push_back(rb_off + i);
+            for (int c = 0; c < 3; c++) C->h_rb_local.push_back(m->vertices_local[3 * i + c]);
+        }
+    }
+    for (int i = 0; i < g.n_t; i++) { for (int k = 0; k < 3; k++) C->h_tri.push_back(g.v_off + m->triangles[3 * i + k]); C->h_t_group.push_back(gi); }
+    for (int i = 0; i < g.n_e; i++) { for (int k = 0; k < 2; k++) C->h_edge.push_back(g.v_off + m->edges[2 * i + k]); C->h_e_group.push_back(gi); }
+    C->groups.push_back(g);
+    if (g.ps == 1) { C->h_blacklist[gi * MAX_GROUPS + gi] = 1; }   // rigid meshes never self-collide (EnergyFrictionalContact.cpp:209)
+    C->topology_dirty = true;
+    if (out_group) *out_group = gi;
+    return SB_OK;
+}
+
+int sb_contact_blacklist(sb_context* ctx, int a, int b)
+{
+    Contact* C = ctx ? ctx->contact : nullptr;
+    if (!C || a < 0 || b < 0 || a >= (int)C->groups.size() || b >= (int)C->groups.size()) return fail(ctx, SB_ERR_ARG, "sb_contact_blacklist: bad group");
+    C->h_blacklist[a * MAX_GROUPS + b] = C->h_blacklist[b * MAX_GROUPS + a] = 1;
+    C->topology_dirty = true;
+    return SB_OK;
+}
+int sb_contact_set_friction(sb_context* ctx, int a, int b, double mu)
+{
+    Contact* C = ctx ? ctx->contact : nullptr;
+    if (!C || a < 0 || b < 0 || a >= (int)C->groups.size() || b >= (int)C->groups.size()) return fail(ctx, SB_ERR_ARG, "sb_contact_set_friction: bad group");
+    C->h_mu[a * MAX_GROUPS + b] = C->h_mu[b * MAX_GROUPS + a] = mu;
+    C->topology_dirty = true;
+    return SB_OK;
+}
+int sb_contact_set_params(sb_context* ctx, double contact_stiffness, double epsv, int enable_pt, int enable_ee, int enable_friction)
+{
+    Contact* C = ctx ? ctx->contact : nullptr;
+    if (!C) return fail(ctx, SB_ERR_STATE, "sb_contact_set_params: call sb_contact_init first");
+    C->stiffness = contact_stiffness; C->epsv = epsv; C->enable_pt = enable_pt; C->enable_ee = enable_ee; C->enable_friction = enable_friction;
+    return SB_OK;
+}
+int sb_contact_update(sb_context* ctx)
+{
+    if (!ctx) return SB_ERR_ARG;
+    return contact_update_internal(ctx);
+}
+int sb_contact_update_friction(sb_context* ctx)
+{
+    Contact* C = ctx ? ctx->contact : nullptr;
+    if (!C) return fail(ctx, SB_ERR_STATE, "sb_contact_update_friction: call sb_contact_init first");
+    if (C->groups.empty()) return SB_OK;
+    int r;
+    if (C->topology_dirty && (r = upload_topology(ctx, C))) return r;
+    if ((r = refresh_params(ctx, C))) return r;
+    if (!C->enable_friction) {
+        for (int t = N_CONTACT_TABLES; t < N_TABLES; t++) ctx->potentials[C->pot[t]].n_elem = 0;
+        return SB_OK;
+    }
+    if ((r = update_vertices(ctx, C, true))) return r;   // dt = 0 (EnergyFrictionalContact.cpp:543)
+    return detect(ctx, C, 1, 2.0 * max_thickness(C));
+}
+int sb_contact_count_intersections(sb_context* ctx, int* out_count)
+{
+    if (!ctx || !out_count) return SB_ERR_ARG;
+    return contact_intersections_internal(ctx, out_count);
+}
+int sb_contact_detect(sb_context* ctx, double enlargement, int with_intersections)
+{
+    Contact* C = ctx ? ctx->contact : nullptr;
+    if (!C) return fail(ctx, SB_ERR_STATE, "sb_contact_detect: call sb_contact_init first");
+    int r;
+    if (C->topology_dirty && (r = upload_topology(ctx, C))) return r;
+    if ((r = refresh_params(ctx, C))) return r;
+    if ((r = update_vertices(ctx, C, false))) return r;
+    return detect(ctx, C, with_intersections ? 3 : 0, enlargement);
+}
+int sb_contact_get_proximity(sb_context* ctx, int kind, int32_t* host_ids, double* host_dist, int capacity, int* out_count, int* out_width)
+{
+    Contact* C = ctx ? ctx->contact : nullptr;
+    if (!C || kind < 0 || kind >= N_LISTS) return fail(ctx, SB_ERR_ARG, "sb_contact_get_proximity: bad argument");
+    const int n = C->h_list_count[kind];
+    if (out_count) *out_count = n;
+    if (out_width) *out_width = LIST_WIDTH[kind];
+    if (host_ids && n > 0) {
+        if (capacity < n) return fail(ctx, SB_ERR_ARG, "sb_contact_get_proximity: buffer too small");
+        SB_CUDA(ctx, cudaMemcpyAsync(host_ids, C->list_ids[kind].p, sizeof(int32_t) * (size_t)n * LIST_WIDTH[kind], cudaMemcpyDeviceToHost, ctx->stream));
+        if (host_dist) SB_CUDA(ctx, cudaMemcpyAsync(host_dist, C->list_dist[kind].p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return SB_OK;
+}
+int sb_contact_get_vertices(sb_context* ctx, int group, double* host_xyz)
+{
+    Contact* C = ctx ? ctx->contact : nullptr;
+    if (!C || group < 0 || group >= (int)C->groups.size() || !host_xyz) return fail(ctx, SB_ERR_ARG, "sb_contact_get_vertices: bad argument");
+    const Group& g = C->groups[group];
+    SB_CUDA(ctx, cudaMemcpyAsync(host_xyz, C->x.p + 3 * (size_t)g.v_off, sizeof(double) * 3 * g.n_v, cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}
+int sb_contact_set_vertices(sb_context* ctx, int group, const double* host_xyz)
+{
+    Contact* C = ctx ? ctx->contact : nullptr;
+    if (!C || group < 0 || group >= (int)C->groups.size() || !host_xyz) return fail(ctx, SB_ERR_ARG, "sb_contact_set_vertices: bad argument");
+    int r;
+    if (C->topology_dirty && (r = upload_topology(ctx, C))) return r;
+    const Group& g = C->groups[group];
+    SB_CUDA(ctx, cudaMemcpyAsync(C->x.p + 3 * (size_t)g.v_off, host_xyz, sizeof(double) * 3 * g.n_v, cudaMemcpyHostToDevice, ctx->stream));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    C->external_vertices = true;
+    return SB_OK;
+}
+int sb_contact_potential(sb_context* ctx, const char* name, int* out_potential)
+{
+    Contact* C = ctx ? ctx->contact : nullptr;
+    if (!C || !name || !out_potential) return fail(ctx, SB_ERR_ARG, "sb_contact_potential: bad argument");
+    *out_potential = -1;
+    for (int t = 0; t < N_TABLES; t++)
+        if (std::strcmp(LAYOUTS[t].name, name) == 0) *out_potential = C->pot[t];
+    return SB_OK;
+}
+
+}  // extern "C"

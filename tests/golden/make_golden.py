@@ -60,6 +60,9 @@ def pack(d):
         out[f"mesh{g}_vertices"] = rd(d, f"mesh{g}_vertices", np.float64).reshape(-1, 3)
         out[f"mesh{g}_triangles"] = rd(d, f"mesh{g}_triangles", np.int32).reshape(-1, 3)
         out[f"mesh{g}_edges"] = rd(d, f"mesh{g}_edges", np.int32).reshape(-1, 2)
+        out[f"mesh{g}_ps_index"] = rd(d, f"mesh{g}_ps_index", np.int32)
+    if "meshes" in meta:
+        out["rigidbody_local_vertices"] = rd(d, "rigidbody_local_vertices", np.float64).reshape(-1, 3)
     for k in ["pt_pp", "pt_pe", "pt_pt", "ee_pp", "ee_pe", "ee_ee"]:
         if f"prox_{k}_n" in meta:
             w = meta[f"prox_{k}_width"]
