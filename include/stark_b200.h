@@ -184,6 +184,7 @@ typedef struct sb_newton_settings {
     int32_t cg_stop_on_indefiniteness;
     double bailout_residual;
     int32_t contact_enabled;   /* run the built-in contact callbacks (update / intersection test) */
+    int32_t skip_converged_state_check;   /* the caller runs the is_converged_state_valid callbacks itself */
 } sb_newton_settings;
 typedef struct sb_newton_stats {
     int32_t result;            /* symx::SolverReturn value (solver_utils.h:15-26) */
@@ -193,9 +194,15 @@ typedef struct sb_newton_stats {
     int32_t n_evaluations;
     double last_residual, last_energy;
     double residuals[64];      /* residual of every evaluation (first 64) */
+    double gpu_ms;             /* device time of the solve: CUDA events on the context stream around the whole call */
 } sb_newton_stats;
 SB_API void sb_newton_default_settings(sb_newton_settings* s);   /* STARK's defaults (S/core/Settings.cpp:40-54) */
 SB_API int sb_newton_solve(sb_context* ctx, const sb_newton_settings* settings, sb_newton_stats* stats);
+
+/* ---- measurement ----------------------------------------------------------------------------------------------------------
+ * Launches the element kernel of ONE potential `reps` times on the current state (mode as sb_eval) and returns the average
+ * launch duration measured with CUDA events on the context stream (bench.py roofline). */
+SB_API int sb_profile_potential(sb_context* ctx, int potential, int mode, int reps, double* out_avg_ms);
 
 #ifdef __cplusplus
 }

@@ -51,6 +51,7 @@ class NewtonSettings(C.Structure):
         ("cg_stop_on_indefiniteness", C.c_int32),
         ("bailout_residual", C.c_double),
         ("contact_enabled", C.c_int32),
+        ("skip_converged_state_check", C.c_int32),
     ]
 
 
@@ -62,6 +63,7 @@ class NewtonStats(C.Structure):
         ("n_evaluations", C.c_int32),
         ("last_residual", C.c_double), ("last_energy", C.c_double),
         ("residuals", C.c_double * 64),
+        ("gpu_ms", C.c_double),
     ]
 
 
@@ -77,7 +79,7 @@ SYMBOLS = [
     "sb_contact_init", "sb_contact_add_mesh", "sb_contact_blacklist", "sb_contact_set_friction", "sb_contact_set_params",
     "sb_contact_update", "sb_contact_update_friction", "sb_contact_count_intersections", "sb_contact_get_proximity",
     "sb_contact_get_vertices", "sb_contact_set_vertices", "sb_contact_detect", "sb_contact_potential",
-    "sb_newton_default_settings", "sb_newton_solve",
+    "sb_newton_default_settings", "sb_newton_solve", "sb_profile_potential",
 ]
 
 

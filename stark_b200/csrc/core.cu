@@ -550,3 +550,43 @@ int sb_du_get(sb_context* ctx, double* host_du)
 }
 
 }  // extern "C"
+
+extern "C" int sb_profile_potential(sb_context* ctx, int potential, int mode, int reps, double* out_avg_ms)
+{
+    int r = check_pot(ctx, potential, "sb_profile_potential"); if (r) return r;
+    if (reps <= 0 || !out_avg_ms) return fail(ctx, SB_ERR_ARG, "sb_profile_potential: bad argument");
+    if (!ctx->have_pgh) return fail(ctx, SB_ERR_STATE, "sb_profile_potential: call sb_eval(SB_EVAL_PGH) first (output buffers)");
+    Potential& p = ctx->potentials[potential];
+    if (p.n_elem == 0) { *out_avg_ms = 0.0; return SB_OK; }
+    r = refresh_slots(ctx, p); if (r) return r;
+    EvalArgs a;
+    a.slots = p.slots.p;
+    a.conn = p.conn_ext ? p.conn_ext : p.conn.p;
+    a.conn_stride = p.conn_stride;
+    a.n_elem = p.n_elem;
+    for (int b = 0; b < MAX_BLOCKS; b++) a.blocks[b] = p.blocks[b];
+    DevBuf<double> grad_tmp;   // scratch gradient so that the solver state is not disturbed
+    grad_tmp.ensure(ctx->ndofs);
+    SB_CUDA(ctx, cudaMemsetAsync(grad_tmp.p, 0, sizeof(double) * ctx->ndofs, ctx->stream));
+    a.grad = grad_tmp.p;
+    a.H = ctx->H.p + p.H_off;
+    a.rows = ctx->rows.p + p.rows_off;
+    a.E_elem = ctx->E_elem.p + p.E_off;
+    a.g_elem = nullptr;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, ctx->stream);
+    for (int i = 0; i < reps; i++) {
+        if (mode == SB_EVAL_PGH) p.k->launch_pgh(a, ctx->stream); else p.k->launch_p(a, ctx->stream);
+        ctx->launches++;
+    }
+    cudaEventRecord(e1, ctx->stream);
+    cudaEventSynchronize(e1);
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    grad_tmp.release();
+    SB_CUDA(ctx, cudaGetLastError());
+    *out_avg_ms = (double)ms / reps;
+    return SB_OK;
+}

@@ -49,6 +49,7 @@ extern "C" void sb_newton_default_settings(sb_newton_settings* s)
     s->cg_stop_on_indefiniteness = 1;
     s->bailout_residual = 1e-10;
     s->contact_enabled = 1;
+    s->skip_converged_state_check = 0;
 }
 
 extern "C" int sb_newton_solve(sb_context* ctx, const sb_newton_settings* S, sb_newton_stats* stats)
@@ -78,6 +79,9 @@ extern "C" int sb_newton_solve(sb_context* ctx, const sb_newton_settings* S, sb_
     int pdn_countdown = 0;
     double ppn_threshold = -1.0;
 
+    cudaEvent_t ev0, ev1;
+    cudaEventCreate(&ev0); cudaEventCreate(&ev1);
+    cudaEventRecord(ev0, ctx->stream);
     bool valid = true;
     if ((rc = state_valid(valid))) return rc;
     if (!valid) result = InvalidInitialState;
@@ -207,11 +211,17 @@ extern "C" int sb_newton_solve(sb_context* ctx, const sb_newton_settings* S, sb_
         }
     }
 
-    if (result == Successful) {
+    if (result == Successful && !S->skip_converged_state_check) {
         if ((rc = state_valid(valid))) return rc;
         if (!valid) result = InvalidConvergedState;
     }
     stats->result = result;
+    cudaEventRecord(ev1, ctx->stream);
+    cudaEventSynchronize(ev1);
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    stats->gpu_ms = ms;
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     stats->newton_iterations = it;
     return SB_OK;
 }
