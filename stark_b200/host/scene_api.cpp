@@ -73,7 +73,7 @@ __attribute__((visibility("default"))) void* sbh_scene_create(const char* name, 
 __attribute__((visibility("default"))) void sbh_scene_destroy(void* h) { delete static_cast<Scene*>(h); }
 
 // out[0] keep_going, [1] accepted, [2] result, [3] newton its, [4] cg its, [5] evaluations, [6] dt, [7] runtime s, [8] solve s,
-// [9] first residual, [10] ls_inv, [11] ls_bt, [12] time, [13] ndofs, [14] contact stiffness
+// [9] first residual, [10] ls_inv, [11] ls_bt, [12] time, [13] ndofs, [14] contact stiffness, [15] device ms of the Newton solve
 __attribute__((visibility("default"))) int sbh_scene_step(void* h, double* out)
 {
     Simulation& sim = *static_cast<Scene*>(h)->sim;
@@ -82,7 +82,7 @@ __attribute__((visibility("default"))) int sbh_scene_step(void* h, double* out)
     if (out) {
         out[0] = keep; out[1] = s.accepted; out[2] = s.result; out[3] = s.newton_iterations; out[4] = s.cg_iterations; out[5] = s.n_evaluations;
         out[6] = s.dt; out[7] = s.runtime_s; out[8] = s.solve_s; out[9] = s.first_residual; out[10] = s.ls_inv; out[11] = s.ls_bt; out[12] = sim.current_time;
-        out[13] = sim.ndofs(); out[14] = sim.contact.contact_stiffness;
+        out[13] = sim.ndofs(); out[14] = sim.contact.contact_stiffness; out[15] = s.solve_gpu_ms;
     }
     return keep ? 1 : 0;
 }
@@ -107,6 +107,15 @@ __attribute__((visibility("default"))) int sbh_scene_positions(void* h, double* 
     if (n_nodes != sim.dyn.size()) return -1;
     std::memcpy(x0, sim.dyn.x0.data.data(), sizeof(double) * 3 * (size_t)n_nodes);
     return 0;
+}
+__attribute__((visibility("default"))) int sbh_scene_potential(void* h, const char* name)
+{
+    Simulation& sim = *static_cast<Scene*>(h)->sim;
+    const std::string n = name;
+    if (n == "EnergyTetStrain") return sim.tet_strain.potential_complete;
+    if (n == "EnergyTetStrain_Elasticity_Only") return sim.tet_strain.potential_elasticity_only;
+    if (n == "EnergyLumpedInertia") return sim.lumped_inertia.potential;
+    return -1;
 }
 __attribute__((visibility("default"))) void* sbh_scene_context(void* h) { return static_cast<Scene*>(h)->sim->context(); }
 

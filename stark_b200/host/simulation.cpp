@@ -601,6 +601,7 @@ bool Simulation::run_one_time_step()
     stats.result = result;
     stats.newton_iterations = st.newton_iterations; stats.cg_iterations = st.cg_iterations; stats.ls_inv = st.ls_inv_iterations; stats.ls_bt = st.ls_bt_iterations;
     stats.n_evaluations = st.n_evaluations;
+    stats.solve_gpu_ms = st.gpu_ms;
     stats.first_residual = st.residuals[0];
     for (int i = 0; i < std::min(64, st.n_evaluations); i++) stats.residuals.push_back(st.residuals[i]);
     total_newton_iterations += st.newton_iterations; total_evaluations += st.n_evaluations; total_cg_iterations += st.cg_iterations;

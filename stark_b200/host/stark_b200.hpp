@@ -165,7 +165,7 @@ public:
 struct StepStats {
     int result = 0;   // symx::SolverReturn
     int newton_iterations = 0, cg_iterations = 0, ls_inv = 0, ls_bt = 0, n_evaluations = 0;
-    double dt = 0.0, runtime_s = 0.0, solve_s = 0.0, first_residual = 0.0;
+    double dt = 0.0, runtime_s = 0.0, solve_s = 0.0, solve_gpu_ms = 0.0, first_residual = 0.0;
     std::vector<double> residuals;
     bool accepted = false;
 };

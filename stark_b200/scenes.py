@@ -25,6 +25,7 @@ def load():
         h.sbh_scene_residuals.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
         h.sbh_scene_totals.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         h.sbh_scene_positions.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
+        h.sbh_scene_potential.argtypes = [C.c_void_p, C.c_char_p]
         h.sbh_scene_context.restype = C.c_void_p
         h.sbh_scene_context.argtypes = [C.c_void_p]
         _host = h
@@ -32,7 +33,7 @@ def load():
 
 
 STEP_FIELDS = ["keep_going", "accepted", "result", "newton_iterations", "cg_iterations", "evaluations", "dt", "runtime_s", "solve_s",
-               "first_residual", "ls_inv", "ls_bt", "time", "ndofs", "contact_stiffness"]
+               "first_residual", "ls_inv", "ls_bt", "time", "ndofs", "contact_stiffness", "solve_gpu_ms"]
 TOTAL_FIELDS = ["nodes", "tets", "ndofs", "h2d_bytes", "d2h_bytes", "launches", "newton_iterations", "solve_s"]
 
 
