@@ -96,6 +96,7 @@ def main():
     ap.add_argument("--impl", default="stark_b200")
     ap.add_argument("--grid", type=int, default=GRID_N)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stage-steps", type=int, default=4, help="extra (untimed) steps run with stage profiling on after the timed region; 0 = off")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -191,6 +192,25 @@ def main():
     except Exception as e:   # the line must still print
         roof = {"error": repr(e)}
 
+    # ---- per-stage breakdown (diagnostic, outside the timed region): extra steps with a stream sync at every stage boundary ----
+    stages = None
+    if args.stage_steps > 0:
+        try:
+            import ctypes as C
+            lib = capi.load()
+            lib.sb_profile_stages(C.c_void_p(ctx_handle), 1)
+            it_s = 0
+            for _ in range(args.stage_steps):
+                it_s += int(sc.step()["newton_iterations"])
+            rep = lib.sb_profile_report(C.c_void_p(ctx_handle)).decode()
+            lib.sb_profile_stages(C.c_void_p(ctx_handle), 0)
+            stages = {"steps": args.stage_steps, "newton_iterations": it_s}
+            for ln in rep.splitlines():
+                name, ms, calls = ln.split()
+                stages[name] = {"ms": round(float(ms), 4), "calls": int(calls)}
+        except Exception as e:
+            stages = {"error": repr(e)}
+
     # ---- CPU baseline: the unmodified reference on this box's host cores, bounded sample ----
     cpu = None
     if not args.no_cpu_baseline and args.gpus == 1:
@@ -213,7 +233,7 @@ def main():
         "gpu_launches": int(t1["launches"] - t0["launches"]),
         "newton_iterations": its_all, "evaluations": evals_all, "cg_iterations": cg_all, "accepted_steps_rank0": accepted, "wall_s_rank0": wall_s,
         "solve_gpu_ms_per_iteration": solve_gpu_ms / max(1.0, its_all / world),
-        "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "stages": stages,
     }
     print(json.dumps(line))
     return 0

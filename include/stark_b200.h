@@ -203,6 +203,11 @@ SB_API int sb_newton_solve(sb_context* ctx, const sb_newton_settings* settings, 
  * Launches the element kernel of ONE potential `reps` times on the current state (mode as sb_eval) and returns the average
  * launch duration measured with CUDA events on the context stream (bench.py roofline). */
 SB_API int sb_profile_potential(sb_context* ctx, int potential, int mode, int reps, double* out_avg_ms);
+/* Stage profiling of the Newton path (the analogue of the reference's symx::Logger scoped timers, symx/solver/Logger.h):
+ * when enabled every stage is bracketed by stream synchronisations and its host wall time accumulated.  The report is
+ * one line per stage: "<name> <total ms> <calls>".  Enabling resets the totals.  Off by default (it serialises the path). */
+SB_API int sb_profile_stages(sb_context* ctx, int enable);
+SB_API const char* sb_profile_report(sb_context* ctx);
 
 #ifdef __cplusplus
 }

@@ -80,6 +80,7 @@ SYMBOLS = [
     "sb_contact_update", "sb_contact_update_friction", "sb_contact_count_intersections", "sb_contact_get_proximity",
     "sb_contact_get_vertices", "sb_contact_set_vertices", "sb_contact_detect", "sb_contact_potential",
     "sb_newton_default_settings", "sb_newton_solve", "sb_profile_potential",
+    "sb_profile_stages", "sb_profile_report",
 ]
 
 
@@ -93,6 +94,7 @@ def load():
     lib = C.CDLL(LIB_PATH)
     lib.sb_last_error.restype = C.c_char_p
     lib.sb_kernel_names.restype = C.c_char_p
+    lib.sb_profile_report.restype = C.c_char_p
     lib.sb_get_stream.restype = C.c_void_p
     lib.sb_launch_count.restype = C.c_int64
     lib.sb_destroy.restype = None

@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(288) k_assemble_numeric(const double* __restri
 
 static int build_symbolic(sb_context* ctx, Assembly* A)
 {
+    StageTimer timer(ctx, ST_ASM_SYMBOLIC);
     cudaStream_t st = ctx->stream;
     const size_t n = ctx->n_blocks_total;
     if (ctx->H_total >= (1ull << 32)) return fail(ctx, SB_ERR_STATE, "sb_assemble: element Hessian storage exceeds 32-bit offsets");
@@ -194,6 +195,7 @@ int assemble_internal(sb_context* ctx)
         int r = build_symbolic(ctx, A);
         if (r) return r;
     }
+    StageTimer timer(ctx, ST_ASM_NUMERIC);
     const size_t nt = 9 * A->nnzb;
     k_assemble_numeric<<<(unsigned)((nt + 287) / 288), 288, 0, ctx->stream>>>(ctx->H.p, A->seg.p, A->sorted_off.p, A->sorted_pitch.p, A->vals.p, A->nnzb);
     ctx->launches++;

@@ -863,6 +863,7 @@ int contact_update_internal(sb_context* ctx)
 {
     Contact* C = ctx->contact;
     if (!C || C->groups.empty()) return 0;
+    StageTimer timer(ctx, ST_CONTACT_UPDATE);
     int r;
     if (C->topology_dirty && (r = upload_topology(ctx, C))) return r;
     if ((r = refresh_params(ctx, C))) return r;
@@ -874,6 +875,7 @@ int contact_intersections_internal(sb_context* ctx, int* out_count)
     Contact* C = ctx->contact;
     *out_count = 0;
     if (!C || C->groups.empty()) return 0;
+    StageTimer timer(ctx, ST_INTERSECTIONS);
     int r;
     if (C->topology_dirty && (r = upload_topology(ctx, C))) return r;
     if ((r = update_vertices(ctx, C, false))) return r;

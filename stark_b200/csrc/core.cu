@@ -1,9 +1,28 @@
 // Context, arrays, DoF sets, potentials and the evaluation driver behind the C-ABI (include/stark_b200.h).
 #include "internal.h"
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 
 namespace sb {
+
+static double now_ms()
+{
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+StageTimer::StageTimer(sb_context* c, int s) : ctx(c), stage(s), t0(0.0)
+{
+    if (!ctx->profile) return;
+    cudaStreamSynchronize(ctx->stream);
+    t0 = now_ms();
+}
+StageTimer::~StageTimer()
+{
+    if (!ctx->profile) return;
+    cudaStreamSynchronize(ctx->stream);
+    ctx->stage_ms[stage] += now_ms() - t0;
+    ctx->stage_calls[stage]++;
+}
 
 int fail(sb_context* ctx, int code, const std::string& msg)
 {
@@ -93,9 +112,13 @@ int refresh_slots(sb_context* ctx, Potential& p)
             s.off = c;
         }
     }
-    p.slots.ensure(h.size());
-    SB_CUDA(ctx, cudaMemcpyAsync(p.slots.p, h.data(), h.size() * sizeof(FetchSlot), cudaMemcpyHostToDevice, ctx->stream));
-    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // h is a stack-owned staging buffer
+    // upload only when a binding moved (arrays are re-allocated rarely); pageable-source async copies are staged by the
+    // driver before the call returns, and slots_host outlives the call anyway
+    if (h.size() != p.slots_host.size() || std::memcmp(h.data(), p.slots_host.data(), h.size() * sizeof(FetchSlot)) != 0) {
+        p.slots.ensure(h.size());
+        p.slots_host = h;
+        SB_CUDA(ctx, cudaMemcpyAsync(p.slots.p, p.slots_host.data(), h.size() * sizeof(FetchSlot), cudaMemcpyHostToDevice, ctx->stream));
+    }
     // DoF block offsets
     for (int b = 0; b < p.k->nb; b++) p.blocks[b].dof_offset = ctx->dof_sets[p.block_set[b]].offset;
     return 0;
@@ -104,6 +127,7 @@ int refresh_slots(sb_context* ctx, Potential& p)
 int eval_internal(sb_context* ctx, int mode, double* out_E, double* out_grad_inf, bool sync_scalars)
 {
     if (mode != SB_EVAL_P && mode != SB_EVAL_PGH) return fail(ctx, SB_ERR_ARG, "sb_eval: unknown mode");
+    StageTimer timer(ctx, mode == SB_EVAL_PGH ? ST_EVAL_PGH : ST_EVAL_P);
     recompute_dof_offsets(ctx);
     if (ctx->ndofs <= 0) return fail(ctx, SB_ERR_STATE, "sb_eval: no degrees of freedom");
     if (ctx->ndofs % 3 != 0) return fail(ctx, SB_ERR_STATE, "sb_eval: ndofs must be divisible by 3");
@@ -111,6 +135,7 @@ int eval_internal(sb_context* ctx, int mode, double* out_E, double* out_grad_inf
     // layout of the shared element-output buffers
     size_t H_total = 0, rows_total = 0, E_total = 0, n_blocks = 0;
     for (auto& p : ctx->potentials) {
+        H_total = (H_total + 15) & ~(size_t)15;   // every potential's Hessian block starts 128 B aligned (bulk stores)
         p.H_off = H_total; p.rows_off = rows_total; p.E_off = E_total;
         const size_t n = p.k->n_dof;
         H_total += (size_t)p.n_elem * n * n;
@@ -139,6 +164,7 @@ int eval_internal(sb_context* ctx, int mode, double* out_E, double* out_grad_inf
         if (r) return r;
         EvalArgs a;
         a.slots = p.slots.p;
+        a.slots_host = p.slots_host.data();
         a.conn = p.conn_ext ? p.conn_ext : p.conn.p;
         a.conn_stride = p.conn_stride;
         a.n_elem = p.n_elem;
@@ -245,6 +271,23 @@ int sb_synchronize(sb_context* ctx)
     return SB_OK;
 }
 int64_t sb_launch_count(const sb_context* ctx) { return ctx ? ctx->launches : 0; }
+
+int sb_profile_stages(sb_context* ctx, int enable)
+{
+    if (!ctx) return SB_ERR_ARG;
+    ctx->profile = enable != 0;
+    for (int i = 0; i < 16; i++) { ctx->stage_ms[i] = 0.0; ctx->stage_calls[i] = 0; }
+    return SB_OK;
+}
+const char* sb_profile_report(sb_context* ctx)
+{
+    if (!ctx) return "";
+    static const char* names[ST_COUNT] = {"contact_update", "intersections", "eval_pgh", "eval_p", "project_to_pd", "assembly_symbolic", "assembly_numeric", "pcg", "line_search_misc"};
+    ctx->profile_report.clear();
+    for (int i = 0; i < ST_COUNT; i++)
+        ctx->profile_report += std::string(names[i]) + " " + std::to_string(ctx->stage_ms[i]) + " " + std::to_string(ctx->stage_calls[i]) + "\n";
+    return ctx->profile_report.c_str();
+}
 
 int sb_array_create(sb_context* ctx, const char* label, int stride, int* out_array)
 {
@@ -460,6 +503,7 @@ int sb_potential_get_element_output(sb_context* ctx, int potential, double* host
     r = refresh_slots(ctx, p); if (r) return r;
     EvalArgs a;
     a.slots = p.slots.p;
+    a.slots_host = p.slots_host.data();
     a.conn = p.conn_ext ? p.conn_ext : p.conn.p;
     a.conn_stride = p.conn_stride;
     a.n_elem = p.n_elem;
@@ -561,6 +605,7 @@ extern "C" int sb_profile_potential(sb_context* ctx, int potential, int mode, in
     r = refresh_slots(ctx, p); if (r) return r;
     EvalArgs a;
     a.slots = p.slots.p;
+    a.slots_host = p.slots_host.data();
     a.conn = p.conn_ext ? p.conn_ext : p.conn.p;
     a.conn_stride = p.conn_stride;
     a.n_elem = p.n_elem;

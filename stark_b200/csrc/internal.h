@@ -28,6 +28,7 @@ struct DofBlock {
 
 struct EvalArgs {
     const FetchSlot* slots;
+    const FetchSlot* slots_host;   // HOST copy of the same table (for launchers that pass it as a kernel parameter)
     const int32_t* conn;
     int32_t conn_stride;
     int32_t n_elem;
@@ -105,8 +106,19 @@ struct Potential {
     const int32_t* conn_ext = nullptr;  // or device-resident table owned by the contact module
     const int32_t* n_elem_dev = nullptr;
     DevBuf<FetchSlot> slots;
+    std::vector<FetchSlot> slots_host;  // what `slots` holds on the device (re-uploaded only when a binding moved)
     // offsets into the shared element-output buffers (recomputed each evaluation)
     size_t H_off = 0, rows_off = 0, E_off = 0;
+};
+
+// Stage profiling (sb_profile_stages): host wall time between two stream synchronisations, accumulated per stage.
+enum Stage { ST_CONTACT_UPDATE, ST_INTERSECTIONS, ST_EVAL_PGH, ST_EVAL_P, ST_PROJECT, ST_ASM_SYMBOLIC, ST_ASM_NUMERIC, ST_PCG, ST_LINE_SEARCH_MISC, ST_COUNT };
+struct StageTimer {
+    sb_context* ctx;
+    int stage;
+    double t0;
+    StageTimer(sb_context* c, int s);
+    ~StageTimer();
 };
 
 struct Assembly;   // assembly.cu
@@ -141,6 +153,11 @@ struct sb_context {
     int64_t n_projected = 0;
     uint64_t pattern_version = 1;   // bumped whenever any connectivity changes
     bool have_pgh = false;
+
+    bool profile = false;           // stage profiling on (adds a stream synchronisation at every stage boundary)
+    double stage_ms[16] = {0};
+    int64_t stage_calls[16] = {0};
+    std::string profile_report;
 
     double* h_scalars = nullptr;    // pinned host scratch (16 doubles)
     double* d_scalars = nullptr;    // device scratch (16 doubles)

@@ -321,6 +321,7 @@ int solve_pcg_internal(sb_context* ctx, double abs_tol, double rel_tol, int max_
     int r = bcsr_view(ctx, &nbr, &nnzb, &rows, &cols, &vals);
     if (r) return r;
     if (3 * nbr != ctx->ndofs) return fail(ctx, SB_ERR_STATE, "sb_solve_pcg: matrix and DoF vector sizes differ");
+    StageTimer timer(ctx, ST_PCG);
     Pcg* P = get(ctx);
     cudaStream_t st = ctx->stream;
     const int n = ctx->ndofs;

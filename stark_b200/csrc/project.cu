@@ -192,6 +192,7 @@ int project_internal(sb_context* ctx, double grad_threshold, double eps, int mir
         if (out_all_projected) *out_all_projected = 0;
         return 0;
     }
+    StageTimer timer(ctx, ST_PROJECT);
     ProjTable T;
     T.n_pots = 0;
     for (auto& p : ctx->potentials) {

@@ -10,68 +10,100 @@
 // and A is a sum of isotropic (delta_rs M_cd), rank-one (u_rc u_sd) and one skew term (the Hessian of det F), so every
 // 3x3 block (a, b) of the 12x12 element Hessian costs a handful of 3-vector operations (formulas in DESIGN.md).
 //
-// Mapping: 16 lanes per element, lane = block (a, b); one warp = two consecutive elements, whose 2 x 1152 B of Hessian are
-// staged in shared memory and written back as nine fully coalesced 256 B stores.  Inputs are gathered once per CTA into
-// shared memory through the generic fetch table (same binding contract as every other potential).
+// Mapping (HBM-bound design: 1,152 of the 1,632 algorithmic bytes per tet are the dense Hessian write; FP64 work is kept
+// at ~1.1 k instructions per tet so the FP64 pipe stays far below the store stream):
+//   * ONE THREAD PER ELEMENT.  The F-space state (G, F, cof F, S, the per-node vectors F g_n, C g_n, S g_n) is computed
+//     exactly once per tet and only the 10 upper-triangular 3x3 blocks are evaluated; the lower ones are their transposes.
+//     (A lane-per-block mapping repeats the ~400-instruction set-up in every lane: 4x the FP64 work, which then bounds
+//     the kernel instead of HBM.)
+//   * one warp = a tile of 32 consecutive elements = 36,864 contiguous bytes of the Hessian store.  Each thread stages its
+//     element in shared memory (row pitch 1,168 B = 1,152 + 16 so that the 8 B stores of a half-warp spread over the
+//     banks) and sends it to global memory with its OWN bulk asynchronous copy (cp.async.bulk.global.shared::cta, the
+//     TMA engine): full 128 B lines, no LSU store traffic, and the copy drains while the warp gathers and sets up its
+//     next tile; the buffer is reclaimed with cp.async.bulk.wait_group.read;
+//   * the fetch table travels as a __grid_constant__ kernel parameter (constant bank, uniform loads);
+//   * persistent grid (3 two-warp CTAs per SM, 73 KB of staging each), tiles strided over the grid;
+//   * gradient: FP64 atomics into the flat gradient; block rows and energy: direct stores.
 #pragma once
 
 namespace sb {
 
-constexpr int TET_THREADS = 128;
-constexpr int TET_ELEMS = TET_THREADS / 16;
+constexpr int TET_WARPS = 2;                     // warps per CTA
+constexpr int TET_THREADS = 32 * TET_WARPS;
+constexpr int TET_TILE = 32;                     // elements per warp tile (one per lane)
+constexpr int TET_PITCH = 146;                   // doubles between two elements in the staging buffer (1,168 B)
+constexpr int TET_MAX_NIN = 43;
+constexpr int TET_SMEM_BYTES = TET_WARPS * TET_TILE * TET_PITCH * 8;
+
+struct TetParams {
+    EvalArgs a;
+    FetchSlot slot[TET_MAX_NIN];
+};
 
 template<bool COMPLETE>
-__global__ void __launch_bounds__(TET_THREADS) k_tet_analytic(const EvalArgs a)
+__global__ void __launch_bounds__(TET_THREADS) k_tet_analytic(const __grid_constant__ TetParams P)
 {
     constexpr int NIN = COMPLETE ? 43 : 40;
-    __shared__ double s_in[TET_ELEMS * NIN];
-    __shared__ double s_H[TET_ELEMS * 144];
-    const int tid = threadIdx.x;
-    const int e_base = blockIdx.x * TET_ELEMS;
-    for (int idx = tid; idx < TET_ELEMS * NIN; idx += TET_THREADS) {
-        const int el = idx / NIN, slot = idx - el * NIN;
-        const int e = e_base + el;
-        if (e < a.n_elem) {
-            const FetchSlot fs = a.slots[slot];
-            const int row = (fs.conn_col >= 0) ? a.conn[(size_t)e * a.conn_stride + fs.conn_col] : 0;
-            s_in[idx] = fs.base[(size_t)row * fs.stride + fs.off];
-        }
-    }
-    __syncthreads();
+    extern __shared__ __align__(128) double s_H[];
+    const EvalArgs& a = P.a;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* sH = s_H + (warp * TET_TILE + lane) * TET_PITCH;          // this thread's element
+    const unsigned sH_addr = (unsigned)__cvta_generic_to_shared(sH);
+    const int n_tiles = (a.n_elem + TET_TILE - 1) / TET_TILE;
+    const bool bulk_ok = ((reinterpret_cast<unsigned long long>(a.H) & 15ull) == 0ull);
+    bool store_pending = false;
 
-    const int el = tid >> 4, l = tid & 15;
-    const int ba = l >> 2, bb = l & 3;
-    const int e = e_base + el;
-    const bool live = e < a.n_elem;
-    if (live) {
-        const double* in = s_in + el * NIN;
-        const double dt = in[NIN - 1], scale = in[36], ym = in[37], nu = in[38];
+    for (int tile = blockIdx.x * TET_WARPS + warp; tile < n_tiles; tile += gridDim.x * TET_WARPS) {
+        const int e = tile * TET_TILE + lane;
+        const bool live = e < a.n_elem;
+        const int32_t* ce = a.conn + (size_t)(live ? e : a.n_elem - 1) * a.conn_stride;   // dead lanes redo the last element
+        auto in = [&](int slot) -> double {
+            const FetchSlot& fs = P.slot[slot];
+            const int row = (fs.conn_col >= 0) ? ce[fs.conn_col] : 0;
+            return fs.base[(size_t)row * fs.stride + fs.off];
+        };
+        const double dt = in(NIN - 1), scale = in(36), ym = in(37), nu = in(38);
+
         // rest shape: B = DX^-1, vol = det(DX) / 6, G = shape-function gradients (4 x 3)
-        double DX[9];
-        for (int c = 0; c < 3; c++)
-            for (int r = 0; r < 3; r++) DX[3 * r + c] = scale * in[24 + 3 * (c + 1) + r] - scale * in[24 + r];
-        const double c00 = DX[4] * DX[8] - DX[5] * DX[7], c01 = DX[5] * DX[6] - DX[3] * DX[8], c02 = DX[3] * DX[7] - DX[4] * DX[6];
-        const double det = DX[0] * c00 + DX[1] * c01 + DX[2] * c02;
-        const double rd = 1.0 / det;
-        double B[9];
-        B[0] = c00 * rd; B[1] = (DX[2] * DX[7] - DX[1] * DX[8]) * rd; B[2] = (DX[1] * DX[5] - DX[2] * DX[4]) * rd;
-        B[3] = c01 * rd; B[4] = (DX[0] * DX[8] - DX[2] * DX[6]) * rd; B[5] = (DX[2] * DX[3] - DX[0] * DX[5]) * rd;
-        B[6] = c02 * rd; B[7] = (DX[1] * DX[6] - DX[0] * DX[7]) * rd; B[8] = (DX[0] * DX[4] - DX[1] * DX[3]) * rd;
-        const double vol = det / 6.0;
         double G[12];
-        for (int c = 0; c < 3; c++) {
-            G[c] = -(B[c] + B[3 + c] + B[6 + c]);
-            G[3 + c] = B[c]; G[6 + c] = B[3 + c]; G[9 + c] = B[6 + c];
+        double vol;
+        {
+            double Xn[12];
+#pragma unroll
+            for (int k = 0; k < 12; k++) Xn[k] = scale * in(24 + k);
+            double DX[9];
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+#pragma unroll
+                for (int r = 0; r < 3; r++) DX[3 * r + c] = Xn[3 * (c + 1) + r] - Xn[r];
+            const double c00 = DX[4] * DX[8] - DX[5] * DX[7], c01 = DX[5] * DX[6] - DX[3] * DX[8], c02 = DX[3] * DX[7] - DX[4] * DX[6];
+            const double det = DX[0] * c00 + DX[1] * c01 + DX[2] * c02;
+            const double rd = 1.0 / det;
+            double B[9];
+            B[0] = c00 * rd; B[1] = (DX[2] * DX[7] - DX[1] * DX[8]) * rd; B[2] = (DX[1] * DX[5] - DX[2] * DX[4]) * rd;
+            B[3] = c01 * rd; B[4] = (DX[0] * DX[8] - DX[2] * DX[6]) * rd; B[5] = (DX[2] * DX[3] - DX[0] * DX[5]) * rd;
+            B[6] = c02 * rd; B[7] = (DX[1] * DX[6] - DX[0] * DX[7]) * rd; B[8] = (DX[0] * DX[4] - DX[1] * DX[3]) * rd;
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                G[c] = -(B[c] + B[3 + c] + B[6 + c]);
+                G[3 + c] = B[c]; G[6 + c] = B[3 + c]; G[9 + c] = B[6 + c];
+            }
+            vol = det / 6.0;
         }
-        // F = sum_a x_a (x) g_a
+        // F = sum_n x_n (x) g_n,  x_n = x0_n + dt v_n
         double F[9];
+#pragma unroll
         for (int k = 0; k < 9; k++) F[k] = 0.0;
+#pragma unroll
         for (int n = 0; n < 4; n++)
+#pragma unroll
             for (int r = 0; r < 3; r++) {
-                const double x = in[12 + 3 * n + r] + dt * in[3 * n + r];
+                const double x = in(12 + 3 * n + r) + dt * in(3 * n + r);
+#pragma unroll
                 for (int c = 0; c < 3; c++) F[3 * r + c] += x * G[3 * n + c];
             }
         double Ic = 0.0;
+#pragma unroll
         for (int k = 0; k < 9; k++) Ic += F[k] * F[k];
         double Cf[9];   // cofactor matrix = dJ/dF
         Cf[0] = F[4] * F[8] - F[5] * F[7]; Cf[1] = F[5] * F[6] - F[3] * F[8]; Cf[2] = F[3] * F[7] - F[4] * F[6];
@@ -85,22 +117,23 @@ __global__ void __launch_bounds__(TET_THREADS) k_tet_analytic(const EvalArgs a)
         const double ri = 1.0 / (Ic + 1.0);
         const double c1 = mu_ * (1.0 - ri);
         double cFF = 2.0 * mu_ * ri * ri;     // coefficient of (F (x) F)
-        const double c3 = lambda_;
         const double c4 = lambda_ * (J - alpha);
         double Psi = 0.5 * mu_ * (Ic - 3.0) + 0.5 * lambda_ * (J - alpha) * (J - alpha) - 0.5 * mu_ * log(Ic + 1.0);
 
-        // second Piola-Kirchhoff-like stress S = dPsi/dE of the E-based terms (symmetric: 00 01 02 11 12 22) and coefficients
+        // stress S = dPsi/dE of the E-based terms (symmetric: 00 01 02 11 12 22) and coefficients
         double S[6] = {0, 0, 0, 0, 0, 0};
-        double kappa = 0.0, cN = 0.0, cD = 0.0, dn_inv = 0.0;
-        double FD[9];           // F dev(E)
-        bool limit_active = false;
+        double kappa = 0.0;
         double FFt[6] = {0, 0, 0, 0, 0, 0};
+        bool limit_active = false;
+        double dvv[6] = {0, 0, 0, 0, 0, 0}, dn_inv = 0.0, cN = 0.0, cD = 0.0;
         if (COMPLETE) {
-            const double limit = in[39], k_sl = in[40], damping = in[41];
+            const double limit = in(39), k_sl = in(40), damping = in(41);
             double E1[6];
             {
                 int q = 0;
+#pragma unroll
                 for (int i = 0; i < 3; i++)
+#pragma unroll
                     for (int j = i; j < 3; j++) {
                         E1[q] = 0.5 * (F[i] * F[j] + F[3 + i] * F[3 + j] + F[6 + i] * F[6 + j] - (i == j ? 1.0 : 0.0));
                         FFt[q] = F[3 * i] * F[3 * j] + F[3 * i + 1] * F[3 * j + 1] + F[3 * i + 2] * F[3 * j + 2];
@@ -109,14 +142,22 @@ __global__ void __launch_bounds__(TET_THREADS) k_tet_analytic(const EvalArgs a)
             }
             if (damping != 0.0) {
                 double F0[9];
+#pragma unroll
                 for (int k = 0; k < 9; k++) F0[k] = 0.0;
+#pragma unroll
                 for (int n = 0; n < 4; n++)
-                    for (int r = 0; r < 3; r++)
-                        for (int c = 0; c < 3; c++) F0[3 * r + c] += in[12 + 3 * n + r] * G[3 * n + c];
+#pragma unroll
+                    for (int r = 0; r < 3; r++) {
+                        const double x0 = in(12 + 3 * n + r);
+#pragma unroll
+                        for (int c = 0; c < 3; c++) F0[3 * r + c] += x0 * G[3 * n + c];
+                    }
                 const double k2 = damping / (dt * dt);
                 int q = 0;
                 double acc = 0.0;
+#pragma unroll
                 for (int i = 0; i < 3; i++)
+#pragma unroll
                     for (int j = i; j < 3; j++) {
                         const double e0 = 0.5 * (F0[i] * F0[j] + F0[3 + i] * F0[3 + j] + F0[6 + i] * F0[6 + j] - (i == j ? 1.0 : 0.0));
                         const double D = E1[q] - e0;
@@ -145,101 +186,151 @@ __global__ void __launch_bounds__(TET_THREADS) k_tet_analytic(const EvalArgs a)
                 cFF -= beta * dn_inv / 3.0;
                 cN = 2.0 * k_sl * dl;
                 cD = -beta * dn_inv * dn_inv * dn_inv;
-                // F dev
-                const double dm[9] = {dv[0], dv[1], dv[2], dv[1], dv[3], dv[4], dv[2], dv[4], dv[5]};
-                for (int r = 0; r < 3; r++)
-                    for (int c = 0; c < 3; c++) FD[3 * r + c] = F[3 * r] * dm[c] + F[3 * r + 1] * dm[3 + c] + F[3 * r + 2] * dm[6 + c];
+#pragma unroll
+                for (int k = 0; k < 6; k++) dvv[k] = dv[k];
             }
         }
 
-        // ---- block (ba, bb) ----
-        const double* ga = G + 3 * ba;
-        const double* gb = G + 3 * bb;
-        const double gg = ga[0] * gb[0] + ga[1] * gb[1] + ga[2] * gb[2];
-        double wa[3], wb[3], ca[3], cb[3];
-        for (int r = 0; r < 3; r++) {
-            wa[r] = F[3 * r] * ga[0] + F[3 * r + 1] * ga[1] + F[3 * r + 2] * ga[2];
-            wb[r] = F[3 * r] * gb[0] + F[3 * r + 1] * gb[1] + F[3 * r + 2] * gb[2];
-            ca[r] = Cf[3 * r] * ga[0] + Cf[3 * r + 1] * ga[1] + Cf[3 * r + 2] * ga[2];
-            cb[r] = Cf[3 * r] * gb[0] + Cf[3 * r + 1] * gb[1] + Cf[3 * r + 2] * gb[2];
-        }
-        const double xg[3] = {ga[1] * gb[2] - ga[2] * gb[1], ga[2] * gb[0] - ga[0] * gb[2], ga[0] * gb[1] - ga[1] * gb[0]};
-        double q[3];
-        for (int r = 0; r < 3; r++) q[r] = F[3 * r] * xg[0] + F[3 * r + 1] * xg[1] + F[3 * r + 2] * xg[2];
-        double iso = c1 * gg;
-        double blk[9];
-        if (COMPLETE) {
-            const double Sg[3] = {S[0] * gb[0] + S[1] * gb[1] + S[2] * gb[2], S[1] * gb[0] + S[3] * gb[1] + S[4] * gb[2], S[2] * gb[0] + S[4] * gb[1] + S[5] * gb[2]};
-            iso += ga[0] * Sg[0] + ga[1] * Sg[1] + ga[2] * Sg[2];
-        }
-        for (int r = 0; r < 3; r++)
-            for (int s = 0; s < 3; s++) blk[3 * r + s] = cFF * wa[r] * wb[s] + c3 * ca[r] * cb[s];
-        blk[0] += iso; blk[4] += iso; blk[8] += iso;
-        blk[1] += c4 * q[2]; blk[2] -= c4 * q[1]; blk[3] -= c4 * q[2]; blk[5] += c4 * q[0]; blk[6] += c4 * q[1]; blk[7] -= c4 * q[0];
-        if (COMPLETE) {
-            if (kappa != 0.0) {
-                const double hk = 0.5 * kappa;
-                const double FFm[9] = {FFt[0], FFt[1], FFt[2], FFt[1], FFt[3], FFt[4], FFt[2], FFt[4], FFt[5]};
-                for (int r = 0; r < 3; r++)
-                    for (int s = 0; s < 3; s++) blk[3 * r + s] += hk * (FFm[3 * r + s] * gg + wb[r] * wa[s]);
-            }
-            if (limit_active) {
-                const double s23d = sqrt(2.0 / 3.0) * dn_inv;
-                double da[3], db[3], na[3], nb[3];
-                for (int r = 0; r < 3; r++) {
-                    da[r] = FD[3 * r] * ga[0] + FD[3 * r + 1] * ga[1] + FD[3 * r + 2] * ga[2];
-                    db[r] = FD[3 * r] * gb[0] + FD[3 * r + 1] * gb[1] + FD[3 * r + 2] * gb[2];
-                    na[r] = wa[r] / 3.0 + s23d * da[r];
-                    nb[r] = wb[r] / 3.0 + s23d * db[r];
-                }
-                for (int r = 0; r < 3; r++)
-                    for (int s = 0; s < 3; s++) blk[3 * r + s] += cN * na[r] * nb[s] + cD * da[r] * db[s];
-            }
-        }
-        const double hs = vol * dt * dt;
-        double* He = s_H + el * 144;
-        for (int r = 0; r < 3; r++)
-            for (int s = 0; s < 3; s++) He[(3 * ba + r) * 12 + 3 * bb + s] = hs * blk[3 * r + s];
-
-        // ---- gradient (lanes bb == 0), block rows, energy ----
-        const int32_t* ce = a.conn + (size_t)e * a.conn_stride;
-        if (bb == 0) {
-            // P g_a with P = c1 F + c4 C + F S
-            double pg[3];
-            for (int r = 0; r < 3; r++) pg[r] = c1 * wa[r] + c4 * ca[r];
-            if (COMPLETE) {
-                const double Sg[3] = {S[0] * ga[0] + S[1] * ga[1] + S[2] * ga[2], S[1] * ga[0] + S[3] * ga[1] + S[4] * ga[2], S[2] * ga[0] + S[4] * ga[1] + S[5] * ga[2]};
-                for (int r = 0; r < 3; r++) pg[r] += F[3 * r] * Sg[0] + F[3 * r + 1] * Sg[1] + F[3 * r + 2] * Sg[2];
-            }
-            const DofBlock b = a.blocks[ba];
-            const int node = ce[b.conn_col];
-            const double gs = vol * dt;
+        // ---- per-node vectors: w_n = F g_n, c_n = C g_n, t_n = S g_n ----
+        double w[12], cc[12], t[12];
+#pragma unroll
+        for (int n = 0; n < 4; n++) {
+            const double* gn = G + 3 * n;
+#pragma unroll
             for (int r = 0; r < 3; r++) {
-                atomicAdd(a.grad + b.dof_offset + 3 * node + r, gs * pg[r]);
-                if (a.g_elem) a.g_elem[(size_t)e * 12 + 3 * ba + r] = gs * pg[r];
+                w[3 * n + r] = F[3 * r] * gn[0] + F[3 * r + 1] * gn[1] + F[3 * r + 2] * gn[2];
+                cc[3 * n + r] = Cf[3 * r] * gn[0] + Cf[3 * r + 1] * gn[1] + Cf[3 * r + 2] * gn[2];
             }
-            a.rows[(size_t)e * 4 + ba] = b.dof_offset / 3 + node;
+            t[3 * n + 0] = S[0] * gn[0] + S[1] * gn[1] + S[2] * gn[2];
+            t[3 * n + 1] = S[1] * gn[0] + S[3] * gn[1] + S[4] * gn[2];
+            t[3 * n + 2] = S[2] * gn[0] + S[4] * gn[1] + S[5] * gn[2];
         }
-        if (l == 0) a.E_elem[e] = vol * Psi;
-    }
-    __syncwarp();
-    // coalesced write-back of the warp's two adjacent element Hessians (2 x 144 doubles)
-    {
-        const int w = tid >> 5, lane = tid & 31;
-        const int e0 = e_base + 2 * w;
-        const int n_here = min(2, a.n_elem - e0);
-        if (n_here > 0) {
-            double* dst = a.H + (size_t)e0 * 144;
-            const double* src = s_H + (2 * w) * 144;
-            for (int k = lane; k < n_here * 144; k += 32) dst[k] = src[k];
+
+        // ---- gradient, block rows, energy: dW/dv_n = dt vol P g_n with P g_n = c1 w_n + c4 c_n + F (S g_n) ----
+        if (live) {
+            const double gs = vol * dt;
+#pragma unroll
+            for (int n = 0; n < 4; n++) {
+                const DofBlock b = a.blocks[n];
+                const int node = ce[b.conn_col];
+#pragma unroll
+                for (int r = 0; r < 3; r++) {
+                    double pg = c1 * w[3 * n + r] + c4 * cc[3 * n + r];
+                    if (COMPLETE) pg += F[3 * r] * t[3 * n] + F[3 * r + 1] * t[3 * n + 1] + F[3 * r + 2] * t[3 * n + 2];
+                    atomicAdd(a.grad + b.dof_offset + 3 * node + r, gs * pg);
+                    if (a.g_elem) a.g_elem[(size_t)e * 12 + 3 * n + r] = gs * pg;
+                }
+                a.rows[(size_t)e * 4 + n] = b.dof_offset / 3 + node;
+            }
+            a.E_elem[e] = vol * Psi;
+        }
+
+        // the previous tile's bulk copy must have finished READING this thread's staging slab before it is overwritten
+        if (store_pending) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            store_pending = false;
+        }
+
+        // ---- Hessian: 10 upper blocks (na <= nb), each stored with its transpose; everything pre-scaled by vol dt^2 ----
+        {
+            const double hs = vol * dt * dt;
+            const double A1 = hs * cFF, A3 = hs * lambda_, Aiso = hs * c1, A4 = hs * c4, Ahk = hs * 0.5 * kappa;
+            const double kF[9] = {Ahk * FFt[0], Ahk * FFt[1], Ahk * FFt[2], Ahk * FFt[1], Ahk * FFt[3], Ahk * FFt[4], Ahk * FFt[2], Ahk * FFt[4], Ahk * FFt[5]};
+#pragma unroll
+            for (int na = 0; na < 4; na++) {
+                const double* ga = G + 3 * na;
+                const double a1w[3] = {A1 * w[3 * na], A1 * w[3 * na + 1], A1 * w[3 * na + 2]};
+                const double a3c[3] = {A3 * cc[3 * na], A3 * cc[3 * na + 1], A3 * cc[3 * na + 2]};
+                const double akw[3] = {Ahk * w[3 * na], Ahk * w[3 * na + 1], Ahk * w[3 * na + 2]};
+#pragma unroll
+                for (int nb = na; nb < 4; nb++) {
+                    const double* gb = G + 3 * nb;
+                    const double gg = ga[0] * gb[0] + ga[1] * gb[1] + ga[2] * gb[2];
+                    double iso = Aiso * gg;
+                    if (COMPLETE) iso += hs * (ga[0] * t[3 * nb] + ga[1] * t[3 * nb + 1] + ga[2] * t[3 * nb + 2]);
+                    double blk[9];
+#pragma unroll
+                    for (int r = 0; r < 3; r++)
+#pragma unroll
+                        for (int s = 0; s < 3; s++) {
+                            double v = a1w[r] * w[3 * nb + s] + a3c[r] * cc[3 * nb + s];
+                            if (COMPLETE) v += kF[3 * r + s] * gg + w[3 * nb + r] * akw[s];
+                            blk[3 * r + s] = v;
+                        }
+                    blk[0] += iso; blk[4] += iso; blk[8] += iso;
+                    if (nb != na) {   // A4 * skew(F (g_a x g_b)); vanishes on the diagonal blocks
+                        const double xg[3] = {ga[1] * gb[2] - ga[2] * gb[1], ga[2] * gb[0] - ga[0] * gb[2], ga[0] * gb[1] - ga[1] * gb[0]};
+                        const double q0 = A4 * (F[0] * xg[0] + F[1] * xg[1] + F[2] * xg[2]);
+                        const double q1 = A4 * (F[3] * xg[0] + F[4] * xg[1] + F[5] * xg[2]);
+                        const double q2 = A4 * (F[6] * xg[0] + F[7] * xg[1] + F[8] * xg[2]);
+                        blk[1] += q2; blk[2] -= q1; blk[3] -= q2; blk[5] += q0; blk[6] += q1; blk[7] -= q0;
+                    }
+#pragma unroll
+                    for (int r = 0; r < 3; r++)
+#pragma unroll
+                        for (int s = 0; s < 3; s++) {
+                            sH[(3 * na + r) * 12 + 3 * nb + s] = blk[3 * r + s];
+                            if (nb != na) sH[(3 * nb + s) * 12 + 3 * na + r] = blk[3 * r + s];
+                        }
+                }
+            }
+            if (COMPLETE && limit_active) {
+                // strain-limit terms cN (F N g_a)(F N g_b)^T + cD (F dev g_a)(F dev g_b)^T, N = I/3 + sqrt(2/3) dev/|dev|  (rare path)
+                const double dm[9] = {dvv[0], dvv[1], dvv[2], dvv[1], dvv[3], dvv[4], dvv[2], dvv[4], dvv[5]};
+                double FD[9];
+#pragma unroll
+                for (int r = 0; r < 3; r++)
+#pragma unroll
+                    for (int c = 0; c < 3; c++) FD[3 * r + c] = F[3 * r] * dm[c] + F[3 * r + 1] * dm[3 + c] + F[3 * r + 2] * dm[6 + c];
+                const double s23d = sqrt(2.0 / 3.0) * dn_inv;
+                double d[12], nn[12];
+#pragma unroll
+                for (int n = 0; n < 4; n++)
+#pragma unroll
+                    for (int r = 0; r < 3; r++) {
+                        d[3 * n + r] = FD[3 * r] * G[3 * n] + FD[3 * r + 1] * G[3 * n + 1] + FD[3 * r + 2] * G[3 * n + 2];
+                        nn[3 * n + r] = w[3 * n + r] / 3.0 + s23d * d[3 * n + r];
+                    }
+                const double hN = hs * cN, hD = hs * cD;
+#pragma unroll
+                for (int i = 0; i < 12; i++)
+#pragma unroll
+                    for (int j = 0; j < 12; j++) sH[i * 12 + j] += hN * nn[i] * nn[j] + hD * d[i] * d[j];
+            }
+        }
+
+        // ---- this element's 1,152 B leave through the TMA engine ----
+        double* dstH = a.H + (size_t)e * 144;
+        if (bulk_ok) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the async proxy
+            if (live) {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dstH), "r"(sH_addr), "r"(144 * 8) : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            store_pending = true;
+        } else if (live) {
+#pragma unroll 1
+            for (int k = 0; k < 144; k++) dstH[k] = sH[k];
         }
     }
+    if (store_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 template<bool COMPLETE> static void launch_tet_analytic_pgh(const EvalArgs& a, cudaStream_t s)
 {
-    const int grid = (a.n_elem + TET_ELEMS - 1) / TET_ELEMS;
-    k_tet_analytic<COMPLETE><<<grid, TET_THREADS, 0, s>>>(a);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(k_tet_analytic<COMPLETE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TET_SMEM_BYTES);
+        configured = true;
+    }
+    TetParams P;
+    P.a = a;
+    const int nin = COMPLETE ? 43 : 40;
+    for (int i = 0; i < nin; i++) P.slot[i] = a.slots_host[i];
+    const int n_tiles = (a.n_elem + TET_TILE - 1) / TET_TILE;
+    const int ctas_needed = (n_tiles + TET_WARPS - 1) / TET_WARPS;
+    const int grid = ctas_needed < 148 * 3 ? ctas_needed : 148 * 3;   // persistent: 3 CTAs per SM
+    k_tet_analytic<COMPLETE><<<grid, TET_THREADS, TET_SMEM_BYTES, s>>>(P);
 }
 
 }  // namespace sb
