@@ -25,12 +25,15 @@ class Golden:
             yield i, p
 
 
-def bind(ctx, g, kernel_names, rename=None, skip=()):
-    """Returns {reference potential index: context potential handle}."""
+def bind(ctx, g, kernel_names, rename=None, skip=(), override=None, split_fetch=None):
+    """Returns {reference potential index: context potential handle}.
+    override: {array index: replacement data}; split_fetch: (potential name, first_symbol) whose binding gets its own
+    copy of the array (same values, different device buffer -- exercises non-canonical fetch tables)."""
     rename = rename or {}
+    override = override or {}
     arrays = {}
     for i, a in enumerate(g.meta["arrays"]):
-        arrays[i] = ctx.array(f"a{i}", a["stride"], g[f"array{i}"])
+        arrays[i] = ctx.array(f"a{i}", a["stride"], override.get(i, g[f"array{i}"]))
     ids = [a["id"] for a in g.meta["arrays"]]
     for did in g.meta["dof_array_ids"]:
         ctx.dof_add(arrays[ids.index(did)])
@@ -40,6 +43,11 @@ def bind(ctx, g, kernel_names, rename=None, skip=()):
         if name not in kernel_names or p["name"] in skip:
             continue
         fetch = [(arrays[m["array"]], m["conn_idx"], m["first_symbol"], m["stride"]) for m in p["maps"]]
+        if split_fetch and split_fetch[0] == p["name"]:
+            for k, m in enumerate(p["maps"]):
+                if m["first_symbol"] == split_fetch[1]:
+                    dup = ctx.array(f"dup{i}_{k}", m["stride"], override.get(m["array"], g[f"array{m['array']}"]))
+                    fetch[k] = (dup, m["conn_idx"], m["first_symbol"], m["stride"])
         h = ctx.potential(name, p["conn_stride"], fetch)
         conn = g[f"pot{i}_conn"]
         active = g[f"pot{i}_active"].astype(bool)

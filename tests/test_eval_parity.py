@@ -84,3 +84,45 @@ def test_tet_ad_and_analytic_kernels_agree():
     assert (np.abs(a[:, 13:] - b[:, 13:]) / scale).max() < 1e-11
     ctx.close()
     ctx2.close()
+
+
+def _tet_arrays(g, idx):
+    """array index bound at each first_symbol of the tet potential"""
+    return {m["first_symbol"]: m["array"] for m in g.meta["potentials"][idx]["maps"]}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["damping", "limit", "damping+limit", "split_fetch"])
+def test_tet_analytic_rare_terms_match_ad(case):
+    """Strain-rate damping and strain-limit terms (EnergyTetStrain.cpp:62-72) are zero in the golden scenes; switch them
+    on, deform the mesh, and hold the hand-derived kernel to the AD kernel (itself pinned to the reference above).
+    'split_fetch' binds one node's x0 through a separate buffer, which takes the kernel's generic gather path."""
+    capi, _ = _ctx()
+    g = Golden("tetdrop_n5")
+    idx = [i for i, p in g.potentials() if p["name"] == "EnergyTetStrain"][0]
+    sym = _tet_arrays(g, idx)
+    rng = np.random.default_rng(7)
+    override = {}
+    v1 = np.array(g[f"array{sym[0]}"], dtype=np.float64, copy=True)
+    override[sym[0]] = v1 + rng.uniform(-3.0, 3.0, v1.shape)          # dt = 0.01 -> a few % of strain
+    if "damping" in case:
+        override[sym[41]] = np.full_like(g[f"array{sym[41]}"], 0.37)
+    if "limit" in case:
+        override[sym[39]] = np.full_like(g[f"array{sym[39]}"], -0.02)  # below the rest state: active in every element
+        override[sym[40]] = np.full_like(g[f"array{sym[40]}"], 5.0e3)
+    split = ("EnergyTetStrain", 18) if case == "split_fetch" else None
+    out = []
+    for rename in (None, {"EnergyTetStrain": "EnergyTetStrain_AD"}):
+        ctx = capi.Context(0)
+        h = bind(ctx, g, set(capi.kernel_names()), rename=rename, override=override, split_fetch=split if rename is None else None)
+        E, res = ctx.eval("PGH")
+        out.append((E, ctx.grad(), ctx.element_output(h[idx])))
+        ctx.close()
+    (E1, g1, a), (E2, g2, b) = out
+    assert abs(E1 - E2) <= 1e-12 * abs(E2)
+    assert np.abs(g1 - g2).max() <= 1e-11 * np.abs(g2).max()
+    np.testing.assert_allclose(a[:, 0], b[:, 0], rtol=1e-11, atol=1e-11 * np.abs(b[:, 0]).max())
+    gs = np.abs(b[:, 1:13]).max(axis=1, keepdims=True)
+    assert (np.abs(a[:, 1:13] - b[:, 1:13]) / gs).max() < 1e-11
+    hs = np.linalg.norm(b[:, 13:], axis=1, keepdims=True)
+    assert (np.abs(a[:, 13:] - b[:, 13:]) / hs).max() < 1e-11
