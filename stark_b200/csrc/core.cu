@@ -282,7 +282,7 @@ int sb_profile_stages(sb_context* ctx, int enable)
 const char* sb_profile_report(sb_context* ctx)
 {
     if (!ctx) return "";
-    static const char* names[ST_COUNT] = {"contact_update", "intersections", "eval_pgh", "eval_p", "project_to_pd", "assembly_symbolic", "assembly_numeric", "pcg", "line_search_misc"};
+    static const char* names[ST_COUNT] = {"contact_update", "intersections", "eval_pgh", "eval_p", "project_to_pd", "assembly_symbolic", "assembly_numeric", "pcg", "line_search_misc", "cg_iterations"};
     ctx->profile_report.clear();
     for (int i = 0; i < ST_COUNT; i++)
         ctx->profile_report += std::string(names[i]) + " " + std::to_string(ctx->stage_ms[i]) + " " + std::to_string(ctx->stage_calls[i]) + "\n";

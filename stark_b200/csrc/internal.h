@@ -112,7 +112,7 @@ struct Potential {
 };
 
 // Stage profiling (sb_profile_stages): host wall time between two stream synchronisations, accumulated per stage.
-enum Stage { ST_CONTACT_UPDATE, ST_INTERSECTIONS, ST_EVAL_PGH, ST_EVAL_P, ST_PROJECT, ST_ASM_SYMBOLIC, ST_ASM_NUMERIC, ST_PCG, ST_LINE_SEARCH_MISC, ST_COUNT };
+enum Stage { ST_CONTACT_UPDATE, ST_INTERSECTIONS, ST_EVAL_PGH, ST_EVAL_P, ST_PROJECT, ST_ASM_SYMBOLIC, ST_ASM_NUMERIC, ST_PCG, ST_LINE_SEARCH_MISC, ST_CG_ITERATIONS /* calls = iterations, ms unused */, ST_COUNT };
 struct StageTimer {
     sb_context* ctx;
     int stage;

@@ -5,49 +5,71 @@
 // bsm/bsm_vector_ops.h.  Same recurrence, same stopping rules (zero RHS, error < abs_tol, error/error_0 < rel_tol,
 // p^T A p <= 0 -> "indefinite", max_iter), same float-storage / double-accumulate arithmetic.
 //
-// The whole working set (matrix ~20 MB at the 200k-tet scene + 6 vectors) lives in the 126 MB L2, so an iteration is
-// bound by launch + reduction latency, not HBM.  Every iteration is therefore three fused kernels whose scalars
-// (alpha, beta, error, flags) never leave the device: each CTA re-reduces the fixed-size partial-sum arrays it needs,
-// and the host only reads the status word once per batch of iterations.  The fixed grid makes all dot products
-// bitwise reproducible run to run (the reference's are thread-count dependent, bsm/ParallelNumber.h:39-47).
+// The ENTIRE solve is ONE persistent cooperative kernel, one 1024-thread CTA per SM.  CTA c owns a contiguous range of
+// block rows holding ~nnzb / #SM blocks and copies ITS SLICE OF THE MATRIX (values, columns, row pointers) and of the
+// vectors x, r, z, Ap, M^-1 INTO SHARED MEMORY ONCE: at the 200k-tet scene the 21.7 MB matrix is spread over the 148 x
+// 227 KB of shared memory of the chip and is never read from L2 / HBM again during the solve; the only global traffic of
+// an iteration is the gather of p (0.9 MB, L2) and each CTA's own slice of p written back.  Slices that do not fit
+// (million-tet scenes) are streamed from global memory by the same code through generic pointers, per CTA.
+// Phases are separated by a grid-wide barrier (one atomic counter, acquire spin), three per iteration.  Dot products go
+// through per-CTA partial sums that every CTA re-reduces in the same fixed order, so alpha, beta, the error and every
+// stopping decision are computed redundantly but IDENTICALLY everywhere (no broadcast; bitwise reproducible run to run --
+// the reference's are thread-count dependent, bsm/ParallelNumber.h:39-47).  The host launches once and reads one record.
 #include "internal.h"
+#include <algorithm>
 
 namespace sb {
 
 int bcsr_view(sb_context* ctx, int* nbr, size_t* nnzb, const unsigned long long** rows, const int32_t** cols, const float** vals);
 
-constexpr int PCG_BLOCKS = 296;    // 2 CTAs per SM on 148 SMs
-constexpr int PCG_THREADS = 256;
-constexpr int LANES_PER_ROW = 8;   // lanes cooperating on one block row of the SpMV
-constexpr int PCG_BATCH = 6;       // iterations launched between two host reads of the status word
+constexpr int PCG_THREADS = 1024;     // one CTA per SM
+constexpr int PCG_MAX_BLOCKS = 1024;  // upper bound of the cooperative grid (partial-sum arrays)
+constexpr int LANES_PER_ROW = 4;      // lanes cooperating on one block row of the SpMV
+constexpr int LONG_ROW = 96;          // rows with more blocks (rigid bodies in contact with many nodes) are swept by the whole CTA
+constexpr int MAX_LONG_ROWS = 32;     // per CTA; further long rows fall back to the 4-lane path
 
-// device-resident solver state
-struct PcgState {
-    double bb;          // ||b||^2
-    double rz;          // r.z of the current iteration
-    double error, error0;
-    double abs_tol, rel_tol;
+struct PcgResult {
+    double du_dot_grad, du_inf, error, bb;
     int it;             // completed iterations
-    int max_iter;
-    int stop_on_indef;
-    int done;           // 0 running, 1 converged, 2 indefinite, 3 max iterations
+    int done;           // 1 converged, 2 indefinite, 3 max iterations
     int found_indef;
     int pad;
+};
+
+struct PcgArgs {
+    const unsigned long long* rows; const int32_t* cols; const float* vals;
+    const double* grad;
+    float* dinv;
+    double *x, *r, *z, *p, *Ap, *du;
+    double* part;          // 3 x PCG_MAX_BLOCKS partial sums
+    int* rp_scratch;       // [nbr + grid + 1] local row pointers of slices whose row pointers do not fit in shared memory
+    unsigned* barrier;     // zeroed before the launch
+    PcgResult* result;
+    int nbr;
+    double abs_tol, rel_tol;
+    int max_iter, stop_on_indef;
+    unsigned long long nnzb;
+    unsigned smem_bytes;   // dynamic shared memory of the launch
 };
 
 struct Pcg {
     DevBuf<double> r, z, p, Ap, x;
     DevBuf<float> dinv;
-    DevBuf<double> part;       // 3 x PCG_BLOCKS partial sums
-    PcgState* d_state = nullptr;
-    PcgState* h_state = nullptr;
+    DevBuf<double> part;
+    DevBuf<int> rp_scratch;
+    unsigned* d_barrier = nullptr;
+    PcgResult* d_result = nullptr;
+    PcgResult* h_result = nullptr;
+    int grid = 0;
+    unsigned smem_bytes = 0;
 };
 static Pcg* get(sb_context* ctx)
 {
     if (!ctx->pcg) {
         ctx->pcg = new Pcg();
-        cudaMalloc(&ctx->pcg->d_state, sizeof(PcgState));
-        cudaMallocHost(&ctx->pcg->h_state, sizeof(PcgState));
+        cudaMalloc(&ctx->pcg->d_barrier, sizeof(unsigned));
+        cudaMalloc(&ctx->pcg->d_result, sizeof(PcgResult));
+        cudaMallocHost(&ctx->pcg->h_result, sizeof(PcgResult));
     }
     return ctx->pcg;
 }
@@ -55,11 +77,29 @@ void pcg_destroy(sb_context* ctx)
 {
     Pcg* P = ctx->pcg;
     if (!P) return;
-    P->r.release(); P->z.release(); P->p.release(); P->Ap.release(); P->x.release(); P->dinv.release(); P->part.release();
-    if (P->d_state) cudaFree(P->d_state);
-    if (P->h_state) cudaFreeHost(P->h_state);
+    P->r.release(); P->z.release(); P->p.release(); P->Ap.release(); P->x.release(); P->dinv.release(); P->part.release(); P->rp_scratch.release();
+    if (P->d_barrier) cudaFree(P->d_barrier);
+    if (P->d_result) cudaFree(P->d_result);
+    if (P->h_result) cudaFreeHost(P->h_result);
     delete P;
     ctx->pcg = nullptr;
+}
+
+// ---- grid-wide barrier: monotonic counter, epoch-th barrier completes when it reaches epoch * gridDim.x ----
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch)
+{
+    __syncthreads();
+    epoch++;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        const unsigned target = epoch * gridDim.x;
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        } while (v < target);
+    }
+    __syncthreads();
 }
 
 // ---- block reductions ------------------------------------------------------------------------------------------
@@ -73,244 +113,330 @@ __device__ __forceinline__ double block_sum(double v, double* s)
     double t = 0.0;
     if (threadIdx.x < PCG_THREADS / 32) t = s[threadIdx.x];
     if (w == 0) {
-        for (int o = 4; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+        for (int o = PCG_THREADS / 64; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
     }
     return t;  // valid in thread 0
 }
-// every CTA sums the same PCG_BLOCKS partials in the same order -> identical value everywhere
-__device__ __forceinline__ double all_partials(const double* __restrict__ part, double* s)
+__device__ __forceinline__ double block_max(double v, double* s)
+{
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) s[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x < PCG_THREADS / 32) t = s[threadIdx.x];
+    if (w == 0) {
+        for (int o = PCG_THREADS / 64; o > 0; o >>= 1) t = fmax(t, __shfl_down_sync(0xffffffffu, t, o));
+    }
+    return t;  // valid in thread 0
+}
+// every CTA sums the same gridDim.x partials in the same order -> identical value everywhere
+__device__ __forceinline__ double all_partials(const double* part, double* s, double* bc)
 {
     double v = 0.0;
-    for (int i = threadIdx.x; i < PCG_BLOCKS; i += PCG_THREADS) v += part[i];
+    for (int i = threadIdx.x; i < gridDim.x; i += PCG_THREADS) v += __ldcg(part + i);
     const double t = block_sum(v, s);
-    __shared__ double bc;
-    if (threadIdx.x == 0) bc = t;
+    if (threadIdx.x == 0) *bc = t;
     __syncthreads();
-    return bc;
+    return *bc;
 }
-
-// closed-form inverse of the symmetric 3x3 diagonal block, in float like the reference (BlockedSparseMatrix.h:1198-1214)
-__global__ void k_block_jacobi(const unsigned long long* __restrict__ rows, const int32_t* __restrict__ cols, const float* __restrict__ vals,
-                               float* __restrict__ dinv, int nbr)
+__device__ __forceinline__ double all_partials_max(const double* part, double* s, double* bc)
 {
-    const int br = blockIdx.x * blockDim.x + threadIdx.x;
-    if (br >= nbr) return;
-    float* mi = dinv + 9 * (size_t)br;
-    for (int k = 0; k < 9; k++) mi[k] = 0.0f;
-    for (unsigned long long j = rows[br]; j < rows[br + 1]; j++) {
-        if (cols[j] == 3 * br) {
-            const float* m = vals + 9 * j;
-            const float tmp0 = m[4] * m[8];
-            const float tmp1 = m[5] * m[5];
-            const float tmp2 = m[2] * m[5];
-            const float tmp3 = m[1] * m[1];
-            const float tmp4 = m[2] * m[2];
-            const float tmp5 = (float)(1.0 / (double)(m[0] * tmp0 - m[0] * tmp1 + 2 * m[1] * tmp2 - m[4] * tmp4 - m[8] * tmp3));
-            mi[8] = tmp5 * (m[0] * m[4] - tmp3);
-            mi[4] = tmp5 * (m[0] * m[8] - tmp4);
-            mi[0] = tmp5 * (tmp0 - tmp1);
-            mi[3] = -tmp5 * (m[1] * m[8] - tmp2);
-            mi[1] = mi[3];
-            mi[6] = tmp5 * (m[1] * m[5] - m[4] * m[2]);
-            mi[2] = mi[6];
-            mi[7] = -tmp5 * (m[0] * m[5] - m[1] * m[2]);
-            mi[5] = mi[7];
-            break;
-        }
-    }
+    double v = 0.0;
+    for (int i = threadIdx.x; i < gridDim.x; i += PCG_THREADS) v = fmax(v, __ldcg(part + i));
+    const double t = block_max(v, s);
+    if (threadIdx.x == 0) *bc = t;
+    __syncthreads();
+    return *bc;
 }
 
-__device__ __forceinline__ void apply_dinv(const float* __restrict__ d, double r0, double r1, double r2, double& z0, double& z1, double& z2)
+__device__ __forceinline__ void apply_dinv(const float* d, double r0, double r1, double r2, double& z0, double& z1, double& z2)
 {
     z0 = (double)d[0] * r0 + (double)d[1] * r1 + (double)d[2] * r2;
     z1 = (double)d[3] * r0 + (double)d[4] * r1 + (double)d[5] * r2;
     z2 = (double)d[6] * r0 + (double)d[7] * r1 + (double)d[8] * r2;
 }
 
-// x = 0, r = b = -grad, z = M^-1 r, p = z ; partials of b.b and r.z
-__global__ void __launch_bounds__(PCG_THREADS) k_pcg_init(const double* __restrict__ grad, const float* __restrict__ dinv,
-                                                            double* __restrict__ x, double* __restrict__ r, double* __restrict__ z, double* __restrict__ p,
-                                                            double* __restrict__ part, int nbr)
+// first row r in [0, nbr] with rows[r] >= t
+__device__ __forceinline__ int row_lower_bound(const unsigned long long* __restrict__ rows, int nbr, unsigned long long t)
 {
-    __shared__ double s[PCG_THREADS / 32];
-    double bb = 0.0, rz = 0.0;
-    for (int br = blockIdx.x * PCG_THREADS + threadIdx.x; br < nbr; br += PCG_BLOCKS * PCG_THREADS) {
-        const double r0 = -grad[3 * br], r1 = -grad[3 * br + 1], r2 = -grad[3 * br + 2];
-        double z0, z1, z2;
-        apply_dinv(dinv + 9 * (size_t)br, r0, r1, r2, z0, z1, z2);
-        x[3 * br] = 0.0; x[3 * br + 1] = 0.0; x[3 * br + 2] = 0.0;
-        r[3 * br] = r0; r[3 * br + 1] = r1; r[3 * br + 2] = r2;
-        z[3 * br] = z0; z[3 * br + 1] = z1; z[3 * br + 2] = z2;
-        p[3 * br] = z0; p[3 * br + 1] = z1; p[3 * br + 2] = z2;
-        bb += r0 * r0 + r1 * r1 + r2 * r2;
-        rz += r0 * z0 + r1 * z1 + r2 * z2;
+    int lo = 0, hi = nbr;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (rows[mid] < t) lo = mid + 1; else hi = mid;
     }
-    const double t0 = block_sum(bb, s);
-    if (threadIdx.x == 0) part[blockIdx.x] = t0;
-    const double t1 = block_sum(rz, s);
-    if (threadIdx.x == 0) part[PCG_BLOCKS + blockIdx.x] = t1;
-}
-__global__ void __launch_bounds__(PCG_THREADS) k_pcg_init_state(PcgState* st, const double* __restrict__ part, double abs_tol, double rel_tol, int max_iter, int stop_on_indef)
-{
-    __shared__ double s[PCG_THREADS / 32];
-    const double bb = all_partials(part, s);
-    const double rz = all_partials(part + PCG_BLOCKS, s);
-    if (threadIdx.x == 0) {
-        st->bb = bb; st->rz = rz;
-        st->abs_tol = abs_tol; st->rel_tol = rel_tol; st->max_iter = max_iter; st->stop_on_indef = stop_on_indef;
-        st->it = 0; st->found_indef = 0; st->pad = 0;
-        st->error = 1.0; st->error0 = 1.0;   // x0 = 0 -> r = b
-        st->done = 0;
-        if (bb < abs_tol * abs_tol) { st->done = 1; st->error = 0.0; }   // zero right-hand side
-        else if (1.0 < abs_tol) st->done = 1;
-        else if (max_iter <= 0) st->done = 3;
-    }
+    return lo;
 }
 
-// Ap = A p with LANES_PER_ROW lanes per block row; partial of p.Ap
-__global__ void __launch_bounds__(PCG_THREADS) k_pcg_spmv(const PcgState* __restrict__ st, const unsigned long long* __restrict__ rows,
-                                                            const int32_t* __restrict__ cols, const float* __restrict__ vals,
-                                                            const double* __restrict__ p, double* __restrict__ Ap, double* __restrict__ part, int nbr)
+__global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_solve(const PcgArgs A)
 {
+    extern __shared__ __align__(16) unsigned char smem[];
     __shared__ double s[PCG_THREADS / 32];
-    if (st->done) return;
-    const int lane = threadIdx.x % LANES_PER_ROW;
-    const int rows_per_cta = PCG_THREADS / LANES_PER_ROW;
-    double pAp = 0.0;
-    for (int base = blockIdx.x * rows_per_cta; base < nbr; base += PCG_BLOCKS * rows_per_cta) {
-        const int br = base + threadIdx.x / LANES_PER_ROW;
-        double y0 = 0.0, y1 = 0.0, y2 = 0.0;
-        if (br < nbr) {
-            const unsigned long long j1 = rows[br + 1];
-            for (unsigned long long j = rows[br] + lane; j < j1; j += LANES_PER_ROW) {
-                const float* m = vals + 9 * j;   // column-major 3x3
-                const int c = cols[j];
-                const double x0 = p[c], x1 = p[c + 1], x2 = p[c + 2];
-                y0 += (double)m[0] * x0 + (double)m[3] * x1 + (double)m[6] * x2;
-                y1 += (double)m[1] * x0 + (double)m[4] * x1 + (double)m[7] * x2;
-                y2 += (double)m[2] * x0 + (double)m[5] * x1 + (double)m[8] * x2;
+    __shared__ double bc;
+    __shared__ int s_range[2];
+    __shared__ int s_long[MAX_LONG_ROWS];
+    __shared__ int s_n_long;
+    const int G = gridDim.x;
+    const int nbr = A.nbr;
+    const int tid = threadIdx.x;
+    unsigned epoch = 0;
+    double* part0 = A.part;
+    double* part1 = A.part + PCG_MAX_BLOCKS;
+    double* part2 = A.part + 2 * PCG_MAX_BLOCKS;
+
+    // ---- this CTA's rows: [r0, r1), holding blocks [b0, b0 + nb) ----
+    if (tid == 0) {
+        s_range[0] = row_lower_bound(A.rows, nbr, (A.nnzb * blockIdx.x) / G);
+        s_range[1] = (blockIdx.x == G - 1) ? nbr : row_lower_bound(A.rows, nbr, (A.nnzb * (blockIdx.x + 1)) / G);
+    }
+    __syncthreads();
+    const int r0 = s_range[0], nr = s_range[1] - s_range[0];
+    const unsigned long long b0 = A.rows[r0];
+    const int nb = (int)(A.rows[r0 + nr] - b0);
+
+    // ---- shared-memory plan: row pointers always; then the vector slices; then the matrix slice; whatever does not fit
+    //      stays in global memory and is reached through the same (generic) pointers ----
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 15) & ~(size_t)15; return o; };
+    const bool rp_fit = ((sizeof(int) * (nr + 1) + 15) & ~(size_t)15) <= A.smem_bytes;
+    int* rp = rp_fit ? reinterpret_cast<int*>(smem + carve(sizeof(int) * (nr + 1))) : A.rp_scratch + r0 + blockIdx.x;
+    const size_t vec_bytes = 4 * ((sizeof(double) * 3 * nr + 15) & ~(size_t)15) + ((sizeof(float) * 9 * nr + 15) & ~(size_t)15);
+    const bool vec_fit = rp_fit && off + vec_bytes <= A.smem_bytes;
+    double *xs, *rs, *zs, *Aps; float* dinv;
+    if (vec_fit) {
+        xs = reinterpret_cast<double*>(smem + carve(sizeof(double) * 3 * nr));
+        rs = reinterpret_cast<double*>(smem + carve(sizeof(double) * 3 * nr));
+        zs = reinterpret_cast<double*>(smem + carve(sizeof(double) * 3 * nr));
+        Aps = reinterpret_cast<double*>(smem + carve(sizeof(double) * 3 * nr));
+        dinv = reinterpret_cast<float*>(smem + carve(sizeof(float) * 9 * nr));
+    } else {
+        xs = A.x + 3 * (size_t)r0; rs = A.r + 3 * (size_t)r0; zs = A.z + 3 * (size_t)r0; Aps = A.Ap + 3 * (size_t)r0; dinv = A.dinv + 9 * (size_t)r0;
+    }
+    const size_t mat_bytes = ((sizeof(int) * (size_t)nb + 15) & ~(size_t)15) + ((sizeof(float) * 9 * (size_t)nb + 15) & ~(size_t)15);
+    const bool mat_fit = vec_fit && off + mat_bytes <= A.smem_bytes;
+    const int32_t* cols; const float* vals;
+    if (mat_fit) {
+        int32_t* cs = reinterpret_cast<int32_t*>(smem + carve(sizeof(int) * (size_t)nb));
+        float* vs = reinterpret_cast<float*>(smem + carve(sizeof(float) * 9 * (size_t)nb));
+        for (int i = tid; i < nb; i += PCG_THREADS) cs[i] = A.cols[b0 + i];
+        for (int i = tid; i < 9 * nb; i += PCG_THREADS) vs[i] = A.vals[9 * b0 + i];
+        cols = cs; vals = vs;
+    } else {
+        cols = A.cols + b0; vals = A.vals + 9 * b0;
+    }
+    for (int i = tid; i <= nr; i += PCG_THREADS) rp[i] = (int)(A.rows[r0 + i] - b0);
+    if (tid == 0) s_n_long = 0;
+    __syncthreads();
+    for (int i = tid; i < nr; i += PCG_THREADS)
+        if (rp[i + 1] - rp[i] > LONG_ROW) {
+            const int k = atomicAdd(&s_n_long, 1);
+            if (k < MAX_LONG_ROWS) s_long[k] = i;
+        }
+    __syncthreads();
+    const int n_long = min(s_n_long, MAX_LONG_ROWS);
+    auto is_swept = [&](int lr) {   // long AND listed (the list order is irrelevant: every listed row gets its own block reduction)
+        if (rp[lr + 1] - rp[lr] <= LONG_ROW) return false;
+        for (int k = 0; k < n_long; k++) if (s_long[k] == lr) return true;
+        return false;
+    };
+    double* pg = A.p + 3 * (size_t)r0;   // own slice of the global direction vector
+
+    int it = 0, done = 0, found_indef = 0;
+    double error = 1.0;               // x0 = 0 -> r = b
+    const double error0 = 1.0;
+
+    // ---- phase 0: M^-1 = block-Jacobi inverse; x = 0, r = b = -grad, z = M^-1 r, p = z ; partials of b.b and r.z ----
+    {
+        double bb = 0.0, rz = 0.0;
+        for (int lr = tid; lr < nr; lr += PCG_THREADS) {
+            const int br = r0 + lr;
+            // closed-form inverse of the symmetric 3x3 diagonal block, in float like the reference (BlockedSparseMatrix.h:1198-1214)
+            float mi[9];
+            for (int k = 0; k < 9; k++) mi[k] = 0.0f;
+            {   // columns are sorted inside a row: binary search for the diagonal block
+                int lo = rp[lr], hi = rp[lr + 1];
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (cols[mid] < 3 * br) lo = mid + 1; else hi = mid;
+                }
+                if (lo < rp[lr + 1] && cols[lo] == 3 * br) {
+                    const float* m = vals + 9 * (size_t)lo;
+                    const float tmp0 = m[4] * m[8];
+                    const float tmp1 = m[5] * m[5];
+                    const float tmp2 = m[2] * m[5];
+                    const float tmp3 = m[1] * m[1];
+                    const float tmp4 = m[2] * m[2];
+                    const float tmp5 = (float)(1.0 / (double)(m[0] * tmp0 - m[0] * tmp1 + 2 * m[1] * tmp2 - m[4] * tmp4 - m[8] * tmp3));
+                    mi[8] = tmp5 * (m[0] * m[4] - tmp3);
+                    mi[4] = tmp5 * (m[0] * m[8] - tmp4);
+                    mi[0] = tmp5 * (tmp0 - tmp1);
+                    mi[3] = -tmp5 * (m[1] * m[8] - tmp2);
+                    mi[1] = mi[3];
+                    mi[6] = tmp5 * (m[1] * m[5] - m[4] * m[2]);
+                    mi[2] = mi[6];
+                    mi[7] = -tmp5 * (m[0] * m[5] - m[1] * m[2]);
+                    mi[5] = mi[7];
+                }
+            }
+            for (int k = 0; k < 9; k++) dinv[9 * lr + k] = mi[k];
+            const double g0 = -A.grad[3 * br], g1 = -A.grad[3 * br + 1], g2 = -A.grad[3 * br + 2];
+            double z0, z1, z2;
+            apply_dinv(mi, g0, g1, g2, z0, z1, z2);
+            xs[3 * lr] = 0.0; xs[3 * lr + 1] = 0.0; xs[3 * lr + 2] = 0.0;
+            rs[3 * lr] = g0; rs[3 * lr + 1] = g1; rs[3 * lr + 2] = g2;
+            __stcg(pg + 3 * lr, z0); __stcg(pg + 3 * lr + 1, z1); __stcg(pg + 3 * lr + 2, z2);
+            bb += g0 * g0 + g1 * g1 + g2 * g2;
+            rz += g0 * z0 + g1 * z1 + g2 * z2;
+        }
+        const double t0 = block_sum(bb, s);
+        if (tid == 0) __stcg(part0 + blockIdx.x, t0);
+        const double t1 = block_sum(rz, s);
+        if (tid == 0) __stcg(part1 + blockIdx.x, t1);
+    }
+    grid_barrier(A.barrier, epoch);
+    const double bb = all_partials(part0, s, &bc);
+    double rz = all_partials(part1, s, &bc);
+    grid_barrier(A.barrier, epoch);   // part0 / part1 are rewritten below
+
+    if (bb < A.abs_tol * A.abs_tol) { done = 1; error = 0.0; }   // zero right-hand side
+    else if (1.0 < A.abs_tol) done = 1;
+    else if (A.max_iter <= 0) done = 3;
+
+    const int lane = tid % LANES_PER_ROW;
+    constexpr int rows_per_pass = PCG_THREADS / LANES_PER_ROW;
+    while (!done) {
+        // ---- Ap = A p (LANES_PER_ROW lanes per block row; matrix from shared memory, p gathered from L2); partial of p.Ap ----
+        {
+            double pAp = 0.0;
+            for (int base = 0; base < nr; base += rows_per_pass) {
+                const int lr = base + tid / LANES_PER_ROW;
+                double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+                const bool swept = (lr < nr) && is_swept(lr);
+                if (lr < nr && !swept) {
+                    const int j1 = rp[lr + 1];
+                    int j = rp[lr] + lane;
+                    // two blocks per trip: their six gathers of p are in flight together
+                    for (; j + LANES_PER_ROW < j1; j += 2 * LANES_PER_ROW) {
+                        const float* m = vals + 9 * (size_t)j;
+                        const float* n = m + 9 * LANES_PER_ROW;
+                        const int ca = cols[j], cb = cols[j + LANES_PER_ROW];
+                        const double a0 = __ldcg(A.p + ca), a1 = __ldcg(A.p + ca + 1), a2 = __ldcg(A.p + ca + 2);
+                        const double b0v = __ldcg(A.p + cb), b1 = __ldcg(A.p + cb + 1), b2 = __ldcg(A.p + cb + 2);
+                        y0 += (double)m[0] * a0 + (double)m[3] * a1 + (double)m[6] * a2;
+                        y1 += (double)m[1] * a0 + (double)m[4] * a1 + (double)m[7] * a2;
+                        y2 += (double)m[2] * a0 + (double)m[5] * a1 + (double)m[8] * a2;
+                        y0 += (double)n[0] * b0v + (double)n[3] * b1 + (double)n[6] * b2;
+                        y1 += (double)n[1] * b0v + (double)n[4] * b1 + (double)n[7] * b2;
+                        y2 += (double)n[2] * b0v + (double)n[5] * b1 + (double)n[8] * b2;
+                    }
+                    if (j < j1) {
+                        const float* m = vals + 9 * (size_t)j;
+                        const int ca = cols[j];
+                        const double a0 = __ldcg(A.p + ca), a1 = __ldcg(A.p + ca + 1), a2 = __ldcg(A.p + ca + 2);
+                        y0 += (double)m[0] * a0 + (double)m[3] * a1 + (double)m[6] * a2;
+                        y1 += (double)m[1] * a0 + (double)m[4] * a1 + (double)m[7] * a2;
+                        y2 += (double)m[2] * a0 + (double)m[5] * a1 + (double)m[8] * a2;
+                    }
+                }
+                for (int o = LANES_PER_ROW / 2; o > 0; o >>= 1) {
+                    y0 += __shfl_down_sync(0xffffffffu, y0, o, LANES_PER_ROW);
+                    y1 += __shfl_down_sync(0xffffffffu, y1, o, LANES_PER_ROW);
+                    y2 += __shfl_down_sync(0xffffffffu, y2, o, LANES_PER_ROW);
+                }
+                if (lane == 0 && lr < nr && !swept) {
+                    Aps[3 * lr] = y0; Aps[3 * lr + 1] = y1; Aps[3 * lr + 2] = y2;
+                    pAp += __ldcg(pg + 3 * lr) * y0 + __ldcg(pg + 3 * lr + 1) * y1 + __ldcg(pg + 3 * lr + 2) * y2;
+                }
+            }
+            // long rows: one block per thread and trip, block-wide reduction (fixed tree: deterministic)
+            for (int k = 0; k < n_long; k++) {
+                const int lr = s_long[k];
+                double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+                for (int j = rp[lr] + tid; j < rp[lr + 1]; j += PCG_THREADS) {
+                    const float* m = vals + 9 * (size_t)j;
+                    const int ca = cols[j];
+                    const double a0 = __ldcg(A.p + ca), a1 = __ldcg(A.p + ca + 1), a2 = __ldcg(A.p + ca + 2);
+                    y0 += (double)m[0] * a0 + (double)m[3] * a1 + (double)m[6] * a2;
+                    y1 += (double)m[1] * a0 + (double)m[4] * a1 + (double)m[7] * a2;
+                    y2 += (double)m[2] * a0 + (double)m[5] * a1 + (double)m[8] * a2;
+                }
+                y0 = block_sum(y0, s); y1 = block_sum(y1, s); y2 = block_sum(y2, s);
+                if (tid == 0) {
+                    Aps[3 * lr] = y0; Aps[3 * lr + 1] = y1; Aps[3 * lr + 2] = y2;
+                    pAp += __ldcg(pg + 3 * lr) * y0 + __ldcg(pg + 3 * lr + 1) * y1 + __ldcg(pg + 3 * lr + 2) * y2;
+                }
+            }
+            const double t = block_sum(pAp, s);   // (its __syncthreads also publish Aps to the update phase below)
+            if (tid == 0) __stcg(part0 + blockIdx.x, t);
+        }
+        grid_barrier(A.barrier, epoch);
+        const double pAp = all_partials(part0, s, &bc);
+        it++;
+        if (pAp <= 0.0) {
+            found_indef = 1;
+            if (A.stop_on_indef) { done = 2; break; }   // x is returned as is (solve_pcg.h:183-192)
+        }
+        // ---- alpha = rz / pAp ; x += alpha p ; r -= alpha Ap ; z = M^-1 r ; partials of r.r and r.z (all in shared memory) ----
+        const double alpha = rz / pAp;
+        {
+            double rr = 0.0, rzn = 0.0;
+            for (int lr = tid; lr < nr; lr += PCG_THREADS) {
+                double q0 = rs[3 * lr], q1 = rs[3 * lr + 1], q2 = rs[3 * lr + 2];
+                xs[3 * lr] += alpha * __ldcg(pg + 3 * lr); xs[3 * lr + 1] += alpha * __ldcg(pg + 3 * lr + 1); xs[3 * lr + 2] += alpha * __ldcg(pg + 3 * lr + 2);
+                q0 -= alpha * Aps[3 * lr]; q1 -= alpha * Aps[3 * lr + 1]; q2 -= alpha * Aps[3 * lr + 2];
+                rs[3 * lr] = q0; rs[3 * lr + 1] = q1; rs[3 * lr + 2] = q2;
+                double z0, z1, z2;
+                apply_dinv(dinv + 9 * lr, q0, q1, q2, z0, z1, z2);
+                zs[3 * lr] = z0; zs[3 * lr + 1] = z1; zs[3 * lr + 2] = z2;
+                rr += q0 * q0 + q1 * q1 + q2 * q2;
+                rzn += q0 * z0 + q1 * z1 + q2 * z2;
+            }
+            const double t0 = block_sum(rr, s);
+            if (tid == 0) __stcg(part1 + blockIdx.x, t0);
+            const double t1 = block_sum(rzn, s);
+            if (tid == 0) __stcg(part2 + blockIdx.x, t1);
+        }
+        grid_barrier(A.barrier, epoch);
+        const double rr = all_partials(part1, s, &bc);
+        error = sqrt(rr / bb);
+        if (error < A.abs_tol || error / error0 < A.rel_tol) { done = 1; break; }
+        const double rz_new = all_partials(part2, s, &bc);
+        const double beta = rz_new / rz;
+        rz = rz_new;
+        if (it >= A.max_iter) { done = 3; break; }
+        // ---- p = z + beta p on the own slice (same thread <-> row mapping as the update phase) ----
+        for (int lr = tid; lr < nr; lr += PCG_THREADS)
+            for (int c = 0; c < 3; c++) __stcg(pg + 3 * lr + c, zs[3 * lr + c] + beta * __ldcg(pg + 3 * lr + c));
+        grid_barrier(A.barrier, epoch);
+    }
+
+    // ---- du = x ; du.grad and |du|_inf ----
+    {
+        double dg = 0.0, mx = 0.0;
+        for (int lr = tid; lr < nr; lr += PCG_THREADS) {
+            for (int c = 0; c < 3; c++) {
+                const double v = xs[3 * lr + c];
+                A.du[3 * (size_t)(r0 + lr) + c] = v;
+                dg += v * A.grad[3 * (size_t)(r0 + lr) + c];
+                mx = fmax(mx, fabs(v));
             }
         }
-        for (int o = LANES_PER_ROW / 2; o > 0; o >>= 1) {
-            y0 += __shfl_down_sync(0xffffffffu, y0, o, LANES_PER_ROW);
-            y1 += __shfl_down_sync(0xffffffffu, y1, o, LANES_PER_ROW);
-            y2 += __shfl_down_sync(0xffffffffu, y2, o, LANES_PER_ROW);
+        const double t0 = block_sum(dg, s);
+        const double t1 = block_max(mx, s);
+        grid_barrier(A.barrier, epoch);   // CTAs that left the loop one reduction behind may still be reading the partial arrays
+        if (tid == 0) { __stcg(part0 + blockIdx.x, t0); __stcg(part1 + blockIdx.x, t1); }
+    }
+    grid_barrier(A.barrier, epoch);
+    if (blockIdx.x == 0) {
+        const double dg = all_partials(part0, s, &bc);
+        const double mx = all_partials_max(part1, s, &bc);
+        if (tid == 0) {
+            PcgResult R;
+            R.du_dot_grad = dg; R.du_inf = mx; R.error = error; R.bb = bb;
+            R.it = it; R.done = done; R.found_indef = found_indef; R.pad = 0;
+            *A.result = R;
         }
-        if (lane == 0 && br < nbr) {
-            Ap[3 * br] = y0; Ap[3 * br + 1] = y1; Ap[3 * br + 2] = y2;
-            pAp += p[3 * br] * y0 + p[3 * br + 1] * y1 + p[3 * br + 2] * y2;
-        }
-    }
-    const double t = block_sum(pAp, s);
-    if (threadIdx.x == 0) part[blockIdx.x] = t;
-}
-
-// alpha = rz / pAp ; x += alpha p ; r -= alpha Ap ; z = M^-1 r ; partials of r.r and r.z
-__global__ void __launch_bounds__(PCG_THREADS) k_pcg_update(const PcgState* __restrict__ st, const float* __restrict__ dinv,
-                                                              const double* __restrict__ p, const double* __restrict__ Ap,
-                                                              double* __restrict__ x, double* __restrict__ r, double* __restrict__ z,
-                                                              double* __restrict__ part, int nbr)
-{
-    __shared__ double s[PCG_THREADS / 32];
-    if (st->done) return;
-    const double pAp = all_partials(part, s);
-    if (pAp <= 0.0 && st->stop_on_indef) return;   // x is returned as is (solve_pcg.h:183-192); k_pcg_direction records the status
-    const double alpha = st->rz / pAp;
-    double rr = 0.0, rz = 0.0;
-    for (int br = blockIdx.x * PCG_THREADS + threadIdx.x; br < nbr; br += PCG_BLOCKS * PCG_THREADS) {
-        double r0 = r[3 * br], r1 = r[3 * br + 1], r2 = r[3 * br + 2];
-        x[3 * br] += alpha * p[3 * br]; x[3 * br + 1] += alpha * p[3 * br + 1]; x[3 * br + 2] += alpha * p[3 * br + 2];
-        r0 -= alpha * Ap[3 * br]; r1 -= alpha * Ap[3 * br + 1]; r2 -= alpha * Ap[3 * br + 2];
-        r[3 * br] = r0; r[3 * br + 1] = r1; r[3 * br + 2] = r2;
-        double z0, z1, z2;
-        apply_dinv(dinv + 9 * (size_t)br, r0, r1, r2, z0, z1, z2);
-        z[3 * br] = z0; z[3 * br + 1] = z1; z[3 * br + 2] = z2;
-        rr += r0 * r0 + r1 * r1 + r2 * r2;
-        rz += r0 * z0 + r1 * z1 + r2 * z2;
-    }
-    const double t0 = block_sum(rr, s);
-    if (threadIdx.x == 0) part[PCG_BLOCKS + blockIdx.x] = t0;
-    const double t1 = block_sum(rz, s);
-    if (threadIdx.x == 0) part[2 * PCG_BLOCKS + blockIdx.x] = t1;
-}
-
-// convergence tests, beta = rz_new / rz_old, p = z + beta p.  CTA 0 publishes the new state AFTER every CTA has read
-// the old one: the state update is deferred to a tiny follow-up kernel so there is no intra-kernel race.
-__global__ void __launch_bounds__(PCG_THREADS) k_pcg_direction(const PcgState* __restrict__ st, const double* __restrict__ z, double* __restrict__ p,
-                                                                 const double* __restrict__ part, int nbr)
-{
-    __shared__ double s[PCG_THREADS / 32];
-    if (st->done) return;
-    const double pAp = all_partials(part, s);
-    if (pAp <= 0.0 && st->stop_on_indef) return;
-    const double rr = all_partials(part + PCG_BLOCKS, s);
-    const double error = sqrt(rr / st->bb);
-    if (error < st->abs_tol || error / st->error0 < st->rel_tol) return;   // converged: p is not needed any more
-    const double rz_new = all_partials(part + 2 * PCG_BLOCKS, s);
-    const double beta = rz_new / st->rz;
-    for (int i = blockIdx.x * PCG_THREADS + threadIdx.x; i < 3 * nbr; i += PCG_BLOCKS * PCG_THREADS) p[i] = z[i] + beta * p[i];
-}
-__global__ void __launch_bounds__(PCG_THREADS) k_pcg_advance(PcgState* st, const double* __restrict__ part)
-{
-    __shared__ double s[PCG_THREADS / 32];
-    if (st->done) return;
-    const double pAp = all_partials(part, s);
-    const double rr = all_partials(part + PCG_BLOCKS, s);
-    const double rz_new = all_partials(part + 2 * PCG_BLOCKS, s);
-    if (threadIdx.x != 0) return;
-    const int it = st->it + 1;
-    st->it = it;
-    if (pAp <= 0.0) {
-        st->found_indef = 1;
-        if (st->stop_on_indef) { st->done = 2; return; }
-    }
-    const double error = sqrt(rr / st->bb);
-    st->error = error;
-    if (error < st->abs_tol || error / st->error0 < st->rel_tol) { st->done = 1; return; }
-    st->rz = rz_new;
-    if (it >= st->max_iter) st->done = 3;
-}
-
-// du = x ; partials of du.grad and |du|_inf
-__global__ void __launch_bounds__(PCG_THREADS) k_pcg_finish(const double* __restrict__ x, const double* __restrict__ grad, double* __restrict__ du,
-                                                              double* __restrict__ part, int n)
-{
-    __shared__ double s[PCG_THREADS / 32];
-    double dg = 0.0, mx = 0.0;
-    for (int i = blockIdx.x * PCG_THREADS + threadIdx.x; i < n; i += PCG_BLOCKS * PCG_THREADS) {
-        const double v = x[i];
-        du[i] = v;
-        dg += v * grad[i];
-        mx = fmax(mx, fabs(v));
-    }
-    const double t = block_sum(dg, s);
-    if (threadIdx.x == 0) part[blockIdx.x] = t;
-    // max via the same tree (values are non-negative)
-    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, o));
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = mx;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double m = 0.0;
-        for (int w = 0; w < PCG_THREADS / 32; w++) m = fmax(m, s[w]);
-        part[PCG_BLOCKS + blockIdx.x] = m;
-    }
-}
-__global__ void __launch_bounds__(PCG_THREADS) k_pcg_finish2(const double* __restrict__ part, double* __restrict__ out)
-{
-    __shared__ double s[PCG_THREADS / 32];
-    const double dg = all_partials(part, s);
-    double mx = 0.0;
-    for (int i = threadIdx.x; i < PCG_BLOCKS; i += PCG_THREADS) mx = fmax(mx, part[PCG_BLOCKS + i]);
-    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, o));
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = mx;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double m = 0.0;
-        for (int w = 0; w < PCG_THREADS / 32; w++) m = fmax(m, s[w]);
-        out[0] = dg;
-        out[1] = m;
     }
 }
 
@@ -326,36 +452,42 @@ int solve_pcg_internal(sb_context* ctx, double abs_tol, double rel_tol, int max_
     cudaStream_t st = ctx->stream;
     const int n = ctx->ndofs;
     P->r.ensure(n); P->z.ensure(n); P->p.ensure(n); P->Ap.ensure(n); P->x.ensure(n); P->dinv.ensure(9 * (size_t)nbr);
-    P->part.ensure(3 * PCG_BLOCKS);
+    P->part.ensure(3 * PCG_MAX_BLOCKS);
+    P->rp_scratch.ensure((size_t)nbr + PCG_MAX_BLOCKS + 1);
     ctx->du.ensure(n);
-
-    k_block_jacobi<<<(nbr + 255) / 256, 256, 0, st>>>(rows, cols, vals, P->dinv.p, nbr);
-    k_pcg_init<<<PCG_BLOCKS, PCG_THREADS, 0, st>>>(ctx->grad.p, P->dinv.p, P->x.p, P->r.p, P->z.p, P->p.p, P->part.p, nbr);
-    k_pcg_init_state<<<1, PCG_THREADS, 0, st>>>(P->d_state, P->part.p, abs_tol, rel_tol, max_iter, stop_on_indef);
-    ctx->launches += 3;
-    int launched = 0;
-    while (true) {
-        for (int b = 0; b < PCG_BATCH && launched < max_iter; b++, launched++) {
-            k_pcg_spmv<<<PCG_BLOCKS, PCG_THREADS, 0, st>>>(P->d_state, rows, cols, vals, P->p.p, P->Ap.p, P->part.p, nbr);
-            k_pcg_update<<<PCG_BLOCKS, PCG_THREADS, 0, st>>>(P->d_state, P->dinv.p, P->p.p, P->Ap.p, P->x.p, P->r.p, P->z.p, P->part.p, nbr);
-            k_pcg_direction<<<PCG_BLOCKS, PCG_THREADS, 0, st>>>(P->d_state, P->z.p, P->p.p, P->part.p, nbr);
-            k_pcg_advance<<<1, PCG_THREADS, 0, st>>>(P->d_state, P->part.p);
-            ctx->launches += 4;
-        }
-        SB_CUDA(ctx, cudaMemcpyAsync(P->h_state, P->d_state, sizeof(PcgState), cudaMemcpyDeviceToHost, st));
-        SB_CUDA(ctx, cudaStreamSynchronize(st));
-        if (P->h_state->done || launched >= max_iter) break;
+    if (P->grid == 0) {
+        int dev = 0, sms = 0, coop = 0, occ = 0, smem_max = 0;
+        SB_CUDA(ctx, cudaGetDevice(&dev));
+        SB_CUDA(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        SB_CUDA(ctx, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+        SB_CUDA(ctx, cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        if (!coop) return fail(ctx, SB_ERR_CUDA, "sb_solve_pcg: the device does not support cooperative launches");
+        cudaFuncAttributes fa;
+        SB_CUDA(ctx, cudaFuncGetAttributes(&fa, k_pcg_solve));
+        P->smem_bytes = (unsigned)(smem_max - (int)fa.sharedSizeBytes - 1024);
+        SB_CUDA(ctx, cudaFuncSetAttribute(k_pcg_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem_bytes));
+        SB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pcg_solve, PCG_THREADS, P->smem_bytes));
+        if (occ < 1) return fail(ctx, SB_ERR_CUDA, "sb_solve_pcg: the persistent kernel does not fit on an SM");
+        P->grid = std::min(sms, PCG_MAX_BLOCKS);
     }
-    k_pcg_finish<<<PCG_BLOCKS, PCG_THREADS, 0, st>>>(P->x.p, ctx->grad.p, ctx->du.p, P->part.p, n);
-    k_pcg_finish2<<<1, PCG_THREADS, 0, st>>>(P->part.p, ctx->d_scalars + 2);
-    ctx->launches += 2;
-    SB_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars + 2, ctx->d_scalars + 2, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    PcgArgs A;
+    A.rows = rows; A.cols = cols; A.vals = vals; A.grad = ctx->grad.p; A.dinv = P->dinv.p;
+    A.x = P->x.p; A.r = P->r.p; A.z = P->z.p; A.p = P->p.p; A.Ap = P->Ap.p; A.du = ctx->du.p;
+    A.part = P->part.p; A.rp_scratch = P->rp_scratch.p; A.barrier = P->d_barrier; A.result = P->d_result;
+    A.nnzb = nnzb; A.smem_bytes = P->smem_bytes;
+    A.nbr = nbr; A.abs_tol = abs_tol; A.rel_tol = rel_tol; A.max_iter = max_iter; A.stop_on_indef = stop_on_indef;
+    SB_CUDA(ctx, cudaMemsetAsync(P->d_barrier, 0, sizeof(unsigned), st));
+    void* args[] = {(void*)&A};
+    SB_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_pcg_solve, dim3(P->grid), dim3(PCG_THREADS), args, P->smem_bytes, st));
+    ctx->launches += 1;
+    SB_CUDA(ctx, cudaMemcpyAsync(P->h_result, P->d_result, sizeof(PcgResult), cudaMemcpyDeviceToHost, st));
     SB_CUDA(ctx, cudaStreamSynchronize(st));
     SB_CUDA(ctx, cudaGetLastError());
-    if (out_iterations) *out_iterations = P->h_state->it;
-    if (out_ok) *out_ok = (P->h_state->done == 1) ? 1 : 0;
-    if (out_du_dot_grad) *out_du_dot_grad = ctx->h_scalars[2];
-    if (out_du_inf) *out_du_inf = ctx->h_scalars[3];
+    if (ctx->profile) ctx->stage_calls[ST_CG_ITERATIONS] += P->h_result->it;
+    if (out_iterations) *out_iterations = P->h_result->it;
+    if (out_ok) *out_ok = (P->h_result->done == 1) ? 1 : 0;
+    if (out_du_dot_grad) *out_du_dot_grad = P->h_result->du_dot_grad;
+    if (out_du_inf) *out_du_inf = P->h_result->du_inf;
     return 0;
 }
 
