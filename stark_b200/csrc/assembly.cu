@@ -40,6 +40,11 @@ struct Assembly {
     DevBuf<int32_t> cols;            // [nnzb] scalar column
     DevBuf<float> vals;              // [9 nnzb]
     DevBuf<uint8_t> temp;            // cub scratch
+    DevBuf<uint32_t> blk_of_src;     // per source (unsorted numbering): its BCSR block
+    DevBuf<uint8_t> dirty;           // per BCSR block: a source changed since the last numeric pass (PD projection)
+    DevBuf<uint32_t> long_blocks;    // BCSR blocks with more than LONG_SEG sources (rigid bodies touched by many contacts)
+    int* d_n_long = nullptr;
+    uint64_t assembled_eval = 0;     // evaluation the values belong to
     bool numeric_valid = false;
 };
 
@@ -54,7 +59,8 @@ void assembly_destroy(sb_context* ctx)
     if (!A) return;
     A->keys.release(); A->keys_sorted.release(); A->ids.release(); A->ids_sorted.release(); A->src_off.release();
     A->src_pitch.release(); A->sorted_off.release(); A->sorted_pitch.release(); A->head.release(); A->blk_of.release();
-    A->seg.release(); A->blk_row.release(); A->rows.release(); A->cols.release(); A->vals.release(); A->temp.release();
+    A->seg.release(); A->blk_row.release(); A->rows.release(); A->cols.release(); A->vals.release(); A->temp.release(); A->blk_of_src.release(); A->dirty.release(); A->long_blocks.release();
+    if (A->d_n_long) cudaFree(A->d_n_long);
     delete A;
     ctx->assembly = nullptr;
 }
@@ -88,13 +94,14 @@ __global__ void k_heads(const uint64_t* __restrict__ keys, uint32_t* __restrict_
 __global__ void k_fill_pattern(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ head, const uint32_t* __restrict__ blk_of,
                                const uint32_t* __restrict__ ids_sorted, const uint32_t* __restrict__ src_off, const uint8_t* __restrict__ src_pitch,
                                uint32_t* __restrict__ sorted_off, uint8_t* __restrict__ sorted_pitch,
-                               uint32_t* __restrict__ seg, int32_t* __restrict__ blk_row, int32_t* __restrict__ cols, size_t n)
+                               uint32_t* __restrict__ seg, int32_t* __restrict__ blk_row, int32_t* __restrict__ cols, uint32_t* __restrict__ blk_of_src, size_t n)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t id = ids_sorted[i];
     sorted_off[i] = src_off[id];
     sorted_pitch[i] = src_pitch[id];
+    blk_of_src[id] = blk_of[i] - 1;
     if (head[i]) {
         const uint32_t b = blk_of[i] - 1;
         const uint64_t k = keys[i];
@@ -118,19 +125,90 @@ __global__ void k_row_ptr(const int32_t* __restrict__ blk_row, unsigned long lon
 }
 
 // Segmented reduction: 9 consecutive threads own one BCSR block (thread k -> entry (r = k % 3, c = k / 3), column-major).
+// Sources are summed in their sorted order (deterministic), four loads in flight per thread.  ONLY_DIRTY: re-sum just the
+// blocks a PD projection touched (the reference's update_global, ElementHessians.cpp:262-294, adds projected - original).
+// a long block is left to k_assemble_long only if it made it into the (capped) list
+__device__ __forceinline__ bool long_rank_ok(size_t b, const uint32_t* __restrict__ long_blocks, const int* __restrict__ n_long)
+{
+    const int n = *n_long;
+    if (n <= 4096) return true;          // nothing was dropped
+    for (int i = 0; i < 4096; i++) if (long_blocks[i] == (uint32_t)b) return true;
+    return false;
+}
+constexpr int LONG_SEG = 64;
+constexpr int LONG_CAP = 4096;      // long blocks beyond this many are summed by the plain path
+constexpr int LONG_CTAS = 64;
+
+__global__ void k_find_long(const uint32_t* __restrict__ seg, uint32_t* __restrict__ long_blocks, int* __restrict__ n_long, size_t nnzb)
+{
+    const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nnzb) return;
+    if (seg[b + 1] - seg[b] > LONG_SEG) {
+        const int k = atomicAdd(n_long, 1);
+        if (k < LONG_CAP) long_blocks[k] = (uint32_t)b;
+    }
+}
+
+// One CTA per long block: 32 strided partial sums per entry, then a fixed shared-memory tree (deterministic).
+template<bool ONLY_DIRTY>
+__global__ void __launch_bounds__(288) k_assemble_long(const double* __restrict__ H, const uint32_t* __restrict__ seg,
+                                                        const uint32_t* __restrict__ sorted_off, const uint8_t* __restrict__ sorted_pitch,
+                                                        float* __restrict__ vals, const uint8_t* __restrict__ dirty,
+                                                        const uint32_t* __restrict__ long_blocks, const int* __restrict__ n_long)
+{
+    __shared__ double sm[32][9];
+    const int total = min(*n_long, LONG_CAP);
+    const int k = threadIdx.x % 9, lane = threadIdx.x / 9;
+    const int r = k % 3, c = k / 3;
+    for (int i = blockIdx.x; i < total; i += gridDim.x) {
+        const uint32_t b = long_blocks[i];
+        if (ONLY_DIRTY && !dirty[b]) continue;   // uniform across the CTA
+        const uint32_t s0 = seg[b], s1 = seg[b + 1];
+        double acc = 0.0;
+        for (uint32_t s = s0 + lane; s < s1; s += 32) acc += H[(size_t)sorted_off[s] + (size_t)r * sorted_pitch[s] + c];
+        sm[lane][k] = acc;
+        __syncthreads();
+        for (int w = 16; w > 0; w >>= 1) {
+            if (lane < w) sm[lane][k] += sm[lane + w][k];
+            __syncthreads();
+        }
+        if (lane == 0) vals[9 * (size_t)b + k] = (float)sm[0][k];
+        __syncthreads();
+    }
+}
+
+template<bool ONLY_DIRTY>
 __global__ void __launch_bounds__(288) k_assemble_numeric(const double* __restrict__ H, const uint32_t* __restrict__ seg,
                                                            const uint32_t* __restrict__ sorted_off, const uint8_t* __restrict__ sorted_pitch,
-                                                           float* __restrict__ vals, size_t nnzb)
+                                                           float* __restrict__ vals, uint8_t* __restrict__ dirty, size_t nnzb,
+                                                           const uint32_t* __restrict__ long_blocks, const int* __restrict__ n_long)
 {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t b = t / 9;
     if (b >= nnzb) return;
+    if (ONLY_DIRTY && !dirty[b]) return;
     const int k = (int)(t - b * 9);
     const int r = k % 3, c = k / 3;
     const uint32_t s0 = seg[b], s1 = seg[b + 1];
+    if (s1 - s0 > LONG_SEG && long_rank_ok(b, long_blocks, n_long)) return;   // summed by k_assemble_long
     double acc = 0.0;
-    for (uint32_t s = s0; s < s1; s++) acc += H[(size_t)sorted_off[s] + (size_t)r * sorted_pitch[s] + c];
+    uint32_t s = s0;
+    for (; s + 4 <= s1; s += 4) {
+        const size_t o0 = (size_t)sorted_off[s] + (size_t)r * sorted_pitch[s] + c;
+        const size_t o1 = (size_t)sorted_off[s + 1] + (size_t)r * sorted_pitch[s + 1] + c;
+        const size_t o2 = (size_t)sorted_off[s + 2] + (size_t)r * sorted_pitch[s + 2] + c;
+        const size_t o3 = (size_t)sorted_off[s + 3] + (size_t)r * sorted_pitch[s + 3] + c;
+        const double v0 = H[o0], v1 = H[o1], v2 = H[o2], v3 = H[o3];
+        acc += v0; acc += v1; acc += v2; acc += v3;
+    }
+    for (; s < s1; s++) acc += H[(size_t)sorted_off[s] + (size_t)r * sorted_pitch[s] + c];
     vals[t] = (float)acc;
+}
+// the dirty flags are cleared by a separate pass (the nine threads of a block must all have seen the flag)
+__global__ void k_clear_dirty(uint8_t* __restrict__ dirty, size_t nnzb)
+{
+    const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nnzb) dirty[b] = 0;
 }
 
 static int build_symbolic(sb_context* ctx, Assembly* A)
@@ -143,7 +221,7 @@ static int build_symbolic(sb_context* ctx, Assembly* A)
     A->nbr = ctx->ndofs / 3;
     A->keys.ensure(n + 1); A->keys_sorted.ensure(n + 1); A->ids.ensure(n + 1); A->ids_sorted.ensure(n + 1);
     A->src_off.ensure(n + 1); A->src_pitch.ensure(n + 1); A->sorted_off.ensure(n + 1); A->sorted_pitch.ensure(n + 1);
-    A->head.ensure(n + 1); A->blk_of.ensure(n + 1);
+    A->head.ensure(n + 1); A->blk_of.ensure(n + 1); A->blk_of_src.ensure(n + 1);
 
     size_t blk_off = 0;
     for (auto& p : ctx->potentials) {
@@ -173,12 +251,18 @@ static int build_symbolic(sb_context* ctx, Assembly* A)
     A->nnzb = nnzb32;
     A->seg.ensure(A->nnzb + 2); A->blk_row.ensure(A->nnzb + 1); A->cols.ensure(A->nnzb + 1); A->vals.ensure(9 * A->nnzb + 9);
     A->rows.ensure(A->nbr + 2);
+    A->dirty.ensure(A->nnzb + 1);
+    SB_CUDA(ctx, cudaMemsetAsync(A->dirty.p, 0, A->nnzb + 1, st));
     k_fill_pattern<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(A->keys_sorted.p, A->head.p, A->blk_of.p, A->ids_sorted.p, A->src_off.p, A->src_pitch.p,
-                                                                 A->sorted_off.p, A->sorted_pitch.p, A->seg.p, A->blk_row.p, A->cols.p, n);
+                                                                 A->sorted_off.p, A->sorted_pitch.p, A->seg.p, A->blk_row.p, A->cols.p, A->blk_of_src.p, n);
     const uint32_t n32 = (uint32_t)n;
     SB_CUDA(ctx, cudaMemcpyAsync(A->seg.p + A->nnzb, &n32, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     k_row_ptr<<<(A->nbr + 1 + 255) / 256, 256, 0, st>>>(A->blk_row.p, A->rows.p, A->nbr, A->nnzb);
-    ctx->launches += 2;
+    if (!A->d_n_long) SB_CUDA(ctx, cudaMalloc(&A->d_n_long, sizeof(int)));
+    A->long_blocks.ensure(LONG_CAP);
+    SB_CUDA(ctx, cudaMemsetAsync(A->d_n_long, 0, sizeof(int), st));
+    k_find_long<<<(unsigned)((A->nnzb + 255) / 256), 256, 0, st>>>(A->seg.p, A->long_blocks.p, A->d_n_long, A->nnzb);
+    ctx->launches += 3;
     SB_CUDA(ctx, cudaStreamSynchronize(st));   // n32 is a stack variable
     SB_CUDA(ctx, cudaGetLastError());
     A->built_version = ctx->pattern_version;
@@ -191,17 +275,38 @@ int assemble_internal(sb_context* ctx)
     if (!ctx->have_pgh) return fail(ctx, SB_ERR_STATE, "sb_assemble: call sb_eval(SB_EVAL_PGH) first");
     Assembly* A = get(ctx);
     if (ctx->n_blocks_total == 0) return fail(ctx, SB_ERR_STATE, "sb_assemble: no element Hessians");
+    bool rebuilt = false;
     if (A->built_version != ctx->pattern_version || A->built_n_src != ctx->n_blocks_total || A->nbr != ctx->ndofs / 3) {
         int r = build_symbolic(ctx, A);
         if (r) return r;
+        rebuilt = true;
     }
     StageTimer timer(ctx, ST_ASM_NUMERIC);
     const size_t nt = 9 * A->nnzb;
-    k_assemble_numeric<<<(unsigned)((nt + 287) / 288), 288, 0, ctx->stream>>>(ctx->H.p, A->seg.p, A->sorted_off.p, A->sorted_pitch.p, A->vals.p, A->nnzb);
-    ctx->launches++;
+    const unsigned grid = (unsigned)((nt + 287) / 288);
+    if (!rebuilt && A->numeric_valid && A->assembled_eval == ctx->eval_id) {
+        // same evaluation, same pattern: only PD-projected elements changed since the last pass
+        k_assemble_numeric<true><<<grid, 288, 0, ctx->stream>>>(ctx->H.p, A->seg.p, A->sorted_off.p, A->sorted_pitch.p, A->vals.p, A->dirty.p, A->nnzb, A->long_blocks.p, A->d_n_long);
+        k_assemble_long<true><<<LONG_CTAS, 288, 0, ctx->stream>>>(ctx->H.p, A->seg.p, A->sorted_off.p, A->sorted_pitch.p, A->vals.p, A->dirty.p, A->long_blocks.p, A->d_n_long);
+    } else {
+        k_assemble_numeric<false><<<grid, 288, 0, ctx->stream>>>(ctx->H.p, A->seg.p, A->sorted_off.p, A->sorted_pitch.p, A->vals.p, A->dirty.p, A->nnzb, A->long_blocks.p, A->d_n_long);
+        k_assemble_long<false><<<LONG_CTAS, 288, 0, ctx->stream>>>(ctx->H.p, A->seg.p, A->sorted_off.p, A->sorted_pitch.p, A->vals.p, A->dirty.p, A->long_blocks.p, A->d_n_long);
+    }
+    k_clear_dirty<<<(unsigned)((A->nnzb + 255) / 256), 256, 0, ctx->stream>>>(A->dirty.p, A->nnzb);
+    ctx->launches += 3;
     SB_CUDA(ctx, cudaGetLastError());
+    A->assembled_eval = ctx->eval_id;
     A->numeric_valid = true;
     return 0;
+}
+
+// for project.cu: where a changed element's blocks land (null when the pattern is stale -> the next assembly is a full one anyway)
+bool assembly_dirty_view(sb_context* ctx, const uint32_t** blk_of_src, uint8_t** dirty)
+{
+    Assembly* A = ctx->assembly;
+    if (!A || A->built_version != ctx->pattern_version || A->built_n_src != ctx->n_blocks_total || A->nbr != ctx->ndofs / 3) return false;
+    *blk_of_src = A->blk_of_src.p; *dirty = A->dirty.p;
+    return true;
 }
 
 // accessors for pcg.cu

@@ -156,12 +156,26 @@ int eval_internal(sb_context* ctx, int mode, double* out_E, double* out_grad_inf
         ctx->n_rows_total = rows_total;
         ctx->H_total = H_total;
         ctx->n_projected = 0;
+        ctx->eval_id++;
     }
 
     for (auto& p : ctx->potentials) {
         if (p.n_elem == 0) continue;
         int r = refresh_slots(ctx, p);
         if (r) return r;
+    }
+    // large potentials stay on the context stream; the small ones are spread over the side streams (fork / join by events)
+    constexpr int SMALL = 16384;
+    int n_small = 0;
+    for (auto& p : ctx->potentials) if (p.n_elem > 0 && p.n_elem < SMALL) n_small++;
+    const bool fork = n_small >= 2;
+    bool side_used[sb_context::N_SIDE] = {false, false, false, false};
+    if (fork) {
+        SB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    }
+    int next_side = 0;
+    for (auto& p : ctx->potentials) {
+        if (p.n_elem == 0) continue;
         EvalArgs a;
         a.slots = p.slots.p;
         a.slots_host = p.slots_host.data();
@@ -174,10 +188,21 @@ int eval_internal(sb_context* ctx, int mode, double* out_E, double* out_grad_inf
         a.rows = ctx->rows.p + p.rows_off;
         a.E_elem = ctx->E_elem.p + p.E_off;
         a.g_elem = nullptr;
-        if (mode == SB_EVAL_PGH) p.k->launch_pgh(a, ctx->stream);
-        else p.k->launch_p(a, ctx->stream);
+        cudaStream_t st = ctx->stream;
+        if (fork && p.n_elem < SMALL) {
+            const int k = next_side++ % sb_context::N_SIDE;
+            if (!side_used[k]) { SB_CUDA(ctx, cudaStreamWaitEvent(ctx->side[k], ctx->ev_fork, 0)); side_used[k] = true; }
+            st = ctx->side[k];
+        }
+        if (mode == SB_EVAL_PGH) p.k->launch_pgh(a, st);
+        else p.k->launch_p(a, st);
         ctx->launches++;
     }
+    for (int k = 0; k < sb_context::N_SIDE; k++)
+        if (side_used[k]) {
+            SB_CUDA(ctx, cudaEventRecord(ctx->ev_join[k], ctx->side[k]));
+            SB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[k], 0));
+        }
     SB_CUDA(ctx, cudaGetLastError());
 
     reduce_sum(ctx, ctx->E_elem.p, E_total, ctx->d_scalars + 0);
@@ -236,6 +261,11 @@ int sb_create(sb_context** out, int device, void* stream)
         if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SB_ERR_CUDA; }
         ctx->own_stream = true;
     }
+    for (int k = 0; k < sb_context::N_SIDE; k++) {
+        if (cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SB_ERR_CUDA; }
+        if (cudaEventCreateWithFlags(&ctx->ev_join[k], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SB_ERR_CUDA; }
+    }
+    if (cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SB_ERR_CUDA; }
     if (cudaMallocHost(&ctx->h_scalars, 64 * sizeof(double)) != cudaSuccess) { delete ctx; return SB_ERR_CUDA; }
     if (cudaMalloc(&ctx->d_scalars, 64 * sizeof(double)) != cudaSuccess) { delete ctx; return SB_ERR_CUDA; }
     cudaMemset(ctx->d_scalars, 0, 64 * sizeof(double));
@@ -258,6 +288,11 @@ void sb_destroy(sb_context* ctx)
     ctx->dofs_saved.release(); ctx->scratch.release(); ctx->projected.release();
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
     if (ctx->d_scalars) cudaFree(ctx->d_scalars);
+    for (int k = 0; k < sb_context::N_SIDE; k++) {
+        if (ctx->side[k]) cudaStreamDestroy(ctx->side[k]);
+        if (ctx->ev_join[k]) cudaEventDestroy(ctx->ev_join[k]);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

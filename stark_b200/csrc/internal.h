@@ -132,6 +132,10 @@ struct sb_context {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    // side streams: the many small potentials (joints, contact and friction tables) of one evaluation run concurrently
+    static constexpr int N_SIDE = 4;
+    cudaStream_t side[N_SIDE] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[N_SIDE] = {nullptr, nullptr, nullptr, nullptr};
     std::string error;
     int64_t launches = 0;
 
@@ -152,6 +156,7 @@ struct sb_context {
     size_t n_hessians = 0, n_blocks_total = 0, n_rows_total = 0, H_total = 0;
     int64_t n_projected = 0;
     uint64_t pattern_version = 1;   // bumped whenever any connectivity changes
+    uint64_t eval_id = 0;           // bumped by every PGH evaluation (the element Hessians are rewritten)
     bool have_pgh = false;
 
     bool profile = false;           // stage profiling on (adds a stream synchronisation at every stage boundary)
@@ -182,6 +187,7 @@ void pcg_destroy(sb_context* ctx);
 void contact_destroy(sb_context* ctx);
 void projector_destroy(sb_context* ctx);
 int assemble_internal(sb_context* ctx);
+bool assembly_dirty_view(sb_context* ctx, const uint32_t** blk_of_src, uint8_t** dirty);
 int project_internal(sb_context* ctx, double grad_threshold, double eps, int mirror, int64_t* out_n_projected, int64_t* out_n_hessians, int* out_all_projected);
 int solve_pcg_internal(sb_context* ctx, double abs_tol, double rel_tol, int max_iter, int stop_on_indef, int* out_iterations, int* out_ok, double* out_du_dot_grad, double* out_du_inf);
 // contact hooks used by the Newton driver (contact.cu)

@@ -22,6 +22,7 @@ struct ProjTable {
     unsigned long long E_off[PROJ_MAX_POTS + 1];   // first global element id of each potential (+ total)
     unsigned long long H_off[PROJ_MAX_POTS];
     unsigned long long rows_off[PROJ_MAX_POTS];
+    unsigned long long blk_off[PROJ_MAX_POTS];     // first source (element block) of each potential in assembly numbering
     int nb[PROJ_MAX_POTS];
 };
 
@@ -69,7 +70,8 @@ __global__ void k_select(const ProjTable* __restrict__ Tp, const int32_t* __rest
 }
 
 __global__ void __launch_bounds__(32 * PROJ_WARPS) k_project(const ProjTable* __restrict__ Tp, double* __restrict__ H_all, const uint32_t* __restrict__ list,
-                                                              const int* __restrict__ n_list, double eps, int mirror, int* __restrict__ n_changed)
+                                                              const int* __restrict__ n_list, double eps, int mirror, int* __restrict__ n_changed,
+                                                              const uint32_t* __restrict__ blk_of_src, uint8_t* __restrict__ dirty)
 {
     __shared__ double sA[PROJ_WARPS][PROJ_MAX_N * PROJ_MAX_N];
     __shared__ double sV[PROJ_WARPS][PROJ_MAX_N * PROJ_MAX_N];
@@ -150,6 +152,11 @@ __global__ void __launch_bounds__(32 * PROJ_WARPS) k_project(const ProjTable* __
                 H[k] = acc;
             }
             if (lane == 0) atomicAdd(n_changed, 1);
+            if (dirty) {   // the BCSR blocks this element contributes to must be re-summed
+                const int nb = T.nb[pi];
+                const unsigned long long src0 = T.blk_off[pi] + (e - T.E_off[pi]) * (unsigned long long)(nb * nb);
+                for (int k = lane; k < nb * nb; k += 32) dirty[blk_of_src[src0 + k]] = 1;
+            }
         }
         __syncwarp();
     }
@@ -195,11 +202,14 @@ int project_internal(sb_context* ctx, double grad_threshold, double eps, int mir
     StageTimer timer(ctx, ST_PROJECT);
     ProjTable T;
     T.n_pots = 0;
+    unsigned long long blk_off = 0;
     for (auto& p : ctx->potentials) {
         if (p.n_elem == 0) continue;
         if (T.n_pots >= PROJ_MAX_POTS) return fail(ctx, SB_ERR_STATE, "sb_project_to_pd: too many active potentials");
         if (p.k->n_dof > PROJ_MAX_N) return fail(ctx, SB_ERR_STATE, "sb_project_to_pd: element size above 24 DoFs is not supported");
         T.E_off[T.n_pots] = p.E_off; T.H_off[T.n_pots] = p.H_off; T.rows_off[T.n_pots] = p.rows_off; T.nb[T.n_pots] = p.k->nb;
+        T.blk_off[T.n_pots] = blk_off;
+        blk_off += (unsigned long long)p.n_elem * p.k->nb * p.k->nb;
         T.n_pots++;
     }
     T.E_off[T.n_pots] = n_elem;
@@ -215,7 +225,10 @@ int project_internal(sb_context* ctx, double grad_threshold, double eps, int mir
     }
     k_select<<<(unsigned)((n_elem + 255) / 256), 256, 0, st>>>(P.d_table, ctx->rows.p, P.active.p, use_active, ctx->projected.p, P.list.p, P.d_counts, n_elem);
     const int grid = (int)std::min<size_t>((n_elem + PROJ_WARPS - 1) / PROJ_WARPS, 148 * 8);
-    k_project<<<grid, 32 * PROJ_WARPS, 0, st>>>(P.d_table, ctx->H.p, P.list.p, P.d_counts, eps, mirror, P.d_counts + 1);
+    const uint32_t* blk_of_src = nullptr;
+    uint8_t* dirty = nullptr;
+    if (!assembly_dirty_view(ctx, &blk_of_src, &dirty)) { blk_of_src = nullptr; dirty = nullptr; }
+    k_project<<<grid, 32 * PROJ_WARPS, 0, st>>>(P.d_table, ctx->H.p, P.list.p, P.d_counts, eps, mirror, P.d_counts + 1, blk_of_src, dirty);
     ctx->launches += 2;
     SB_CUDA(ctx, cudaMemcpyAsync(P.h_counts, P.d_counts, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
     SB_CUDA(ctx, cudaStreamSynchronize(st));   // also protects the stack-resident table T
