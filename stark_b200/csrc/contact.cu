@@ -109,6 +109,10 @@ struct Contact {
     int h_list_count[N_LISTS] = {0};
     int h_table_count[N_TABLES] = {0};
     bool external_vertices = false;
+    // detection results are a pure function of the state: a repeated call at an unchanged state (the line search's last
+    // trial and the next iteration's evaluation see the same DoFs) is answered from the cache
+    uint64_t contacts_state = 0, intersections_state = 0;
+    int cached_intersections = 0;
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -863,24 +867,30 @@ int contact_update_internal(sb_context* ctx)
 {
     Contact* C = ctx->contact;
     if (!C || C->groups.empty()) return 0;
+    if (!C->external_vertices && !C->topology_dirty && C->contacts_state == ctx->state_version) return 0;
     StageTimer timer(ctx, ST_CONTACT_UPDATE);
     int r;
     if (C->topology_dirty && (r = upload_topology(ctx, C))) return r;
     if ((r = refresh_params(ctx, C))) return r;
     if ((r = update_vertices(ctx, C, false))) return r;
-    return detect(ctx, C, 0, 2.0 * max_thickness(C));
+    if ((r = detect(ctx, C, 0, 2.0 * max_thickness(C)))) return r;
+    C->contacts_state = ctx->state_version;
+    return 0;
 }
 int contact_intersections_internal(sb_context* ctx, int* out_count)
 {
     Contact* C = ctx->contact;
     *out_count = 0;
     if (!C || C->groups.empty()) return 0;
+    if (!C->external_vertices && !C->topology_dirty && C->intersections_state == ctx->state_version) { *out_count = C->cached_intersections; return 0; }
     StageTimer timer(ctx, ST_INTERSECTIONS);
     int r;
     if (C->topology_dirty && (r = upload_topology(ctx, C))) return r;
     if ((r = update_vertices(ctx, C, false))) return r;
     if ((r = detect(ctx, C, 2, 0.0))) return r;
     *out_count = C->h_list_count[6];
+    C->cached_intersections = *out_count;
+    C->intersections_state = ctx->state_version;
     return 0;
 }
 
@@ -974,6 +984,7 @@ int sb_contact_add_mesh(sb_context* ctx, const sb_contact_mesh* m, int* out_grou
     C->groups.push_back(g);
     if (g.ps == 1) { C->h_blacklist[gi * MAX_GROUPS + gi] = 1; }   // rigid meshes never self-collide (EnergyFrictionalContact.cpp:209)
     C->topology_dirty = true;
+    ctx->state_version++;
     if (out_group) *out_group = gi;
     return SB_OK;
 }
@@ -984,6 +995,7 @@ int sb_contact_blacklist(sb_context* ctx, int a, int b)
     if (!C || a < 0 || b < 0 || a >= (int)C->groups.size() || b >= (int)C->groups.size()) return fail(ctx, SB_ERR_ARG, "sb_contact_blacklist: bad group");
     C->h_blacklist[a * MAX_GROUPS + b] = C->h_blacklist[b * MAX_GROUPS + a] = 1;
     C->topology_dirty = true;
+    ctx->state_version++;
     return SB_OK;
 }
 int sb_contact_set_friction(sb_context* ctx, int a, int b, double mu)
@@ -992,6 +1004,7 @@ int sb_contact_set_friction(sb_context* ctx, int a, int b, double mu)
     if (!C || a < 0 || b < 0 || a >= (int)C->groups.size() || b >= (int)C->groups.size()) return fail(ctx, SB_ERR_ARG, "sb_contact_set_friction: bad group");
     C->h_mu[a * MAX_GROUPS + b] = C->h_mu[b * MAX_GROUPS + a] = mu;
     C->topology_dirty = true;
+    ctx->state_version++;
     return SB_OK;
 }
 int sb_contact_set_params(sb_context* ctx, double contact_stiffness, double epsv, int enable_pt, int enable_ee, int enable_friction)
@@ -999,6 +1012,7 @@ int sb_contact_set_params(sb_context* ctx, double contact_stiffness, double epsv
     Contact* C = ctx ? ctx->contact : nullptr;
     if (!C) return fail(ctx, SB_ERR_STATE, "sb_contact_set_params: call sb_contact_init first");
     C->stiffness = contact_stiffness; C->epsv = epsv; C->enable_pt = enable_pt; C->enable_ee = enable_ee; C->enable_friction = enable_friction;
+    ctx->state_version++;
     return SB_OK;
 }
 int sb_contact_update(sb_context* ctx)
@@ -1034,6 +1048,7 @@ int sb_contact_detect(sb_context* ctx, double enlargement, int with_intersection
     if (C->topology_dirty && (r = upload_topology(ctx, C))) return r;
     if ((r = refresh_params(ctx, C))) return r;
     if ((r = update_vertices(ctx, C, false))) return r;
+    C->contacts_state = 0; C->intersections_state = 0;   // tables / lists are rewritten with a caller-chosen enlargement
     return detect(ctx, C, with_intersections ? 3 : 0, enlargement);
 }
 int sb_contact_get_proximity(sb_context* ctx, int kind, int32_t* host_ids, double* host_dist, int capacity, int* out_count, int* out_width)
@@ -1069,6 +1084,7 @@ int sb_contact_set_vertices(sb_context* ctx, int group, const double* host_xyz)
     const Group& g = C->groups[group];
     SB_CUDA(ctx, cudaMemcpyAsync(C->x.p + 3 * (size_t)g.v_off, host_xyz, sizeof(double) * 3 * g.n_v, cudaMemcpyHostToDevice, ctx->stream));
     SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->state_version++;
     C->external_vertices = true;
     return SB_OK;
 }

@@ -317,7 +317,7 @@ int sb_profile_stages(sb_context* ctx, int enable)
 const char* sb_profile_report(sb_context* ctx)
 {
     if (!ctx) return "";
-    static const char* names[ST_COUNT] = {"contact_update", "intersections", "eval_pgh", "eval_p", "project_to_pd", "assembly_symbolic", "assembly_numeric", "pcg", "line_search_misc", "cg_iterations"};
+    static const char* names[ST_COUNT] = {"contact_update", "intersections", "eval_pgh", "eval_p", "project_to_pd", "assembly_symbolic", "assembly_numeric", "pcg", "line_search_misc", "cg_iterations", "pcg_kernel_setup", "project_selected", "project_changed"};
     ctx->profile_report.clear();
     for (int i = 0; i < ST_COUNT; i++)
         ctx->profile_report += std::string(names[i]) + " " + std::to_string(ctx->stage_ms[i]) + " " + std::to_string(ctx->stage_calls[i]) + "\n";
@@ -347,6 +347,7 @@ int sb_array_upload(sb_context* ctx, int array, const double* host, int n_rows)
     Array& a = ctx->arrays[array];
     a.d.ensure((size_t)std::max(n_rows, 1) * a.stride);
     a.n_rows = n_rows;
+    ctx->state_version++;
     if (n_rows > 0) {
         SB_CUDA(ctx, cudaMemcpyAsync(a.d.p, host, sizeof(double) * (size_t)n_rows * a.stride, cudaMemcpyHostToDevice, ctx->stream));
         SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host buffer is only borrowed for this call
@@ -402,6 +403,7 @@ int sb_dofs_get(sb_context* ctx, double* host_u)
 int sb_dofs_set(sb_context* ctx, const double* host_u)
 {
     if (!ctx || !host_u) return fail(ctx, SB_ERR_ARG, "sb_dofs_set: bad argument");
+    ctx->state_version++;
     recompute_dof_offsets(ctx);
     for (auto& s : ctx->dof_sets) {
         Array& a = ctx->arrays[s.array];
@@ -604,6 +606,7 @@ int sb_dofs_apply_step(sb_context* ctx, double step)
 {
     if (!ctx) return SB_ERR_ARG;
     if (!ctx->du.p || !ctx->dofs_saved.p) return fail(ctx, SB_ERR_STATE, "sb_dofs_apply_step: no saved DoFs / direction");
+    ctx->state_version++;
     for (auto& s : ctx->dof_sets) {
         Array& a = ctx->arrays[s.array];
         const int n = a.n_rows * a.stride;

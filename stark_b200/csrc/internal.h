@@ -112,7 +112,7 @@ struct Potential {
 };
 
 // Stage profiling (sb_profile_stages): host wall time between two stream synchronisations, accumulated per stage.
-enum Stage { ST_CONTACT_UPDATE, ST_INTERSECTIONS, ST_EVAL_PGH, ST_EVAL_P, ST_PROJECT, ST_ASM_SYMBOLIC, ST_ASM_NUMERIC, ST_PCG, ST_LINE_SEARCH_MISC, ST_CG_ITERATIONS /* calls = iterations, ms unused */, ST_COUNT };
+enum Stage { ST_CONTACT_UPDATE, ST_INTERSECTIONS, ST_EVAL_PGH, ST_EVAL_P, ST_PROJECT, ST_ASM_SYMBOLIC, ST_ASM_NUMERIC, ST_PCG, ST_LINE_SEARCH_MISC, ST_CG_ITERATIONS /* calls = iterations, ms = in-kernel time of the iteration loop */, ST_PCG_SETUP /* in-kernel: slice load + preconditioner */, ST_PROJ_SELECTED /* calls = elements selected */, ST_PROJ_CHANGED /* calls = elements modified */, ST_COUNT };
 struct StageTimer {
     sb_context* ctx;
     int stage;
@@ -156,6 +156,7 @@ struct sb_context {
     size_t n_hessians = 0, n_blocks_total = 0, n_rows_total = 0, H_total = 0;
     int64_t n_projected = 0;
     uint64_t pattern_version = 1;   // bumped whenever any connectivity changes
+    uint64_t state_version = 1;     // bumped whenever an array / the DoFs / the contact set-up change (caches keyed on the state)
     uint64_t eval_id = 0;           // bumped by every PGH evaluation (the element Hessians are rewritten)
     bool have_pgh = false;
 

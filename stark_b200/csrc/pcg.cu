@@ -34,6 +34,7 @@ struct PcgResult {
     int done;           // 1 converged, 2 indefinite, 3 max iterations
     int found_indef;
     int pad;
+    unsigned long long t_start, t_loaded, t_loop, t_end;   // %globaltimer (ns) of CTA 0: kernel entry, slices resident, first iteration, exit
 };
 
 struct PcgArgs {
@@ -169,8 +170,16 @@ __device__ __forceinline__ int row_lower_bound(const unsigned long long* __restr
     return lo;
 }
 
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_solve(const PcgArgs A)
 {
+    const unsigned long long t_start = global_ns();
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ double s[PCG_THREADS / 32];
     __shared__ double bc;
@@ -241,6 +250,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_solve(const PcgArgs A)
         return false;
     };
     double* pg = A.p + 3 * (size_t)r0;   // own slice of the global direction vector
+    const unsigned long long t_loaded = global_ns();
 
     int it = 0, done = 0, found_indef = 0;
     double error = 1.0;               // x0 = 0 -> r = b
@@ -303,6 +313,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_solve(const PcgArgs A)
     else if (1.0 < A.abs_tol) done = 1;
     else if (A.max_iter <= 0) done = 3;
 
+    const unsigned long long t_loop = global_ns();
     const int lane = tid % LANES_PER_ROW;
     constexpr int rows_per_pass = PCG_THREADS / LANES_PER_ROW;
     while (!done) {
@@ -435,6 +446,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_solve(const PcgArgs A)
             PcgResult R;
             R.du_dot_grad = dg; R.du_inf = mx; R.error = error; R.bb = bb;
             R.it = it; R.done = done; R.found_indef = found_indef; R.pad = 0;
+            R.t_start = t_start; R.t_loaded = t_loaded; R.t_loop = t_loop; R.t_end = global_ns();
             *A.result = R;
         }
     }
@@ -483,7 +495,12 @@ int solve_pcg_internal(sb_context* ctx, double abs_tol, double rel_tol, int max_
     SB_CUDA(ctx, cudaMemcpyAsync(P->h_result, P->d_result, sizeof(PcgResult), cudaMemcpyDeviceToHost, st));
     SB_CUDA(ctx, cudaStreamSynchronize(st));
     SB_CUDA(ctx, cudaGetLastError());
-    if (ctx->profile) ctx->stage_calls[ST_CG_ITERATIONS] += P->h_result->it;
+    if (ctx->profile) {
+        ctx->stage_calls[ST_CG_ITERATIONS] += P->h_result->it;
+        ctx->stage_ms[ST_CG_ITERATIONS] += 1e-6 * (double)(P->h_result->t_end - P->h_result->t_loop);          // iterations + final reduction
+        ctx->stage_ms[ST_PCG_SETUP] += 1e-6 * (double)(P->h_result->t_loop - P->h_result->t_start);              // slice load + preconditioner
+        ctx->stage_calls[ST_PCG_SETUP]++;
+    }
     if (out_iterations) *out_iterations = P->h_result->it;
     if (out_ok) *out_ok = (P->h_result->done == 1) ? 1 : 0;
     if (out_du_dot_grad) *out_du_dot_grad = P->h_result->du_dot_grad;

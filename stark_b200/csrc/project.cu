@@ -10,6 +10,7 @@
 // in the element-Hessian store and the next numeric assembly re-sums every BCSR block (instead of the reference's
 // "add (projected - original)" update pass; same matrix up to float rounding).
 #include "internal.h"
+#include <algorithm>
 
 namespace sb {
 
@@ -69,96 +70,151 @@ __global__ void k_select(const ProjTable* __restrict__ Tp, const int32_t* __rest
     }
 }
 
-__global__ void __launch_bounds__(32 * PROJ_WARPS) k_project(const ProjTable* __restrict__ Tp, double* __restrict__ H_all, const uint32_t* __restrict__ list,
-                                                              const int* __restrict__ n_list, double eps, int mirror, int* __restrict__ n_changed,
-                                                              const uint32_t* __restrict__ blk_of_src, uint8_t* __restrict__ dirty)
+// One 128-thread CTA per selected element.
+//  1. cheap exit: lambda_min(A) > eps  <=>  A - eps I has an LDL^T factorisation with positive pivots (n steps);
+//  2. otherwise a PARALLEL-ORDER two-sided Jacobi eigen-solve: the n/2 disjoint rotations of one round-robin step are
+//     computed from the same matrix and applied together (columns of A and V, then rows of A), n-1 steps per sweep --
+//     the dependent chain of a sweep is n-1 steps instead of the n(n-1)/2 rotations of the cyclic order;
+//  3. clamp / mirror the eigenvalues below eps and rebuild H = V diag(l) V^T.
+constexpr int PROJ_THREADS = 128;
+__global__ void __launch_bounds__(PROJ_THREADS) k_project(const ProjTable* __restrict__ Tp, double* __restrict__ H_all, const uint32_t* __restrict__ list,
+                                                           const int* __restrict__ n_list, double eps, int mirror, int* __restrict__ n_changed,
+                                                           const uint32_t* __restrict__ blk_of_src, uint8_t* __restrict__ dirty)
 {
-    __shared__ double sA[PROJ_WARPS][PROJ_MAX_N * PROJ_MAX_N];
-    __shared__ double sV[PROJ_WARPS][PROJ_MAX_N * PROJ_MAX_N];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __shared__ double A[PROJ_MAX_N * PROJ_MAX_N];
+    __shared__ double V[PROJ_MAX_N * PROJ_MAX_N];
+    __shared__ double s_c[PROJ_MAX_N / 2], s_s[PROJ_MAX_N / 2];
+    __shared__ int s_p[PROJ_MAX_N / 2], s_q[PROJ_MAX_N / 2];
+    __shared__ double s_red[2][PROJ_THREADS / 32];
+    __shared__ int s_flag;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const ProjTable& T = *Tp;
     const int total = *n_list;
-    double* A = sA[w];
-    double* V = sV[w];
-    for (int item = blockIdx.x * PROJ_WARPS + w; item < total; item += gridDim.x * PROJ_WARPS) {
+    for (int item = blockIdx.x; item < total; item += gridDim.x) {
         const unsigned long long e = list[item];
         const int pi = find_pot(T, e);
         const int n = 3 * T.nb[pi];
         double* H = H_all + T.H_off[pi] + (e - T.E_off[pi]) * (unsigned long long)(n * n);
-        // load (symmetrised) + identity
-        for (int k = lane; k < n * n; k += 32) {
+        __syncthreads();   // previous item fully done
+        // load (symmetrised); V = A - eps I for the factorisation test
+        for (int k = tid; k < n * n; k += PROJ_THREADS) {
             const int i = k / n, j = k - i * n;
-            A[k] = 0.5 * (H[i * n + j] + H[j * n + i]);
+            const double a = 0.5 * (H[i * n + j] + H[j * n + i]);
+            A[k] = a;
+            V[k] = a - ((i == j) ? eps : 0.0);
+        }
+        __syncthreads();
+        bool pd = true;
+        for (int j = 0; j < n; j++) {
+            const double d = V[j * n + j];
+            if (!(d > 0.0)) { pd = false; break; }   // shared value: uniform across the CTA
+            const double inv = 1.0 / d;
+            const int m = n - 1 - j;                  // trailing block: rows / cols j+1 .. n-1 (lower triangle incl. diagonal)
+            for (int t = tid; t < m * m; t += PROJ_THREADS) {
+                const int i = j + 1 + t / m, k2 = j + 1 + t % m;
+                if (k2 <= i) V[i * n + k2] -= V[i * n + j] * V[k2 * n + j] * inv;
+            }
+            __syncthreads();
+        }
+        if (pd) continue;
+        __syncthreads();
+        for (int k = tid; k < n * n; k += PROJ_THREADS) {
+            const int i = k / n, j = k - i * n;
             V[k] = (i == j) ? 1.0 : 0.0;
         }
-        __syncwarp();
+        const int ne = (n + 1) & ~1;       // even number of players (a dummy index n when n is odd)
+        const int np = ne / 2;             // pairs per step
+        __syncthreads();
         for (int sweep = 0; sweep < 30; sweep++) {
             // convergence: off-diagonal mass vs total
             double off = 0.0, diag = 0.0;
-            for (int k = lane; k < n * n; k += 32) {
+            for (int k = tid; k < n * n; k += PROJ_THREADS) {
                 const int i = k / n, j = k - i * n;
                 const double v = A[k] * A[k];
                 if (i == j) diag += v; else off += v;
             }
             for (int o = 16; o > 0; o >>= 1) { off += __shfl_xor_sync(0xffffffffu, off, o); diag += __shfl_xor_sync(0xffffffffu, diag, o); }
+            if (lane == 0) { s_red[0][warp] = off; s_red[1][warp] = diag; }
+            __syncthreads();
+            off = 0.0; diag = 0.0;
+            for (int w = 0; w < PROJ_THREADS / 32; w++) { off += s_red[0][w]; diag += s_red[1][w]; }
+            __syncthreads();
             if (off <= 1e-30 * (diag + off) || off == 0.0) break;
-            for (int p = 0; p < n - 1; p++) {
-                for (int q = p + 1; q < n; q++) {
-                    const double apq = A[p * n + q];
-                    if (apq == 0.0) continue;   // uniform across the warp (shared value)
-                    const double app = A[p * n + p], aqq = A[q * n + q];
-                    const double tau = (aqq - app) / (2.0 * apq);
-                    const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-                    const double c = 1.0 / sqrt(1.0 + t * t), s = t * c;
-                    __syncwarp();
-                    // columns p, q of A and V
-                    for (int k = lane; k < n; k += 32) {
-                        const double akp = A[k * n + p], akq = A[k * n + q];
-                        A[k * n + p] = c * akp - s * akq;
-                        A[k * n + q] = s * akp + c * akq;
-                        const double vkp = V[k * n + p], vkq = V[k * n + q];
-                        V[k * n + p] = c * vkp - s * vkq;
-                        V[k * n + q] = s * vkp + c * vkq;
+            for (int step = 0; step < ne - 1; step++) {
+                // round-robin pairing: player ne-1 is fixed, the others rotate
+                if (tid < np) {
+                    int p, q;
+                    if (tid == 0) { p = ne - 1; q = step; }
+                    else { p = (step + tid) % (ne - 1); q = (step - tid + (ne - 1)) % (ne - 1); }
+                    if (p > q) { const int t = p; p = q; q = t; }
+                    double c = 1.0, sn = 0.0;
+                    if (q < n) {   // (a pair with the dummy index does nothing)
+                        const double apq = A[p * n + q];
+                        if (apq != 0.0) {
+                            const double app = A[p * n + p], aqq = A[q * n + q];
+                            const double tau = (aqq - app) / (2.0 * apq);
+                            const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                            c = 1.0 / sqrt(1.0 + t * t);
+                            sn = t * c;
+                        }
                     }
-                    __syncwarp();
-                    // rows p, q of A
-                    for (int k = lane; k < n; k += 32) {
-                        const double apk = A[p * n + k], aqk = A[q * n + k];
-                        A[p * n + k] = c * apk - s * aqk;
-                        A[q * n + k] = s * apk + c * aqk;
-                    }
-                    __syncwarp();
+                    s_p[tid] = p; s_q[tid] = (q < n) ? q : -1; s_c[tid] = c; s_s[tid] = sn;
                 }
+                __syncthreads();
+                // columns p, q of A and V (all rows)
+                for (int t = tid; t < np * n; t += PROJ_THREADS) {
+                    const int pr = t / n, k = t - pr * n;
+                    const int p = s_p[pr], q = s_q[pr];
+                    if (q < 0) continue;
+                    const double c = s_c[pr], sn = s_s[pr];
+                    const double akp = A[k * n + p], akq = A[k * n + q];
+                    A[k * n + p] = c * akp - sn * akq;
+                    A[k * n + q] = sn * akp + c * akq;
+                    const double vkp = V[k * n + p], vkq = V[k * n + q];
+                    V[k * n + p] = c * vkp - sn * vkq;
+                    V[k * n + q] = sn * vkp + c * vkq;
+                }
+                __syncthreads();
+                // rows p, q of A (all columns)
+                for (int t = tid; t < np * n; t += PROJ_THREADS) {
+                    const int pr = t / n, k = t - pr * n;
+                    const int p = s_p[pr], q = s_q[pr];
+                    if (q < 0) continue;
+                    const double c = s_c[pr], sn = s_s[pr];
+                    const double apk = A[p * n + k], aqk = A[q * n + k];
+                    A[p * n + k] = c * apk - sn * aqk;
+                    A[q * n + k] = sn * apk + c * aqk;
+                }
+                __syncthreads();
             }
         }
-        __syncwarp();
+        __syncthreads();
         // clamp / mirror
-        bool changed = false;
-        for (int i = 0; i < n; i++) {
-            const double l = A[i * n + i];
-            if (l < eps) changed = true;
+        if (tid == 0) {
+            int changed = 0;
+            for (int i = 0; i < n; i++) if (A[i * n + i] < eps) changed = 1;
+            s_flag = changed;
         }
-        if (changed) {
-            __syncwarp();
-            if (lane < n) {
-                const double l = A[lane * n + lane];
-                A[lane * n + lane] = (l < eps) ? (mirror ? -l : eps) : l;
+        __syncthreads();
+        if (s_flag) {
+            if (tid < n) {
+                const double l = A[tid * n + tid];
+                A[tid * n + tid] = (l < eps) ? (mirror ? -l : eps) : l;
             }
-            __syncwarp();
-            for (int k = lane; k < n * n; k += 32) {
+            __syncthreads();
+            for (int k = tid; k < n * n; k += PROJ_THREADS) {
                 const int i = k / n, j = k - i * n;
                 double acc = 0.0;
                 for (int m = 0; m < n; m++) acc += V[i * n + m] * A[m * n + m] * V[j * n + m];
                 H[k] = acc;
             }
-            if (lane == 0) atomicAdd(n_changed, 1);
+            if (tid == 0) atomicAdd(n_changed, 1);
             if (dirty) {   // the BCSR blocks this element contributes to must be re-summed
                 const int nb = T.nb[pi];
                 const unsigned long long src0 = T.blk_off[pi] + (e - T.E_off[pi]) * (unsigned long long)(nb * nb);
-                for (int k = lane; k < nb * nb; k += 32) dirty[blk_of_src[src0 + k]] = 1;
+                for (int k = tid; k < nb * nb; k += PROJ_THREADS) dirty[blk_of_src[src0 + k]] = 1;
             }
         }
-        __syncwarp();
     }
 }
 
@@ -234,6 +290,7 @@ int project_internal(sb_context* ctx, double grad_threshold, double eps, int mir
     SB_CUDA(ctx, cudaStreamSynchronize(st));   // also protects the stack-resident table T
     SB_CUDA(ctx, cudaGetLastError());
     ctx->n_projected += P.h_counts[0];
+    if (ctx->profile) { ctx->stage_calls[ST_PROJ_SELECTED] += P.h_counts[0]; ctx->stage_calls[ST_PROJ_CHANGED] += P.h_counts[1]; }
     if (out_n_projected) *out_n_projected = ctx->n_projected;
     if (out_all_projected) *out_all_projected = use_active ? (P.h_counts[2] == 0) : 1;
     return 0;
