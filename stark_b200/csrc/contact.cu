@@ -827,6 +827,8 @@ static int detect(sb_context* ctx, Contact* C, int mode, double enlargement)
     // publish the table sizes to the potentials / friction arrays
     const int t0 = (mode == 0) ? 0 : N_CONTACT_TABLES, t1 = (mode == 0) ? N_CONTACT_TABLES : N_TABLES;
     if (mode == 0 || mode == 1) {
+        bool any = false;   // empty before and empty now: neither the connectivity nor the pattern changed
+        for (int t = t0; t < t1; t++) any = any || C->h_counters[16 + t] != 0 || C->h_table_count[t] != 0 || ctx->potentials[C->pot[t]].n_elem != 0;
         for (int t = t0; t < t1; t++) {
             const int n = C->h_counters[16 + t];
             C->h_table_count[t] = n;
@@ -839,8 +841,10 @@ static int detect(sb_context* ctx, Contact* C, int mode, double enlargement)
                 if (C->a_fbary[f] >= 0) ctx->arrays[C->a_fbary[f]].n_rows = n;
             }
         }
-        ctx->pattern_version++;
-        ctx->have_pgh = false;
+        if (any) {
+            ctx->pattern_version++;
+            ctx->have_pgh = false;
+        }
     }
     return 0;
 }

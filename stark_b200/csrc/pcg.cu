@@ -2,19 +2,28 @@
 //
 // Replaces bsm::solve_pcg (bsm/solve_pcg.h:83-232), BlockedSparseMatrix::{prepare_preconditioning,
 // apply_preconditioning, _spmxv} (bsm/BlockedSparseMatrix.h:1147-1361, 988-1138) and the vector kernels of
-// bsm/bsm_vector_ops.h.  Same recurrence, same stopping rules (zero RHS, error < abs_tol, error/error_0 < rel_tol,
-// p^T A p <= 0 -> "indefinite", max_iter), same float-storage / double-accumulate arithmetic.
+// bsm/bsm_vector_ops.h.  Same stopping rules (zero RHS, error < abs_tol, error/error_0 < rel_tol, p^T A p <= 0 ->
+// "indefinite", max_iter), same float-storage / double-accumulate arithmetic, same block-Jacobi preconditioner.
 //
-// The ENTIRE solve is ONE persistent cooperative kernel, one 1024-thread CTA per SM.  CTA c owns a contiguous range of
-// block rows holding ~nnzb / #SM blocks and copies ITS SLICE OF THE MATRIX (values, columns, row pointers) and of the
-// vectors x, r, z, Ap, M^-1 INTO SHARED MEMORY ONCE: at the 200k-tet scene the 21.7 MB matrix is spread over the 148 x
-// 227 KB of shared memory of the chip and is never read from L2 / HBM again during the solve; the only global traffic of
-// an iteration is the gather of p (0.9 MB, L2) and each CTA's own slice of p written back.  Slices that do not fit
-// (million-tet scenes) are streamed from global memory by the same code through generic pointers, per CTA.
-// Phases are separated by a grid-wide barrier (one atomic counter, acquire spin), three per iteration.  Dot products go
-// through per-CTA partial sums that every CTA re-reduces in the same fixed order, so alpha, beta, the error and every
-// stopping decision are computed redundantly but IDENTICALLY everywhere (no broadcast; bitwise reproducible run to run --
-// the reference's are thread-count dependent, bsm/ParallelNumber.h:39-47).  The host launches once and reads one record.
+// The ENTIRE solve is ONE persistent cooperative kernel, one 1024-thread CTA per SM:
+//   * CTA c owns a contiguous range of block rows holding ~nnzb / #SM blocks and copies ITS SLICE OF THE MATRIX (values,
+//     columns, row pointers) and of the vectors INTO SHARED MEMORY ONCE: at the 200k-tet scene the 21.7 MB matrix is
+//     spread over the 148 x 227 KB of shared memory of the chip and is never read from L2 / HBM again during the solve.
+//     Slices that do not fit (million-tet scenes) are streamed from global memory by the same code (generic pointers).
+//   * The only vector that crosses CTAs is the preconditioned residual u = M^-1 r (the SpMV operand).  Every iteration
+//     each CTA pulls the WINDOW of u around its own rows into shared memory with one TMA bulk copy
+//     (cp.async.bulk.shared.global + mbarrier) -- the band of a mesh-ordered matrix -- and gathers from shared memory;
+//     the few columns outside the window (rigid bodies, far contacts) are gathered from L2.
+//   * The recurrence is the Chronopoulos-Gear form of PCG (same iterates as the textbook form in exact arithmetic):
+//         p = u + beta p ; s = w + beta s ; x += alpha p ; r -= alpha s ; u = M^-1 r ; w = A u
+//         gamma' = r.u ; delta = w.u ; beta = gamma'/gamma ; alpha = gamma' / (delta - beta gamma'/alpha)
+//     s = A p is carried by recurrence, so an iteration needs TWO grid-wide barriers (u visible -> SpMV -> dot
+//     products visible) instead of three, and p^T A p of the next iteration is the denominator of alpha (its sign is the
+//     reference's indefiniteness test).  Phases are separated by a grid barrier (one atomic counter, acquire spin).
+//   * Dot products go through per-CTA partial sums that every CTA re-reduces in the same fixed order, so alpha, beta,
+//     the error and every stopping decision are computed redundantly but IDENTICALLY everywhere (no broadcast; bitwise
+//     reproducible run to run -- the reference's are thread-count dependent, bsm/ParallelNumber.h:39-47).
+// The host launches once and reads one record.
 #include "internal.h"
 #include <algorithm>
 
@@ -35,26 +44,30 @@ struct PcgResult {
     int found_indef;
     int pad;
     unsigned long long t_start, t_loaded, t_loop, t_end;   // %globaltimer (ns) of CTA 0: kernel entry, slices resident, first iteration, exit
+    long long c_spmv, c_bar, c_red, c_vec;                 // clock64 cycles of CTA 0 inside the loop (only when instrumented)
 };
 
 struct PcgArgs {
     const unsigned long long* rows; const int32_t* cols; const float* vals;
     const double* grad;
-    float* dinv;
-    double *x, *r, *z, *p, *Ap, *du;
-    double* part;          // 3 x PCG_MAX_BLOCKS partial sums
-    int* rp_scratch;       // [nbr + grid + 1] local row pointers of slices whose row pointers do not fit in shared memory
-    unsigned* barrier;     // zeroed before the launch
+    float* dinv;                    // global fallbacks of the per-CTA slices
+    double *x, *r, *p, *s, *w;
+    double* u;                      // preconditioned residual, the one vector every CTA reads
+    double* du;
+    double* part;                   // 3 x PCG_MAX_BLOCKS partial sums
+    int* rp_scratch;                // [nbr + grid + 1] local row pointers of slices whose row pointers do not fit in shared memory
+    unsigned* barrier;              // zeroed before the launch
     PcgResult* result;
     int nbr;
     double abs_tol, rel_tol;
     int max_iter, stop_on_indef;
     unsigned long long nnzb;
-    unsigned smem_bytes;   // dynamic shared memory of the launch
+    unsigned smem_bytes;            // dynamic shared memory of the launch
+    int instrument;
 };
 
 struct Pcg {
-    DevBuf<double> r, z, p, Ap, x;
+    DevBuf<double> r, p, s, w, u, x;
     DevBuf<float> dinv;
     DevBuf<double> part;
     DevBuf<int> rp_scratch;
@@ -78,7 +91,7 @@ void pcg_destroy(sb_context* ctx)
 {
     Pcg* P = ctx->pcg;
     if (!P) return;
-    P->r.release(); P->z.release(); P->p.release(); P->Ap.release(); P->x.release(); P->dinv.release(); P->part.release(); P->rp_scratch.release();
+    P->r.release(); P->p.release(); P->s.release(); P->w.release(); P->u.release(); P->x.release(); P->dinv.release(); P->part.release(); P->rp_scratch.release();
     if (P->d_barrier) cudaFree(P->d_barrier);
     if (P->d_result) cudaFree(P->d_result);
     if (P->h_result) cudaFreeHost(P->h_result);
@@ -103,7 +116,32 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch)
     __syncthreads();
 }
 
-// ---- block reductions ------------------------------------------------------------------------------------------
+// ---- mbarrier + TMA bulk load (global -> shared) ----
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_bulk(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+// ---- block reductions (fixed tree) ----
 __device__ __forceinline__ double block_sum(double v, double* s)
 {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
@@ -179,13 +217,14 @@ __device__ __forceinline__ unsigned long long global_ns()
 
 __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_solve(const PcgArgs A)
 {
-    const unsigned long long t_start = global_ns();
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ double s[PCG_THREADS / 32];
     __shared__ double bc;
     __shared__ int s_range[2];
     __shared__ int s_long[MAX_LONG_ROWS];
     __shared__ int s_n_long;
+    __shared__ __align__(8) unsigned long long s_mbar;
+    const unsigned long long t_start = global_ns();
     const int G = gridDim.x;
     const int nbr = A.nbr;
     const int tid = threadIdx.x;
@@ -198,32 +237,36 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_solve(const PcgArgs A)
     if (tid == 0) {
         s_range[0] = row_lower_bound(A.rows, nbr, (A.nnzb * blockIdx.x) / G);
         s_range[1] = (blockIdx.x == G - 1) ? nbr : row_lower_bound(A.rows, nbr, (A.nnzb * (blockIdx.x + 1)) / G);
+        mbar_init(&s_mbar, 1);
     }
     __syncthreads();
     const int r0 = s_range[0], nr = s_range[1] - s_range[0];
     const unsigned long long b0 = A.rows[r0];
     const int nb = (int)(A.rows[r0 + nr] - b0);
 
-    // ---- shared-memory plan: row pointers always; then the vector slices; then the matrix slice; whatever does not fit
-    //      stays in global memory and is reached through the same (generic) pointers ----
+    // ---- shared-memory plan: row pointers; the vector slices r, p, s, w, M^-1; the matrix slice; the window of u gets
+    //      what is left.  Whatever does not fit stays in global memory and is reached through the same (generic) pointers ----
     size_t off = 0;
     auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 15) & ~(size_t)15; return o; };
     const bool rp_fit = ((sizeof(int) * (nr + 1) + 15) & ~(size_t)15) <= A.smem_bytes;
     int* rp = rp_fit ? reinterpret_cast<int*>(smem + carve(sizeof(int) * (nr + 1))) : A.rp_scratch + r0 + blockIdx.x;
     const size_t vec_bytes = 4 * ((sizeof(double) * 3 * nr + 15) & ~(size_t)15) + ((sizeof(float) * 9 * nr + 15) & ~(size_t)15);
     const bool vec_fit = rp_fit && off + vec_bytes <= A.smem_bytes;
-    double *xs, *rs, *zs, *Aps; float* dinv;
+    double *rs, *ps, *ss, *ws; float* dinv;
     if (vec_fit) {
-        xs = reinterpret_cast<double*>(smem + carve(sizeof(double) * 3 * nr));
         rs = reinterpret_cast<double*>(smem + carve(sizeof(double) * 3 * nr));
-        zs = reinterpret_cast<double*>(smem + carve(sizeof(double) * 3 * nr));
-        Aps = reinterpret_cast<double*>(smem + carve(sizeof(double) * 3 * nr));
+        ps = reinterpret_cast<double*>(smem + carve(sizeof(double) * 3 * nr));
+        ss = reinterpret_cast<double*>(smem + carve(sizeof(double) * 3 * nr));
+        ws = reinterpret_cast<double*>(smem + carve(sizeof(double) * 3 * nr));
         dinv = reinterpret_cast<float*>(smem + carve(sizeof(float) * 9 * nr));
     } else {
-        xs = A.x + 3 * (size_t)r0; rs = A.r + 3 * (size_t)r0; zs = A.z + 3 * (size_t)r0; Aps = A.Ap + 3 * (size_t)r0; dinv = A.dinv + 9 * (size_t)r0;
+        rs = A.r + 3 * (size_t)r0; ps = A.p + 3 * (size_t)r0; ss = A.s + 3 * (size_t)r0; ws = A.w + 3 * (size_t)r0; dinv = A.dinv + 9 * (size_t)r0;
     }
+    // window of u: as many rows around the own range as fit after the matrix slice (or, when the matrix does not fit, in
+    // what is left after the vectors); at least the own rows, else no window at all
     const size_t mat_bytes = ((sizeof(int) * (size_t)nb + 15) & ~(size_t)15) + ((sizeof(float) * 9 * (size_t)nb + 15) & ~(size_t)15);
-    const bool mat_fit = vec_fit && off + mat_bytes <= A.smem_bytes;
+    const size_t min_win = ((sizeof(double) * 3 * ((size_t)nr + 2) + 15) & ~(size_t)15);
+    const bool mat_fit = vec_fit && off + mat_bytes + min_win <= A.smem_bytes;
     const int32_t* cols; const float* vals;
     if (mat_fit) {
         int32_t* cs = reinterpret_cast<int32_t*>(smem + carve(sizeof(int) * (size_t)nb));
@@ -234,6 +277,20 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_solve(const PcgArgs A)
     } else {
         cols = A.cols + b0; vals = A.vals + 9 * b0;
     }
+    int w0 = r0, nwin = 0;     // window = block rows [w0, w0 + nwin)
+    double* uwin = nullptr;
+    if (vec_fit && off + min_win <= A.smem_bytes) {
+        const int cap_rows = (int)(((size_t)A.smem_bytes - off) / (sizeof(double) * 3)) & ~1;   // even: 16 B granularity of the bulk copy
+        const int half = (cap_rows - nr) / 2;
+        w0 = max(0, r0 - half) & ~1;
+        int w1 = min(nbr, w0 + cap_rows);
+        nwin = w1 - w0;
+        uwin = reinterpret_cast<double*>(smem + off);
+    }
+    const bool own_in_win = nwin > 0;   // by construction the window then contains [r0, r0 + nr)
+    // the bulk copy moves multiples of 16 B: with an odd row count (only possible at the very end of the vector) it also
+    // copies the 8 B of padding behind u (the buffer is allocated with that slack)
+    const unsigned win_bytes = (unsigned)((sizeof(double) * 3 * (size_t)nwin + 15) & ~(size_t)15);
     for (int i = tid; i <= nr; i += PCG_THREADS) rp[i] = (int)(A.rows[r0 + i] - b0);
     if (tid == 0) s_n_long = 0;
     __syncthreads();
@@ -244,21 +301,89 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_solve(const PcgArgs A)
         }
     __syncthreads();
     const int n_long = min(s_n_long, MAX_LONG_ROWS);
-    auto is_swept = [&](int lr) {   // long AND listed (the list order is irrelevant: every listed row gets its own block reduction)
+    auto is_swept = [&](int lr) {   // long AND listed (every listed row gets its own block reduction)
         if (rp[lr + 1] - rp[lr] <= LONG_ROW) return false;
         for (int k = 0; k < n_long; k++) if (s_long[k] == lr) return true;
         return false;
     };
-    double* pg = A.p + 3 * (size_t)r0;   // own slice of the global direction vector
+    double* ug = A.u + 3 * (size_t)r0;                           // own slice of the global u
+    const double* uo_win = own_in_win ? uwin + 3 * (size_t)(r0 - w0) : nullptr;
+    auto uo = [&](int i) -> double { return own_in_win ? uo_win[i] : __ldcg(ug + i); };   // own slice of u as this CTA reads it
+    double* xg = A.x + 3 * (size_t)r0;                           // x is only ever touched by its owner thread
     const unsigned long long t_loaded = global_ns();
 
-    int it = 0, done = 0, found_indef = 0;
-    double error = 1.0;               // x0 = 0 -> r = b
-    const double error0 = 1.0;
+    // gather of u at scalar column c (first of the three of a block column)
+    const int win_lo = 3 * w0, win_hi = 3 * (w0 + nwin);
+    auto gather3 = [&](int c, double& a0, double& a1, double& a2) {
+        if (c >= win_lo && c < win_hi) { const double* q = uwin + (c - win_lo); a0 = q[0]; a1 = q[1]; a2 = q[2]; }
+        else { a0 = __ldcg(A.u + c); a1 = __ldcg(A.u + c + 1); a2 = __ldcg(A.u + c + 2); }
+    };
+    unsigned win_phase = 0;
+    // pull the window of u (all CTAs have published their slices: call after a grid barrier)
+    auto load_window = [&]() {
+        if (!own_in_win) return;
+        if (tid == 0) {
+            asm volatile("fence.proxy.async;" ::: "memory");
+            mbar_expect_tx(&s_mbar, win_bytes);
+            tma_load_bulk(uwin, A.u + 3 * (size_t)w0, win_bytes, &s_mbar);
+        }
+        mbar_wait(&s_mbar, win_phase);
+        win_phase ^= 1u;
+    };
+    // w = A u on the own rows; returns this thread's share of w.u
+    const int lane = tid % LANES_PER_ROW;
+    constexpr int rows_per_pass = PCG_THREADS / LANES_PER_ROW;
+    auto spmv = [&]() -> double {
+        double wu = 0.0;
+        for (int base = 0; base < nr; base += rows_per_pass) {
+            const int lr = base + tid / LANES_PER_ROW;
+            double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+            const bool swept = (lr < nr) && is_swept(lr);
+            if (lr < nr && !swept) {
+                const int j1 = rp[lr + 1];
+                for (int j = rp[lr] + lane; j < j1; j += LANES_PER_ROW) {
+                    const float* m = vals + 9 * (size_t)j;   // column-major 3x3
+                    double a0, a1, a2;
+                    gather3(cols[j], a0, a1, a2);
+                    y0 += (double)m[0] * a0 + (double)m[3] * a1 + (double)m[6] * a2;
+                    y1 += (double)m[1] * a0 + (double)m[4] * a1 + (double)m[7] * a2;
+                    y2 += (double)m[2] * a0 + (double)m[5] * a1 + (double)m[8] * a2;
+                }
+            }
+            for (int o = LANES_PER_ROW / 2; o > 0; o >>= 1) {
+                y0 += __shfl_down_sync(0xffffffffu, y0, o, LANES_PER_ROW);
+                y1 += __shfl_down_sync(0xffffffffu, y1, o, LANES_PER_ROW);
+                y2 += __shfl_down_sync(0xffffffffu, y2, o, LANES_PER_ROW);
+            }
+            if (lane == 0 && lr < nr && !swept) {
+                ws[3 * lr] = y0; ws[3 * lr + 1] = y1; ws[3 * lr + 2] = y2;
+                wu += uo(3 * lr) * y0 + uo(3 * lr + 1) * y1 + uo(3 * lr + 2) * y2;
+            }
+        }
+        // long rows: one block per thread and trip, block-wide reduction (fixed tree: deterministic)
+        for (int k = 0; k < n_long; k++) {
+            const int lr = s_long[k];
+            double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+            for (int j = rp[lr] + tid; j < rp[lr + 1]; j += PCG_THREADS) {
+                const float* m = vals + 9 * (size_t)j;
+                double a0, a1, a2;
+                gather3(cols[j], a0, a1, a2);
+                y0 += (double)m[0] * a0 + (double)m[3] * a1 + (double)m[6] * a2;
+                y1 += (double)m[1] * a0 + (double)m[4] * a1 + (double)m[7] * a2;
+                y2 += (double)m[2] * a0 + (double)m[5] * a1 + (double)m[8] * a2;
+            }
+            y0 = block_sum(y0, s); y1 = block_sum(y1, s); y2 = block_sum(y2, s);
+            if (tid == 0) {
+                ws[3 * lr] = y0; ws[3 * lr + 1] = y1; ws[3 * lr + 2] = y2;
+                wu += uo(3 * lr) * y0 + uo(3 * lr + 1) * y1 + uo(3 * lr + 2) * y2;
+            }
+        }
+        return wu;
+    };
 
-    // ---- phase 0: M^-1 = block-Jacobi inverse; x = 0, r = b = -grad, z = M^-1 r, p = z ; partials of b.b and r.z ----
+    // ---- phase 0: M^-1 = block-Jacobi inverse; x = 0, r = b = -grad, u = M^-1 r, p = s = 0 ; partials of b.b and r.u ----
     {
-        double bb = 0.0, rz = 0.0;
+        double bb = 0.0, ru = 0.0;
         for (int lr = tid; lr < nr; lr += PCG_THREADS) {
             const int br = r0 + lr;
             // closed-form inverse of the symmetric 3x3 diagonal block, in float like the reference (BlockedSparseMatrix.h:1198-1214)
@@ -293,133 +418,103 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_solve(const PcgArgs A)
             const double g0 = -A.grad[3 * br], g1 = -A.grad[3 * br + 1], g2 = -A.grad[3 * br + 2];
             double z0, z1, z2;
             apply_dinv(mi, g0, g1, g2, z0, z1, z2);
-            xs[3 * lr] = 0.0; xs[3 * lr + 1] = 0.0; xs[3 * lr + 2] = 0.0;
+            for (int c = 0; c < 3; c++) { xg[3 * lr + c] = 0.0; ps[3 * lr + c] = 0.0; ss[3 * lr + c] = 0.0; }
             rs[3 * lr] = g0; rs[3 * lr + 1] = g1; rs[3 * lr + 2] = g2;
-            __stcg(pg + 3 * lr, z0); __stcg(pg + 3 * lr + 1, z1); __stcg(pg + 3 * lr + 2, z2);
+            __stcg(ug + 3 * lr, z0); __stcg(ug + 3 * lr + 1, z1); __stcg(ug + 3 * lr + 2, z2);
             bb += g0 * g0 + g1 * g1 + g2 * g2;
-            rz += g0 * z0 + g1 * z1 + g2 * z2;
+            ru += g0 * z0 + g1 * z1 + g2 * z2;
         }
         const double t0 = block_sum(bb, s);
         if (tid == 0) __stcg(part0 + blockIdx.x, t0);
-        const double t1 = block_sum(rz, s);
+        const double t1 = block_sum(ru, s);
         if (tid == 0) __stcg(part1 + blockIdx.x, t1);
     }
     grid_barrier(A.barrier, epoch);
     const double bb = all_partials(part0, s, &bc);
-    double rz = all_partials(part1, s, &bc);
-    grid_barrier(A.barrier, epoch);   // part0 / part1 are rewritten below
+    double gamma = all_partials(part1, s, &bc);
 
+    int it = 0, done = 0, found_indef = 0;
+    double error = 1.0;               // x0 = 0 -> r = b
+    const double error0 = 1.0;
     if (bb < A.abs_tol * A.abs_tol) { done = 1; error = 0.0; }   // zero right-hand side
     else if (1.0 < A.abs_tol) done = 1;
     else if (A.max_iter <= 0) done = 3;
 
     const unsigned long long t_loop = global_ns();
-    const int lane = tid % LANES_PER_ROW;
-    constexpr int rows_per_pass = PCG_THREADS / LANES_PER_ROW;
-    while (!done) {
-        // ---- Ap = A p (LANES_PER_ROW lanes per block row; matrix from shared memory, p gathered from L2); partial of p.Ap ----
-        {
-            double pAp = 0.0;
-            for (int base = 0; base < nr; base += rows_per_pass) {
-                const int lr = base + tid / LANES_PER_ROW;
-                double y0 = 0.0, y1 = 0.0, y2 = 0.0;
-                const bool swept = (lr < nr) && is_swept(lr);
-                if (lr < nr && !swept) {
-                    const int j1 = rp[lr + 1];
-                    int j = rp[lr] + lane;
-                    // two blocks per trip: their six gathers of p are in flight together
-                    for (; j + LANES_PER_ROW < j1; j += 2 * LANES_PER_ROW) {
-                        const float* m = vals + 9 * (size_t)j;
-                        const float* n = m + 9 * LANES_PER_ROW;
-                        const int ca = cols[j], cb = cols[j + LANES_PER_ROW];
-                        const double a0 = __ldcg(A.p + ca), a1 = __ldcg(A.p + ca + 1), a2 = __ldcg(A.p + ca + 2);
-                        const double b0v = __ldcg(A.p + cb), b1 = __ldcg(A.p + cb + 1), b2 = __ldcg(A.p + cb + 2);
-                        y0 += (double)m[0] * a0 + (double)m[3] * a1 + (double)m[6] * a2;
-                        y1 += (double)m[1] * a0 + (double)m[4] * a1 + (double)m[7] * a2;
-                        y2 += (double)m[2] * a0 + (double)m[5] * a1 + (double)m[8] * a2;
-                        y0 += (double)n[0] * b0v + (double)n[3] * b1 + (double)n[6] * b2;
-                        y1 += (double)n[1] * b0v + (double)n[4] * b1 + (double)n[7] * b2;
-                        y2 += (double)n[2] * b0v + (double)n[5] * b1 + (double)n[8] * b2;
-                    }
-                    if (j < j1) {
-                        const float* m = vals + 9 * (size_t)j;
-                        const int ca = cols[j];
-                        const double a0 = __ldcg(A.p + ca), a1 = __ldcg(A.p + ca + 1), a2 = __ldcg(A.p + ca + 2);
-                        y0 += (double)m[0] * a0 + (double)m[3] * a1 + (double)m[6] * a2;
-                        y1 += (double)m[1] * a0 + (double)m[4] * a1 + (double)m[7] * a2;
-                        y2 += (double)m[2] * a0 + (double)m[5] * a1 + (double)m[8] * a2;
-                    }
-                }
-                for (int o = LANES_PER_ROW / 2; o > 0; o >>= 1) {
-                    y0 += __shfl_down_sync(0xffffffffu, y0, o, LANES_PER_ROW);
-                    y1 += __shfl_down_sync(0xffffffffu, y1, o, LANES_PER_ROW);
-                    y2 += __shfl_down_sync(0xffffffffu, y2, o, LANES_PER_ROW);
-                }
-                if (lane == 0 && lr < nr && !swept) {
-                    Aps[3 * lr] = y0; Aps[3 * lr + 1] = y1; Aps[3 * lr + 2] = y2;
-                    pAp += __ldcg(pg + 3 * lr) * y0 + __ldcg(pg + 3 * lr + 1) * y1 + __ldcg(pg + 3 * lr + 2) * y2;
-                }
-            }
-            // long rows: one block per thread and trip, block-wide reduction (fixed tree: deterministic)
-            for (int k = 0; k < n_long; k++) {
-                const int lr = s_long[k];
-                double y0 = 0.0, y1 = 0.0, y2 = 0.0;
-                for (int j = rp[lr] + tid; j < rp[lr + 1]; j += PCG_THREADS) {
-                    const float* m = vals + 9 * (size_t)j;
-                    const int ca = cols[j];
-                    const double a0 = __ldcg(A.p + ca), a1 = __ldcg(A.p + ca + 1), a2 = __ldcg(A.p + ca + 2);
-                    y0 += (double)m[0] * a0 + (double)m[3] * a1 + (double)m[6] * a2;
-                    y1 += (double)m[1] * a0 + (double)m[4] * a1 + (double)m[7] * a2;
-                    y2 += (double)m[2] * a0 + (double)m[5] * a1 + (double)m[8] * a2;
-                }
-                y0 = block_sum(y0, s); y1 = block_sum(y1, s); y2 = block_sum(y2, s);
-                if (tid == 0) {
-                    Aps[3 * lr] = y0; Aps[3 * lr + 1] = y1; Aps[3 * lr + 2] = y2;
-                    pAp += __ldcg(pg + 3 * lr) * y0 + __ldcg(pg + 3 * lr + 1) * y1 + __ldcg(pg + 3 * lr + 2) * y2;
-                }
-            }
-            const double t = block_sum(pAp, s);   // (its __syncthreads also publish Aps to the update phase below)
-            if (tid == 0) __stcg(part0 + blockIdx.x, t);
-        }
+    long long c_spmv = 0, c_bar = 0, c_red = 0, c_vec = 0, c_t = A.instrument ? clock64() : 0;
+#define PCG_TICK(acc) if (A.instrument) { const long long _n = clock64(); acc += _n - c_t; c_t = _n; }
+    double alpha = 0.0, beta = 0.0;
+    if (!done) {
+        // ---- first product: w = A u ; delta = w.u = p^T A p of the first iteration ----
+        load_window();
+        const double wu = spmv();
+        const double t = block_sum(wu, s);
+        if (tid == 0) __stcg(part2 + blockIdx.x, t);
+        PCG_TICK(c_spmv);
         grid_barrier(A.barrier, epoch);
-        const double pAp = all_partials(part0, s, &bc);
-        it++;
-        if (pAp <= 0.0) {
+        PCG_TICK(c_bar);
+        const double delta = all_partials(part2, s, &bc);
+        PCG_TICK(c_red);
+        if (delta <= 0.0) {
             found_indef = 1;
-            if (A.stop_on_indef) { done = 2; break; }   // x is returned as is (solve_pcg.h:183-192)
+            if (A.stop_on_indef) { it = 1; done = 2; }   // x is returned as is (solve_pcg.h:183-192)
         }
-        // ---- alpha = rz / pAp ; x += alpha p ; r -= alpha Ap ; z = M^-1 r ; partials of r.r and r.z (all in shared memory) ----
-        const double alpha = rz / pAp;
+        alpha = gamma / delta;
+    }
+    while (!done) {
+        it++;
+        // ---- p = u + beta p ; s = w + beta s ; x += alpha p ; r -= alpha s ; u = M^-1 r ; partials of r.r and r.u ----
         {
-            double rr = 0.0, rzn = 0.0;
+            double rr = 0.0, ru = 0.0;
             for (int lr = tid; lr < nr; lr += PCG_THREADS) {
-                double q0 = rs[3 * lr], q1 = rs[3 * lr + 1], q2 = rs[3 * lr + 2];
-                xs[3 * lr] += alpha * __ldcg(pg + 3 * lr); xs[3 * lr + 1] += alpha * __ldcg(pg + 3 * lr + 1); xs[3 * lr + 2] += alpha * __ldcg(pg + 3 * lr + 2);
-                q0 -= alpha * Aps[3 * lr]; q1 -= alpha * Aps[3 * lr + 1]; q2 -= alpha * Aps[3 * lr + 2];
-                rs[3 * lr] = q0; rs[3 * lr + 1] = q1; rs[3 * lr + 2] = q2;
-                double z0, z1, z2;
-                apply_dinv(dinv + 9 * lr, q0, q1, q2, z0, z1, z2);
-                zs[3 * lr] = z0; zs[3 * lr + 1] = z1; zs[3 * lr + 2] = z2;
-                rr += q0 * q0 + q1 * q1 + q2 * q2;
-                rzn += q0 * z0 + q1 * z1 + q2 * z2;
+                double q[3], z0, z1, z2;
+                for (int c = 0; c < 3; c++) {
+                    const double pn = uo(3 * lr + c) + beta * ps[3 * lr + c];
+                    const double sn = ws[3 * lr + c] + beta * ss[3 * lr + c];
+                    ps[3 * lr + c] = pn; ss[3 * lr + c] = sn;
+                    xg[3 * lr + c] += alpha * pn;
+                    q[c] = rs[3 * lr + c] - alpha * sn;
+                    rs[3 * lr + c] = q[c];
+                }
+                apply_dinv(dinv + 9 * lr, q[0], q[1], q[2], z0, z1, z2);
+                __stcg(ug + 3 * lr, z0); __stcg(ug + 3 * lr + 1, z1); __stcg(ug + 3 * lr + 2, z2);
+                rr += q[0] * q[0] + q[1] * q[1] + q[2] * q[2];
+                ru += q[0] * z0 + q[1] * z1 + q[2] * z2;
             }
             const double t0 = block_sum(rr, s);
-            if (tid == 0) __stcg(part1 + blockIdx.x, t0);
-            const double t1 = block_sum(rzn, s);
-            if (tid == 0) __stcg(part2 + blockIdx.x, t1);
+            if (tid == 0) __stcg(part0 + blockIdx.x, t0);
+            const double t1 = block_sum(ru, s);
+            if (tid == 0) __stcg(part1 + blockIdx.x, t1);
         }
+        PCG_TICK(c_vec);
         grid_barrier(A.barrier, epoch);
-        const double rr = all_partials(part1, s, &bc);
+        PCG_TICK(c_bar);
+        const double rr = all_partials(part0, s, &bc);
         error = sqrt(rr / bb);
         if (error < A.abs_tol || error / error0 < A.rel_tol) { done = 1; break; }
-        const double rz_new = all_partials(part2, s, &bc);
-        const double beta = rz_new / rz;
-        rz = rz_new;
+        const double gamma_new = all_partials(part1, s, &bc);
+        PCG_TICK(c_red);
         if (it >= A.max_iter) { done = 3; break; }
-        // ---- p = z + beta p on the own slice (same thread <-> row mapping as the update phase) ----
-        for (int lr = tid; lr < nr; lr += PCG_THREADS)
-            for (int c = 0; c < 3; c++) __stcg(pg + 3 * lr + c, zs[3 * lr + c] + beta * __ldcg(pg + 3 * lr + c));
+        // ---- w = A u ; delta = w.u ----
+        load_window();
+        {
+            const double wu = spmv();
+            const double t = block_sum(wu, s);
+            if (tid == 0) __stcg(part2 + blockIdx.x, t);
+        }
+        PCG_TICK(c_spmv);
         grid_barrier(A.barrier, epoch);
+        PCG_TICK(c_bar);
+        const double delta = all_partials(part2, s, &bc);
+        PCG_TICK(c_red);
+        beta = gamma_new / gamma;
+        const double pAp = delta - beta * gamma_new / alpha;     // p^T A p of the coming iteration
+        gamma = gamma_new;
+        if (pAp <= 0.0) {
+            found_indef = 1;
+            if (A.stop_on_indef) { it++; done = 2; break; }      // the reference counts the iteration that meets it
+        }
+        alpha = gamma / pAp;
     }
 
     // ---- du = x ; du.grad and |du|_inf ----
@@ -427,7 +522,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_solve(const PcgArgs A)
         double dg = 0.0, mx = 0.0;
         for (int lr = tid; lr < nr; lr += PCG_THREADS) {
             for (int c = 0; c < 3; c++) {
-                const double v = xs[3 * lr + c];
+                const double v = xg[3 * lr + c];
                 A.du[3 * (size_t)(r0 + lr) + c] = v;
                 dg += v * A.grad[3 * (size_t)(r0 + lr) + c];
                 mx = fmax(mx, fabs(v));
@@ -446,6 +541,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_solve(const PcgArgs A)
             PcgResult R;
             R.du_dot_grad = dg; R.du_inf = mx; R.error = error; R.bb = bb;
             R.it = it; R.done = done; R.found_indef = found_indef; R.pad = 0;
+            R.c_spmv = c_spmv; R.c_bar = c_bar; R.c_red = c_red; R.c_vec = c_vec;
             R.t_start = t_start; R.t_loaded = t_loaded; R.t_loop = t_loop; R.t_end = global_ns();
             *A.result = R;
         }
@@ -463,7 +559,7 @@ int solve_pcg_internal(sb_context* ctx, double abs_tol, double rel_tol, int max_
     Pcg* P = get(ctx);
     cudaStream_t st = ctx->stream;
     const int n = ctx->ndofs;
-    P->r.ensure(n); P->z.ensure(n); P->p.ensure(n); P->Ap.ensure(n); P->x.ensure(n); P->dinv.ensure(9 * (size_t)nbr);
+    P->r.ensure(n); P->p.ensure(n); P->s.ensure(n); P->w.ensure(n); P->u.ensure(n + 2); P->x.ensure(n); P->dinv.ensure(9 * (size_t)nbr);
     P->part.ensure(3 * PCG_MAX_BLOCKS);
     P->rp_scratch.ensure((size_t)nbr + PCG_MAX_BLOCKS + 1);
     ctx->du.ensure(n);
@@ -484,9 +580,9 @@ int solve_pcg_internal(sb_context* ctx, double abs_tol, double rel_tol, int max_
     }
     PcgArgs A;
     A.rows = rows; A.cols = cols; A.vals = vals; A.grad = ctx->grad.p; A.dinv = P->dinv.p;
-    A.x = P->x.p; A.r = P->r.p; A.z = P->z.p; A.p = P->p.p; A.Ap = P->Ap.p; A.du = ctx->du.p;
+    A.x = P->x.p; A.r = P->r.p; A.p = P->p.p; A.s = P->s.p; A.w = P->w.p; A.u = P->u.p; A.du = ctx->du.p;
     A.part = P->part.p; A.rp_scratch = P->rp_scratch.p; A.barrier = P->d_barrier; A.result = P->d_result;
-    A.nnzb = nnzb; A.smem_bytes = P->smem_bytes;
+    A.nnzb = nnzb; A.smem_bytes = P->smem_bytes; A.instrument = ctx->profile ? 1 : 0;
     A.nbr = nbr; A.abs_tol = abs_tol; A.rel_tol = rel_tol; A.max_iter = max_iter; A.stop_on_indef = stop_on_indef;
     SB_CUDA(ctx, cudaMemsetAsync(P->d_barrier, 0, sizeof(unsigned), st));
     void* args[] = {(void*)&A};
@@ -500,6 +596,8 @@ int solve_pcg_internal(sb_context* ctx, double abs_tol, double rel_tol, int max_
         ctx->stage_ms[ST_CG_ITERATIONS] += 1e-6 * (double)(P->h_result->t_end - P->h_result->t_loop);          // iterations + final reduction
         ctx->stage_ms[ST_PCG_SETUP] += 1e-6 * (double)(P->h_result->t_loop - P->h_result->t_start);              // slice load + preconditioner
         ctx->stage_calls[ST_PCG_SETUP]++;
+        ctx->stage_calls[ST_PCG_C_SPMV] += P->h_result->c_spmv; ctx->stage_calls[ST_PCG_C_BAR] += P->h_result->c_bar;
+        ctx->stage_calls[ST_PCG_C_RED] += P->h_result->c_red; ctx->stage_calls[ST_PCG_C_VEC] += P->h_result->c_vec;
     }
     if (out_iterations) *out_iterations = P->h_result->it;
     if (out_ok) *out_ok = (P->h_result->done == 1) ? 1 : 0;
