@@ -1,15 +1,24 @@
 // Global Hessian assembly: element Hessians (COO of 3x3 blocks) -> 3x3-block CSR, float storage.
 //
 // Replaces ElementHessians::{assemble_global, update_global} (symx/solver/second_order/ElementHessians.cpp:224-294)
-// and BlockedSparseMatrix::{start_insertion, add_block, end_insertion} (bsm/BlockedSparseMatrix.h:332-593, 782-895).
-// The reference inserts every block under a per-row mutex after a binary search; here assembly is split into
-//   * a SYMBOLIC phase, run only when some connectivity changed: one 64-bit key (block_row, block_col) per element
-//     block, radix sort, run-length heads -> BCSR pattern + for every BCSR block the contiguous list of its sources;
+// and BlockedSparseMatrix::{start_insertion, add_block, update_block, end_insertion} (bsm/BlockedSparseMatrix.h:332-593,
+// 782-895).  The reference inserts every block under a per-row mutex after a binary search; here assembly is
+//   * a STATIC SYMBOLIC phase, run only when a mesh / joint connectivity changes (practically once): one 64-bit key
+//     (block_row, block_col) per element block of the static potentials (3.4 M at the 200k-tet scene), radix sort,
+//     run-length heads -> the static block list and, per block, the contiguous list of its sources;
+//   * a DYNAMIC SYMBOLIC phase, run whenever the contact / friction tables changed (every evaluation in contact): the few
+//     thousand blocks of the contact elements are sorted and reduced the same way, then MERGED into the static list --
+//     a binary search per dynamic block, a rank per static block -- which yields the final pattern (rows / cols) and, per
+//     final block, its static and its dynamic source segment.  Cost: O(#contact blocks log) + two passes over the
+//     pattern, instead of re-sorting millions of unchanged keys;
 //   * a NUMERIC phase: a segmented reduction -- nine threads per BCSR block sum their sources in FP64 and store float
-//     (the reference accumulates in float in thread order, BlockedSparseMatrix.h:899-952).
+//     (the reference accumulates in float in thread order, BlockedSparseMatrix.h:899-952); blocks with very many sources
+//     (a rigid body touched by thousands of contacts) get a CTA each; after a PD projection only the blocks of the
+//     projected elements are re-summed (the reference's update_global adds projected - original).
 // Output layout is the reference's (BlockedSparseMatrix.h:266-271): rows = offsets per block row, cols = first scalar
 // column of the block, vals = 9 floats per block, column-major inside the block.
 #include "internal.h"
+#include <algorithm>
 #include <cub/cub.cuh>
 
 namespace sb {
@@ -17,50 +26,76 @@ namespace sb {
 struct PotDesc {
     unsigned long long H_off;     // offset of the potential's element Hessians in ctx->H
     unsigned long long rows_off;  // offset of its block rows in ctx->rows
-    unsigned long long blk_off;   // offset of its element blocks in the source numbering
+    unsigned long long blk_off;   // offset of its element blocks in the source numbering of its class (static / dynamic)
     int n_elem, nb;
 };
 
-struct Assembly {
-    uint64_t built_version = 0;
-    size_t built_n_src = 0;
-    size_t n_src = 0;
-    int nbr = 0;
-    size_t nnzb = 0;
+// one sorted-and-reduced class of sources (static or dynamic)
+struct SourceSet {
+    size_t n = 0;                    // sources
+    size_t n_blocks = 0;             // distinct (row, col) keys
     DevBuf<uint64_t> keys, keys_sorted;
     DevBuf<uint32_t> ids, ids_sorted;
     DevBuf<uint32_t> src_off;        // per source (unsorted numbering): offset of its (0,0) entry in ctx->H
     DevBuf<uint8_t> src_pitch;       // per source: row pitch n of its element Hessian
     DevBuf<uint32_t> sorted_off;     // per sorted source
     DevBuf<uint8_t> sorted_pitch;
-    DevBuf<uint32_t> head, blk_of;   // head flags / BCSR block of every sorted source
-    DevBuf<uint32_t> seg;            // [nnzb + 1] first sorted source of every BCSR block
+    DevBuf<uint32_t> head, blk_of;   // head flags / 1-based block of every sorted source
+    DevBuf<uint64_t> blk_key;        // [n_blocks] key of every distinct block
+    DevBuf<uint32_t> seg;            // [n_blocks + 1] first sorted source of every block
+    DevBuf<uint32_t> blk_of_src;     // per source (unsorted numbering): its block in THIS set
+    void release()
+    {
+        keys.release(); keys_sorted.release(); ids.release(); ids_sorted.release(); src_off.release(); src_pitch.release();
+        sorted_off.release(); sorted_pitch.release(); head.release(); blk_of.release(); blk_key.release(); seg.release(); blk_of_src.release();
+    }
+};
+
+struct Assembly {
+    uint64_t built_static = 0, built_dynamic = 0;
+    size_t built_n_src = 0;
+    int nbr = 0;
+    size_t nnzb = 0;
+    SourceSet S, D;                  // static / dynamic sources
+    // merge
+    DevBuf<uint32_t> d_pos;          // per dynamic block: lower bound in the static block list
+    DevBuf<uint32_t> d_isnew, d_newrank;   // per dynamic block: not in the static list / inclusive rank among the new ones
+    DevBuf<uint32_t> newpos;         // per new block: its d_pos (ascending)
+    DevBuf<uint32_t> s_final;        // per static block: final BCSR block
+    DevBuf<uint32_t> d_final;        // per dynamic block: final BCSR block
+    DevBuf<int4> seg4;               // per final block: static [x, y) and dynamic [z, w) sorted-source ranges
     DevBuf<int32_t> blk_row;         // [nnzb] block row of every BCSR block
     DevBuf<unsigned long long> rows; // [nbr + 1]
     DevBuf<int32_t> cols;            // [nnzb] scalar column
     DevBuf<float> vals;              // [9 nnzb]
     DevBuf<uint8_t> temp;            // cub scratch
-    DevBuf<uint32_t> blk_of_src;     // per source (unsorted numbering): its BCSR block
     DevBuf<uint8_t> dirty;           // per BCSR block: a source changed since the last numeric pass (PD projection)
-    DevBuf<uint32_t> long_blocks;    // BCSR blocks with more than LONG_SEG sources (rigid bodies touched by many contacts)
-    int* d_n_long = nullptr;
+    DevBuf<uint32_t> long_blocks;    // BCSR blocks with more than LONG_SEG sources
+    int* d_counts = nullptr;         // [0] long blocks [1] new blocks
+    int* h_counts = nullptr;
     uint64_t assembled_eval = 0;     // evaluation the values belong to
     bool numeric_valid = false;
 };
 
 static Assembly* get(sb_context* ctx)
 {
-    if (!ctx->assembly) ctx->assembly = new Assembly();
+    if (!ctx->assembly) {
+        ctx->assembly = new Assembly();
+        cudaMalloc(&ctx->assembly->d_counts, 4 * sizeof(int));
+        cudaMallocHost(&ctx->assembly->h_counts, 4 * sizeof(int));
+    }
     return ctx->assembly;
 }
 void assembly_destroy(sb_context* ctx)
 {
     Assembly* A = ctx->assembly;
     if (!A) return;
-    A->keys.release(); A->keys_sorted.release(); A->ids.release(); A->ids_sorted.release(); A->src_off.release();
-    A->src_pitch.release(); A->sorted_off.release(); A->sorted_pitch.release(); A->head.release(); A->blk_of.release();
-    A->seg.release(); A->blk_row.release(); A->rows.release(); A->cols.release(); A->vals.release(); A->temp.release(); A->blk_of_src.release(); A->dirty.release(); A->long_blocks.release();
-    if (A->d_n_long) cudaFree(A->d_n_long);
+    A->S.release(); A->D.release();
+    A->d_pos.release(); A->d_isnew.release(); A->d_newrank.release(); A->newpos.release(); A->s_final.release(); A->d_final.release();
+    A->seg4.release(); A->blk_row.release(); A->rows.release(); A->cols.release(); A->vals.release(); A->temp.release();
+    A->dirty.release(); A->long_blocks.release();
+    if (A->d_counts) cudaFree(A->d_counts);
+    if (A->h_counts) cudaFreeHost(A->h_counts);
     delete A;
     ctx->assembly = nullptr;
 }
@@ -90,25 +125,91 @@ __global__ void k_heads(const uint64_t* __restrict__ keys, uint32_t* __restrict_
     head[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
 }
 
-// blk_of = inclusive scan of head (1-based); fill the pattern at heads, gather the per-source offsets in sorted order
-__global__ void k_fill_pattern(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ head, const uint32_t* __restrict__ blk_of,
-                               const uint32_t* __restrict__ ids_sorted, const uint32_t* __restrict__ src_off, const uint8_t* __restrict__ src_pitch,
-                               uint32_t* __restrict__ sorted_off, uint8_t* __restrict__ sorted_pitch,
-                               uint32_t* __restrict__ seg, int32_t* __restrict__ blk_row, int32_t* __restrict__ cols, uint32_t* __restrict__ blk_of_src, size_t n)
+// blk_of = inclusive scan of head (1-based); block keys and segment starts at heads; per-source offsets in sorted order
+__global__ void k_fill_set(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ head, const uint32_t* __restrict__ blk_of,
+                           const uint32_t* __restrict__ ids_sorted, const uint32_t* __restrict__ src_off, const uint8_t* __restrict__ src_pitch,
+                           uint32_t* __restrict__ sorted_off, uint8_t* __restrict__ sorted_pitch,
+                           uint32_t* __restrict__ seg, uint64_t* __restrict__ blk_key, uint32_t* __restrict__ blk_of_src, size_t n)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t id = ids_sorted[i];
     sorted_off[i] = src_off[id];
     sorted_pitch[i] = src_pitch[id];
-    blk_of_src[id] = blk_of[i] - 1;
+    const uint32_t b = blk_of[i] - 1;
+    blk_of_src[id] = b;
     if (head[i]) {
-        const uint32_t b = blk_of[i] - 1;
-        const uint64_t k = keys[i];
         seg[b] = (uint32_t)i;
-        blk_row[b] = (int32_t)(k >> 32);
-        cols[b] = 3 * (int32_t)(k & 0xffffffffu);
+        blk_key[b] = keys[i];
     }
+    if (i == n - 1) seg[b + 1] = (uint32_t)n;
+}
+
+// ---- merge of the dynamic block list into the static one ----
+__global__ void k_dyn_locate(const uint64_t* __restrict__ dkey, size_t ndb, const uint64_t* __restrict__ skey, size_t nsb,
+                             uint32_t* __restrict__ d_pos, uint32_t* __restrict__ d_isnew)
+{
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ndb) return;
+    const uint64_t k = dkey[j];
+    size_t lo = 0, hi = nsb;
+    while (lo < hi) {
+        const size_t mid = (lo + hi) >> 1;
+        if (skey[mid] < k) lo = mid + 1; else hi = mid;
+    }
+    d_pos[j] = (uint32_t)lo;
+    d_isnew[j] = (lo < nsb && skey[lo] == k) ? 0u : 1u;
+}
+// compacted list of the positions of the new blocks; their total
+__global__ void k_dyn_compact(const uint32_t* __restrict__ d_pos, const uint32_t* __restrict__ d_isnew, const uint32_t* __restrict__ d_newrank_incl,
+                              uint32_t* __restrict__ newpos, size_t ndb, int* __restrict__ n_new)
+{
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ndb) return;
+    if (d_isnew[j]) newpos[d_newrank_incl[j] - 1] = d_pos[j];
+    if (j == ndb - 1) *n_new = (int)d_newrank_incl[j];
+}
+// final index of every static block = own index + number of new blocks inserted before it (new keys with pos <= i)
+__global__ void k_static_final(const uint64_t* __restrict__ skey, const uint32_t* __restrict__ sseg, size_t nsb,
+                               const uint32_t* __restrict__ newpos, const int* __restrict__ n_new_p,
+                               uint32_t* __restrict__ s_final, int4* __restrict__ seg4, int32_t* __restrict__ blk_row, int32_t* __restrict__ cols)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nsb) return;
+    const int n_new = *n_new_p;
+    int lo = 0, hi = n_new;       // upper_bound(newpos, i)
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (newpos[mid] <= (uint32_t)i) lo = mid + 1; else hi = mid;
+    }
+    const uint32_t f = (uint32_t)i + (uint32_t)lo;
+    s_final[i] = f;
+    seg4[f] = make_int4((int)sseg[i], (int)sseg[i + 1], 0, 0);
+    const uint64_t k = skey[i];
+    blk_row[f] = (int32_t)(k >> 32);
+    cols[f] = 3 * (int32_t)(k & 0xffffffffu);
+}
+__global__ void k_dyn_final(const uint64_t* __restrict__ dkey, const uint32_t* __restrict__ dseg, size_t ndb,
+                            const uint32_t* __restrict__ d_pos, const uint32_t* __restrict__ d_isnew, const uint32_t* __restrict__ d_newrank_incl,
+                            const uint32_t* __restrict__ s_final, uint32_t* __restrict__ d_final,
+                            int4* __restrict__ seg4, int32_t* __restrict__ blk_row, int32_t* __restrict__ cols)
+{
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ndb) return;
+    uint32_t f;
+    if (d_isnew[j]) {
+        f = d_pos[j] + (d_newrank_incl[j] - 1);
+        seg4[f] = make_int4(0, 0, (int)dseg[j], (int)dseg[j + 1]);
+        const uint64_t k = dkey[j];
+        blk_row[f] = (int32_t)(k >> 32);
+        cols[f] = 3 * (int32_t)(k & 0xffffffffu);
+    } else {
+        f = s_final[d_pos[j]];
+        // the static thread wrote (x, y, 0, 0); only z, w are touched here (k_static_final has completed: stream order)
+        seg4[f].z = (int)dseg[j];
+        seg4[f].w = (int)dseg[j + 1];
+    }
+    d_final[j] = f;
 }
 
 // rows[r] = first BCSR block whose block row is >= r (blocks are sorted by (row, col))
@@ -124,85 +225,93 @@ __global__ void k_row_ptr(const int32_t* __restrict__ blk_row, unsigned long lon
     rows[r] = lo;
 }
 
-// Segmented reduction: 9 consecutive threads own one BCSR block (thread k -> entry (r = k % 3, c = k / 3), column-major).
-// Sources are summed in their sorted order (deterministic), four loads in flight per thread.  ONLY_DIRTY: re-sum just the
-// blocks a PD projection touched (the reference's update_global, ElementHessians.cpp:262-294, adds projected - original).
-// a long block is left to k_assemble_long only if it made it into the (capped) list
-__device__ __forceinline__ bool long_rank_ok(size_t b, const uint32_t* __restrict__ long_blocks, const int* __restrict__ n_long)
-{
-    const int n = *n_long;
-    if (n <= 4096) return true;          // nothing was dropped
-    for (int i = 0; i < 4096; i++) if (long_blocks[i] == (uint32_t)b) return true;
-    return false;
-}
 constexpr int LONG_SEG = 64;
 constexpr int LONG_CAP = 4096;      // long blocks beyond this many are summed by the plain path
 constexpr int LONG_CTAS = 64;
 
-__global__ void k_find_long(const uint32_t* __restrict__ seg, uint32_t* __restrict__ long_blocks, int* __restrict__ n_long, size_t nnzb)
+// a long block is left to k_assemble_long only if it made it into the (capped) list
+__device__ __forceinline__ bool long_rank_ok(size_t b, const uint32_t* __restrict__ long_blocks, const int* __restrict__ n_long)
+{
+    const int n = *n_long;
+    if (n <= LONG_CAP) return true;          // nothing was dropped
+    for (int i = 0; i < LONG_CAP; i++) if (long_blocks[i] == (uint32_t)b) return true;
+    return false;
+}
+
+__global__ void k_find_long(const int4* __restrict__ seg4, uint32_t* __restrict__ long_blocks, int* __restrict__ n_long, size_t nnzb)
 {
     const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nnzb) return;
-    if (seg[b + 1] - seg[b] > LONG_SEG) {
+    const int4 g = seg4[b];
+    if ((g.y - g.x) + (g.w - g.z) > LONG_SEG) {
         const int k = atomicAdd(n_long, 1);
         if (k < LONG_CAP) long_blocks[k] = (uint32_t)b;
     }
 }
 
+struct NumericArgs {
+    const double* H;
+    const int4* seg4;
+    const uint32_t* s_off; const uint8_t* s_pitch;   // static sources, sorted
+    const uint32_t* d_off; const uint8_t* d_pitch;   // dynamic sources, sorted
+    float* vals;
+    uint8_t* dirty;
+    const uint32_t* long_blocks; const int* n_long;
+    size_t nnzb;
+};
+
 // One CTA per long block: 32 strided partial sums per entry, then a fixed shared-memory tree (deterministic).
 template<bool ONLY_DIRTY>
-__global__ void __launch_bounds__(288) k_assemble_long(const double* __restrict__ H, const uint32_t* __restrict__ seg,
-                                                        const uint32_t* __restrict__ sorted_off, const uint8_t* __restrict__ sorted_pitch,
-                                                        float* __restrict__ vals, const uint8_t* __restrict__ dirty,
-                                                        const uint32_t* __restrict__ long_blocks, const int* __restrict__ n_long)
+__global__ void __launch_bounds__(288) k_assemble_long(const NumericArgs a)
 {
     __shared__ double sm[32][9];
-    const int total = min(*n_long, LONG_CAP);
+    const int total = min(*a.n_long, LONG_CAP);
     const int k = threadIdx.x % 9, lane = threadIdx.x / 9;
     const int r = k % 3, c = k / 3;
     for (int i = blockIdx.x; i < total; i += gridDim.x) {
-        const uint32_t b = long_blocks[i];
-        if (ONLY_DIRTY && !dirty[b]) continue;   // uniform across the CTA
-        const uint32_t s0 = seg[b], s1 = seg[b + 1];
+        const uint32_t b = a.long_blocks[i];
+        if (ONLY_DIRTY && !a.dirty[b]) continue;   // uniform across the CTA
+        const int4 g = a.seg4[b];
         double acc = 0.0;
-        for (uint32_t s = s0 + lane; s < s1; s += 32) acc += H[(size_t)sorted_off[s] + (size_t)r * sorted_pitch[s] + c];
+        for (int s = g.x + lane; s < g.y; s += 32) acc += a.H[(size_t)a.s_off[s] + (size_t)r * a.s_pitch[s] + c];
+        for (int s = g.z + lane; s < g.w; s += 32) acc += a.H[(size_t)a.d_off[s] + (size_t)r * a.d_pitch[s] + c];
         sm[lane][k] = acc;
         __syncthreads();
         for (int w = 16; w > 0; w >>= 1) {
             if (lane < w) sm[lane][k] += sm[lane + w][k];
             __syncthreads();
         }
-        if (lane == 0) vals[9 * (size_t)b + k] = (float)sm[0][k];
+        if (lane == 0) a.vals[9 * (size_t)b + k] = (float)sm[0][k];
         __syncthreads();
     }
 }
 
+// Segmented reduction: 9 consecutive threads own one BCSR block (thread k -> entry (r = k % 3, c = k / 3), column-major).
+// Sources are summed in their sorted order (deterministic): static ones first, then dynamic ones; four loads in flight.
 template<bool ONLY_DIRTY>
-__global__ void __launch_bounds__(288) k_assemble_numeric(const double* __restrict__ H, const uint32_t* __restrict__ seg,
-                                                           const uint32_t* __restrict__ sorted_off, const uint8_t* __restrict__ sorted_pitch,
-                                                           float* __restrict__ vals, uint8_t* __restrict__ dirty, size_t nnzb,
-                                                           const uint32_t* __restrict__ long_blocks, const int* __restrict__ n_long)
+__global__ void __launch_bounds__(288) k_assemble_numeric(const NumericArgs a)
 {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t b = t / 9;
-    if (b >= nnzb) return;
-    if (ONLY_DIRTY && !dirty[b]) return;
+    if (b >= a.nnzb) return;
+    if (ONLY_DIRTY && !a.dirty[b]) return;
     const int k = (int)(t - b * 9);
     const int r = k % 3, c = k / 3;
-    const uint32_t s0 = seg[b], s1 = seg[b + 1];
-    if (s1 - s0 > LONG_SEG && long_rank_ok(b, long_blocks, n_long)) return;   // summed by k_assemble_long
+    const int4 g = a.seg4[b];
+    if ((g.y - g.x) + (g.w - g.z) > LONG_SEG && long_rank_ok(b, a.long_blocks, a.n_long)) return;   // summed by k_assemble_long
     double acc = 0.0;
-    uint32_t s = s0;
-    for (; s + 4 <= s1; s += 4) {
-        const size_t o0 = (size_t)sorted_off[s] + (size_t)r * sorted_pitch[s] + c;
-        const size_t o1 = (size_t)sorted_off[s + 1] + (size_t)r * sorted_pitch[s + 1] + c;
-        const size_t o2 = (size_t)sorted_off[s + 2] + (size_t)r * sorted_pitch[s + 2] + c;
-        const size_t o3 = (size_t)sorted_off[s + 3] + (size_t)r * sorted_pitch[s + 3] + c;
-        const double v0 = H[o0], v1 = H[o1], v2 = H[o2], v3 = H[o3];
+    int s = g.x;
+    for (; s + 4 <= g.y; s += 4) {
+        const size_t o0 = (size_t)a.s_off[s] + (size_t)r * a.s_pitch[s] + c;
+        const size_t o1 = (size_t)a.s_off[s + 1] + (size_t)r * a.s_pitch[s + 1] + c;
+        const size_t o2 = (size_t)a.s_off[s + 2] + (size_t)r * a.s_pitch[s + 2] + c;
+        const size_t o3 = (size_t)a.s_off[s + 3] + (size_t)r * a.s_pitch[s + 3] + c;
+        const double v0 = a.H[o0], v1 = a.H[o1], v2 = a.H[o2], v3 = a.H[o3];
         acc += v0; acc += v1; acc += v2; acc += v3;
     }
-    for (; s < s1; s++) acc += H[(size_t)sorted_off[s] + (size_t)r * sorted_pitch[s] + c];
-    vals[t] = (float)acc;
+    for (; s < g.y; s++) acc += a.H[(size_t)a.s_off[s] + (size_t)r * a.s_pitch[s] + c];
+    for (s = g.z; s < g.w; s++) acc += a.H[(size_t)a.d_off[s] + (size_t)r * a.d_pitch[s] + c];
+    a.vals[t] = (float)acc;
 }
 // the dirty flags are cleared by a separate pass (the nine threads of a block must all have seen the flag)
 __global__ void k_clear_dirty(uint8_t* __restrict__ dirty, size_t nnzb)
@@ -211,63 +320,105 @@ __global__ void k_clear_dirty(uint8_t* __restrict__ dirty, size_t nnzb)
     if (b < nnzb) dirty[b] = 0;
 }
 
-static int build_symbolic(sb_context* ctx, Assembly* A)
+// sort + reduce one class of sources
+static int build_set(sb_context* ctx, Assembly* A, SourceSet& X, bool dynamic)
 {
-    StageTimer timer(ctx, ST_ASM_SYMBOLIC);
     cudaStream_t st = ctx->stream;
-    const size_t n = ctx->n_blocks_total;
-    if (ctx->H_total >= (1ull << 32)) return fail(ctx, SB_ERR_STATE, "sb_assemble: element Hessian storage exceeds 32-bit offsets");
-    A->n_src = n;
-    A->nbr = ctx->ndofs / 3;
-    A->keys.ensure(n + 1); A->keys_sorted.ensure(n + 1); A->ids.ensure(n + 1); A->ids_sorted.ensure(n + 1);
-    A->src_off.ensure(n + 1); A->src_pitch.ensure(n + 1); A->sorted_off.ensure(n + 1); A->sorted_pitch.ensure(n + 1);
-    A->head.ensure(n + 1); A->blk_of.ensure(n + 1); A->blk_of_src.ensure(n + 1);
-
+    size_t n = 0;
+    for (auto& p : ctx->potentials) if (p.dynamic == dynamic) n += (size_t)p.n_elem * p.k->nb * p.k->nb;
+    X.n = n;
+    X.n_blocks = 0;
+    if (n == 0) return 0;
+    X.keys.ensure(n + 1); X.keys_sorted.ensure(n + 1); X.ids.ensure(n + 1); X.ids_sorted.ensure(n + 1);
+    X.src_off.ensure(n + 1); X.src_pitch.ensure(n + 1); X.sorted_off.ensure(n + 1); X.sorted_pitch.ensure(n + 1);
+    X.head.ensure(n + 1); X.blk_of.ensure(n + 1); X.blk_of_src.ensure(n + 1);
+    X.blk_key.ensure(n + 1); X.seg.ensure(n + 2);   // upper bounds: every source its own block
     size_t blk_off = 0;
-    for (auto& p : ctx->potentials) {
-        if (p.n_elem == 0) continue;
+    for (int pi : layout_order(ctx)) {
+        Potential& p = ctx->potentials[pi];
+        if (p.dynamic != dynamic || p.n_elem == 0) continue;
         PotDesc d;
         d.H_off = p.H_off; d.rows_off = p.rows_off; d.blk_off = blk_off; d.n_elem = p.n_elem; d.nb = p.k->nb;
         const size_t cnt = (size_t)p.n_elem * d.nb * d.nb;
-        k_make_keys<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(d, ctx->rows.p, A->keys.p, A->ids.p, A->src_off.p, A->src_pitch.p);
+        k_make_keys<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(d, ctx->rows.p, X.keys.p, X.ids.p, X.src_off.p, X.src_pitch.p);
         ctx->launches++;
         blk_off += cnt;
     }
     int row_bits = 1;
     while ((1ll << row_bits) < A->nbr + 1) row_bits++;
     size_t temp_bytes = 0, tb2 = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, A->keys.p, A->keys_sorted.p, A->ids.p, A->ids_sorted.p, (int)n, 0, 32 + row_bits, st);
-    cub::DeviceScan::InclusiveSum(nullptr, tb2, A->head.p, A->blk_of.p, (int)n, st);
+    cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, X.keys.p, X.keys_sorted.p, X.ids.p, X.ids_sorted.p, (int)n, 0, 32 + row_bits, st);
+    cub::DeviceScan::InclusiveSum(nullptr, tb2, X.head.p, X.blk_of.p, (int)n, st);
     A->temp.ensure(std::max(temp_bytes, tb2) + 16);
     temp_bytes = A->temp.cap;
-    SB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(A->temp.p, temp_bytes, A->keys.p, A->keys_sorted.p, A->ids.p, A->ids_sorted.p, (int)n, 0, 32 + row_bits, st));
-    k_heads<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(A->keys_sorted.p, A->head.p, n);
+    SB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(A->temp.p, temp_bytes, X.keys.p, X.keys_sorted.p, X.ids.p, X.ids_sorted.p, (int)n, 0, 32 + row_bits, st));
+    k_heads<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(X.keys_sorted.p, X.head.p, n);
     temp_bytes = A->temp.cap;
-    SB_CUDA(ctx, cub::DeviceScan::InclusiveSum(A->temp.p, temp_bytes, A->head.p, A->blk_of.p, (int)n, st));
-    ctx->launches += 6;
-    uint32_t nnzb32 = 0;
-    SB_CUDA(ctx, cudaMemcpyAsync(&nnzb32, A->blk_of.p + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    SB_CUDA(ctx, cub::DeviceScan::InclusiveSum(A->temp.p, temp_bytes, X.head.p, X.blk_of.p, (int)n, st));
+    k_fill_set<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(X.keys_sorted.p, X.head.p, X.blk_of.p, X.ids_sorted.p, X.src_off.p, X.src_pitch.p,
+                                                             X.sorted_off.p, X.sorted_pitch.p, X.seg.p, X.blk_key.p, X.blk_of_src.p, n);
+    ctx->launches += 7;
+    uint32_t nb32 = 0;
+    SB_CUDA(ctx, cudaMemcpyAsync(&nb32, X.blk_of.p + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     SB_CUDA(ctx, cudaStreamSynchronize(st));
-    A->nnzb = nnzb32;
-    A->seg.ensure(A->nnzb + 2); A->blk_row.ensure(A->nnzb + 1); A->cols.ensure(A->nnzb + 1); A->vals.ensure(9 * A->nnzb + 9);
-    A->rows.ensure(A->nbr + 2);
-    A->dirty.ensure(A->nnzb + 1);
-    SB_CUDA(ctx, cudaMemsetAsync(A->dirty.p, 0, A->nnzb + 1, st));
-    k_fill_pattern<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(A->keys_sorted.p, A->head.p, A->blk_of.p, A->ids_sorted.p, A->src_off.p, A->src_pitch.p,
-                                                                 A->sorted_off.p, A->sorted_pitch.p, A->seg.p, A->blk_row.p, A->cols.p, A->blk_of_src.p, n);
-    const uint32_t n32 = (uint32_t)n;
-    SB_CUDA(ctx, cudaMemcpyAsync(A->seg.p + A->nnzb, &n32, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    k_row_ptr<<<(A->nbr + 1 + 255) / 256, 256, 0, st>>>(A->blk_row.p, A->rows.p, A->nbr, A->nnzb);
-    if (!A->d_n_long) SB_CUDA(ctx, cudaMalloc(&A->d_n_long, sizeof(int)));
-    A->long_blocks.ensure(LONG_CAP);
-    SB_CUDA(ctx, cudaMemsetAsync(A->d_n_long, 0, sizeof(int), st));
-    k_find_long<<<(unsigned)((A->nnzb + 255) / 256), 256, 0, st>>>(A->seg.p, A->long_blocks.p, A->d_n_long, A->nnzb);
-    ctx->launches += 3;
-    SB_CUDA(ctx, cudaStreamSynchronize(st));   // n32 is a stack variable
-    SB_CUDA(ctx, cudaGetLastError());
-    A->built_version = ctx->pattern_version;
-    A->built_n_src = n;
+    X.n_blocks = nb32;
     return 0;
+}
+
+static int build_symbolic(sb_context* ctx, Assembly* A, bool rebuild_static)
+{
+    StageTimer timer(ctx, ST_ASM_SYMBOLIC);
+    cudaStream_t st = ctx->stream;
+    if (ctx->H_total >= (1ull << 32)) return fail(ctx, SB_ERR_STATE, "sb_assemble: element Hessian storage exceeds 32-bit offsets");
+    A->nbr = ctx->ndofs / 3;
+    int r;
+    if (rebuild_static && (r = build_set(ctx, A, A->S, false))) return r;
+    if ((r = build_set(ctx, A, A->D, true))) return r;
+    const size_t nsb = A->S.n_blocks, ndb = A->D.n_blocks;
+    if (nsb + ndb == 0) return fail(ctx, SB_ERR_STATE, "sb_assemble: no element Hessians");
+    const size_t cap = nsb + ndb;   // upper bound of the merged pattern
+    A->seg4.ensure(cap + 1); A->blk_row.ensure(cap + 1); A->cols.ensure(cap + 1); A->vals.ensure(9 * cap + 9);
+    A->rows.ensure(A->nbr + 2); A->dirty.ensure(cap + 1); A->long_blocks.ensure(LONG_CAP);
+    A->s_final.ensure(nsb + 1); A->d_final.ensure(ndb + 1);
+    A->d_pos.ensure(ndb + 1); A->d_isnew.ensure(ndb + 1); A->d_newrank.ensure(ndb + 1); A->newpos.ensure(ndb + 1);
+    SB_CUDA(ctx, cudaMemsetAsync(A->d_counts, 0, 4 * sizeof(int), st));
+    if (ndb > 0) {
+        k_dyn_locate<<<(unsigned)((ndb + 255) / 256), 256, 0, st>>>(A->D.blk_key.p, ndb, A->S.blk_key.p, nsb, A->d_pos.p, A->d_isnew.p);
+        size_t tb = 0;
+        cub::DeviceScan::InclusiveSum(nullptr, tb, A->d_isnew.p, A->d_newrank.p, (int)ndb, st);
+        A->temp.ensure(tb + 16);
+        tb = A->temp.cap;
+        SB_CUDA(ctx, cub::DeviceScan::InclusiveSum(A->temp.p, tb, A->d_isnew.p, A->d_newrank.p, (int)ndb, st));
+        k_dyn_compact<<<(unsigned)((ndb + 255) / 256), 256, 0, st>>>(A->d_pos.p, A->d_isnew.p, A->d_newrank.p, A->newpos.p, ndb, A->d_counts + 1);
+        ctx->launches += 3;
+    }
+    if (nsb > 0) {
+        k_static_final<<<(unsigned)((nsb + 255) / 256), 256, 0, st>>>(A->S.blk_key.p, A->S.seg.p, nsb, A->newpos.p, A->d_counts + 1,
+                                                                       A->s_final.p, A->seg4.p, A->blk_row.p, A->cols.p);
+        ctx->launches++;
+    }
+    if (ndb > 0) {
+        k_dyn_final<<<(unsigned)((ndb + 255) / 256), 256, 0, st>>>(A->D.blk_key.p, A->D.seg.p, ndb, A->d_pos.p, A->d_isnew.p, A->d_newrank.p,
+                                                                    A->s_final.p, A->d_final.p, A->seg4.p, A->blk_row.p, A->cols.p);
+        ctx->launches++;
+    }
+    SB_CUDA(ctx, cudaMemcpyAsync(A->h_counts, A->d_counts, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    SB_CUDA(ctx, cudaStreamSynchronize(st));
+    A->nnzb = nsb + (size_t)A->h_counts[1];
+    k_row_ptr<<<(A->nbr + 1 + 255) / 256, 256, 0, st>>>(A->blk_row.p, A->rows.p, A->nbr, A->nnzb);
+    k_find_long<<<(unsigned)((A->nnzb + 255) / 256), 256, 0, st>>>(A->seg4.p, A->long_blocks.p, A->d_counts, A->nnzb);
+    SB_CUDA(ctx, cudaMemsetAsync(A->dirty.p, 0, A->nnzb + 1, st));
+    ctx->launches += 2;
+    SB_CUDA(ctx, cudaGetLastError());
+    A->built_static = ctx->static_version;
+    A->built_dynamic = ctx->dynamic_version;
+    A->built_n_src = ctx->n_blocks_total;
+    return 0;
+}
+
+static bool pattern_current(sb_context* ctx, Assembly* A)
+{
+    return A->built_static == ctx->static_version && A->built_dynamic == ctx->dynamic_version && A->built_n_src == ctx->n_blocks_total && A->nbr == ctx->ndofs / 3;
 }
 
 int assemble_internal(sb_context* ctx)
@@ -276,21 +427,25 @@ int assemble_internal(sb_context* ctx)
     Assembly* A = get(ctx);
     if (ctx->n_blocks_total == 0) return fail(ctx, SB_ERR_STATE, "sb_assemble: no element Hessians");
     bool rebuilt = false;
-    if (A->built_version != ctx->pattern_version || A->built_n_src != ctx->n_blocks_total || A->nbr != ctx->ndofs / 3) {
-        int r = build_symbolic(ctx, A);
+    if (!pattern_current(ctx, A)) {
+        const bool rebuild_static = A->built_static != ctx->static_version || A->nbr != ctx->ndofs / 3 || A->S.n != ctx->n_static_blocks;
+        int r = build_symbolic(ctx, A, rebuild_static);
         if (r) return r;
         rebuilt = true;
     }
     StageTimer timer(ctx, ST_ASM_NUMERIC);
+    NumericArgs a;
+    a.H = ctx->H.p; a.seg4 = A->seg4.p; a.s_off = A->S.sorted_off.p; a.s_pitch = A->S.sorted_pitch.p; a.d_off = A->D.sorted_off.p; a.d_pitch = A->D.sorted_pitch.p;
+    a.vals = A->vals.p; a.dirty = A->dirty.p; a.long_blocks = A->long_blocks.p; a.n_long = A->d_counts; a.nnzb = A->nnzb;
     const size_t nt = 9 * A->nnzb;
     const unsigned grid = (unsigned)((nt + 287) / 288);
     if (!rebuilt && A->numeric_valid && A->assembled_eval == ctx->eval_id) {
         // same evaluation, same pattern: only PD-projected elements changed since the last pass
-        k_assemble_numeric<true><<<grid, 288, 0, ctx->stream>>>(ctx->H.p, A->seg.p, A->sorted_off.p, A->sorted_pitch.p, A->vals.p, A->dirty.p, A->nnzb, A->long_blocks.p, A->d_n_long);
-        k_assemble_long<true><<<LONG_CTAS, 288, 0, ctx->stream>>>(ctx->H.p, A->seg.p, A->sorted_off.p, A->sorted_pitch.p, A->vals.p, A->dirty.p, A->long_blocks.p, A->d_n_long);
+        k_assemble_numeric<true><<<grid, 288, 0, ctx->stream>>>(a);
+        k_assemble_long<true><<<LONG_CTAS, 288, 0, ctx->stream>>>(a);
     } else {
-        k_assemble_numeric<false><<<grid, 288, 0, ctx->stream>>>(ctx->H.p, A->seg.p, A->sorted_off.p, A->sorted_pitch.p, A->vals.p, A->dirty.p, A->nnzb, A->long_blocks.p, A->d_n_long);
-        k_assemble_long<false><<<LONG_CTAS, 288, 0, ctx->stream>>>(ctx->H.p, A->seg.p, A->sorted_off.p, A->sorted_pitch.p, A->vals.p, A->dirty.p, A->long_blocks.p, A->d_n_long);
+        k_assemble_numeric<false><<<grid, 288, 0, ctx->stream>>>(a);
+        k_assemble_long<false><<<LONG_CTAS, 288, 0, ctx->stream>>>(a);
     }
     k_clear_dirty<<<(unsigned)((A->nnzb + 255) / 256), 256, 0, ctx->stream>>>(A->dirty.p, A->nnzb);
     ctx->launches += 3;
@@ -300,12 +455,15 @@ int assemble_internal(sb_context* ctx)
     return 0;
 }
 
-// for project.cu: where a changed element's blocks land (null when the pattern is stale -> the next assembly is a full one anyway)
-bool assembly_dirty_view(sb_context* ctx, const uint32_t** blk_of_src, uint8_t** dirty)
+// for project.cu: where a changed element's blocks land (false when the pattern is stale -> the next assembly is a full one anyway)
+bool assembly_dirty_view(sb_context* ctx, DirtyView* v)
 {
     Assembly* A = ctx->assembly;
-    if (!A || A->built_version != ctx->pattern_version || A->built_n_src != ctx->n_blocks_total || A->nbr != ctx->ndofs / 3) return false;
-    *blk_of_src = A->blk_of_src.p; *dirty = A->dirty.p;
+    if (!A || !pattern_current(ctx, A)) return false;
+    v->n_static = (unsigned long long)A->S.n;
+    v->s_blk_of_src = A->S.blk_of_src.p; v->s_final = A->s_final.p;
+    v->d_blk_of_src = A->D.blk_of_src.p; v->d_final = A->d_final.p;
+    v->dirty = A->dirty.p;
     return true;
 }
 

@@ -842,7 +842,7 @@ static int detect(sb_context* ctx, Contact* C, int mode, double enlargement)
             }
         }
         if (any) {
-            ctx->pattern_version++;
+            ctx->dynamic_version++;
             ctx->have_pgh = false;
         }
     }
@@ -955,6 +955,7 @@ int sb_contact_init(sb_context* ctx, const sb_contact_bindings* b)
         if (r) return r;
         C->pot[t] = pot;
         ctx->potentials[pot].conn_ext = nullptr;
+        ctx->potentials[pot].dynamic = true;
     }
     return SB_OK;
 }

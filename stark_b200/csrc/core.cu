@@ -85,6 +85,15 @@ void reduce_absmax(sb_context* ctx, const double* d_in, size_t n, double* d_out)
     ctx->launches += 2;
 }
 
+std::vector<int> layout_order(const sb_context* ctx)
+{
+    std::vector<int> order;
+    for (int pass = 0; pass < 2; pass++)
+        for (int i = 0; i < (int)ctx->potentials.size(); i++)
+            if ((int)ctx->potentials[i].dynamic == pass) order.push_back(i);
+    return order;
+}
+
 int recompute_dof_offsets(sb_context* ctx)
 {
     int off = 0;
@@ -134,7 +143,8 @@ int eval_internal(sb_context* ctx, int mode, double* out_E, double* out_grad_inf
 
     // layout of the shared element-output buffers
     size_t H_total = 0, rows_total = 0, E_total = 0, n_blocks = 0;
-    for (auto& p : ctx->potentials) {
+    for (int pi : layout_order(ctx)) {
+        Potential& p = ctx->potentials[pi];
         H_total = (H_total + 15) & ~(size_t)15;   // every potential's Hessian block starts 128 B aligned (bulk stores)
         p.H_off = H_total; p.rows_off = rows_total; p.E_off = E_total;
         const size_t n = p.k->n_dof;
@@ -153,6 +163,11 @@ int eval_internal(sb_context* ctx, int mode, double* out_E, double* out_grad_inf
         SB_CUDA(ctx, cudaMemsetAsync(ctx->projected.p, 0, E_total + 1, ctx->stream));
         ctx->n_hessians = E_total;
         ctx->n_blocks_total = n_blocks;
+        {   // blocks of the static potentials (numbered first)
+            size_t nsb = 0;
+            for (auto& p : ctx->potentials) if (!p.dynamic) nsb += (size_t)p.n_elem * p.k->nb * p.k->nb;
+            ctx->n_static_blocks = nsb;
+        }
         ctx->n_rows_total = rows_total;
         ctx->H_total = H_total;
         ctx->n_projected = 0;
@@ -474,7 +489,7 @@ int sb_potential_create(sb_context* ctx, const char* kernel_name, int conn_strid
     for (int b = k->nb; b < MAX_BLOCKS; b++) { p.blocks[b].conn_col = 0; p.blocks[b].dof_offset = 0; p.block_set[b] = 0; }
     ctx->potentials.push_back(std::move(p));
     if (out_potential) *out_potential = (int)ctx->potentials.size() - 1;
-    ctx->pattern_version++;
+    ctx->static_version++;
     return SB_OK;
 }
 
@@ -496,7 +511,7 @@ int sb_potential_set_connectivity(sb_context* ctx, int potential, const int32_t*
         SB_CUDA(ctx, cudaMemcpyAsync(p.conn.p, conn, sizeof(int32_t) * (size_t)n_elements * p.conn_stride, cudaMemcpyHostToDevice, ctx->stream));
         SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
-    ctx->pattern_version++;
+    ctx->static_version++;
     ctx->have_pgh = false;
     return SB_OK;
 }

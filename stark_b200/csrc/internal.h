@@ -104,6 +104,7 @@ struct Potential {
     int n_elem = 0;
     DevBuf<int32_t> conn;       // owned connectivity (host-provided)
     const int32_t* conn_ext = nullptr;  // or device-resident table owned by the contact module
+    bool dynamic = false;               // element set changes at every evaluation (contact / friction tables)
     const int32_t* n_elem_dev = nullptr;
     DevBuf<FetchSlot> slots;
     std::vector<FetchSlot> slots_host;  // what `slots` holds on the device (re-uploaded only when a binding moved)
@@ -156,7 +157,10 @@ struct sb_context {
     sb::DevBuf<uint8_t> projected;  // per element Hessian: already projected
     size_t n_hessians = 0, n_blocks_total = 0, n_rows_total = 0, H_total = 0;
     int64_t n_projected = 0;
-    uint64_t pattern_version = 1;   // bumped whenever any connectivity changes
+    // Connectivity versions.  STATIC potentials (meshes, joints) change rarely; DYNAMIC ones (contact / friction tables)
+    // change at every detection.  The element-output buffers are laid out static-first so that static offsets never move.
+    uint64_t static_version = 1, dynamic_version = 1;
+    size_t n_static_blocks = 0;     // element blocks of the static potentials (they are numbered first)
     uint64_t state_version = 1;     // bumped whenever an array / the DoFs / the contact set-up change (caches keyed on the state)
     uint64_t eval_id = 0;           // bumped by every PGH evaluation (the element Hessians are rewritten)
     bool have_pgh = false;
@@ -180,6 +184,8 @@ int fail(sb_context* ctx, int code, const std::string& msg);
 int check_cuda(sb_context* ctx, cudaError_t e, const char* what);
 #define SB_CUDA(ctx, call) do { int _r = sb::check_cuda((ctx), (call), #call); if (_r) return _r; } while (0)
 int recompute_dof_offsets(sb_context* ctx);
+// potential indices in buffer-layout order: static potentials first, then dynamic ones
+std::vector<int> layout_order(const sb_context* ctx);
 int refresh_slots(sb_context* ctx, Potential& p);
 // reductions (core.cu): deterministic sum / inf-norm into d_out[0]
 void reduce_sum(sb_context* ctx, const double* d_in, size_t n, double* d_out);
@@ -189,7 +195,15 @@ void pcg_destroy(sb_context* ctx);
 void contact_destroy(sb_context* ctx);
 void projector_destroy(sb_context* ctx);
 int assemble_internal(sb_context* ctx);
-bool assembly_dirty_view(sb_context* ctx, const uint32_t** blk_of_src, uint8_t** dirty);
+// where the blocks of an element land in the assembled matrix: sources are numbered static-first; a static source maps
+// through its static block, a dynamic one through its dynamic block
+struct DirtyView {
+    unsigned long long n_static;
+    const uint32_t* s_blk_of_src; const uint32_t* s_final;
+    const uint32_t* d_blk_of_src; const uint32_t* d_final;
+    uint8_t* dirty;
+};
+bool assembly_dirty_view(sb_context* ctx, DirtyView* v);
 int project_internal(sb_context* ctx, double grad_threshold, double eps, int mirror, int64_t* out_n_projected, int64_t* out_n_hessians, int* out_all_projected);
 int solve_pcg_internal(sb_context* ctx, double abs_tol, double rel_tol, int max_iter, int stop_on_indef, int* out_iterations, int* out_ok, double* out_du_dot_grad, double* out_du_inf);
 // contact hooks used by the Newton driver (contact.cu)
