@@ -52,6 +52,14 @@ SB_API int sb_array_create(sb_context* ctx, const char* label, int stride, int* 
 SB_API int sb_array_upload(sb_context* ctx, int array, const double* host, int n_rows);
 SB_API int sb_array_download(sb_context* ctx, int array, double* host, int n_rows);
 SB_API int sb_array_rows(sb_context* ctx, int array, int* out_rows);
+/* every entry of the first n_rows rows = value (the reference zeroes soft.v1 / rigid.v1 / rigid.w1 before every time step,
+ * S/models/deformables/PointDynamics.cpp:58-62, S/models/rigidbodies/RigidBodyDynamics.cpp:136-147) */
+SB_API int sb_array_fill(sb_context* ctx, int array, int n_rows, double value);
+/* Pinned mirrors (SURVEY.md 8(b) "Data ownership"): a host buffer registered here is page-locked in place, and uploads
+ * FROM it are asynchronous -- the buffer must stay untouched until the next call that synchronises (any download, sb_eval,
+ * sb_newton_solve, sb_synchronize).  Unregistered (pageable) buffers keep the borrow-for-the-call contract. */
+SB_API int sb_host_register(sb_context* ctx, void* host, uint64_t bytes);
+SB_API int sb_host_unregister(sb_context* ctx, void* host);
 
 /* ---- degrees of freedom ---------------------------------------------------------------------------------------
  * replaces: GlobalPotential::add_dof / get_dofs / set_dofs / get_dofs_offsets (symx/solver/GlobalPotential.cpp:86-144).

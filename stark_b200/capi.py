@@ -70,7 +70,7 @@ class NewtonStats(C.Structure):
 # every symbol include/stark_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = [
     "sb_create", "sb_destroy", "sb_last_error", "sb_get_stream", "sb_synchronize", "sb_launch_count",
-    "sb_array_create", "sb_array_upload", "sb_array_download", "sb_array_rows",
+    "sb_array_create", "sb_array_upload", "sb_array_download", "sb_array_rows", "sb_array_fill", "sb_host_register", "sb_host_unregister",
     "sb_dof_add", "sb_dof_total", "sb_dofs_get", "sb_dofs_set",
     "sb_potential_create", "sb_potential_set_connectivity", "sb_potential_info", "sb_kernel_names",
     "sb_eval", "sb_grad_get", "sb_potential_get_element_output", "sb_potential_get_block_rows", "sb_potential_get_hessians",

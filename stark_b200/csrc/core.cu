@@ -245,6 +245,11 @@ __global__ void k_axpy_set(double* __restrict__ dst, const double* __restrict__ 
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = base[i] + s * d[i];
 }
+__global__ void k_fill(double* __restrict__ x, double v, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = v;
+}
 __global__ void k_scale(double* __restrict__ x, double s, int n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -293,6 +298,8 @@ void sb_destroy(sb_context* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    for (auto& r : ctx->host_regions) cudaHostUnregister(r.first);
+    ctx->host_regions.clear();
     assembly_destroy(ctx);
     pcg_destroy(ctx);
     contact_destroy(ctx);
@@ -364,10 +371,53 @@ int sb_array_upload(sb_context* ctx, int array, const double* host, int n_rows)
     a.n_rows = n_rows;
     ctx->state_version++;
     if (n_rows > 0) {
+        // pageable source: the driver stages the data before the call returns; registered (pinned) source: truly asynchronous,
+        // the caller keeps the buffer untouched until the next synchronising call (sb_host_register contract)
         SB_CUDA(ctx, cudaMemcpyAsync(a.d.p, host, sizeof(double) * (size_t)n_rows * a.stride, cudaMemcpyHostToDevice, ctx->stream));
-        SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host buffer is only borrowed for this call
+        cudaPointerAttributes at;
+        const bool pinned = (cudaPointerGetAttributes(&at, host) == cudaSuccess) && at.type == cudaMemoryTypeHost;
+        cudaGetLastError();   // an unregistered pointer may leave a sticky-free error code behind on old drivers
+        if (pinned) {
+            bool ours = false;
+            for (auto& r : ctx->host_regions) if ((const char*)host >= (const char*)r.first && (const char*)host < (const char*)r.first + r.second) ours = true;
+            if (!ours) SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // pinned by someone else: keep the borrow-for-the-call contract
+        }
     }
     return SB_OK;
+}
+int sb_array_fill(sb_context* ctx, int array, int n_rows, double value)
+{
+    int r = check_array(ctx, array, "sb_array_fill"); if (r) return r;
+    if (n_rows < 0) return fail(ctx, SB_ERR_ARG, "sb_array_fill: bad argument");
+    Array& a = ctx->arrays[array];
+    a.d.ensure((size_t)std::max(n_rows, 1) * a.stride);
+    a.n_rows = n_rows;
+    ctx->state_version++;
+    const int n = n_rows * a.stride;
+    if (n > 0) {
+        if (value == 0.0) SB_CUDA(ctx, cudaMemsetAsync(a.d.p, 0, sizeof(double) * (size_t)n, ctx->stream));
+        else { k_fill<<<(n + 255) / 256, 256, 0, ctx->stream>>>(a.d.p, value, n); ctx->launches++; }
+    }
+    return SB_OK;
+}
+int sb_host_register(sb_context* ctx, void* host, uint64_t bytes)
+{
+    if (!ctx || !host || bytes == 0) return fail(ctx, SB_ERR_ARG, "sb_host_register: bad argument");
+    SB_CUDA(ctx, cudaHostRegister(host, (size_t)bytes, cudaHostRegisterDefault));
+    ctx->host_regions.push_back({host, (size_t)bytes});
+    return SB_OK;
+}
+int sb_host_unregister(sb_context* ctx, void* host)
+{
+    if (!ctx || !host) return fail(ctx, SB_ERR_ARG, "sb_host_unregister: bad argument");
+    for (size_t i = 0; i < ctx->host_regions.size(); i++)
+        if (ctx->host_regions[i].first == host) {
+            SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            SB_CUDA(ctx, cudaHostUnregister(host));
+            ctx->host_regions.erase(ctx->host_regions.begin() + i);
+            return SB_OK;
+        }
+    return fail(ctx, SB_ERR_ARG, "sb_host_unregister: not a registered buffer");
 }
 int sb_array_download(sb_context* ctx, int array, double* host, int n_rows)
 {

@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <utility>
 #include <vector>
 #include "../../include/stark_b200.h"
 
@@ -141,6 +142,7 @@ struct sb_context {
     std::string error;
     int64_t launches = 0;
 
+    std::vector<std::pair<void*, size_t>> host_regions;   // sb_host_register: pinned mirrors
     std::vector<sb::Array> arrays;
     std::vector<sb::DofSet> dof_sets;
     int ndofs = 0;

@@ -360,8 +360,19 @@ void Simulation::reg(DeviceArray& a, const char* label, int stride)
 }
 void Simulation::upload(DeviceArray& a)
 {
+    if (!a.volatile_data) {
+        if (a.has_shadow && a.shadow == a.data) return;   // the device already holds these values
+        a.shadow = a.data;
+        a.has_shadow = true;
+    }
     check(sb_array_upload(ctx, a.id, a.data.data(), a.rows()), "sb_array_upload");
     h2d_bytes += (long long)a.data.size() * 8;
+}
+void Simulation::pin(DeviceArray& a)
+{   // large per-step arrays become pinned mirrors: their uploads are asynchronous DMA without a staging copy
+    if (a.pinned || a.data.empty()) return;
+    check(sb_host_register(ctx, a.data.data(), (uint64_t)a.data.size() * 8), "sb_host_register");
+    a.pinned = true;
 }
 void Simulation::download(DeviceArray& a)
 {
@@ -445,6 +456,8 @@ void Simulation::initialize()
     reg(cp.a_loc, "points.a_loc", 3); reg(cp.b_loc, "points.b_loc", 3); reg(cp.stiffness, "points.stiffness", 1); reg(cp.is_active, "points.is_active", 1);
     auto& cd = rb_constraints.directions;
     reg(cd.da_loc, "directions.da_loc", 3); reg(cd.db_loc, "directions.db_loc", 3); reg(cd.stiffness, "directions.stiffness", 1); reg(cd.is_active, "directions.is_active", 1);
+    for (DeviceArray* a : {&dyn.x0, &dyn.v0, &dyn.v1}) { a->volatile_data = true; pin(*a); }
+    for (DeviceArray* a : {&rb.v1, &rb.w1}) a->volatile_data = true;   // DoF arrays: the solve rewrites them on the device
     for (DeviceArray* a : all_arrays) upload(*a);
 
     // ---- DoF sets in the reference's registration order: soft.v1, rigid.v1, rigid.w1 ----
@@ -565,7 +578,8 @@ bool Simulation::run_one_time_step()
     // per-step state to the device (SURVEY.md Appendix B "once per time step" + "scalars that may change between retries")
     dt_arr.data[0] = dt;
     gravity_arr.data = {gravity[0], gravity[1], gravity[2]};
-    for (DeviceArray* a : {&dyn.v1, &dyn.x0, &dyn.v0, &dyn.a, &dyn.f, &rb.v1, &rb.w1, &rb.t0, &rb.q0_, &rb.v0, &rb.w0, &rb.a, &rb.aa, &rb.force, &rb.torque, &dt_arr, &gravity_arr,
+    check(sb_array_fill(ctx, dyn.v1.id, dyn.v1.rows(), 0.0), "sb_array_fill");   // v1 <- 0 on the device (no transfer)
+    for (DeviceArray* a : {&dyn.x0, &dyn.v0, &dyn.a, &dyn.f, &rb.v1, &rb.w1, &rb.t0, &rb.q0_, &rb.v0, &rb.w0, &rb.a, &rb.aa, &rb.force, &rb.torque, &dt_arr, &gravity_arr,
                            &rb_inertia.J0_glob, &prescribed_positions.target_positions, &prescribed_positions.stiffness, &rb_constraints.global_points.target_glob,
                            &rb_constraints.global_points.stiffness, &rb_constraints.global_directions.target_d_glob, &rb_constraints.global_directions.stiffness,
                            &rb_constraints.points.stiffness, &rb_constraints.directions.stiffness})

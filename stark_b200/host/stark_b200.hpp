@@ -46,6 +46,10 @@ struct Settings {
 // A host array mirrored on the device through the C-ABI (symx::DataMap analogue)
 struct DeviceArray {
     std::vector<double> data;
+    std::vector<double> shadow;   // what the device holds (uploads of unchanged arrays are skipped)
+    bool has_shadow = false;
+    bool volatile_data = false;   // rewritten every step: no shadow bookkeeping, always uploaded
+    bool pinned = false;          // registered as a pinned mirror (asynchronous uploads)
     int stride = 1;
     int id = -1;
     std::string label;
@@ -217,6 +221,7 @@ private:
     void initialize();
     void reg(DeviceArray& a, const char* label, int stride);
     void upload(DeviceArray& a);
+    void pin(DeviceArray& a);
     void download(DeviceArray& a);
     void check(int status, const char* what);
 };
