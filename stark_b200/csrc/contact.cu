@@ -60,6 +60,9 @@ struct Dev {
     const int32_t* edge;         // [n_e][2]
     const int32_t* e_group;
     float* bb_p; float* bb_t; float* bb_e;   // [n][6] bottom xyz, top xyz
+    float* tb_p; float* tb_t; float* tb_e;   // [n_tiles][6] boxes of TILE consecutive primitives
+    int2* tile_pairs[3];                     // per broad-phase kind: overlapping (tile A, tile B) pairs
+    int tile_pair_cap[3];
     const int32_t* g_ps; const int32_t* g_body; const int32_t* g_voff; const int32_t* g_toff; const int32_t* g_eoff;
     const double* g_thickness;
     const uint8_t* blacklist;    // [MAX_GROUPS * MAX_GROUPS]
@@ -98,7 +101,8 @@ struct Contact {
     DevBuf<int32_t> v_group, v_ps, tri, t_group, edge, e_group, g_i32;
     DevBuf<double> g_f64, mu;
     DevBuf<uint8_t> blacklist;
-    DevBuf<float> bb_p, bb_t, bb_e;
+    DevBuf<float> bb_p, bb_t, bb_e, tb_p, tb_t, tb_e;
+    DevBuf<int2> tile_pairs[3];
     DevBuf<int2> cand_pt, cand_ee, cand_et;
     DevBuf<int> counters;
     DevBuf<int32_t> list_ids[N_LISTS];
@@ -194,6 +198,43 @@ __device__ __forceinline__ bool bb_overlap(const float* a, const float* b)
 // broad phase: tiled all-pairs.  KIND 0: point(A) x triangle(B); 1: edge(A) x edge(B), A < B; 2: edge(A) x triangle(B)
 // ---------------------------------------------------------------------------------------------------
 constexpr int TILE = 256;
+
+// box of every tile of TILE consecutive primitives (one CTA per tile)
+__global__ void __launch_bounds__(TILE) k_tile_boxes(const float* __restrict__ bb, float* __restrict__ tb, int n)
+{
+    __shared__ float s_lo[3][TILE / 32], s_hi[3][TILE / 32];
+    const int i = blockIdx.x * TILE + threadIdx.x;
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    if (i < n) for (int c = 0; c < 3; c++) { lo[c] = bb[6 * i + c]; hi[c] = bb[6 * i + 3 + c]; }
+    for (int c = 0; c < 3; c++) {
+        for (int o = 16; o > 0; o >>= 1) { lo[c] = fminf(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o)); hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o)); }
+        if ((threadIdx.x & 31) == 0) { s_lo[c][threadIdx.x >> 5] = lo[c]; s_hi[c][threadIdx.x >> 5] = hi[c]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        const int c = threadIdx.x;
+        float l = FLT_MAX, h = -FLT_MAX;
+        for (int w = 0; w < TILE / 32; w++) { l = fminf(l, s_lo[c][w]); h = fmaxf(h, s_hi[c][w]); }
+        tb[6 * blockIdx.x + c] = l; tb[6 * blockIdx.x + 3 + c] = h;
+    }
+}
+
+// overlapping tile pairs of one broad-phase kind (KIND 1: edge tiles, B >= A only)
+template<int KIND>
+__global__ void k_tile_pairs(Dev d, int nTa, int nTb)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nTa * nTb) return;
+    const int ta = t / nTb, tb = t - ta * nTb;
+    if (KIND == 1 && tb < ta) return;
+    const float* A = ((KIND == 0) ? d.tb_p : d.tb_e) + 6 * ta;
+    const float* B = ((KIND == 1) ? d.tb_e : d.tb_t) + 6 * tb;
+    if (!bb_overlap(A, B)) return;
+    const int slot = atomicAdd(d.counters + 4 + KIND, 1);
+    if (slot < d.tile_pair_cap[KIND]) d.tile_pairs[KIND][slot] = make_int2(ta, tb); else d.counters[3] = 1;
+}
+
+// all-pairs test inside the overlapping tile pairs (persistent CTAs, B tile staged in shared memory)
 template<int KIND>
 __global__ void __launch_bounds__(TILE) k_broad(Dev d)
 {
@@ -204,37 +245,62 @@ __global__ void __launch_bounds__(TILE) k_broad(Dev d)
     const int nB = (KIND == 1) ? d.n_e : d.n_t;
     const float* bbA = (KIND == 0) ? d.bb_p : d.bb_e;
     const float* bbB = (KIND == 1) ? d.bb_e : d.bb_t;
-    const int a = blockIdx.x * TILE + threadIdx.x;
-    const int b0 = blockIdx.y * TILE;
-    if (KIND == 1 && b0 + TILE - 1 <= blockIdx.x * TILE) return;   // whole tile has B <= A
-    {
-        const int b = b0 + threadIdx.x;
-        if (b < nB) {
-            for (int c = 0; c < 6; c++) s_bb[threadIdx.x][c] = bbB[6 * b + c];
-            if (KIND == 1) { s_v[threadIdx.x][0] = d.edge[2 * b]; s_v[threadIdx.x][1] = d.edge[2 * b + 1]; s_v[threadIdx.x][2] = -1; s_g[threadIdx.x] = d.e_group[b]; }
-            else { s_v[threadIdx.x][0] = d.tri[3 * b]; s_v[threadIdx.x][1] = d.tri[3 * b + 1]; s_v[threadIdx.x][2] = d.tri[3 * b + 2]; s_g[threadIdx.x] = d.t_group[b]; }
+    // candidates of one tile pair are queued in shared memory and appended to the global list with ONE global atomic
+    // (tens of thousands of same-address global atomics would serialise in L2 and dominate the kernel)
+    constexpr int QCAP = 2048;
+    __shared__ int2 s_q[QCAP];
+    __shared__ int s_qn, s_qbase;
+    int2* out = (KIND == 0) ? d.cand_pt : (KIND == 1 ? d.cand_ee : d.cand_et);
+    const int n_pairs = min(d.counters[4 + KIND], d.tile_pair_cap[KIND]);
+    for (int pi = blockIdx.x; pi < n_pairs; pi += gridDim.x) {
+        const int2 tp = d.tile_pairs[KIND][pi];
+        const int a = tp.x * TILE + threadIdx.x;
+        const int b0 = tp.y * TILE;
+        __syncthreads();   // previous pair done with the shared tile and queue
+        if (threadIdx.x == 0) s_qn = 0;
+        {
+            const int b = b0 + threadIdx.x;
+            if (b < nB) {
+                for (int c = 0; c < 6; c++) s_bb[threadIdx.x][c] = bbB[6 * b + c];
+                if (KIND == 1) { s_v[threadIdx.x][0] = d.edge[2 * b]; s_v[threadIdx.x][1] = d.edge[2 * b + 1]; s_v[threadIdx.x][2] = -1; s_g[threadIdx.x] = d.e_group[b]; }
+                else { s_v[threadIdx.x][0] = d.tri[3 * b]; s_v[threadIdx.x][1] = d.tri[3 * b + 1]; s_v[threadIdx.x][2] = d.tri[3 * b + 2]; s_g[threadIdx.x] = d.t_group[b]; }
+            }
         }
-    }
-    __syncthreads();
-    if (a >= nA) return;
-    float ba[6];
-    for (int c = 0; c < 6; c++) ba[c] = bbA[6 * a + c];
-    int va0, va1, ga;
-    if (KIND == 0) { va0 = a; va1 = -2; ga = d.v_group[a]; }
-    else { va0 = d.edge[2 * a]; va1 = d.edge[2 * a + 1]; ga = d.e_group[a]; }
-    const int nb = min(TILE, nB - b0);
-    for (int j = 0; j < nb; j++) {
-        const int b = b0 + j;
-        if (KIND == 1 && b <= a) continue;
-        if (!bb_overlap(ba, s_bb[j])) continue;
-        const int gb = s_g[j];
-        // shared-vertex ("orphan") discard: same set and a common vertex (collision vertex ids are global, so equality suffices)
-        const bool orphan = (va0 == s_v[j][0]) || (va0 == s_v[j][1]) || (va0 == s_v[j][2]) || (va1 == s_v[j][0]) || (va1 == s_v[j][1]) || (va1 == s_v[j][2]);
-        if (orphan) continue;
-        if (d.blacklist[ga * MAX_GROUPS + gb]) continue;
-        int2* out = (KIND == 0) ? d.cand_pt : (KIND == 1 ? d.cand_ee : d.cand_et);
-        const int slot = atomicAdd(d.counters + KIND, 1);
-        if (slot < d.cand_cap) out[slot] = make_int2(a, b); else d.counters[3] = 1;
+        __syncthreads();
+        if (a < nA) {
+            float ba[6];
+            for (int c = 0; c < 6; c++) ba[c] = bbA[6 * a + c];
+            int va0, va1, ga;
+            if (KIND == 0) { va0 = a; va1 = -2; ga = d.v_group[a]; }
+            else { va0 = d.edge[2 * a]; va1 = d.edge[2 * a + 1]; ga = d.e_group[a]; }
+            const int nb = min(TILE, nB - b0);
+            for (int j = 0; j < nb; j++) {
+                const int b = b0 + j;
+                if (KIND == 1 && b <= a) continue;
+                if (!bb_overlap(ba, s_bb[j])) continue;
+                const int gb = s_g[j];
+                // shared-vertex ("orphan") discard: same set and a common vertex (collision vertex ids are global, so equality suffices)
+                const bool orphan = (va0 == s_v[j][0]) || (va0 == s_v[j][1]) || (va0 == s_v[j][2]) || (va1 == s_v[j][0]) || (va1 == s_v[j][1]) || (va1 == s_v[j][2]);
+                if (orphan) continue;
+                if (d.blacklist[ga * MAX_GROUPS + gb]) continue;
+                const int k = atomicAdd(&s_qn, 1);
+                if (k < QCAP) s_q[k] = make_int2(a, b);
+                else {   // queue full (dense contact): straight to the global list
+                    const int slot = atomicAdd(d.counters + KIND, 1);
+                    if (slot < d.cand_cap) out[slot] = make_int2(a, b); else d.counters[3] = 1;
+                }
+            }
+        }
+        __syncthreads();
+        const int nq = min(s_qn, QCAP);
+        if (threadIdx.x == 0 && nq > 0) s_qbase = atomicAdd(d.counters + KIND, nq);
+        __syncthreads();
+        if (nq > 0) {
+            const int base = s_qbase;
+            for (int i = threadIdx.x; i < nq; i += TILE) {
+                if (base + i < d.cand_cap) out[base + i] = s_q[i]; else d.counters[3] = 1;
+            }
+        }
     }
 }
 
@@ -679,7 +745,8 @@ void contact_destroy(sb_context* ctx)
     Contact* C = ctx->contact;
     if (!C) return;
     C->x.release(); C->v_group.release(); C->v_ps.release(); C->tri.release(); C->t_group.release(); C->edge.release(); C->e_group.release();
-    C->g_i32.release(); C->g_f64.release(); C->mu.release(); C->blacklist.release(); C->bb_p.release(); C->bb_t.release(); C->bb_e.release();
+    C->g_i32.release(); C->g_f64.release(); C->mu.release(); C->blacklist.release(); C->bb_p.release(); C->bb_t.release(); C->bb_e.release(); C->tb_p.release(); C->tb_t.release(); C->tb_e.release();
+    for (int k = 0; k < 3; k++) C->tile_pairs[k].release();
     C->cand_pt.release(); C->cand_ee.release(); C->cand_et.release(); C->counters.release();
     for (int l = 0; l < N_LISTS; l++) { C->list_ids[l].release(); C->list_dist[l].release(); }
     for (int t = 0; t < N_TABLES; t++) C->table[t].release();
@@ -735,6 +802,12 @@ static void ensure_capacities(sb_context* ctx, Contact* C)
 {
     C->cand_pt.ensure(C->cand_cap); C->cand_ee.ensure(C->cand_cap); C->cand_et.ensure(C->cand_cap);
     C->counters.ensure(64);
+    {   // tile boxes and the (never overflowing) lists of overlapping tile pairs
+        const size_t nv = C->h_v_group.size(), nt = C->h_t_group.size(), ne = C->h_e_group.size();
+        const size_t Tv = (nv + TILE - 1) / TILE, Tt = (nt + TILE - 1) / TILE, Te = (ne + TILE - 1) / TILE;
+        C->tb_p.ensure(6 * Tv + 6); C->tb_t.ensure(6 * Tt + 6); C->tb_e.ensure(6 * Te + 6);
+        C->tile_pairs[0].ensure(Tv * Tt + 1); C->tile_pairs[1].ensure(Te * Te + 1); C->tile_pairs[2].ensure(Te * Tt + 1);
+    }
     for (int l = 0; l < N_LISTS; l++) { C->list_ids[l].ensure((size_t)C->list_cap * LIST_WIDTH[l]); C->list_dist[l].ensure(C->list_cap); }
     for (int t = 0; t < N_TABLES; t++) C->table[t].ensure((size_t)C->table_cap * LAYOUTS[t].conn_stride);
     for (int f = 0; f < N_FRICTION; f++) {
@@ -751,6 +824,8 @@ static Dev make_dev(sb_context* ctx, Contact* C)
     d.n_v = (int)C->h_v_group.size(); d.n_t = (int)C->h_t_group.size(); d.n_e = (int)C->h_e_group.size(); d.n_groups = (int)C->groups.size();
     d.x = C->x.p; d.v_group = C->v_group.p; d.v_ps_index = C->v_ps.p; d.tri = C->tri.p; d.t_group = C->t_group.p; d.edge = C->edge.p; d.e_group = C->e_group.p;
     d.bb_p = C->bb_p.p; d.bb_t = C->bb_t.p; d.bb_e = C->bb_e.p;
+    d.tb_p = C->tb_p.p; d.tb_t = C->tb_t.p; d.tb_e = C->tb_e.p;
+    for (int k = 0; k < 3; k++) { d.tile_pairs[k] = C->tile_pairs[k].p; d.tile_pair_cap[k] = (int)C->tile_pairs[k].cap; }
     d.g_ps = C->g_i32.p; d.g_body = C->g_i32.p + MAX_GROUPS; d.g_voff = C->g_i32.p + 2 * MAX_GROUPS; d.g_toff = C->g_i32.p + 3 * MAX_GROUPS; d.g_eoff = C->g_i32.p + 4 * MAX_GROUPS;
     d.g_thickness = C->g_f64.p; d.blacklist = C->blacklist.p; d.mu = C->mu.p;
     d.cand_pt = C->cand_pt.p; d.cand_ee = C->cand_ee.p; d.cand_et = C->cand_et.p; d.cand_cap = C->cand_cap;
@@ -787,31 +862,52 @@ static int detect(sb_context* ctx, Contact* C, int mode, double enlargement)
         Dev d = make_dev(ctx, C);
         const int nmax = std::max(d.n_v, std::max(d.n_t, d.n_e));
         // only the counters this mode rewrites are cleared (contact and friction tables live side by side)
-        SB_CUDA(ctx, cudaMemsetAsync(C->counters.p, 0, 4 * sizeof(int), st));
+        SB_CUDA(ctx, cudaMemsetAsync(C->counters.p, 0, 8 * sizeof(int), st));
         if (mode == 0 || mode == 3) { SB_CUDA(ctx, cudaMemsetAsync(C->counters.p + 8, 0, 6 * sizeof(int), st)); SB_CUDA(ctx, cudaMemsetAsync(C->counters.p + 16, 0, N_CONTACT_TABLES * sizeof(int), st)); }
         if (mode == 1) { SB_CUDA(ctx, cudaMemsetAsync(C->counters.p + 8, 0, 6 * sizeof(int), st)); SB_CUDA(ctx, cudaMemsetAsync(C->counters.p + 16 + N_CONTACT_TABLES, 0, N_FRICTION * sizeof(int), st)); }
         if (mode == 2 || mode == 3) SB_CUDA(ctx, cudaMemsetAsync(C->counters.p + 8 + 6, 0, sizeof(int), st));
-        const dim3 gpt((d.n_v + TILE - 1) / TILE, (d.n_t + TILE - 1) / TILE), gee((d.n_e + TILE - 1) / TILE, (d.n_e + TILE - 1) / TILE), get((d.n_e + TILE - 1) / TILE, (d.n_t + TILE - 1) / TILE);
+        const int Tv = (d.n_v + TILE - 1) / TILE, Tt = (d.n_t + TILE - 1) / TILE, Te = (d.n_e + TILE - 1) / TILE;
+        auto broad_grid = [](int n_tile_pairs) { return std::max(1, std::min(n_tile_pairs, 148 * 6)); };
         if (mode != 2) {
             const float extra = (float)enlargement + FLT_EPSILON;
             k_aabbs<<<(nmax + 255) / 256, 256, 0, st>>>(d, extra, 1);
-            if (C->enable_pt && d.n_t > 0 && d.n_v > 0) k_broad<0><<<gpt, TILE, 0, st>>>(d);
-            if (C->enable_ee && d.n_e > 1) k_broad<1><<<gee, TILE, 0, st>>>(d);
+            ctx->launches++;
+            if (C->enable_pt && d.n_t > 0 && d.n_v > 0) {
+                k_tile_boxes<<<Tv, TILE, 0, st>>>(d.bb_p, d.tb_p, d.n_v);
+                k_tile_boxes<<<Tt, TILE, 0, st>>>(d.bb_t, d.tb_t, d.n_t);
+                k_tile_pairs<0><<<(Tv * Tt + 255) / 256, 256, 0, st>>>(d, Tv, Tt);
+                k_broad<0><<<broad_grid(Tv * Tt), TILE, 0, st>>>(d);
+                ctx->launches += 4;
+            }
+            if (C->enable_ee && d.n_e > 1) {
+                k_tile_boxes<<<Te, TILE, 0, st>>>(d.bb_e, d.tb_e, d.n_e);
+                k_tile_pairs<1><<<(Te * Te + 255) / 256, 256, 0, st>>>(d, Te, Te);
+                k_broad<1><<<broad_grid(Te * Te), TILE, 0, st>>>(d);
+                ctx->launches += 3;
+            }
             const int emit_mode = (mode == 3) ? 2 : mode;   // 2 = lists only (no table matches mode 2 inside emit_*)
             if (C->enable_pt) k_narrow_pt<<<148, 128, 0, st>>>(d, enlargement * enlargement, emit_mode, C->stiffness);
             if (C->enable_ee) k_narrow_ee<<<148, 128, 0, st>>>(d, enlargement * enlargement, emit_mode, C->stiffness, 1e-30);
-            ctx->launches += 5;
+            ctx->launches += 2;
         }
         if (mode == 2 || mode == 3) {
             const float extra = 0.0f + FLT_EPSILON;   // IntersectionDetection uses non-enlarged AABBs (tmcd/BroadPhaseET.cpp:38)
             k_aabbs<<<(nmax + 255) / 256, 256, 0, st>>>(d, extra, 0);
-            if (d.n_e > 0 && d.n_t > 0) k_broad<2><<<get, TILE, 0, st>>>(d);
+            ctx->launches++;
+            if (d.n_e > 0 && d.n_t > 0) {
+                k_tile_boxes<<<Te, TILE, 0, st>>>(d.bb_e, d.tb_e, d.n_e);
+                k_tile_boxes<<<Tt, TILE, 0, st>>>(d.bb_t, d.tb_t, d.n_t);
+                k_tile_pairs<2><<<(Te * Tt + 255) / 256, 256, 0, st>>>(d, Te, Tt);
+                k_broad<2><<<broad_grid(Te * Tt), TILE, 0, st>>>(d);
+                ctx->launches += 4;
+            }
             k_narrow_et<<<148, 128, 0, st>>>(d);
-            ctx->launches += 3;
+            ctx->launches++;
         }
         SB_CUDA(ctx, cudaMemcpyAsync(C->h_counters, C->counters.p, 64 * sizeof(int), cudaMemcpyDeviceToHost, st));
         SB_CUDA(ctx, cudaStreamSynchronize(st));
         SB_CUDA(ctx, cudaGetLastError());
+        if (ctx->profile) for (int k = 0; k < 3; k++) { ctx->stage_calls[ST_TILE_PAIRS_PT + k] += C->h_counters[4 + k]; ctx->stage_calls[ST_CAND_PT + k] += C->h_counters[k]; }
         if (!C->h_counters[3]) break;
         // overflow: grow whatever was too small and run again
         const int mc = std::max(C->h_counters[0], std::max(C->h_counters[1], C->h_counters[2]));
