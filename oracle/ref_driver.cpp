@@ -129,7 +129,7 @@ static stark::Settings base_settings(const Args& a, const std::string& name)
 	settings.output.output_directory = "/tmp/stark_ref_out/" + name;
 	if (!a.codegen.empty()) settings.output.codegen_directory = a.codegen;
 	settings.output.enable_frame_writes = false;
-	settings.output.enable_output = false;
+	settings.output.enable_output = a.verbose;
 	settings.output.console_verbosity = a.verbose ? symx::Verbosity::Full : symx::Verbosity::Minimal;
 	settings.output.file_verbosity = symx::Verbosity::Minimal;
 	settings.simulation.max_time_step_size = a.dt;
@@ -210,8 +210,98 @@ static Scene scene_cloth(const Args& a, bool discrete_shells, double mu)
 	return sc;
 }
 
+// Rigid-rigid contact + friction and the two velocity controllers: a tilted box resting on a fixed floor box, a second
+// box driven along x by a linear-velocity controller and a third one spun by an angular-velocity controller.
+static Scene scene_boxes(const Args& a)
+{
+	Scene sc;
+	stark::Settings settings = base_settings(a, "boxes");
+	sc.sim = std::make_unique<stark::Simulation>(settings);
+	auto& sim = *sc.sim;
+	stark::EnergyFrictionalContact::GlobalParams cp;
+	cp.default_contact_thickness = 0.002;
+	cp.min_contact_stiffness = 1e6;
+	sim.interactions->contact->set_global_params(cp);
+
+	auto [Vf, Cf, floor] = sim.presets->rigidbodies->add_box("floor", 1.0, { 2.0, 2.0, 0.1 });
+	floor.rigidbody.set_translation({ 0.0, 0.0, -0.05 });
+	sim.rigidbodies->add_constraint_fix(floor.rigidbody);
+
+	auto [V1, C1, b1] = sim.presets->rigidbodies->add_box("b1", 1.0, 0.2);
+	b1.rigidbody.set_rotation(7.0, { 1.0, 0.3, 0.1 });
+	b1.rigidbody.set_translation({ -0.4, 0.05, 0.1 + 0.022 + a.drop });
+	b1.rigidbody.set_velocity({ 0.3, 0.0, -a.vz });
+	sim.interactions->contact->set_friction(floor.contact, b1.contact, 0.5);
+
+	auto [V2, C2, b2] = sim.presets->rigidbodies->add_box("b2", 2.0, { 0.2, 0.15, 0.1 });
+	b2.rigidbody.set_translation({ 0.3, -0.3, 0.05 + 0.0035 });
+	sim.interactions->contact->set_friction(floor.contact, b2.contact, 0.3);
+	sim.rigidbodies->add_constraint_linear_velocity(floor.rigidbody, b2.rigidbody, { 1.0, 0.2, 0.0 }, 0.25, 5.0, 0.02);
+
+	auto [V3, C3, b3] = sim.presets->rigidbodies->add_box("b3", 0.5, 0.12);
+	b3.rigidbody.set_translation({ 0.4, 0.5, 0.4 });
+	sim.rigidbodies->add_constraint_angular_velocity(floor.rigidbody, b3.rigidbody, { 0.0, 0.3, 1.0 }, 2.0, 0.4, 0.05);
+	// b3 leans on b2's top edge region later in the fall: rigid-rigid edge-edge pairs
+	sim.interactions->contact->set_friction(b2.contact, b3.contact, 0.2);
+
+	// two small cubes standing on a vertex (body diagonal vertical), held in place: the vertex of b4 hovers 1.4 mm off the
+	// floor's top EDGE, the one of b5 1.8 mm off the floor's CORNER -> point-edge / point-point and the edge-edge derived
+	// point-edge / point-point pairs (contact and friction)
+	const double h = 0.05, diag = h * std::sqrt(3.0), tilt = std::acos(1.0 / std::sqrt(3.0)) * 180.0 / M_PI;
+	auto [V4, C4, b4] = sim.presets->rigidbodies->add_box("b4", 0.3, 2.0 * h);
+	b4.rigidbody.set_rotation(tilt, { 1.0, -1.0, 0.0 });
+	b4.rigidbody.set_translation({ 1.0012, 0.3, 0.0008 + diag });
+	sim.rigidbodies->add_constraint_fix(b4.rigidbody);
+	sim.interactions->contact->set_friction(floor.contact, b4.contact, 0.4);
+	auto [V5, C5, b5] = sim.presets->rigidbodies->add_box("b5", 0.3, 2.0 * h);
+	b5.rigidbody.set_rotation(tilt, { 1.0, -1.0, 0.0 });
+	b5.rigidbody.set_translation({ 1.001, 1.0012, 0.0009 + diag });
+	sim.rigidbodies->add_constraint_fix(b5.rigidbody);
+	sim.interactions->contact->set_friction(floor.contact, b5.contact, 0.4);
+	return sc;
+}
+
+// All five attachment potentials (examples/main.cpp:268-312 scaled down): two cloth patches attached point-triangle by
+// distance, explicit point-point / point-edge / edge-edge pairs, and a rigid box attached to the second patch.
+static Scene scene_attach(const Args& a)
+{
+	Scene sc;
+	stark::Settings settings = base_settings(a, "attach");
+	settings.simulation.init_frictional_contact = false;
+	sc.sim = std::make_unique<stark::Simulation>(settings);
+	auto& sim = *sc.sim;
+	const int n = a.n;
+	const double d = 1.0, hd = 0.5, gap = 0.001;
+	auto params = stark::Surface::Params::Cotton_Fabric();
+	auto [V1, T1, H1] = sim.presets->deformables->add_surface_grid("A", { d, d }, { n, n }, params);
+	auto [V2, T2, H2] = sim.presets->deformables->add_surface_grid("B", { d, d }, { n, n }, params);
+	H2.point_set.add_rotation(45.0, Eigen::Vector3d::UnitZ());
+	H2.point_set.add_displacement({ d, 0.0, gap });
+	const double bs = 0.25;
+	const stark::Mesh<3> box_mesh = stark::make_box({ bs, bs, bs });
+	auto [V, C, box] = sim.presets->rigidbodies->add_box("box", 0.1, bs);
+	box.rigidbody.add_translation({ 1.7, 0.0, 0.5 * bs + 2.0 * gap });
+
+	auto ap = stark::EnergyAttachments::Params().set_tolerance(0.01);
+	sim.interactions->attachments->add_by_distance(H2.point_set, H1.point_set, H2.point_set.all(), T1, 2.0 * gap, ap);
+	sim.interactions->attachments->add_by_distance(box.rigidbody, H2.point_set, box_mesh.vertices, box_mesh.conn, H2.point_set.all(), 4.0 * gap, ap);
+	// explicit pairs between the two patches
+	const int np = (n + 1) * (n + 1);
+	sim.interactions->attachments->add(H1.point_set, H2.point_set, std::vector<int>{ 0, np / 2 }, std::vector<int>{ 1, np / 3 }, ap);
+	sim.interactions->attachments->add(H1.point_set, H2.point_set, std::vector<int>{ 2, 5 }, std::vector<std::array<int, 2>>{ { 0, 1 }, { 3, 4 } },
+		std::vector<std::array<double, 2>>{ { 0.25, 0.75 }, { 0.6, 0.4 } }, ap);
+	sim.interactions->attachments->add(H1.point_set, H2.point_set, std::vector<std::array<int, 2>>{ { 0, 1 }, { 4, 5 } }, std::vector<std::array<int, 2>>{ { 2, 3 }, { 6, 7 } },
+		std::vector<std::array<double, 2>>{ { 0.5, 0.5 }, { 0.1, 0.9 } }, std::vector<std::array<double, 2>>{ { 0.3, 0.7 }, { 0.8, 0.2 } }, ap);
+
+	sim.deformables->prescribed_positions->add_inside_aabb(H1.point_set, { -hd, -hd, 0.0 }, { 0.001, 0.001, 0.001 }, stark::EnergyPrescribedPositions::Params());
+	sim.deformables->prescribed_positions->add_inside_aabb(H1.point_set, { -hd, hd, 0.0 }, { 0.001, 0.001, 0.001 }, stark::EnergyPrescribedPositions::Params());
+	return sc;
+}
+
 static Scene make_scene(const Args& a)
 {
+	if (a.scene == "boxes") return scene_boxes(a);
+	if (a.scene == "attach") return scene_attach(a);
 	if (a.scene == "tetdrop") return scene_tetdrop(a);
 	if (a.scene == "tetbar") return scene_tetbar(a);
 	if (a.scene == "cloth") return scene_cloth(a, false, 0.0);

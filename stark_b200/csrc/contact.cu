@@ -27,17 +27,18 @@ namespace sb {
 enum Role { R_SOFT_V1, R_SOFT_X0, R_SOFT_X, R_RB_V1, R_RB_W1, R_RB_T0, R_RB_Q0, R_DT, R_THICKNESS, R_STIFFNESS, R_RB_LOCAL, R_EPSV,
             R_F_T, R_F_BARY, R_F_MU, R_F_FN };
 struct LayoutEntry { int role, col, slot, stride; };
-struct Layout { const char* name; int conn_stride; int n; LayoutEntry e[32]; };
+struct Layout { const char* name; int conn_stride; int n; LayoutEntry e[40]; };
 static const Layout LAYOUTS[] = {
 #include "contact_layouts.inc"
 };
-constexpr int N_TABLES = 25;       // 15 contact + 10 friction, in the order of contact_layouts.inc
-constexpr int N_CONTACT_TABLES = 15;
-constexpr int N_FRICTION = 10;
+constexpr int N_TABLES = 35;       // 21 contact + 14 friction, in the order of contact_layouts.inc
+constexpr int N_CONTACT_TABLES = 21;
+constexpr int N_FRICTION = 14;
 enum Table {
     CT_DD_PT_PP, CT_DD_PT_PE, CT_DD_PT_PT, CT_DD_EE_PP, CT_DD_EE_PE, CT_DD_EE_EE,
+    CT_RR_PT_PP, CT_RR_PT_PE, CT_RR_PT_PT, CT_RR_EE_PP, CT_RR_EE_PE, CT_RR_EE_EE,
     CT_RD_PT_PP, CT_RD_PT_PE, CT_RD_PT_PT, CT_RD_PT_EP, CT_RD_PT_TP, CT_RD_EE_PP, CT_RD_EE_PE, CT_RD_EE_EE, CT_RD_EE_EP,
-    FT_DD_PP, FT_DD_PE, FT_DD_PT, FT_DD_EE, FT_RD_PP, FT_RD_PE, FT_RD_PT, FT_RD_EE, FT_RD_EP, FT_RD_TP
+    FT_DD_PP, FT_DD_PE, FT_DD_PT, FT_DD_EE, FT_RR_PP, FT_RR_PE, FT_RR_PT, FT_RR_EE, FT_RD_PP, FT_RD_PE, FT_RD_PT, FT_RD_EE, FT_RD_EP, FT_RD_TP
 };
 constexpr int N_LISTS = 7;         // pt_pp pt_pe pt_pt ee_pp ee_pe ee_ee intersections
 static const int LIST_WIDTH[N_LISTS] = {5, 6, 4, 6, 5, 4, 4};
@@ -524,13 +525,16 @@ __device__ void emit_pt(const Dev& d, int mode, double dist, double stiffness, i
     int b[3];
     for (int k = 0; k < nB; k++) b[k] = d.v_ps_index[vB[k]];
     const bool A_soft = (A.ps == 0), B_soft = (B.ps == 0);
-    if (!A_soft && !B_soft) return;   // rigid-rigid pairs: potentials not built yet (rb_rb tables)
     if (mode == 0) {
         int row[8];
         if (A_soft && B_soft) {
             row[0] = A.group; row[1] = B.group; row[2] = a;
             for (int k = 0; k < nB; k++) row[3 + k] = b[k];
             push_row(d, nB == 1 ? CT_DD_PT_PP : (nB == 2 ? CT_DD_PT_PE : CT_DD_PT_PT), row);
+        } else if (!A_soft && !B_soft) {   // rigid point vs rigid primitive
+            row[0] = A.group; row[1] = B.group; row[2] = A.body; row[3] = B.body; row[4] = a;
+            for (int k = 0; k < nB; k++) row[5 + k] = b[k];
+            push_row(d, nB == 1 ? CT_RR_PT_PP : (nB == 2 ? CT_RR_PT_PE : CT_RR_PT_PT), row);
         } else if (!A_soft) {   // rigid point vs deformable primitive
             row[0] = A.group; row[1] = B.group; row[2] = A.body; row[3] = a;
             for (int k = 0; k < nB; k++) row[4 + k] = b[k];
@@ -551,6 +555,7 @@ __device__ void emit_pt(const Dev& d, int mode, double dist, double stiffness, i
         if (nB == 1) {
             proj_point_point(P, ld(d.x + 3 * vB[0]), T);
             if (A_soft && B_soft) { row[1] = a; row[2] = b[0]; push_friction(d, FT_DD_PP, row, T, bary, 0, mu, fn); }
+            else if (!A_soft && !B_soft) { row[1] = A.body; row[2] = B.body; row[3] = a; row[4] = b[0]; push_friction(d, FT_RR_PP, row, T, bary, 0, mu, fn); }
             else if (!A_soft) { row[1] = A.body; row[2] = a; row[3] = b[0]; push_friction(d, FT_RD_PP, row, T, bary, 0, mu, fn); }
             else { row[1] = B.body; row[2] = b[0]; row[3] = a; push_friction(d, FT_RD_PP, row, T, bary, 0, mu, fn); }
         } else if (nB == 2) {
@@ -558,6 +563,7 @@ __device__ void emit_pt(const Dev& d, int mode, double dist, double stiffness, i
             bary_point_edge(P, E0, E1, bary);
             proj_point_edge(P, E0, E1, T);
             if (A_soft && B_soft) { row[1] = a; row[2] = b[0]; row[3] = b[1]; push_friction(d, FT_DD_PE, row, T, bary, 2, mu, fn); }
+            else if (!A_soft && !B_soft) { row[1] = A.body; row[2] = B.body; row[3] = a; row[4] = b[0]; row[5] = b[1]; push_friction(d, FT_RR_PE, row, T, bary, 2, mu, fn); }
             else if (!A_soft) { row[1] = A.body; row[2] = a; row[3] = b[0]; row[4] = b[1]; push_friction(d, FT_RD_PE, row, T, bary, 2, mu, fn); }
             else { row[1] = B.body; row[2] = b[0]; row[3] = b[1]; row[4] = a; push_friction(d, FT_RD_EP, row, T, bary, 2, mu, fn); }
         } else {
@@ -565,6 +571,7 @@ __device__ void emit_pt(const Dev& d, int mode, double dist, double stiffness, i
             bary_point_triangle(P, T0, T1, T2, bary);
             proj_triangle(T0, T1, T2, T);
             if (A_soft && B_soft) { row[1] = a; row[2] = b[0]; row[3] = b[1]; row[4] = b[2]; push_friction(d, FT_DD_PT, row, T, bary, 3, mu, fn); }
+            else if (!A_soft && !B_soft) { row[1] = A.body; row[2] = B.body; row[3] = a; row[4] = b[0]; row[5] = b[1]; row[6] = b[2]; push_friction(d, FT_RR_PT, row, T, bary, 3, mu, fn); }
             else if (!A_soft) { row[1] = A.body; row[2] = a; row[3] = b[0]; row[4] = b[1]; row[5] = b[2]; push_friction(d, FT_RD_PT, row, T, bary, 3, mu, fn); }
             else { row[1] = B.body; row[2] = b[0]; row[3] = b[1]; row[4] = b[2]; row[5] = a; push_friction(d, FT_RD_TP, row, T, bary, 3, mu, fn); }
         }
@@ -623,21 +630,23 @@ __device__ void emit_ee(const Dev& d, int mode, double dist, double stiffness, i
     const double dhat = d.g_thickness[A.group] + d.g_thickness[B.group];
     if (dist > dhat) return;
     const bool A_soft = (A.ps == 0), B_soft = (B.ps == 0);
-    if (!A_soft && !B_soft) return;
     const int a0 = d.v_ps_index[eA[0]], a1 = d.v_ps_index[eA[1]], b0 = d.v_ps_index[eB[0]], b1 = d.v_ps_index[eB[1]];
     const int ap = (pA >= 0) ? d.v_ps_index[pA] : -1, bp = (pB >= 0) ? d.v_ps_index[pB] : -1;
     if (mode == 0) {
         int row[10];
         if (kind == 0) {
             if (A_soft && B_soft) { const int r[8] = {A.group, B.group, a0, a1, ap, b0, b1, bp}; push_row(d, CT_DD_EE_PP, r); }
+            else if (!A_soft && !B_soft) { const int r[10] = {A.group, B.group, A.body, B.body, a0, a1, ap, b0, b1, bp}; push_row(d, CT_RR_EE_PP, r); }
             else if (!A_soft) { const int r[9] = {A.group, B.group, A.body, a0, a1, ap, b0, b1, bp}; push_row(d, CT_RD_EE_PP, r); }
             else { const int r[9] = {B.group, A.group, B.body, b0, b1, bp, a0, a1, ap}; push_row(d, CT_RD_EE_PP, r); }
         } else if (kind == 1) {
             if (A_soft && B_soft) { const int r[7] = {A.group, B.group, a0, a1, ap, b0, b1}; push_row(d, CT_DD_EE_PE, r); }
+            else if (!A_soft && !B_soft) { const int r[9] = {A.group, B.group, A.body, B.body, a0, a1, ap, b0, b1}; push_row(d, CT_RR_EE_PE, r); }
             else if (!A_soft) { const int r[8] = {A.group, B.group, A.body, a0, a1, ap, b0, b1}; push_row(d, CT_RD_EE_PE, r); }
             else { const int r[8] = {B.group, A.group, B.body, b0, b1, a0, a1, ap}; push_row(d, CT_RD_EE_EP, r); }
         } else {
             if (A_soft && B_soft) { const int r[6] = {A.group, B.group, a0, a1, b0, b1}; push_row(d, CT_DD_EE_EE, r); }
+            else if (!A_soft && !B_soft) { const int r[8] = {A.group, B.group, A.body, B.body, a0, a1, b0, b1}; push_row(d, CT_RR_EE_EE, r); }
             else if (!A_soft) { const int r[7] = {A.group, B.group, A.body, a0, a1, b0, b1}; push_row(d, CT_RD_EE_EE, r); }
             else { const int r[7] = {B.group, A.group, B.body, b0, b1, a0, a1}; push_row(d, CT_RD_EE_EE, r); }
         }
@@ -651,6 +660,7 @@ __device__ void emit_ee(const Dev& d, int mode, double dist, double stiffness, i
         if (kind == 0) {
             proj_point_point(ld(d.x + 3 * pA), ld(d.x + 3 * pB), T);
             if (A_soft && B_soft) { row[1] = ap; row[2] = bp; push_friction(d, FT_DD_PP, row, T, bary, 0, mu, fn); }
+            else if (!A_soft && !B_soft) { row[1] = A.body; row[2] = B.body; row[3] = ap; row[4] = bp; push_friction(d, FT_RR_PP, row, T, bary, 0, mu, fn); }
             else if (!A_soft) { row[1] = A.body; row[2] = ap; row[3] = bp; push_friction(d, FT_RD_PP, row, T, bary, 0, mu, fn); }
             else { row[1] = B.body; row[2] = bp; row[3] = ap; push_friction(d, FT_RD_PP, row, T, bary, 0, mu, fn); }
         } else if (kind == 1) {
@@ -658,6 +668,7 @@ __device__ void emit_ee(const Dev& d, int mode, double dist, double stiffness, i
             bary_point_edge(P, E0, E1, bary);
             proj_point_edge(P, E0, E1, T);
             if (A_soft && B_soft) { row[1] = ap; row[2] = b0; row[3] = b1; push_friction(d, FT_DD_PE, row, T, bary, 2, mu, fn); }
+            else if (!A_soft && !B_soft) { row[1] = A.body; row[2] = B.body; row[3] = ap; row[4] = b0; row[5] = b1; push_friction(d, FT_RR_PE, row, T, bary, 2, mu, fn); }
             else if (!A_soft) { row[1] = A.body; row[2] = ap; row[3] = b0; row[4] = b1; push_friction(d, FT_RD_PE, row, T, bary, 2, mu, fn); }
             else { row[1] = B.body; row[2] = b0; row[3] = b1; row[4] = ap; push_friction(d, FT_RD_EP, row, T, bary, 2, mu, fn); }
         } else {
@@ -665,6 +676,7 @@ __device__ void emit_ee(const Dev& d, int mode, double dist, double stiffness, i
             bary_edge_edge(EA0, EA1, EB0, EB1, bary);     // in detection order, like the reference (even when the table swaps A and B)
             proj_edge_edge(EA0, EA1, EB0, EB1, T);
             if (A_soft && B_soft) { row[1] = a0; row[2] = a1; row[3] = b0; row[4] = b1; push_friction(d, FT_DD_EE, row, T, bary, 2, mu, fn); }
+            else if (!A_soft && !B_soft) { row[1] = A.body; row[2] = B.body; row[3] = a0; row[4] = a1; row[5] = b0; row[6] = b1; push_friction(d, FT_RR_EE, row, T, bary, 2, mu, fn); }
             else if (!A_soft) { row[1] = A.body; row[2] = a0; row[3] = a1; row[4] = b0; row[5] = b1; push_friction(d, FT_RD_EE, row, T, bary, 2, mu, fn); }
             else { row[1] = B.body; row[2] = b0; row[3] = b1; row[4] = a0; row[5] = a1; push_friction(d, FT_RD_EE, row, T, bary, 2, mu, fn); }
         }

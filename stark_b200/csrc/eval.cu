@@ -138,12 +138,25 @@ const std::vector<KernelInfo>& all_kernels()
         SB_KERNEL(rb_constraint_directions, "rb_constraint_directions"),
         SB_KERNEL(rb_constraint_angle_limits, "rb_constraint_angle_limits"),
         SB_KERNEL(rb_constraint_damped_spring, "rb_constraint_damped_spring"),
+        SB_KERNEL(rb_constraint_linear_velocity, "rb_constraint_linear_velocity"),
+        SB_KERNEL(rb_constraint_angular_velocity, "rb_constraint_angular_velocity"),
+        SB_KERNEL(EnergyAttachments_d_d_p_p, "EnergyAttachments_d_d_p_p"),
+        SB_KERNEL(EnergyAttachments_d_d_p_e, "EnergyAttachments_d_d_p_e"),
+        SB_KERNEL(EnergyAttachments_d_d_p_t, "EnergyAttachments_d_d_p_t"),
+        SB_KERNEL(EnergyAttachments_d_d_e_e, "EnergyAttachments_d_d_e_e"),
+        SB_KERNEL(EnergyAttachments_rb_d, "EnergyAttachments_rb_d"),
         SB_KERNEL(contact_d_d_pt_pp, "contact_d_d_pt_pp_cubic"),
         SB_KERNEL(contact_d_d_pt_pe, "contact_d_d_pt_pe_cubic"),
         SB_KERNEL(contact_d_d_pt_pt, "contact_d_d_pt_pt_cubic"),
         SB_KERNEL(contact_d_d_ee_pp, "contact_d_d_ee_pp_cubic"),
         SB_KERNEL(contact_d_d_ee_pe, "contact_d_d_ee_pe_cubic"),
         SB_KERNEL(contact_d_d_ee_ee, "contact_d_d_ee_ee_cubic"),
+        SB_KERNEL(contact_rb_rb_pt_pp, "contact_rb_rb_pt_pp_cubic"),
+        SB_KERNEL(contact_rb_rb_pt_pe, "contact_rb_rb_pt_pe_cubic"),
+        SB_KERNEL(contact_rb_rb_pt_pt, "contact_rb_rb_pt_pt_cubic"),
+        SB_KERNEL(contact_rb_rb_ee_pp, "contact_rb_rb_ee_pp_cubic"),
+        SB_KERNEL(contact_rb_rb_ee_pe, "contact_rb_rb_ee_pe_cubic"),
+        SB_KERNEL(contact_rb_rb_ee_ee, "contact_rb_rb_ee_ee_cubic"),
         SB_KERNEL(contact_rb_d_pt_pp, "contact_rb_d_pt_pp_cubic"),
         SB_KERNEL(contact_rb_d_pt_pe, "contact_rb_d_pt_pe_cubic"),
         SB_KERNEL(contact_rb_d_pt_pt, "contact_rb_d_pt_pt_cubic"),
@@ -157,6 +170,10 @@ const std::vector<KernelInfo>& all_kernels()
         SB_KERNEL(friction_d_d_pe, "friction_d_d_pe_C0"),
         SB_KERNEL(friction_d_d_pt, "friction_d_d_pt_C0"),
         SB_KERNEL(friction_d_d_ee, "friction_d_d_ee_C0"),
+        SB_KERNEL(friction_rb_rb_pp, "friction_rb_rb_pp_C0"),
+        SB_KERNEL(friction_rb_rb_pe, "friction_rb_rb_pe_C0"),
+        SB_KERNEL(friction_rb_rb_pt, "friction_rb_rb_pt_C0"),
+        SB_KERNEL(friction_rb_rb_ee, "friction_rb_rb_ee_C0"),
         SB_KERNEL(friction_rb_d_pp, "friction_rb_d_pp_C0"),
         SB_KERNEL(friction_rb_d_pe, "friction_rb_d_pe_C0"),
         SB_KERNEL(friction_rb_d_pt, "friction_rb_d_pt_C0"),

@@ -839,4 +839,224 @@ struct friction_rb_d_tp {
     }
 };
 
+
+// ---- velocity controllers (EnergyRigidBodyConstraints.cpp:198-239 + RigidBodyConstraints.h:54-69 c1_controller_energy) ----
+template<class T> SB_HD T c1_controller(const V3<T>& da1, const V3<T>& va1, const V3<T>& vb1, double target, double max_force, double delay, double dt)
+{
+    const T v = dot(da1, vb1 - va1);
+    const double k = max_force / delay;
+    const double eps = delay / 2.0;
+    const T dv = v - target;
+    if (val(dv) < -delay) return -(max_force * (dv - eps) * dt);
+    if (val(dv) < delay) return 0.5 * k * sq(dv) * dt;
+    return max_force * (dv - eps) * dt;
+}
+// DoF order: va, vb, wa
+struct rb_constraint_linear_velocity {
+    static constexpr int N_IN = 21, N_DOF = 9, NB = 3;
+    static constexpr int DOF_SLOT[NB] = {7, 10, 13};
+    template<class T> SB_HD static T energy(const double* in, const Seed<T>& s)
+    {
+        const double dt = in[20];
+        const M3<T> Ra = rotation_q1(s.dof3(6, in + 13), in + 16, dt);
+        const V3<T> da1 = mul(Ra, ld3(in + 0));
+        return c1_controller(da1, s.dof3(0, in + 7), s.dof3(3, in + 10), in[3], in[4], in[5], dt);
+    }
+};
+// DoF order: wa, wb
+struct rb_constraint_angular_velocity {
+    static constexpr int N_IN = 18, N_DOF = 6, NB = 2;
+    static constexpr int DOF_SLOT[NB] = {7, 10};
+    template<class T> SB_HD static T energy(const double* in, const Seed<T>& s)
+    {
+        const double dt = in[17];
+        const V3<T> wa = s.dof3(0, in + 7), wb = s.dof3(3, in + 10);
+        const M3<T> Ra = rotation_q1(wa, in + 13, dt);
+        const V3<T> da1 = mul(Ra, ld3(in + 0));
+        return c1_controller(da1, wa, wb, in[3], in[4], in[5], dt);
+    }
+};
+
+// =====================================================================================================
+// attachments (S/models/interactions/EnergyAttachments.cpp:17-135): 0.5 k |q - p|^2 between (barycentric) points
+// =====================================================================================================
+struct EnergyAttachments_d_d_p_p {
+    static constexpr int N_IN = 14, N_DOF = 6, NB = 2;
+    static constexpr int DOF_SLOT[NB] = {0, 3};
+    template<class T> SB_HD static T energy(const double* in, const Seed<T>& s)
+    {
+        const double dt = in[13];
+        const V3<T> a = soft_x1(s, 0, in + 0, in + 6, dt), b = soft_x1(s, 3, in + 3, in + 9, dt);
+        return 0.5 * in[12] * norm2(b - a);
+    }
+};
+struct EnergyAttachments_d_d_p_e {
+    static constexpr int N_IN = 22, N_DOF = 9, NB = 3;
+    static constexpr int DOF_SLOT[NB] = {0, 3, 6};
+    template<class T> SB_HD static T energy(const double* in, const Seed<T>& s)
+    {
+        const double dt = in[21];
+        const V3<T> p = soft_x1(s, 0, in + 0, in + 9, dt);
+        const V3<T> q = in[18] * soft_x1(s, 3, in + 3, in + 12, dt) + in[19] * soft_x1(s, 6, in + 6, in + 15, dt);
+        return 0.5 * in[20] * norm2(q - p);
+    }
+};
+struct EnergyAttachments_d_d_p_t {
+    static constexpr int N_IN = 29, N_DOF = 12, NB = 4;
+    static constexpr int DOF_SLOT[NB] = {0, 3, 6, 9};
+    template<class T> SB_HD static T energy(const double* in, const Seed<T>& s)
+    {
+        const double dt = in[28];
+        const V3<T> p = soft_x1(s, 0, in + 0, in + 12, dt);
+        const V3<T> q = in[24] * soft_x1(s, 3, in + 3, in + 15, dt) + in[25] * soft_x1(s, 6, in + 6, in + 18, dt) + in[26] * soft_x1(s, 9, in + 9, in + 21, dt);
+        return 0.5 * in[27] * norm2(q - p);
+    }
+};
+struct EnergyAttachments_d_d_e_e {
+    static constexpr int N_IN = 30, N_DOF = 12, NB = 4;
+    static constexpr int DOF_SLOT[NB] = {0, 3, 6, 9};
+    template<class T> SB_HD static T energy(const double* in, const Seed<T>& s)
+    {
+        const double dt = in[29];
+        const V3<T> p = in[24] * soft_x1(s, 0, in + 0, in + 12, dt) + in[25] * soft_x1(s, 3, in + 3, in + 15, dt);
+        const V3<T> q = in[26] * soft_x1(s, 6, in + 6, in + 18, dt) + in[27] * soft_x1(s, 9, in + 9, in + 21, dt);
+        return 0.5 * in[28] * norm2(q - p);
+    }
+};
+// DoF order: soft point, rb v, rb w
+struct EnergyAttachments_rb_d {
+    static constexpr int N_IN = 24, N_DOF = 9, NB = 3;
+    static constexpr int DOF_SLOT[NB] = {2, 11, 14};
+    template<class T> SB_HD static T energy(const double* in, const Seed<T>& s)
+    {
+        const double dt = in[1];
+        const V3<T> xd = soft_x1(s, 0, in + 2, in + 5, dt);
+        const RigidFrame<T> f = rigid_frame(s, 3, 6, in + 11, in + 14, in + 17, in + 20, dt);
+        return 0.5 * in[0] * norm2(xd - rigid_x1(f, in + 8));
+    }
+};
+
+// =====================================================================================================
+// rigid - rigid contact (EnergyFrictionalContact.cpp:900-968) ; DoF order: v_a, v_b, w_a, w_b (each symbol set of a body
+// that the reference creates separately -- edge and edge-point of ee_pp / ee_pe -- is its own block)
+// =====================================================================================================
+struct contact_rb_rb_pt_pp {
+    static constexpr int N_IN = 37, N_DOF = 12, NB = 4;
+    static constexpr int DOF_SLOT[NB] = {4, 21, 7, 24};
+    template<class T> SB_HD static T energy(const double* in, const Seed<T>& s)
+    {
+        const RigidFrame<T> fa = rigid_frame(s, 0, 6, in + 4, in + 7, in + 10, in + 13, in[0]);
+        const RigidFrame<T> fb = rigid_frame(s, 3, 9, in + 21, in + 24, in + 27, in + 30, in[17]);
+        return barrier_cubic(distance_point_point(rigid_x1(fa, in + 1), rigid_x1(fb, in + 18)), in[34] + in[35], in[36]);
+    }
+};
+struct contact_rb_rb_pt_pe {
+    static constexpr int N_IN = 40, N_DOF = 12, NB = 4;
+    static constexpr int DOF_SLOT[NB] = {4, 24, 7, 27};
+    template<class T> SB_HD static T energy(const double* in, const Seed<T>& s)
+    {
+        const RigidFrame<T> fa = rigid_frame(s, 0, 6, in + 4, in + 7, in + 10, in + 13, in[0]);
+        const RigidFrame<T> fb = rigid_frame(s, 3, 9, in + 24, in + 27, in + 30, in + 33, in[17]);
+        return barrier_cubic(distance_point_line(rigid_x1(fa, in + 1), rigid_x1(fb, in + 18), rigid_x1(fb, in + 21)), in[37] + in[38], in[39]);
+    }
+};
+struct contact_rb_rb_pt_pt {
+    static constexpr int N_IN = 43, N_DOF = 12, NB = 4;
+    static constexpr int DOF_SLOT[NB] = {4, 27, 7, 30};
+    template<class T> SB_HD static T energy(const double* in, const Seed<T>& s)
+    {
+        const RigidFrame<T> fa = rigid_frame(s, 0, 6, in + 4, in + 7, in + 10, in + 13, in[0]);
+        const RigidFrame<T> fb = rigid_frame(s, 3, 9, in + 27, in + 30, in + 33, in + 36, in[17]);
+        return barrier_cubic(distance_point_plane(rigid_x1(fa, in + 1), rigid_x1(fb, in + 18), rigid_x1(fb, in + 21), rigid_x1(fb, in + 24)), in[40] + in[41], in[42]);
+    }
+};
+// blocks: v_a (edge), v_a (point), v_b (edge), v_b (point), w_a (edge), w_a (point), w_b (edge), w_b (point)
+struct contact_rb_rb_ee_pp {
+    static constexpr int N_IN = 89, N_DOF = 24, NB = 8;
+    static constexpr int DOF_SLOT[NB] = {7, 30, 50, 73, 10, 33, 53, 76};
+    template<class T> SB_HD static T energy(const double* in, const Seed<T>& s)
+    {
+        const RigidFrame<T> fea = rigid_frame(s, 0, 12, in + 7, in + 10, in + 13, in + 16, in[0]);
+        const RigidFrame<T> fpa = rigid_frame(s, 3, 15, in + 30, in + 33, in + 36, in + 39, in[26]);
+        const RigidFrame<T> feb = rigid_frame(s, 6, 18, in + 50, in + 53, in + 56, in + 59, in[43]);
+        const RigidFrame<T> fpb = rigid_frame(s, 9, 21, in + 73, in + 76, in + 79, in + 82, in[69]);
+        const V3<T> ea0 = rigid_x1(fea, in + 1), ea1 = rigid_x1(fea, in + 4), eb0 = rigid_x1(feb, in + 44), eb1 = rigid_x1(feb, in + 47);
+        const T d = distance_point_point(rigid_x1(fpa, in + 27), rigid_x1(fpb, in + 70));
+        return ee_mollifier(ea0, ea1, eb0, eb1, in + 20, in + 23, in + 63, in + 66) * barrier_cubic(d, in[87] + in[88], in[86]);
+    }
+};
+// blocks: v_a (edge), v_a (point), v_b, w_a (edge), w_a (point), w_b
+struct contact_rb_rb_ee_pe {
+    static constexpr int N_IN = 72, N_DOF = 18, NB = 6;
+    static constexpr int DOF_SLOT[NB] = {7, 30, 50, 10, 33, 53};
+    template<class T> SB_HD static T energy(const double* in, const Seed<T>& s)
+    {
+        const RigidFrame<T> fea = rigid_frame(s, 0, 9, in + 7, in + 10, in + 13, in + 16, in[0]);
+        const RigidFrame<T> fpa = rigid_frame(s, 3, 12, in + 30, in + 33, in + 36, in + 39, in[26]);
+        const RigidFrame<T> feb = rigid_frame(s, 6, 15, in + 50, in + 53, in + 56, in + 59, in[43]);
+        const V3<T> ea0 = rigid_x1(fea, in + 1), ea1 = rigid_x1(fea, in + 4), eb0 = rigid_x1(feb, in + 44), eb1 = rigid_x1(feb, in + 47);
+        const T d = distance_point_line(rigid_x1(fpa, in + 27), eb0, eb1);
+        return ee_mollifier(ea0, ea1, eb0, eb1, in + 20, in + 23, in + 63, in + 66) * barrier_cubic(d, in[70] + in[71], in[69]);
+    }
+};
+struct contact_rb_rb_ee_ee {
+    static constexpr int N_IN = 55, N_DOF = 12, NB = 4;
+    static constexpr int DOF_SLOT[NB] = {7, 33, 10, 36};
+    template<class T> SB_HD static T energy(const double* in, const Seed<T>& s)
+    {
+        const RigidFrame<T> fa = rigid_frame(s, 0, 6, in + 7, in + 10, in + 13, in + 16, in[0]);
+        const RigidFrame<T> fb = rigid_frame(s, 3, 9, in + 33, in + 36, in + 39, in + 42, in[26]);
+        const V3<T> ea0 = rigid_x1(fa, in + 1), ea1 = rigid_x1(fa, in + 4), eb0 = rigid_x1(fb, in + 27), eb1 = rigid_x1(fb, in + 30);
+        const T d = distance_line_line(ea0, ea1, eb0, eb1);
+        return ee_mollifier(ea0, ea1, eb0, eb1, in + 20, in + 23, in + 46, in + 49) * barrier_cubic(d, in[53] + in[54], in[52]);
+    }
+};
+
+// ---- rigid - rigid friction (EnergyFrictionalContact.cpp:1119-1158) ; DoF order: v_a, v_b, w_a, w_b ----
+struct friction_rb_rb_pp {
+    static constexpr int N_IN = 44, N_DOF = 12, NB = 4;
+    static constexpr int DOF_SLOT[NB] = {4, 21, 7, 24};
+    template<class T> SB_HD static T energy(const double* in, const Seed<T>& s)
+    {
+        const RigidFrame<T> fa = rigid_frame(s, 0, 6, in + 4, in + 7, in + 10, in + 13, in[0]);
+        const RigidFrame<T> fb = rigid_frame(s, 3, 9, in + 21, in + 24, in + 27, in + 30, in[17]);
+        return friction_C0(rigid_v1(fb, in + 18) - rigid_v1(fa, in + 1), in + 34, in[40], in[41], in[42], in[43]);
+    }
+};
+struct friction_rb_rb_pe {
+    static constexpr int N_IN = 49, N_DOF = 12, NB = 4;
+    static constexpr int DOF_SLOT[NB] = {4, 24, 7, 27};
+    template<class T> SB_HD static T energy(const double* in, const Seed<T>& s)
+    {
+        const RigidFrame<T> fa = rigid_frame(s, 0, 6, in + 4, in + 7, in + 10, in + 13, in[0]);
+        const RigidFrame<T> fb = rigid_frame(s, 3, 9, in + 24, in + 27, in + 30, in + 33, in[17]);
+        const V3<T> vb = in[37] * rigid_v1(fb, in + 18) + in[38] * rigid_v1(fb, in + 21);
+        return friction_C0(vb - rigid_v1(fa, in + 1), in + 39, in[45], in[46], in[47], in[48]);
+    }
+};
+struct friction_rb_rb_pt {
+    static constexpr int N_IN = 53, N_DOF = 12, NB = 4;
+    static constexpr int DOF_SLOT[NB] = {4, 27, 7, 30};
+    template<class T> SB_HD static T energy(const double* in, const Seed<T>& s)
+    {
+        const RigidFrame<T> fa = rigid_frame(s, 0, 6, in + 4, in + 7, in + 10, in + 13, in[0]);
+        const RigidFrame<T> fb = rigid_frame(s, 3, 9, in + 27, in + 30, in + 33, in + 36, in[17]);
+        const V3<T> vb = in[40] * rigid_v1(fb, in + 18) + in[41] * rigid_v1(fb, in + 21) + in[42] * rigid_v1(fb, in + 24);
+        return friction_C0(vb - rigid_v1(fa, in + 1), in + 43, in[49], in[50], in[51], in[52]);
+    }
+};
+struct friction_rb_rb_ee {
+    static constexpr int N_IN = 52, N_DOF = 12, NB = 4;
+    static constexpr int DOF_SLOT[NB] = {7, 27, 10, 30};
+    template<class T> SB_HD static T energy(const double* in, const Seed<T>& s)
+    {
+        const RigidFrame<T> fa = rigid_frame(s, 0, 6, in + 7, in + 10, in + 13, in + 16, in[0]);
+        const RigidFrame<T> fb = rigid_frame(s, 3, 9, in + 27, in + 30, in + 33, in + 36, in[20]);
+        const V3<T> a0 = rigid_v1(fa, in + 1), a1 = rigid_v1(fa, in + 4), b0 = rigid_v1(fb, in + 21), b1 = rigid_v1(fb, in + 24);
+        const V3<T> va = a0 + in[40] * (a1 - a0);
+        const V3<T> vb = b0 + in[41] * (b1 - b0);
+        return friction_C0(vb - va, in + 42, in[48], in[49], in[50], in[51]);
+    }
+};
+
 }  // namespace sbpot

@@ -26,6 +26,10 @@ FIXTURES = {
     "tetbar_n2": ["--scene", "tetbar", "--n", "2", "--nz", "10", "--steps", "3"],
     "cloth_n8": ["--scene", "cloth", "--n", "8", "--steps", "12", "--dt", "0.01"],
     "cloth_shells_n8": ["--scene", "cloth_shells", "--n", "8", "--steps", "12", "--dt", "0.01"],
+    # rigid-rigid contact + friction (all six + four tables), linear / angular velocity controllers
+    "boxes": ["--scene", "boxes", "--n", "1", "--steps", "4", "--vz", "0.5"],
+    # the five attachment potentials
+    "attach_n6": ["--scene", "attach", "--n", "6", "--steps", "3"],
 }
 
 

@@ -5,7 +5,7 @@ import pytest
 
 from golden_util import Golden, bind
 
-FIXTURES = ["tetdrop_n3", "tetdrop_n5", "tetbar_n2", "cloth_n8", "cloth_shells_n8"]
+FIXTURES = ["tetdrop_n3", "tetdrop_n5", "tetbar_n2", "cloth_n8", "cloth_shells_n8", "boxes", "attach_n6"]
 RTOL = 1e-10  # north_star: 1e-10 relative on gradient / residual
 
 
@@ -30,7 +30,10 @@ def test_element_outputs_match_reference(fixture):
         n = p["n_dofs"]
         assert out.shape == ref.shape, p["name"]
         # energy
-        np.testing.assert_allclose(out[:, 0], ref[:, 0], rtol=RTOL, atol=RTOL * np.abs(ref[:, 0]).max(), err_msg=p["name"] + " E")
+        # (bending energies of a nearly flat sheet are ~1e-14 and dominated by cancellation in both implementations: the
+        #  absolute floor is RTOL of the scene's energy per element, far below anything the solver can see)
+        e_floor = RTOL * max(np.abs(ref[:, 0]).max(), abs(g.meta["E"]) / max(1, len(ref)))
+        np.testing.assert_allclose(out[:, 0], ref[:, 0], rtol=RTOL, atol=e_floor, err_msg=p["name"] + " E")
         # gradient: relative to the element's own gradient scale
         gs = np.abs(ref[:, 1:1 + n]).max(axis=1, keepdims=True) + 1e-300
         # The dihedral angle is acos((1 - 1e-12) n0.n1): on a nearly flat cloth d(acos)/dx ~ 1/sqrt(2e-12) amplifies the
