@@ -117,6 +117,10 @@ SB_API int sb_bcsr_get(sb_context* ctx, int64_t* host_rows, int32_t* host_cols, 
  * Solves H du = -grad.  out_ok = 0 when p^T A p <= 0 was met (indefiniteness) or max_iterations was hit. */
 SB_API int sb_solve_pcg(sb_context* ctx, double abs_tol, double rel_tol, int max_iterations, int stop_on_indefiniteness,
                  int* out_iterations, int* out_ok, double* out_du_dot_grad, double* out_du_inf);
+/* DirectLLT branch of the same function (NewtonsMethod.cpp:395-418: to_triplets -> Eigen::SimplicialLLT): dense blocked
+ * Cholesky in FP64 of the assembled matrix, n <= 32768 DoFs.  out_ok = 0 when the matrix is not positive definite
+ * (Eigen's info() != Success). */
+SB_API int sb_solve_llt(sb_context* ctx, int* out_ok, double* out_du_dot_grad, double* out_du_inf);
 SB_API int sb_du_get(sb_context* ctx, double* host_du);
 
 /* ---- line search support ----------------------------------------------------------------------------------------------
@@ -186,7 +190,7 @@ typedef struct sb_newton_settings {
     double projection_eps;
     int32_t project_to_pd_use_mirroring, project_on_demand_countdown;
     double ppn_tightening_factor, ppn_release_factor;
-    int32_t linear_solver;     /* 0 DirectLLT (not built yet), 1 BDPCG */
+    int32_t linear_solver;     /* 0 DirectLLT (dense, n <= 32768), 1 BDPCG */
     int32_t cg_max_iterations;
     double cg_abs_tolerance, cg_rel_tolerance;
     int32_t cg_stop_on_indefiniteness;

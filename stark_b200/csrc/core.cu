@@ -304,6 +304,7 @@ void sb_destroy(sb_context* ctx)
     pcg_destroy(ctx);
     contact_destroy(ctx);
     projector_destroy(ctx);
+    direct_destroy(ctx);
     for (auto& a : ctx->arrays) a.d.release();
     for (auto& p : ctx->potentials) { p.conn.release(); p.slots.release(); }
     ctx->H.release(); ctx->rows.release(); ctx->E_elem.release(); ctx->grad.release(); ctx->du.release();

@@ -129,6 +129,7 @@ struct Assembly;   // assembly.cu
 struct Pcg;        // pcg.cu
 struct Contact;    // contact.cu
 struct Projector;  // project.cu
+struct Direct;     // direct.cu
 
 }  // namespace sb
 
@@ -180,6 +181,7 @@ struct sb_context {
     sb::Pcg* pcg = nullptr;
     sb::Contact* contact = nullptr;
     sb::Projector* projector = nullptr;
+    sb::Direct* direct = nullptr;
 };
 
 namespace sb {
@@ -197,6 +199,8 @@ void assembly_destroy(sb_context* ctx);
 void pcg_destroy(sb_context* ctx);
 void contact_destroy(sb_context* ctx);
 void projector_destroy(sb_context* ctx);
+void direct_destroy(sb_context* ctx);
+int solve_llt_internal(sb_context* ctx, int* out_ok, double* out_du_dot_grad, double* out_du_inf);
 int assemble_internal(sb_context* ctx);
 // where the blocks of an element land in the assembled matrix: sources are numbered static-first; a static source maps
 // through its static block, a dynamic one through its dynamic block

@@ -55,7 +55,7 @@ extern "C" void sb_newton_default_settings(sb_newton_settings* s)
 extern "C" int sb_newton_solve(sb_context* ctx, const sb_newton_settings* S, sb_newton_stats* stats)
 {
     if (!ctx || !S || !stats) return fail(ctx, SB_ERR_ARG, "sb_newton_solve: bad argument");
-    if (S->linear_solver != 1) return fail(ctx, SB_ERR_ARG, "sb_newton_solve: only BDPCG is built (DirectLLT is a later row)");
+    if (S->linear_solver != 0 && S->linear_solver != 1) return fail(ctx, SB_ERR_ARG, "sb_newton_solve: unknown linear solver");
     recompute_dof_offsets(ctx);
     const int ndofs = ctx->ndofs;
     if (ndofs <= 0) return fail(ctx, SB_ERR_STATE, "sb_newton_solve: no degrees of freedom");
@@ -147,7 +147,9 @@ extern "C" int sb_newton_solve(sb_context* ctx, const sb_newton_settings* S, sb_
             const double forcing = std::min(1e-2, residual * std::min(0.5, std::sqrt(residual)));
             const double abs_tol = std::max(forcing, S->cg_abs_tolerance);
             int cg_it = 0, ok = 0;
-            if ((rc = solve_pcg_internal(ctx, abs_tol, S->cg_rel_tolerance, S->cg_max_iterations, S->cg_stop_on_indefiniteness, &cg_it, &ok, &du_dot_grad, &du_inf))) return rc;
+            if (S->linear_solver == 0) {
+                if ((rc = solve_llt_internal(ctx, &ok, &du_dot_grad, &du_inf))) return rc;
+            } else if ((rc = solve_pcg_internal(ctx, abs_tol, S->cg_rel_tolerance, S->cg_max_iterations, S->cg_stop_on_indefiniteness, &cg_it, &ok, &du_dot_grad, &du_inf))) return rc;
             stats->cg_iterations += cg_it;
             const bool can_project_more = (S->projection_mode != PNewton) && !all_projected;
             if (!ok) {

@@ -148,3 +148,63 @@ def test_newton_converges_from_injected_state(fixture):
     assert st.last_energy < E0
     assert 1 <= st.newton_iterations <= 20
     ctx.close()
+
+
+def _dense(rows, cols, vals):
+    n = 3 * (len(rows) - 1)
+    A = np.zeros((n, n))
+    v = vals.astype(np.float64).reshape(-1, 3, 3)   # column-major inside the block
+    for br in range(len(rows) - 1):
+        for j in range(rows[br], rows[br + 1]):
+            A[3 * br:3 * br + 3, cols[j]:cols[j] + 3] = v[j].T
+    return A
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fixture", ["tetdrop_n3", "tetbar_n2", "cloth_n8", "attach_n6"])
+def test_direct_llt(fixture):
+    """DirectLLT branch (NewtonsMethod.cpp:395-418): the dense blocked Cholesky solves the assembled (float-stored) matrix
+    like a FP64 direct solver does; an indefinite matrix is reported as a failed solve."""
+    capi, ctx, g, handles = setup(fixture)
+    ctx.eval("PGH")
+    ctx.project_to_pd(0.0)          # every element PD -> the assembled matrix is PD
+    ctx.assemble()
+    rows, cols, vals = ctx.bcsr()
+    grad = ctx.grad()
+    out = ctx.solve_llt()
+    assert out["ok"]
+    du = ctx.du()
+    A = _dense(rows, cols, vals)
+    A = np.tril(A) + np.tril(A, -1).T   # the factorisation reads the lower triangle
+    x = np.linalg.solve(A, -grad)
+    assert np.abs(du - x).max() <= 1e-9 * np.abs(x).max()
+    assert abs(out["du_dot_grad"] - du @ grad) <= 1e-12 * abs(du @ grad)
+    assert out["du_inf"] == np.abs(du).max()
+    assert out["du_dot_grad"] < 0
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_direct_llt_reports_indefinite_matrix():
+    capi, ctx, g, handles = setup("tetdrop_n3")   # unprojected barrier Hessians: lambda_min = -4.85
+    ctx.eval("PGH")
+    ctx.assemble()
+    rows, cols, vals = ctx.bcsr()
+    A = _dense(rows, cols, vals)
+    A = np.tril(A) + np.tril(A, -1).T
+    assert np.linalg.eigvalsh(A).min() < 0
+    assert not ctx.solve_llt()["ok"]
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_newton_with_direct_llt():
+    capi, ctx, g, handles = setup("tetbar_n2")
+    s = ctx.newton_default_settings()
+    s.contact_enabled = 0
+    s.max_iterations = 50
+    s.linear_solver = 0
+    st = ctx.newton_solve(s)
+    assert st.result == 0 and st.cg_iterations == 0
+    assert st.last_residual < 1e-6 or st.n_evaluations > 1
+    ctx.close()
