@@ -298,8 +298,45 @@ static Scene scene_attach(const Args& a)
 	return sc;
 }
 
+// C4: n^3 tet grid (Soft_Rubber, bottom face prescribed) under a chain of nb rigid boxes joined by hinges (pattern of
+// examples/rb_constraint_test_scenes.cpp:173-183), first box fixed; the chain swings down onto the soft body (coupled
+// solve through rigid-deformable contact + friction).  nb = --ny (default 10).
+static Scene scene_tetchain(const Args& a)
+{
+	Scene sc;
+	stark::Settings settings = base_settings(a, "tetchain");
+	sc.sim = std::make_unique<stark::Simulation>(settings);
+	auto& sim = *sc.sim;
+	stark::EnergyFrictionalContact::GlobalParams cp;
+	cp.default_contact_thickness = 0.001;
+	cp.min_contact_stiffness = 1e7;
+	sim.interactions->contact->set_global_params(cp);
+	auto material = stark::Volume::Params::Soft_Rubber();
+	material.inertia.density = 50.0;   // light foam: the block keeps its shape under its own weight
+	auto [V, T, H] = sim.presets->deformables->add_volume_grid("body", { 1.0, 1.0, 1.0 }, { a.n, a.n, a.n }, material);
+	H.point_set.add_displacement({ 0.0, 0.0, 0.5 });
+	sim.deformables->prescribed_positions->add_inside_aabb(H.point_set, { 0.0, 0.0, 0.0 }, { 1.0, 1.0, 0.001 }, stark::EnergyPrescribedPositions::Params().set_stiffness(1e7));
+	const int nb = (a.ny > 0) ? a.ny : 10;
+	std::vector<stark::RigidBodyHandler> bodies;
+	std::vector<stark::ContactHandler> contacts;
+	for (int i = 0; i < nb; i++) {
+		auto [Vb, Cb, b] = sim.presets->rigidbodies->add_box("b" + std::to_string(i), 1.0, 0.08);
+		b.rigidbody.set_translation({ -0.2 + 0.1 * i, 0.0, 1.0 + 0.04 + a.drop + 0.04 });
+		sim.interactions->contact->set_friction(b.contact, H.contact, 0.3);
+		if (i == 0) sim.rigidbodies->add_constraint_fix(b.rigidbody);
+		else {
+			sim.rigidbodies->add_constraint_hinge(bodies.back(), b.rigidbody, { -0.25 + 0.1 * i, 0.0, 1.0 + 0.04 + a.drop + 0.04 }, Eigen::Vector3d::UnitY());
+			sim.interactions->contact->disable_collision(contacts.back(), b.contact);
+		}
+		bodies.push_back(b.rigidbody);
+		contacts.push_back(b.contact);
+	}
+	return sc;
+}
+
 static Scene make_scene(const Args& a)
 {
+	if (a.scene == "tetchain") return scene_tetchain(a);
 	if (a.scene == "boxes") return scene_boxes(a);
 	if (a.scene == "attach") return scene_attach(a);
 	if (a.scene == "tetdrop") return scene_tetdrop(a);

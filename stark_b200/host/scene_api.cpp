@@ -57,6 +57,40 @@ void build_tetbar(Scene& sc, int nx, int ny, int nz, double dt, int device, void
     Simulation* ps = &sim;
     sim.add_time_event([ps, g1](double t) { ps->prescribed_positions.set_transformation(g1, {0.0, 0.0, 0.0}, 90.0 * t, {0.0, 0.0, 1.0}); });
 }
+
+// C4: n^3 tet grid with a prescribed bottom face under a chain of nb hinged rigid boxes, first box fixed
+// (oracle/ref_driver.cpp scene_tetchain)
+void build_tetchain(Scene& sc, int n, int nb, double dt, double drop, int device, void* stream)
+{
+    Settings s;
+    s.simulation.max_time_step_size = dt;
+    s.device = device; s.stream = stream;
+    sc.sim = std::make_unique<Simulation>(s);
+    Simulation& sim = *sc.sim;
+    EnergyFrictionalContact::GlobalParams cp;
+    cp.default_contact_thickness = 0.001;
+    cp.min_contact_stiffness = 1e7;
+    sim.contact.set_global_params(cp);
+    VolumeParams material = VolumeParams::Soft_Rubber();
+    material.density = 50.0;   // light foam: the block keeps its shape under its own weight
+    auto H = sim.add_volume_grid({1.0, 1.0, 1.0}, {n, n, n}, material);
+    sim.dyn.add_displacement(H.point_set, {0.0, 0.0, 0.5});
+    sim.prescribed_positions.add_inside_aabb(sim.dyn, H.point_set, {0.0, 0.0, 0.0}, {1.0, 1.0, 0.001}, 1e7, std::numeric_limits<double>::max());
+    if (nb <= 0) nb = 10;
+    const double z = 1.0 + 0.04 + drop + 0.04;
+    Simulation::BoxHandle prev{-1, -1};
+    for (int i = 0; i < nb; i++) {
+        auto b = sim.add_box(1.0, {0.08, 0.08, 0.08});
+        sim.set_translation(b.body, {-0.2 + 0.1 * i, 0.0, z});
+        sim.contact.set_friction(b.contact_group, H.contact_group, 0.3);
+        if (i == 0) sim.rb_constraints.add_fix(sim.rb, b.body);
+        else {
+            sim.rb_constraints.add_hinge(sim.rb, prev.body, b.body, {-0.25 + 0.1 * i, 0.0, z}, {0.0, 1.0, 0.0});
+            sim.contact.disable_collision(prev.contact_group, b.contact_group);
+        }
+        prev = b;
+    }
+}
 }  // namespace
 
 extern "C" {
@@ -67,6 +101,7 @@ __attribute__((visibility("default"))) void* sbh_scene_create(const char* name, 
     sc->name = name;
     if (sc->name == "tetdrop") build_tetdrop(*sc, n, dt, drop, vz, device, stream);
     else if (sc->name == "tetbar") build_tetbar(*sc, n, ny, nz, dt, device, stream);
+    else if (sc->name == "tetchain") build_tetchain(*sc, n, ny, dt, drop, device, stream);
     else { delete sc; return nullptr; }
     return sc;
 }

@@ -28,6 +28,8 @@ FIXTURES = {
     "cloth_shells_n8": ["--scene", "cloth_shells", "--n", "8", "--steps", "12", "--dt", "0.01"],
     # rigid-rigid contact + friction (all six + four tables), linear / angular velocity controllers
     "boxes": ["--scene", "boxes", "--n", "1", "--steps", "4", "--vz", "0.5"],
+    # C4 at small size: tet cube under a chain of 4 hinged boxes (rb_constraint points + directions, rb_d contact)
+    "tetchain_n3": ["--scene", "tetchain", "--n", "3", "--ny", "4", "--steps", "14"],
     # the five attachment potentials
     "attach_n6": ["--scene", "attach", "--n", "6", "--steps", "3"],
 }

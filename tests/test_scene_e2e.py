@@ -64,3 +64,21 @@ def test_tetdrop_runs_many_steps_without_penetration():
     x = sc.positions()
     assert x[:, 2].min() > -5e-3      # resting on the (softly constrained, 1e6 N/m) floor whose top face starts at z = 0
     assert all(s["result"] in (0, 6, 8) for s in log)
+
+
+@pytest.mark.gpu
+def test_tetchain_coupled_trajectory():
+    """C4 at small size: foam block under a chain of hinged rigid boxes (joints + rigid-deformable contact), through the host
+    layer, against the reference's trajectory: same accepted steps / retries up to the dump, same first residual of the next
+    step, iteration count +-1."""
+    g = Golden("tetchain_n3")
+    steps_before = g.meta["steps_before_dump"]
+    sc, log = run("tetchain", steps_before + 1, n=3, ny=4)
+    assert int(log[0]["ndofs"]) == g.meta["ndofs"]
+    t_ref = g.meta["time"]
+    t_mine = log[steps_before - 1]["time"]
+    assert abs(t_mine - t_ref) < 1e-12, (t_mine, t_ref)
+    ref_res = g["next_step_residuals"]
+    res = log[steps_before]["residuals"]
+    assert abs(res[0] - ref_res[0]) <= 1e-3 * ref_res[0], (res, ref_res)
+    assert abs(int(log[steps_before]["newton_iterations"]) - g.meta["next_step_stats"]["newton_iterations"]) <= 1
