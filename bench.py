@@ -40,7 +40,8 @@ def workload_config(n_gpus):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe): the sampler runs from
+    before the warm-up, every sample is stamped on arrival and only those inside [t_begin, t_end] are summarised."""
 
     def __init__(self, index):
         self.index, self.samples, self.proc = index, [], None
@@ -48,7 +49,7 @@ class ClockSampler:
     def start(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -56,15 +57,19 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append([x.strip() for x in line.split(",")])
+            self.samples.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
         if self.proc:
             self.proc.terminate()
-        sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
-        mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
+        inside = [s for t, s in self.samples if t_begin is None or (t_begin <= t <= t_end)]
+        if not inside and self.samples:   # very short region: the sample closest to it
+            mid = 0.5 * ((t_begin or 0.0) + (t_end or 0.0))
+            inside = [min(self.samples, key=lambda ts: abs(ts[0] - mid))[1]]
+        sm = sorted(int(s[0]) for s in inside if s and s[0].isdigit())
+        mx = [int(s[1]) for s in inside if len(s) > 1 and s[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for s in self.samples if len(s) >= 6 for i in range(4) if s[2 + i].lower().startswith("active")})
+        reasons = sorted({names[i] for s in inside if len(s) >= 6 for i in range(4) if s[2 + i].lower().startswith("active")})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
@@ -105,16 +110,18 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        ref_steps = max(3, min(args.steps, 20))
-        r = run_reference(ref_steps, max(1, min(args.warmup, 2)), args.grid)
+        # the same window of time steps as the stark_b200 arm (same warm-up rule), bounded so that the run ends within minutes
+        ref_steps = max(1, min(args.steps, 200))
+        ref_warmup = max(args.warmup, 3)
+        r = run_reference(ref_steps, ref_warmup, args.grid)
         if r is None:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_driver has not been built (oracle/Makefile.ref)"}))
             return 0
         v = r["newton_it_per_s"]
-        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": ref_steps, "warmup": max(1, min(args.warmup, 2)),
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": ref_steps, "warmup": ref_warmup,
                 "ms_per_step": 1e3 * r["wall_s"] / max(1, r["steps"]), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic", "config": workload_config(1),
-                "cpu_baseline": {"value": v, "unit": UNIT, "cores": r["threads"], "kind": "reference", "sample": f"{ref_steps} time steps of the same scene after {max(1, min(args.warmup, 2))} warm-up steps"},
+                "data": "synthetic", "config": workload_config(1), "newton_iterations": r["newton_iterations"],
+                "cpu_baseline": {"value": v, "unit": UNIT, "cores": r["threads"], "kind": "reference", "sample": f"{ref_steps} time steps of the same scene after {ref_warmup} warm-up steps (unmodified reference, all host threads)"},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
@@ -122,6 +129,7 @@ def main():
     import torch
     import torch.distributed as dist
     from stark_b200 import capi, scenes
+    from stark_b200 import dist as sbdist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the stark_b200 hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -131,16 +139,14 @@ def main():
     sc = scenes.Scene("tetdrop", n=args.grid, dt=0.01, drop=0.003, device=local_rank, stream=stream.cuda_stream)
 
     def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        sbdist.barrier(torch.device("cuda", local_rank))
 
-    for _ in range(max(args.warmup, 3)):
-        sc.step()
-    t0 = sc.totals()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        sc.step()
+    t0 = sc.totals()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
@@ -155,19 +161,15 @@ def main():
     barrier()
     e2e_ms = ev0.elapsed_time(ev1)
     wall_s = time.perf_counter() - wall0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(wall0, wall0 + wall_s) if rank == 0 else None
     t1 = sc.totals()
 
     # max over ranks of the timed regions, sum over ranks of the work
-    vals = torch.tensor([e2e_ms, solve_gpu_ms, float(its), float(evals), float(cg)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        mx = vals.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = vals.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        e2e_ms, solve_gpu_ms = mx[0].item(), mx[1].item()
-        its_all, evals_all, cg_all = sm[2].item(), sm[3].item(), sm[4].item()
-    else:
-        its_all, evals_all, cg_all = float(its), float(evals), float(cg)
+    (e2e_ms, solve_gpu_ms), (its_all, evals_all, cg_all) = sbdist.aggregate([e2e_ms, solve_gpu_ms], [float(its), float(evals), float(cg)], device="cuda")
     if rank != 0:
+        if world > 1:
+            dist.barrier()   # rank 0 finishes its single-GPU diagnostics before the group is torn down
+            dist.destroy_process_group()
         return 0
 
     # ---- roofline of the dominant kernel: EnergyTetStrain P+grad+Hessian element evaluation, timed alone (CUDA events) ----
@@ -215,10 +217,11 @@ def main():
     cpu = None
     if not args.no_cpu_baseline and args.gpus == 1:
         try:
-            r = run_reference(6, 1, args.grid)
+            n_cpu = max(1, min(args.steps, 12))
+            r = run_reference(n_cpu, max(args.warmup, 3), args.grid)
             if r is not None:
                 cpu = {"value": r["newton_it_per_s"], "unit": UNIT, "cores": r["threads"], "kind": "reference",
-                       "sample": "6 time steps of the same scene after 1 warm-up step (unmodified reference, all host threads)",
+                       "sample": f"{n_cpu} time steps of the same scene after {max(args.warmup, 3)} warm-up steps (unmodified reference, all host threads)",
                        "newton_iterations": r["newton_iterations"], "wall_s": r["wall_s"]}
         except Exception as e:
             cpu = {"error": repr(e)}
@@ -236,6 +239,9 @@ def main():
         "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "stages": stages,
     }
     print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     return 0
 
 
