@@ -69,149 +69,154 @@ __global__ void k_select(const ProjTable* __restrict__ Tp, const int32_t* __rest
     }
 }
 
-// One 128-thread CTA per selected element.
-//  1. cheap exit: lambda_min(A) > eps  <=>  A - eps I has an LDL^T factorisation with positive pivots (n steps);
-//  2. otherwise a PARALLEL-ORDER two-sided Jacobi eigen-solve: the n/2 disjoint rotations of one round-robin step are
-//     computed from the same matrix and applied together (columns of A and V, then rows of A), n-1 steps per sweep --
-//     the dependent chain of a sweep is n-1 steps instead of the n(n-1)/2 rotations of the cyclic order;
+// One WARP per selected element (everything between the lanes of a warp is __syncwarp / shuffles), eight elements per CTA,
+// one kernel instance per element size N (compile-time loop bounds and index arithmetic):
+//  1. cheap exit: lambda_min(A) > eps  <=>  A - eps I has an LDL^T factorisation with positive pivots (N steps);
+//  2. otherwise a PARALLEL-ORDER two-sided Jacobi eigen-solve: the N/2 disjoint rotations of one round-robin step are
+//     computed from the same matrix and applied together (columns of A and V, then rows of A), N-1 steps per sweep --
+//     the dependent chain of a sweep is N-1 steps instead of the N(N-1)/2 rotations of the cyclic order;
 //  3. clamp / mirror the eigenvalues below eps and rebuild H = V diag(l) V^T.
-constexpr int PROJ_THREADS = 128;
+// Contact-heavy steps project thousands of 12 x 12 tet Hessians per call; the kernel is instruction-bound, so the per-size
+// instances (no runtime divisions) and 2.4 KB of shared memory per 12 x 12 element (64 warps resident per SM) matter.
+constexpr int PROJ_WARPS = 8;
+constexpr int PROJ_THREADS = 32 * PROJ_WARPS;
+template<int N> constexpr size_t proj_smem_per_warp() { return sizeof(double) * (2 * N * N + 2 * ((N + 1) / 2)) + sizeof(int) * 2 * ((N + 1) / 2 + 1); }
+
+template<int N>
 __global__ void __launch_bounds__(PROJ_THREADS) k_project(const ProjTable* __restrict__ Tp, double* __restrict__ H_all, const uint32_t* __restrict__ list,
                                                            const int* __restrict__ n_list, double eps, int mirror, int* __restrict__ n_changed,
                                                            const DirtyView dv)
 {
-    __shared__ double A[PROJ_MAX_N * PROJ_MAX_N];
-    __shared__ double V[PROJ_MAX_N * PROJ_MAX_N];
-    __shared__ double s_c[PROJ_MAX_N / 2], s_s[PROJ_MAX_N / 2];
-    __shared__ int s_p[PROJ_MAX_N / 2], s_q[PROJ_MAX_N / 2];
-    __shared__ double s_red[2][PROJ_THREADS / 32];
-    __shared__ int s_flag;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NE = (N + 1) & ~1;   // even number of players (a dummy index N when N is odd)
+    constexpr int NP = NE / 2;         // pairs per step
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* base = smem_raw + (size_t)warp * ((proj_smem_per_warp<N>() + 15) & ~(size_t)15);
+    double* A = reinterpret_cast<double*>(base);
+    double* V = A + N * N;
+    double* cs_c = V + N * N;
+    double* cs_s = cs_c + NP;
+    int* pp = reinterpret_cast<int*>(cs_s + NP);
+    int* pq = pp + NP + 1;
     const ProjTable& T = *Tp;
     const int total = *n_list;
-    for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    for (int item = blockIdx.x * PROJ_WARPS + warp; item < total; item += gridDim.x * PROJ_WARPS) {
         const unsigned long long e = list[item];
         const int pi = find_pot(T, e);
-        const int n = 3 * T.nb[pi];
-        double* H = H_all + T.H_off[pi] + (e - T.E_off[pi]) * (unsigned long long)(n * n);
-        __syncthreads();   // previous item fully done
+        if (3 * T.nb[pi] != N) continue;   // another size class: handled by its own kernel instance
+        double* H = H_all + T.H_off[pi] + (e - T.E_off[pi]) * (unsigned long long)(N * N);
+        __syncwarp();   // previous item fully done
         // load (symmetrised); V = A - eps I for the factorisation test
-        for (int k = tid; k < n * n; k += PROJ_THREADS) {
-            const int i = k / n, j = k - i * n;
-            const double a = 0.5 * (H[i * n + j] + H[j * n + i]);
+        for (int k = lane; k < N * N; k += 32) {
+            const int i = k / N, j = k - i * N;
+            const double a = 0.5 * (H[i * N + j] + H[j * N + i]);
             A[k] = a;
             V[k] = a - ((i == j) ? eps : 0.0);
         }
-        __syncthreads();
+        __syncwarp();
         bool pd = true;
-        for (int j = 0; j < n; j++) {
-            const double d = V[j * n + j];
-            if (!(d > 0.0)) { pd = false; break; }   // shared value: uniform across the CTA
+        for (int j = 0; j < N; j++) {
+            const double d = V[j * N + j];
+            if (!(d > 0.0)) { pd = false; break; }   // shared value: uniform across the warp
             const double inv = 1.0 / d;
-            const int m = n - 1 - j;                  // trailing block: rows / cols j+1 .. n-1 (lower triangle incl. diagonal)
-            for (int t = tid; t < m * m; t += PROJ_THREADS) {
+            const int m = N - 1 - j;                  // trailing block: rows / cols j+1 .. N-1 (lower triangle incl. diagonal)
+            for (int t = lane; t < m * m; t += 32) {
                 const int i = j + 1 + t / m, k2 = j + 1 + t % m;
-                if (k2 <= i) V[i * n + k2] -= V[i * n + j] * V[k2 * n + j] * inv;
+                if (k2 <= i) V[i * N + k2] -= V[i * N + j] * V[k2 * N + j] * inv;
             }
-            __syncthreads();
+            __syncwarp();
         }
         if (pd) continue;
-        __syncthreads();
-        for (int k = tid; k < n * n; k += PROJ_THREADS) {
-            const int i = k / n, j = k - i * n;
+        __syncwarp();
+        for (int k = lane; k < N * N; k += 32) {
+            const int i = k / N, j = k - i * N;
             V[k] = (i == j) ? 1.0 : 0.0;
         }
-        const int ne = (n + 1) & ~1;       // even number of players (a dummy index n when n is odd)
-        const int np = ne / 2;             // pairs per step
-        __syncthreads();
+        __syncwarp();
+        int sweeps_done = 0;
         for (int sweep = 0; sweep < 30; sweep++) {
+            sweeps_done = sweep;
             // convergence: off-diagonal mass vs total
             double off = 0.0, diag = 0.0;
-            for (int k = tid; k < n * n; k += PROJ_THREADS) {
-                const int i = k / n, j = k - i * n;
+            for (int k = lane; k < N * N; k += 32) {
+                const int i = k / N, j = k - i * N;
                 const double v = A[k] * A[k];
                 if (i == j) diag += v; else off += v;
             }
             for (int o = 16; o > 0; o >>= 1) { off += __shfl_xor_sync(0xffffffffu, off, o); diag += __shfl_xor_sync(0xffffffffu, diag, o); }
-            if (lane == 0) { s_red[0][warp] = off; s_red[1][warp] = diag; }
-            __syncthreads();
-            off = 0.0; diag = 0.0;
-            for (int w = 0; w < PROJ_THREADS / 32; w++) { off += s_red[0][w]; diag += s_red[1][w]; }
-            __syncthreads();
             if (off <= 1e-25 * (diag + off) || off == 0.0) break;   // |off| / |A| <= 3e-13: eigenvalue error ~ |off|^2 / gap, far below 1e-10 parity
-            for (int step = 0; step < ne - 1; step++) {
-                // round-robin pairing: player ne-1 is fixed, the others rotate
-                if (tid < np) {
+            for (int step = 0; step < NE - 1; step++) {
+                // round-robin pairing: player NE-1 is fixed, the others rotate
+                if (lane < NP) {
                     int p, q;
-                    if (tid == 0) { p = ne - 1; q = step; }
-                    else { p = (step + tid) % (ne - 1); q = (step - tid + (ne - 1)) % (ne - 1); }
+                    if (lane == 0) { p = NE - 1; q = step; }
+                    else { p = (step + lane) % (NE - 1); q = (step - lane + (NE - 1)) % (NE - 1); }
                     if (p > q) { const int t = p; p = q; q = t; }
                     double c = 1.0, sn = 0.0;
-                    if (q < n) {   // (a pair with the dummy index does nothing)
-                        const double apq = A[p * n + q];
+                    if (q < N) {   // (a pair with the dummy index does nothing)
+                        const double apq = A[p * N + q];
                         if (apq != 0.0) {
-                            const double app = A[p * n + p], aqq = A[q * n + q];
+                            const double app = A[p * N + p], aqq = A[q * N + q];
                             const double tau = (aqq - app) / (2.0 * apq);
                             const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-                            c = 1.0 / sqrt(1.0 + t * t);
+                            c = rsqrt(1.0 + t * t);
                             sn = t * c;
                         }
                     }
-                    s_p[tid] = p; s_q[tid] = (q < n) ? q : -1; s_c[tid] = c; s_s[tid] = sn;
+                    pp[lane] = p; pq[lane] = (q < N) ? q : -1; cs_c[lane] = c; cs_s[lane] = sn;
                 }
-                __syncthreads();
+                __syncwarp();
                 // columns p, q of A and V (all rows)
-                for (int t = tid; t < np * n; t += PROJ_THREADS) {
-                    const int pr = t / n, k = t - pr * n;
-                    const int p = s_p[pr], q = s_q[pr];
+                for (int t = lane; t < NP * N; t += 32) {
+                    const int pr = t / N, k = t - pr * N;
+                    const int p = pp[pr], q = pq[pr];
                     if (q < 0) continue;
-                    const double c = s_c[pr], sn = s_s[pr];
-                    const double akp = A[k * n + p], akq = A[k * n + q];
-                    A[k * n + p] = c * akp - sn * akq;
-                    A[k * n + q] = sn * akp + c * akq;
-                    const double vkp = V[k * n + p], vkq = V[k * n + q];
-                    V[k * n + p] = c * vkp - sn * vkq;
-                    V[k * n + q] = sn * vkp + c * vkq;
+                    const double c = cs_c[pr], sn = cs_s[pr];
+                    const double akp = A[k * N + p], akq = A[k * N + q];
+                    A[k * N + p] = c * akp - sn * akq;
+                    A[k * N + q] = sn * akp + c * akq;
+                    const double vkp = V[k * N + p], vkq = V[k * N + q];
+                    V[k * N + p] = c * vkp - sn * vkq;
+                    V[k * N + q] = sn * vkp + c * vkq;
                 }
-                __syncthreads();
+                __syncwarp();
                 // rows p, q of A (all columns)
-                for (int t = tid; t < np * n; t += PROJ_THREADS) {
-                    const int pr = t / n, k = t - pr * n;
-                    const int p = s_p[pr], q = s_q[pr];
+                for (int t = lane; t < NP * N; t += 32) {
+                    const int pr = t / N, k = t - pr * N;
+                    const int p = pp[pr], q = pq[pr];
                     if (q < 0) continue;
-                    const double c = s_c[pr], sn = s_s[pr];
-                    const double apk = A[p * n + k], aqk = A[q * n + k];
-                    A[p * n + k] = c * apk - sn * aqk;
-                    A[q * n + k] = sn * apk + c * aqk;
+                    const double c = cs_c[pr], sn = cs_s[pr];
+                    const double apk = A[p * N + k], aqk = A[q * N + k];
+                    A[p * N + k] = c * apk - sn * aqk;
+                    A[q * N + k] = sn * apk + c * aqk;
                 }
-                __syncthreads();
+                __syncwarp();
             }
         }
-        __syncthreads();
+        __syncwarp();
+        if (lane == 0) atomicAdd(n_changed + 2, sweeps_done);   // diagnostic: total Jacobi sweeps (d_counts[3])
         // clamp / mirror
-        if (tid == 0) {
-            int changed = 0;
-            for (int i = 0; i < n; i++) if (A[i * n + i] < eps) changed = 1;
-            s_flag = changed;
-        }
-        __syncthreads();
-        if (s_flag) {
-            if (tid < n) {
-                const double l = A[tid * n + tid];
-                A[tid * n + tid] = (l < eps) ? (mirror ? -l : eps) : l;
+        bool changed = false;
+        for (int i = 0; i < N; i++) if (A[i * N + i] < eps) changed = true;   // shared values: uniform across the warp
+        if (changed) {
+            __syncwarp();
+            if (lane < N) {
+                const double l = A[lane * N + lane];
+                A[lane * N + lane] = (l < eps) ? (mirror ? -l : eps) : l;
             }
-            __syncthreads();
-            for (int k = tid; k < n * n; k += PROJ_THREADS) {
-                const int i = k / n, j = k - i * n;
+            __syncwarp();
+            for (int k = lane; k < N * N; k += 32) {
+                const int i = k / N, j = k - i * N;
                 double acc = 0.0;
-                for (int m = 0; m < n; m++) acc += V[i * n + m] * A[m * n + m] * V[j * n + m];
+#pragma unroll
+                for (int m = 0; m < N; m++) acc += V[i * N + m] * A[m * N + m] * V[j * N + m];
                 H[k] = acc;
             }
-            if (tid == 0) atomicAdd(n_changed, 1);
+            if (lane == 0) atomicAdd(n_changed, 1);
             if (dv.dirty) {   // the BCSR blocks this element contributes to must be re-summed
-                const int nb = T.nb[pi];
+                constexpr int nb = N / 3;
                 const unsigned long long src0 = T.blk_off[pi] + (e - T.E_off[pi]) * (unsigned long long)(nb * nb);
-                for (int k = tid; k < nb * nb; k += PROJ_THREADS) {
+                for (int k = lane; k < nb * nb; k += 32) {
                     const unsigned long long src = src0 + k;
                     const uint32_t f = (src < dv.n_static) ? dv.s_final[dv.s_blk_of_src[src]] : dv.d_final[dv.d_blk_of_src[src - dv.n_static]];
                     dv.dirty[f] = 1;
@@ -219,6 +224,22 @@ __global__ void __launch_bounds__(PROJ_THREADS) k_project(const ProjTable* __res
             }
         }
     }
+}
+
+template<int N> static cudaError_t launch_project(int grid, cudaStream_t st, const ProjTable* Tp, double* H, const uint32_t* list, const int* n_list,
+                                                  double eps, int mirror, int* n_changed, const DirtyView& dv)
+{
+    const size_t smem = PROJ_WARPS * ((proj_smem_per_warp<N>() + 15) & ~(size_t)15);
+    static bool configured = false;
+    if (!configured) {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(k_project<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        configured = true;
+    }
+    k_project<N><<<grid, PROJ_THREADS, smem, st>>>(Tp, H, list, n_list, eps, mirror, n_changed, dv);
+    return cudaGetLastError();
 }
 
 struct Projector {
@@ -284,16 +305,33 @@ int project_internal(sb_context* ctx, double grad_threshold, double eps, int mir
         ctx->launches++;
     }
     k_select<<<(unsigned)((n_elem + 255) / 256), 256, 0, st>>>(P.d_table, ctx->rows.p, P.active.p, use_active, ctx->projected.p, P.list.p, P.d_counts, n_elem);
-    const int grid = (int)std::min<size_t>(n_elem, 148 * 8);
+    const int grid = (int)std::min<size_t>((n_elem + PROJ_WARPS - 1) / PROJ_WARPS, 148 * 8);
     DirtyView dv;
     if (!assembly_dirty_view(ctx, &dv)) dv.dirty = nullptr;
-    k_project<<<grid, PROJ_THREADS, 0, st>>>(P.d_table, ctx->H.p, P.list.p, P.d_counts, eps, mirror, P.d_counts + 1, dv);
-    ctx->launches += 2;
+    bool sizes[PROJ_MAX_N / 3 + 1] = {false};
+    for (auto& p : ctx->potentials) if (p.n_elem > 0) sizes[p.k->nb] = true;
+    for (int nb = 1; nb <= PROJ_MAX_N / 3; nb++) {
+        if (!sizes[nb]) continue;
+        cudaError_t e = cudaSuccess;
+        switch (nb) {
+        case 1: e = launch_project<3>(grid, st, P.d_table, ctx->H.p, P.list.p, P.d_counts, eps, mirror, P.d_counts + 1, dv); break;
+        case 2: e = launch_project<6>(grid, st, P.d_table, ctx->H.p, P.list.p, P.d_counts, eps, mirror, P.d_counts + 1, dv); break;
+        case 3: e = launch_project<9>(grid, st, P.d_table, ctx->H.p, P.list.p, P.d_counts, eps, mirror, P.d_counts + 1, dv); break;
+        case 4: e = launch_project<12>(grid, st, P.d_table, ctx->H.p, P.list.p, P.d_counts, eps, mirror, P.d_counts + 1, dv); break;
+        case 5: e = launch_project<15>(grid, st, P.d_table, ctx->H.p, P.list.p, P.d_counts, eps, mirror, P.d_counts + 1, dv); break;
+        case 6: e = launch_project<18>(grid, st, P.d_table, ctx->H.p, P.list.p, P.d_counts, eps, mirror, P.d_counts + 1, dv); break;
+        case 7: e = launch_project<21>(grid, st, P.d_table, ctx->H.p, P.list.p, P.d_counts, eps, mirror, P.d_counts + 1, dv); break;
+        case 8: e = launch_project<24>(grid, st, P.d_table, ctx->H.p, P.list.p, P.d_counts, eps, mirror, P.d_counts + 1, dv); break;
+        }
+        SB_CUDA(ctx, e);
+        ctx->launches++;
+    }
+    ctx->launches += 1;
     SB_CUDA(ctx, cudaMemcpyAsync(P.h_counts, P.d_counts, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
     SB_CUDA(ctx, cudaStreamSynchronize(st));   // also protects the stack-resident table T
     SB_CUDA(ctx, cudaGetLastError());
     ctx->n_projected += P.h_counts[0];
-    if (ctx->profile) { ctx->stage_calls[ST_PROJ_SELECTED] += P.h_counts[0]; ctx->stage_calls[ST_PROJ_CHANGED] += P.h_counts[1]; }
+    if (ctx->profile) { ctx->stage_calls[ST_PROJ_SELECTED] += P.h_counts[0]; ctx->stage_calls[ST_PROJ_CHANGED] += P.h_counts[1]; ctx->stage_calls[ST_PROJ_SWEEPS] += P.h_counts[3]; }
     if (out_n_projected) *out_n_projected = ctx->n_projected;
     if (out_all_projected) *out_all_projected = use_active ? (P.h_counts[2] == 0) : 1;
     return 0;
