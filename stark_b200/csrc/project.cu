@@ -24,6 +24,7 @@ struct ProjTable {
     unsigned long long rows_off[PROJ_MAX_POTS];
     unsigned long long blk_off[PROJ_MAX_POTS];     // first source (element block) of each potential in assembly numbering
     int nb[PROJ_MAX_POTS];
+    int invariant[PROJ_MAX_POTS];                  // energy invariant under a common translation of all its nodes
 };
 
 __device__ __forceinline__ int find_pot(const ProjTable& T, unsigned long long e)
@@ -71,33 +72,165 @@ __global__ void k_select(const ProjTable* __restrict__ Tp, const int32_t* __rest
 
 // One WARP per selected element (everything between the lanes of a warp is __syncwarp / shuffles), eight elements per CTA,
 // one kernel instance per element size N (compile-time loop bounds and index arithmetic):
-//  1. cheap exit: lambda_min(A) > eps  <=>  A - eps I has an LDL^T factorisation with positive pivots (N steps);
-//  2. otherwise a PARALLEL-ORDER two-sided Jacobi eigen-solve: the N/2 disjoint rotations of one round-robin step are
-//     computed from the same matrix and applied together (columns of A and V, then rows of A), N-1 steps per sweep --
-//     the dependent chain of a sweep is N-1 steps instead of the N(N-1)/2 rotations of the cyclic order;
-//  3. clamp / mirror the eigenvalues below eps and rebuild H = V diag(l) V^T.
-// Contact-heavy steps project thousands of 12 x 12 tet Hessians per call; the kernel is instruction-bound, so the per-size
-// instances (no runtime divisions) and 2.4 KB of shared memory per 12 x 12 element (64 warps resident per SM) matter.
+//  0. TRANSLATION-INVARIANT potentials (strain, bending, deformable-deformable contact / friction / attachments: the energy
+//     depends on differences of the nodal DoFs only) have three exact null vectors (the rigid translations), so A - eps I is
+//     never positive definite and the cheap exit below could never fire.  Their Hessian is first compressed to the
+//     3 (nn - 1)-dimensional complement, M = Q^T H Q with Q = W (x) I3 and W the fixed Helmert basis of the nn nodes
+//     (orthonormal, orthogonal to (1..1)); eig(H) = eig(M) + three zeros, so H_proj = Q M_proj Q^T + eps (I - Q Q^T) is the
+//     same matrix the reference's 12 x 12 eigen-solve produces (its three null eigenvalues, +-1e-17 |H|, are clamped to
+//     eps = 1e-10 as well), up to rounding.  A tet becomes a 9 x 9 problem and, when the tet is not inverted / buckled,
+//     exits after the factorisation;
+//  1. cheap exit: lambda_min(A) > eps  <=>  A - eps I has an LDL^T factorisation with positive pivots (R steps);
+//  2. otherwise a PARALLEL-ORDER two-sided Jacobi eigen-solve: the R/2 disjoint rotations of one round-robin step are
+//     computed from the same matrix and applied together (columns of A and V, then rows of A), R-1 steps per sweep --
+//     the dependent chain of a sweep is R-1 steps instead of the R(R-1)/2 rotations of the cyclic order;
+//  3. clamp / mirror the eigenvalues below eps and rebuild V diag(l) V^T.
 constexpr int PROJ_WARPS = 8;
 constexpr int PROJ_THREADS = 32 * PROJ_WARPS;
-template<int N> constexpr size_t proj_smem_per_warp() { return sizeof(double) * (2 * N * N + 2 * ((N + 1) / 2)) + sizeof(int) * 2 * ((N + 1) / 2 + 1); }
+template<int N> constexpr size_t proj_smem_per_warp() { return sizeof(double) * (2 * N * N + N + 2 * ((N + 1) / 2)) + sizeof(int) * 2 * ((N + 1) / 2 + 1); }
+
+struct ProjScratch {
+    double* A; double* V; double* lam; double* cs_c; double* cs_s; int* pp; int* pq;
+};
+
+// PD test + eigen-projection of the symmetric R x R matrix in S.A (row-major, pitch R).  Returns true when eigenvalues were
+// clamped; S.A then holds the projected matrix.  Returns false when the matrix is left as it is.
+template<int R>
+__device__ bool project_small(const ProjScratch& S, double eps, int mirror, int lane, int& sweeps_done)
+{
+    constexpr int NE = (R + 1) & ~1;   // even number of players (a dummy index R when R is odd)
+    constexpr int NP = NE / 2;         // pairs per step
+    double* A = S.A; double* V = S.V;
+    for (int k = lane; k < R * R; k += 32) {
+        const int i = k / R, j = k - i * R;
+        V[k] = A[k] - ((i == j) ? eps : 0.0);
+    }
+    __syncwarp();
+    bool pd = true;
+    for (int j = 0; j < R; j++) {
+        const double d = V[j * R + j];
+        if (!(d > 0.0)) { pd = false; break; }   // shared value: uniform across the warp
+        const double inv = 1.0 / d;
+        const int m = R - 1 - j;                  // trailing block: rows / cols j+1 .. R-1 (lower triangle incl. diagonal)
+        for (int t = lane; t < m * m; t += 32) {
+            const int i = j + 1 + t / m, k2 = j + 1 + t % m;
+            if (k2 <= i) V[i * R + k2] -= V[i * R + j] * V[k2 * R + j] * inv;
+        }
+        __syncwarp();
+    }
+    if (pd) return false;
+    __syncwarp();
+    for (int k = lane; k < R * R; k += 32) {
+        const int i = k / R, j = k - i * R;
+        V[k] = (i == j) ? 1.0 : 0.0;
+    }
+    __syncwarp();
+    for (int sweep = 0; sweep < 30; sweep++) {
+        sweeps_done = sweep;
+        // convergence: off-diagonal mass vs total
+        double off = 0.0, diag = 0.0;
+        for (int k = lane; k < R * R; k += 32) {
+            const int i = k / R, j = k - i * R;
+            const double v = A[k] * A[k];
+            if (i == j) diag += v; else off += v;
+        }
+        for (int o = 16; o > 0; o >>= 1) { off += __shfl_xor_sync(0xffffffffu, off, o); diag += __shfl_xor_sync(0xffffffffu, diag, o); }
+        if (off <= 1e-25 * (diag + off) || off == 0.0) break;   // |off| / |A| <= 3e-13: eigenvalue error ~ |off|^2 / gap, far below 1e-10 parity
+        for (int step = 0; step < NE - 1; step++) {
+            // round-robin pairing: player NE-1 is fixed, the others rotate
+            if (lane < NP) {
+                int p, q;
+                if (lane == 0) { p = NE - 1; q = step; }
+                else { p = (step + lane) % (NE - 1); q = (step - lane + (NE - 1)) % (NE - 1); }
+                if (p > q) { const int t = p; p = q; q = t; }
+                double c = 1.0, sn = 0.0;
+                if (q < R) {   // (a pair with the dummy index does nothing)
+                    const double apq = A[p * R + q];
+                    if (apq != 0.0) {
+                        const double app = A[p * R + p], aqq = A[q * R + q];
+                        const double tau = (aqq - app) / (2.0 * apq);
+                        const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                        c = rsqrt(1.0 + t * t);
+                        sn = t * c;
+                    }
+                }
+                S.pp[lane] = p; S.pq[lane] = (q < R) ? q : -1; S.cs_c[lane] = c; S.cs_s[lane] = sn;
+            }
+            __syncwarp();
+            // columns p, q of A and V (all rows)
+            for (int t = lane; t < NP * R; t += 32) {
+                const int pr = t / R, k = t - pr * R;
+                const int p = S.pp[pr], q = S.pq[pr];
+                if (q < 0) continue;
+                const double c = S.cs_c[pr], sn = S.cs_s[pr];
+                const double akp = A[k * R + p], akq = A[k * R + q];
+                A[k * R + p] = c * akp - sn * akq;
+                A[k * R + q] = sn * akp + c * akq;
+                const double vkp = V[k * R + p], vkq = V[k * R + q];
+                V[k * R + p] = c * vkp - sn * vkq;
+                V[k * R + q] = sn * vkp + c * vkq;
+            }
+            __syncwarp();
+            // rows p, q of A (all columns)
+            for (int t = lane; t < NP * R; t += 32) {
+                const int pr = t / R, k = t - pr * R;
+                const int p = S.pp[pr], q = S.pq[pr];
+                if (q < 0) continue;
+                const double c = S.cs_c[pr], sn = S.cs_s[pr];
+                const double apk = A[p * R + k], aqk = A[q * R + k];
+                A[p * R + k] = c * apk - sn * aqk;
+                A[q * R + k] = sn * apk + c * aqk;
+            }
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+    // clamp / mirror
+    bool changed = false;
+    for (int i = 0; i < R; i++) if (A[i * R + i] < eps) changed = true;   // shared values: uniform across the warp
+    if (!changed) return false;
+    if (lane < R) {
+        const double l = A[lane * R + lane];
+        S.lam[lane] = (l < eps) ? (mirror ? -l : eps) : l;
+    }
+    __syncwarp();
+    for (int k = lane; k < R * R; k += 32) {
+        const int i = k / R, j = k - i * R;
+        double acc = 0.0;
+#pragma unroll
+        for (int m = 0; m < R; m++) acc += V[i * R + m] * S.lam[m] * V[j * R + m];
+        A[k] = acc;   // (reads V and lam only)
+    }
+    __syncwarp();
+    return true;
+}
+
+// Helmert basis of nn nodes: column j (0 <= j < nn-1) = (1, .., 1, -(j+1), 0, ..) / sqrt((j+1)(j+2)) with j+1 leading ones
+__device__ __forceinline__ double helmert(int a, int j)
+{
+    const double s = rsqrt((double)((j + 1) * (j + 2)));
+    return (a <= j) ? s : ((a == j + 1) ? -(double)(j + 1) * s : 0.0);
+}
 
 template<int N>
 __global__ void __launch_bounds__(PROJ_THREADS) k_project(const ProjTable* __restrict__ Tp, double* __restrict__ H_all, const uint32_t* __restrict__ list,
                                                            const int* __restrict__ n_list, double eps, int mirror, int* __restrict__ n_changed,
                                                            const DirtyView dv)
 {
-    constexpr int NE = (N + 1) & ~1;   // even number of players (a dummy index N when N is odd)
-    constexpr int NP = NE / 2;         // pairs per step
+    constexpr int NN = N / 3;                       // nodes
+    constexpr int R = (N > 3) ? N - 3 : N;          // size after removing the translations
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* base = smem_raw + (size_t)warp * ((proj_smem_per_warp<N>() + 15) & ~(size_t)15);
-    double* A = reinterpret_cast<double*>(base);
-    double* V = A + N * N;
-    double* cs_c = V + N * N;
-    double* cs_s = cs_c + NP;
-    int* pp = reinterpret_cast<int*>(cs_s + NP);
-    int* pq = pp + NP + 1;
+    ProjScratch S;
+    S.A = reinterpret_cast<double*>(base);
+    S.V = S.A + N * N;
+    S.lam = S.V + N * N;
+    S.cs_c = S.lam + N;
+    S.cs_s = S.cs_c + (N + 1) / 2;
+    S.pp = reinterpret_cast<int*>(S.cs_s + (N + 1) / 2);
+    S.pq = S.pp + (N + 1) / 2 + 1;
+    double* A = S.A; double* V = S.V;
     const ProjTable& T = *Tp;
     const int total = *n_list;
     for (int item = blockIdx.x * PROJ_WARPS + warp; item < total; item += gridDim.x * PROJ_WARPS) {
@@ -105,113 +238,64 @@ __global__ void __launch_bounds__(PROJ_THREADS) k_project(const ProjTable* __res
         const int pi = find_pot(T, e);
         if (3 * T.nb[pi] != N) continue;   // another size class: handled by its own kernel instance
         double* H = H_all + T.H_off[pi] + (e - T.E_off[pi]) * (unsigned long long)(N * N);
+        const bool invariant = (N > 3) && T.invariant[pi];
         __syncwarp();   // previous item fully done
-        // load (symmetrised); V = A - eps I for the factorisation test
-        for (int k = lane; k < N * N; k += 32) {
+        for (int k = lane; k < N * N; k += 32) {   // load (symmetrised)
             const int i = k / N, j = k - i * N;
-            const double a = 0.5 * (H[i * N + j] + H[j * N + i]);
-            A[k] = a;
-            V[k] = a - ((i == j) ? eps : 0.0);
+            A[k] = 0.5 * (H[i * N + j] + H[j * N + i]);
         }
         __syncwarp();
-        bool pd = true;
-        for (int j = 0; j < N; j++) {
-            const double d = V[j * N + j];
-            if (!(d > 0.0)) { pd = false; break; }   // shared value: uniform across the warp
-            const double inv = 1.0 / d;
-            const int m = N - 1 - j;                  // trailing block: rows / cols j+1 .. N-1 (lower triangle incl. diagonal)
-            for (int t = lane; t < m * m; t += 32) {
-                const int i = j + 1 + t / m, k2 = j + 1 + t % m;
-                if (k2 <= i) V[i * N + k2] -= V[i * N + j] * V[k2 * N + j] * inv;
-            }
-            __syncwarp();
-        }
-        if (pd) continue;
-        __syncwarp();
-        for (int k = lane; k < N * N; k += 32) {
-            const int i = k / N, j = k - i * N;
-            V[k] = (i == j) ? 1.0 : 0.0;
-        }
-        __syncwarp();
-        int sweeps_done = 0;
-        for (int sweep = 0; sweep < 30; sweep++) {
-            sweeps_done = sweep;
-            // convergence: off-diagonal mass vs total
-            double off = 0.0, diag = 0.0;
-            for (int k = lane; k < N * N; k += 32) {
-                const int i = k / N, j = k - i * N;
-                const double v = A[k] * A[k];
-                if (i == j) diag += v; else off += v;
-            }
-            for (int o = 16; o > 0; o >>= 1) { off += __shfl_xor_sync(0xffffffffu, off, o); diag += __shfl_xor_sync(0xffffffffu, diag, o); }
-            if (off <= 1e-25 * (diag + off) || off == 0.0) break;   // |off| / |A| <= 3e-13: eigenvalue error ~ |off|^2 / gap, far below 1e-10 parity
-            for (int step = 0; step < NE - 1; step++) {
-                // round-robin pairing: player NE-1 is fixed, the others rotate
-                if (lane < NP) {
-                    int p, q;
-                    if (lane == 0) { p = NE - 1; q = step; }
-                    else { p = (step + lane) % (NE - 1); q = (step - lane + (NE - 1)) % (NE - 1); }
-                    if (p > q) { const int t = p; p = q; q = t; }
-                    double c = 1.0, sn = 0.0;
-                    if (q < N) {   // (a pair with the dummy index does nothing)
-                        const double apq = A[p * N + q];
-                        if (apq != 0.0) {
-                            const double app = A[p * N + p], aqq = A[q * N + q];
-                            const double tau = (aqq - app) / (2.0 * apq);
-                            const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-                            c = rsqrt(1.0 + t * t);
-                            sn = t * c;
-                        }
-                    }
-                    pp[lane] = p; pq[lane] = (q < N) ? q : -1; cs_c[lane] = c; cs_s[lane] = sn;
-                }
-                __syncwarp();
-                // columns p, q of A and V (all rows)
-                for (int t = lane; t < NP * N; t += 32) {
-                    const int pr = t / N, k = t - pr * N;
-                    const int p = pp[pr], q = pq[pr];
-                    if (q < 0) continue;
-                    const double c = cs_c[pr], sn = cs_s[pr];
-                    const double akp = A[k * N + p], akq = A[k * N + q];
-                    A[k * N + p] = c * akp - sn * akq;
-                    A[k * N + q] = sn * akp + c * akq;
-                    const double vkp = V[k * N + p], vkq = V[k * N + q];
-                    V[k * N + p] = c * vkp - sn * vkq;
-                    V[k * N + q] = sn * vkp + c * vkq;
-                }
-                __syncwarp();
-                // rows p, q of A (all columns)
-                for (int t = lane; t < NP * N; t += 32) {
-                    const int pr = t / N, k = t - pr * N;
-                    const int p = pp[pr], q = pq[pr];
-                    if (q < 0) continue;
-                    const double c = cs_c[pr], sn = cs_s[pr];
-                    const double apk = A[p * N + k], aqk = A[q * N + k];
-                    A[p * N + k] = c * apk - sn * aqk;
-                    A[q * N + k] = sn * apk + c * aqk;
-                }
-                __syncwarp();
-            }
-        }
-        __syncwarp();
-        if (lane == 0) atomicAdd(n_changed + 2, sweeps_done);   // diagnostic: total Jacobi sweeps (d_counts[3])
-        // clamp / mirror
-        bool changed = false;
-        for (int i = 0; i < N; i++) if (A[i * N + i] < eps) changed = true;   // shared values: uniform across the warp
-        if (changed) {
-            __syncwarp();
-            if (lane < N) {
-                const double l = A[lane * N + lane];
-                A[lane * N + lane] = (l < eps) ? (mirror ? -l : eps) : l;
-            }
-            __syncwarp();
-            for (int k = lane; k < N * N; k += 32) {
-                const int i = k / N, j = k - i * N;
+        int sweeps = 0;
+        bool changed;
+        if (invariant) {
+            // T1 = H Q  (N x R):  T1[(a r), (j s)] = sum_b H[(a r), (b s)] W[b][j]
+            for (int k = lane; k < N * R; k += 32) {
+                const int row = k / R, col = k - row * R;
+                const int j = col / 3, sc = col - 3 * j;
                 double acc = 0.0;
 #pragma unroll
-                for (int m = 0; m < N; m++) acc += V[i * N + m] * A[m * N + m] * V[j * N + m];
-                H[k] = acc;
+                for (int b = 0; b < NN; b++) acc += A[row * N + 3 * b + sc] * helmert(b, j);
+                V[k] = acc;
             }
+            __syncwarp();
+            // M = Q^T T1  (R x R):  M[(i r), c] = sum_a W[a][i] T1[(a r), c]
+            for (int k = lane; k < R * R; k += 32) {
+                const int row = k / R, col = k - row * R;
+                const int i = row / 3, rc = row - 3 * i;
+                double acc = 0.0;
+#pragma unroll
+                for (int a = 0; a < NN; a++) acc += helmert(a, i) * V[(3 * a + rc) * R + col];
+                A[k] = acc;
+            }
+            __syncwarp();
+            changed = project_small<R>(S, eps, mirror, lane, sweeps);
+            if (changed) {
+                // T1' = Q M'  (N x R), then H = T1' Q^T + eps (I - Q Q^T);  I - Q Q^T = (1/nn) ones (x) I3
+                for (int k = lane; k < N * R; k += 32) {
+                    const int row = k / R, col = k - row * R;
+                    const int a = row / 3, rc = row - 3 * a;
+                    double acc = 0.0;
+#pragma unroll
+                    for (int i = 0; i < NN - 1; i++) acc += helmert(a, i) * A[(3 * i + rc) * R + col];
+                    V[k] = acc;
+                }
+                __syncwarp();
+                for (int k = lane; k < N * N; k += 32) {
+                    const int row = k / N, col = k - row * N;
+                    const int b = col / 3, sc = col - 3 * b;
+                    double acc = ((row % 3) == sc) ? eps / (double)NN : 0.0;
+#pragma unroll
+                    for (int j = 0; j < NN - 1; j++) acc += V[row * R + 3 * j + sc] * helmert(b, j);
+                    H[k] = acc;
+                }
+            }
+        } else {
+            changed = project_small<N>(S, eps, mirror, lane, sweeps);
+            if (changed)
+                for (int k = lane; k < N * N; k += 32) H[k] = A[k];
+        }
+        if (lane == 0 && sweeps) atomicAdd(n_changed + 2, sweeps);   // diagnostic: total Jacobi sweeps (d_counts[3])
+        if (changed) {
             if (lane == 0) atomicAdd(n_changed, 1);
             if (dv.dirty) {   // the BCSR blocks this element contributes to must be re-summed
                 constexpr int nb = N / 3;
@@ -240,6 +324,15 @@ template<int N> static cudaError_t launch_project(int grid, cudaStream_t st, con
     }
     k_project<N><<<grid, PROJ_THREADS, smem, st>>>(Tp, H, list, n_list, eps, mirror, n_changed, dv);
     return cudaGetLastError();
+}
+
+// potentials whose DoF blocks are all deformable points and whose energy depends on their differences only
+static bool translation_invariant(const std::string& name)
+{
+    static const char* prefixes[] = {"EnergyTetStrain", "EnergyTriangleStrain", "EnergySegmentStrain", "EnergyDiscreteShells", "EnergyBendingFlat",
+                                     "EnergyAttachments_d_d", "contact_d_d", "friction_d_d"};
+    for (const char* p : prefixes) if (name.rfind(p, 0) == 0) return true;
+    return false;
 }
 
 struct Projector {
@@ -290,6 +383,7 @@ int project_internal(sb_context* ctx, double grad_threshold, double eps, int mir
         if (p.k->n_dof > PROJ_MAX_N) return fail(ctx, SB_ERR_STATE, "sb_project_to_pd: element size above 24 DoFs is not supported");
         T.E_off[T.n_pots] = p.E_off; T.H_off[T.n_pots] = p.H_off; T.rows_off[T.n_pots] = p.rows_off; T.nb[T.n_pots] = p.k->nb;
         T.blk_off[T.n_pots] = blk_off;
+        T.invariant[T.n_pots] = translation_invariant(p.name) ? 1 : 0;
         blk_off += (unsigned long long)p.n_elem * p.k->nb * p.k->nb;
         T.n_pots++;
     }
