@@ -30,6 +30,10 @@ METRIC = "newton_iterations_per_second"
 UNIT = "Newton it/s"
 GRID_N = 26            # 26^3 hexahedra x 12 tets = 210,912 tets (BASELINE.json configs[1])
 TET_BYTES = 1632       # algorithmic bytes of one EnergyTetStrain element in PGH mode
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_tet_analytic launch at GRID_N = 26 from the `ncu --set full` capture
+# committed as profiles/r1_ncu_full_tet_assembly.csv (8.70 MB read + 199.07 MB written; gathers hit L2, the tail of the
+# Hessian stream is still in L2 when the kernel ends)
+TET_DRAM_TRAFFIC_NCU = 207.8e6
 
 
 def workload_config(n_gpus):
@@ -190,7 +194,7 @@ def main():
         achieved = TET_BYTES * n_tets / (ms.value * 1e-3) / 1e9
         roof = {"kernel": "EnergyTetStrain element evaluation (P + grad + dense 12x12 Hessian)", "bound": "hbm", "achieved": achieved, "peak": peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)", "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "launch_ms": ms.value, "algorithmic_bytes_per_launch": TET_BYTES * n_tets}
+                "traffic": TET_DRAM_TRAFFIC_NCU if args.grid == GRID_N else None, "traffic_source": "ncu --set full, profiles/r1_ncu_full_tet_assembly.csv", "launch_ms": ms.value, "algorithmic_bytes_per_launch": TET_BYTES * n_tets}
     except Exception as e:   # the line must still print
         roof = {"error": repr(e)}
 
