@@ -21,6 +21,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cstring>
+#include <cub/cub.cuh>
 
 namespace sb {
 
@@ -61,7 +62,8 @@ struct Dev {
     const int32_t* edge;         // [n_e][2]
     const int32_t* e_group;
     float* bb_p; float* bb_t; float* bb_e;   // [n][6] bottom xyz, top xyz
-    float* tb_p; float* tb_t; float* tb_e;   // [n_tiles][6] boxes of TILE consecutive primitives
+    const int32_t* perm_p; const int32_t* perm_t; const int32_t* perm_e;   // slot -> primitive (Morton order of the AABB centres)
+    float* tb_p; float* tb_t; float* tb_e;   // [n_tiles][6] boxes of TILE consecutive SLOTS
     int2* tile_pairs[3];                     // per broad-phase kind: overlapping (tile A, tile B) pairs
     int tile_pair_cap[3];
     const int32_t* g_ps; const int32_t* g_body; const int32_t* g_voff; const int32_t* g_toff; const int32_t* g_eoff;
@@ -103,6 +105,11 @@ struct Contact {
     DevBuf<double> g_f64, mu;
     DevBuf<uint8_t> blacklist;
     DevBuf<float> bb_p, bb_t, bb_e, tb_p, tb_t, tb_e;
+    DevBuf<int32_t> perm_p, perm_t, perm_e, perm_tmp;
+    DevBuf<uint32_t> morton, morton_tmp;
+    DevBuf<float> bounds;            // scene box (6 floats)
+    DevBuf<uint8_t> sort_temp;
+    int reorder_countdown = 0;       // detections until the spatial order of the primitives is refreshed
     DevBuf<int2> tile_pairs[3];
     DevBuf<int2> cand_pt, cand_ee, cand_et;
     DevBuf<int> counters;
@@ -116,6 +123,7 @@ struct Contact {
     bool external_vertices = false;
     // detection results are a pure function of the state: a repeated call at an unchanged state (the line search's last
     // trial and the next iteration's evaluation see the same DoFs) is answered from the cache
+    double uploaded_stiffness = -1.0, uploaded_epsv = -1.0;
     uint64_t contacts_state = 0, intersections_state = 0;
     int cached_intersections = 0;
 };
@@ -167,24 +175,111 @@ __device__ __forceinline__ void bb_expand(float* b, const double* x)
 {
     for (int c = 0; c < 3; c++) { const float v = (float)x[c]; b[c] = fminf(b[c], v); b[3 + c] = fmaxf(b[3 + c], v); }
 }
+constexpr int TILE = 64;   // slots per broad-phase tile
+
+// AABBs are stored per SLOT: slot i holds primitive perm[i] (spatially sorted, so that a tile of consecutive slots is compact)
 __global__ void k_aabbs(Dev d, float extra, int do_points)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     float b[6];
     if (do_points && i < d.n_v) {
-        bb_init(b); bb_expand(b, d.x + 3 * i);
+        const int p = d.perm_p[i];
+        bb_init(b); bb_expand(b, d.x + 3 * p);
         for (int c = 0; c < 3; c++) { d.bb_p[6 * i + c] = b[c] - extra; d.bb_p[6 * i + 3 + c] = b[3 + c] + extra; }
     }
     if (i < d.n_t) {
+        const int t = d.perm_t[i];
         bb_init(b);
-        for (int k = 0; k < 3; k++) bb_expand(b, d.x + 3 * d.tri[3 * i + k]);
+        for (int k = 0; k < 3; k++) bb_expand(b, d.x + 3 * d.tri[3 * t + k]);
         for (int c = 0; c < 3; c++) { d.bb_t[6 * i + c] = b[c] - extra; d.bb_t[6 * i + 3 + c] = b[3 + c] + extra; }
     }
     if (i < d.n_e) {
+        const int e = d.perm_e[i];
         bb_init(b);
-        for (int k = 0; k < 2; k++) bb_expand(b, d.x + 3 * d.edge[2 * i + k]);
+        for (int k = 0; k < 2; k++) bb_expand(b, d.x + 3 * d.edge[2 * e + k]);
         for (int c = 0; c < 3; c++) { d.bb_e[6 * i + c] = b[c] - extra; d.bb_e[6 * i + 3 + c] = b[3 + c] + extra; }
     }
+}
+
+// One launch per detection: AABBs of every slot, the box of every tile (CTA = tile) and the counters this detection rewrites.
+// CTAs [0, Tv) are point tiles, [Tv, Tv + Tt) triangle tiles, the rest edge tiles.  clear_mask bit k clears counters
+// [8 k, 8 k + 8) (k = 0: candidates / tile pairs / overflow, 1: proximity lists, 2-4: contact tables, 5-6: friction tables ...).
+__global__ void __launch_bounds__(TILE) k_aabbs_tiles(Dev d, float extra, int do_points, int Tv, int Tt, unsigned long long clear_mask)
+{
+    __shared__ float s_lo[3][TILE / 32], s_hi[3][TILE / 32];
+    if (blockIdx.x == 0 && threadIdx.x < 64 && ((clear_mask >> threadIdx.x) & 1ull)) d.counters[threadIdx.x] = 0;
+    int cls, tile;
+    if ((int)blockIdx.x < Tv) { cls = 0; tile = blockIdx.x; }
+    else if ((int)blockIdx.x < Tv + Tt) { cls = 1; tile = blockIdx.x - Tv; }
+    else { cls = 2; tile = blockIdx.x - Tv - Tt; }
+    if (cls == 0 && !do_points) return;
+    const int n = (cls == 0) ? d.n_v : (cls == 1 ? d.n_t : d.n_e);
+    float* bb = (cls == 0) ? d.bb_p : (cls == 1 ? d.bb_t : d.bb_e);
+    float* tb = (cls == 0) ? d.tb_p : (cls == 1 ? d.tb_t : d.tb_e);
+    const int i = tile * TILE + threadIdx.x;
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    if (i < n) {
+        float b[6];
+        bb_init(b);
+        if (cls == 0) bb_expand(b, d.x + 3 * d.perm_p[i]);
+        else if (cls == 1) { const int t = d.perm_t[i]; for (int k = 0; k < 3; k++) bb_expand(b, d.x + 3 * d.tri[3 * t + k]); }
+        else { const int e = d.perm_e[i]; for (int k = 0; k < 2; k++) bb_expand(b, d.x + 3 * d.edge[2 * e + k]); }
+        for (int c = 0; c < 3; c++) { lo[c] = b[c] - extra; hi[c] = b[3 + c] + extra; bb[6 * i + c] = lo[c]; bb[6 * i + 3 + c] = hi[c]; }
+    }
+    for (int c = 0; c < 3; c++) {
+        for (int o = 16; o > 0; o >>= 1) { lo[c] = fminf(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o)); hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o)); }
+        if ((threadIdx.x & 31) == 0) { s_lo[c][threadIdx.x >> 5] = lo[c]; s_hi[c][threadIdx.x >> 5] = hi[c]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        const int c = threadIdx.x;
+        float l = FLT_MAX, h = -FLT_MAX;
+        for (int w = 0; w < TILE / 32; w++) { l = fminf(l, s_lo[c][w]); h = fmaxf(h, s_hi[c][w]); }
+        tb[6 * tile + c] = l; tb[6 * tile + 3 + c] = h;
+    }
+}
+
+// ---- spatial order of the primitives: 30-bit Morton code of the AABB centre inside the scene box ----
+__global__ void k_iota(int32_t* __restrict__ p, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i;
+}
+// scene box = union of the tile boxes of one primitive class (one CTA)
+__global__ void __launch_bounds__(256) k_scene_bounds(const float* __restrict__ tb, int n_tiles, float* __restrict__ bounds, int accumulate)
+{
+    __shared__ float s[6][256];
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int t = threadIdx.x; t < n_tiles; t += 256)
+        for (int c = 0; c < 3; c++) { lo[c] = fminf(lo[c], tb[6 * t + c]); hi[c] = fmaxf(hi[c], tb[6 * t + 3 + c]); }
+    for (int c = 0; c < 3; c++) { s[c][threadIdx.x] = lo[c]; s[3 + c][threadIdx.x] = hi[c]; }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        const int c = threadIdx.x;
+        float v = s[c][0];
+        for (int k = 1; k < 256; k++) v = (c < 3) ? fminf(v, s[c][k]) : fmaxf(v, s[c][k]);
+        if (accumulate) v = (c < 3) ? fminf(v, bounds[c]) : fmaxf(v, bounds[c]);
+        bounds[c] = v;
+    }
+}
+__device__ __forceinline__ uint32_t spread3(uint32_t v)
+{
+    v = (v | (v << 16)) & 0x030000FFu; v = (v | (v << 8)) & 0x0300F00Fu; v = (v | (v << 4)) & 0x030C30C3u; v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+__global__ void k_morton(const float* __restrict__ bb, const int32_t* __restrict__ perm, const float* __restrict__ bounds,
+                         uint32_t* __restrict__ code, int32_t* __restrict__ ids, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t q[3];
+    for (int c = 0; c < 3; c++) {
+        const float ext = fmaxf(bounds[3 + c] - bounds[c], 1e-30f);
+        const float u = (0.5f * (bb[6 * i + c] + bb[6 * i + 3 + c]) - bounds[c]) / ext;
+        q[c] = (uint32_t)fminf(fmaxf(u * 1024.0f, 0.0f), 1023.0f);
+    }
+    code[i] = (spread3(q[2]) << 2) | (spread3(q[1]) << 1) | spread3(q[0]);
+    ids[i] = perm[i];
 }
 
 // tmcd/helpers.h:35-44
@@ -198,7 +293,6 @@ __device__ __forceinline__ bool bb_overlap(const float* a, const float* b)
 // ---------------------------------------------------------------------------------------------------
 // broad phase: tiled all-pairs.  KIND 0: point(A) x triangle(B); 1: edge(A) x edge(B), A < B; 2: edge(A) x triangle(B)
 // ---------------------------------------------------------------------------------------------------
-constexpr int TILE = 256;
 
 // box of every tile of TILE consecutive primitives (one CTA per tile)
 __global__ void __launch_bounds__(TILE) k_tile_boxes(const float* __restrict__ bb, float* __restrict__ tb, int n)
@@ -222,10 +316,8 @@ __global__ void __launch_bounds__(TILE) k_tile_boxes(const float* __restrict__ b
 
 // overlapping tile pairs of one broad-phase kind (KIND 1: edge tiles, B >= A only)
 template<int KIND>
-__global__ void k_tile_pairs(Dev d, int nTa, int nTb)
+__device__ __forceinline__ void tile_pair_test(const Dev& d, int t, int nTa, int nTb)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nTa * nTb) return;
     const int ta = t / nTb, tb = t - ta * nTb;
     if (KIND == 1 && tb < ta) return;
     const float* A = ((KIND == 0) ? d.tb_p : d.tb_e) + 6 * ta;
@@ -234,61 +326,90 @@ __global__ void k_tile_pairs(Dev d, int nTa, int nTb)
     const int slot = atomicAdd(d.counters + 4 + KIND, 1);
     if (slot < d.tile_pair_cap[KIND]) d.tile_pairs[KIND][slot] = make_int2(ta, tb); else d.counters[3] = 1;
 }
+// proximity: point-triangle (n0 = Tv Tt threads) and edge-edge (n1 = Te Te threads) in one launch; intersections: n0 = 0
+// and the n1 range tests edge-triangle tiles
+__global__ void k_tile_pairs_all(Dev d, int Tv, int Tt, int Te, int n0, int n1, int intersections)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n0) tile_pair_test<0>(d, t, Tv, Tt);
+    else if (t < n0 + n1) {
+        if (intersections) tile_pair_test<2>(d, t - n0, Te, Tt);
+        else tile_pair_test<1>(d, t - n0, Te, Te);
+    }
+}
 
 // all-pairs test inside the overlapping tile pairs (persistent CTAs, B tile staged in shared memory)
+constexpr int QCAP = 2048;
+struct BroadSmem {
+    float bb[TILE][6];
+    int v[TILE][3];
+    int g[TILE];
+    int id[TILE];
+    int2 q[QCAP];
+    int qn, qbase;
+};
 template<int KIND>
-__global__ void __launch_bounds__(TILE) k_broad(Dev d)
+__device__ void broad_kind(const Dev& d, BroadSmem& S)
 {
-    __shared__ float s_bb[TILE][6];
-    __shared__ int s_v[TILE][3];
-    __shared__ int s_g[TILE];
+    float (*s_bb)[6] = S.bb;
+    int (*s_v)[3] = S.v;
+    int* s_g = S.g;
+    int* s_id = S.id;
+    int2* s_q = S.q;
+    int& s_qn = S.qn;
+    int& s_qbase = S.qbase;
     const int nA = (KIND == 0) ? d.n_v : d.n_e;
     const int nB = (KIND == 1) ? d.n_e : d.n_t;
     const float* bbA = (KIND == 0) ? d.bb_p : d.bb_e;
     const float* bbB = (KIND == 1) ? d.bb_e : d.bb_t;
+    const int32_t* permA = (KIND == 0) ? d.perm_p : d.perm_e;
+    const int32_t* permB = (KIND == 1) ? d.perm_e : d.perm_t;
     // candidates of one tile pair are queued in shared memory and appended to the global list with ONE global atomic
     // (tens of thousands of same-address global atomics would serialise in L2 and dominate the kernel)
-    constexpr int QCAP = 2048;
-    __shared__ int2 s_q[QCAP];
-    __shared__ int s_qn, s_qbase;
     int2* out = (KIND == 0) ? d.cand_pt : (KIND == 1 ? d.cand_ee : d.cand_et);
     const int n_pairs = min(d.counters[4 + KIND], d.tile_pair_cap[KIND]);
     for (int pi = blockIdx.x; pi < n_pairs; pi += gridDim.x) {
         const int2 tp = d.tile_pairs[KIND][pi];
-        const int a = tp.x * TILE + threadIdx.x;
-        const int b0 = tp.y * TILE;
+        const int a = tp.x * TILE + threadIdx.x;     // slot of A
+        const int b0 = tp.y * TILE;                  // first slot of the B tile
         __syncthreads();   // previous pair done with the shared tile and queue
         if (threadIdx.x == 0) s_qn = 0;
         {
             const int b = b0 + threadIdx.x;
             if (b < nB) {
                 for (int c = 0; c < 6; c++) s_bb[threadIdx.x][c] = bbB[6 * b + c];
-                if (KIND == 1) { s_v[threadIdx.x][0] = d.edge[2 * b]; s_v[threadIdx.x][1] = d.edge[2 * b + 1]; s_v[threadIdx.x][2] = -1; s_g[threadIdx.x] = d.e_group[b]; }
-                else { s_v[threadIdx.x][0] = d.tri[3 * b]; s_v[threadIdx.x][1] = d.tri[3 * b + 1]; s_v[threadIdx.x][2] = d.tri[3 * b + 2]; s_g[threadIdx.x] = d.t_group[b]; }
+                const int pb = permB[b];
+                s_id[threadIdx.x] = pb;
+                if (KIND == 1) { s_v[threadIdx.x][0] = d.edge[2 * pb]; s_v[threadIdx.x][1] = d.edge[2 * pb + 1]; s_v[threadIdx.x][2] = -1; s_g[threadIdx.x] = d.e_group[pb]; }
+                else { s_v[threadIdx.x][0] = d.tri[3 * pb]; s_v[threadIdx.x][1] = d.tri[3 * pb + 1]; s_v[threadIdx.x][2] = d.tri[3 * pb + 2]; s_g[threadIdx.x] = d.t_group[pb]; }
             }
         }
         __syncthreads();
         if (a < nA) {
             float ba[6];
             for (int c = 0; c < 6; c++) ba[c] = bbA[6 * a + c];
+            const int pa = permA[a];
             int va0, va1, ga;
-            if (KIND == 0) { va0 = a; va1 = -2; ga = d.v_group[a]; }
-            else { va0 = d.edge[2 * a]; va1 = d.edge[2 * a + 1]; ga = d.e_group[a]; }
+            if (KIND == 0) { va0 = pa; va1 = -2; ga = d.v_group[pa]; }
+            else { va0 = d.edge[2 * pa]; va1 = d.edge[2 * pa + 1]; ga = d.e_group[pa]; }
             const int nb = min(TILE, nB - b0);
             for (int j = 0; j < nb; j++) {
                 const int b = b0 + j;
-                if (KIND == 1 && b <= a) continue;
+                if (KIND == 1 && b <= a) continue;     // every unordered pair of slots once
                 if (!bb_overlap(ba, s_bb[j])) continue;
                 const int gb = s_g[j];
                 // shared-vertex ("orphan") discard: same set and a common vertex (collision vertex ids are global, so equality suffices)
                 const bool orphan = (va0 == s_v[j][0]) || (va0 == s_v[j][1]) || (va0 == s_v[j][2]) || (va1 == s_v[j][0]) || (va1 == s_v[j][1]) || (va1 == s_v[j][2]);
                 if (orphan) continue;
                 if (d.blacklist[ga * MAX_GROUPS + gb]) continue;
+                const int pb = s_id[j];
+                // edge-edge pairs keep the reference's role convention: first edge = lower primitive id
+                const int2 cand = (KIND == 1 && pb < pa) ? make_int2(pb, pa) : make_int2(pa, pb);
                 const int k = atomicAdd(&s_qn, 1);
-                if (k < QCAP) s_q[k] = make_int2(a, b);
+                if (k < QCAP) s_q[k] = cand;
                 else {   // queue full (dense contact): straight to the global list
                     const int slot = atomicAdd(d.counters + KIND, 1);
-                    if (slot < d.cand_cap) out[slot] = make_int2(a, b); else d.counters[3] = 1;
+                    if (slot < d.cand_cap) out[slot] = cand; else d.counters[3] = 1;
                 }
             }
         }
@@ -303,6 +424,15 @@ __global__ void __launch_bounds__(TILE) k_broad(Dev d)
             }
         }
     }
+}
+
+// all broad-phase kinds of one detection in one persistent launch (K1 < 0: only K0)
+template<int K0, int K1>
+__global__ void __launch_bounds__(TILE) k_broad_all(Dev d)
+{
+    __shared__ BroadSmem S;
+    broad_kind<K0>(d, S);
+    if (K1 >= 0) { __syncthreads(); broad_kind<(K1 >= 0 ? K1 : 0)>(d, S); }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -578,7 +708,7 @@ __device__ void emit_pt(const Dev& d, int mode, double dist, double stiffness, i
     }
 }
 
-__global__ void __launch_bounds__(128) k_narrow_pt(Dev d, double enl_sq, int mode, double stiffness)
+__device__ void narrow_pt(const Dev& d, double enl_sq, int mode, double stiffness)
 {
     const int total = min(d.counters[0], d.cand_cap);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -683,7 +813,7 @@ __device__ void emit_ee(const Dev& d, int mode, double dist, double stiffness, i
     }
 }
 
-__global__ void __launch_bounds__(128) k_narrow_ee(Dev d, double enl_sq, int mode, double stiffness, double parallel_tol)
+__device__ void narrow_ee(const Dev& d, double enl_sq, int mode, double stiffness, double parallel_tol)
 {
     const int total = min(d.counters[1], d.cand_cap);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -749,6 +879,13 @@ __global__ void __launch_bounds__(128) k_narrow_et(Dev d)
     }
 }
 
+// point-triangle and edge-edge narrow phases of one detection in one launch
+__global__ void __launch_bounds__(128) k_narrow_all(Dev d, double enl_sq, int mode, double stiffness, double parallel_tol, int do_pt, int do_ee)
+{
+    if (do_pt) narrow_pt(d, enl_sq, mode, stiffness);
+    if (do_ee) narrow_ee(d, enl_sq, mode, stiffness, parallel_tol);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
@@ -758,6 +895,7 @@ void contact_destroy(sb_context* ctx)
     if (!C) return;
     C->x.release(); C->v_group.release(); C->v_ps.release(); C->tri.release(); C->t_group.release(); C->edge.release(); C->e_group.release();
     C->g_i32.release(); C->g_f64.release(); C->mu.release(); C->blacklist.release(); C->bb_p.release(); C->bb_t.release(); C->bb_e.release(); C->tb_p.release(); C->tb_t.release(); C->tb_e.release();
+    C->perm_p.release(); C->perm_t.release(); C->perm_e.release(); C->perm_tmp.release(); C->morton.release(); C->morton_tmp.release(); C->bounds.release(); C->sort_temp.release();
     for (int k = 0; k < 3; k++) C->tile_pairs[k].release();
     C->cand_pt.release(); C->cand_ee.release(); C->cand_et.release(); C->counters.release();
     for (int l = 0; l < N_LISTS; l++) { C->list_ids[l].release(); C->list_dist[l].release(); }
@@ -798,6 +936,11 @@ static int upload_topology(sb_context* ctx, Contact* C)
     up(C->g_i32, gi); up(C->g_f64, gf);
     C->x.ensure(3 * (size_t)nv + 3);
     C->bb_p.ensure(6 * (size_t)nv + 6); C->bb_t.ensure(6 * (size_t)nt + 6); C->bb_e.ensure(6 * (size_t)ne + 6);
+    C->perm_p.ensure(nv + 1); C->perm_t.ensure(nt + 1); C->perm_e.ensure(ne + 1);
+    if (nv) k_iota<<<(nv + 255) / 256, 256, 0, st>>>(C->perm_p.p, nv);
+    if (nt) k_iota<<<(nt + 255) / 256, 256, 0, st>>>(C->perm_t.p, nt);
+    if (ne) k_iota<<<(ne + 255) / 256, 256, 0, st>>>(C->perm_e.p, ne);
+    C->reorder_countdown = 0;
     SB_CUDA(ctx, cudaStreamSynchronize(st));
     // module-owned arrays seen by the potentials
     Array& th = ctx->arrays[C->a_thickness];
@@ -837,6 +980,7 @@ static Dev make_dev(sb_context* ctx, Contact* C)
     d.x = C->x.p; d.v_group = C->v_group.p; d.v_ps_index = C->v_ps.p; d.tri = C->tri.p; d.t_group = C->t_group.p; d.edge = C->edge.p; d.e_group = C->e_group.p;
     d.bb_p = C->bb_p.p; d.bb_t = C->bb_t.p; d.bb_e = C->bb_e.p;
     d.tb_p = C->tb_p.p; d.tb_t = C->tb_t.p; d.tb_e = C->tb_e.p;
+    d.perm_p = C->perm_p.p; d.perm_t = C->perm_t.p; d.perm_e = C->perm_e.p;
     for (int k = 0; k < 3; k++) { d.tile_pairs[k] = C->tile_pairs[k].p; d.tile_pair_cap[k] = (int)C->tile_pairs[k].cap; }
     d.g_ps = C->g_i32.p; d.g_body = C->g_i32.p + MAX_GROUPS; d.g_voff = C->g_i32.p + 2 * MAX_GROUPS; d.g_toff = C->g_i32.p + 3 * MAX_GROUPS; d.g_eoff = C->g_i32.p + 4 * MAX_GROUPS;
     d.g_thickness = C->g_f64.p; d.blacklist = C->blacklist.p; d.mu = C->mu.p;
@@ -865,53 +1009,84 @@ static int update_vertices(sb_context* ctx, Contact* C, bool zero_dt)
     return 0;
 }
 
+// Refresh the spatial (Morton) order of points, triangles and edges from the current vertex positions: the broad phase
+// culls whole 256-slot tiles, which only works when consecutive slots are neighbours in space.  Run at the first detection
+// after a topology change and every REORDER_PERIOD detections (deformation moves primitives slowly); ~10 small launches.
+constexpr int REORDER_PERIOD = 64;
+static int reorder_primitives(sb_context* ctx, Contact* C)
+{
+    cudaStream_t st = ctx->stream;
+    ensure_capacities(ctx, C);
+    Dev d = make_dev(ctx, C);
+    const int nmax = std::max(d.n_v, std::max(d.n_t, d.n_e));
+    if (nmax == 0) return 0;
+    C->bounds.ensure(8); C->morton.ensure(nmax + 1); C->morton_tmp.ensure(nmax + 1); C->perm_tmp.ensure(nmax + 1);
+    const int Tv = (d.n_v + TILE - 1) / TILE, Tt = (d.n_t + TILE - 1) / TILE, Te = (d.n_e + TILE - 1) / TILE;
+    k_aabbs<<<(nmax + 255) / 256, 256, 0, st>>>(d, 0.0f, 1);                 // boxes in the CURRENT slot order
+    if (d.n_v) k_tile_boxes<<<Tv, TILE, 0, st>>>(d.bb_p, d.tb_p, d.n_v);
+    if (d.n_t) k_tile_boxes<<<Tt, TILE, 0, st>>>(d.bb_t, d.tb_t, d.n_t);
+    if (d.n_e) k_tile_boxes<<<Te, TILE, 0, st>>>(d.bb_e, d.tb_e, d.n_e);
+    if (d.n_v) k_scene_bounds<<<1, 256, 0, st>>>(d.tb_p, Tv, C->bounds.p, 0);  // every edge / triangle vertex is a point
+    ctx->launches += 5;
+    struct Cls { int n; const float* bb; DevBuf<int32_t>* perm; } cls[3] = {{d.n_v, d.bb_p, &C->perm_p}, {d.n_t, d.bb_t, &C->perm_t}, {d.n_e, d.bb_e, &C->perm_e}};
+    for (auto& c : cls) {
+        if (c.n == 0) continue;
+        k_morton<<<(c.n + 255) / 256, 256, 0, st>>>(c.bb, c.perm->p, C->bounds.p, C->morton.p, C->perm_tmp.p, c.n);
+        size_t tb = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tb, C->morton.p, C->morton_tmp.p, C->perm_tmp.p, c.perm->p, c.n, 0, 30, st);
+        C->sort_temp.ensure(tb + 16);
+        tb = C->sort_temp.cap;
+        SB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(C->sort_temp.p, tb, C->morton.p, C->morton_tmp.p, C->perm_tmp.p, c.perm->p, c.n, 0, 30, st));
+        ctx->launches += 5;
+    }
+    SB_CUDA(ctx, cudaGetLastError());
+    C->reorder_countdown = REORDER_PERIOD;
+    return 0;
+}
+
 // mode 0: proximity + contact tables; 1: proximity + friction tables; 2: intersections only; 3: proximity lists only + intersections
 static int detect(sb_context* ctx, Contact* C, int mode, double enlargement)
 {
     cudaStream_t st = ctx->stream;
+    if (C->reorder_countdown-- <= 0) { int r = reorder_primitives(ctx, C); if (r) return r; }
     for (int attempt = 0; attempt < 8; attempt++) {
         ensure_capacities(ctx, C);
         Dev d = make_dev(ctx, C);
         const int nmax = std::max(d.n_v, std::max(d.n_t, d.n_e));
-        // only the counters this mode rewrites are cleared (contact and friction tables live side by side)
-        SB_CUDA(ctx, cudaMemsetAsync(C->counters.p, 0, 8 * sizeof(int), st));
-        if (mode == 0 || mode == 3) { SB_CUDA(ctx, cudaMemsetAsync(C->counters.p + 8, 0, 6 * sizeof(int), st)); SB_CUDA(ctx, cudaMemsetAsync(C->counters.p + 16, 0, N_CONTACT_TABLES * sizeof(int), st)); }
-        if (mode == 1) { SB_CUDA(ctx, cudaMemsetAsync(C->counters.p + 8, 0, 6 * sizeof(int), st)); SB_CUDA(ctx, cudaMemsetAsync(C->counters.p + 16 + N_CONTACT_TABLES, 0, N_FRICTION * sizeof(int), st)); }
-        if (mode == 2 || mode == 3) SB_CUDA(ctx, cudaMemsetAsync(C->counters.p + 8 + 6, 0, sizeof(int), st));
+        // only the counters this mode rewrites are cleared (contact and friction tables live side by side): bit t = counters[t]
+        auto bits = [](int lo, int n) { unsigned long long m = 0; for (int t = lo; t < lo + n; t++) m |= 1ull << t; return m; };
+        unsigned long long clear = bits(0, 8);
+        if (mode == 0 || mode == 3) clear |= bits(8, 6) | bits(16, N_CONTACT_TABLES);
+        if (mode == 1) clear |= bits(8, 6) | bits(16 + N_CONTACT_TABLES, N_FRICTION);
+        if (mode == 2 || mode == 3) clear |= bits(8 + 6, 1);
         const int Tv = (d.n_v + TILE - 1) / TILE, Tt = (d.n_t + TILE - 1) / TILE, Te = (d.n_e + TILE - 1) / TILE;
-        auto broad_grid = [](int n_tile_pairs) { return std::max(1, std::min(n_tile_pairs, 148 * 6)); };
+        auto broad_grid = [](long long n_tile_pairs) { return (int)std::max(1ll, std::min(n_tile_pairs, 148ll * 16)); };
+        (void)nmax;
         if (mode != 2) {
             const float extra = (float)enlargement + FLT_EPSILON;
-            k_aabbs<<<(nmax + 255) / 256, 256, 0, st>>>(d, extra, 1);
-            ctx->launches++;
-            if (C->enable_pt && d.n_t > 0 && d.n_v > 0) {
-                k_tile_boxes<<<Tv, TILE, 0, st>>>(d.bb_p, d.tb_p, d.n_v);
-                k_tile_boxes<<<Tt, TILE, 0, st>>>(d.bb_t, d.tb_t, d.n_t);
-                k_tile_pairs<0><<<(Tv * Tt + 255) / 256, 256, 0, st>>>(d, Tv, Tt);
-                k_broad<0><<<broad_grid(Tv * Tt), TILE, 0, st>>>(d);
-                ctx->launches += 4;
-            }
-            if (C->enable_ee && d.n_e > 1) {
-                k_tile_boxes<<<Te, TILE, 0, st>>>(d.bb_e, d.tb_e, d.n_e);
-                k_tile_pairs<1><<<(Te * Te + 255) / 256, 256, 0, st>>>(d, Te, Te);
-                k_broad<1><<<broad_grid(Te * Te), TILE, 0, st>>>(d);
+            const bool pt = C->enable_pt && d.n_t > 0 && d.n_v > 0, ee = C->enable_ee && d.n_e > 1;
+            const int n0 = pt ? Tv * Tt : 0, n1 = ee ? Te * Te : 0;
+            k_aabbs_tiles<<<Tv + Tt + Te, TILE, 0, st>>>(d, extra, 1, Tv, Tt, clear);
+            if (n0 + n1 > 0) {
+                k_tile_pairs_all<<<(n0 + n1 + 255) / 256, 256, 0, st>>>(d, Tv, Tt, Te, n0, n1, 0);
+                if (pt && ee) k_broad_all<0, 1><<<broad_grid((long long)n0 + n1), TILE, 0, st>>>(d);
+                else if (pt) k_broad_all<0, -1><<<broad_grid(n0), TILE, 0, st>>>(d);
+                else k_broad_all<1, -1><<<broad_grid(n1), TILE, 0, st>>>(d);
+                const int emit_mode = (mode == 3) ? 2 : mode;   // 2 = lists only (no table matches mode 2 inside emit_*)
+                k_narrow_all<<<148 * 2, 128, 0, st>>>(d, enlargement * enlargement, emit_mode, C->stiffness, 1e-30, pt ? 1 : 0, ee ? 1 : 0);
                 ctx->launches += 3;
             }
-            const int emit_mode = (mode == 3) ? 2 : mode;   // 2 = lists only (no table matches mode 2 inside emit_*)
-            if (C->enable_pt) k_narrow_pt<<<148, 128, 0, st>>>(d, enlargement * enlargement, emit_mode, C->stiffness);
-            if (C->enable_ee) k_narrow_ee<<<148, 128, 0, st>>>(d, enlargement * enlargement, emit_mode, C->stiffness, 1e-30);
-            ctx->launches += 2;
+            ctx->launches += 1;
+            clear = 0;   // (mode 3: the intersection pass below must not wipe what the proximity pass just counted)
         }
         if (mode == 2 || mode == 3) {
             const float extra = 0.0f + FLT_EPSILON;   // IntersectionDetection uses non-enlarged AABBs (tmcd/BroadPhaseET.cpp:38)
-            k_aabbs<<<(nmax + 255) / 256, 256, 0, st>>>(d, extra, 0);
+            k_aabbs_tiles<<<Tv + Tt + Te, TILE, 0, st>>>(d, extra, 0, Tv, Tt, clear);
             ctx->launches++;
             if (d.n_e > 0 && d.n_t > 0) {
-                k_tile_boxes<<<Te, TILE, 0, st>>>(d.bb_e, d.tb_e, d.n_e);
-                k_tile_boxes<<<Tt, TILE, 0, st>>>(d.bb_t, d.tb_t, d.n_t);
-                k_tile_pairs<2><<<(Te * Tt + 255) / 256, 256, 0, st>>>(d, Te, Tt);
-                k_broad<2><<<broad_grid(Te * Tt), TILE, 0, st>>>(d);
-                ctx->launches += 4;
+                k_tile_pairs_all<<<(Te * Tt + 255) / 256, 256, 0, st>>>(d, Tv, Tt, Te, 0, Te * Tt, 1);
+                k_broad_all<2, -1><<<broad_grid((long long)Te * Tt), TILE, 0, st>>>(d);
+                ctx->launches += 2;
             }
             k_narrow_et<<<148, 128, 0, st>>>(d);
             ctx->launches++;
@@ -969,6 +1144,9 @@ static int refresh_params(sb_context* ctx, Contact* C)
     Array& ks = ctx->arrays[C->a_stiffness];
     Array& ev = ctx->arrays[C->a_epsv];
     ks.d.ensure(1); ks.n_rows = 1; ev.d.ensure(1); ev.n_rows = 1;
+    if (C->uploaded_stiffness == C->stiffness && C->uploaded_epsv == C->epsv) return 0;
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the pinned staging words may still be in flight
+    C->uploaded_stiffness = C->stiffness; C->uploaded_epsv = C->epsv;
     ctx->h_scalars[8] = C->stiffness; ctx->h_scalars[9] = C->epsv;
     SB_CUDA(ctx, cudaMemcpyAsync(ks.d.p, ctx->h_scalars + 8, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     SB_CUDA(ctx, cudaMemcpyAsync(ev.d.p, ctx->h_scalars + 9, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
