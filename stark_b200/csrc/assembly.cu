@@ -71,6 +71,8 @@ struct Assembly {
     DevBuf<uint8_t> temp;            // cub scratch
     DevBuf<uint8_t> dirty;           // per BCSR block: a source changed since the last numeric pass (PD projection)
     DevBuf<uint32_t> long_blocks;    // BCSR blocks with more than LONG_SEG sources
+    int key_shift = 20;              // key = block_row << key_shift | block_col
+    DevBuf<PotDesc> descs;           // per-class potential descriptors of the key kernel
     int* d_counts = nullptr;         // [0] long blocks [1] new blocks
     int* h_counts = nullptr;
     uint64_t assembled_eval = 0;     // evaluation the values belong to
@@ -93,26 +95,34 @@ void assembly_destroy(sb_context* ctx)
     A->S.release(); A->D.release();
     A->d_pos.release(); A->d_isnew.release(); A->d_newrank.release(); A->newpos.release(); A->s_final.release(); A->d_final.release();
     A->seg4.release(); A->blk_row.release(); A->rows.release(); A->cols.release(); A->vals.release(); A->temp.release();
-    A->dirty.release(); A->long_blocks.release();
+    A->dirty.release(); A->long_blocks.release(); A->descs.release();
     if (A->d_counts) cudaFree(A->d_counts);
     if (A->h_counts) cudaFreeHost(A->h_counts);
     delete A;
     ctx->assembly = nullptr;
 }
 
-__global__ void k_make_keys(PotDesc d, const int32_t* __restrict__ rows_all, uint64_t* __restrict__ keys, uint32_t* __restrict__ ids,
-                            uint32_t* __restrict__ src_off, uint8_t* __restrict__ src_pitch)
+// keys of the element blocks of ALL potentials of one class in one launch (descs sorted by blk_off; key = row << shift | col)
+__global__ void k_make_keys(const PotDesc* __restrict__ descs, int n_descs, size_t n_total, int shift, const int32_t* __restrict__ rows_all,
+                            uint64_t* __restrict__ keys, uint32_t* __restrict__ ids, uint32_t* __restrict__ src_off, uint8_t* __restrict__ src_pitch)
 {
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_total) return;
+    int lo = 0, hi = n_descs - 1;   // last desc with blk_off <= g
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (descs[mid].blk_off <= g) lo = mid; else hi = mid - 1;
+    }
+    const PotDesc d = descs[lo];
+    const size_t t = g - d.blk_off;
     const int nb2 = d.nb * d.nb;
-    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (size_t)d.n_elem * nb2) return;
     const int e = (int)(t / nb2);
     const int k = (int)(t - (size_t)e * nb2);
     const int bi = k / d.nb, bj = k - bi * d.nb;
     const int32_t* r = rows_all + d.rows_off + (size_t)e * d.nb;
     const size_t id = d.blk_off + t;
     const int n = 3 * d.nb;
-    keys[id] = ((uint64_t)(uint32_t)r[bi] << 32) | (uint32_t)r[bj];
+    keys[id] = ((uint64_t)(uint32_t)r[bi] << shift) | (uint32_t)r[bj];
     ids[id] = (uint32_t)id;
     src_off[id] = (uint32_t)(d.H_off + (size_t)e * n * n + (size_t)(3 * bi) * n + 3 * bj);
     src_pitch[id] = (uint8_t)n;
@@ -146,11 +156,12 @@ __global__ void k_fill_set(const uint64_t* __restrict__ keys, const uint32_t* __
 }
 
 // ---- merge of the dynamic block list into the static one ----
-__global__ void k_dyn_locate(const uint64_t* __restrict__ dkey, size_t ndb, const uint64_t* __restrict__ skey, size_t nsb,
+__global__ void k_dyn_locate(const uint64_t* __restrict__ dkey, const uint32_t* __restrict__ ndb_p, size_t n_upper, const uint64_t* __restrict__ skey, size_t nsb,
                              uint32_t* __restrict__ d_pos, uint32_t* __restrict__ d_isnew)
 {
     const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= ndb) return;
+    if (j >= n_upper) return;
+    if (j >= *ndb_p) { d_pos[j] = 0; d_isnew[j] = 0; return; }   // padding up to the host-side upper bound
     const uint64_t k = dkey[j];
     size_t lo = 0, hi = nsb;
     while (lo < hi) {
@@ -162,17 +173,17 @@ __global__ void k_dyn_locate(const uint64_t* __restrict__ dkey, size_t ndb, cons
 }
 // compacted list of the positions of the new blocks; their total
 __global__ void k_dyn_compact(const uint32_t* __restrict__ d_pos, const uint32_t* __restrict__ d_isnew, const uint32_t* __restrict__ d_newrank_incl,
-                              uint32_t* __restrict__ newpos, size_t ndb, int* __restrict__ n_new)
+                              uint32_t* __restrict__ newpos, size_t n_upper, int* __restrict__ n_new)
 {
     const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= ndb) return;
+    if (j >= n_upper) return;
     if (d_isnew[j]) newpos[d_newrank_incl[j] - 1] = d_pos[j];
-    if (j == ndb - 1) *n_new = (int)d_newrank_incl[j];
+    if (j == n_upper - 1) *n_new = (int)d_newrank_incl[j];
 }
 // final index of every static block = own index + number of new blocks inserted before it (new keys with pos <= i)
 __global__ void k_static_final(const uint64_t* __restrict__ skey, const uint32_t* __restrict__ sseg, size_t nsb,
                                const uint32_t* __restrict__ newpos, const int* __restrict__ n_new_p,
-                               uint32_t* __restrict__ s_final, int4* __restrict__ seg4, int32_t* __restrict__ blk_row, int32_t* __restrict__ cols)
+                               uint32_t* __restrict__ s_final, int4* __restrict__ seg4, int32_t* __restrict__ blk_row, int32_t* __restrict__ cols, int shift)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nsb) return;
@@ -186,23 +197,23 @@ __global__ void k_static_final(const uint64_t* __restrict__ skey, const uint32_t
     s_final[i] = f;
     seg4[f] = make_int4((int)sseg[i], (int)sseg[i + 1], 0, 0);
     const uint64_t k = skey[i];
-    blk_row[f] = (int32_t)(k >> 32);
-    cols[f] = 3 * (int32_t)(k & 0xffffffffu);
+    blk_row[f] = (int32_t)(k >> shift);
+    cols[f] = 3 * (int32_t)(k & ((1ull << shift) - 1));
 }
-__global__ void k_dyn_final(const uint64_t* __restrict__ dkey, const uint32_t* __restrict__ dseg, size_t ndb,
+__global__ void k_dyn_final(const uint64_t* __restrict__ dkey, const uint32_t* __restrict__ dseg, const uint32_t* __restrict__ ndb_p,
                             const uint32_t* __restrict__ d_pos, const uint32_t* __restrict__ d_isnew, const uint32_t* __restrict__ d_newrank_incl,
                             const uint32_t* __restrict__ s_final, uint32_t* __restrict__ d_final,
-                            int4* __restrict__ seg4, int32_t* __restrict__ blk_row, int32_t* __restrict__ cols)
+                            int4* __restrict__ seg4, int32_t* __restrict__ blk_row, int32_t* __restrict__ cols, int shift)
 {
     const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= ndb) return;
+    if (j >= *ndb_p) return;
     uint32_t f;
     if (d_isnew[j]) {
         f = d_pos[j] + (d_newrank_incl[j] - 1);
         seg4[f] = make_int4(0, 0, (int)dseg[j], (int)dseg[j + 1]);
         const uint64_t k = dkey[j];
-        blk_row[f] = (int32_t)(k >> 32);
-        cols[f] = 3 * (int32_t)(k & 0xffffffffu);
+        blk_row[f] = (int32_t)(k >> shift);
+        cols[f] = 3 * (int32_t)(k & ((1ull << shift) - 1));
     } else {
         f = s_final[d_pos[j]];
         // the static thread wrote (x, y, 0, 0); only z, w are touched here (k_static_final has completed: stream order)
@@ -333,31 +344,34 @@ static int build_set(sb_context* ctx, Assembly* A, SourceSet& X, bool dynamic)
     X.src_off.ensure(n + 1); X.src_pitch.ensure(n + 1); X.sorted_off.ensure(n + 1); X.sorted_pitch.ensure(n + 1);
     X.head.ensure(n + 1); X.blk_of.ensure(n + 1); X.blk_of_src.ensure(n + 1);
     X.blk_key.ensure(n + 1); X.seg.ensure(n + 2);   // upper bounds: every source its own block
+    std::vector<PotDesc> descs;
     size_t blk_off = 0;
     for (int pi : layout_order(ctx)) {
         Potential& p = ctx->potentials[pi];
         if (p.dynamic != dynamic || p.n_elem == 0) continue;
         PotDesc d;
         d.H_off = p.H_off; d.rows_off = p.rows_off; d.blk_off = blk_off; d.n_elem = p.n_elem; d.nb = p.k->nb;
-        const size_t cnt = (size_t)p.n_elem * d.nb * d.nb;
-        k_make_keys<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(d, ctx->rows.p, X.keys.p, X.ids.p, X.src_off.p, X.src_pitch.p);
-        ctx->launches++;
-        blk_off += cnt;
+        descs.push_back(d);
+        blk_off += (size_t)p.n_elem * d.nb * d.nb;
     }
-    int row_bits = 1;
-    while ((1ll << row_bits) < A->nbr + 1) row_bits++;
+    A->descs.ensure(descs.size() + 1);
+    SB_CUDA(ctx, cudaMemcpyAsync(A->descs.p, descs.data(), descs.size() * sizeof(PotDesc), cudaMemcpyHostToDevice, st));   // pageable source: staged before return
+    k_make_keys<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(A->descs.p, (int)descs.size(), n, A->key_shift, ctx->rows.p, X.keys.p, X.ids.p, X.src_off.p, X.src_pitch.p);
+    ctx->launches++;
+    const int key_bits = 2 * A->key_shift;
     size_t temp_bytes = 0, tb2 = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, X.keys.p, X.keys_sorted.p, X.ids.p, X.ids_sorted.p, (int)n, 0, 32 + row_bits, st);
+    cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, X.keys.p, X.keys_sorted.p, X.ids.p, X.ids_sorted.p, (int)n, 0, key_bits, st);
     cub::DeviceScan::InclusiveSum(nullptr, tb2, X.head.p, X.blk_of.p, (int)n, st);
     A->temp.ensure(std::max(temp_bytes, tb2) + 16);
     temp_bytes = A->temp.cap;
-    SB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(A->temp.p, temp_bytes, X.keys.p, X.keys_sorted.p, X.ids.p, X.ids_sorted.p, (int)n, 0, 32 + row_bits, st));
+    SB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(A->temp.p, temp_bytes, X.keys.p, X.keys_sorted.p, X.ids.p, X.ids_sorted.p, (int)n, 0, key_bits, st));
     k_heads<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(X.keys_sorted.p, X.head.p, n);
     temp_bytes = A->temp.cap;
     SB_CUDA(ctx, cub::DeviceScan::InclusiveSum(A->temp.p, temp_bytes, X.head.p, X.blk_of.p, (int)n, st));
     k_fill_set<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(X.keys_sorted.p, X.head.p, X.blk_of.p, X.ids_sorted.p, X.src_off.p, X.src_pitch.p,
                                                              X.sorted_off.p, X.sorted_pitch.p, X.seg.p, X.blk_key.p, X.blk_of_src.p, n);
     ctx->launches += 7;
+    if (dynamic) { X.n_blocks = n; return 0; }   // upper bound; the exact count stays on the device (blk_of[n - 1])
     uint32_t nb32 = 0;
     SB_CUDA(ctx, cudaMemcpyAsync(&nb32, X.blk_of.p + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     SB_CUDA(ctx, cudaStreamSynchronize(st));
@@ -365,16 +379,23 @@ static int build_set(sb_context* ctx, Assembly* A, SourceSet& X, bool dynamic)
     return 0;
 }
 
-static int build_symbolic(sb_context* ctx, Assembly* A, bool rebuild_static)
+static int build_symbolic(sb_context* ctx, Assembly* A, bool rebuild_static_in)
 {
+    bool rebuild_static = rebuild_static_in;
     StageTimer timer(ctx, ST_ASM_SYMBOLIC);
     cudaStream_t st = ctx->stream;
     if (ctx->H_total >= (1ull << 32)) return fail(ctx, SB_ERR_STATE, "sb_assemble: element Hessian storage exceeds 32-bit offsets");
     A->nbr = ctx->ndofs / 3;
+    {
+        int bits = 1;
+        while ((1ll << bits) < A->nbr + 1) bits++;
+        if (bits != A->key_shift) { A->key_shift = bits; rebuild_static = true; }   // the static keys use the same encoding
+    }
     int r;
     if (rebuild_static && (r = build_set(ctx, A, A->S, false))) return r;
     if ((r = build_set(ctx, A, A->D, true))) return r;
-    const size_t nsb = A->S.n_blocks, ndb = A->D.n_blocks;
+    const size_t nsb = A->S.n_blocks, ndb = A->D.n_blocks;   // ndb: host-side UPPER bound (= number of dynamic sources)
+    const uint32_t* ndb_dev = (A->D.n > 0) ? A->D.blk_of.p + (A->D.n - 1) : nullptr;
     if (nsb + ndb == 0) return fail(ctx, SB_ERR_STATE, "sb_assemble: no element Hessians");
     const size_t cap = nsb + ndb;   // upper bound of the merged pattern
     A->seg4.ensure(cap + 1); A->blk_row.ensure(cap + 1); A->cols.ensure(cap + 1); A->vals.ensure(9 * cap + 9);
@@ -383,7 +404,7 @@ static int build_symbolic(sb_context* ctx, Assembly* A, bool rebuild_static)
     A->d_pos.ensure(ndb + 1); A->d_isnew.ensure(ndb + 1); A->d_newrank.ensure(ndb + 1); A->newpos.ensure(ndb + 1);
     SB_CUDA(ctx, cudaMemsetAsync(A->d_counts, 0, 4 * sizeof(int), st));
     if (ndb > 0) {
-        k_dyn_locate<<<(unsigned)((ndb + 255) / 256), 256, 0, st>>>(A->D.blk_key.p, ndb, A->S.blk_key.p, nsb, A->d_pos.p, A->d_isnew.p);
+        k_dyn_locate<<<(unsigned)((ndb + 255) / 256), 256, 0, st>>>(A->D.blk_key.p, ndb_dev, ndb, A->S.blk_key.p, nsb, A->d_pos.p, A->d_isnew.p);
         size_t tb = 0;
         cub::DeviceScan::InclusiveSum(nullptr, tb, A->d_isnew.p, A->d_newrank.p, (int)ndb, st);
         A->temp.ensure(tb + 16);
@@ -394,12 +415,12 @@ static int build_symbolic(sb_context* ctx, Assembly* A, bool rebuild_static)
     }
     if (nsb > 0) {
         k_static_final<<<(unsigned)((nsb + 255) / 256), 256, 0, st>>>(A->S.blk_key.p, A->S.seg.p, nsb, A->newpos.p, A->d_counts + 1,
-                                                                       A->s_final.p, A->seg4.p, A->blk_row.p, A->cols.p);
+                                                                       A->s_final.p, A->seg4.p, A->blk_row.p, A->cols.p, A->key_shift);
         ctx->launches++;
     }
     if (ndb > 0) {
-        k_dyn_final<<<(unsigned)((ndb + 255) / 256), 256, 0, st>>>(A->D.blk_key.p, A->D.seg.p, ndb, A->d_pos.p, A->d_isnew.p, A->d_newrank.p,
-                                                                    A->s_final.p, A->d_final.p, A->seg4.p, A->blk_row.p, A->cols.p);
+        k_dyn_final<<<(unsigned)((ndb + 255) / 256), 256, 0, st>>>(A->D.blk_key.p, A->D.seg.p, ndb_dev, A->d_pos.p, A->d_isnew.p, A->d_newrank.p,
+                                                                    A->s_final.p, A->d_final.p, A->seg4.p, A->blk_row.p, A->cols.p, A->key_shift);
         ctx->launches++;
     }
     SB_CUDA(ctx, cudaMemcpyAsync(A->h_counts, A->d_counts, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));

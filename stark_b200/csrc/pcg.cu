@@ -170,6 +170,31 @@ __device__ __forceinline__ double block_max(double v, double* s)
     }
     return t;  // valid in thread 0
 }
+// two sums at once (one pair of barriers instead of two)
+__device__ __forceinline__ void block_sum2(double& a, double& b, double* s)
+{
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_down_sync(0xffffffffu, a, o); b += __shfl_down_sync(0xffffffffu, b, o); }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) { s[w] = a; s[PCG_THREADS / 32 + w] = b; }
+    __syncthreads();
+    double ta = 0.0, tb = 0.0;
+    if (threadIdx.x < PCG_THREADS / 32) { ta = s[threadIdx.x]; tb = s[PCG_THREADS / 32 + threadIdx.x]; }
+    if (w == 0) {
+        for (int o = PCG_THREADS / 64; o > 0; o >>= 1) { ta += __shfl_down_sync(0xffffffffu, ta, o); tb += __shfl_down_sync(0xffffffffu, tb, o); }
+    }
+    a = ta; b = tb;   // valid in thread 0
+}
+// every CTA sums the same gridDim.x partials of two arrays in the same order -> identical values everywhere
+__device__ __forceinline__ void all_partials2(const double* partA, const double* partB, double* s, double* bc, double& outA, double& outB)
+{
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < gridDim.x; i += PCG_THREADS) { a += __ldcg(partA + i); b += __ldcg(partB + i); }
+    block_sum2(a, b, s);
+    if (threadIdx.x == 0) { bc[0] = a; bc[1] = b; }
+    __syncthreads();
+    outA = bc[0]; outB = bc[1];
+}
 // every CTA sums the same gridDim.x partials in the same order -> identical value everywhere
 __device__ __forceinline__ double all_partials(const double* part, double* s, double* bc)
 {
@@ -218,8 +243,9 @@ __device__ __forceinline__ unsigned long long global_ns()
 __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_solve(const PcgArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ double s[PCG_THREADS / 32];
-    __shared__ double bc;
+    __shared__ double s[2 * (PCG_THREADS / 32)];
+    __shared__ double bc2[2];
+    double& bc = bc2[0];
     __shared__ int s_range[2];
     __shared__ int s_long[MAX_LONG_ROWS];
     __shared__ int s_n_long;
@@ -424,14 +450,12 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_solve(const PcgArgs A)
             bb += g0 * g0 + g1 * g1 + g2 * g2;
             ru += g0 * z0 + g1 * z1 + g2 * z2;
         }
-        const double t0 = block_sum(bb, s);
-        if (tid == 0) __stcg(part0 + blockIdx.x, t0);
-        const double t1 = block_sum(ru, s);
-        if (tid == 0) __stcg(part1 + blockIdx.x, t1);
+        block_sum2(bb, ru, s);
+        if (tid == 0) { __stcg(part0 + blockIdx.x, bb); __stcg(part1 + blockIdx.x, ru); }
     }
     grid_barrier(A.barrier, epoch);
-    const double bb = all_partials(part0, s, &bc);
-    double gamma = all_partials(part1, s, &bc);
+    double bb, gamma;
+    all_partials2(part0, part1, s, bc2, bb, gamma);
 
     int it = 0, done = 0, found_indef = 0;
     double error = 1.0;               // x0 = 0 -> r = b
@@ -481,19 +505,17 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_solve(const PcgArgs A)
                 rr += q[0] * q[0] + q[1] * q[1] + q[2] * q[2];
                 ru += q[0] * z0 + q[1] * z1 + q[2] * z2;
             }
-            const double t0 = block_sum(rr, s);
-            if (tid == 0) __stcg(part0 + blockIdx.x, t0);
-            const double t1 = block_sum(ru, s);
-            if (tid == 0) __stcg(part1 + blockIdx.x, t1);
+            block_sum2(rr, ru, s);
+            if (tid == 0) { __stcg(part0 + blockIdx.x, rr); __stcg(part1 + blockIdx.x, ru); }
         }
         PCG_TICK(c_vec);
         grid_barrier(A.barrier, epoch);
         PCG_TICK(c_bar);
-        const double rr = all_partials(part0, s, &bc);
+        double rr, gamma_new;
+        all_partials2(part0, part1, s, bc2, rr, gamma_new);
         error = sqrt(rr / bb);
-        if (error < A.abs_tol || error / error0 < A.rel_tol) { done = 1; break; }
-        const double gamma_new = all_partials(part1, s, &bc);
         PCG_TICK(c_red);
+        if (error < A.abs_tol || error / error0 < A.rel_tol) { done = 1; break; }
         if (it >= A.max_iter) { done = 3; break; }
         // ---- w = A u ; delta = w.u ----
         load_window();

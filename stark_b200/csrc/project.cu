@@ -213,15 +213,11 @@ __device__ __forceinline__ double helmert(int a, int j)
 }
 
 template<int N>
-__global__ void __launch_bounds__(PROJ_THREADS) k_project(const ProjTable* __restrict__ Tp, double* __restrict__ H_all, const uint32_t* __restrict__ list,
-                                                           const int* __restrict__ n_list, double eps, int mirror, int* __restrict__ n_changed,
-                                                           const DirtyView dv)
+__device__ void project_item(unsigned char* base, const ProjTable& T, int pi, unsigned long long e, double* __restrict__ H_all, double eps, int mirror,
+                             int* __restrict__ n_changed, const DirtyView& dv, int lane)
 {
     constexpr int NN = N / 3;                       // nodes
     constexpr int R = (N > 3) ? N - 3 : N;          // size after removing the translations
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char* base = smem_raw + (size_t)warp * ((proj_smem_per_warp<N>() + 15) & ~(size_t)15);
     ProjScratch S;
     S.A = reinterpret_cast<double*>(base);
     S.V = S.A + N * N;
@@ -231,12 +227,7 @@ __global__ void __launch_bounds__(PROJ_THREADS) k_project(const ProjTable* __res
     S.pp = reinterpret_cast<int*>(S.cs_s + (N + 1) / 2);
     S.pq = S.pp + (N + 1) / 2 + 1;
     double* A = S.A; double* V = S.V;
-    const ProjTable& T = *Tp;
-    const int total = *n_list;
-    for (int item = blockIdx.x * PROJ_WARPS + warp; item < total; item += gridDim.x * PROJ_WARPS) {
-        const unsigned long long e = list[item];
-        const int pi = find_pot(T, e);
-        if (3 * T.nb[pi] != N) continue;   // another size class: handled by its own kernel instance
+    {
         double* H = H_all + T.H_off[pi] + (e - T.E_off[pi]) * (unsigned long long)(N * N);
         const bool invariant = (N > 3) && T.invariant[pi];
         __syncwarp();   // previous item fully done
@@ -310,20 +301,44 @@ __global__ void __launch_bounds__(PROJ_THREADS) k_project(const ProjTable* __res
     }
 }
 
-template<int N> static cudaError_t launch_project(int grid, cudaStream_t st, const ProjTable* Tp, double* H, const uint32_t* list, const int* n_list,
-                                                  double eps, int mirror, int* n_changed, const DirtyView& dv)
+// one launch for all element sizes: the warp dispatches on the size of its element (uniform across the warp)
+__global__ void __launch_bounds__(PROJ_THREADS) k_project(const ProjTable* __restrict__ Tp, double* __restrict__ H_all, const uint32_t* __restrict__ list,
+                                                           const int* __restrict__ n_list, double eps, int mirror, int* __restrict__ n_changed,
+                                                           const DirtyView dv, int smem_per_warp)
 {
-    const size_t smem = PROJ_WARPS * ((proj_smem_per_warp<N>() + 15) & ~(size_t)15);
-    static bool configured = false;
-    if (!configured) {
-        if (smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(k_project<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* base = smem_raw + (size_t)warp * smem_per_warp;
+    const ProjTable& T = *Tp;
+    const int total = *n_list;
+    for (int item = blockIdx.x * PROJ_WARPS + warp; item < total; item += gridDim.x * PROJ_WARPS) {
+        const unsigned long long e = list[item];
+        const int pi = find_pot(T, e);
+        switch (T.nb[pi]) {
+        case 1: project_item<3>(base, T, pi, e, H_all, eps, mirror, n_changed, dv, lane); break;
+        case 2: project_item<6>(base, T, pi, e, H_all, eps, mirror, n_changed, dv, lane); break;
+        case 3: project_item<9>(base, T, pi, e, H_all, eps, mirror, n_changed, dv, lane); break;
+        case 4: project_item<12>(base, T, pi, e, H_all, eps, mirror, n_changed, dv, lane); break;
+        case 5: project_item<15>(base, T, pi, e, H_all, eps, mirror, n_changed, dv, lane); break;
+        case 6: project_item<18>(base, T, pi, e, H_all, eps, mirror, n_changed, dv, lane); break;
+        case 7: project_item<21>(base, T, pi, e, H_all, eps, mirror, n_changed, dv, lane); break;
+        default: project_item<24>(base, T, pi, e, H_all, eps, mirror, n_changed, dv, lane); break;
         }
-        configured = true;
     }
-    k_project<N><<<grid, PROJ_THREADS, smem, st>>>(Tp, H, list, n_list, eps, mirror, n_changed, dv);
-    return cudaGetLastError();
+}
+
+static size_t proj_smem_for(int nb)
+{
+    switch (nb) {
+    case 1: return proj_smem_per_warp<3>();
+    case 2: return proj_smem_per_warp<6>();
+    case 3: return proj_smem_per_warp<9>();
+    case 4: return proj_smem_per_warp<12>();
+    case 5: return proj_smem_per_warp<15>();
+    case 6: return proj_smem_per_warp<18>();
+    case 7: return proj_smem_per_warp<21>();
+    default: return proj_smem_per_warp<24>();
+    }
 }
 
 // potentials whose DoF blocks are all deformable points and whose energy depends on their differences only
@@ -341,6 +356,7 @@ struct Projector {
     ProjTable* d_table = nullptr;
     int* d_counts = nullptr;   // [0] n_list, [1] n_changed, [2] n_inactive
     int* h_counts = nullptr;
+    size_t smem_configured = 0;
 };
 void projector_destroy(sb_context* ctx)
 {
@@ -402,24 +418,17 @@ int project_internal(sb_context* ctx, double grad_threshold, double eps, int mir
     const int grid = (int)std::min<size_t>((n_elem + PROJ_WARPS - 1) / PROJ_WARPS, 148 * 8);
     DirtyView dv;
     if (!assembly_dirty_view(ctx, &dv)) dv.dirty = nullptr;
-    bool sizes[PROJ_MAX_N / 3 + 1] = {false};
-    for (auto& p : ctx->potentials) if (p.n_elem > 0) sizes[p.k->nb] = true;
-    for (int nb = 1; nb <= PROJ_MAX_N / 3; nb++) {
-        if (!sizes[nb]) continue;
-        cudaError_t e = cudaSuccess;
-        switch (nb) {
-        case 1: e = launch_project<3>(grid, st, P.d_table, ctx->H.p, P.list.p, P.d_counts, eps, mirror, P.d_counts + 1, dv); break;
-        case 2: e = launch_project<6>(grid, st, P.d_table, ctx->H.p, P.list.p, P.d_counts, eps, mirror, P.d_counts + 1, dv); break;
-        case 3: e = launch_project<9>(grid, st, P.d_table, ctx->H.p, P.list.p, P.d_counts, eps, mirror, P.d_counts + 1, dv); break;
-        case 4: e = launch_project<12>(grid, st, P.d_table, ctx->H.p, P.list.p, P.d_counts, eps, mirror, P.d_counts + 1, dv); break;
-        case 5: e = launch_project<15>(grid, st, P.d_table, ctx->H.p, P.list.p, P.d_counts, eps, mirror, P.d_counts + 1, dv); break;
-        case 6: e = launch_project<18>(grid, st, P.d_table, ctx->H.p, P.list.p, P.d_counts, eps, mirror, P.d_counts + 1, dv); break;
-        case 7: e = launch_project<21>(grid, st, P.d_table, ctx->H.p, P.list.p, P.d_counts, eps, mirror, P.d_counts + 1, dv); break;
-        case 8: e = launch_project<24>(grid, st, P.d_table, ctx->H.p, P.list.p, P.d_counts, eps, mirror, P.d_counts + 1, dv); break;
-        }
-        SB_CUDA(ctx, e);
-        ctx->launches++;
+    int nb_max = 1;
+    for (auto& p : ctx->potentials) if (p.n_elem > 0) nb_max = std::max(nb_max, p.k->nb);
+    const size_t per_warp = (proj_smem_for(nb_max) + 15) & ~(size_t)15;   // shared memory sized for the largest element present
+    const size_t smem = PROJ_WARPS * per_warp;
+    if (smem > P.smem_configured) {
+        SB_CUDA(ctx, cudaFuncSetAttribute(k_project, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+        P.smem_configured = smem;
     }
+    k_project<<<grid, PROJ_THREADS, smem, st>>>(P.d_table, ctx->H.p, P.list.p, P.d_counts, eps, mirror, P.d_counts + 1, dv, (int)per_warp);
+    SB_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
     ctx->launches += 1;
     SB_CUDA(ctx, cudaMemcpyAsync(P.h_counts, P.d_counts, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
     SB_CUDA(ctx, cudaStreamSynchronize(st));   // also protects the stack-resident table T
