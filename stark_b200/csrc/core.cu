@@ -341,7 +341,7 @@ const char* sb_profile_report(sb_context* ctx)
 {
     if (!ctx) return "";
     static const char* names[ST_COUNT] = {"contact_update", "intersections", "eval_pgh", "eval_p", "project_to_pd", "assembly_symbolic", "assembly_numeric", "pcg", "line_search_misc", "cg_iterations", "pcg_kernel_setup", "project_selected", "project_changed", "pcg_cycles_spmv", "pcg_cycles_barrier", "pcg_cycles_reduce", "pcg_cycles_vector",
-                                            "tile_pairs_pt", "tile_pairs_ee", "tile_pairs_et", "candidates_pt", "candidates_ee", "candidates_et", "project_sweeps"};
+                                            "tile_pairs_pt", "tile_pairs_ee", "tile_pairs_et", "candidates_pt", "candidates_ee", "candidates_et", "project_sweeps", "pcg_cycles_window"};
     ctx->profile_report.clear();
     for (int i = 0; i < ST_COUNT; i++)
         ctx->profile_report += std::string(names[i]) + " " + std::to_string(ctx->stage_ms[i]) + " " + std::to_string(ctx->stage_calls[i]) + "\n";

@@ -116,7 +116,7 @@ struct Potential {
 // Stage profiling (sb_profile_stages): host wall time between two stream synchronisations, accumulated per stage.
 enum Stage { ST_CONTACT_UPDATE, ST_INTERSECTIONS, ST_EVAL_PGH, ST_EVAL_P, ST_PROJECT, ST_ASM_SYMBOLIC, ST_ASM_NUMERIC, ST_PCG, ST_LINE_SEARCH_MISC, ST_CG_ITERATIONS /* calls = iterations, ms = in-kernel time of the iteration loop */, ST_PCG_SETUP /* in-kernel: slice load + preconditioner */, ST_PROJ_SELECTED /* calls = elements selected */, ST_PROJ_CHANGED /* calls = elements modified */,
              ST_PCG_C_SPMV, ST_PCG_C_BAR, ST_PCG_C_RED, ST_PCG_C_VEC /* calls = SM cycles of CTA 0 in the PCG loop */,
-             ST_TILE_PAIRS_PT, ST_TILE_PAIRS_EE, ST_TILE_PAIRS_ET, ST_CAND_PT, ST_CAND_EE, ST_CAND_ET /* calls = totals over the detections */, ST_PROJ_SWEEPS /* calls = Jacobi sweeps */, ST_COUNT };
+             ST_TILE_PAIRS_PT, ST_TILE_PAIRS_EE, ST_TILE_PAIRS_ET, ST_CAND_PT, ST_CAND_EE, ST_CAND_ET /* calls = totals over the detections */, ST_PROJ_SWEEPS /* calls = Jacobi sweeps */, ST_PCG_C_WIN /* cycles: TMA window load */, ST_COUNT };
 struct StageTimer {
     sb_context* ctx;
     int stage;

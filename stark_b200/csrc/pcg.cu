@@ -44,7 +44,7 @@ struct PcgResult {
     int found_indef;
     int pad;
     unsigned long long t_start, t_loaded, t_loop, t_end;   // %globaltimer (ns) of CTA 0: kernel entry, slices resident, first iteration, exit
-    long long c_spmv, c_bar, c_red, c_vec;                 // clock64 cycles of CTA 0 inside the loop (only when instrumented)
+    long long c_spmv, c_bar, c_red, c_vec, c_win;          // clock64 cycles of CTA 0 inside the loop (only when instrumented)
 };
 
 struct PcgArgs {
@@ -240,17 +240,25 @@ __device__ __forceinline__ unsigned long long global_ns()
     return t;
 }
 
-__global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_solve(const PcgArgs A)
+// The dynamic shared memory of the solver.  A CTA whose slices all fit (the normal case) runs the FAST instance of the solve
+// body, in which every slice pointer is derived from this symbol, so that the compiler emits shared-memory loads / stores
+// (LDS / STS); pointers that may be either shared or global are generic and every access pays the generic-address path of
+// the LSU, which made the SpMV 4x slower.
+extern __shared__ __align__(16) unsigned char pcg_smem[];
+
+struct PcgPlan {
+    int r0, nr, w0, nwin, n_long;
+    bool own_in_win;
+    unsigned win_bytes;
+    unsigned off_rp, off_r, off_p, off_s, off_w, off_dinv, off_cols, off_vals, off_win;   // byte offsets in pcg_smem (FAST)
+    int* rp; double *rs, *ps, *ss, *ws; float* dinv; const int32_t* cols; const float* vals; double* uwin;   // generic pointers
+    double* s; double* bc2; int* s_long; unsigned long long* mbar;
+    unsigned long long t_start, t_loaded;
+};
+
+template<bool FAST>
+__device__ __forceinline__ void pcg_body(const PcgArgs& A, const PcgPlan& P)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ double s[2 * (PCG_THREADS / 32)];
-    __shared__ double bc2[2];
-    double& bc = bc2[0];
-    __shared__ int s_range[2];
-    __shared__ int s_long[MAX_LONG_ROWS];
-    __shared__ int s_n_long;
-    __shared__ __align__(8) unsigned long long s_mbar;
-    const unsigned long long t_start = global_ns();
     const int G = gridDim.x;
     const int nbr = A.nbr;
     const int tid = threadIdx.x;
@@ -258,75 +266,25 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_solve(const PcgArgs A)
     double* part0 = A.part;
     double* part1 = A.part + PCG_MAX_BLOCKS;
     double* part2 = A.part + 2 * PCG_MAX_BLOCKS;
-
-    // ---- this CTA's rows: [r0, r1), holding blocks [b0, b0 + nb) ----
-    if (tid == 0) {
-        s_range[0] = row_lower_bound(A.rows, nbr, (A.nnzb * blockIdx.x) / G);
-        s_range[1] = (blockIdx.x == G - 1) ? nbr : row_lower_bound(A.rows, nbr, (A.nnzb * (blockIdx.x + 1)) / G);
-        mbar_init(&s_mbar, 1);
-    }
-    __syncthreads();
-    const int r0 = s_range[0], nr = s_range[1] - s_range[0];
-    const unsigned long long b0 = A.rows[r0];
-    const int nb = (int)(A.rows[r0 + nr] - b0);
-
-    // ---- shared-memory plan: row pointers; the vector slices r, p, s, w, M^-1; the matrix slice; the window of u gets
-    //      what is left.  Whatever does not fit stays in global memory and is reached through the same (generic) pointers ----
-    size_t off = 0;
-    auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 15) & ~(size_t)15; return o; };
-    const bool rp_fit = ((sizeof(int) * (nr + 1) + 15) & ~(size_t)15) <= A.smem_bytes;
-    int* rp = rp_fit ? reinterpret_cast<int*>(smem + carve(sizeof(int) * (nr + 1))) : A.rp_scratch + r0 + blockIdx.x;
-    const size_t vec_bytes = 4 * ((sizeof(double) * 3 * nr + 15) & ~(size_t)15) + ((sizeof(float) * 9 * nr + 15) & ~(size_t)15);
-    const bool vec_fit = rp_fit && off + vec_bytes <= A.smem_bytes;
-    double *rs, *ps, *ss, *ws; float* dinv;
-    if (vec_fit) {
-        rs = reinterpret_cast<double*>(smem + carve(sizeof(double) * 3 * nr));
-        ps = reinterpret_cast<double*>(smem + carve(sizeof(double) * 3 * nr));
-        ss = reinterpret_cast<double*>(smem + carve(sizeof(double) * 3 * nr));
-        ws = reinterpret_cast<double*>(smem + carve(sizeof(double) * 3 * nr));
-        dinv = reinterpret_cast<float*>(smem + carve(sizeof(float) * 9 * nr));
-    } else {
-        rs = A.r + 3 * (size_t)r0; ps = A.p + 3 * (size_t)r0; ss = A.s + 3 * (size_t)r0; ws = A.w + 3 * (size_t)r0; dinv = A.dinv + 9 * (size_t)r0;
-    }
-    // window of u: as many rows around the own range as fit after the matrix slice (or, when the matrix does not fit, in
-    // what is left after the vectors); at least the own rows, else no window at all
-    const size_t mat_bytes = ((sizeof(int) * (size_t)nb + 15) & ~(size_t)15) + ((sizeof(float) * 9 * (size_t)nb + 15) & ~(size_t)15);
-    const size_t min_win = ((sizeof(double) * 3 * ((size_t)nr + 2) + 15) & ~(size_t)15);
-    const bool mat_fit = vec_fit && off + mat_bytes + min_win <= A.smem_bytes;
-    const int32_t* cols; const float* vals;
-    if (mat_fit) {
-        int32_t* cs = reinterpret_cast<int32_t*>(smem + carve(sizeof(int) * (size_t)nb));
-        float* vs = reinterpret_cast<float*>(smem + carve(sizeof(float) * 9 * (size_t)nb));
-        for (int i = tid; i < nb; i += PCG_THREADS) cs[i] = A.cols[b0 + i];
-        for (int i = tid; i < 9 * nb; i += PCG_THREADS) vs[i] = A.vals[9 * b0 + i];
-        cols = cs; vals = vs;
-    } else {
-        cols = A.cols + b0; vals = A.vals + 9 * b0;
-    }
-    int w0 = r0, nwin = 0;     // window = block rows [w0, w0 + nwin)
-    double* uwin = nullptr;
-    if (vec_fit && off + min_win <= A.smem_bytes) {
-        const int cap_rows = (int)(((size_t)A.smem_bytes - off) / (sizeof(double) * 3)) & ~1;   // even: 16 B granularity of the bulk copy
-        const int half = (cap_rows - nr) / 2;
-        w0 = max(0, r0 - half) & ~1;
-        int w1 = min(nbr, w0 + cap_rows);
-        nwin = w1 - w0;
-        uwin = reinterpret_cast<double*>(smem + off);
-    }
-    const bool own_in_win = nwin > 0;   // by construction the window then contains [r0, r0 + nr)
-    // the bulk copy moves multiples of 16 B: with an odd row count (only possible at the very end of the vector) it also
-    // copies the 8 B of padding behind u (the buffer is allocated with that slack)
-    const unsigned win_bytes = (unsigned)((sizeof(double) * 3 * (size_t)nwin + 15) & ~(size_t)15);
-    for (int i = tid; i <= nr; i += PCG_THREADS) rp[i] = (int)(A.rows[r0 + i] - b0);
-    if (tid == 0) s_n_long = 0;
-    __syncthreads();
-    for (int i = tid; i < nr; i += PCG_THREADS)
-        if (rp[i + 1] - rp[i] > LONG_ROW) {
-            const int k = atomicAdd(&s_n_long, 1);
-            if (k < MAX_LONG_ROWS) s_long[k] = i;
-        }
-    __syncthreads();
-    const int n_long = min(s_n_long, MAX_LONG_ROWS);
+    double* s = P.s;
+    double* bc2 = P.bc2;
+    double& bc = bc2[0];
+    int* s_long = P.s_long;
+    unsigned long long& s_mbar = *P.mbar;
+    const int r0 = P.r0, nr = P.nr, w0 = P.w0, nwin = P.nwin, n_long = P.n_long;
+    const bool own_in_win = P.own_in_win;
+    const unsigned win_bytes = P.win_bytes;
+    const unsigned long long t_start = P.t_start, t_loaded = P.t_loaded;
+    int* rp = FAST ? reinterpret_cast<int*>(pcg_smem + P.off_rp) : P.rp;
+    double* rs = FAST ? reinterpret_cast<double*>(pcg_smem + P.off_r) : P.rs;
+    double* ps = FAST ? reinterpret_cast<double*>(pcg_smem + P.off_p) : P.ps;
+    double* ss = FAST ? reinterpret_cast<double*>(pcg_smem + P.off_s) : P.ss;
+    double* ws = FAST ? reinterpret_cast<double*>(pcg_smem + P.off_w) : P.ws;
+    float* dinv = FAST ? reinterpret_cast<float*>(pcg_smem + P.off_dinv) : P.dinv;
+    const int32_t* cols = FAST ? reinterpret_cast<const int32_t*>(pcg_smem + P.off_cols) : P.cols;
+    const float* vals = FAST ? reinterpret_cast<const float*>(pcg_smem + P.off_vals) : P.vals;
+    double* uwin = FAST ? reinterpret_cast<double*>(pcg_smem + P.off_win) : P.uwin;
+    (void)G; (void)nbr; (void)bc;
     auto is_swept = [&](int lr) {   // long AND listed (every listed row gets its own block reduction)
         if (rp[lr + 1] - rp[lr] <= LONG_ROW) return false;
         for (int k = 0; k < n_long; k++) if (s_long[k] == lr) return true;
@@ -336,7 +294,6 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_solve(const PcgArgs A)
     const double* uo_win = own_in_win ? uwin + 3 * (size_t)(r0 - w0) : nullptr;
     auto uo = [&](int i) -> double { return own_in_win ? uo_win[i] : __ldcg(ug + i); };   // own slice of u as this CTA reads it
     double* xg = A.x + 3 * (size_t)r0;                           // x is only ever touched by its owner thread
-    const unsigned long long t_loaded = global_ns();
 
     // gather of u at scalar column c (first of the three of a block column)
     const int win_lo = 3 * w0, win_hi = 3 * (w0 + nwin);
@@ -367,13 +324,27 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_solve(const PcgArgs A)
             const bool swept = (lr < nr) && is_swept(lr);
             if (lr < nr && !swept) {
                 const int j1 = rp[lr + 1];
-                for (int j = rp[lr] + lane; j < j1; j += LANES_PER_ROW) {
-                    const float* m = vals + 9 * (size_t)j;   // column-major 3x3
-                    double a0, a1, a2;
-                    gather3(cols[j], a0, a1, a2);
-                    y0 += (double)m[0] * a0 + (double)m[3] * a1 + (double)m[6] * a2;
-                    y1 += (double)m[1] * a0 + (double)m[4] * a1 + (double)m[7] * a2;
-                    y2 += (double)m[2] * a0 + (double)m[5] * a1 + (double)m[8] * a2;
+                // four blocks per trip: their gathers of u (shared-memory window, or L2 for far columns -- hex-centre nodes,
+                // rigid bodies) are all issued before the first product, so a row costs one memory round trip, not one per block
+                constexpr int U = 4;
+                for (int j = rp[lr] + lane; j < j1; j += U * LANES_PER_ROW) {
+                    double a[U][3];
+#pragma unroll
+                    for (int t = 0; t < U; t++) {
+                        const int jj = j + t * LANES_PER_ROW;
+                        a[t][0] = 0.0; a[t][1] = 0.0; a[t][2] = 0.0;
+                        if (jj < j1) gather3(cols[jj], a[t][0], a[t][1], a[t][2]);
+                    }
+#pragma unroll
+                    for (int t = 0; t < U; t++) {
+                        const int jj = j + t * LANES_PER_ROW;
+                        if (jj < j1) {
+                            const float* m = vals + 9 * (size_t)jj;   // column-major 3x3
+                            y0 += (double)m[0] * a[t][0] + (double)m[3] * a[t][1] + (double)m[6] * a[t][2];
+                            y1 += (double)m[1] * a[t][0] + (double)m[4] * a[t][1] + (double)m[7] * a[t][2];
+                            y2 += (double)m[2] * a[t][0] + (double)m[5] * a[t][1] + (double)m[8] * a[t][2];
+                        }
+                    }
                 }
             }
             for (int o = LANES_PER_ROW / 2; o > 0; o >>= 1) {
@@ -465,7 +436,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_solve(const PcgArgs A)
     else if (A.max_iter <= 0) done = 3;
 
     const unsigned long long t_loop = global_ns();
-    long long c_spmv = 0, c_bar = 0, c_red = 0, c_vec = 0, c_t = A.instrument ? clock64() : 0;
+    long long c_spmv = 0, c_bar = 0, c_red = 0, c_vec = 0, c_win = 0, c_t = A.instrument ? clock64() : 0;
 #define PCG_TICK(acc) if (A.instrument) { const long long _n = clock64(); acc += _n - c_t; c_t = _n; }
     double alpha = 0.0, beta = 0.0;
     if (!done) {
@@ -519,6 +490,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_solve(const PcgArgs A)
         if (it >= A.max_iter) { done = 3; break; }
         // ---- w = A u ; delta = w.u ----
         load_window();
+        PCG_TICK(c_win);
         {
             const double wu = spmv();
             const double t = block_sum(wu, s);
@@ -563,11 +535,110 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_solve(const PcgArgs A)
             PcgResult R;
             R.du_dot_grad = dg; R.du_inf = mx; R.error = error; R.bb = bb;
             R.it = it; R.done = done; R.found_indef = found_indef; R.pad = 0;
-            R.c_spmv = c_spmv; R.c_bar = c_bar; R.c_red = c_red; R.c_vec = c_vec;
+            R.c_spmv = c_spmv; R.c_bar = c_bar; R.c_red = c_red; R.c_vec = c_vec; R.c_win = c_win;
             R.t_start = t_start; R.t_loaded = t_loaded; R.t_loop = t_loop; R.t_end = global_ns();
             *A.result = R;
         }
     }
+}
+
+__global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_solve(const PcgArgs A)
+{
+    unsigned char* const smem = pcg_smem;
+    __shared__ double s[2 * (PCG_THREADS / 32)];
+    __shared__ double bc2[2];
+    double& bc = bc2[0];
+    __shared__ int s_range[2];
+    __shared__ int s_long[MAX_LONG_ROWS];
+    __shared__ int s_n_long;
+    __shared__ __align__(8) unsigned long long s_mbar;
+    const unsigned long long t_start = global_ns();
+    const int G = gridDim.x;
+    const int nbr = A.nbr;
+    const int tid = threadIdx.x;
+    unsigned epoch = 0;
+    double* part0 = A.part;
+    double* part1 = A.part + PCG_MAX_BLOCKS;
+    double* part2 = A.part + 2 * PCG_MAX_BLOCKS;
+
+    // ---- this CTA's rows: [r0, r1), holding blocks [b0, b0 + nb) ----
+    if (tid == 0) {
+        s_range[0] = row_lower_bound(A.rows, nbr, (A.nnzb * blockIdx.x) / G);
+        s_range[1] = (blockIdx.x == G - 1) ? nbr : row_lower_bound(A.rows, nbr, (A.nnzb * (blockIdx.x + 1)) / G);
+        mbar_init(&s_mbar, 1);
+    }
+    __syncthreads();
+    const int r0 = s_range[0], nr = s_range[1] - s_range[0];
+    const unsigned long long b0 = A.rows[r0];
+    const int nb = (int)(A.rows[r0 + nr] - b0);
+
+    // ---- shared-memory plan: row pointers; the vector slices r, p, s, w, M^-1; the matrix slice; the window of u gets
+    //      what is left.  Whatever does not fit stays in global memory and is reached through the same (generic) pointers ----
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 15) & ~(size_t)15; return o; };
+    const bool rp_fit = ((sizeof(int) * (nr + 1) + 15) & ~(size_t)15) <= A.smem_bytes;
+    PcgPlan P;
+    P.off_rp = P.off_r = P.off_p = P.off_s = P.off_w = P.off_dinv = P.off_cols = P.off_vals = P.off_win = 0;
+    if (rp_fit) P.off_rp = (unsigned)off;
+    int* rp = rp_fit ? reinterpret_cast<int*>(smem + carve(sizeof(int) * (nr + 1))) : A.rp_scratch + r0 + blockIdx.x;
+    const size_t vec_bytes = 4 * ((sizeof(double) * 3 * nr + 15) & ~(size_t)15) + ((sizeof(float) * 9 * nr + 15) & ~(size_t)15);
+    const bool vec_fit = rp_fit && off + vec_bytes <= A.smem_bytes;
+    double *rs, *ps, *ss, *ws; float* dinv;
+    if (vec_fit) {
+        P.off_r = (unsigned)off; rs = reinterpret_cast<double*>(smem + carve(sizeof(double) * 3 * nr));
+        P.off_p = (unsigned)off; ps = reinterpret_cast<double*>(smem + carve(sizeof(double) * 3 * nr));
+        P.off_s = (unsigned)off; ss = reinterpret_cast<double*>(smem + carve(sizeof(double) * 3 * nr));
+        P.off_w = (unsigned)off; ws = reinterpret_cast<double*>(smem + carve(sizeof(double) * 3 * nr));
+        P.off_dinv = (unsigned)off; dinv = reinterpret_cast<float*>(smem + carve(sizeof(float) * 9 * nr));
+    } else {
+        rs = A.r + 3 * (size_t)r0; ps = A.p + 3 * (size_t)r0; ss = A.s + 3 * (size_t)r0; ws = A.w + 3 * (size_t)r0; dinv = A.dinv + 9 * (size_t)r0;
+    }
+    // window of u: as many rows around the own range as fit after the matrix slice (or, when the matrix does not fit, in
+    // what is left after the vectors); at least the own rows, else no window at all
+    const size_t mat_bytes = ((sizeof(int) * (size_t)nb + 15) & ~(size_t)15) + ((sizeof(float) * 9 * (size_t)nb + 15) & ~(size_t)15);
+    const size_t min_win = ((sizeof(double) * 3 * ((size_t)nr + 2) + 15) & ~(size_t)15);
+    const bool mat_fit = vec_fit && off + mat_bytes + min_win <= A.smem_bytes;
+    const int32_t* cols; const float* vals;
+    if (mat_fit) {
+        P.off_cols = (unsigned)off; int32_t* cs = reinterpret_cast<int32_t*>(smem + carve(sizeof(int) * (size_t)nb));
+        P.off_vals = (unsigned)off; float* vs = reinterpret_cast<float*>(smem + carve(sizeof(float) * 9 * (size_t)nb));
+        for (int i = tid; i < nb; i += PCG_THREADS) cs[i] = A.cols[b0 + i];
+        for (int i = tid; i < 9 * nb; i += PCG_THREADS) vs[i] = A.vals[9 * b0 + i];
+        cols = cs; vals = vs;
+    } else {
+        cols = A.cols + b0; vals = A.vals + 9 * b0;
+    }
+    int w0 = r0, nwin = 0;     // window = block rows [w0, w0 + nwin)
+    double* uwin = nullptr;
+    if (vec_fit && off + min_win <= A.smem_bytes) {
+        const int cap_rows = (int)(((size_t)A.smem_bytes - off) / (sizeof(double) * 3)) & ~1;   // even: 16 B granularity of the bulk copy
+        const int half = (cap_rows - nr) / 2;
+        w0 = max(0, r0 - half) & ~1;
+        int w1 = min(nbr, w0 + cap_rows);
+        nwin = w1 - w0;
+        P.off_win = (unsigned)off;
+        uwin = reinterpret_cast<double*>(smem + off);
+    }
+    const bool own_in_win = nwin > 0;   // by construction the window then contains [r0, r0 + nr)
+    // the bulk copy moves multiples of 16 B: with an odd row count (only possible at the very end of the vector) it also
+    // copies the 8 B of padding behind u (the buffer is allocated with that slack)
+    const unsigned win_bytes = (unsigned)((sizeof(double) * 3 * (size_t)nwin + 15) & ~(size_t)15);
+    for (int i = tid; i <= nr; i += PCG_THREADS) rp[i] = (int)(A.rows[r0 + i] - b0);
+    if (tid == 0) s_n_long = 0;
+    __syncthreads();
+    for (int i = tid; i < nr; i += PCG_THREADS)
+        if (rp[i + 1] - rp[i] > LONG_ROW) {
+            const int k = atomicAdd(&s_n_long, 1);
+            if (k < MAX_LONG_ROWS) s_long[k] = i;
+        }
+    __syncthreads();
+    const int n_long = min(s_n_long, MAX_LONG_ROWS);
+    P.r0 = r0; P.nr = nr; P.w0 = w0; P.nwin = nwin; P.n_long = n_long; P.own_in_win = own_in_win; P.win_bytes = win_bytes;
+    P.rp = rp; P.rs = rs; P.ps = ps; P.ss = ss; P.ws = ws; P.dinv = dinv; P.cols = cols; P.vals = vals; P.uwin = uwin;
+    P.s = s; P.bc2 = bc2; P.s_long = s_long; P.mbar = &s_mbar;
+    P.t_start = t_start; P.t_loaded = global_ns();
+    if (rp_fit && vec_fit && mat_fit && own_in_win) pcg_body<true>(A, P);
+    else pcg_body<false>(A, P);
 }
 
 int solve_pcg_internal(sb_context* ctx, double abs_tol, double rel_tol, int max_iter, int stop_on_indef,
@@ -620,6 +691,7 @@ int solve_pcg_internal(sb_context* ctx, double abs_tol, double rel_tol, int max_
         ctx->stage_calls[ST_PCG_SETUP]++;
         ctx->stage_calls[ST_PCG_C_SPMV] += P->h_result->c_spmv; ctx->stage_calls[ST_PCG_C_BAR] += P->h_result->c_bar;
         ctx->stage_calls[ST_PCG_C_RED] += P->h_result->c_red; ctx->stage_calls[ST_PCG_C_VEC] += P->h_result->c_vec;
+        ctx->stage_calls[ST_PCG_C_WIN] += P->h_result->c_win;
     }
     if (out_iterations) *out_iterations = P->h_result->it;
     if (out_ok) *out_ok = (P->h_result->done == 1) ? 1 : 0;
