@@ -26,6 +26,7 @@
 // The host launches once and reads one record.
 #include "internal.h"
 #include <algorithm>
+#include <cstdlib>
 
 namespace sb {
 
@@ -666,6 +667,12 @@ int solve_pcg_internal(sb_context* ctx, double abs_tol, double rel_tol, int max_
         cudaFuncAttributes fa;
         SB_CUDA(ctx, cudaFuncGetAttributes(&fa, k_pcg_solve));
         P->smem_bytes = (unsigned)(smem_max - (int)fa.sharedSizeBytes - 1024);
+        // test hook: SB_PCG_SMEM_LIMIT=<bytes> shrinks the budget so that small fixtures exercise the streaming (slices in global
+        // memory) and partial-window paths that million-tet scenes take
+        if (const char* lim = std::getenv("SB_PCG_SMEM_LIMIT")) {
+            const long v = std::atol(lim);
+            if (v >= 1024 && (unsigned)v < P->smem_bytes) P->smem_bytes = (unsigned)v;
+        }
         SB_CUDA(ctx, cudaFuncSetAttribute(k_pcg_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem_bytes));
         SB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pcg_solve, PCG_THREADS, P->smem_bytes));
         if (occ < 1) return fail(ctx, SB_ERR_CUDA, "sb_solve_pcg: the persistent kernel does not fit on an SM");

@@ -210,3 +210,36 @@ def test_newton_with_direct_llt():
     assert st.result == 0 and st.cg_iterations == 0
     assert st.last_residual < 1e-6 or st.n_evaluations > 1
     ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("limit", [1024, 4096, 16384])
+def test_pcg_streaming_paths(limit):
+    """The persistent PCG keeps matrix / vector slices in shared memory when they fit; SB_PCG_SMEM_LIMIT shrinks the budget so
+    that this small fixture takes the paths of scenes that do not fit (slices streamed from global memory, partial or no
+    window of the SpMV operand).  Same iterates as the resident path."""
+    import subprocess, sys, json, textwrap
+    code = textwrap.dedent("""
+        import sys, json, numpy as np
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        from golden_util import Golden, bind
+        from stark_b200 import capi
+        g = Golden("tetdrop_n5"); ctx = capi.Context(0)
+        bind(ctx, g, set(capi.kernel_names()))
+        ctx.eval("PGH"); ctx.assemble()
+        out = ctx.solve_pcg(g.meta["pcg_abs_tol"], g.meta["pcg_rel_tol"], 10000, True)
+        du = ctx.du()
+        print(json.dumps({"it": out["iterations"], "ok": out["ok"], "dg": out["du_dot_grad"], "du": du.tolist()}))
+    """) % (os.path.dirname(os.path.abspath(__file__)), os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    res = []
+    for lim in (None, limit):
+        env = dict(os.environ)
+        if lim is not None:
+            env["SB_PCG_SMEM_LIMIT"] = str(lim)
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        res.append(json.loads(out.stdout.strip().splitlines()[-1]))
+    a, b = res
+    assert a["ok"] and b["ok"] and a["it"] == b["it"]
+    da, db = np.array(a["du"]), np.array(b["du"])
+    assert np.abs(da - db).max() <= 1e-12 * np.abs(da).max()
