@@ -123,8 +123,8 @@ const std::vector<KernelInfo>& all_kernels()
         SB_KERNEL(EnergyDiscreteShells, "EnergyDiscreteShells"),
         SB_KERNEL(EnergyBendingFlat, "EnergyBendingFlat"),
         // hand-derived analytic tet kernels (tet_analytic.cuh) are the product path; the AD ones stay as cross-checks
-        KernelInfo { "EnergyTetStrain", 43, 12, 4, sbpot::EnergyTetStrain::DOF_SLOT, &launch_tet_analytic_pgh<true>, &launch_p<sbpot::EnergyTetStrain> },
-        KernelInfo { "EnergyTetStrain_Elasticity_Only", 40, 12, 4, sbpot::EnergyTetStrain_Elasticity_Only::DOF_SLOT, &launch_tet_analytic_pgh<false>, &launch_p<sbpot::EnergyTetStrain_Elasticity_Only> },
+        KernelInfo { "EnergyTetStrain", 43, 12, 4, sbpot::EnergyTetStrain::DOF_SLOT, &launch_tet_analytic_pgh<true>, &launch_tet_analytic_p<true> },
+        KernelInfo { "EnergyTetStrain_Elasticity_Only", 40, 12, 4, sbpot::EnergyTetStrain_Elasticity_Only::DOF_SLOT, &launch_tet_analytic_pgh<false>, &launch_tet_analytic_p<false> },
         SB_KERNEL(EnergyTetStrain, "EnergyTetStrain_AD"),
         SB_KERNEL(EnergyTetStrain_Elasticity_Only, "EnergyTetStrain_Elasticity_Only_AD"),
         SB_KERNEL(EnergyRigidBodyInertia_Linear, "EnergyRigidBodyInertia_Linear"),

@@ -26,6 +26,8 @@
 // The host launches once and reads one record.
 #include "internal.h"
 #include <algorithm>
+#include <vector>
+#include <cstdio>
 #include <cstdlib>
 
 namespace sb {
@@ -36,6 +38,8 @@ constexpr int PCG_THREADS = 1024;     // one CTA per SM
 constexpr int PCG_MAX_BLOCKS = 1024;  // upper bound of the cooperative grid (partial-sum arrays)
 constexpr int LANES_PER_ROW = 4;      // lanes cooperating on one block row of the SpMV
 constexpr int LONG_ROW = 96;          // rows with more blocks (rigid bodies in contact with many nodes) are swept by the whole CTA
+constexpr int MAX_SEGS = 128;         // segments of the long rows of one CTA
+constexpr int MIN_SEG = 16;           // blocks per segment (longer when a CTA holds more than MAX_SEGS * MIN_SEG long-row blocks)
 constexpr int MAX_LONG_ROWS = 32;     // per CTA; further long rows fall back to the 4-lane path
 
 struct PcgResult {
@@ -53,7 +57,8 @@ struct PcgArgs {
     const double* grad;
     float* dinv;                    // global fallbacks of the per-CTA slices
     double *x, *r, *p, *s, *w;
-    double* u;                      // preconditioned residual, the one vector every CTA reads
+    double* u;                      // preconditioned residual, the one vector every CTA reads (compact: the TMA window source)
+    double* u4;                     // the same, one 32-byte (x, y, z, 0) record per block row: far gathers take one request
     double* du;
     double* part;                   // 3 x PCG_MAX_BLOCKS partial sums
     int* rp_scratch;                // [nbr + grid + 1] local row pointers of slices whose row pointers do not fit in shared memory
@@ -65,10 +70,11 @@ struct PcgArgs {
     unsigned long long nnzb;
     unsigned smem_bytes;            // dynamic shared memory of the launch
     int instrument;
+    long long* dbg;                 // [5 x grid + 2] per-CTA cycle counters (SB_PCG_DUMP diagnostics, else null)
 };
 
 struct Pcg {
-    DevBuf<double> r, p, s, w, u, x;
+    DevBuf<double> r, p, s, w, u, u4, x;
     DevBuf<float> dinv;
     DevBuf<double> part;
     DevBuf<int> rp_scratch;
@@ -92,7 +98,7 @@ void pcg_destroy(sb_context* ctx)
 {
     Pcg* P = ctx->pcg;
     if (!P) return;
-    P->r.release(); P->p.release(); P->s.release(); P->w.release(); P->u.release(); P->x.release(); P->dinv.release(); P->part.release(); P->rp_scratch.release();
+    P->r.release(); P->p.release(); P->s.release(); P->w.release(); P->u.release(); P->u4.release(); P->x.release(); P->dinv.release(); P->part.release(); P->rp_scratch.release();
     if (P->d_barrier) cudaFree(P->d_barrier);
     if (P->d_result) cudaFree(P->d_result);
     if (P->h_result) cudaFreeHost(P->h_result);
@@ -254,6 +260,7 @@ struct PcgPlan {
     unsigned off_rp, off_r, off_p, off_s, off_w, off_dinv, off_cols, off_vals, off_win;   // byte offsets in pcg_smem (FAST)
     int* rp; double *rs, *ps, *ss, *ws; float* dinv; const int32_t* cols; const float* vals; double* uwin;   // generic pointers
     double* s; double* bc2; int* s_long; unsigned long long* mbar;
+    int n_seg; int *s_seg_j0, *s_seg_j1, *s_seg_first; double* s_seg_y;
     unsigned long long t_start, t_loaded;
 };
 
@@ -271,6 +278,9 @@ __device__ __forceinline__ void pcg_body(const PcgArgs& A, const PcgPlan& P)
     double* bc2 = P.bc2;
     double& bc = bc2[0];
     int* s_long = P.s_long;
+    const int n_seg = P.n_seg;
+    const int* s_seg_j0 = P.s_seg_j0; const int* s_seg_j1 = P.s_seg_j1; const int* s_seg_first = P.s_seg_first;
+    double* s_seg_y = P.s_seg_y;
     unsigned long long& s_mbar = *P.mbar;
     const int r0 = P.r0, nr = P.nr, w0 = P.w0, nwin = P.nwin, n_long = P.n_long;
     const bool own_in_win = P.own_in_win;
@@ -292,6 +302,9 @@ __device__ __forceinline__ void pcg_body(const PcgArgs& A, const PcgPlan& P)
         return false;
     };
     double* ug = A.u + 3 * (size_t)r0;                           // own slice of the global u
+    auto store_u4 = [&](int br, double z0, double z1, double z2) {   // padded copy for the far gathers
+        asm volatile("st.global.cg.v4.f64 [%0], {%1, %2, %3, %4};" :: "l"(A.u4 + 4 * (size_t)br), "d"(z0), "d"(z1), "d"(z2), "d"(0.0) : "memory");
+    };
     const double* uo_win = own_in_win ? uwin + 3 * (size_t)(r0 - w0) : nullptr;
     auto uo = [&](int i) -> double { return own_in_win ? uo_win[i] : __ldcg(ug + i); };   // own slice of u as this CTA reads it
     double* xg = A.x + 3 * (size_t)r0;                           // x is only ever touched by its owner thread
@@ -300,7 +313,12 @@ __device__ __forceinline__ void pcg_body(const PcgArgs& A, const PcgPlan& P)
     const int win_lo = 3 * w0, win_hi = 3 * (w0 + nwin);
     auto gather3 = [&](int c, double& a0, double& a1, double& a2) {
         if (c >= win_lo && c < win_hi) { const double* q = uwin + (c - win_lo); a0 = q[0]; a1 = q[1]; a2 = q[2]; }
-        else { a0 = __ldcg(A.u + c); a1 = __ldcg(A.u + c + 1); a2 = __ldcg(A.u + c + 2); }
+        else {
+            // far column (hex-centre node, rigid body): ONE 32-byte request to the padded copy of u.  The SM's miss path
+            // takes about two cycles per request whatever its size, so three 8-byte loads cost three times as much
+            double pad;
+            asm volatile("ld.global.cg.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a0), "=d"(a1), "=d"(a2), "=d"(pad) : "l"(A.u4 + 4 * (size_t)(c / 3)));
+        }
     };
     unsigned win_phase = 0;
     // pull the window of u (all CTAs have published their slices: call after a grid barrier)
@@ -319,32 +337,39 @@ __device__ __forceinline__ void pcg_body(const PcgArgs& A, const PcgPlan& P)
     constexpr int rows_per_pass = PCG_THREADS / LANES_PER_ROW;
     auto spmv = [&]() -> double {
         double wu = 0.0;
-        for (int base = 0; base < nr; base += rows_per_pass) {
-            const int lr = base + tid / LANES_PER_ROW;
+        // groups of LANES_PER_ROW lanes take one row each; the segments of the long rows (rigid bodies in contact with many
+        // nodes) queue behind the rows as further groups, so a 700-block row costs a few trips of idle groups instead of a
+        // sweep and a 1024-thread reduction by the whole CTA
+        const int n_groups = nr + n_seg;
+        for (int base = 0; base < n_groups; base += rows_per_pass) {
+            const int g = base + tid / LANES_PER_ROW;
             double y0 = 0.0, y1 = 0.0, y2 = 0.0;
-            const bool swept = (lr < nr) && is_swept(lr);
-            if (lr < nr && !swept) {
-                const int j1 = rp[lr + 1];
-                // four blocks per trip: their gathers of u (shared-memory window, or L2 for far columns -- hex-centre nodes,
-                // rigid bodies) are all issued before the first product, so a row costs one memory round trip, not one per block
-                constexpr int U = 4;
-                for (int j = rp[lr] + lane; j < j1; j += U * LANES_PER_ROW) {
-                    double a[U][3];
+            int j0 = 0, j1 = 0;
+            bool is_row = false, is_seg = false;
+            if (g < nr) {
+                if (!is_swept(g)) { j0 = rp[g]; j1 = rp[g + 1]; is_row = true; }
+            } else if (g < n_groups) {
+                j0 = s_seg_j0[g - nr]; j1 = s_seg_j1[g - nr]; is_seg = true;
+            }
+            // four blocks per trip: their gathers of u (shared-memory window, or L2 for far columns -- hex-centre nodes,
+            // rigid bodies) are all issued before the first product, so a row costs one memory round trip, not one per block
+            constexpr int U = 4;
+            for (int j = j0 + lane; j < j1; j += U * LANES_PER_ROW) {
+                double a[U][3];
 #pragma unroll
-                    for (int t = 0; t < U; t++) {
-                        const int jj = j + t * LANES_PER_ROW;
-                        a[t][0] = 0.0; a[t][1] = 0.0; a[t][2] = 0.0;
-                        if (jj < j1) gather3(cols[jj], a[t][0], a[t][1], a[t][2]);
-                    }
+                for (int t = 0; t < U; t++) {
+                    const int jj = j + t * LANES_PER_ROW;
+                    a[t][0] = 0.0; a[t][1] = 0.0; a[t][2] = 0.0;
+                    if (jj < j1) gather3(cols[jj], a[t][0], a[t][1], a[t][2]);
+                }
 #pragma unroll
-                    for (int t = 0; t < U; t++) {
-                        const int jj = j + t * LANES_PER_ROW;
-                        if (jj < j1) {
-                            const float* m = vals + 9 * (size_t)jj;   // column-major 3x3
-                            y0 += (double)m[0] * a[t][0] + (double)m[3] * a[t][1] + (double)m[6] * a[t][2];
-                            y1 += (double)m[1] * a[t][0] + (double)m[4] * a[t][1] + (double)m[7] * a[t][2];
-                            y2 += (double)m[2] * a[t][0] + (double)m[5] * a[t][1] + (double)m[8] * a[t][2];
-                        }
+                for (int t = 0; t < U; t++) {
+                    const int jj = j + t * LANES_PER_ROW;
+                    if (jj < j1) {
+                        const float* m = vals + 9 * (size_t)jj;   // column-major 3x3
+                        y0 += (double)m[0] * a[t][0] + (double)m[3] * a[t][1] + (double)m[6] * a[t][2];
+                        y1 += (double)m[1] * a[t][0] + (double)m[4] * a[t][1] + (double)m[7] * a[t][2];
+                        y2 += (double)m[2] * a[t][0] + (double)m[5] * a[t][1] + (double)m[8] * a[t][2];
                     }
                 }
             }
@@ -353,27 +378,24 @@ __device__ __forceinline__ void pcg_body(const PcgArgs& A, const PcgPlan& P)
                 y1 += __shfl_down_sync(0xffffffffu, y1, o, LANES_PER_ROW);
                 y2 += __shfl_down_sync(0xffffffffu, y2, o, LANES_PER_ROW);
             }
-            if (lane == 0 && lr < nr && !swept) {
-                ws[3 * lr] = y0; ws[3 * lr + 1] = y1; ws[3 * lr + 2] = y2;
-                wu += uo(3 * lr) * y0 + uo(3 * lr + 1) * y1 + uo(3 * lr + 2) * y2;
+            if (lane == 0 && is_row) {
+                ws[3 * g] = y0; ws[3 * g + 1] = y1; ws[3 * g + 2] = y2;
+                wu += uo(3 * g) * y0 + uo(3 * g + 1) * y1 + uo(3 * g + 2) * y2;
+            }
+            if (lane == 0 && is_seg) {
+                s_seg_y[3 * (g - nr)] = y0; s_seg_y[3 * (g - nr) + 1] = y1; s_seg_y[3 * (g - nr) + 2] = y2;
             }
         }
-        // long rows: one block per thread and trip, block-wide reduction (fixed tree: deterministic)
-        for (int k = 0; k < n_long; k++) {
-            const int lr = s_long[k];
-            double y0 = 0.0, y1 = 0.0, y2 = 0.0;
-            for (int j = rp[lr] + tid; j < rp[lr + 1]; j += PCG_THREADS) {
-                const float* m = vals + 9 * (size_t)j;
-                double a0, a1, a2;
-                gather3(cols[j], a0, a1, a2);
-                y0 += (double)m[0] * a0 + (double)m[3] * a1 + (double)m[6] * a2;
-                y1 += (double)m[1] * a0 + (double)m[4] * a1 + (double)m[7] * a2;
-                y2 += (double)m[2] * a0 + (double)m[5] * a1 + (double)m[8] * a2;
-            }
-            y0 = block_sum(y0, s); y1 = block_sum(y1, s); y2 = block_sum(y2, s);
-            if (tid == 0) {
-                ws[3 * lr] = y0; ws[3 * lr + 1] = y1; ws[3 * lr + 2] = y2;
-                wu += uo(3 * lr) * y0 + uo(3 * lr + 1) * y1 + uo(3 * lr + 2) * y2;
+        // long rows: segment sums added in segment order (deterministic)
+        if (n_long) {
+            __syncthreads();
+            if (tid < 3 * n_long) {
+                const int q = tid / 3, c = tid % 3;
+                double t = 0.0;
+                for (int k = s_seg_first[q]; k < s_seg_first[q + 1]; k++) t += s_seg_y[3 * k + c];
+                const int lr = s_long[q];
+                ws[3 * lr + c] = t;
+                wu += uo(3 * lr + c) * t;
             }
         }
         return wu;
@@ -419,6 +441,7 @@ __device__ __forceinline__ void pcg_body(const PcgArgs& A, const PcgPlan& P)
             for (int c = 0; c < 3; c++) { xg[3 * lr + c] = 0.0; ps[3 * lr + c] = 0.0; ss[3 * lr + c] = 0.0; }
             rs[3 * lr] = g0; rs[3 * lr + 1] = g1; rs[3 * lr + 2] = g2;
             __stcg(ug + 3 * lr, z0); __stcg(ug + 3 * lr + 1, z1); __stcg(ug + 3 * lr + 2, z2);
+            store_u4(r0 + lr, z0, z1, z2);
             bb += g0 * g0 + g1 * g1 + g2 * g2;
             ru += g0 * z0 + g1 * z1 + g2 * z2;
         }
@@ -474,6 +497,7 @@ __device__ __forceinline__ void pcg_body(const PcgArgs& A, const PcgPlan& P)
                 }
                 apply_dinv(dinv + 9 * lr, q[0], q[1], q[2], z0, z1, z2);
                 __stcg(ug + 3 * lr, z0); __stcg(ug + 3 * lr + 1, z1); __stcg(ug + 3 * lr + 2, z2);
+                store_u4(r0 + lr, z0, z1, z2);
                 rr += q[0] * q[0] + q[1] * q[1] + q[2] * q[2];
                 ru += q[0] * z0 + q[1] * z1 + q[2] * z2;
             }
@@ -529,6 +553,11 @@ __device__ __forceinline__ void pcg_body(const PcgArgs& A, const PcgPlan& P)
         if (tid == 0) { __stcg(part0 + blockIdx.x, t0); __stcg(part1 + blockIdx.x, t1); }
     }
     grid_barrier(A.barrier, epoch);
+    if (A.dbg && tid == 0) {
+        const int G = gridDim.x;
+        A.dbg[blockIdx.x] = c_spmv; A.dbg[G + blockIdx.x] = c_bar + c_red; A.dbg[2 * G + blockIdx.x] = c_vec; A.dbg[3 * G + blockIdx.x] = c_win;
+        A.dbg[4 * G + blockIdx.x] = ((long long)nr << 32) | (unsigned)(rp[nr] - rp[0]);
+    }
     if (blockIdx.x == 0) {
         const double dg = all_partials(part0, s, &bc);
         const double mx = all_partials_max(part1, s, &bc);
@@ -551,6 +580,9 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_solve(const PcgArgs A)
     double& bc = bc2[0];
     __shared__ int s_range[2];
     __shared__ int s_long[MAX_LONG_ROWS];
+    __shared__ int s_seg_j0[MAX_SEGS], s_seg_j1[MAX_SEGS], s_seg_first[MAX_LONG_ROWS + 1];
+    __shared__ int s_n_seg;
+    __shared__ double s_seg_y[3 * MAX_SEGS];
     __shared__ int s_n_long;
     __shared__ __align__(8) unsigned long long s_mbar;
     const unsigned long long t_start = global_ns();
@@ -634,6 +666,23 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_solve(const PcgArgs A)
         }
     __syncthreads();
     const int n_long = min(s_n_long, MAX_LONG_ROWS);
+    // cut the listed long rows into segments of equal length (at most MAX_SEGS in all)
+    if (tid == 0) {
+        long long total = 0;
+        for (int q = 0; q < n_long; q++) total += rp[s_long[q] + 1] - rp[s_long[q]];
+        int seg_len = MIN_SEG;
+        if (n_long) seg_len = max(MIN_SEG, (int)((total + (MAX_SEGS - n_long) - 1) / (MAX_SEGS - n_long)));
+        int n = 0;
+        for (int q = 0; q < n_long; q++) {
+            s_seg_first[q] = n;
+            const int lr = s_long[q];
+            for (int j = rp[lr]; j < rp[lr + 1]; j += seg_len) { s_seg_j0[n] = j; s_seg_j1[n] = min(j + seg_len, rp[lr + 1]); n++; }
+        }
+        s_seg_first[n_long] = n;
+        s_n_seg = n;
+    }
+    __syncthreads();
+    P.n_seg = s_n_seg; P.s_seg_j0 = s_seg_j0; P.s_seg_j1 = s_seg_j1; P.s_seg_first = s_seg_first; P.s_seg_y = s_seg_y;
     P.r0 = r0; P.nr = nr; P.w0 = w0; P.nwin = nwin; P.n_long = n_long; P.own_in_win = own_in_win; P.win_bytes = win_bytes;
     P.rp = rp; P.rs = rs; P.ps = ps; P.ss = ss; P.ws = ws; P.dinv = dinv; P.cols = cols; P.vals = vals; P.uwin = uwin;
     P.s = s; P.bc2 = bc2; P.s_long = s_long; P.mbar = &s_mbar;
@@ -653,7 +702,7 @@ int solve_pcg_internal(sb_context* ctx, double abs_tol, double rel_tol, int max_
     Pcg* P = get(ctx);
     cudaStream_t st = ctx->stream;
     const int n = ctx->ndofs;
-    P->r.ensure(n); P->p.ensure(n); P->s.ensure(n); P->w.ensure(n); P->u.ensure(n + 2); P->x.ensure(n); P->dinv.ensure(9 * (size_t)nbr);
+    P->r.ensure(n); P->p.ensure(n); P->s.ensure(n); P->w.ensure(n); P->u.ensure(n + 2); P->u4.ensure(4 * (size_t)nbr); P->x.ensure(n); P->dinv.ensure(9 * (size_t)nbr);
     P->part.ensure(3 * PCG_MAX_BLOCKS);
     P->rp_scratch.ensure((size_t)nbr + PCG_MAX_BLOCKS + 1);
     ctx->du.ensure(n);
@@ -680,17 +729,34 @@ int solve_pcg_internal(sb_context* ctx, double abs_tol, double rel_tol, int max_
     }
     PcgArgs A;
     A.rows = rows; A.cols = cols; A.vals = vals; A.grad = ctx->grad.p; A.dinv = P->dinv.p;
-    A.x = P->x.p; A.r = P->r.p; A.p = P->p.p; A.s = P->s.p; A.w = P->w.p; A.u = P->u.p; A.du = ctx->du.p;
+    A.x = P->x.p; A.r = P->r.p; A.p = P->p.p; A.s = P->s.p; A.w = P->w.p; A.u = P->u.p; A.u4 = P->u4.p; A.du = ctx->du.p;
     A.part = P->part.p; A.rp_scratch = P->rp_scratch.p; A.barrier = P->d_barrier; A.result = P->d_result;
     A.nnzb = nnzb; A.smem_bytes = P->smem_bytes; A.instrument = ctx->profile ? 1 : 0;
     A.nbr = nbr; A.abs_tol = abs_tol; A.rel_tol = rel_tol; A.max_iter = max_iter; A.stop_on_indef = stop_on_indef;
     SB_CUDA(ctx, cudaMemsetAsync(P->d_barrier, 0, sizeof(unsigned), st));
+    // SB_PCG_DUMP=1: per-CTA cycle counters of every solve on stderr (load-balance diagnostics)
+    static const bool dump = std::getenv("SB_PCG_DUMP") != nullptr;
+    static long long* d_dbg = nullptr;
+    if (dump && !d_dbg) cudaMalloc(&d_dbg, (5 * PCG_MAX_BLOCKS + 8) * sizeof(long long));
+    if (dump) cudaMemsetAsync(d_dbg, 0, (5 * PCG_MAX_BLOCKS + 8) * sizeof(long long), st);
+    A.dbg = dump ? d_dbg : nullptr;
+    if (dump) A.instrument = 1;
     void* args[] = {(void*)&A};
     SB_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_pcg_solve, dim3(P->grid), dim3(PCG_THREADS), args, P->smem_bytes, st));
     ctx->launches += 1;
     SB_CUDA(ctx, cudaMemcpyAsync(P->h_result, P->d_result, sizeof(PcgResult), cudaMemcpyDeviceToHost, st));
     SB_CUDA(ctx, cudaStreamSynchronize(st));
     SB_CUDA(ctx, cudaGetLastError());
+    if (dump) {
+        const int G = P->grid;
+        std::vector<long long> h(5 * (size_t)G + 8);
+        cudaMemcpy(h.data(), d_dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        const int its = P->h_result->it > 0 ? P->h_result->it : 1;
+        fprintf(stderr, "PCGDUMP its=%d\n", P->h_result->it);
+        for (int b = 0; b < G; b++)
+            fprintf(stderr, "PCGDUMP cta=%d rows=%lld blocks=%lld spmv=%lld wait=%lld vec=%lld win=%lld\n", b, h[4 * G + b] >> 32, h[4 * G + b] & 0xffffffffll,
+                    h[b] / its, h[G + b] / its, h[2 * G + b] / its, h[3 * G + b] / its);
+    }
     if (ctx->profile) {
         ctx->stage_calls[ST_CG_ITERATIONS] += P->h_result->it;
         ctx->stage_ms[ST_CG_ITERATIONS] += 1e-6 * (double)(P->h_result->t_end - P->h_result->t_loop);          // iterations + final reduction

@@ -402,6 +402,144 @@ __global__ void __launch_bounds__(TET_THREADS) k_tet_analytic(const __grid_const
     if (store_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+// Energy only (line-search evaluations): the same expressions as above up to Psi, one thread per element, nothing staged.
+// Reads 16 B of connectivity per tet plus the gathered node data (L2-resident), writes 8 B.
+template<bool COMPLETE, bool CANON>
+__global__ void __launch_bounds__(128) k_tet_energy(const __grid_constant__ TetParams P)
+{
+    constexpr int NIN = COMPLETE ? 43 : 40;
+    const EvalArgs& a = P.a;
+    const int e = blockIdx.x * 128 + threadIdx.x;
+    if (e >= a.n_elem) return;
+    const int32_t* ce = a.conn + (size_t)e * a.conn_stride;
+    auto in = [&](int slot) -> double {
+        const FetchSlot& fs = P.slot[slot];
+        const int row = (fs.conn_col >= 0) ? ce[fs.conn_col] : 0;
+        return fs.base[(size_t)row * fs.stride + fs.off];
+    };
+    double vv[12], xx[12], XX[12];
+    if (CANON) {
+        int node[4];
+#pragma unroll
+        for (int n = 0; n < 4; n++) node[n] = ce[P.slot[3 * n].conn_col];
+        const double* bv = P.slot[0].base + P.slot[0].off;
+        const double* bx = P.slot[12].base + P.slot[12].off;
+        const double* bX = P.slot[24].base + P.slot[24].off;
+        const int sv = P.slot[0].stride, sx = P.slot[12].stride, sX = P.slot[24].stride;
+#pragma unroll
+        for (int n = 0; n < 4; n++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                vv[3 * n + c] = bv[(size_t)node[n] * sv + c];
+                xx[3 * n + c] = bx[(size_t)node[n] * sx + c];
+                XX[3 * n + c] = bX[(size_t)node[n] * sX + c];
+            }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 12; k++) { vv[k] = in(k); xx[k] = in(12 + k); XX[k] = in(24 + k); }
+    }
+    const double dt = in(NIN - 1), scale = in(36), ym = in(37), nu = in(38);
+    double G[12];
+    double vol;
+    {
+#pragma unroll
+        for (int k = 0; k < 12; k++) XX[k] = scale * XX[k];
+        double DX[9];
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+#pragma unroll
+            for (int r = 0; r < 3; r++) DX[3 * r + c] = XX[3 * (c + 1) + r] - XX[r];
+        const double c00 = DX[4] * DX[8] - DX[5] * DX[7], c01 = DX[5] * DX[6] - DX[3] * DX[8], c02 = DX[3] * DX[7] - DX[4] * DX[6];
+        const double det = DX[0] * c00 + DX[1] * c01 + DX[2] * c02;
+        const double rd = 1.0 / det;
+        double B[9];
+        B[0] = c00 * rd; B[1] = (DX[2] * DX[7] - DX[1] * DX[8]) * rd; B[2] = (DX[1] * DX[5] - DX[2] * DX[4]) * rd;
+        B[3] = c01 * rd; B[4] = (DX[0] * DX[8] - DX[2] * DX[6]) * rd; B[5] = (DX[2] * DX[3] - DX[0] * DX[5]) * rd;
+        B[6] = c02 * rd; B[7] = (DX[1] * DX[6] - DX[0] * DX[7]) * rd; B[8] = (DX[0] * DX[4] - DX[1] * DX[3]) * rd;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            G[c] = -(B[c] + B[3 + c] + B[6 + c]);
+            G[3 + c] = B[c]; G[6 + c] = B[3 + c]; G[9 + c] = B[6 + c];
+        }
+        vol = det / 6.0;
+    }
+    double F[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) F[k] = 0.0;
+#pragma unroll
+    for (int n = 0; n < 4; n++)
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            const double x = xx[3 * n + r] + dt * vv[3 * n + r];
+#pragma unroll
+            for (int c = 0; c < 3; c++) F[3 * r + c] += x * G[3 * n + c];
+        }
+    double Ic = 0.0;
+#pragma unroll
+    for (int k = 0; k < 9; k++) Ic += F[k] * F[k];
+    const double J = F[0] * (F[4] * F[8] - F[5] * F[7]) + F[1] * (F[5] * F[6] - F[3] * F[8]) + F[2] * (F[3] * F[7] - F[4] * F[6]);
+    const double mu = ym / (2.0 * (1.0 + nu));
+    const double lambda = (ym * nu) / ((1.0 + nu) * (1.0 - 2.0 * nu));
+    const double mu_ = 4.0 / 3.0 * mu, lambda_ = lambda + 5.0 / 6.0 * mu;
+    const double alpha = 1.0 + mu_ / lambda_ - mu_ / (4.0 * lambda_);
+    double Psi = 0.5 * mu_ * (Ic - 3.0) + 0.5 * lambda_ * (J - alpha) * (J - alpha) - 0.5 * mu_ * log(Ic + 1.0);
+    if (COMPLETE) {
+        const double limit = in(39), k_sl = in(40), damping = in(41);
+        double E1[6];
+        {
+            int q = 0;
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int j = i; j < 3; j++) {
+                    E1[q] = 0.5 * (F[i] * F[j] + F[3 + i] * F[3 + j] + F[6 + i] * F[6 + j] - (i == j ? 1.0 : 0.0));
+                    q++;
+                }
+        }
+        if (damping != 0.0) {
+            double F0[9];
+#pragma unroll
+            for (int k = 0; k < 9; k++) F0[k] = 0.0;
+#pragma unroll
+            for (int n = 0; n < 4; n++)
+#pragma unroll
+                for (int r = 0; r < 3; r++)
+#pragma unroll
+                    for (int c = 0; c < 3; c++) F0[3 * r + c] += xx[3 * n + r] * G[3 * n + c];
+            const double k2 = damping / (dt * dt);
+            int q = 0;
+            double acc = 0.0;
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int j = i; j < 3; j++) {
+                    const double e0 = 0.5 * (F0[i] * F0[j] + F0[3 + i] * F0[3 + j] + F0[6 + i] * F0[6 + j] - (i == j ? 1.0 : 0.0));
+                    const double D = E1[q] - e0;
+                    acc += (i == j ? 1.0 : 2.0) * D * D;
+                    q++;
+                }
+            Psi += 0.5 * k2 * acc;
+        }
+        const double m = (E1[0] + E1[3] + E1[5]) / 3.0;
+        const double dv[6] = {E1[0] - m, E1[1], E1[2], E1[3] - m, E1[4], E1[5] - m};
+        const double dn = sqrt(dv[0] * dv[0] + dv[3] * dv[3] + dv[5] * dv[5] + 2.0 * (dv[1] * dv[1] + dv[2] * dv[2] + dv[4] * dv[4]));
+        const double dl = m + sqrt(2.0 / 3.0) * dn - limit;
+        if (dl > 0.0) Psi += k_sl * dl * dl * dl / 3.0;
+    }
+    a.E_elem[e] = vol * Psi;
+}
+
+template<bool COMPLETE> static void launch_tet_analytic_p(const EvalArgs& a, cudaStream_t s)
+{
+    TetParams P;
+    P.a = a;
+    const int nin = COMPLETE ? 43 : 40;
+    for (int i = 0; i < nin; i++) P.slot[i] = a.slots_host[i];
+    const int grid = (a.n_elem + 127) / 128;
+    if (tet_layout_is_canonical(P.slot)) k_tet_energy<COMPLETE, true><<<grid, 128, 0, s>>>(P);
+    else k_tet_energy<COMPLETE, false><<<grid, 128, 0, s>>>(P);
+}
+
 template<bool COMPLETE> static void launch_tet_analytic_pgh(const EvalArgs& a, cudaStream_t s)
 {
     static bool configured = false;

@@ -120,10 +120,13 @@ def test_tet_analytic_rare_terms_match_ad(case):
         ctx = capi.Context(0)
         h = bind(ctx, g, set(capi.kernel_names()), rename=rename, override=override, split_fetch=split if rename is None else None)
         E, res = ctx.eval("PGH")
-        out.append((E, ctx.grad(), ctx.element_output(h[idx])))
+        out.append((E, ctx.grad(), ctx.element_output(h[idx]), ctx.eval("P")))
         ctx.close()
-    (E1, g1, a), (E2, g2, b) = out
+    (E1, g1, a, P1), (E2, g2, b, P2) = out
     assert abs(E1 - E2) <= 1e-12 * abs(E2)
+    # the energy-only kernel of the line search (k_tet_energy) against the AD energy, and against its own P+G+H kernel
+    assert abs(P1 - P2) <= 1e-12 * abs(P2)
+    assert abs(P1 - E1) <= 1e-13 * abs(E1)
     assert np.abs(g1 - g2).max() <= 1e-11 * np.abs(g2).max()
     np.testing.assert_allclose(a[:, 0], b[:, 0], rtol=1e-11, atol=1e-11 * np.abs(b[:, 0]).max())
     gs = np.abs(b[:, 1:13]).max(axis=1, keepdims=True)
