@@ -75,22 +75,34 @@ __global__ void __launch_bounds__(Geo<Pot>::BLOCK) k_eval_pgh(const EvalArgs a)
     if (p == 0) a.E_elem[e] = r.v;
 }
 
+// energy only (line-search evaluations): the same cooperative gather (all loads of a CTA's elements in flight together --
+// a thread walking its own fetch table serially makes a 100-element contact table cost 25 us of dependent loads), then one
+// thread per element
+template<class Pot> struct GeoP {
+    static constexpr int BY_SMEM = (40 * 1024) / (8 * Pot::N_IN);
+    static constexpr int EP = BY_SMEM >= 128 ? 128 : (BY_SMEM / 32) * 32;   // elements per CTA
+    static_assert(EP >= 32, "fetch table too long for the shared-memory gather");
+};
 template<class Pot>
 __global__ void __launch_bounds__(128) k_eval_p(const EvalArgs a)
 {
-    constexpr int NIN = Pot::N_IN;
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= a.n_elem) return;
-    double in[NIN];
-    const int32_t* ce = a.conn + (size_t)e * a.conn_stride;
-#pragma unroll 1
-    for (int slot = 0; slot < NIN; slot++) {
-        const FetchSlot fs = a.slots[slot];
-        const int row = (fs.conn_col >= 0) ? ce[fs.conn_col] : 0;
-        in[slot] = fs.base[(size_t)row * fs.stride + fs.off];
+    constexpr int NIN = Pot::N_IN, EP = GeoP<Pot>::EP;
+    __shared__ double s_in[EP * NIN];
+    const int e_base = blockIdx.x * EP;
+    for (int idx = threadIdx.x; idx < EP * NIN; idx += 128) {
+        const int el = idx / NIN, slot = idx - el * NIN;
+        const int e = e_base + el;
+        if (e < a.n_elem) {
+            const FetchSlot fs = a.slots[slot];
+            const int row = (fs.conn_col >= 0) ? a.conn[(size_t)e * a.conn_stride + fs.conn_col] : 0;
+            s_in[idx] = fs.base[(size_t)row * fs.stride + fs.off];
+        }
     }
+    __syncthreads();
+    const int e = e_base + threadIdx.x;
+    if (threadIdx.x >= EP || e >= a.n_elem) return;
     sbad::Seed<double> seed;
-    a.E_elem[e] = Pot::template energy<double>(in, seed);
+    a.E_elem[e] = Pot::template energy<double>(s_in + threadIdx.x * NIN, seed);
 }
 
 template<class Pot> static void launch_pgh(const EvalArgs& a, cudaStream_t s)
@@ -100,7 +112,7 @@ template<class Pot> static void launch_pgh(const EvalArgs& a, cudaStream_t s)
 }
 template<class Pot> static void launch_p(const EvalArgs& a, cudaStream_t s)
 {
-    const int grid = (a.n_elem + 127) / 128;
+    const int grid = (a.n_elem + GeoP<Pot>::EP - 1) / GeoP<Pot>::EP;
     k_eval_p<Pot><<<grid, 128, 0, s>>>(a);
 }
 
