@@ -189,8 +189,20 @@ int eval_internal(sb_context* ctx, int mode, double* out_E, double* out_grad_inf
         SB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
     }
     int next_side = 0;
+    // energy-only evaluation: every small potential goes into one multi-potential launch on a side stream
+    MultiPArgs M;
+    M.n = 0; M.pad = 0;
+    int multi_ctas = 0;
+    const bool use_multi = (mode == SB_EVAL_P) && n_small >= 2;
     for (auto& p : ctx->potentials) {
         if (p.n_elem == 0) continue;
+        if (use_multi && p.n_elem < SMALL && p.k->p_kind >= 0 && M.n < MULTI_P_MAX) {
+            MultiPItem& it = M.it[M.n++];
+            it.slots = p.slots.p; it.conn = p.conn_ext ? p.conn_ext : p.conn.p; it.E_elem = ctx->E_elem.p + p.E_off;
+            it.conn_stride = p.conn_stride; it.n_elem = p.n_elem; it.kind = p.k->p_kind; it.cta0 = multi_ctas;
+            multi_ctas += multi_p_ctas(p.k->p_kind, p.n_elem);
+            continue;
+        }
         EvalArgs a;
         a.slots = p.slots.p;
         a.slots_host = p.slots_host.data();
@@ -211,6 +223,12 @@ int eval_internal(sb_context* ctx, int mode, double* out_E, double* out_grad_inf
         }
         if (mode == SB_EVAL_PGH) p.k->launch_pgh(a, st);
         else p.k->launch_p(a, st);
+        ctx->launches++;
+    }
+    if (M.n > 0) {
+        const int k = next_side++ % sb_context::N_SIDE;
+        if (!side_used[k]) { SB_CUDA(ctx, cudaStreamWaitEvent(ctx->side[k], ctx->ev_fork, 0)); side_used[k] = true; }
+        launch_p_multi(M, multi_ctas, ctx->side[k]);
         ctx->launches++;
     }
     for (int k = 0; k < sb_context::N_SIDE; k++)

@@ -78,31 +78,38 @@ __global__ void __launch_bounds__(Geo<Pot>::BLOCK) k_eval_pgh(const EvalArgs a)
 // energy only (line-search evaluations): the same cooperative gather (all loads of a CTA's elements in flight together --
 // a thread walking its own fetch table serially makes a 100-element contact table cost 25 us of dependent loads), then one
 // thread per element
+constexpr int EVAL_P_SMEM_DOUBLES = 5120;   // 40 KB of gathered inputs per CTA
 template<class Pot> struct GeoP {
-    static constexpr int BY_SMEM = (40 * 1024) / (8 * Pot::N_IN);
+    static constexpr int BY_SMEM = EVAL_P_SMEM_DOUBLES / Pot::N_IN;
     static constexpr int EP = BY_SMEM >= 128 ? 128 : (BY_SMEM / 32) * 32;   // elements per CTA
     static_assert(EP >= 32, "fetch table too long for the shared-memory gather");
 };
 template<class Pot>
-__global__ void __launch_bounds__(128) k_eval_p(const EvalArgs a)
+__device__ __forceinline__ void eval_p_body(const FetchSlot* __restrict__ slots, const int32_t* __restrict__ conn, int conn_stride, int n_elem,
+                                            double* __restrict__ E_elem, int cta, double* s_in)
 {
     constexpr int NIN = Pot::N_IN, EP = GeoP<Pot>::EP;
-    __shared__ double s_in[EP * NIN];
-    const int e_base = blockIdx.x * EP;
+    const int e_base = cta * EP;
     for (int idx = threadIdx.x; idx < EP * NIN; idx += 128) {
         const int el = idx / NIN, slot = idx - el * NIN;
         const int e = e_base + el;
-        if (e < a.n_elem) {
-            const FetchSlot fs = a.slots[slot];
-            const int row = (fs.conn_col >= 0) ? a.conn[(size_t)e * a.conn_stride + fs.conn_col] : 0;
+        if (e < n_elem) {
+            const FetchSlot fs = slots[slot];
+            const int row = (fs.conn_col >= 0) ? conn[(size_t)e * conn_stride + fs.conn_col] : 0;
             s_in[idx] = fs.base[(size_t)row * fs.stride + fs.off];
         }
     }
     __syncthreads();
     const int e = e_base + threadIdx.x;
-    if (threadIdx.x >= EP || e >= a.n_elem) return;
+    if (threadIdx.x >= EP || e >= n_elem) return;
     sbad::Seed<double> seed;
-    a.E_elem[e] = Pot::template energy<double>(s_in + threadIdx.x * NIN, seed);
+    E_elem[e] = Pot::template energy<double>(s_in + threadIdx.x * NIN, seed);
+}
+template<class Pot>
+__global__ void __launch_bounds__(128) k_eval_p(const EvalArgs a)
+{
+    __shared__ double s_in[GeoP<Pot>::EP * Pot::N_IN];
+    eval_p_body<Pot>(a.slots, a.conn, a.conn_stride, a.n_elem, a.E_elem, blockIdx.x, s_in);
 }
 
 template<class Pot> static void launch_pgh(const EvalArgs& a, cudaStream_t s)
@@ -116,12 +123,116 @@ template<class Pot> static void launch_p(const EvalArgs& a, cudaStream_t s)
     k_eval_p<Pot><<<grid, 128, 0, s>>>(a);
 }
 
+
+// ---- all small potentials of one energy-only evaluation in ONE launch ----
+// A line-search evaluation of a contact scene touches a dozen potentials with a few hundred elements each; launched one by
+// one (even spread over side streams) the evaluation is bound by the host's launch rate.  Here the CTA looks up which
+// potential its block index falls into and runs that potential's body.
+#define SB_ALL_POTS(X) \
+    X(EnergyLumpedInertia) \
+    X(EnergyPrescribedPositions) \
+    X(EnergySegmentStrain) \
+    X(EnergySegmentStrain_Elasticity_Only) \
+    X(EnergyTriangleStrain) \
+    X(EnergyTriangleStrain_Elasticity_Only) \
+    X(EnergyDiscreteShells) \
+    X(EnergyBendingFlat) \
+    X(EnergyTetStrain) \
+    X(EnergyTetStrain_Elasticity_Only) \
+    X(EnergyRigidBodyInertia_Linear) \
+    X(EnergyRigidBodyInertia_Angular) \
+    X(rb_constraint_global_points) \
+    X(rb_constraint_global_directions) \
+    X(rb_constraint_points) \
+    X(rb_constraint_point_on_axis) \
+    X(rb_constraint_distances) \
+    X(rb_constraint_distance_limits) \
+    X(rb_constraint_directions) \
+    X(rb_constraint_angle_limits) \
+    X(rb_constraint_damped_spring) \
+    X(rb_constraint_linear_velocity) \
+    X(rb_constraint_angular_velocity) \
+    X(EnergyAttachments_d_d_p_p) \
+    X(EnergyAttachments_d_d_p_e) \
+    X(EnergyAttachments_d_d_p_t) \
+    X(EnergyAttachments_d_d_e_e) \
+    X(EnergyAttachments_rb_d) \
+    X(contact_d_d_pt_pp) \
+    X(contact_d_d_pt_pe) \
+    X(contact_d_d_pt_pt) \
+    X(contact_d_d_ee_pp) \
+    X(contact_d_d_ee_pe) \
+    X(contact_d_d_ee_ee) \
+    X(contact_rb_rb_pt_pp) \
+    X(contact_rb_rb_pt_pe) \
+    X(contact_rb_rb_pt_pt) \
+    X(contact_rb_rb_ee_pp) \
+    X(contact_rb_rb_ee_pe) \
+    X(contact_rb_rb_ee_ee) \
+    X(contact_rb_d_pt_pp) \
+    X(contact_rb_d_pt_pe) \
+    X(contact_rb_d_pt_pt) \
+    X(contact_rb_d_pt_ep) \
+    X(contact_rb_d_pt_tp) \
+    X(contact_rb_d_ee_pp) \
+    X(contact_rb_d_ee_pe) \
+    X(contact_rb_d_ee_ee) \
+    X(contact_rb_d_ee_ep) \
+    X(friction_d_d_pp) \
+    X(friction_d_d_pe) \
+    X(friction_d_d_pt) \
+    X(friction_d_d_ee) \
+    X(friction_rb_rb_pp) \
+    X(friction_rb_rb_pe) \
+    X(friction_rb_rb_pt) \
+    X(friction_rb_rb_ee) \
+    X(friction_rb_d_pp) \
+    X(friction_rb_d_pe) \
+    X(friction_rb_d_pt) \
+    X(friction_rb_d_ee) \
+    X(friction_rb_d_ep) \
+    X(friction_rb_d_tp)
+
+enum PotKind {
+#define X(S) PK_##S,
+    SB_ALL_POTS(X)
+#undef X
+    PK_COUNT
+};
+__global__ void __launch_bounds__(128) k_eval_p_multi(const __grid_constant__ MultiPArgs M)
+{
+    __shared__ double s_in[EVAL_P_SMEM_DOUBLES];
+    int i = 0;
+    while (i + 1 < M.n && (int)blockIdx.x >= M.it[i + 1].cta0) i++;
+    const MultiPItem& a = M.it[i];
+    const int cta = blockIdx.x - a.cta0;
+    switch (a.kind) {
+#define X(S) case PK_##S: eval_p_body<sbpot::S>(a.slots, a.conn, a.conn_stride, a.n_elem, a.E_elem, cta, s_in); break;
+    SB_ALL_POTS(X)
+#undef X
+    default: break;
+    }
+}
+int multi_p_ctas(int p_kind, int n_elem)
+{
+    switch (p_kind) {
+#define X(S) case PK_##S: return (n_elem + GeoP<sbpot::S>::EP - 1) / GeoP<sbpot::S>::EP;
+    SB_ALL_POTS(X)
+#undef X
+    default: return 0;
+    }
+}
+void launch_p_multi(const MultiPArgs& M, int total_ctas, cudaStream_t s)
+{
+    k_eval_p_multi<<<total_ctas, 128, 0, s>>>(M);
+}
+
 }  // namespace sb
 #include "tet_analytic.cuh"
 namespace sb {
 
 #define SB_KERNEL(STRUCT, NAME) \
-    KernelInfo { NAME, sbpot::STRUCT::N_IN, sbpot::STRUCT::N_DOF, sbpot::STRUCT::NB, sbpot::STRUCT::DOF_SLOT, &launch_pgh<sbpot::STRUCT>, &launch_p<sbpot::STRUCT> }
+    KernelInfo { NAME, sbpot::STRUCT::N_IN, sbpot::STRUCT::N_DOF, sbpot::STRUCT::NB, sbpot::STRUCT::DOF_SLOT, &launch_pgh<sbpot::STRUCT>, &launch_p<sbpot::STRUCT>, PK_##STRUCT }
 
 const std::vector<KernelInfo>& all_kernels()
 {
@@ -135,8 +246,8 @@ const std::vector<KernelInfo>& all_kernels()
         SB_KERNEL(EnergyDiscreteShells, "EnergyDiscreteShells"),
         SB_KERNEL(EnergyBendingFlat, "EnergyBendingFlat"),
         // hand-derived analytic tet kernels (tet_analytic.cuh) are the product path; the AD ones stay as cross-checks
-        KernelInfo { "EnergyTetStrain", 43, 12, 4, sbpot::EnergyTetStrain::DOF_SLOT, &launch_tet_analytic_pgh<true>, &launch_tet_analytic_p<true> },
-        KernelInfo { "EnergyTetStrain_Elasticity_Only", 40, 12, 4, sbpot::EnergyTetStrain_Elasticity_Only::DOF_SLOT, &launch_tet_analytic_pgh<false>, &launch_tet_analytic_p<false> },
+        KernelInfo { "EnergyTetStrain", 43, 12, 4, sbpot::EnergyTetStrain::DOF_SLOT, &launch_tet_analytic_pgh<true>, &launch_tet_analytic_p<true>, -1 },
+        KernelInfo { "EnergyTetStrain_Elasticity_Only", 40, 12, 4, sbpot::EnergyTetStrain_Elasticity_Only::DOF_SLOT, &launch_tet_analytic_pgh<false>, &launch_tet_analytic_p<false>, -1 },
         SB_KERNEL(EnergyTetStrain, "EnergyTetStrain_AD"),
         SB_KERNEL(EnergyTetStrain_Elasticity_Only, "EnergyTetStrain_Elasticity_Only_AD"),
         SB_KERNEL(EnergyRigidBodyInertia_Linear, "EnergyRigidBodyInertia_Linear"),

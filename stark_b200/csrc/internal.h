@@ -47,7 +47,14 @@ struct KernelInfo {
     const int* dof_slot;
     void (*launch_pgh)(const EvalArgs&, cudaStream_t);
     void (*launch_p)(const EvalArgs&, cudaStream_t);
+    int p_kind;     // index into the multi-potential energy kernel's dispatch (-1: own kernel only)
 };
+// one launch for the energy-only evaluation of many small potentials (eval.cu)
+struct MultiPItem { const FetchSlot* slots; const int32_t* conn; double* E_elem; int conn_stride, n_elem, kind, cta0; };
+constexpr int MULTI_P_MAX = 64;
+struct MultiPArgs { int n; int pad; MultiPItem it[MULTI_P_MAX]; };
+int multi_p_ctas(int p_kind, int n_elem);
+void launch_p_multi(const MultiPArgs& M, int total_ctas, cudaStream_t s);
 const KernelInfo* find_kernel(const char* name);
 const std::vector<KernelInfo>& all_kernels();
 

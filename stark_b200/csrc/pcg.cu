@@ -229,13 +229,17 @@ __device__ __forceinline__ void apply_dinv(const float* d, double r0, double r1,
     z2 = (double)d[6] * r0 + (double)d[7] * r1 + (double)d[8] * r2;
 }
 
-// first row r in [0, nbr] with rows[r] >= t
+// Row partition: a CTA's iteration costs about one unit per block (product) plus ROW_COST units per block row (vector
+// phase, row bookkeeping), so the rows are cut into slices of equal  blocks + ROW_COST * rows.  (Cutting by blocks alone gives
+// the slices of sparse rows -- hex-centre nodes: 9 blocks per row instead of 27 -- twice the rows and twice the vector phase.)
+constexpr unsigned long long ROW_COST = 4;
+// first row r in [0, nbr] with rows[r] + ROW_COST * r >= t
 __device__ __forceinline__ int row_lower_bound(const unsigned long long* __restrict__ rows, int nbr, unsigned long long t)
 {
     int lo = 0, hi = nbr;
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if (rows[mid] < t) lo = mid + 1; else hi = mid;
+        if (rows[mid] + ROW_COST * (unsigned long long)mid < t) lo = mid + 1; else hi = mid;
     }
     return lo;
 }
@@ -577,7 +581,6 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_solve(const PcgArgs A)
     unsigned char* const smem = pcg_smem;
     __shared__ double s[2 * (PCG_THREADS / 32)];
     __shared__ double bc2[2];
-    double& bc = bc2[0];
     __shared__ int s_range[2];
     __shared__ int s_long[MAX_LONG_ROWS];
     __shared__ int s_seg_j0[MAX_SEGS], s_seg_j1[MAX_SEGS], s_seg_first[MAX_LONG_ROWS + 1];
@@ -589,15 +592,12 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_solve(const PcgArgs A)
     const int G = gridDim.x;
     const int nbr = A.nbr;
     const int tid = threadIdx.x;
-    unsigned epoch = 0;
-    double* part0 = A.part;
-    double* part1 = A.part + PCG_MAX_BLOCKS;
-    double* part2 = A.part + 2 * PCG_MAX_BLOCKS;
 
     // ---- this CTA's rows: [r0, r1), holding blocks [b0, b0 + nb) ----
     if (tid == 0) {
-        s_range[0] = row_lower_bound(A.rows, nbr, (A.nnzb * blockIdx.x) / G);
-        s_range[1] = (blockIdx.x == G - 1) ? nbr : row_lower_bound(A.rows, nbr, (A.nnzb * (blockIdx.x + 1)) / G);
+        const unsigned long long cost = A.nnzb + ROW_COST * (unsigned long long)nbr;
+        s_range[0] = row_lower_bound(A.rows, nbr, (cost * blockIdx.x) / G);
+        s_range[1] = (blockIdx.x == G - 1) ? nbr : row_lower_bound(A.rows, nbr, (cost * (blockIdx.x + 1)) / G);
         mbar_init(&s_mbar, 1);
     }
     __syncthreads();
