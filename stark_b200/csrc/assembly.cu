@@ -442,6 +442,18 @@ static bool pattern_current(sb_context* ctx, Assembly* A)
     return A->built_static == ctx->static_version && A->built_dynamic == ctx->dynamic_version && A->built_n_src == ctx->n_blocks_total && A->nbr == ctx->ndofs / 3;
 }
 
+void preload_assembly_kernels()
+{
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, k_make_keys); cudaFuncGetAttributes(&fa, k_heads); cudaFuncGetAttributes(&fa, k_fill_set);
+    cudaFuncGetAttributes(&fa, k_dyn_locate); cudaFuncGetAttributes(&fa, k_dyn_compact); cudaFuncGetAttributes(&fa, k_static_final);
+    cudaFuncGetAttributes(&fa, k_dyn_final); cudaFuncGetAttributes(&fa, k_row_ptr); cudaFuncGetAttributes(&fa, k_find_long);
+    cudaFuncGetAttributes(&fa, k_assemble_numeric<true>); cudaFuncGetAttributes(&fa, k_assemble_numeric<false>);
+    cudaFuncGetAttributes(&fa, k_assemble_long<true>); cudaFuncGetAttributes(&fa, k_assemble_long<false>);
+    cudaFuncGetAttributes(&fa, k_clear_dirty);
+    cudaGetLastError();
+}
+
 int assemble_internal(sb_context* ctx)
 {
     if (!ctx->have_pgh) return fail(ctx, SB_ERR_STATE, "sb_assemble: call sb_eval(SB_EVAL_PGH) first");
@@ -460,14 +472,21 @@ int assemble_internal(sb_context* ctx)
     a.vals = A->vals.p; a.dirty = A->dirty.p; a.long_blocks = A->long_blocks.p; a.n_long = A->d_counts; a.nnzb = A->nnzb;
     const size_t nt = 9 * A->nnzb;
     const unsigned grid = (unsigned)((nt + 287) / 288);
+    // the few long blocks (a rigid body's diagonal: thousands of sources, one CTA each, latency-bound) are summed on a side
+    // stream while the bulk kernel streams the element Hessians; the two write disjoint blocks
+    cudaStream_t side = ctx->side[0];
+    SB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    SB_CUDA(ctx, cudaStreamWaitEvent(side, ctx->ev_fork, 0));
     if (!rebuilt && A->numeric_valid && A->assembled_eval == ctx->eval_id) {
         // same evaluation, same pattern: only PD-projected elements changed since the last pass
+        k_assemble_long<true><<<LONG_CTAS, 288, 0, side>>>(a);
         k_assemble_numeric<true><<<grid, 288, 0, ctx->stream>>>(a);
-        k_assemble_long<true><<<LONG_CTAS, 288, 0, ctx->stream>>>(a);
     } else {
+        k_assemble_long<false><<<LONG_CTAS, 288, 0, side>>>(a);
         k_assemble_numeric<false><<<grid, 288, 0, ctx->stream>>>(a);
-        k_assemble_long<false><<<LONG_CTAS, 288, 0, ctx->stream>>>(a);
     }
+    SB_CUDA(ctx, cudaEventRecord(ctx->ev_join[0], side));
+    SB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[0], 0));
     k_clear_dirty<<<(unsigned)((A->nnzb + 255) / 256), 256, 0, ctx->stream>>>(A->dirty.p, A->nnzb);
     ctx->launches += 3;
     SB_CUDA(ctx, cudaGetLastError());

@@ -172,6 +172,7 @@ int eval_internal(sb_context* ctx, int mode, double* out_E, double* out_grad_inf
         ctx->H_total = H_total;
         ctx->n_projected = 0;
         ctx->eval_id++;
+        projector_prepare(ctx);
     }
 
     for (auto& p : ctx->potentials) {
@@ -180,7 +181,7 @@ int eval_internal(sb_context* ctx, int mode, double* out_E, double* out_grad_inf
         if (r) return r;
     }
     // large potentials stay on the context stream; the small ones are spread over the side streams (fork / join by events)
-    constexpr int SMALL = 16384;
+    constexpr int SMALL = 100000;   // (everything but the volume elements of a large mesh: the per-node inertia terms overlap with them too)
     int n_small = 0;
     for (auto& p : ctx->potentials) if (p.n_elem > 0 && p.n_elem < SMALL) n_small++;
     const bool fork = n_small >= 2;
@@ -307,6 +308,10 @@ int sb_create(sb_context** out, int device, void* stream)
     if (cudaMallocHost(&ctx->h_scalars, 64 * sizeof(double)) != cudaSuccess) { delete ctx; return SB_ERR_CUDA; }
     if (cudaMalloc(&ctx->d_scalars, 64 * sizeof(double)) != cudaSuccess) { delete ctx; return SB_ERR_CUDA; }
     cudaMemset(ctx->d_scalars, 0, 64 * sizeof(double));
+    {
+        static bool preloaded = false;
+        if (!preloaded) { preload_eval_kernels(); preload_project_kernels(); preload_assembly_kernels(); preloaded = true; }
+    }
     *out = ctx;
     return SB_OK;
 }

@@ -307,6 +307,28 @@ const std::vector<KernelInfo>& all_kernels()
     return k;
 }
 
+// CUDA loads a kernel's code at its first launch (lazy module loading): a contact or friction potential first used in the
+// middle of a run would stall that Newton iteration for milliseconds.  Touching a kernel's attributes loads it.
+template<class Pot> static void preload_pot()
+{
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, k_eval_pgh<Pot>);
+    cudaFuncGetAttributes(&fa, k_eval_p<Pot>);
+}
+void preload_eval_kernels()
+{
+#define X(S) preload_pot<sbpot::S>();
+    SB_ALL_POTS(X)
+#undef X
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, k_eval_p_multi);
+    cudaFuncGetAttributes(&fa, k_tet_analytic<true, true>); cudaFuncGetAttributes(&fa, k_tet_analytic<true, false>);
+    cudaFuncGetAttributes(&fa, k_tet_analytic<false, true>); cudaFuncGetAttributes(&fa, k_tet_analytic<false, false>);
+    cudaFuncGetAttributes(&fa, k_tet_energy<true, true>); cudaFuncGetAttributes(&fa, k_tet_energy<true, false>);
+    cudaFuncGetAttributes(&fa, k_tet_energy<false, true>); cudaFuncGetAttributes(&fa, k_tet_energy<false, false>);
+    cudaGetLastError();
+}
+
 const KernelInfo* find_kernel(const char* name)
 {
     for (const auto& k : all_kernels())

@@ -56,6 +56,11 @@ struct MultiPArgs { int n; int pad; MultiPItem it[MULTI_P_MAX]; };
 int multi_p_ctas(int p_kind, int n_elem);
 void launch_p_multi(const MultiPArgs& M, int total_ctas, cudaStream_t s);
 const KernelInfo* find_kernel(const char* name);
+// load the kernels' code now instead of at their first launch (called once from sb_create)
+void preload_eval_kernels();
+void preload_project_kernels();
+void projector_prepare(sb_context* ctx);
+void preload_assembly_kernels();
 const std::vector<KernelInfo>& all_kernels();
 
 template<class T> struct DevBuf {

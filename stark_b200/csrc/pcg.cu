@@ -326,16 +326,21 @@ __device__ __forceinline__ void pcg_body(const PcgArgs& A, const PcgPlan& P)
     };
     unsigned win_phase = 0;
     // pull the window of u (all CTAs have published their slices: call after a grid barrier)
-    auto load_window = [&]() {
+    // (issue and wait are separate so that the copy runs under the all-reduce that follows the barrier)
+    auto issue_window = [&]() {
         if (!own_in_win) return;
         if (tid == 0) {
             asm volatile("fence.proxy.async;" ::: "memory");
             mbar_expect_tx(&s_mbar, win_bytes);
             tma_load_bulk(uwin, A.u + 3 * (size_t)w0, win_bytes, &s_mbar);
         }
+    };
+    auto wait_window = [&]() {
+        if (!own_in_win) return;
         mbar_wait(&s_mbar, win_phase);
         win_phase ^= 1u;
     };
+    auto load_window = [&]() { issue_window(); wait_window(); };
     // w = A u on the own rows; returns this thread's share of w.u
     const int lane = tid % LANES_PER_ROW;
     constexpr int rows_per_pass = PCG_THREADS / LANES_PER_ROW;
@@ -511,15 +516,16 @@ __device__ __forceinline__ void pcg_body(const PcgArgs& A, const PcgPlan& P)
         PCG_TICK(c_vec);
         grid_barrier(A.barrier, epoch);
         PCG_TICK(c_bar);
+        issue_window();     // every slice of u is published: the window copy runs under the reduction below
         double rr, gamma_new;
         all_partials2(part0, part1, s, bc2, rr, gamma_new);
         error = sqrt(rr / bb);
         PCG_TICK(c_red);
+        wait_window();      // (also on the way out: no copy may be in flight when the CTA leaves)
+        PCG_TICK(c_win);
         if (error < A.abs_tol || error / error0 < A.rel_tol) { done = 1; break; }
         if (it >= A.max_iter) { done = 3; break; }
         // ---- w = A u ; delta = w.u ----
-        load_window();
-        PCG_TICK(c_win);
         {
             const double wu = spmv();
             const double t = block_sum(wu, s);

@@ -428,6 +428,29 @@ void projector_destroy(sb_context* ctx)
     ctx->projector = nullptr;
 }
 
+void preload_project_kernels()
+{
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, k_active_blocks); cudaFuncGetAttributes(&fa, k_select);
+    cudaFuncGetAttributes(&fa, k_project<32>); cudaFuncGetAttributes(&fa, k_project<8>);
+    cudaGetLastError();
+}
+
+// buffers of the projector, sized for the current evaluation (called from the P+G+H evaluation so that the first projection
+// of a run -- typically the first iteration in contact -- does not pay for pinned-memory and device allocations)
+void projector_prepare(sb_context* ctx)
+{
+    if (!ctx->projector) ctx->projector = new Projector();
+    Projector& P = *ctx->projector;
+    if (!P.d_table) {
+        cudaMalloc(&P.d_table, sizeof(ProjTable));
+        cudaMalloc(&P.d_counts, 4 * sizeof(int));
+        cudaMallocHost(&P.h_counts, 4 * sizeof(int));
+    }
+    P.active.ensure(ctx->ndofs / 3 + 1);
+    P.list.ensure(ctx->n_hessians + 1);
+}
+
 int project_internal(sb_context* ctx, double grad_threshold, double eps, int mirror, int64_t* out_n_projected, int64_t* out_n_hessians, int* out_all_projected)
 {
     if (!ctx->have_pgh) return fail(ctx, SB_ERR_STATE, "sb_project_to_pd: call sb_eval(SB_EVAL_PGH) first");
