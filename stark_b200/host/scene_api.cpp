@@ -3,6 +3,7 @@
 // reference's public API (same generators, parameters and order of add_* calls).
 #include "stark_b200.hpp"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <memory>
@@ -34,6 +35,30 @@ void build_tetdrop(Scene& sc, int n, double dt, double drop, double vz, int devi
     sim.set_translation(floor.body, {0.0, 0.0, -0.05});
     sim.rb_constraints.add_fix(sim.rb, floor.body);
     sim.contact.set_friction(floor.contact_group, H.contact_group, 0.5);
+}
+
+// C1 / C3: n x n cloth grid (Cotton_Fabric) over a fixed, scripted rigid box (oracle/ref_driver.cpp scene_cloth;
+// examples/main.cpp:371-414).  discrete_shells = true uses the dihedral-angle bending energy with friction mu.
+void build_cloth(Scene& sc, int n, double dt, double drop, bool discrete_shells, double mu, int device, void* stream)
+{
+    Settings s;
+    s.simulation.max_time_step_size = dt;
+    s.device = device; s.stream = stream;
+    sc.sim = std::make_unique<Simulation>(s);
+    Simulation& sim = *sc.sim;
+    EnergyFrictionalContact::GlobalParams cp;
+    cp.default_contact_thickness = 0.002;
+    sim.contact.set_global_params(cp);
+    SurfaceParams material = SurfaceParams::Cotton_Fabric();
+    if (discrete_shells) material.flat_rest_angle = false;
+    auto cloth = sim.add_surface_grid({0.4, 0.4}, {n, n}, material);
+    if (drop != 0.003) sim.dyn.add_displacement(cloth.point_set, {0.0, 0.0, drop});
+    auto box = sim.add_box(1.0, {0.08, 0.08, 0.08});
+    sim.set_translation(box.body, {0.0, 0.0, -0.08});
+    const auto fix = sim.rb_constraints.add_fix(sim.rb, box.body);
+    if (mu > 0.0) sim.contact.set_friction(box.contact_group, cloth.contact_group, mu);
+    Simulation* ps = &sim;
+    sim.add_time_event([ps, fix](double t) { ps->rb_constraints.set_fix_transformation(fix, {0.0, 0.0, -0.08 - 0.1 * std::sin(t)}, 90.0 * t, {0.0, 0.0, 1.0}); });
 }
 
 // C5: tet bar, both end caps prescribed, one cap rotating 90 deg/s, no contact (oracle/ref_driver.cpp scene_tetbar)
@@ -102,6 +127,8 @@ __attribute__((visibility("default"))) void* sbh_scene_create(const char* name, 
     if (sc->name == "tetdrop") build_tetdrop(*sc, n, dt, drop, vz, device, stream);
     else if (sc->name == "tetbar") build_tetbar(*sc, n, ny, nz, dt, device, stream);
     else if (sc->name == "tetchain") build_tetchain(*sc, n, ny, dt, drop, device, stream);
+    else if (sc->name == "cloth") build_cloth(*sc, n, dt, drop, false, 0.0, device, stream);
+    else if (sc->name == "cloth_shells") build_cloth(*sc, n, dt, drop, true, 0.3, device, stream);
     else { delete sc; return nullptr; }
     return sc;
 }
@@ -151,6 +178,33 @@ __attribute__((visibility("default"))) int sbh_scene_potential(void* h, const ch
     if (n == "EnergyTetStrain_Elasticity_Only") return sim.tet_strain.potential_elasticity_only;
     if (n == "EnergyLumpedInertia") return sim.lumped_inertia.potential;
     return -1;
+}
+// host copy of a bound array by its label (e.g. "shells.rest_angle"); returns the number of doubles, -1 if unknown
+__attribute__((visibility("default"))) int sbh_scene_array(void* h, const char* label, double* out, int cap)
+{
+    const DeviceArray* a = static_cast<Scene*>(h)->sim->find_array(label);
+    if (!a) return -1;
+    const int n = (int)a->data.size();
+    if (out) std::memcpy(out, a->data.data(), sizeof(double) * (size_t)std::min(n, cap));
+    return n;
+}
+// connectivity table of a deformable potential by name; returns the number of int32 entries, -1 if unknown
+__attribute__((visibility("default"))) int sbh_scene_connectivity(void* h, const char* name, int32_t* out, int cap)
+{
+    Simulation& sim = *static_cast<Scene*>(h)->sim;
+    const std::string n = name;
+    const int32_t* p = nullptr;
+    int len = 0;
+    auto take = [&](const auto& conn) { len = (int)(conn.size() * sizeof(conn[0]) / sizeof(int32_t)); p = conn.empty() ? nullptr : conn[0].data(); };
+    if (n == "EnergyDiscreteShells") take(sim.discrete_shells.conn_complete);
+    else if (n == "EnergyBendingFlat") take(sim.discrete_shells.conn_flat_rest);
+    else if (n == "EnergyTriangleStrain") take(sim.triangle_strain.conn_complete);
+    else if (n == "EnergyTriangleStrain_Elasticity_Only") take(sim.triangle_strain.conn_elasticity_only);
+    else if (n == "EnergyLumpedInertia") take(sim.lumped_inertia.conn);
+    else if (n == "EnergyTetStrain") take(sim.tet_strain.conn_complete);
+    else return -1;
+    if (out && p) std::memcpy(out, p, sizeof(int32_t) * (size_t)std::min(len, cap));
+    return len;
 }
 __attribute__((visibility("default"))) void* sbh_scene_context(void* h) { return static_cast<Scene*>(h)->sim->context(); }
 

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
+#include <iterator>
 #include <map>
 
 namespace stark_b200 {
@@ -116,6 +117,47 @@ std::vector<std::array<int, 2>> find_edges_from_triangles(const std::vector<std:
     return e;
 }
 
+void generate_triangle_grid(std::vector<Vec3>& V, std::vector<std::array<int, 3>>& T, const std::array<double, 2>& center, const std::array<double, 2>& dim, const std::array<int, 2>& n, double z)
+{   // two triangles per quad, diagonals alternating in a checkerboard (S/utils/mesh_generators.cpp:100-167)
+    const double bx = center[0] - 0.5 * dim[0], by = center[1] - 0.5 * dim[1];
+    const int nx = n[0] + 1, ny = n[1] + 1;
+    const double dx = dim[0] / n[0], dy = dim[1] / n[1];
+    V.assign((size_t)nx * ny, Vec3{0, 0, 0});
+    for (int i = 0; i < nx; i++) for (int j = 0; j < ny; j++) V[(size_t)ny * i + j] = {bx + i * dx, by + j * dy, z};
+    T.clear();
+    for (int ei = 0; ei < n[0]; ei++)
+        for (int ej = 0; ej < n[1]; ej++) {
+            const int q[4] = {ny * ei + ej, ny * ei + ej + 1, ny * (ei + 1) + ej, ny * (ei + 1) + ej + 1};
+            if (ei % 2 == ej % 2) { T.push_back({q[0], q[2], q[3]}); T.push_back({q[0], q[3], q[1]}); }
+            else { T.push_back({q[0], q[2], q[1]}); T.push_back({q[2], q[3], q[1]}); }
+        }
+}
+void find_internal_angles(std::vector<std::array<int, 4>>& out, const std::vector<std::array<int, 3>>& tris, int n_nodes)
+{   // for every edge, the two nodes adjacent to both end points (S/utils/mesh_utils.cpp:217-252)
+    out.clear();
+    if (tris.empty()) return;
+    std::vector<std::vector<int>> nn(n_nodes);
+    auto add = [&](int a, int b) { if (std::find(nn[a].begin(), nn[a].end(), b) == nn[a].end()) nn[a].push_back(b); };
+    for (const auto& t : tris)
+        for (int i = 0; i < 3; i++) for (int j = i + 1; j < 3; j++) { add(t[i], t[j]); add(t[j], t[i]); }
+    for (auto& v : nn) std::sort(v.begin(), v.end());
+    std::vector<int> buf;
+    for (const auto& e : find_edges_from_triangles(tris, n_nodes)) {
+        buf.clear();
+        std::set_intersection(nn[e[0]].begin(), nn[e[0]].end(), nn[e[1]].begin(), nn[e[1]].end(), std::back_inserter(buf));
+        if (buf.size() == 2) out.push_back({e[0], e[1], buf[0], buf[1]});
+        else if (buf.size() > 2) die("triangle mesh has edges with more than two incident triangles.");
+    }
+}
+static Mat3 angle_axis_rotation(double angle_deg, const Vec3& axis)
+{   // Eigen::AngleAxisd(deg2rad(angle), axis).toRotationMatrix() (Rodrigues)
+    const double th = angle_deg * M_PI / 180.0, c = std::cos(th), sn = std::sin(th);
+    const Vec3 u = (1.0 / norm(axis)) * axis;
+    return {c + u[0] * u[0] * (1 - c), u[0] * u[1] * (1 - c) - u[2] * sn, u[0] * u[2] * (1 - c) + u[1] * sn,
+            u[1] * u[0] * (1 - c) + u[2] * sn, c + u[1] * u[1] * (1 - c), u[1] * u[2] * (1 - c) - u[0] * sn,
+            u[2] * u[0] * (1 - c) - u[1] * sn, u[2] * u[1] * (1 - c) + u[0] * sn, c + u[2] * u[2] * (1 - c)};
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // deformables
 // ---------------------------------------------------------------------------------------------------------------------
@@ -150,6 +192,65 @@ int EnergyLumpedInertia::add(PointDynamics& dyn, int set, const std::vector<std:
             conn.push_back({(int32_t)conn.size(), dyn.get_global_index(set, i), group});
             push1(lumped_volume, lumped[i]);
         }
+    }
+    return group;
+}
+int EnergyLumpedInertia::add(PointDynamics& dyn, int set, const std::vector<std::array<int, 3>>& tris, double rho, double damp)
+{   // S/models/deformables/point/EnergyLumpedInertia.cpp:116-138 (a third of every incident triangle area; density per m^2)
+    const int group = density.rows();
+    push1(density, rho); push1(damping, damp); push1(is_quasistatic, 0.0);
+    std::vector<double> lumped(dyn.get_set_size(set), 0.0);
+    for (const auto& t : tris) {
+        const Vec3 A = get3(dyn.X, dyn.get_global_index(set, t[0])), B = get3(dyn.X, dyn.get_global_index(set, t[1])), C = get3(dyn.X, dyn.get_global_index(set, t[2]));
+        const double area = 0.5 * norm(cross(A - C, B - C));
+        for (int k = 0; k < 3; k++) lumped[t[k]] += area / 3.0;
+    }
+    for (int i = 0; i < (int)lumped.size(); i++) {
+        if (lumped[i] > 0.0) {
+            conn.push_back({(int32_t)conn.size(), dyn.get_global_index(set, i), group});
+            push1(lumped_volume, lumped[i]);
+        }
+    }
+    return group;
+}
+
+int EnergyTriangleStrain::add(PointDynamics& dyn, int set, const std::vector<std::array<int, 3>>& tris, const SurfaceParams& p)
+{   // S/models/deformables/surface/EnergyTriangleStrain.cpp:131-155
+    const int group = youngs_modulus.rows();
+    push1(scale, p.scale); push1(thickness, p.thickness); push1(youngs_modulus, p.youngs_modulus); push1(poissons_ratio, p.poissons_ratio);
+    push1(strain_damping, p.strain_damping); push1(strain_limit, p.strain_limit); push1(strain_limit_stiffness, p.strain_limit_stiffness); push1(inflation, p.inflation);
+    auto& conn = p.elasticity_only ? conn_elasticity_only : conn_complete;
+    for (const auto& t : tris)
+        conn.push_back({(int32_t)conn.size(), group, dyn.get_global_index(set, t[0]), dyn.get_global_index(set, t[1]), dyn.get_global_index(set, t[2])});
+    return group;
+}
+
+int EnergyDiscreteShells::add(PointDynamics& dyn, int set, const std::vector<std::array<int, 3>>& tris, const SurfaceParams& p)
+{   // S/models/deformables/surface/EnergyDiscreteShells.cpp:93-166
+    constexpr double EPSILON = 1e-12;
+    const int group = bending_stiffness.rows();
+    push1(scale, p.bending_scale); push1(bending_stiffness, p.bending_stiffness); push1(bending_damping, p.bending_damping);
+    if (p.flat_rest_angle && p.bending_scale != 1.0) die("EnergyDiscreteShells::add(): scale cannot be different from 1.0 if flat_rest_angle == true");
+    std::vector<std::array<int, 4>> angles;
+    find_internal_angles(angles, tris, dyn.get_set_size(set));
+    auto cot = [](const Vec3& v, const Vec3& w) { return dot(v, w) / norm(cross(v, w)); };
+    auto& conn = p.flat_rest_angle ? conn_flat_rest : conn_complete;
+    bergou_K.stride = 4;
+    for (const auto& a : angles) {
+        const int g[4] = {dyn.get_global_index(set, a[0]), dyn.get_global_index(set, a[1]), dyn.get_global_index(set, a[2]), dyn.get_global_index(set, a[3])};
+        conn.push_back({(int32_t)conn.size(), group, g[0], g[1], g[2], g[3]});
+        const Vec3 X0 = get3(dyn.X, g[0]), X1 = get3(dyn.X, g[1]), X2 = get3(dyn.X, g[2]), X3 = get3(dyn.X, g[3]);
+        const Vec3 e0 = X1 - X0, e1 = X2 - X0, e2 = X3 - X0, e3 = X2 - X1, e4 = X3 - X1;
+        const double len = norm(e0);
+        push1(rest_edge_length, len);
+        const Vec3 n0 = cross(e0, e1), n1 = -1.0 * cross(e0, e2);
+        push1(rest_dihedral_angle_rad, std::acos((1.0 - EPSILON) * dot((1.0 / norm(n0)) * n0, (1.0 / norm(n1)) * n1)));
+        const double A0 = 0.5 * norm(n0), A1 = 0.5 * norm(n1);
+        push1(rest_height, 1.0 / 6.0 * (2.0 * A0 / len + 2.0 * A1 / len));
+        const Vec3 me0 = -1.0 * e0;
+        const double c01 = cot(e0, e1), c02 = cot(e0, e2), c03 = cot(me0, e3), c04 = cot(me0, e4);
+        push1(bergou_coef, 3.0 / (A0 + A1) * 0.5);
+        for (double k : {c03 + c04, c01 + c02, -c01 - c03, -c02 - c04}) bergou_K.data.push_back(k);
     }
     return group;
 }
@@ -246,9 +347,13 @@ void EnergyRigidBodyInertia::before_time_step(const RigidBodyDynamics& rb)
     }
 }
 
-void EnergyRigidBodyConstraints::add_fix(const RigidBodyDynamics& rb, int body)
+EnergyRigidBodyConstraints::Fix EnergyRigidBodyConstraints::add_fix(const RigidBodyDynamics& rb, int body)
 {   // RigidBodies::add_constraint_fix (S/models/rigidbodies/RigidBodies.cpp:205-212): anchor point + z lock + x lock
     const Vec3 t = get3(rb.t0, body);
+    Fix fix;
+    fix.anchor_point = (int)global_points.conn.size();
+    fix.z_lock = (int)global_directions.conn.size();
+    fix.x_lock = fix.z_lock + 1;
     {
         auto& d = global_points;
         d.conn.push_back({(int32_t)d.conn.size(), body});
@@ -259,8 +364,16 @@ void EnergyRigidBodyConstraints::add_fix(const RigidBodyDynamics& rb, int body)
         auto& d = global_directions;
         d.conn.push_back({(int32_t)d.conn.size(), body});
         push3(d.d_loc, matTvec(rb.R0[body], dir)); push3(d.target_d_glob, dir);
+        d.d_loc_rest.push_back(matTvec(rb.R0[body], dir));
         push1(d.stiffness, default_stiffness); push1(d.is_active, 1.0); d.tolerance_in_deg.push_back(default_tolerance_in_deg);
     }
+    return fix;
+}
+void EnergyRigidBodyConstraints::set_fix_transformation(const Fix& fix, const Vec3& translation, double angle_deg, const Vec3& axis)
+{   // RBCFixHandler::set_transformation (rigidbody_constraints_ui.h:369-379): new anchor target; the locks' LOCAL directions become R d_loc_rest
+    set3(global_points.target_glob, fix.anchor_point, translation);
+    const Mat3 R = angle_axis_rotation(angle_deg, axis);
+    for (int k : {fix.z_lock, fix.x_lock}) set3(global_directions.d_loc, k, matvec(R, global_directions.d_loc_rest[k]));
 }
 void EnergyRigidBodyConstraints::add_hinge(const RigidBodyDynamics& rb, int a, int b, const Vec3& p, const Vec3& dg)
 {   // RigidBodies::add_constraint_hinge (RigidBodies.cpp:245-252): point + direction
@@ -406,6 +519,24 @@ Simulation::VolumeHandle Simulation::add_volume_grid(const Vec3& dim, const std:
     return {set, group, (int)V.size(), (int)T.size()};
 }
 
+Simulation::SurfaceHandle Simulation::add_surface_grid(const std::array<double, 2>& dim, const std::array<int, 2>& sub, const SurfaceParams& p)
+{   // DeformablesPresets::add_surface_grid -> add_surface (S/models/presets/DeformablesPresets.cpp:31-50)
+    std::vector<Vec3> V;
+    std::vector<std::array<int, 3>> T;
+    generate_triangle_grid(V, T, {0.0, 0.0}, dim, sub);
+    const int set = dyn.add(V);
+    lumped_inertia.add(dyn, set, T, p.density, p.inertia_damping);
+    triangle_strain.add(dyn, set, T, p);
+    discrete_shells.add(dyn, set, T, p);
+    int group = -1;
+    if (settings.simulation.init_frictional_contact) {
+        std::vector<int32_t> vg;
+        for (int v = 0; v < (int)V.size(); v++) vg.push_back(dyn.get_global_index(set, v));
+        group = contact.add_triangles_deformable(set, vg, T, p.contact_thickness);
+    }
+    return {set, group, (int)V.size(), (int)T.size()};
+}
+
 Simulation::BoxHandle Simulation::add_box(double mass, const Vec3& size, double thickness)
 {   // RigidBodyPresets::add_box (S/models/presets/RigidBodyPresets.cpp:47-53): par_shapes unit cube, centred, scaled
     static const double C[8][3] = {{0, 0, 0}, {0, 1, 0}, {1, 1, 0}, {1, 0, 0}, {0, 0, 1}, {0, 1, 1}, {1, 1, 1}, {1, 0, 1}};
@@ -444,6 +575,13 @@ void Simulation::initialize()
     auto& ts = tet_strain;
     reg(ts.scale, "tet.scale", 1); reg(ts.youngs_modulus, "tet.E", 1); reg(ts.poissons_ratio, "tet.nu", 1); reg(ts.strain_limit, "tet.strain_limit", 1);
     reg(ts.strain_limit_stiffness, "tet.sl_stiffness", 1); reg(ts.strain_damping, "tet.damping", 1);
+    auto& tri = triangle_strain;
+    reg(tri.scale, "tri.scale", 1); reg(tri.thickness, "tri.thickness", 1); reg(tri.youngs_modulus, "tri.E", 1); reg(tri.poissons_ratio, "tri.nu", 1);
+    reg(tri.strain_damping, "tri.damping", 1); reg(tri.strain_limit, "tri.strain_limit", 1); reg(tri.strain_limit_stiffness, "tri.sl_stiffness", 1); reg(tri.inflation, "tri.inflation", 1);
+    auto& ds = discrete_shells;
+    reg(ds.rest_dihedral_angle_rad, "shells.rest_angle", 1); reg(ds.rest_edge_length, "shells.rest_edge_length", 1); reg(ds.rest_height, "shells.rest_height", 1);
+    reg(ds.bergou_K, "shells.bergou_K", 4); reg(ds.bergou_coef, "shells.bergou_coef", 1);
+    reg(ds.scale, "shells.scale", 1); reg(ds.bending_stiffness, "shells.stiffness", 1); reg(ds.bending_damping, "shells.damping", 1);
     auto& pp = prescribed_positions;
     reg(pp.target_positions, "prescribed.target", 3); reg(pp.stiffness, "prescribed.stiffness", 1);
     auto& ri = rb_inertia;
@@ -483,6 +621,33 @@ void Simulation::initialize()
         std::vector<sb_fetch> f;
         push_fetch(f, dyn.v1, 1, 0); push_fetch(f, dyn.x0, 1, 3); push_fetch(f, pp.target_positions, 0, 6); push_fetch(f, pp.stiffness, 2, 9); push_fetch(f, dt_arr, -1, 10);
         pp.potential = create("EnergyPrescribedPositions", 3, f, pp.conn.empty() ? nullptr : pp.conn[0].data(), (int)pp.conn.size());
+    }
+    for (int complete = 1; complete >= 0; complete--) {   // EnergyTriangleStrain (surface/EnergyTriangleStrain.cpp:13-34, 82-98)
+        std::vector<sb_fetch> f;
+        for (int k = 0; k < 3; k++) push_fetch(f, dyn.v1, 2 + k, 3 * k);
+        for (int k = 0; k < 3; k++) push_fetch(f, dyn.x0, 2 + k, 9 + 3 * k);
+        for (int k = 0; k < 3; k++) push_fetch(f, dyn.X, 2 + k, 18 + 3 * k);
+        push_fetch(f, tri.scale, 1, 27); push_fetch(f, tri.thickness, 1, 28); push_fetch(f, tri.youngs_modulus, 1, 29); push_fetch(f, tri.poissons_ratio, 1, 30);
+        if (complete) {
+            push_fetch(f, tri.strain_damping, 1, 31); push_fetch(f, tri.strain_limit, 1, 32); push_fetch(f, tri.strain_limit_stiffness, 1, 33);
+            push_fetch(f, tri.inflation, 1, 34); push_fetch(f, dt_arr, -1, 35);
+        } else { push_fetch(f, tri.inflation, 1, 31); push_fetch(f, dt_arr, -1, 32); }
+        auto& conn = complete ? tri.conn_complete : tri.conn_elasticity_only;
+        const int pot = create(complete ? "EnergyTriangleStrain" : "EnergyTriangleStrain_Elasticity_Only", 5, f, conn.empty() ? nullptr : conn[0].data(), (int)conn.size());
+        (complete ? tri.potential_complete : tri.potential_elasticity_only) = pot;
+    }
+    {   // EnergyDiscreteShells / EnergyBendingFlat (surface/EnergyDiscreteShells.cpp:26-62, 64-92)
+        std::vector<sb_fetch> f;
+        for (int k = 0; k < 4; k++) push_fetch(f, dyn.v1, 2 + k, 3 * k);
+        for (int k = 0; k < 4; k++) push_fetch(f, dyn.x0, 2 + k, 12 + 3 * k);
+        push_fetch(f, ds.rest_dihedral_angle_rad, 0, 24); push_fetch(f, ds.rest_edge_length, 0, 25); push_fetch(f, ds.rest_height, 0, 26);
+        push_fetch(f, ds.scale, 1, 27); push_fetch(f, ds.bending_stiffness, 1, 28); push_fetch(f, ds.bending_damping, 1, 29); push_fetch(f, dt_arr, -1, 30);
+        ds.potential_complete = create("EnergyDiscreteShells", 6, f, ds.conn_complete.empty() ? nullptr : ds.conn_complete[0].data(), (int)ds.conn_complete.size());
+        f.clear();
+        for (int k = 0; k < 4; k++) push_fetch(f, dyn.v1, 2 + k, 3 * k);
+        for (int k = 0; k < 4; k++) push_fetch(f, dyn.x0, 2 + k, 12 + 3 * k);
+        push_fetch(f, ds.bergou_K, 0, 24); push_fetch(f, ds.bergou_coef, 0, 28); push_fetch(f, ds.bending_stiffness, 1, 29); push_fetch(f, dt_arr, -1, 30);
+        ds.potential_flat_rest = create("EnergyBendingFlat", 6, f, ds.conn_flat_rest.empty() ? nullptr : ds.conn_flat_rest[0].data(), (int)ds.conn_flat_rest.size());
     }
     for (int complete = 1; complete >= 0; complete--) {   // EnergyTetStrain (volume/EnergyTetStrain.cpp:16-28, 84-93)
         std::vector<sb_fetch> f;
@@ -582,6 +747,7 @@ bool Simulation::run_one_time_step()
     for (DeviceArray* a : {&dyn.x0, &dyn.v0, &dyn.a, &dyn.f, &rb.v1, &rb.w1, &rb.t0, &rb.q0_, &rb.v0, &rb.w0, &rb.a, &rb.aa, &rb.force, &rb.torque, &dt_arr, &gravity_arr,
                            &rb_inertia.J0_glob, &prescribed_positions.target_positions, &prescribed_positions.stiffness, &rb_constraints.global_points.target_glob,
                            &rb_constraints.global_points.stiffness, &rb_constraints.global_directions.target_d_glob, &rb_constraints.global_directions.stiffness,
+                           &rb_constraints.global_directions.d_loc,   // (scripted fix constraints rotate the LOCAL lock directions)
                            &rb_constraints.points.stiffness, &rb_constraints.directions.stiffness})
         upload(*a);
     if (settings.newton.contact_enabled) {

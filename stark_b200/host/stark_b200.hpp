@@ -79,12 +79,42 @@ struct VolumeParams {   // stark::Volume::Params (S/models/presets/deformables_p
     static VolumeParams Soft_Rubber() { return VolumeParams(); }
 };
 
+struct SurfaceParams {   // stark::Surface::Params (S/models/presets/deformables_preset_types.{h,cpp})
+    double density = 0.2, inertia_damping = 0.1;   // density in kg/m^2
+    bool elasticity_only = false;
+    double scale = 1.0, thickness = 0.001, youngs_modulus = 5e3, poissons_ratio = 0.3, strain_damping = 0.1 * 0.001 * 5e3, strain_limit = 0.1, strain_limit_stiffness = 1e6, inflation = 0.0;
+    double bending_scale = 1.0, bending_stiffness = 1e-6, bending_damping = 0.1 * 1e-6;
+    bool flat_rest_angle = true;
+    double contact_thickness = 0.0;
+    static SurfaceParams Cotton_Fabric() { return SurfaceParams(); }
+};
+
 class EnergyLumpedInertia {
 public:
     std::vector<std::array<int32_t, 3>> conn;   // {idx, glob, group}
     DeviceArray lumped_volume, density, damping, is_quasistatic;
     int potential = -1;
     int add(PointDynamics& dyn, int set, const std::vector<std::array<int, 4>>& tets, double density, double damping);
+    int add(PointDynamics& dyn, int set, const std::vector<std::array<int, 3>>& triangles, double density, double damping);
+private:
+    int add_lumped(PointDynamics& dyn, int set, const std::vector<double>& lumped, double density, double damping);
+};
+
+class EnergyTriangleStrain {
+public:
+    std::vector<std::array<int32_t, 5>> conn_complete, conn_elasticity_only;   // {idx, group, i, j, k}
+    DeviceArray scale, thickness, youngs_modulus, poissons_ratio, strain_damping, strain_limit, strain_limit_stiffness, inflation;
+    int potential_complete = -1, potential_elasticity_only = -1;
+    int add(PointDynamics& dyn, int set, const std::vector<std::array<int, 3>>& triangles, const SurfaceParams& p);
+};
+
+class EnergyDiscreteShells {
+public:
+    std::vector<std::array<int32_t, 6>> conn_complete, conn_flat_rest;   // {idx, group, v_edge_0, v_edge_1, v_opp_0, v_opp_1}
+    DeviceArray rest_dihedral_angle_rad, rest_edge_length, rest_height, bergou_K, bergou_coef;   // per hinge (bergou_K stride 4)
+    DeviceArray scale, bending_stiffness, bending_damping;                                       // per group
+    int potential_complete = -1, potential_flat_rest = -1;
+    int add(PointDynamics& dyn, int set, const std::vector<std::array<int, 3>>& triangles, const SurfaceParams& p);
 };
 
 class EnergyTetStrain {
@@ -135,12 +165,14 @@ public:
 class EnergyRigidBodyConstraints {
 public:
     struct GlobalPoints { std::vector<std::array<int32_t, 2>> conn; DeviceArray loc, target_glob, stiffness, is_active; std::vector<double> tolerance_in_m; int potential = -1; } global_points;
-    struct GlobalDirections { std::vector<std::array<int32_t, 2>> conn; DeviceArray d_loc, target_d_glob, stiffness, is_active; std::vector<double> tolerance_in_deg; int potential = -1; } global_directions;
+    struct GlobalDirections { std::vector<std::array<int32_t, 2>> conn; DeviceArray d_loc, target_d_glob, stiffness, is_active; std::vector<double> tolerance_in_deg; std::vector<Vec3> d_loc_rest; int potential = -1; } global_directions;
+    struct Fix { int anchor_point, z_lock, x_lock; };   // RBCFixHandler (rigidbody_constraints_ui.h:333-380)
     struct Points { std::vector<std::array<int32_t, 3>> conn; DeviceArray a_loc, b_loc, stiffness, is_active; std::vector<double> tolerance_in_m; int potential = -1; } points;
     struct Directions { std::vector<std::array<int32_t, 3>> conn; DeviceArray da_loc, db_loc, stiffness, is_active; std::vector<double> tolerance_in_deg; int potential = -1; } directions;
     double default_stiffness = 1e6, default_tolerance_in_m = 0.001, default_tolerance_in_deg = 1.0;
     double stiffness_hard_multiplier = 2.0, stiffness_soft_multiplier = 1.05, soft_constraint_capacity_hardening_point = 0.75;
-    void add_fix(const RigidBodyDynamics& rb, int body);
+    Fix add_fix(const RigidBodyDynamics& rb, int body);
+    void set_fix_transformation(const Fix& fix, const Vec3& translation, double angle_deg, const Vec3& axis);
     void add_hinge(const RigidBodyDynamics& rb, int body_a, int body_b, const Vec3& p_glob, const Vec3& d_glob);
     bool adjust_stiffness(const RigidBodyDynamics& rb, double dt, double cap, double multiplier, bool positions_set);
 };
@@ -188,6 +220,8 @@ public:
     PointDynamics dyn;
     EnergyLumpedInertia lumped_inertia;
     EnergyTetStrain tet_strain;
+    EnergyTriangleStrain triangle_strain;
+    EnergyDiscreteShells discrete_shells;
     EnergyPrescribedPositions prescribed_positions;
     RigidBodyDynamics rb;
     EnergyRigidBodyInertia rb_inertia;
@@ -197,7 +231,9 @@ public:
     // presets (S/models/presets/DeformablesPresets.cpp:73-85, RigidBodyPresets.cpp:47-53)
     struct VolumeHandle { int point_set, contact_group; int n_vertices, n_tets; };
     struct BoxHandle { int body, contact_group; };
+    struct SurfaceHandle { int point_set, contact_group; int n_vertices, n_triangles; };
     VolumeHandle add_volume_grid(const Vec3& dim, const std::array<int, 3>& subdivisions, const VolumeParams& params);
+    SurfaceHandle add_surface_grid(const std::array<double, 2>& dim, const std::array<int, 2>& subdivisions, const SurfaceParams& params);
     BoxHandle add_box(double mass, const Vec3& size, double contact_thickness = 0.0);
     void set_translation(int body, const Vec3& t);
     void add_time_event(std::function<void(double)> f) { time_events.push_back(f); }
@@ -206,6 +242,7 @@ public:
     bool run_one_time_step();
     const StepStats& last_step() const { return stats; }
     sb_context* context() { return ctx; }
+    const DeviceArray* find_array(const std::string& label) const { for (const DeviceArray* a : all_arrays) if (a->label == label) return a; return nullptr; }
     int ndofs();
     // totals over all steps taken so far
     long long total_newton_iterations = 0, total_evaluations = 0, total_cg_iterations = 0, h2d_bytes = 0, d2h_bytes = 0;
@@ -227,6 +264,8 @@ private:
 };
 
 // mesh helpers (S/utils/mesh_generators.cpp:264-377, S/utils/mesh_utils.cpp:278-327, S/utils/mesh_utils.h:153-166)
+void generate_triangle_grid(std::vector<Vec3>& vertices, std::vector<std::array<int, 3>>& triangles, const std::array<double, 2>& center, const std::array<double, 2>& dim, const std::array<int, 2>& n, double z = 0.0);
+void find_internal_angles(std::vector<std::array<int, 4>>& internal_angles, const std::vector<std::array<int, 3>>& triangles, int n_nodes);
 void generate_tet_grid(std::vector<Vec3>& vertices, std::vector<std::array<int, 4>>& tets, const Vec3& center, const Vec3& dim, const std::array<int, 3>& n);
 void find_surface(std::vector<std::array<int, 3>>& triangles, std::vector<int>& triangle_to_tet_node_map, const std::vector<Vec3>& vertices, const std::vector<std::array<int, 4>>& tets);
 std::vector<std::array<int, 2>> find_edges_from_triangles(const std::vector<std::array<int, 3>>& triangles, int n_nodes);

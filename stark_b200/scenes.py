@@ -26,6 +26,8 @@ def load():
         h.sbh_scene_totals.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         h.sbh_scene_positions.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
         h.sbh_scene_potential.argtypes = [C.c_void_p, C.c_char_p]
+        h.sbh_scene_array.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.c_int]
+        h.sbh_scene_connectivity.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int32), C.c_int]
         h.sbh_scene_context.restype = C.c_void_p
         h.sbh_scene_context.argtypes = [C.c_void_p]
         _host = h
@@ -38,8 +40,9 @@ TOTAL_FIELDS = ["nodes", "tets", "ndofs", "h2d_bytes", "d2h_bytes", "launches", 
 
 
 class Scene:
-    """One BASELINE.json configuration: 'tetdrop' (C2: n^3 Soft_Rubber tet grid onto a fixed rigid floor, IPC + friction)
-    or 'tetbar' (C5: prescribed twisted bar, no contact)."""
+    """One BASELINE.json configuration: 'tetdrop' (C2: n^3 Soft_Rubber tet grid onto a fixed rigid floor, IPC + friction),
+    'tetbar' (C5: prescribed twisted bar, no contact), 'tetchain' (C4: tet block + hinged chain of boxes), 'cloth' /
+    'cloth_shells' (C1 / C3: n x n Cotton_Fabric grid over a scripted rigid box; flat-bending or discrete-shell hinges)."""
 
     def __init__(self, name, n, ny=-1, nz=-1, dt=0.01, drop=0.003, vz=0.0, device=0, stream=None):
         self.lib = load()
@@ -61,6 +64,23 @@ class Scene:
         out = (C.c_double * 8)()
         self.lib.sbh_scene_totals(self.h, out)
         return dict(zip(TOTAL_FIELDS, list(out)))
+
+    def array(self, label):
+        """Host copy of a bound array by label (flat)."""
+        n = self.lib.sbh_scene_array(self.h, label.encode(), None, 0)
+        if n < 0:
+            raise KeyError(label)
+        buf = np.empty(n)
+        self.lib.sbh_scene_array(self.h, label.encode(), buf.ctypes.data_as(C.POINTER(C.c_double)), n)
+        return buf
+
+    def connectivity(self, potential_name):
+        n = self.lib.sbh_scene_connectivity(self.h, potential_name.encode(), None, 0)
+        if n < 0:
+            raise KeyError(potential_name)
+        buf = np.empty(n, dtype=np.int32)
+        self.lib.sbh_scene_connectivity(self.h, potential_name.encode(), buf.ctypes.data_as(C.POINTER(C.c_int32)), n)
+        return buf
 
     def positions(self):
         n = int(self.totals()["nodes"])
