@@ -38,6 +38,7 @@ constexpr int PCG_THREADS = 1024;     // one CTA per SM
 constexpr int PCG_MAX_BLOCKS = 1024;  // upper bound of the cooperative grid (partial-sum arrays)
 constexpr int LANES_PER_ROW = 4;      // lanes cooperating on one block row of the SpMV
 constexpr int LONG_ROW = 96;          // rows with more blocks (rigid bodies in contact with many nodes) are swept by the whole CTA
+constexpr unsigned PCG_STREAM_SMEM = 112 * 1024;   // dynamic shared memory of a solve whose matrix streams (leaves ~96 KB of L1)
 constexpr int MAX_SEGS = 128;         // segments of the long rows of one CTA
 constexpr int MIN_SEG = 16;           // blocks per segment (longer when a CTA holds more than MAX_SEGS * MIN_SEG long-row blocks)
 constexpr int MAX_LONG_ROWS = 32;     // per CTA; further long rows fall back to the 4-lane path
@@ -83,6 +84,7 @@ struct Pcg {
     PcgResult* h_result = nullptr;
     int grid = 0;
     unsigned smem_bytes = 0;
+    unsigned smem_launch_last = 0;
 };
 static Pcg* get(sb_context* ctx)
 {
@@ -268,7 +270,10 @@ struct PcgPlan {
     unsigned long long t_start, t_loaded;
 };
 
-template<bool FAST>
+// MODE 1: every slice (row pointers, vectors, matrix, window) in shared memory.  MODE 2 (scenes whose matrix slice does not fit:
+// 66 k-node cloth, million-tet bars): the same, except that the matrix streams from global memory / L2 through the read-only
+// path every iteration.  MODE 0: anything may live in global memory (generic pointers; only tiny shared-memory budgets).
+template<int MODE>
 __device__ __forceinline__ void pcg_body(const PcgArgs& A, const PcgPlan& P)
 {
     const int G = gridDim.x;
@@ -290,15 +295,17 @@ __device__ __forceinline__ void pcg_body(const PcgArgs& A, const PcgPlan& P)
     const bool own_in_win = P.own_in_win;
     const unsigned win_bytes = P.win_bytes;
     const unsigned long long t_start = P.t_start, t_loaded = P.t_loaded;
-    int* rp = FAST ? reinterpret_cast<int*>(pcg_smem + P.off_rp) : P.rp;
-    double* rs = FAST ? reinterpret_cast<double*>(pcg_smem + P.off_r) : P.rs;
-    double* ps = FAST ? reinterpret_cast<double*>(pcg_smem + P.off_p) : P.ps;
-    double* ss = FAST ? reinterpret_cast<double*>(pcg_smem + P.off_s) : P.ss;
-    double* ws = FAST ? reinterpret_cast<double*>(pcg_smem + P.off_w) : P.ws;
-    float* dinv = FAST ? reinterpret_cast<float*>(pcg_smem + P.off_dinv) : P.dinv;
-    const int32_t* cols = FAST ? reinterpret_cast<const int32_t*>(pcg_smem + P.off_cols) : P.cols;
-    const float* vals = FAST ? reinterpret_cast<const float*>(pcg_smem + P.off_vals) : P.vals;
-    double* uwin = FAST ? reinterpret_cast<double*>(pcg_smem + P.off_win) : P.uwin;
+    int* rp = (MODE != 0) ? reinterpret_cast<int*>(pcg_smem + P.off_rp) : P.rp;
+    double* rs = (MODE != 0) ? reinterpret_cast<double*>(pcg_smem + P.off_r) : P.rs;
+    double* ps = (MODE != 0) ? reinterpret_cast<double*>(pcg_smem + P.off_p) : P.ps;
+    double* ss = (MODE != 0) ? reinterpret_cast<double*>(pcg_smem + P.off_s) : P.ss;
+    double* ws = (MODE != 0) ? reinterpret_cast<double*>(pcg_smem + P.off_w) : P.ws;
+    float* dinv = (MODE != 0) ? reinterpret_cast<float*>(pcg_smem + P.off_dinv) : P.dinv;
+    const int32_t* cols = (MODE == 1) ? reinterpret_cast<const int32_t*>(pcg_smem + P.off_cols) : P.cols;
+    const float* vals = (MODE == 1) ? reinterpret_cast<const float*>(pcg_smem + P.off_vals) : P.vals;
+    auto COL = [&](int j) -> int { return (MODE == 2) ? __ldg(cols + j) : cols[j]; };
+    auto VAL = [&](const float* q) -> float { return (MODE == 2) ? __ldg(q) : *q; };
+    double* uwin = (MODE != 0) ? reinterpret_cast<double*>(pcg_smem + P.off_win) : P.uwin;
     (void)G; (void)nbr; (void)bc;
     auto is_swept = [&](int lr) {   // long AND listed (every listed row gets its own block reduction)
         if (rp[lr + 1] - rp[lr] <= LONG_ROW) return false;
@@ -369,16 +376,16 @@ __device__ __forceinline__ void pcg_body(const PcgArgs& A, const PcgPlan& P)
                 for (int t = 0; t < U; t++) {
                     const int jj = j + t * LANES_PER_ROW;
                     a[t][0] = 0.0; a[t][1] = 0.0; a[t][2] = 0.0;
-                    if (jj < j1) gather3(cols[jj], a[t][0], a[t][1], a[t][2]);
+                    if (jj < j1) gather3(COL(jj), a[t][0], a[t][1], a[t][2]);
                 }
 #pragma unroll
                 for (int t = 0; t < U; t++) {
                     const int jj = j + t * LANES_PER_ROW;
                     if (jj < j1) {
                         const float* m = vals + 9 * (size_t)jj;   // column-major 3x3
-                        y0 += (double)m[0] * a[t][0] + (double)m[3] * a[t][1] + (double)m[6] * a[t][2];
-                        y1 += (double)m[1] * a[t][0] + (double)m[4] * a[t][1] + (double)m[7] * a[t][2];
-                        y2 += (double)m[2] * a[t][0] + (double)m[5] * a[t][1] + (double)m[8] * a[t][2];
+                        y0 += (double)VAL(m + 0) * a[t][0] + (double)VAL(m + 3) * a[t][1] + (double)VAL(m + 6) * a[t][2];
+                        y1 += (double)VAL(m + 1) * a[t][0] + (double)VAL(m + 4) * a[t][1] + (double)VAL(m + 7) * a[t][2];
+                        y2 += (double)VAL(m + 2) * a[t][0] + (double)VAL(m + 5) * a[t][1] + (double)VAL(m + 8) * a[t][2];
                     }
                 }
             }
@@ -422,9 +429,9 @@ __device__ __forceinline__ void pcg_body(const PcgArgs& A, const PcgPlan& P)
                 int lo = rp[lr], hi = rp[lr + 1];
                 while (lo < hi) {
                     const int mid = (lo + hi) >> 1;
-                    if (cols[mid] < 3 * br) lo = mid + 1; else hi = mid;
+                    if (COL(mid) < 3 * br) lo = mid + 1; else hi = mid;
                 }
-                if (lo < rp[lr + 1] && cols[lo] == 3 * br) {
+                if (lo < rp[lr + 1] && COL(lo) == 3 * br) {
                     const float* m = vals + 9 * (size_t)lo;
                     const float tmp0 = m[4] * m[8];
                     const float tmp1 = m[5] * m[5];
@@ -693,8 +700,9 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_solve(const PcgArgs A)
     P.rp = rp; P.rs = rs; P.ps = ps; P.ss = ss; P.ws = ws; P.dinv = dinv; P.cols = cols; P.vals = vals; P.uwin = uwin;
     P.s = s; P.bc2 = bc2; P.s_long = s_long; P.mbar = &s_mbar;
     P.t_start = t_start; P.t_loaded = global_ns();
-    if (rp_fit && vec_fit && mat_fit && own_in_win) pcg_body<true>(A, P);
-    else pcg_body<false>(A, P);
+    if (rp_fit && vec_fit && mat_fit && own_in_win) pcg_body<1>(A, P);
+    else if (rp_fit && vec_fit && own_in_win) pcg_body<2>(A, P);
+    else pcg_body<0>(A, P);
 }
 
 int solve_pcg_internal(sb_context* ctx, double abs_tol, double rel_tol, int max_iter, int stop_on_indef,
@@ -737,7 +745,22 @@ int solve_pcg_internal(sb_context* ctx, double abs_tol, double rel_tol, int max_
     A.rows = rows; A.cols = cols; A.vals = vals; A.grad = ctx->grad.p; A.dinv = P->dinv.p;
     A.x = P->x.p; A.r = P->r.p; A.p = P->p.p; A.s = P->s.p; A.w = P->w.p; A.u = P->u.p; A.u4 = P->u4.p; A.du = ctx->du.p;
     A.part = P->part.p; A.rp_scratch = P->rp_scratch.p; A.barrier = P->d_barrier; A.result = P->d_result;
-    A.nnzb = nnzb; A.smem_bytes = P->smem_bytes; A.instrument = ctx->profile ? 1 : 0;
+    // Shared memory of this launch.  When the slices fit (per-CTA estimate; the rows are cut by cost, see ROW_COST) the kernel
+    // takes everything and the matrix stays resident.  When they cannot, the matrix streams from L2 every iteration, and a
+    // full carve-out would leave no L1: every 4-byte load of a block would be its own L2 request (the SM's miss path takes
+    // ~2 cycles per request: 40 us per product at 66 k cloth nodes).  Such solves run with a smaller carve-out, so that the
+    // nine loads of a 36-byte block share one or two L1 line fills.
+    unsigned smem_launch = P->smem_bytes;
+    {
+        const double resident = 1.08 * (40.0 * (double)nnzb + 160.0 * (double)nbr) / P->grid;
+        if (resident > (double)P->smem_bytes) smem_launch = std::min(P->smem_bytes, PCG_STREAM_SMEM);
+    }
+    if (smem_launch != P->smem_launch_last) {
+        const int pct = (int)std::min<long>(100, (100L * (smem_launch + 16 * 1024)) / (228 * 1024) + 1);
+        SB_CUDA(ctx, cudaFuncSetAttribute(k_pcg_solve, cudaFuncAttributePreferredSharedMemoryCarveout, smem_launch == P->smem_bytes ? (int)cudaSharedmemCarveoutMaxShared : pct));
+        P->smem_launch_last = smem_launch;
+    }
+    A.nnzb = nnzb; A.smem_bytes = smem_launch; A.instrument = ctx->profile ? 1 : 0;
     A.nbr = nbr; A.abs_tol = abs_tol; A.rel_tol = rel_tol; A.max_iter = max_iter; A.stop_on_indef = stop_on_indef;
     SB_CUDA(ctx, cudaMemsetAsync(P->d_barrier, 0, sizeof(unsigned), st));
     // SB_PCG_DUMP=1: per-CTA cycle counters of every solve on stderr (load-balance diagnostics)
@@ -748,7 +771,7 @@ int solve_pcg_internal(sb_context* ctx, double abs_tol, double rel_tol, int max_
     A.dbg = dump ? d_dbg : nullptr;
     if (dump) A.instrument = 1;
     void* args[] = {(void*)&A};
-    SB_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_pcg_solve, dim3(P->grid), dim3(PCG_THREADS), args, P->smem_bytes, st));
+    SB_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_pcg_solve, dim3(P->grid), dim3(PCG_THREADS), args, smem_launch, st));
     ctx->launches += 1;
     SB_CUDA(ctx, cudaMemcpyAsync(P->h_result, P->d_result, sizeof(PcgResult), cudaMemcpyDeviceToHost, st));
     SB_CUDA(ctx, cudaStreamSynchronize(st));
