@@ -398,7 +398,7 @@ static int build_symbolic(sb_context* ctx, Assembly* A, bool rebuild_static_in)
     const uint32_t* ndb_dev = (A->D.n > 0) ? A->D.blk_of.p + (A->D.n - 1) : nullptr;
     if (nsb + ndb == 0) return fail(ctx, SB_ERR_STATE, "sb_assemble: no element Hessians");
     const size_t cap = nsb + ndb;   // upper bound of the merged pattern
-    A->seg4.ensure(cap + 1); A->blk_row.ensure(cap + 1); A->cols.ensure(cap + 1); A->vals.ensure(9 * cap + 9);
+    A->seg4.ensure(cap + 1); A->blk_row.ensure(cap + 1); A->cols.ensure(cap + 8); A->vals.ensure(9 * cap + 72);   // (slack: the PCG streams 4-block-aligned tiles that may run 3 blocks past the end)
     A->rows.ensure(A->nbr + 2); A->dirty.ensure(cap + 1); A->long_blocks.ensure(LONG_CAP);
     A->s_final.ensure(nsb + 1); A->d_final.ensure(ndb + 1);
     A->d_pos.ensure(ndb + 1); A->d_isnew.ensure(ndb + 1); A->d_newrank.ensure(ndb + 1); A->newpos.ensure(ndb + 1);

@@ -38,6 +38,8 @@ constexpr int PCG_THREADS = 1024;     // one CTA per SM
 constexpr int PCG_MAX_BLOCKS = 1024;  // upper bound of the cooperative grid (partial-sum arrays)
 constexpr int LANES_PER_ROW = 4;      // lanes cooperating on one block row of the SpMV
 constexpr int LONG_ROW = 96;          // rows with more blocks (rigid bodies in contact with many nodes) are swept by the whole CTA
+constexpr int PCG_TILE_BLOCKS = 768;                // blocks per streamed tile (multiple of 4: 16-byte granularity of the bulk copies)
+constexpr unsigned PCG_TILE_BYTES = PCG_TILE_BLOCKS * 40u;   // columns (4 B) then values (36 B) of the tile's blocks
 constexpr unsigned PCG_STREAM_SMEM = 112 * 1024;   // dynamic shared memory of a solve whose matrix streams (leaves ~96 KB of L1)
 constexpr int MAX_SEGS = 128;         // segments of the long rows of one CTA
 constexpr int MIN_SEG = 16;           // blocks per segment (longer when a CTA holds more than MAX_SEGS * MIN_SEG long-row blocks)
@@ -71,6 +73,8 @@ struct PcgArgs {
     unsigned long long nnzb;
     unsigned smem_bytes;            // dynamic shared memory of the launch
     int instrument;
+    int force_stream;               // test hook: never keep the matrix slice resident
+    int tiled;                      // experimental: stream through TMA-filled tile buffers (MODE 3) instead of ordinary loads
     long long* dbg;                 // [5 x grid + 2] per-CTA cycle counters (SB_PCG_DUMP diagnostics, else null)
 };
 
@@ -267,12 +271,20 @@ struct PcgPlan {
     int* rp; double *rs, *ps, *ss, *ws; float* dinv; const int32_t* cols; const float* vals; double* uwin;   // generic pointers
     double* s; double* bc2; int* s_long; unsigned long long* mbar;
     int n_seg; int *s_seg_j0, *s_seg_j1, *s_seg_first; double* s_seg_y;
+    unsigned long long b0;                 // first global block of the slice
+    unsigned off_tile[2];                  // tile buffers (MODE 2)
+    unsigned long long* tbar;              // their mbarriers
     unsigned long long t_start, t_loaded;
 };
 
-// MODE 1: every slice (row pointers, vectors, matrix, window) in shared memory.  MODE 2 (scenes whose matrix slice does not fit:
-// 66 k-node cloth, million-tet bars): the same, except that the matrix streams from global memory / L2 through the read-only
-// path every iteration.  MODE 0: anything may live in global memory (generic pointers; only tiny shared-memory budgets).
+// MODE 1: every slice (row pointers, vectors, matrix, window) in shared memory.  MODE 2 (the matrix slice does not fit: 66 k-node
+// cloth): row pointers, vectors and window in shared memory, the matrix read from global memory / L2 through the read-only
+// path every iteration.  MODE 3 (experimental, SB_PCG_TILED=1): as MODE 2, but the matrix slice streams through two
+// shared-memory tile buffers filled by TMA bulk copies (double buffered; the first two tiles of the next product are
+// prefetched under the vector phase and the barriers).  Measured at C2 with the matrix forced out of shared memory: product
+// 5.0 us resident, 11.4 us MODE 2, 19.8 us MODE 3 -- one 30 KB bulk copy in flight per SM does not cover the copy latency;
+// it needs a deeper ring of smaller tiles before it can replace MODE 2.  MODE 0: anything may live in global memory (generic
+// pointers; million-tet slices, tiny budgets).
 template<int MODE>
 __device__ __forceinline__ void pcg_body(const PcgArgs& A, const PcgPlan& P)
 {
@@ -303,8 +315,8 @@ __device__ __forceinline__ void pcg_body(const PcgArgs& A, const PcgPlan& P)
     float* dinv = (MODE != 0) ? reinterpret_cast<float*>(pcg_smem + P.off_dinv) : P.dinv;
     const int32_t* cols = (MODE == 1) ? reinterpret_cast<const int32_t*>(pcg_smem + P.off_cols) : P.cols;
     const float* vals = (MODE == 1) ? reinterpret_cast<const float*>(pcg_smem + P.off_vals) : P.vals;
-    auto COL = [&](int j) -> int { return (MODE == 2) ? __ldg(cols + j) : cols[j]; };
-    auto VAL = [&](const float* q) -> float { return (MODE == 2) ? __ldg(q) : *q; };
+    auto COL = [&](int j) -> int { return (MODE >= 2) ? __ldg(cols + j) : cols[j]; };
+    auto VAL = [&](const float* q) -> float { return (MODE >= 2) ? __ldg(q) : *q; };
     double* uwin = (MODE != 0) ? reinterpret_cast<double*>(pcg_smem + P.off_win) : P.uwin;
     (void)G; (void)nbr; (void)bc;
     auto is_swept = [&](int lr) {   // long AND listed (every listed row gets its own block reduction)
@@ -417,6 +429,116 @@ __device__ __forceinline__ void pcg_body(const PcgArgs& A, const PcgPlan& P)
         return wu;
     };
 
+    // ---- MODE 3: product over streamed tiles ----
+    constexpr int TB = PCG_TILE_BLOCKS;
+    const int nb_own = rp[nr];
+    const int d_al = (int)(P.b0 & 3ull);                               // the slice starts d_al blocks into its first (4-aligned) tile
+    const int n_tiles = (MODE == 3 && nb_own > 0) ? (nb_own + d_al + TB - 1) / TB : 0;
+    unsigned long long* tbar = P.tbar;
+    unsigned tphase[2] = {0u, 0u};
+    bool tloaded[2] = {false, false};
+    int tile_use = 0;
+    auto tile_cols = [&](int buf) { return reinterpret_cast<int32_t*>(pcg_smem + P.off_tile[buf]); };
+    auto tile_vals = [&](int buf) { return reinterpret_cast<float*>(pcg_smem + P.off_tile[buf] + TB * 4); };
+    auto issue_tile = [&](int t, int buf) {   // (one thread)
+        const int first = t * TB;
+        const unsigned cnt = (unsigned)min(TB, (nb_own + d_al - first + 3) & ~3);   // may run up to 3 blocks past the slice (allocation slack)
+        const unsigned long long start = (P.b0 - (unsigned long long)d_al) + (unsigned long long)first;
+        asm volatile("fence.proxy.async;" ::: "memory");
+        mbar_expect_tx(&tbar[buf], cnt * 40u);
+        tma_load_bulk(tile_cols(buf), A.cols + start, cnt * 4u, &tbar[buf]);
+        tma_load_bulk(tile_vals(buf), A.vals + 9 * start, cnt * 36u, &tbar[buf]);
+    };
+    if (MODE == 3 && tid == 0) {
+        if (n_tiles > 0) issue_tile(0, 0);
+        if (n_tiles > 1) issue_tile(1, 1);
+    }
+    auto spmv_tiled = [&]() -> double {
+        for (int i = tid; i < 3 * nr; i += PCG_THREADS) ws[i] = 0.0;
+        for (int i = tid; i < 3 * n_seg; i += PCG_THREADS) s_seg_y[i] = 0.0;
+        __syncthreads();
+        for (int tt = 0; tt < n_tiles; tt++) {
+            const int buf = (n_tiles > 2) ? (tile_use & 1) : tt;   // (one or two tiles: they stay where they were loaded)
+            if (n_tiles > 2 || !tloaded[buf]) {
+                mbar_wait(&tbar[buf], tphase[buf]);
+                tphase[buf] ^= 1u;
+                tloaded[buf] = true;
+            }
+            const int tb0 = tt * TB - d_al;                        // local block range of the tile (negative start in tile 0)
+            const int lo = max(tb0, 0), hi = min(tb0 + TB, nb_own);
+            // rows [ra, rb) and segments [sa, sb) with blocks in [lo, hi)
+            int ra, rb, sa, sb;
+            { int a = 0, b = nr; while (a < b) { const int m = (a + b) >> 1; if (rp[m + 1] <= lo) a = m + 1; else b = m; } ra = a; }
+            { int a = ra, b = nr; while (a < b) { const int m = (a + b) >> 1; if (rp[m] < hi) a = m + 1; else b = m; } rb = a; }
+            { int a = 0, b = n_seg; while (a < b) { const int m = (a + b) >> 1; if (s_seg_j1[m] <= lo) a = m + 1; else b = m; } sa = a; }
+            { int a = sa, b = n_seg; while (a < b) { const int m = (a + b) >> 1; if (s_seg_j0[m] < hi) a = m + 1; else b = m; } sb = a; }
+            const int n_rows_t = rb - ra, n_items = n_rows_t + (sb - sa);
+            const int32_t* tc = tile_cols(buf) - tb0;              // indexed by the local block number
+            const float* tv = tile_vals(buf) - 9 * tb0;
+            for (int base = 0; base < n_items; base += rows_per_pass) {
+                const int it2 = base + tid / LANES_PER_ROW;
+                int j0 = 0, j1 = 0, row = -1, seg = -1;
+                if (it2 < n_rows_t) {
+                    const int g = ra + it2;
+                    if (!is_swept(g)) { j0 = max(rp[g], lo); j1 = min(rp[g + 1], hi); row = g; }
+                } else if (it2 < n_items) {
+                    seg = sa + (it2 - n_rows_t);
+                    j0 = max(s_seg_j0[seg], lo); j1 = min(s_seg_j1[seg], hi);
+                }
+                double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+                constexpr int U = 4;
+                for (int j = j0 + lane; j < j1; j += U * LANES_PER_ROW) {
+                    double a[U][3];
+#pragma unroll
+                    for (int t = 0; t < U; t++) {
+                        const int jj = j + t * LANES_PER_ROW;
+                        a[t][0] = 0.0; a[t][1] = 0.0; a[t][2] = 0.0;
+                        if (jj < j1) gather3(tc[jj], a[t][0], a[t][1], a[t][2]);
+                    }
+#pragma unroll
+                    for (int t = 0; t < U; t++) {
+                        const int jj = j + t * LANES_PER_ROW;
+                        if (jj < j1) {
+                            const float* m = tv + 9 * jj;
+                            y0 += (double)m[0] * a[t][0] + (double)m[3] * a[t][1] + (double)m[6] * a[t][2];
+                            y1 += (double)m[1] * a[t][0] + (double)m[4] * a[t][1] + (double)m[7] * a[t][2];
+                            y2 += (double)m[2] * a[t][0] + (double)m[5] * a[t][1] + (double)m[8] * a[t][2];
+                        }
+                    }
+                }
+                for (int o = LANES_PER_ROW / 2; o > 0; o >>= 1) {
+                    y0 += __shfl_down_sync(0xffffffffu, y0, o, LANES_PER_ROW);
+                    y1 += __shfl_down_sync(0xffffffffu, y1, o, LANES_PER_ROW);
+                    y2 += __shfl_down_sync(0xffffffffu, y2, o, LANES_PER_ROW);
+                }
+                if (lane == 0 && row >= 0) { ws[3 * row] += y0; ws[3 * row + 1] += y1; ws[3 * row + 2] += y2; }   // (a row split over two tiles adds twice)
+                if (lane == 0 && seg >= 0) { s_seg_y[3 * seg] += y0; s_seg_y[3 * seg + 1] += y1; s_seg_y[3 * seg + 2] += y2; }
+            }
+            __syncthreads();     // the buffer is free, and this tile's sums are visible to the next tile's
+            if (n_tiles > 2 && tid == 0) issue_tile((tt + 2) % max(n_tiles, 1), buf);
+            tile_use++;
+        }
+        if (n_long) {
+            if (tid < 3 * n_long) {
+                const int q = tid / 3, c = tid % 3;
+                double t = 0.0;
+                for (int k = s_seg_first[q]; k < s_seg_first[q + 1]; k++) t += s_seg_y[3 * k + c];
+                ws[3 * s_long[q] + c] = t;
+            }
+            __syncthreads();
+        }
+        double wu = 0.0;
+        for (int i = tid; i < 3 * nr; i += PCG_THREADS) wu += uo(i) * ws[i];
+        return wu;
+    };
+    auto product = [&]() -> double { return (MODE == 3) ? spmv_tiled() : spmv(); };
+    // no bulk copy may be in flight when the CTA leaves
+    auto drain_tiles = [&]() {
+        if (MODE != 3) return;
+        for (int buf = 0; buf < 2 && buf < n_tiles; buf++)
+            if (n_tiles > 2 || !tloaded[buf]) mbar_wait(&tbar[buf], tphase[buf]);
+    };
+
     // ---- phase 0: M^-1 = block-Jacobi inverse; x = 0, r = b = -grad, u = M^-1 r, p = s = 0 ; partials of b.b and r.u ----
     {
         double bb = 0.0, ru = 0.0;
@@ -482,7 +604,7 @@ __device__ __forceinline__ void pcg_body(const PcgArgs& A, const PcgPlan& P)
     if (!done) {
         // ---- first product: w = A u ; delta = w.u = p^T A p of the first iteration ----
         load_window();
-        const double wu = spmv();
+        const double wu = product();
         const double t = block_sum(wu, s);
         if (tid == 0) __stcg(part2 + blockIdx.x, t);
         PCG_TICK(c_spmv);
@@ -534,7 +656,7 @@ __device__ __forceinline__ void pcg_body(const PcgArgs& A, const PcgPlan& P)
         if (it >= A.max_iter) { done = 3; break; }
         // ---- w = A u ; delta = w.u ----
         {
-            const double wu = spmv();
+            const double wu = product();
             const double t = block_sum(wu, s);
             if (tid == 0) __stcg(part2 + blockIdx.x, t);
         }
@@ -553,6 +675,7 @@ __device__ __forceinline__ void pcg_body(const PcgArgs& A, const PcgPlan& P)
         alpha = gamma / pAp;
     }
 
+    drain_tiles();
     // ---- du = x ; du.grad and |du|_inf ----
     {
         double dg = 0.0, mx = 0.0;
@@ -601,6 +724,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_solve(const PcgArgs A)
     __shared__ double s_seg_y[3 * MAX_SEGS];
     __shared__ int s_n_long;
     __shared__ __align__(8) unsigned long long s_mbar;
+    __shared__ __align__(8) unsigned long long s_tbar[2];
     const unsigned long long t_start = global_ns();
     const int G = gridDim.x;
     const int nbr = A.nbr;
@@ -612,6 +736,8 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_solve(const PcgArgs A)
         s_range[0] = row_lower_bound(A.rows, nbr, (cost * blockIdx.x) / G);
         s_range[1] = (blockIdx.x == G - 1) ? nbr : row_lower_bound(A.rows, nbr, (cost * (blockIdx.x + 1)) / G);
         mbar_init(&s_mbar, 1);
+        mbar_init(&s_tbar[0], 1);
+        mbar_init(&s_tbar[1], 1);
     }
     __syncthreads();
     const int r0 = s_range[0], nr = s_range[1] - s_range[0];
@@ -643,7 +769,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_solve(const PcgArgs A)
     // what is left after the vectors); at least the own rows, else no window at all
     const size_t mat_bytes = ((sizeof(int) * (size_t)nb + 15) & ~(size_t)15) + ((sizeof(float) * 9 * (size_t)nb + 15) & ~(size_t)15);
     const size_t min_win = ((sizeof(double) * 3 * ((size_t)nr + 2) + 15) & ~(size_t)15);
-    const bool mat_fit = vec_fit && off + mat_bytes + min_win <= A.smem_bytes;
+    const bool mat_fit = !A.force_stream && vec_fit && off + mat_bytes + min_win <= A.smem_bytes;
     const int32_t* cols; const float* vals;
     if (mat_fit) {
         P.off_cols = (unsigned)off; int32_t* cs = reinterpret_cast<int32_t*>(smem + carve(sizeof(int) * (size_t)nb));
@@ -653,6 +779,14 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_solve(const PcgArgs A)
         cols = cs; vals = vs;
     } else {
         cols = A.cols + b0; vals = A.vals + 9 * b0;
+    }
+    // streamed matrix: two tile buffers, if they fit next to the vectors and a window of at least the own rows
+    bool tile_fit = false;
+    P.off_tile[0] = P.off_tile[1] = 0;
+    if (A.tiled && !mat_fit && vec_fit && off + 2 * (size_t)PCG_TILE_BYTES + min_win <= A.smem_bytes) {
+        tile_fit = true;
+        P.off_tile[0] = (unsigned)carve(PCG_TILE_BYTES);
+        P.off_tile[1] = (unsigned)carve(PCG_TILE_BYTES);
     }
     int w0 = r0, nwin = 0;     // window = block rows [w0, w0 + nwin)
     double* uwin = nullptr;
@@ -679,8 +813,15 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_solve(const PcgArgs A)
         }
     __syncthreads();
     const int n_long = min(s_n_long, MAX_LONG_ROWS);
-    // cut the listed long rows into segments of equal length (at most MAX_SEGS in all)
+    // cut the listed long rows into segments of equal length (at most MAX_SEGS in all); rows in ascending order, so that the
+    // segments are ordered by their first block (the streamed product finds a tile's segments by bisection)
     if (tid == 0) {
+        for (int i = 1; i < n_long; i++) {
+            const int v = s_long[i];
+            int k = i - 1;
+            while (k >= 0 && s_long[k] > v) { s_long[k + 1] = s_long[k]; k--; }
+            s_long[k + 1] = v;
+        }
         long long total = 0;
         for (int q = 0; q < n_long; q++) total += rp[s_long[q] + 1] - rp[s_long[q]];
         int seg_len = MIN_SEG;
@@ -700,7 +841,9 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_solve(const PcgArgs A)
     P.rp = rp; P.rs = rs; P.ps = ps; P.ss = ss; P.ws = ws; P.dinv = dinv; P.cols = cols; P.vals = vals; P.uwin = uwin;
     P.s = s; P.bc2 = bc2; P.s_long = s_long; P.mbar = &s_mbar;
     P.t_start = t_start; P.t_loaded = global_ns();
+    P.b0 = b0; P.tbar = s_tbar;
     if (rp_fit && vec_fit && mat_fit && own_in_win) pcg_body<1>(A, P);
+    else if (rp_fit && vec_fit && tile_fit && own_in_win) pcg_body<3>(A, P);
     else if (rp_fit && vec_fit && own_in_win) pcg_body<2>(A, P);
     else pcg_body<0>(A, P);
 }
@@ -746,14 +889,17 @@ int solve_pcg_internal(sb_context* ctx, double abs_tol, double rel_tol, int max_
     A.x = P->x.p; A.r = P->r.p; A.p = P->p.p; A.s = P->s.p; A.w = P->w.p; A.u = P->u.p; A.u4 = P->u4.p; A.du = ctx->du.p;
     A.part = P->part.p; A.rp_scratch = P->rp_scratch.p; A.barrier = P->d_barrier; A.result = P->d_result;
     // Shared memory of this launch.  When the slices fit (per-CTA estimate; the rows are cut by cost, see ROW_COST) the kernel
-    // takes everything and the matrix stays resident.  When they cannot, the matrix streams from L2 every iteration, and a
-    // full carve-out would leave no L1: every 4-byte load of a block would be its own L2 request (the SM's miss path takes
-    // ~2 cycles per request: 40 us per product at 66 k cloth nodes).  Such solves run with a smaller carve-out, so that the
-    // nine loads of a 36-byte block share one or two L1 line fills.
+    // takes everything and the matrix stays resident.  Otherwise the matrix is read with ordinary loads every iteration, and a
+    // full carve-out would leave no L1: every 4-byte load of a block would be its own L2 request (the SM's miss path takes ~2
+    // cycles per request).  Such solves run with a smaller carve-out, so that the nine loads of a 36-byte block share one or two
+    // L1 line fills.  (The experimental tiled mode needs no L1 and takes everything again.)
     unsigned smem_launch = P->smem_bytes;
     {
         const double resident = 1.08 * (40.0 * (double)nnzb + 160.0 * (double)nbr) / P->grid;
-        if (resident > (double)P->smem_bytes) smem_launch = std::min(P->smem_bytes, PCG_STREAM_SMEM);
+        const double rows_max = 1.6 * (double)nbr / P->grid;                               // (sparse-row slices hold more rows)
+        const double tiled = 140.0 * rows_max + 2.0 * PCG_TILE_BYTES + 24.0 * (rows_max + 2.0) + 64.0;
+        static const bool tiled_on = std::getenv("SB_PCG_TILED") != nullptr;
+        if (resident > (double)P->smem_bytes && (!tiled_on || tiled > (double)P->smem_bytes)) smem_launch = std::min(P->smem_bytes, PCG_STREAM_SMEM);
     }
     if (smem_launch != P->smem_launch_last) {
         const int pct = (int)std::min<long>(100, (100L * (smem_launch + 16 * 1024)) / (228 * 1024) + 1);
@@ -761,6 +907,11 @@ int solve_pcg_internal(sb_context* ctx, double abs_tol, double rel_tol, int max_
         P->smem_launch_last = smem_launch;
     }
     A.nnzb = nnzb; A.smem_bytes = smem_launch; A.instrument = ctx->profile ? 1 : 0;
+    // test hook: SB_PCG_FORCE_STREAM=1 sends scenes that would be resident through the streamed-tile product
+    static const bool force_stream = std::getenv("SB_PCG_FORCE_STREAM") != nullptr;
+    A.force_stream = force_stream ? 1 : 0;
+    static const bool tiled_env = std::getenv("SB_PCG_TILED") != nullptr;
+    A.tiled = tiled_env ? 1 : 0;
     A.nbr = nbr; A.abs_tol = abs_tol; A.rel_tol = rel_tol; A.max_iter = max_iter; A.stop_on_indef = stop_on_indef;
     SB_CUDA(ctx, cudaMemsetAsync(P->d_barrier, 0, sizeof(unsigned), st));
     // SB_PCG_DUMP=1: per-CTA cycle counters of every solve on stderr (load-balance diagnostics)

@@ -131,3 +131,45 @@ def test_cloth_host_tables_equal_reference():
             b = np.asarray(g[f"array{ref_id}"]).reshape(-1, width)
             assert a.shape == b.shape, (label, a.shape, b.shape)
             assert np.abs(a - b).max() <= 1e-14 * max(1.0, np.abs(b).max()), label   # (a few ulp: cotangent sums)
+
+
+@pytest.mark.gpu
+def test_streamed_matrix_product_matches_resident():
+    """Scenes whose matrix slice does not fit in shared memory (66 k-node cloth) read it from L2 every iteration (pcg.cu
+    MODE 2) or, experimentally, stream it through TMA-filled tile buffers (MODE 3, SB_PCG_TILED=1).  SB_PCG_FORCE_STREAM=1
+    sends a mid-sized contact scene (3-4 tiles per CTA, rows split across tiles, rigid-body long rows cut into segments)
+    down those paths; the trajectories must equal the resident one up to the summation order inside a block row."""
+    import os, subprocess, sys, textwrap
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = textwrap.dedent("""
+        import sys, json
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        from stark_b200 import scenes
+        sc = scenes.Scene("tetdrop", n=22)
+        log = []
+        for _ in range(6):
+            s = sc.step()
+            log.append([s["accepted"], s["newton_iterations"], s["cg_iterations"], s["first_residual"]])
+        x = sc.positions()
+        print(json.dumps({"log": log, "x": x[::97].tolist()}))
+    """) % (here, os.path.dirname(here))
+    out = []
+    for force, tiled in ((False, False), (True, False), (True, True)):
+        env = dict(os.environ)
+        env.pop("SB_PCG_FORCE_STREAM", None)
+        env.pop("SB_PCG_TILED", None)
+        if force:
+            env["SB_PCG_FORCE_STREAM"] = "1"
+        if tiled:
+            env["SB_PCG_TILED"] = "1"
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    a = out[0]
+    for b in out[1:]:
+        for sa, sb in zip(a["log"], b["log"]):
+            assert sa[0] == sb[0] and sa[1] == sb[1], (sa, sb)
+            assert abs(sa[2] - sb[2]) <= 2, (sa, sb)
+            assert abs(sa[3] - sb[3]) <= 1e-6 * abs(sa[3]), (sa, sb)
+        xa, xb = np.array(a["x"]), np.array(b["x"])
+        assert np.abs(xa - xb).max() <= 1e-8
