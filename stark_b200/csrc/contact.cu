@@ -340,8 +340,8 @@ __global__ void k_tile_pairs_all(Dev d, int Tv, int Tt, int Te, int n0, int n1, 
 
 // all-pairs test inside the overlapping tile pairs (persistent CTAs, B tile staged in shared memory)
 constexpr int QCAP = 2048;
-struct BroadSmem {
-    float bb[TILE][6];
+struct alignas(16) BroadSmem {
+    float bb[TILE][8];       // (min xyz, max xyz, 2 pad: one 128-bit + one 64-bit shared load per box)
     int v[TILE][3];
     int g[TILE];
     int id[TILE];
@@ -351,7 +351,7 @@ struct BroadSmem {
 template<int KIND>
 __device__ void broad_kind(const Dev& d, BroadSmem& S)
 {
-    float (*s_bb)[6] = S.bb;
+    float (*s_bb)[8] = S.bb;
     int (*s_v)[3] = S.v;
     int* s_g = S.g;
     int* s_id = S.id;
@@ -385,18 +385,26 @@ __device__ void broad_kind(const Dev& d, BroadSmem& S)
             }
         }
         __syncthreads();
-        if (a < nA) {
+        {
+            // (every thread walks the B tile, so that the warp can skip a box none of its lanes overlaps with one vote: with a
+            //  hit rate of a few per thousand tests, everything after the box test is off the common path)
+            const bool act = a < nA;
+            const int aa = act ? a : 0;
             float ba[6];
-            for (int c = 0; c < 6; c++) ba[c] = bbA[6 * a + c];
-            const int pa = permA[a];
+            for (int c = 0; c < 6; c++) ba[c] = bbA[6 * aa + c];
+            const int pa = permA[aa];
             int va0, va1, ga;
             if (KIND == 0) { va0 = pa; va1 = -2; ga = d.v_group[pa]; }
             else { va0 = d.edge[2 * pa]; va1 = d.edge[2 * pa + 1]; ga = d.e_group[pa]; }
             const int nb = min(TILE, nB - b0);
             for (int j = 0; j < nb; j++) {
                 const int b = b0 + j;
-                if (KIND == 1 && b <= a) continue;     // every unordered pair of slots once
-                if (!bb_overlap(ba, s_bb[j])) continue;
+                const float4 blo = *reinterpret_cast<const float4*>(&s_bb[j][0]);   // min x, min y, min z, max x
+                const float2 bhi = *reinterpret_cast<const float2*>(&s_bb[j][4]);   // max y, max z
+                bool hit = act && !(ba[0] > blo.w || blo.x > ba[3] || ba[1] > bhi.x || blo.y > ba[4] || ba[2] > bhi.y || blo.z > ba[5]);
+                if (KIND == 1 && b <= a) hit = false;  // every unordered pair of slots once
+                if (!__any_sync(0xffffffffu, hit)) continue;
+                if (!hit) continue;
                 const int gb = s_g[j];
                 // shared-vertex ("orphan") discard: same set and a common vertex (collision vertex ids are global, so equality suffices)
                 const bool orphan = (va0 == s_v[j][0]) || (va0 == s_v[j][1]) || (va0 == s_v[j][2]) || (va1 == s_v[j][0]) || (va1 == s_v[j][1]) || (va1 == s_v[j][2]);
