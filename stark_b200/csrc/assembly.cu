@@ -77,6 +77,11 @@ struct Assembly {
     int* h_counts = nullptr;
     uint64_t assembled_eval = 0;     // evaluation the values belong to
     bool numeric_valid = false;
+    // symbolic phase launched ahead on a side stream by the P+G+H evaluation (see assembly_prefetch_symbolic)
+    bool pf_pending = false;
+    uint64_t pf_static = 0, pf_dynamic = 0;
+    size_t pf_n_src = 0;
+    cudaEvent_t ev_sym = nullptr;
 };
 
 static Assembly* get(sb_context* ctx)
@@ -85,6 +90,7 @@ static Assembly* get(sb_context* ctx)
         ctx->assembly = new Assembly();
         cudaMalloc(&ctx->assembly->d_counts, 4 * sizeof(int));
         cudaMallocHost(&ctx->assembly->h_counts, 4 * sizeof(int));
+        cudaEventCreateWithFlags(&ctx->assembly->ev_sym, cudaEventDisableTiming);
     }
     return ctx->assembly;
 }
@@ -98,6 +104,7 @@ void assembly_destroy(sb_context* ctx)
     A->dirty.release(); A->long_blocks.release(); A->descs.release();
     if (A->d_counts) cudaFree(A->d_counts);
     if (A->h_counts) cudaFreeHost(A->h_counts);
+    if (A->ev_sym) { cudaEventSynchronize(A->ev_sym); cudaEventDestroy(A->ev_sym); }
     delete A;
     ctx->assembly = nullptr;
 }
@@ -332,9 +339,8 @@ __global__ void k_clear_dirty(uint8_t* __restrict__ dirty, size_t nnzb)
 }
 
 // sort + reduce one class of sources
-static int build_set(sb_context* ctx, Assembly* A, SourceSet& X, bool dynamic)
+static int build_set(sb_context* ctx, Assembly* A, SourceSet& X, bool dynamic, cudaStream_t st)
 {
-    cudaStream_t st = ctx->stream;
     size_t n = 0;
     for (auto& p : ctx->potentials) if (p.dynamic == dynamic) n += (size_t)p.n_elem * p.k->nb * p.k->nb;
     X.n = n;
@@ -379,11 +385,11 @@ static int build_set(sb_context* ctx, Assembly* A, SourceSet& X, bool dynamic)
     return 0;
 }
 
-static int build_symbolic(sb_context* ctx, Assembly* A, bool rebuild_static_in)
+// Phase A of the symbolic build, on stream st, without a host synchronisation: sort the sources, merge the dynamic blocks into
+// the static list, and start the copy of the block count to the host.  Phase B (below) needs that count.
+static int symbolic_phase_a(sb_context* ctx, Assembly* A, bool rebuild_static_in, cudaStream_t st)
 {
     bool rebuild_static = rebuild_static_in;
-    StageTimer timer(ctx, ST_ASM_SYMBOLIC);
-    cudaStream_t st = ctx->stream;
     if (ctx->H_total >= (1ull << 32)) return fail(ctx, SB_ERR_STATE, "sb_assemble: element Hessian storage exceeds 32-bit offsets");
     A->nbr = ctx->ndofs / 3;
     {
@@ -392,8 +398,8 @@ static int build_symbolic(sb_context* ctx, Assembly* A, bool rebuild_static_in)
         if (bits != A->key_shift) { A->key_shift = bits; rebuild_static = true; }   // the static keys use the same encoding
     }
     int r;
-    if (rebuild_static && (r = build_set(ctx, A, A->S, false))) return r;
-    if ((r = build_set(ctx, A, A->D, true))) return r;
+    if (rebuild_static && (r = build_set(ctx, A, A->S, false, st))) return r;
+    if ((r = build_set(ctx, A, A->D, true, st))) return r;
     const size_t nsb = A->S.n_blocks, ndb = A->D.n_blocks;   // ndb: host-side UPPER bound (= number of dynamic sources)
     const uint32_t* ndb_dev = (A->D.n > 0) ? A->D.blk_of.p + (A->D.n - 1) : nullptr;
     if (nsb + ndb == 0) return fail(ctx, SB_ERR_STATE, "sb_assemble: no element Hessians");
@@ -424,7 +430,13 @@ static int build_symbolic(sb_context* ctx, Assembly* A, bool rebuild_static_in)
         ctx->launches++;
     }
     SB_CUDA(ctx, cudaMemcpyAsync(A->h_counts, A->d_counts, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    SB_CUDA(ctx, cudaStreamSynchronize(st));
+    return 0;
+}
+// Phase B, on the context stream, once phase A has completed (the caller has synchronised with it)
+static int symbolic_phase_b(sb_context* ctx, Assembly* A)
+{
+    cudaStream_t st = ctx->stream;
+    const size_t nsb = A->S.n_blocks;
     A->nnzb = nsb + (size_t)A->h_counts[1];
     k_row_ptr<<<(A->nbr + 1 + 255) / 256, 256, 0, st>>>(A->blk_row.p, A->rows.p, A->nbr, A->nnzb);
     k_find_long<<<(unsigned)((A->nnzb + 255) / 256), 256, 0, st>>>(A->seg4.p, A->long_blocks.p, A->d_counts, A->nnzb);
@@ -435,6 +447,14 @@ static int build_symbolic(sb_context* ctx, Assembly* A, bool rebuild_static_in)
     A->built_dynamic = ctx->dynamic_version;
     A->built_n_src = ctx->n_blocks_total;
     return 0;
+}
+static int build_symbolic(sb_context* ctx, Assembly* A, bool rebuild_static)
+{
+    StageTimer timer(ctx, ST_ASM_SYMBOLIC);
+    int r = symbolic_phase_a(ctx, A, rebuild_static, ctx->stream);
+    if (r) return r;
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return symbolic_phase_b(ctx, A);
 }
 
 static bool pattern_current(sb_context* ctx, Assembly* A)
@@ -454,6 +474,39 @@ void preload_assembly_kernels()
     cudaGetLastError();
 }
 
+static bool static_part_stale(sb_context* ctx, Assembly* A)
+{
+    return A->built_static != ctx->static_version || A->nbr != ctx->ndofs / 3 || A->S.n != ctx->n_static_blocks;
+}
+
+// Called by the P+G+H evaluation once the kernels of the dynamic (contact / friction) potentials are enqueued on the side
+// streams: if only the dynamic part of the pattern is stale -- every Newton iteration in contact -- the symbolic phase (a
+// chain of ~20 small kernels, ~120 us) is launched on a side stream NOW, behind those kernels, and runs under the volume
+// elements' evaluation, the reductions and the PD projection instead of after them.  assemble_internal picks the result up.
+void assembly_prefetch_symbolic(sb_context* ctx)
+{
+    Assembly* A = ctx->assembly;
+    if (!A || !A->numeric_valid || A->pf_pending || ctx->n_blocks_total == 0) return;
+    if (pattern_current(ctx, A) || static_part_stale(ctx, A)) return;
+    {
+        int bits = 1;
+        while ((1ll << bits) < ctx->ndofs / 3 + 1) bits++;
+        if (bits != A->key_shift) return;
+    }
+    cudaStream_t st = ctx->side[sb_context::N_SIDE - 1];
+    for (int k = 0; k < sb_context::N_SIDE; k++) cudaStreamWaitEvent(st, ctx->ev_join[k], 0);   // the dynamic potentials' block rows are written
+    if (symbolic_phase_a(ctx, A, false, st)) { cudaStreamSynchronize(st); return; }
+    cudaEventRecord(A->ev_sym, st);
+    A->pf_pending = true;
+    A->pf_static = ctx->static_version; A->pf_dynamic = ctx->dynamic_version; A->pf_n_src = ctx->n_blocks_total;
+}
+// before anything the prefetched phase reads (block rows, layout) is rewritten
+void assembly_prefetch_drain(sb_context* ctx)
+{
+    Assembly* A = ctx->assembly;
+    if (A && A->pf_pending) cudaEventSynchronize(A->ev_sym);
+}
+
 int assemble_internal(sb_context* ctx)
 {
     if (!ctx->have_pgh) return fail(ctx, SB_ERR_STATE, "sb_assemble: call sb_eval(SB_EVAL_PGH) first");
@@ -461,10 +514,22 @@ int assemble_internal(sb_context* ctx)
     if (ctx->n_blocks_total == 0) return fail(ctx, SB_ERR_STATE, "sb_assemble: no element Hessians");
     bool rebuilt = false;
     if (!pattern_current(ctx, A)) {
-        const bool rebuild_static = A->built_static != ctx->static_version || A->nbr != ctx->ndofs / 3 || A->S.n != ctx->n_static_blocks;
-        int r = build_symbolic(ctx, A, rebuild_static);
+        int r;
+        if (A->pf_pending && A->pf_static == ctx->static_version && A->pf_dynamic == ctx->dynamic_version && A->pf_n_src == ctx->n_blocks_total &&
+            !static_part_stale(ctx, A)) {
+            StageTimer timer(ctx, ST_ASM_SYMBOLIC);
+            SB_CUDA(ctx, cudaEventSynchronize(A->ev_sym));
+            r = symbolic_phase_b(ctx, A);
+        } else {
+            if (A->pf_pending) cudaEventSynchronize(A->ev_sym);   // (a stale prefetch: let it finish before its buffers are reused)
+            r = build_symbolic(ctx, A, static_part_stale(ctx, A));
+        }
+        A->pf_pending = false;
         if (r) return r;
         rebuilt = true;
+    } else if (A->pf_pending) {
+        cudaEventSynchronize(A->ev_sym);
+        A->pf_pending = false;
     }
     StageTimer timer(ctx, ST_ASM_NUMERIC);
     NumericArgs a;

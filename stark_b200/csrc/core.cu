@@ -137,6 +137,7 @@ int eval_internal(sb_context* ctx, int mode, double* out_E, double* out_grad_inf
 {
     if (mode != SB_EVAL_P && mode != SB_EVAL_PGH) return fail(ctx, SB_ERR_ARG, "sb_eval: unknown mode");
     StageTimer timer(ctx, mode == SB_EVAL_PGH ? ST_EVAL_PGH : ST_EVAL_P);
+    if (mode == SB_EVAL_PGH) assembly_prefetch_drain(ctx);   // (a prefetched symbolic phase still reads the previous evaluation's block rows)
     recompute_dof_offsets(ctx);
     if (ctx->ndofs <= 0) return fail(ctx, SB_ERR_STATE, "sb_eval: no degrees of freedom");
     if (ctx->ndofs % 3 != 0) return fail(ctx, SB_ERR_STATE, "sb_eval: ndofs must be divisible by 3");
@@ -238,6 +239,11 @@ int eval_internal(sb_context* ctx, int mode, double* out_E, double* out_grad_inf
             SB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[k], 0));
         }
     SB_CUDA(ctx, cudaGetLastError());
+    if (mode == SB_EVAL_PGH && fork) {   // the pattern of the coming assembly, under this evaluation
+        bool dyn_on_side = true;         // (the prefetch waits for the side streams only: every dynamic potential must be there)
+        for (auto& p : ctx->potentials) if (p.dynamic && p.n_elem >= SMALL) dyn_on_side = false;
+        if (dyn_on_side) assembly_prefetch_symbolic(ctx);
+    }
 
     reduce_sum(ctx, ctx->E_elem.p, E_total, ctx->d_scalars + 0);
     if (mode == SB_EVAL_PGH) {

@@ -61,6 +61,8 @@ void preload_eval_kernels();
 void preload_project_kernels();
 void projector_prepare(sb_context* ctx);
 void preload_assembly_kernels();
+void assembly_prefetch_symbolic(sb_context* ctx);   // assembly.cu: symbolic phase ahead of time on a side stream
+void assembly_prefetch_drain(sb_context* ctx);
 const std::vector<KernelInfo>& all_kernels();
 
 template<class T> struct DevBuf {
