@@ -9,11 +9,16 @@
 //   * CTA c owns a contiguous range of block rows holding ~nnzb / #SM blocks and copies ITS SLICE OF THE MATRIX (values,
 //     columns, row pointers) and of the vectors INTO SHARED MEMORY ONCE: at the 200k-tet scene the 21.7 MB matrix is
 //     spread over the 148 x 227 KB of shared memory of the chip and is never read from L2 / HBM again during the solve.
-//     Slices that do not fit (million-tet scenes) are streamed from global memory by the same code (generic pointers).
+//     Slices that do not fit (66 k-node cloth, million-tet scenes) are read from L2 every iteration instead (see the MODE
+//     comment at pcg_body: typed read-only-path loads with a smaller carve-out, or generic pointers when nothing fits).
+//   * Rows are cut into slices of equal  blocks + ROW_COST * rows;  rows with more than LONG_ROW blocks (a rigid body in
+//     contact with hundreds of nodes) are cut into segments that queue behind the ordinary rows as further 4-lane groups.
 //   * The only vector that crosses CTAs is the preconditioned residual u = M^-1 r (the SpMV operand).  Every iteration
 //     each CTA pulls the WINDOW of u around its own rows into shared memory with one TMA bulk copy
 //     (cp.async.bulk.shared.global + mbarrier) -- the band of a mesh-ordered matrix -- and gathers from shared memory;
-//     the few columns outside the window (rigid bodies, far contacts) are gathered from L2.
+//     the few columns outside the window (rigid bodies, hex-centre nodes, far contacts) are gathered from a padded copy of
+//     u in L2 with one 256-bit load each.  The copy of the next product's window is issued right after the barrier and
+//     lands under the dot-product reduction.
 //   * The recurrence is the Chronopoulos-Gear form of PCG (same iterates as the textbook form in exact arithmetic):
 //         p = u + beta p ; s = w + beta s ; x += alpha p ; r -= alpha s ; u = M^-1 r ; w = A u
 //         gamma' = r.u ; delta = w.u ; beta = gamma'/gamma ; alpha = gamma' / (delta - beta gamma'/alpha)
@@ -37,7 +42,7 @@ int bcsr_view(sb_context* ctx, int* nbr, size_t* nnzb, const unsigned long long*
 constexpr int PCG_THREADS = 1024;     // one CTA per SM
 constexpr int PCG_MAX_BLOCKS = 1024;  // upper bound of the cooperative grid (partial-sum arrays)
 constexpr int LANES_PER_ROW = 4;      // lanes cooperating on one block row of the SpMV
-constexpr int LONG_ROW = 96;          // rows with more blocks (rigid bodies in contact with many nodes) are swept by the whole CTA
+constexpr int LONG_ROW = 96;          // rows with more blocks (rigid bodies in contact with many nodes) are cut into segments
 constexpr int PCG_TILE_BLOCKS = 768;                // blocks per streamed tile (multiple of 4: 16-byte granularity of the bulk copies)
 constexpr unsigned PCG_TILE_BYTES = PCG_TILE_BLOCKS * 40u;   // columns (4 B) then values (36 B) of the tile's blocks
 constexpr unsigned PCG_STREAM_SMEM = 112 * 1024;   // dynamic shared memory of a solve whose matrix streams (leaves ~96 KB of L1)
