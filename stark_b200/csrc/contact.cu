@@ -1052,7 +1052,8 @@ static int reorder_primitives(sb_context* ctx, Contact* C)
     return 0;
 }
 
-// mode 0: proximity + contact tables; 1: proximity + friction tables; 2: intersections only; 3: proximity lists only + intersections
+// mode 0: proximity + contact tables; 1: proximity + friction tables; 2: intersections only; 3: proximity lists only + intersections;
+// 4: proximity + contact tables + intersections (a line-search trial: validity test and the tables of the evaluation that follows)
 static int detect(sb_context* ctx, Contact* C, int mode, double enlargement)
 {
     cudaStream_t st = ctx->stream;
@@ -1064,9 +1065,9 @@ static int detect(sb_context* ctx, Contact* C, int mode, double enlargement)
         // only the counters this mode rewrites are cleared (contact and friction tables live side by side): bit t = counters[t]
         auto bits = [](int lo, int n) { unsigned long long m = 0; for (int t = lo; t < lo + n; t++) m |= 1ull << t; return m; };
         unsigned long long clear = bits(0, 8);
-        if (mode == 0 || mode == 3) clear |= bits(8, 6) | bits(16, N_CONTACT_TABLES);
+        if (mode == 0 || mode == 3 || mode == 4) clear |= bits(8, 6) | bits(16, N_CONTACT_TABLES);
         if (mode == 1) clear |= bits(8, 6) | bits(16 + N_CONTACT_TABLES, N_FRICTION);
-        if (mode == 2 || mode == 3) clear |= bits(8 + 6, 1);
+        if (mode == 2 || mode == 3 || mode == 4) clear |= bits(8 + 6, 1);
         const int Tv = (d.n_v + TILE - 1) / TILE, Tt = (d.n_t + TILE - 1) / TILE, Te = (d.n_e + TILE - 1) / TILE;
         auto broad_grid = [](long long n_tile_pairs) { return (int)std::max(1ll, std::min(n_tile_pairs, 148ll * 16)); };
         (void)nmax;
@@ -1080,14 +1081,14 @@ static int detect(sb_context* ctx, Contact* C, int mode, double enlargement)
                 if (pt && ee) k_broad_all<0, 1><<<broad_grid((long long)n0 + n1), TILE, 0, st>>>(d);
                 else if (pt) k_broad_all<0, -1><<<broad_grid(n0), TILE, 0, st>>>(d);
                 else k_broad_all<1, -1><<<broad_grid(n1), TILE, 0, st>>>(d);
-                const int emit_mode = (mode == 3) ? 2 : mode;   // 2 = lists only (no table matches mode 2 inside emit_*)
+                const int emit_mode = (mode == 3) ? 2 : (mode == 4 ? 0 : mode);   // 2 = lists only (no table matches mode 2 inside emit_*)
                 k_narrow_all<<<148 * 2, 128, 0, st>>>(d, enlargement * enlargement, emit_mode, C->stiffness, 1e-30, pt ? 1 : 0, ee ? 1 : 0);
                 ctx->launches += 3;
             }
             ctx->launches += 1;
             clear = 0;   // (mode 3: the intersection pass below must not wipe what the proximity pass just counted)
         }
-        if (mode == 2 || mode == 3) {
+        if (mode == 2 || mode == 3 || mode == 4) {
             const float extra = 0.0f + FLT_EPSILON;   // IntersectionDetection uses non-enlarged AABBs (tmcd/BroadPhaseET.cpp:38)
             k_aabbs_tiles<<<Tv + Tt + Te, TILE, 0, st>>>(d, extra, 0, Tv, Tt, clear);
             ctx->launches++;
@@ -1116,8 +1117,9 @@ static int detect(sb_context* ctx, Contact* C, int mode, double enlargement)
     }
     for (int l = 0; l < N_LISTS; l++) C->h_list_count[l] = C->h_counters[8 + l];
     // publish the table sizes to the potentials / friction arrays
-    const int t0 = (mode == 0) ? 0 : N_CONTACT_TABLES, t1 = (mode == 0) ? N_CONTACT_TABLES : N_TABLES;
-    if (mode == 0 || mode == 1) {
+    const bool contact_tables = (mode == 0 || mode == 4);
+    const int t0 = contact_tables ? 0 : N_CONTACT_TABLES, t1 = contact_tables ? N_CONTACT_TABLES : N_TABLES;
+    if (mode == 0 || mode == 1 || mode == 4) {
         bool any = false;   // empty before and empty now: neither the connectivity nor the pattern changed
         for (int t = t0; t < t1; t++) any = any || C->h_counters[16 + t] != 0 || C->h_table_count[t] != 0 || ctx->potentials[C->pot[t]].n_elem != 0;
         for (int t = t0; t < t1; t++) {
@@ -1184,11 +1186,17 @@ int contact_intersections_internal(sb_context* ctx, int* out_count)
     StageTimer timer(ctx, ST_INTERSECTIONS);
     int r;
     if (C->topology_dirty && (r = upload_topology(ctx, C))) return r;
+    // A state that passes this test is evaluated next (line-search trial -> energy; accepted step -> next iteration), and
+    // that evaluation starts with a contact update at the very same state: both detections share one vertex update, one
+    // launch sequence and one host synchronisation.  (If the state is rejected the tables are simply rebuilt at the next one.)
+    const bool with_tables = !C->external_vertices && C->contacts_state != ctx->state_version;
+    if (with_tables && (r = refresh_params(ctx, C))) return r;
     if ((r = update_vertices(ctx, C, false))) return r;
-    if ((r = detect(ctx, C, 2, 0.0))) return r;
+    if ((r = detect(ctx, C, with_tables ? 4 : 2, with_tables ? 2.0 * max_thickness(C) : 0.0))) return r;
     *out_count = C->h_list_count[6];
     C->cached_intersections = *out_count;
     C->intersections_state = ctx->state_version;
+    if (with_tables) C->contacts_state = ctx->state_version;
     return 0;
 }
 
