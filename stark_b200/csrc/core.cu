@@ -136,8 +136,16 @@ int refresh_slots(sb_context* ctx, Potential& p)
 int eval_internal(sb_context* ctx, int mode, double* out_E, double* out_grad_inf, bool sync_scalars)
 {
     if (mode != SB_EVAL_P && mode != SB_EVAL_PGH) return fail(ctx, SB_ERR_ARG, "sb_eval: unknown mode");
+    // The line search evaluates its first trial state with gradient and Hessians (newton.cu): when the trial is accepted, the
+    // next iteration's evaluation is this one again -- same DoFs, same tables, element Hessians not yet projected.
+    if (mode == SB_EVAL_PGH && sync_scalars && ctx->have_pgh && ctx->pgh_cache_ok && ctx->pgh_state == ctx->state_version &&
+        ctx->pgh_dynamic == ctx->dynamic_version && ctx->pgh_static == ctx->static_version) {
+        if (out_E) *out_E = ctx->pgh_E;
+        if (out_grad_inf) *out_grad_inf = ctx->pgh_residual;
+        return 0;
+    }
     StageTimer timer(ctx, mode == SB_EVAL_PGH ? ST_EVAL_PGH : ST_EVAL_P);
-    if (mode == SB_EVAL_PGH) assembly_prefetch_drain(ctx);   // (a prefetched symbolic phase still reads the previous evaluation's block rows)
+    if (mode == SB_EVAL_PGH) { assembly_prefetch_drain(ctx); ctx->pgh_cache_ok = false; }   // (a prefetched symbolic phase still reads the previous evaluation's block rows)
     recompute_dof_offsets(ctx);
     if (ctx->ndofs <= 0) return fail(ctx, SB_ERR_STATE, "sb_eval: no degrees of freedom");
     if (ctx->ndofs % 3 != 0) return fail(ctx, SB_ERR_STATE, "sb_eval: ndofs must be divisible by 3");
@@ -255,6 +263,11 @@ int eval_internal(sb_context* ctx, int mode, double* out_E, double* out_grad_inf
         SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (out_E) *out_E = ctx->h_scalars[0];
         if (out_grad_inf && mode == SB_EVAL_PGH) *out_grad_inf = ctx->h_scalars[1];
+        if (mode == SB_EVAL_PGH) {
+            ctx->pgh_cache_ok = true;
+            ctx->pgh_state = ctx->state_version; ctx->pgh_dynamic = ctx->dynamic_version; ctx->pgh_static = ctx->static_version;
+            ctx->pgh_E = ctx->h_scalars[0]; ctx->pgh_residual = ctx->h_scalars[1];
+        }
     }
     return 0;
 }

@@ -182,6 +182,10 @@ struct sb_context {
     uint64_t state_version = 1;     // bumped whenever an array / the DoFs / the contact set-up change (caches keyed on the state)
     uint64_t eval_id = 0;           // bumped by every PGH evaluation (the element Hessians are rewritten)
     bool have_pgh = false;
+    // the last P+G+H evaluation, reusable while nothing it depends on has changed (see eval_internal)
+    bool pgh_cache_ok = false;
+    uint64_t pgh_state = 0, pgh_dynamic = 0, pgh_static = 0;
+    double pgh_E = 0.0, pgh_residual = 0.0;
 
     bool profile = false;           // stage profiling on (adds a stream synchronisation at every stage boundary)
     double stage_ms[32] = {0};

@@ -202,7 +202,11 @@ extern "C" int sb_newton_solve(sb_context* ctx, const sb_newton_settings* S, sb_
             int k = 0;
             for (; k < S->max_backtracking_armijo_iterations; ++k) {
                 if (contact && (rc = contact_update_internal(ctx))) return rc;
-                if ((rc = eval_internal(ctx, SB_EVAL_P, &E1, nullptr, true))) return rc;
+                // The first trial is almost always accepted, and the next iteration then evaluates energy, gradient and
+                // Hessians at this very state: evaluate them now (eval_internal hands the result out again) instead of the
+                // energy alone.  Later trials (after a backtrack) are energy-only.
+                if (k == 0) { double res_unused = 0.0; if ((rc = eval_internal(ctx, SB_EVAL_PGH, &E1, &res_unused, true))) return rc; }
+                else if ((rc = eval_internal(ctx, SB_EVAL_P, &E1, nullptr, true))) return rc;
                 if (E1 < E_threshold) break;
                 step *= 0.5;
                 if ((rc = sb_dofs_apply_step(ctx, step))) return rc;

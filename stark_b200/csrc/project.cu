@@ -470,6 +470,7 @@ int project_internal(sb_context* ctx, double grad_threshold, double eps, int mir
         return 0;
     }
     StageTimer timer(ctx, ST_PROJECT);
+    ctx->pgh_cache_ok = false;   // the element Hessians are about to be modified in place
     const auto t_begin = std::chrono::steady_clock::now();
     ProjTable T;
     T.n_pots = 0;
