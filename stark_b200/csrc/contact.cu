@@ -105,6 +105,7 @@ struct Contact {
     DevBuf<double> g_f64, mu;
     DevBuf<uint8_t> blacklist;
     DevBuf<float> bb_p, bb_t, bb_e, tb_p, tb_t, tb_e;
+    DevBuf<float> bb0_p, bb0_t, bb0_e, tb0_p, tb0_t, tb0_e;   // the intersection pass's own (non-enlarged) boxes: it runs beside the proximity pass
     DevBuf<int32_t> perm_p, perm_t, perm_e, perm_tmp;
     DevBuf<uint32_t> morton, morton_tmp;
     DevBuf<float> bounds;            // scene box (6 floats)
@@ -903,6 +904,7 @@ void contact_destroy(sb_context* ctx)
     if (!C) return;
     C->x.release(); C->v_group.release(); C->v_ps.release(); C->tri.release(); C->t_group.release(); C->edge.release(); C->e_group.release();
     C->g_i32.release(); C->g_f64.release(); C->mu.release(); C->blacklist.release(); C->bb_p.release(); C->bb_t.release(); C->bb_e.release(); C->tb_p.release(); C->tb_t.release(); C->tb_e.release();
+    C->bb0_p.release(); C->bb0_t.release(); C->bb0_e.release(); C->tb0_p.release(); C->tb0_t.release(); C->tb0_e.release();
     C->perm_p.release(); C->perm_t.release(); C->perm_e.release(); C->perm_tmp.release(); C->morton.release(); C->morton_tmp.release(); C->bounds.release(); C->sort_temp.release();
     for (int k = 0; k < 3; k++) C->tile_pairs[k].release();
     C->cand_pt.release(); C->cand_ee.release(); C->cand_et.release(); C->counters.release();
@@ -944,6 +946,7 @@ static int upload_topology(sb_context* ctx, Contact* C)
     up(C->g_i32, gi); up(C->g_f64, gf);
     C->x.ensure(3 * (size_t)nv + 3);
     C->bb_p.ensure(6 * (size_t)nv + 6); C->bb_t.ensure(6 * (size_t)nt + 6); C->bb_e.ensure(6 * (size_t)ne + 6);
+    C->bb0_p.ensure(6 * (size_t)nv + 6); C->bb0_t.ensure(6 * (size_t)nt + 6); C->bb0_e.ensure(6 * (size_t)ne + 6);
     C->perm_p.ensure(nv + 1); C->perm_t.ensure(nt + 1); C->perm_e.ensure(ne + 1);
     if (nv) k_iota<<<(nv + 255) / 256, 256, 0, st>>>(C->perm_p.p, nv);
     if (nt) k_iota<<<(nt + 255) / 256, 256, 0, st>>>(C->perm_t.p, nt);
@@ -969,6 +972,7 @@ static void ensure_capacities(sb_context* ctx, Contact* C)
         const size_t nv = C->h_v_group.size(), nt = C->h_t_group.size(), ne = C->h_e_group.size();
         const size_t Tv = (nv + TILE - 1) / TILE, Tt = (nt + TILE - 1) / TILE, Te = (ne + TILE - 1) / TILE;
         C->tb_p.ensure(6 * Tv + 6); C->tb_t.ensure(6 * Tt + 6); C->tb_e.ensure(6 * Te + 6);
+        C->tb0_p.ensure(6 * Tv + 6); C->tb0_t.ensure(6 * Tt + 6); C->tb0_e.ensure(6 * Te + 6);
         C->tile_pairs[0].ensure(Tv * Tt + 1); C->tile_pairs[1].ensure(Te * Te + 1); C->tile_pairs[2].ensure(Te * Tt + 1);
     }
     for (int l = 0; l < N_LISTS; l++) { C->list_ids[l].ensure((size_t)C->list_cap * LIST_WIDTH[l]); C->list_dist[l].ensure(C->list_cap); }
@@ -1061,6 +1065,9 @@ static int detect(sb_context* ctx, Contact* C, int mode, double enlargement)
     for (int attempt = 0; attempt < 8; attempt++) {
         ensure_capacities(ctx, C);
         Dev d = make_dev(ctx, C);
+        Dev d0 = d;   // the intersection pass's view: its own boxes
+        d0.bb_p = C->bb0_p.p; d0.bb_t = C->bb0_t.p; d0.bb_e = C->bb0_e.p; d0.tb_p = C->tb0_p.p; d0.tb_t = C->tb0_t.p; d0.tb_e = C->tb0_e.p;
+        const bool both = (mode == 3 || mode == 4);
         const int nmax = std::max(d.n_v, std::max(d.n_t, d.n_e));
         // only the counters this mode rewrites are cleared (contact and friction tables live side by side): bit t = counters[t]
         auto bits = [](int lo, int n) { unsigned long long m = 0; for (int t = lo; t < lo + n; t++) m |= 1ull << t; return m; };
@@ -1076,6 +1083,7 @@ static int detect(sb_context* ctx, Contact* C, int mode, double enlargement)
             const bool pt = C->enable_pt && d.n_t > 0 && d.n_v > 0, ee = C->enable_ee && d.n_e > 1;
             const int n0 = pt ? Tv * Tt : 0, n1 = ee ? Te * Te : 0;
             k_aabbs_tiles<<<Tv + Tt + Te, TILE, 0, st>>>(d, extra, 1, Tv, Tt, clear);
+            if (both) SB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));   // (the counters are cleared: the intersection pass may start)
             if (n0 + n1 > 0) {
                 k_tile_pairs_all<<<(n0 + n1 + 255) / 256, 256, 0, st>>>(d, Tv, Tt, Te, n0, n1, 0);
                 if (pt && ee) k_broad_all<0, 1><<<broad_grid((long long)n0 + n1), TILE, 0, st>>>(d);
@@ -1089,16 +1097,24 @@ static int detect(sb_context* ctx, Contact* C, int mode, double enlargement)
             clear = 0;   // (mode 3: the intersection pass below must not wipe what the proximity pass just counted)
         }
         if (mode == 2 || mode == 3 || mode == 4) {
+            // The intersection pass has its own boxes, tile-pair list, candidate list and counters: next to a proximity pass it
+            // runs on a side stream at the same time (both are chains of latency-bound kernels).
             const float extra = 0.0f + FLT_EPSILON;   // IntersectionDetection uses non-enlarged AABBs (tmcd/BroadPhaseET.cpp:38)
-            k_aabbs_tiles<<<Tv + Tt + Te, TILE, 0, st>>>(d, extra, 0, Tv, Tt, clear);
+            cudaStream_t s2 = both ? ctx->side[0] : st;
+            if (both) SB_CUDA(ctx, cudaStreamWaitEvent(s2, ctx->ev_fork, 0));
+            k_aabbs_tiles<<<Tv + Tt + Te, TILE, 0, s2>>>(d0, extra, 0, Tv, Tt, clear);
             ctx->launches++;
             if (d.n_e > 0 && d.n_t > 0) {
-                k_tile_pairs_all<<<(Te * Tt + 255) / 256, 256, 0, st>>>(d, Tv, Tt, Te, 0, Te * Tt, 1);
-                k_broad_all<2, -1><<<broad_grid((long long)Te * Tt), TILE, 0, st>>>(d);
+                k_tile_pairs_all<<<(Te * Tt + 255) / 256, 256, 0, s2>>>(d0, Tv, Tt, Te, 0, Te * Tt, 1);
+                k_broad_all<2, -1><<<broad_grid((long long)Te * Tt), TILE, 0, s2>>>(d0);
                 ctx->launches += 2;
             }
-            k_narrow_et<<<148, 128, 0, st>>>(d);
+            k_narrow_et<<<148, 128, 0, s2>>>(d0);
             ctx->launches++;
+            if (both) {
+                SB_CUDA(ctx, cudaEventRecord(ctx->ev_join[0], s2));
+                SB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join[0], 0));
+            }
         }
         SB_CUDA(ctx, cudaMemcpyAsync(C->h_counters, C->counters.p, 64 * sizeof(int), cudaMemcpyDeviceToHost, st));
         SB_CUDA(ctx, cudaStreamSynchronize(st));
