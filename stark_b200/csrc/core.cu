@@ -247,19 +247,21 @@ int eval_internal(sb_context* ctx, int mode, double* out_E, double* out_grad_inf
             SB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[k], 0));
         }
     SB_CUDA(ctx, cudaGetLastError());
-    if (mode == SB_EVAL_PGH && fork) {   // the pattern of the coming assembly, under this evaluation
-        bool dyn_on_side = true;         // (the prefetch waits for the side streams only: every dynamic potential must be there)
-        for (auto& p : ctx->potentials) if (p.dynamic && p.n_elem >= SMALL) dyn_on_side = false;
-        if (dyn_on_side) assembly_prefetch_symbolic(ctx);
-    }
 
     reduce_sum(ctx, ctx->E_elem.p, E_total, ctx->d_scalars + 0);
     if (mode == SB_EVAL_PGH) {
         reduce_absmax(ctx, ctx->grad.p, ctx->ndofs, ctx->d_scalars + 1);
         ctx->have_pgh = true;
     }
+    if (sync_scalars) SB_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    // The pattern of the coming assembly, under this evaluation.  Issued LAST: its ~20 launches take the host longer than the
+    // volume kernel runs, and the reductions above must already be queued behind that kernel when it ends.
+    if (mode == SB_EVAL_PGH && fork) {
+        bool dyn_on_side = true;         // (the prefetch waits for the side streams only: every dynamic potential must be there)
+        for (auto& p : ctx->potentials) if (p.dynamic && p.n_elem >= SMALL) dyn_on_side = false;
+        if (dyn_on_side) assembly_prefetch_symbolic(ctx);
+    }
     if (sync_scalars) {
-        SB_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (out_E) *out_E = ctx->h_scalars[0];
         if (out_grad_inf && mode == SB_EVAL_PGH) *out_grad_inf = ctx->h_scalars[1];
