@@ -255,6 +255,25 @@ __device__ __forceinline__ int row_lower_bound(const unsigned long long* __restr
     return lo;
 }
 
+// the same bound found by one warp: 32 probes per round, four rounds instead of sixteen dependent global loads for 37 k rows
+__device__ __forceinline__ int row_lower_bound_warp(const unsigned long long* __restrict__ rows, int nbr, unsigned long long t)
+{
+    const int lane = threadIdx.x & 31;
+    int lo = 0, hi = nbr;   // the answer is in [lo, hi]; rows below lo fail the test, hi passes it (or is nbr)
+    while (lo < hi) {
+        const int step = max(1, (hi - lo) / 32);
+        const int p = lo + lane * step;
+        const bool ge = (p >= hi) || (rows[p] + ROW_COST * (unsigned long long)p >= t);
+        const unsigned m = __ballot_sync(0xffffffffu, ge);
+        if (m == 0u) { lo = lo + 31 * step + 1; continue; }
+        const int first = __ffs(m) - 1;
+        const int nhi = min(lo + first * step, hi);
+        lo = (first > 0) ? lo + (first - 1) * step + 1 : lo;
+        hi = nhi;
+    }
+    return lo;
+}
+
 __device__ __forceinline__ unsigned long long global_ns()
 {
     unsigned long long t;
@@ -736,10 +755,14 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_solve(const PcgArgs A)
     const int tid = threadIdx.x;
 
     // ---- this CTA's rows: [r0, r1), holding blocks [b0, b0 + nb) ----
-    if (tid == 0) {
+    if (tid < 64) {   // (warps 0 and 1: one boundary each)
         const unsigned long long cost = A.nnzb + ROW_COST * (unsigned long long)nbr;
-        s_range[0] = row_lower_bound(A.rows, nbr, (cost * blockIdx.x) / G);
-        s_range[1] = (blockIdx.x == G - 1) ? nbr : row_lower_bound(A.rows, nbr, (cost * (blockIdx.x + 1)) / G);
+        const int which = tid >> 5;
+        int r = row_lower_bound_warp(A.rows, nbr, (cost * (blockIdx.x + which)) / G);
+        if (which == 1 && blockIdx.x == G - 1) r = nbr;
+        if ((tid & 31) == 0) s_range[which] = r;
+    }
+    if (tid == 0) {
         mbar_init(&s_mbar, 1);
         mbar_init(&s_tbar[0], 1);
         mbar_init(&s_tbar[1], 1);
@@ -779,8 +802,21 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_solve(const PcgArgs A)
     if (mat_fit) {
         P.off_cols = (unsigned)off; int32_t* cs = reinterpret_cast<int32_t*>(smem + carve(sizeof(int) * (size_t)nb));
         P.off_vals = (unsigned)off; float* vs = reinterpret_cast<float*>(smem + carve(sizeof(float) * 9 * (size_t)nb));
-        for (int i = tid; i < nb; i += PCG_THREADS) cs[i] = A.cols[b0 + i];
-        for (int i = tid; i < 9 * nb; i += PCG_THREADS) vs[i] = A.vals[9 * b0 + i];
+        // (eight loads in flight per thread: one load per trip makes the 150 KB copy a chain of ~35 L2 round trips)
+        for (int i = tid; i < nb; i += 8 * PCG_THREADS) {
+            int32_t v[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) { const int k = i + q * PCG_THREADS; v[q] = (k < nb) ? __ldg(A.cols + b0 + k) : 0; }
+#pragma unroll
+            for (int q = 0; q < 8; q++) { const int k = i + q * PCG_THREADS; if (k < nb) cs[k] = v[q]; }
+        }
+        for (int i = tid; i < 9 * nb; i += 8 * PCG_THREADS) {
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) { const int k = i + q * PCG_THREADS; v[q] = (k < 9 * nb) ? __ldg(A.vals + 9 * b0 + k) : 0.0f; }
+#pragma unroll
+            for (int q = 0; q < 8; q++) { const int k = i + q * PCG_THREADS; if (k < 9 * nb) vs[k] = v[q]; }
+        }
         cols = cs; vals = vs;
     } else {
         cols = A.cols + b0; vals = A.vals + 9 * b0;

@@ -13,6 +13,7 @@
 #include "internal.h"
 #include <algorithm>
 #include <cstdio>
+#include <cstring>
 #include <chrono>
 #include <cstdlib>
 
@@ -412,6 +413,8 @@ struct Projector {
     DevBuf<uint8_t> active;
     DevBuf<uint32_t> list;
     ProjTable* d_table = nullptr;
+    ProjTable table_host;
+    bool table_valid = false;
     int* d_counts = nullptr;   // [0] n_list, [1] n_changed, [2] n_inactive
     int* h_counts = nullptr;
     size_t smem_configured = 0;
@@ -473,6 +476,7 @@ int project_internal(sb_context* ctx, double grad_threshold, double eps, int mir
     ctx->pgh_cache_ok = false;   // the element Hessians are about to be modified in place
     const auto t_begin = std::chrono::steady_clock::now();
     ProjTable T;
+    std::memset(&T, 0, sizeof(T));   // (compared bytewise with the uploaded copy)
     T.n_pots = 0;
     unsigned long long blk_off = 0;
     for (int pidx : layout_order(ctx)) {
@@ -487,7 +491,13 @@ int project_internal(sb_context* ctx, double grad_threshold, double eps, int mir
         T.n_pots++;
     }
     T.E_off[T.n_pots] = n_elem;
-    SB_CUDA(ctx, cudaMemcpyAsync(P.d_table, &T, sizeof(ProjTable), cudaMemcpyHostToDevice, st));
+    // (uploaded only when it changed: a copy from pageable memory blocks the host, and the PPN loop calls this several times
+    //  per Newton iteration with the same layout)
+    if (!P.table_valid || std::memcmp(&P.table_host, &T, sizeof(ProjTable)) != 0) {
+        SB_CUDA(ctx, cudaMemcpyAsync(P.d_table, &T, sizeof(ProjTable), cudaMemcpyHostToDevice, st));
+        P.table_host = T;
+        P.table_valid = true;
+    }
     SB_CUDA(ctx, cudaMemsetAsync(P.d_counts, 0, 4 * sizeof(int), st));
     const int nbr = ctx->ndofs / 3;
     P.active.ensure(nbr + 1);
