@@ -111,8 +111,11 @@ extern "C" int sb_newton_solve(sb_context* ctx, const sb_newton_settings* S, sb_
         bool solved = false;
         double du_inf = 0.0;
         int64_t n_proj = 0, n_hess = 0;
+        bool have_prev = false;      // a solve of this iteration's current matrix has already been made (and did not give a descent direction)
+        int prev_ok = 0, prev_cg_it = 0;
         while (!solved) {
             bool all_projected = false;
+            const int64_t n_proj_before = n_proj;
             // _project_and_assemble (NewtonsMethod.cpp:254-352).  The reference assembles the unprojected matrix first and
             // then adds (projected - original) blocks; here the projected Hessians replace the originals in the element
             // store and one numeric assembly follows, so projection simply runs first.
@@ -139,17 +142,26 @@ extern "C" int sb_newton_solve(sb_context* ctx, const sb_newton_settings* S, sb_
                 break;
             default: return fail(ctx, SB_ERR_ARG, "sb_newton_solve: unknown projection mode");
             }
-            if (!assembled || projected_now) {
-                if ((rc = assemble_internal(ctx))) return rc;
-                assembled = true;
-            }
-            // _solve_linear_system (NewtonsMethod.cpp:420-451): forcing sequence
-            const double forcing = std::min(1e-2, residual * std::min(0.5, std::sqrt(residual)));
-            const double abs_tol = std::max(forcing, S->cg_abs_tolerance);
+            // A tightened threshold that selects no new element leaves the matrix as it is, and the (deterministic) solve would
+            // fail exactly as it just did: the reference assembles and solves again; here the previous outcome is reused (its CG
+            // iterations are counted again, so the statistics stay comparable) and the threshold is tightened further.
+            const bool same_matrix = have_prev && assembled && projected_now && n_proj == n_proj_before;
             int cg_it = 0, ok = 0;
-            if (S->linear_solver == 0) {
-                if ((rc = solve_llt_internal(ctx, &ok, &du_dot_grad, &du_inf))) return rc;
-            } else if ((rc = solve_pcg_internal(ctx, abs_tol, S->cg_rel_tolerance, S->cg_max_iterations, S->cg_stop_on_indefiniteness, &cg_it, &ok, &du_dot_grad, &du_inf))) return rc;
+            if (same_matrix) {
+                ok = prev_ok; cg_it = prev_cg_it;
+            } else {
+                if (!assembled || projected_now) {
+                    if ((rc = assemble_internal(ctx))) return rc;
+                    assembled = true;
+                }
+                // _solve_linear_system (NewtonsMethod.cpp:420-451): forcing sequence
+                const double forcing = std::min(1e-2, residual * std::min(0.5, std::sqrt(residual)));
+                const double abs_tol = std::max(forcing, S->cg_abs_tolerance);
+                if (S->linear_solver == 0) {
+                    if ((rc = solve_llt_internal(ctx, &ok, &du_dot_grad, &du_inf))) return rc;
+                } else if ((rc = solve_pcg_internal(ctx, abs_tol, S->cg_rel_tolerance, S->cg_max_iterations, S->cg_stop_on_indefiniteness, &cg_it, &ok, &du_dot_grad, &du_inf))) return rc;
+            }
+            have_prev = true; prev_ok = ok; prev_cg_it = cg_it;
             stats->cg_iterations += cg_it;
             const bool can_project_more = (S->projection_mode != PNewton) && !all_projected;
             if (!ok) {
