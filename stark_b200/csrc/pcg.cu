@@ -973,7 +973,8 @@ int solve_pcg_internal(sb_context* ctx, double abs_tol, double rel_tol, int max_
         std::vector<long long> h(5 * (size_t)G + 8);
         cudaMemcpy(h.data(), d_dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
         const int its = P->h_result->it > 0 ? P->h_result->it : 1;
-        fprintf(stderr, "PCGDUMP its=%d\n", P->h_result->it);
+        fprintf(stderr, "PCGDUMP its=%d load_ns=%lld phase0_ns=%lld loop_ns=%lld\n", P->h_result->it, (long long)(P->h_result->t_loaded - P->h_result->t_start),
+                (long long)(P->h_result->t_loop - P->h_result->t_loaded), (long long)(P->h_result->t_end - P->h_result->t_loop));
         for (int b = 0; b < G; b++)
             fprintf(stderr, "PCGDUMP cta=%d rows=%lld blocks=%lld spmv=%lld wait=%lld vec=%lld win=%lld\n", b, h[4 * G + b] >> 32, h[4 * G + b] & 0xffffffffll,
                     h[b] / its, h[G + b] / its, h[2 * G + b] / its, h[3 * G + b] / its);
