@@ -18,6 +18,7 @@
 // Output layout is the reference's (BlockedSparseMatrix.h:266-271): rows = offsets per block row, cols = first scalar
 // column of the block, vals = 9 floats per block, column-major inside the block.
 #include "internal.h"
+#include <cstdlib>
 #include <algorithm>
 #include <cub/cub.cuh>
 
@@ -486,6 +487,8 @@ static bool static_part_stale(sb_context* ctx, Assembly* A)
 void assembly_prefetch_symbolic(sb_context* ctx)
 {
     Assembly* A = ctx->assembly;
+    static const bool disabled = std::getenv("SB_NO_PREFETCH") != nullptr;   // diagnostic hook
+    if (disabled) return;
     if (!A || !A->numeric_valid || A->pf_pending || ctx->n_blocks_total == 0) return;
     if (pattern_current(ctx, A) || static_part_stale(ctx, A)) return;
     {

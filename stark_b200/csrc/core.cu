@@ -186,7 +186,10 @@ int eval_internal(sb_context* ctx, int mode, double* out_E, double* out_grad_inf
         return 0;
     }
     StageTimer timer(ctx, mode == SB_EVAL_PGH ? ST_EVAL_PGH : ST_EVAL_P);
-    if (mode == SB_EVAL_PGH) { assembly_prefetch_drain(ctx); ctx->pgh_cache_ok = false; }   // (a prefetched symbolic phase still reads the previous evaluation's block rows)
+    static const bool eval_dump = std::getenv("SB_EVAL_DUMP") != nullptr;   // diagnostic: host time of the phases of every evaluation
+    const double td0 = eval_dump ? now_ms() : 0.0;
+    if (mode == SB_EVAL_PGH) { assembly_prefetch_drain(ctx); ctx->pgh_cache_ok = false; }
+    const double td1 = eval_dump ? now_ms() : 0.0;   // (a prefetched symbolic phase still reads the previous evaluation's block rows)
     recompute_dof_offsets(ctx);
     if (ctx->ndofs <= 0) return fail(ctx, SB_ERR_STATE, "sb_eval: no degrees of freedom");
     if (ctx->ndofs % 3 != 0) return fail(ctx, SB_ERR_STATE, "sb_eval: ndofs must be divisible by 3");
@@ -296,6 +299,7 @@ int eval_internal(sb_context* ctx, int mode, double* out_E, double* out_grad_inf
         reduce_sum(ctx, ctx->E_elem.p, E_total, ctx->d_scalars + 0);
     }
     if (sync_scalars) SB_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    const double td2 = eval_dump ? now_ms() : 0.0;
     // The pattern of the coming assembly, under this evaluation.  Issued LAST: its ~20 launches take the host longer than the
     // volume kernel runs, and the reductions above must already be queued behind that kernel when it ends.
     if (mode == SB_EVAL_PGH && fork) {
@@ -303,8 +307,10 @@ int eval_internal(sb_context* ctx, int mode, double* out_E, double* out_grad_inf
         for (auto& p : ctx->potentials) if (p.dynamic && p.n_elem >= SMALL) dyn_on_side = false;
         if (dyn_on_side) assembly_prefetch_symbolic(ctx);
     }
+    const double td3 = eval_dump ? now_ms() : 0.0;
     if (sync_scalars) {
         SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (eval_dump) fprintf(stderr, "EVALDUMP mode=%d drain=%.1f issue=%.1f prefetch=%.1f sync=%.1f us\n", mode, 1e3 * (td1 - td0), 1e3 * (td2 - td1), 1e3 * (td3 - td2), 1e3 * (now_ms() - td3));
         if (out_E) *out_E = ctx->h_scalars[0];
         if (out_grad_inf && mode == SB_EVAL_PGH) *out_grad_inf = ctx->h_scalars[1];
         if (mode == SB_EVAL_PGH) {

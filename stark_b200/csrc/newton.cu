@@ -8,6 +8,7 @@
 //   before_energy_evaluation  -> contact_update_internal       (EnergyFrictionalContact.cpp:368-530)
 //   is_*_state_valid          -> contact_intersections_internal (EnergyFrictionalContact.cpp:774-799)
 #include "internal.h"
+#include <cstdlib>
 #include <algorithm>
 #include <cmath>
 #include <limits>
@@ -217,7 +218,8 @@ extern "C" int sb_newton_solve(sb_context* ctx, const sb_newton_settings* S, sb_
                 // The first trial is almost always accepted, and the next iteration then evaluates energy, gradient and
                 // Hessians at this very state: evaluate them now (eval_internal hands the result out again) instead of the
                 // energy alone.  Later trials (after a backtrack) are energy-only.
-                if (k == 0) { double res_unused = 0.0; if ((rc = eval_internal(ctx, SB_EVAL_PGH, &E1, &res_unused, true))) return rc; }
+                static const bool no_spec = std::getenv("SB_NO_SPECULATION") != nullptr;   // diagnostic hook
+                if (k == 0 && !no_spec) { double res_unused = 0.0; if ((rc = eval_internal(ctx, SB_EVAL_PGH, &E1, &res_unused, true))) return rc; }
                 else if ((rc = eval_internal(ctx, SB_EVAL_P, &E1, nullptr, true))) return rc;
                 if (E1 < E_threshold) break;
                 step *= 0.5;
