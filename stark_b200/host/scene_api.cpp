@@ -206,6 +206,44 @@ __attribute__((visibility("default"))) int sbh_scene_connectivity(void* h, const
     if (out && p) std::memcpy(out, p, sizeof(int32_t) * (size_t)std::min(len, cap));
     return len;
 }
+// ---- mesh helpers of the presets, callable without a GPU (CPU tests) ----
+// triangle grid (generate_triangle_grid): returns the number of triangles; V gets 3 (n0+1)(n1+1) doubles, T 3 ints per triangle
+__attribute__((visibility("default"))) int sbh_mesh_triangle_grid(int n0, int n1, double dx, double dy, double* V, int32_t* T)
+{
+    std::vector<Vec3> v;
+    std::vector<std::array<int, 3>> t;
+    generate_triangle_grid(v, t, {0.0, 0.0}, {dx, dy}, {n0, n1});
+    if (V) for (size_t i = 0; i < v.size(); i++) for (int c = 0; c < 3; c++) V[3 * i + c] = v[i][c];
+    if (T) for (size_t i = 0; i < t.size(); i++) for (int c = 0; c < 3; c++) T[3 * i + c] = t[i][c];
+    return (int)t.size();
+}
+// hinges of a triangle mesh (find_internal_angles): returns their number; out gets 4 ints each {edge_0, edge_1, opp_0, opp_1}
+__attribute__((visibility("default"))) int sbh_mesh_internal_angles(const int32_t* T, int n_tri, int n_nodes, int32_t* out, int cap)
+{
+    std::vector<std::array<int, 3>> t(n_tri);
+    for (int i = 0; i < n_tri; i++) t[i] = {T[3 * i], T[3 * i + 1], T[3 * i + 2]};
+    std::vector<std::array<int, 4>> a;
+    find_internal_angles(a, t, n_nodes);
+    if (out) for (size_t i = 0; i < a.size() && (int)i < cap; i++) for (int c = 0; c < 4; c++) out[4 * i + c] = a[i][c];
+    return (int)a.size();
+}
+// tet grid (generate_tet_grid) and its boundary (find_surface): returns the number of tets; n_surface gets the triangle count
+__attribute__((visibility("default"))) int sbh_mesh_tet_grid(int n0, int n1, int n2, double dx, double dy, double dz, double* V, int32_t* T, int* n_vertices, int* n_surface)
+{
+    std::vector<Vec3> v;
+    std::vector<std::array<int, 4>> t;
+    generate_tet_grid(v, t, {0.0, 0.0, 0.0}, {dx, dy, dz}, {n0, n1, n2});
+    if (V) for (size_t i = 0; i < v.size(); i++) for (int c = 0; c < 3; c++) V[3 * i + c] = v[i][c];
+    if (T) for (size_t i = 0; i < t.size(); i++) for (int c = 0; c < 4; c++) T[4 * i + c] = t[i][c];
+    if (n_vertices) *n_vertices = (int)v.size();
+    if (n_surface) {
+        std::vector<std::array<int, 3>> tris;
+        std::vector<int> map;
+        find_surface(tris, map, v, t);
+        *n_surface = (int)tris.size();
+    }
+    return (int)t.size();
+}
 __attribute__((visibility("default"))) void* sbh_scene_context(void* h) { return static_cast<Scene*>(h)->sim->context(); }
 
 }  // extern "C"
