@@ -163,7 +163,9 @@ SB_API int sb_contact_set_params(sb_context* ctx, double contact_stiffness, doub
 SB_API int sb_contact_update(sb_context* ctx);
 /* before_time_step: proximity at dt = 0 + friction tables with T / bary / fn / mu */
 SB_API int sb_contact_update_friction(sb_context* ctx);
-/* is_intermediate_state_valid: number of edge-triangle intersections at the current DoFs */
+/* is_intermediate_state_valid: number of edge-triangle intersections at the current DoFs.  When the contact tables are not
+ * current at these DoFs, the same detection also rebuilds them (what sb_contact_update would do next at this state: the
+ * evaluation that follows a valid state starts with it), so the two share one vertex update and one synchronisation. */
 SB_API int sb_contact_count_intersections(sb_context* ctx, int* out_count);
 /* raw results for parity tests: kind 0..5 = pt_pp, pt_pe, pt_pt, ee_pp, ee_pe, ee_ee; 6 = intersections.
  * ids rows as in tests/golden (see oracle/ref_driver.cpp); call with NULL buffers to query the count. */
