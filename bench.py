@@ -36,11 +36,13 @@ TET_BYTES = 1632       # algorithmic bytes of one EnergyTetStrain element in PGH
 TET_DRAM_TRAFFIC_NCU = 207.8e6
 
 
-def workload_config(n_gpus):
-    return {"workload": f"C2 tetdrop: {GRID_N}^3 Soft_Rubber tet grid (12 tets/hex) on a fixed rigid floor, IPC contact d=1mm k_min=1e8 mu=0.5, dt=10ms, PPN+BDPCG defaults",
-            "tets": 12 * GRID_N ** 3, "grid": GRID_N, "dt": 0.01,
+def workload_config(n_gpus, grid=GRID_N):
+    name = "C2 tetdrop" if grid == GRID_N else "tetdrop (reduced grid: NOT the benchmark configuration)"
+    return {"workload": f"{name}: {grid}^3 Soft_Rubber tet grid (12 tets/hex) on a fixed rigid floor, IPC contact d=1mm k_min=1e8 mu=0.5, dt=10ms, PPN+BDPCG defaults",
+            "tets": 12 * grid ** 3, "grid": grid, "dt": 0.01,
             "parallelism": "single GPU" if n_gpus == 1 else f"{n_gpus} independent replicas (one scene per GPU)",
-            "l2_policy": "working set per evaluation (~350 MB element outputs) exceeds the 126 MB L2"}
+            "l2_policy": ("working set per evaluation (~350 MB element outputs) exceeds the 126 MB L2" if grid == GRID_N
+                          else f"working set per evaluation ~{12 * grid ** 3 * 1632 / 1e6:.0f} MB")}
 
 
 class ClockSampler:
@@ -124,7 +126,7 @@ def main():
         v = r["newton_it_per_s"]
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": ref_steps, "warmup": ref_warmup,
                 "ms_per_step": 1e3 * r["wall_s"] / max(1, r["steps"]), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic", "config": workload_config(1), "newton_iterations": r["newton_iterations"],
+                "data": "synthetic", "config": workload_config(1, args.grid), "newton_iterations": r["newton_iterations"],
                 "cpu_baseline": {"value": v, "unit": UNIT, "cores": r["threads"], "kind": "reference", "sample": f"{ref_steps} time steps of the same scene after {ref_warmup} warm-up steps (unmodified reference, all host threads)"},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -234,7 +236,7 @@ def main():
     line = {
         "metric": METRIC, "value": its_all / (solve_gpu_ms * 1e-3), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": e2e_ms / steps_total, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.gpus),
+        "config": workload_config(args.gpus, args.grid),
         "e2e": {"value": its_all / (e2e_ms * 1e-3), "unit": UNIT,
                 "h2d_bytes_per_step": (t1["h2d_bytes"] - t0["h2d_bytes"]) / steps_total, "d2h_bytes_per_step": (t1["d2h_bytes"] - t0["d2h_bytes"]) / steps_total},
         "gpu_launches": int(t1["launches"] - t0["launches"]),
