@@ -91,6 +91,10 @@ SB_API const char* sb_kernel_names(void);
  * replaces: SecondOrderCompiledGlobal::{evaluate_P, evaluate_P__dP_du__local_d2P_du2}
  * (symx/solver/second_order/SecondOrderCompiledGlobal.cpp:72-93, 119-142). */
 enum sb_eval_mode { SB_EVAL_P = 0, SB_EVAL_PGH = 2 };
+/* A SB_EVAL_PGH call at a state that has just been evaluated with SB_EVAL_PGH -- no upload, DoF change, connectivity or
+ * contact-table change and no PD projection in between -- returns the stored energy and gradient norm without launching
+ * anything: gradient, element Hessians and block rows on the device are still that evaluation's.  (sb_newton_solve uses this:
+ * the first line-search trial is evaluated with SB_EVAL_PGH and becomes the next iteration's evaluation when accepted.) */
 SB_API int sb_eval(sb_context* ctx, int mode, double* out_E, double* out_grad_inf);
 SB_API int sb_grad_get(sb_context* ctx, double* host_grad);   /* flat, length ndofs */
 /* per-element output of one potential as the reference lays it out: [E | grad(n) | hess(n*n) row-major] per element */
