@@ -203,6 +203,9 @@ typedef struct sb_newton_settings {
     double bailout_residual;
     int32_t contact_enabled;   /* run the built-in contact callbacks (update / intersection test) */
     int32_t skip_converged_state_check;   /* the caller runs the is_converged_state_valid callbacks itself */
+    /* EnergyFrictionalContact::GlobalParams::intersection_test_enabled (S/models/interactions/EnergyFrictionalContact.cpp:774-799):
+     * 0 = is_initial / is_intermediate / is_converged_state_valid always answer "valid" (no edge-triangle test, no step halving) */
+    int32_t intersection_test_enabled;
 } sb_newton_settings;
 typedef struct sb_newton_stats {
     int32_t result;            /* symx::SolverReturn value (solver_utils.h:15-26) */

@@ -85,6 +85,7 @@ struct Args
 	bool verbose = false;
 	double vz = 0.0;     // initial downward speed (to reach contact quickly in small fixtures)
 	bool llt = false;
+	double inject = 1.0; // dump: injected DoF state v1 := inject * v0 + small deterministic noise
 };
 
 static Args parse(int argc, char** argv)
@@ -108,6 +109,7 @@ static Args parse(int argc, char** argv)
 		else if (s == "--codegen") a.codegen = next();
 		else if (s == "--verbose") a.verbose = true;
 		else if (s == "--llt") a.llt = true;
+		else if (s == "--inject") a.inject = std::stod(next());
 		else { std::cerr << "unknown arg " << s << "\n"; exit(2); }
 	}
 	return a;
@@ -334,8 +336,149 @@ static Scene scene_tetchain(const Args& a)
 	return sc;
 }
 
+// Every deformable-deformable contact / friction table, the point-side rigid-deformable ones, the three
+// "_Elasticity_Only" strain potentials and both rod potentials in one scene: three cloth patches in free fall whose
+// boundaries and corners face each other at less than d^, a folded strip (self contact), an elasticity-only tet block and
+// two rods lying on the first patch, and three small cubes standing on a vertex just outside the edge / corner of a patch.
+// Everything falls together (no supports), so the relative configuration survives the steps before the dump.
+static Scene scene_zoo(const Args& a)
+{
+	Scene sc;
+	stark::Settings settings = base_settings(a, "zoo");
+	sc.sim = std::make_unique<stark::Simulation>(settings);
+	auto& sim = *sc.sim;
+	stark::EnergyFrictionalContact::GlobalParams cp;
+	cp.default_contact_thickness = 0.002;
+	cp.min_contact_stiffness = 1e4;
+	sim.interactions->contact->set_global_params(cp);
+	const int n = a.n;
+	auto full = stark::Surface::Params::Cotton_Fabric();
+	auto eonly = stark::Surface::Params::Cotton_Fabric();
+	eonly.strain.elasticity_only = true;
+	std::vector<stark::ContactHandler> soft, all;
+
+	// A: elasticity-only patch at z = 0
+	auto [VA, TA, A] = sim.presets->deformables->add_surface_grid("A", { 1.0, 1.0 }, { n, n }, eonly);
+	soft.push_back(A.contact);
+	// B: slightly rotated, overlapping A's +x boundary strip from above (pt / ee interior types + boundary pe / pp types)
+	auto [VB, TB, B] = sim.presets->deformables->add_surface_grid("B", { 1.0, 1.0 }, { n, n }, full);
+	B.point_set.add_rotation(3.0, Eigen::Vector3d::UnitZ());
+	B.point_set.add_displacement({ 0.96, 0.013, 0.0026 });
+	soft.push_back(B.contact);
+	// C: corner to corner with A (point-point), 1.5 mm lower
+	auto [VC, TC, Cc] = sim.presets->deformables->add_surface_grid("C", { 1.0, 1.0 }, { n, n }, full);
+	Cc.point_set.add_displacement({ -1.0006, -1.0009, -0.0015 });
+	soft.push_back(Cc.contact);
+	// D: edge to edge with A along A's -y boundary, vertices staggered (point-edge, edge-edge point-edge)
+	auto [VD, TD, Dd] = sim.presets->deformables->add_surface_grid("D", { 1.0, 1.0 }, { n, n }, full);
+	Dd.point_set.add_displacement({ 0.37 / n, 1.0011, 0.0012 });
+	soft.push_back(Dd.contact);
+	// F: a strip folded back on itself 2.4 mm above its own lower half (self contact within one mesh)
+	{
+		const int m = std::max(4, n);
+		std::vector<Eigen::Vector3d> v;
+		std::vector<std::array<int, 3>> t;
+		const double w = 0.3, L = 0.6, gap = 0.0024;
+		for (int j = 0; j <= 2; j++) for (int i = 0; i <= 2 * m; i++) {
+			const double s = L * i / (2.0 * m);
+			Eigen::Vector3d p;
+			if (i <= m) p = { s, w * j / 2.0, 0.0 };
+			else p = { L - s + 0.013, w * j / 2.0 + 0.011, gap };
+			v.push_back(p + Eigen::Vector3d(-0.3, -2.2, 0.0));
+		}
+		auto id = [&](int i, int j) { return j * (2 * m + 1) + i; };
+		for (int j = 0; j < 2; j++) for (int i = 0; i < 2 * m; i++) {
+			t.push_back({ id(i, j), id(i + 1, j), id(i + 1, j + 1) });
+			t.push_back({ id(i, j), id(i + 1, j + 1), id(i, j + 1) });
+		}
+		auto shells = stark::Surface::Params::Cotton_Fabric();
+		shells.bending.flat_rest_angle = false;
+		auto F = sim.presets->deformables->add_surface("F", v, t, shells);
+		sim.interactions->contact->set_friction(F.contact, F.contact, 0.35);
+		all.push_back(F.contact);
+	}
+	// T: elasticity-only tet block resting 2.5 mm above A
+	auto vol = stark::Volume::Params::Soft_Rubber();
+	vol.strain.elasticity_only = true;
+	auto [VT, TT, Tt] = sim.presets->deformables->add_volume_grid("T", { 0.3, 0.3, 0.3 }, { 2, 2, 2 }, vol);
+	Tt.point_set.add_rotation(11.0, Eigen::Vector3d::UnitZ());
+	Tt.point_set.add_displacement({ -0.21, 0.17, 0.15 + 0.0025 });
+	soft.push_back(Tt.contact);
+	// two rods lying 2.2 mm above A (complete and elasticity-only strain models)
+	auto rod = stark::Line::Params::Elastic_Rubberband();
+	auto [VR, SR, R1] = sim.presets->deformables->add_line_as_segments("rod1", { -0.43, -0.31, 0.0022 }, { 0.21, -0.12, 0.0022 }, 7, rod);
+	rod.strain.elasticity_only = true;
+	auto [VR2, SR2, R2] = sim.presets->deformables->add_line_as_segments("rod2", { -0.4, -0.1, 0.0045 }, { 0.3, -0.35, 0.0045 }, 5, rod);
+	soft.push_back(R1.contact);
+	soft.push_back(R2.contact);
+	// stretch the rods a little (strain and strain-limit terms active)
+	for (int i = 0; i < R1.point_set.size(); i++) R1.point_set.set_velocity(i, { 0.9 * i, 0.0, 0.0 });
+	for (int i = 0; i < R2.point_set.size(); i++) R2.point_set.set_velocity(i, { 0.2 * i, -0.1 * i, 0.0 });
+
+	// cubes on a vertex: vertex 1.5 mm off B's +x boundary edge, 1.7 mm off B's far corner, 1.3 mm above the inside of A
+	const double h = 0.05, diag = h * std::sqrt(3.0), tilt = std::acos(1.0 / std::sqrt(3.0)) * 180.0 / M_PI;
+	const Eigen::AngleAxisd rotB(3.0 * M_PI / 180.0, Eigen::Vector3d::UnitZ());
+	auto onB = [&](double x, double y, double z) { Eigen::Vector3d p = rotB * Eigen::Vector3d(x, y, 0.0) + Eigen::Vector3d(0.96, 0.013, 0.0026 + z); return p; };
+	std::vector<Eigen::Vector3d> tips = { onB(0.5012, 0.11, 0.0009), onB(0.5011, 0.5010, 0.0008), Eigen::Vector3d(-0.33, -0.37, 0.0013) };
+	for (size_t k = 0; k < tips.size(); k++) {
+		auto [Vk, Ck, bk] = sim.presets->rigidbodies->add_box("cube" + std::to_string(k), 0.3, 2.0 * h);
+		bk.rigidbody.set_rotation(tilt, { 1.0, -1.0, 0.0 });
+		bk.rigidbody.set_translation(tips[k] + Eigen::Vector3d(0.0, 0.0, diag));
+		all.push_back(bk.contact);
+	}
+	for (auto& c : soft) all.push_back(c);
+	for (size_t i = 0; i < all.size(); i++) for (size_t j = i + 1; j < all.size(); j++) sim.interactions->contact->set_friction(all[i], all[j], 0.2 + 0.03 * ((i + j) % 5));
+	// relative sliding so that the friction potentials see a tangential velocity
+	for (int i = 0; i < B.point_set.size(); i++) B.point_set.set_velocity(i, { 0.05, -0.02, 0.0 });
+	for (int i = 0; i < Dd.point_set.size(); i++) Dd.point_set.set_velocity(i, { -0.03, 0.0, 0.0 });
+	return sc;
+}
+
+// The five rigid-body constraint potentials no other scene holds (tests/rb_constraints.cpp:106-232 patterns): slider
+// (point_on_axis), distance, distance limits, angle limit and damped spring between a fixed anchor and free boxes pushed by
+// external forces / torques so that every constraint is violated (and active) at the dump.
+static Scene scene_joints(const Args& a)
+{
+	Scene sc;
+	stark::Settings settings = base_settings(a, "joints");
+	settings.simulation.init_frictional_contact = false;
+	sc.sim = std::make_unique<stark::Simulation>(settings);
+	auto& sim = *sc.sim;
+	const double mass = 1.3;
+	auto I = stark::inertia_tensor_box(mass, { 0.1, 0.12, 0.08 });
+	auto anchor = sim.rigidbodies->add(mass, I);
+	sim.rigidbodies->add_constraint_fix(anchor);
+	auto mk = [&](const Eigen::Vector3d& t, double deg) {
+		auto b = sim.rigidbodies->add(mass, I);
+		b.set_translation(t);
+		b.set_rotation(deg, { 0.3, 1.0, -0.2 });
+		return b;
+	};
+	auto b1 = mk({ 0.2, 0.0, 0.0 }, 5.0);
+	sim.rigidbodies->add_constraint_slider(anchor, b1, { 0.05, 0.01, 0.0 }, Eigen::Vector3d(0.1, 0.2, 1.0).normalized());
+	b1.add_force_at_centroid({ 7.0, -3.0, 1.0 });
+	auto b2 = mk({ 0.0, 0.3, 0.0 }, -8.0);
+	sim.rigidbodies->add_constraint_distance(anchor, b2, { 0.01, 0.02, 0.03 }, { 0.02, 0.28, 0.01 });
+	b2.add_force_at_centroid({ 1.0, 9.0, 2.0 });
+	auto b3 = mk({ 0.0, -0.3, 0.1 }, 13.0);
+	sim.rigidbodies->add_constraint_distance_limits(anchor, b3, { 0.0, -0.02, 0.01 }, { 0.01, -0.27, 0.08 }, 0.2, 0.2605);
+	b3.add_force_at_centroid({ 0.5, -12.0, 3.0 });
+	auto b4 = mk({ -0.3, 0.0, 0.0 }, 0.0);
+	sim.rigidbodies->add_constraint_point_with_angle_limit(anchor, b4, { -0.15, 0.0, 0.0 }, Eigen::Vector3d(0.0, 0.2, 1.0).normalized(), 2.0);
+	b4.add_torque({ 3.0, 1.0, 0.5 });
+	auto b5 = mk({ 0.0, 0.0, 0.4 }, 21.0);
+	sim.rigidbodies->add_constraint_spring(anchor, b5, { 0.0, 0.01, 0.04 }, { 0.02, 0.0, 0.36 }, 250.0, 3.0);
+	b5.add_force_at_centroid({ 2.0, 1.0, 6.0 });
+	auto b6 = mk({ 0.3, 0.3, 0.0 }, -4.0);
+	sim.rigidbodies->add_constraint_spring_with_limits(b2, b6, { 0.02, 0.3, 0.0 }, { 0.29, 0.31, 0.01 }, 120.0, 0.2, 0.2715, 1.0);
+	b6.add_force_at_centroid({ 8.0, 0.0, -1.0 });
+	return sc;
+}
+
 static Scene make_scene(const Args& a)
 {
+	if (a.scene == "zoo") return scene_zoo(a);
+	if (a.scene == "joints") return scene_joints(a);
 	if (a.scene == "tetchain") return scene_tetchain(a);
 	if (a.scene == "boxes") return scene_boxes(a);
 	if (a.scene == "attach") return scene_attach(a);
@@ -373,9 +516,9 @@ static void dump_iteration(const Args& a, stark::Simulation& sim)
 	st.callbacks->run_before_time_step();
 	{
 		auto& dyn = *sim.deformables->point_sets;
-		for (int i = 0; i < dyn.size(); i++) dyn.v1[i] = dyn.v0[i];
+		for (int i = 0; i < dyn.size(); i++) dyn.v1[i] = a.inject * dyn.v0[i];
 		auto& rb = *sim.rigidbodies->rb;
-		for (int i = 0; i < rb.get_n_bodies(); i++) { rb.v1[i] = rb.v0[i]; rb.w1[i] = rb.w0[i]; }
+		for (int i = 0; i < rb.get_n_bodies(); i++) { rb.v1[i] = a.inject * rb.v0[i]; rb.w1[i] = a.inject * rb.w0[i]; }
 		// small deterministic perturbation so that rigid DoFs and symmetric nodes are not exactly zero
 		for (int i = 0; i < dyn.size(); i++) {
 			dyn.v1[i] += 1e-3 * Eigen::Vector3d(std::sin(0.37 * i), std::cos(0.91 * i), std::sin(1.3 * i + 0.5));

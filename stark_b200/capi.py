@@ -52,6 +52,7 @@ class NewtonSettings(C.Structure):
         ("bailout_residual", C.c_double),
         ("contact_enabled", C.c_int32),
         ("skip_converged_state_check", C.c_int32),
+        ("intersection_test_enabled", C.c_int32),
     ]
 
 

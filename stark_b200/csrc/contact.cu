@@ -21,6 +21,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cstring>
+#include <cstdlib>
 #include <cub/cub.cuh>
 
 namespace sb {
@@ -976,13 +977,24 @@ static void ensure_capacities(sb_context* ctx, Contact* C)
         C->tile_pairs[0].ensure(Tv * Tt + 1); C->tile_pairs[1].ensure(Te * Te + 1); C->tile_pairs[2].ensure(Te * Tt + 1);
     }
     for (int l = 0; l < N_LISTS; l++) { C->list_ids[l].ensure((size_t)C->list_cap * LIST_WIDTH[l]); C->list_dist[l].ensure(C->list_cap); }
-    for (int t = 0; t < N_TABLES; t++) C->table[t].ensure((size_t)C->table_cap * LAYOUTS[t].conn_stride);
-    for (int f = 0; f < N_FRICTION; f++) {
-        ctx->arrays[C->a_fT[f]].d.ensure(6 * (size_t)C->table_cap);
-        ctx->arrays[C->a_fmu[f]].d.ensure(C->table_cap);
-        ctx->arrays[C->a_ffn[f]].d.ensure(C->table_cap);
-        if (C->a_fbary[f] >= 0) ctx->arrays[C->a_fbary[f]].d.ensure((size_t)ctx->arrays[C->a_fbary[f]].stride * C->table_cap);
+    // Contact and friction tables share one capacity, but a detection rewrites only one of the two families (friction tables
+    // are built once per time step): a table that is not being rewritten must survive a growth caused by the other family,
+    // so every reallocation keeps the rows in use, and the potentials are re-pointed at the new buffers.
+    bool moved = false;
+    for (int t = 0; t < N_TABLES; t++) {
+        const int32_t* before = C->table[t].p;
+        const size_t stride = LAYOUTS[t].conn_stride;
+        C->table[t].ensure_keep((size_t)C->table_cap * stride, (size_t)C->h_table_count[t] * stride, ctx->stream);
+        moved = moved || before != C->table[t].p;
     }
+    for (int f = 0; f < N_FRICTION; f++) {
+        const size_t n = (size_t)C->h_table_count[N_CONTACT_TABLES + f];
+        ctx->arrays[C->a_fT[f]].d.ensure_keep(6 * (size_t)C->table_cap, 6 * n, ctx->stream);
+        ctx->arrays[C->a_fmu[f]].d.ensure_keep(C->table_cap, n, ctx->stream);
+        ctx->arrays[C->a_ffn[f]].d.ensure_keep(C->table_cap, n, ctx->stream);
+        if (C->a_fbary[f] >= 0) { const size_t st = (size_t)ctx->arrays[C->a_fbary[f]].stride; ctx->arrays[C->a_fbary[f]].d.ensure_keep(st * C->table_cap, st * n, ctx->stream); }
+    }
+    if (moved) for (int t = 0; t < N_TABLES; t++) if (C->pot[t] >= 0) ctx->potentials[C->pot[t]].conn_ext = C->table[t].p;
 }
 
 static Dev make_dev(sb_context* ctx, Contact* C)
@@ -1231,6 +1243,9 @@ int sb_contact_init(sb_context* ctx, const sb_contact_bindings* b)
         if (ids[i] < 0 || ids[i] >= (int)ctx->arrays.size()) return fail(ctx, SB_ERR_ARG, "sb_contact_init: unknown array handle in bindings");
     Contact* C = new Contact();
     C->bind = *b;
+    for (int t = 0; t < N_TABLES; t++) C->pot[t] = -1;
+    // test hook: a small initial table capacity makes tables overflow (and grow) in the middle of a step
+    if (const char* cap = std::getenv("SB_CONTACT_TABLE_CAP")) C->table_cap = std::max(1, std::atoi(cap));
     C->h_blacklist.assign(MAX_GROUPS * MAX_GROUPS, 0);
     C->h_mu.assign(MAX_GROUPS * MAX_GROUPS, 0.0);
     cudaMallocHost(&C->h_counters, 64 * sizeof(int));

@@ -408,6 +408,8 @@ void sb_destroy(sb_context* ctx)
         if (ctx->ev_join[k]) cudaEventDestroy(ctx->ev_join[k]);
     }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
+    if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -704,18 +706,26 @@ int sb_potential_get_element_output(sb_context* ctx, int potential, double* host
     a.conn_stride = p.conn_stride;
     a.n_elem = p.n_elem;
     for (int b = 0; b < MAX_BLOCKS; b++) a.blocks[b] = p.blocks[b];
+    // outputs go to scratch buffers: the live element Hessians (possibly PD-projected, with dirty flags and an assembled
+    // matrix that refer to them) are not touched by this diagnostic call
+    DevBuf<double> H_tmp, E_tmp;
+    DevBuf<int32_t> rows_tmp;
+    H_tmp.ensure((size_t)p.n_elem * n * n + 32);   // (+ slack: the bulk stores of the tet kernel want 128-byte aligned tiles)
+    E_tmp.ensure(p.n_elem);
+    rows_tmp.ensure((size_t)p.n_elem * p.k->nb);
     a.grad = grad_tmp.p;
-    a.H = ctx->H.p + p.H_off;
-    a.rows = ctx->rows.p + p.rows_off;
-    a.E_elem = ctx->E_elem.p + p.E_off;
+    a.H = H_tmp.p;
+    a.rows = rows_tmp.p;
+    a.E_elem = E_tmp.p;
     a.g_elem = g_elem.p;
     p.k->launch_pgh(a, ctx->stream);
     ctx->launches++;
     std::vector<double> E(p.n_elem), g((size_t)p.n_elem * n), H((size_t)p.n_elem * n * n);
-    SB_CUDA(ctx, cudaMemcpyAsync(E.data(), ctx->E_elem.p + p.E_off, E.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(ctx, cudaMemcpyAsync(E.data(), E_tmp.p, E.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     SB_CUDA(ctx, cudaMemcpyAsync(g.data(), g_elem.p, g.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    SB_CUDA(ctx, cudaMemcpyAsync(H.data(), ctx->H.p + p.H_off, H.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(ctx, cudaMemcpyAsync(H.data(), H_tmp.p, H.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    H_tmp.release(); E_tmp.release(); rows_tmp.release();
     for (int e = 0; e < p.n_elem; e++) {
         double* o = host_sol + (size_t)e * n_out;
         o[0] = E[e];
@@ -810,10 +820,17 @@ extern "C" int sb_profile_potential(sb_context* ctx, int potential, int mode, in
     DevBuf<double> grad_tmp;   // scratch gradient so that the solver state is not disturbed
     grad_tmp.ensure(ctx->ndofs);
     SB_CUDA(ctx, cudaMemsetAsync(grad_tmp.p, 0, sizeof(double) * ctx->ndofs, ctx->stream));
+    // scratch outputs: the solver's element Hessians / block rows / energies stay as the last evaluation left them
+    DevBuf<double> H_tmp, E_tmp;
+    DevBuf<int32_t> rows_tmp;
+    const size_t nd = p.k->n_dof;
+    H_tmp.ensure((size_t)p.n_elem * nd * nd + 32);
+    E_tmp.ensure(p.n_elem);
+    rows_tmp.ensure((size_t)p.n_elem * p.k->nb);
     a.grad = grad_tmp.p;
-    a.H = ctx->H.p + p.H_off;
-    a.rows = ctx->rows.p + p.rows_off;
-    a.E_elem = ctx->E_elem.p + p.E_off;
+    a.H = H_tmp.p;
+    a.rows = rows_tmp.p;
+    a.E_elem = E_tmp.p;
     a.g_elem = nullptr;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -827,7 +844,7 @@ extern "C" int sb_profile_potential(sb_context* ctx, int potential, int mode, in
     float ms = 0.0f;
     cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    grad_tmp.release();
+    grad_tmp.release(); H_tmp.release(); E_tmp.release(); rows_tmp.release();
     SB_CUDA(ctx, cudaGetLastError());
     *out_avg_ms = (double)ms / reps;
     return SB_OK;

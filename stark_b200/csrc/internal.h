@@ -155,6 +155,7 @@ struct sb_context {
     static constexpr int N_SIDE = 4;
     cudaStream_t side[N_SIDE] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[N_SIDE] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;   // sb_newton_solve's timing events
     std::string error;
     int64_t launches = 0;
 

@@ -51,6 +51,7 @@ extern "C" void sb_newton_default_settings(sb_newton_settings* s)
     s->bailout_residual = 1e-10;
     s->contact_enabled = 1;
     s->skip_converged_state_check = 0;
+    s->intersection_test_enabled = 1;
 }
 
 extern "C" int sb_newton_solve(sb_context* ctx, const sb_newton_settings* S, sb_newton_stats* stats)
@@ -67,7 +68,7 @@ extern "C" int sb_newton_solve(sb_context* ctx, const sb_newton_settings* S, sb_
     auto record = [&](double r) { if (stats->n_evaluations < 64) stats->residuals[stats->n_evaluations] = r; stats->n_evaluations++; };
     auto state_valid = [&](bool& valid) -> int {
         valid = true;
-        if (!contact) return 0;
+        if (!contact || !S->intersection_test_enabled) return 0;
         int n = 0;
         int r = contact_intersections_internal(ctx, &n);
         if (r) return r;
@@ -80,8 +81,11 @@ extern "C" int sb_newton_solve(sb_context* ctx, const sb_newton_settings* S, sb_
     int pdn_countdown = 0;
     double ppn_threshold = -1.0;
 
-    cudaEvent_t ev0, ev1;
-    cudaEventCreate(&ev0); cudaEventCreate(&ev1);
+    // (the two timing events live in the context: an error return below leaks nothing; `result` stays "Running" for a
+    //  caller that ignores the return code)
+    stats->result = Running;
+    if (!ctx->ev_t0) { cudaEventCreate(&ctx->ev_t0); cudaEventCreate(&ctx->ev_t1); }
+    cudaEvent_t ev0 = ctx->ev_t0, ev1 = ctx->ev_t1;
     cudaEventRecord(ev0, ctx->stream);
     bool valid = true;
     if ((rc = state_valid(valid))) return rc;
@@ -241,7 +245,6 @@ extern "C" int sb_newton_solve(sb_context* ctx, const sb_newton_settings* S, sb_
     float ms = 0.0f;
     cudaEventElapsedTime(&ms, ev0, ev1);
     stats->gpu_ms = ms;
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     stats->newton_iterations = it;
     return SB_OK;
 }

@@ -758,6 +758,7 @@ bool Simulation::run_one_time_step()
 
     // ---- Newton solve on the device ----
     sb_newton_settings ns = settings.newton;
+    ns.intersection_test_enabled = contact.global_params.intersection_test_enabled ? 1 : 0;
     ns.skip_converged_state_check = 1;   // the host runs the converged-state callbacks below, in the reference's order
     sb_newton_stats st;
     const auto t_solve = clk::now();

@@ -32,6 +32,13 @@ FIXTURES = {
     "tetchain_n3": ["--scene", "tetchain", "--n", "3", "--ny", "4", "--steps", "14"],
     # the five attachment potentials
     "attach_n6": ["--scene", "attach", "--n", "6", "--steps", "3"],
+    # all ten deformable-deformable contact / friction tables (two-mesh and self contact), the point-side rigid-deformable
+    # ones, the three _Elasticity_Only strain potentials and both rod potentials; state injected at v1 ~ 0 (contacts of x0)
+    "zoo_n4": ["--scene", "zoo", "--n", "4", "--steps", "1", "--inject", "0"],
+    # same scene, state injected at v1 = v0 (bodies separating and sliding: friction beyond the stick threshold)
+    "zoo_slide_n4": ["--scene", "zoo", "--n", "4", "--steps", "1"],
+    # slider, distance, distance-limit, angle-limit and damped-spring rigid-body constraints, all violated
+    "joints": ["--scene", "joints", "--n", "1", "--steps", "6"],
 }
 
 

@@ -10,8 +10,9 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 class Golden:
-    def __init__(self, name):
-        self.z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    def __init__(self, name, data=None):
+        """`data`: an already packed dump (tests/golden/make_golden.py:pack) instead of a committed fixture."""
+        self.z = data if data is not None else np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
         self.meta = json.loads(bytes(self.z["meta_json"]))
         self.name = name
 

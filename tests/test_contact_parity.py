@@ -8,7 +8,7 @@ import pytest
 from golden_util import Golden, bind
 
 KINDS = ["pt_pp", "pt_pe", "pt_pt", "ee_pp", "ee_pe", "ee_ee"]
-FIXTURES = ["tetdrop_n3", "tetdrop_n5", "cloth_n8", "cloth_shells_n8", "boxes", "tetchain_n3"]
+FIXTURES = ["tetdrop_n3", "tetdrop_n5", "cloth_n8", "cloth_shells_n8", "boxes", "tetchain_n3", "zoo_n4", "zoo_slide_n4"]
 # array roles in the fixtures (docs/potential_layouts.txt): a1 x0, a13 X, a9 dt, a59 t0, a60 q0 (w,x,y,z)
 X0, XREST, DT, RB_T0, RB_Q0 = 1, 13, 9, 59, 60
 

@@ -175,3 +175,38 @@ def test_streamed_matrix_product_matches_resident():
             assert abs(sa[3] - sb[3]) <= 1e-4 * abs(sa[3]), (sa, sb)
         xa, xb = np.array(a["x"]), np.array(b["x"])
         assert np.abs(xa - xb).max() <= 1e-6
+
+
+@pytest.mark.gpu
+def test_contact_tables_growing_mid_step_keep_friction_tables():
+    """Contact and friction tables share one capacity and friction tables are only built at the start of a step: when a contact
+    table overflows in the middle of a step (SB_CONTACT_TABLE_CAP forces a tiny initial capacity) the friction tables and their
+    data arrays must survive the reallocation.  Same trajectory as with the default capacity."""
+    import os, subprocess, sys, textwrap
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = textwrap.dedent("""
+        import sys, json
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        from stark_b200 import scenes
+        sc = scenes.Scene("tetdrop", n=6, vz=0.6)
+        log = []
+        for _ in range(12):
+            s = sc.step()
+            log.append([s["accepted"], s["newton_iterations"], s["result"], s["first_residual"]])
+        print(json.dumps({"log": log, "x": sc.positions()[::7].tolist()}))
+    """) % (here, os.path.dirname(here))
+    out = []
+    for cap in (None, "4"):
+        env = dict(os.environ)
+        env.pop("SB_CONTACT_TABLE_CAP", None)
+        if cap:
+            env["SB_CONTACT_TABLE_CAP"] = cap
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    a, b = out
+    assert sum(s[1] for s in a["log"]) > 12      # contact reached: more than one Newton iteration per step
+    for sa, sb in zip(a["log"], b["log"]):
+        assert sa[:3] == sb[:3], (sa, sb)
+        assert abs(sa[3] - sb[3]) <= 1e-4 * abs(sa[3]), (sa, sb)
+    assert np.abs(np.array(a["x"]) - np.array(b["x"])).max() <= 1e-6
