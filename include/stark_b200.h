@@ -55,6 +55,15 @@ SB_API int sb_array_rows(sb_context* ctx, int array, int* out_rows);
 /* every entry of the first n_rows rows = value (the reference zeroes soft.v1 / rigid.v1 / rigid.w1 before every time step,
  * S/models/deformables/PointDynamics.cpp:58-62, S/models/rigidbodies/RigidBodyDynamics.cpp:136-147) */
 SB_API int sb_array_fill(sb_context* ctx, int array, int n_rows, double value);
+/* State roll of an accepted time step on the device: y += alpha * x (x0 += dt v1) and dst = src (v0 = v1) over the first n_rows
+ * rows; replaces the host loops of PointDynamics::_on_time_step_accepted (S/models/deformables/PointDynamics.cpp:64-78). */
+SB_API int sb_array_axpy(sb_context* ctx, int y, int x, double alpha, int n_rows);
+SB_API int sb_array_copy(sb_context* ctx, int dst, int src, int n_rows);
+/* Asynchronous read-back into a buffer registered with sb_host_register: ordered behind everything submitted so far, runs beside
+ * whatever is submitted next, complete after sb_download_wait.  (The host mirrors of x0 / v0 are refreshed this way while the
+ * next time step is already being solved.) */
+SB_API int sb_array_download_async(sb_context* ctx, int array, double* host, int n_rows);
+SB_API int sb_download_wait(sb_context* ctx);
 /* Pinned mirrors (SURVEY.md 8(b) "Data ownership"): a host buffer registered here is page-locked in place, and uploads
  * FROM it are asynchronous -- the buffer must stay untouched until the next call that synchronises (any download, sb_eval,
  * sb_newton_solve, sb_synchronize).  Unregistered (pageable) buffers keep the borrow-for-the-call contract. */
@@ -167,6 +176,11 @@ SB_API int sb_contact_set_params(sb_context* ctx, double contact_stiffness, doub
 SB_API int sb_contact_update(sb_context* ctx);
 /* before_time_step: proximity at dt = 0 + friction tables with T / bary / fn / mu */
 SB_API int sb_contact_update_friction(sb_context* ctx);
+/* before_time_step in one detection: friction tables (dt = 0) and -- when every DoF array is zero, as in the reference's callback
+ * order (PointDynamics.cpp:58-62 and RigidBodyDynamics.cpp:136-147 zero v1 / w1 before EnergyFrictionalContact.cpp:531 runs) --
+ * also the contact tables and the intersection count of the initial Newton state, which sb_newton_solve then finds cached.
+ * dofs_are_zero = 0: same as sb_contact_update_friction. */
+SB_API int sb_contact_begin_time_step(sb_context* ctx, int dofs_are_zero);
 /* is_intermediate_state_valid: number of edge-triangle intersections at the current DoFs.  When the contact tables are not
  * current at these DoFs, the same detection also rebuilds them (what sb_contact_update would do next at this state: the
  * evaluation that follows a valid state starts with it), so the two share one vertex update and one synchronisation. */

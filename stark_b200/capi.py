@@ -71,14 +71,14 @@ class NewtonStats(C.Structure):
 # every symbol include/stark_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = [
     "sb_create", "sb_destroy", "sb_last_error", "sb_get_stream", "sb_synchronize", "sb_launch_count",
-    "sb_array_create", "sb_array_upload", "sb_array_download", "sb_array_rows", "sb_array_fill", "sb_host_register", "sb_host_unregister",
+    "sb_array_create", "sb_array_upload", "sb_array_download", "sb_array_rows", "sb_array_fill", "sb_array_axpy", "sb_array_copy", "sb_array_download_async", "sb_download_wait", "sb_host_register", "sb_host_unregister",
     "sb_dof_add", "sb_dof_total", "sb_dofs_get", "sb_dofs_set",
     "sb_potential_create", "sb_potential_set_connectivity", "sb_potential_info", "sb_kernel_names",
     "sb_eval", "sb_grad_get", "sb_potential_get_element_output", "sb_potential_get_block_rows", "sb_potential_get_hessians",
     "sb_project_to_pd", "sb_assemble", "sb_bcsr_info", "sb_bcsr_get",
     "sb_solve_pcg", "sb_solve_llt", "sb_du_get", "sb_dofs_save", "sb_dofs_apply_step", "sb_du_scale",
     "sb_contact_init", "sb_contact_add_mesh", "sb_contact_blacklist", "sb_contact_set_friction", "sb_contact_set_params",
-    "sb_contact_update", "sb_contact_update_friction", "sb_contact_count_intersections", "sb_contact_get_proximity",
+    "sb_contact_update", "sb_contact_update_friction", "sb_contact_begin_time_step", "sb_contact_count_intersections", "sb_contact_get_proximity",
     "sb_contact_get_vertices", "sb_contact_set_vertices", "sb_contact_detect", "sb_contact_potential",
     "sb_newton_default_settings", "sb_newton_solve", "sb_profile_potential",
     "sb_profile_stages", "sb_profile_report",

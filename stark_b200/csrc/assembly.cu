@@ -82,6 +82,7 @@ struct Assembly {
     bool pf_pending = false;
     uint64_t pf_static = 0, pf_dynamic = 0;
     size_t pf_n_src = 0;
+    bool pf_failed = false;
     cudaEvent_t ev_sym = nullptr;
 };
 
@@ -105,6 +106,7 @@ void assembly_destroy(sb_context* ctx)
     A->dirty.release(); A->long_blocks.release(); A->descs.release();
     if (A->d_counts) cudaFree(A->d_counts);
     if (A->h_counts) cudaFreeHost(A->h_counts);
+    if (ctx->issuer) ctx->issuer->wait();
     if (A->ev_sym) { cudaEventSynchronize(A->ev_sym); cudaEventDestroy(A->ev_sym); }
     delete A;
     ctx->assembly = nullptr;
@@ -484,7 +486,7 @@ static bool static_part_stale(sb_context* ctx, Assembly* A)
 // streams: if only the dynamic part of the pattern is stale -- every Newton iteration in contact -- the symbolic phase (a
 // chain of ~20 small kernels, ~120 us) is launched on a side stream NOW, behind those kernels, and runs under the volume
 // elements' evaluation, the reductions and the PD projection instead of after them.  assemble_internal picks the result up.
-void assembly_prefetch_symbolic(sb_context* ctx)
+void assembly_prefetch_symbolic(sb_context* ctx, unsigned side_mask)
 {
     Assembly* A = ctx->assembly;
     static const bool disabled = std::getenv("SB_NO_PREFETCH") != nullptr;   // diagnostic hook
@@ -496,18 +498,28 @@ void assembly_prefetch_symbolic(sb_context* ctx)
         while ((1ll << bits) < ctx->ndofs / 3 + 1) bits++;
         if (bits != A->key_shift) return;
     }
-    cudaStream_t st = ctx->side[sb_context::N_SIDE - 1];
-    for (int k = 0; k < sb_context::N_SIDE; k++) cudaStreamWaitEvent(st, ctx->ev_join[k], 0);   // the dynamic potentials' block rows are written
-    if (symbolic_phase_a(ctx, A, false, st)) { cudaStreamSynchronize(st); return; }
-    cudaEventRecord(A->ev_sym, st);
     A->pf_pending = true;
+    A->pf_failed = false;
     A->pf_static = ctx->static_version; A->pf_dynamic = ctx->dynamic_version; A->pf_n_src = ctx->n_blocks_total;
+    // SB_HELPER_THREAD=1: issued by the helper thread while this thread goes on launching the rest of the evaluation (measured:
+    // no gain -- launches from two threads serialise in the driver); default: issued here
+    static const bool helper = std::getenv("SB_HELPER_THREAD") != nullptr;
+    auto job = [ctx, A, side_mask] {
+        cudaStream_t st = ctx->sym_stream;
+        for (int k = 0; k < sb_context::N_SIDE; k++) if (side_mask & (1u << k)) cudaStreamWaitEvent(st, ctx->ev_dyn[k], 0);   // the dynamic potentials' block rows are written
+        timeline_point(st, "symbolic: dependencies met");
+        if (symbolic_phase_a(ctx, A, false, st)) { cudaStreamSynchronize(st); A->pf_failed = true; }
+        cudaEventRecord(A->ev_sym, st);
+        timeline_point(st, "symbolic: phase A done");
+    };
+    if (helper) ctx->issuer->post(job); else job();
 }
-// before anything the prefetched phase reads (block rows, layout) is rewritten
+// host-side join with the helper thread, then device-side: before anything the prefetched phase reads (block rows, layout) is
+// rewritten
 void assembly_prefetch_drain(sb_context* ctx)
 {
     Assembly* A = ctx->assembly;
-    if (A && A->pf_pending) cudaEventSynchronize(A->ev_sym);
+    if (A && A->pf_pending) { ctx->issuer->wait(); cudaEventSynchronize(A->ev_sym); }
 }
 
 int assemble_internal(sb_context* ctx)
@@ -516,6 +528,10 @@ int assemble_internal(sb_context* ctx)
     Assembly* A = get(ctx);
     if (ctx->n_blocks_total == 0) return fail(ctx, SB_ERR_STATE, "sb_assemble: no element Hessians");
     bool rebuilt = false;
+    if (A->pf_pending) {
+        ctx->issuer->wait();
+        if (A->pf_failed) { cudaEventSynchronize(A->ev_sym); A->pf_pending = false; }   // (falls back to the in-place build below)
+    }
     if (!pattern_current(ctx, A)) {
         int r;
         if (A->pf_pending && A->pf_static == ctx->static_version && A->pf_dynamic == ctx->dynamic_version && A->pf_n_src == ctx->n_blocks_total &&

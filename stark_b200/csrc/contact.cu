@@ -83,6 +83,7 @@ struct Dev {
     int32_t* table[N_TABLES];
     int table_stride[N_TABLES];
     int table_cap;
+    unsigned long long* hash;    // [2 * N_CONTACT_TABLES] order-independent 128-bit digest of every contact table's rows
     double* fT[N_FRICTION]; double* fmu[N_FRICTION]; double* ffn[N_FRICTION]; double* fbary[N_FRICTION];
 };
 
@@ -118,6 +119,16 @@ struct Contact {
     DevBuf<int32_t> list_ids[N_LISTS];
     DevBuf<double> list_dist[N_LISTS];
     DevBuf<int32_t> table[N_TABLES];
+    // Contact tables are written into BACK buffers and swapped in only when the new tables differ from the current ones as sets
+    // of rows (count + 128-bit digest per table): in resting / sliding contact consecutive detections find the same pairs, and
+    // keeping the current tables (same rows, old order) keeps the potentials' connectivity, the element layout and the symbolic
+    // phase of the assembly valid -- nothing downstream changes.
+    DevBuf<int32_t> table_back[N_CONTACT_TABLES];
+    DevBuf<unsigned long long> hash;
+    unsigned long long* h_hash = nullptr;
+    unsigned long long cur_hash[2 * N_CONTACT_TABLES] = {0};
+    bool cur_valid = false;
+    long long n_tables_same = 0, n_tables_changed = 0;
     int cand_cap = 1 << 16, list_cap = 1 << 14, table_cap = 1 << 14;
     int* h_counters = nullptr;
     int h_list_count[N_LISTS] = {0};
@@ -210,6 +221,7 @@ __global__ void __launch_bounds__(TILE) k_aabbs_tiles(Dev d, float extra, int do
 {
     __shared__ float s_lo[3][TILE / 32], s_hi[3][TILE / 32];
     if (blockIdx.x == 0 && threadIdx.x < 64 && ((clear_mask >> threadIdx.x) & 1ull)) d.counters[threadIdx.x] = 0;
+    if (blockIdx.x == 0 && threadIdx.x < 2 * N_CONTACT_TABLES && ((clear_mask >> 16) & 1ull)) d.hash[threadIdx.x] = 0ull;   // (the contact tables are rewritten)
     int cls, tile;
     if ((int)blockIdx.x < Tv) { cls = 0; tile = blockIdx.x; }
     else if ((int)blockIdx.x < Tv + Tt) { cls = 1; tile = blockIdx.x - Tv; }
@@ -625,7 +637,17 @@ __device__ __forceinline__ int push_row(const Dev& d, int table, const int* row)
     const int slot = atomicAdd(d.counters + 16 + table, 1);
     if (slot >= d.table_cap) { d.counters[3] = 1; return -1; }
     int32_t* dst = d.table[table] + (size_t)slot * d.table_stride[table];
-    for (int k = 0; k < d.table_stride[table]; k++) dst[k] = row[k];
+    unsigned long long x = 0x9E3779B97F4A7C15ull * (unsigned long long)(table + 1);
+    for (int k = 0; k < d.table_stride[table]; k++) {
+        dst[k] = row[k];
+        x = (x ^ (unsigned long long)(unsigned)row[k]) * 0xBF58476D1CE4E5B9ull;
+        x ^= x >> 29;
+    }
+    // digest of the table as a SET of rows (the append order depends on scheduling): sums of two independent mixes of every row
+    unsigned long long h1 = x * 0x94D049BB133111EBull; h1 ^= h1 >> 31;
+    unsigned long long h2 = (x ^ 0xD6E8FEB86659FD93ull) * 0xFF51AFD7ED558CCDull; h2 ^= h2 >> 33; h2 *= 0xC4CEB9FE1A85EC53ull; h2 ^= h2 >> 33;
+    atomicAdd(d.hash + 2 * table, h1);
+    atomicAdd(d.hash + 2 * table + 1, h2);
     return slot;
 }
 __device__ __forceinline__ void push_list(const Dev& d, int list, int width, const int* ids, double dist)
@@ -656,7 +678,7 @@ __device__ __forceinline__ Side side_of(const Dev& d, int g) { return {g, d.g_ps
 
 // One point (A) - primitive of a triangle (B) proximity pair.  nB = number of B vertices (1 point, 2 edge, 3 triangle).
 // mode 0: contact tables (EnergyFrictionalContact.cpp:381-455), mode 1: friction tables (:600-690)
-__device__ void emit_pt(const Dev& d, int mode, double dist, double stiffness, int nB, int pA, const int* vB, Side A, Side B)
+__device__ void emit_pt_one(const Dev& d, int mode, double dist, double stiffness, int nB, int pA, const int* vB, Side A, Side B)
 {
     if (mode > 1) return;   // raw lists only
     const double dhat = d.g_thickness[A.group] + d.g_thickness[B.group];
@@ -718,6 +740,7 @@ __device__ void emit_pt(const Dev& d, int mode, double dist, double stiffness, i
     }
 }
 
+__device__ __forceinline__ void emit_pt(const Dev& d, int mode, double dist, double stiffness, int nB, int pA, const int* vB, Side A, Side B);
 __device__ void narrow_pt(const Dev& d, double enl_sq, int mode, double stiffness)
 {
     const int total = min(d.counters[0], d.cand_cap);
@@ -764,7 +787,13 @@ __device__ void narrow_pt(const Dev& d, double enl_sq, int mode, double stiffnes
 
 // Edge-edge derived pairs.  kind 0: point(A edge-point) - point(B edge-point); 1: edge-point(A) - edge(B); 2: edge(A) - edge(B)
 // (EnergyFrictionalContact.cpp:457-529 contact, :692-772 friction).  eA / eB: the full edges (for the mollifier tables).
-__device__ void emit_ee(const Dev& d, int mode, double dist, double stiffness, int kind, const int* eA, int pA, const int* eB, int pB, Side A, Side B)
+// mode 3: contact AND friction tables from one detection (start of a time step: both are built at the same positions)
+__device__ __forceinline__ void emit_pt(const Dev& d, int mode, double dist, double stiffness, int nB, int pA, const int* vB, Side A, Side B)
+{
+    if (mode == 3) { emit_pt_one(d, 0, dist, stiffness, nB, pA, vB, A, B); emit_pt_one(d, 1, dist, stiffness, nB, pA, vB, A, B); }
+    else emit_pt_one(d, mode, dist, stiffness, nB, pA, vB, A, B);
+}
+__device__ void emit_ee_one(const Dev& d, int mode, double dist, double stiffness, int kind, const int* eA, int pA, const int* eB, int pB, Side A, Side B)
 {
     if (mode > 1) return;   // raw lists only
     const double dhat = d.g_thickness[A.group] + d.g_thickness[B.group];
@@ -823,6 +852,11 @@ __device__ void emit_ee(const Dev& d, int mode, double dist, double stiffness, i
     }
 }
 
+__device__ __forceinline__ void emit_ee(const Dev& d, int mode, double dist, double stiffness, int kind, const int* eA, int pA, const int* eB, int pB, Side A, Side B)
+{
+    if (mode == 3) { emit_ee_one(d, 0, dist, stiffness, kind, eA, pA, eB, pB, A, B); emit_ee_one(d, 1, dist, stiffness, kind, eA, pA, eB, pB, A, B); }
+    else emit_ee_one(d, mode, dist, stiffness, kind, eA, pA, eB, pB, A, B);
+}
 __device__ void narrow_ee(const Dev& d, double enl_sq, int mode, double stiffness, double parallel_tol)
 {
     const int total = min(d.counters[1], d.cand_cap);
@@ -911,7 +945,11 @@ void contact_destroy(sb_context* ctx)
     C->cand_pt.release(); C->cand_ee.release(); C->cand_et.release(); C->counters.release();
     for (int l = 0; l < N_LISTS; l++) { C->list_ids[l].release(); C->list_dist[l].release(); }
     for (int t = 0; t < N_TABLES; t++) C->table[t].release();
+    for (int t = 0; t < N_CONTACT_TABLES; t++) C->table_back[t].release();
+    C->hash.release();
+    if (std::getenv("SB_CONTACT_DUMP")) fprintf(stderr, "[stark_b200 contact] detections that rebuilt the contact tables: %lld unchanged as sets (tables kept), %lld changed\n", C->n_tables_same, C->n_tables_changed);
     if (C->h_counters) cudaFreeHost(C->h_counters);
+    if (C->h_hash) cudaFreeHost(C->h_hash);
     delete C;
     ctx->contact = nullptr;
 }
@@ -995,9 +1033,11 @@ static void ensure_capacities(sb_context* ctx, Contact* C)
         if (C->a_fbary[f] >= 0) { const size_t st = (size_t)ctx->arrays[C->a_fbary[f]].stride; ctx->arrays[C->a_fbary[f]].d.ensure_keep(st * C->table_cap, st * n, ctx->stream); }
     }
     if (moved) for (int t = 0; t < N_TABLES; t++) if (C->pot[t] >= 0) ctx->potentials[C->pot[t]].conn_ext = C->table[t].p;
+    for (int t = 0; t < N_CONTACT_TABLES; t++) C->table_back[t].ensure((size_t)C->table_cap * LAYOUTS[t].conn_stride);
+    C->hash.ensure(2 * N_CONTACT_TABLES);
 }
 
-static Dev make_dev(sb_context* ctx, Contact* C)
+static Dev make_dev(sb_context* ctx, Contact* C, bool back_tables = false)
 {
     Dev d;
     d.n_v = (int)C->h_v_group.size(); d.n_t = (int)C->h_t_group.size(); d.n_e = (int)C->h_e_group.size(); d.n_groups = (int)C->groups.size();
@@ -1012,8 +1052,9 @@ static Dev make_dev(sb_context* ctx, Contact* C)
     d.counters = C->counters.p;
     for (int l = 0; l < N_LISTS; l++) { d.list_ids[l] = C->list_ids[l].p; d.list_dist[l] = C->list_dist[l].p; }
     d.list_cap = C->list_cap;
-    for (int t = 0; t < N_TABLES; t++) { d.table[t] = C->table[t].p; d.table_stride[t] = LAYOUTS[t].conn_stride; }
+    for (int t = 0; t < N_TABLES; t++) { d.table[t] = (back_tables && t < N_CONTACT_TABLES) ? C->table_back[t].p : C->table[t].p; d.table_stride[t] = LAYOUTS[t].conn_stride; }
     d.table_cap = C->table_cap;
+    d.hash = C->hash.p;
     for (int f = 0; f < N_FRICTION; f++) {
         d.fT[f] = ctx->arrays[C->a_fT[f]].d.p; d.fmu[f] = ctx->arrays[C->a_fmu[f]].d.p; d.ffn[f] = ctx->arrays[C->a_ffn[f]].d.p;
         d.fbary[f] = (C->a_fbary[f] >= 0) ? ctx->arrays[C->a_fbary[f]].d.p : nullptr;
@@ -1076,17 +1117,17 @@ static int detect(sb_context* ctx, Contact* C, int mode, double enlargement)
     if (C->reorder_countdown-- <= 0) { int r = reorder_primitives(ctx, C); if (r) return r; }
     for (int attempt = 0; attempt < 8; attempt++) {
         ensure_capacities(ctx, C);
-        Dev d = make_dev(ctx, C);
+        Dev d = make_dev(ctx, C, mode == 0 || mode == 4 || mode == 5);   // (contact tables go to the back buffers, see Contact::table_back)
         Dev d0 = d;   // the intersection pass's view: its own boxes
         d0.bb_p = C->bb0_p.p; d0.bb_t = C->bb0_t.p; d0.bb_e = C->bb0_e.p; d0.tb_p = C->tb0_p.p; d0.tb_t = C->tb0_t.p; d0.tb_e = C->tb0_e.p;
-        const bool both = (mode == 3 || mode == 4);
+        const bool both = (mode == 3 || mode == 4 || mode == 5);
         const int nmax = std::max(d.n_v, std::max(d.n_t, d.n_e));
         // only the counters this mode rewrites are cleared (contact and friction tables live side by side): bit t = counters[t]
         auto bits = [](int lo, int n) { unsigned long long m = 0; for (int t = lo; t < lo + n; t++) m |= 1ull << t; return m; };
         unsigned long long clear = bits(0, 8);
-        if (mode == 0 || mode == 3 || mode == 4) clear |= bits(8, 6) | bits(16, N_CONTACT_TABLES);
-        if (mode == 1) clear |= bits(8, 6) | bits(16 + N_CONTACT_TABLES, N_FRICTION);
-        if (mode == 2 || mode == 3 || mode == 4) clear |= bits(8 + 6, 1);
+        if (mode == 0 || mode == 3 || mode == 4 || mode == 5) clear |= bits(8, 6) | bits(16, N_CONTACT_TABLES);
+        if (mode == 1 || mode == 5) clear |= bits(8, 6) | bits(16 + N_CONTACT_TABLES, N_FRICTION);
+        if (mode == 2 || mode == 3 || mode == 4 || mode == 5) clear |= bits(8 + 6, 1);
         const int Tv = (d.n_v + TILE - 1) / TILE, Tt = (d.n_t + TILE - 1) / TILE, Te = (d.n_e + TILE - 1) / TILE;
         auto broad_grid = [](long long n_tile_pairs) { return (int)std::max(1ll, std::min(n_tile_pairs, 148ll * 16)); };
         (void)nmax;
@@ -1094,21 +1135,25 @@ static int detect(sb_context* ctx, Contact* C, int mode, double enlargement)
             const float extra = (float)enlargement + FLT_EPSILON;
             const bool pt = C->enable_pt && d.n_t > 0 && d.n_v > 0, ee = C->enable_ee && d.n_e > 1;
             const int n0 = pt ? Tv * Tt : 0, n1 = ee ? Te * Te : 0;
+            timeline_point(st, "detect: begin");
             k_aabbs_tiles<<<Tv + Tt + Te, TILE, 0, st>>>(d, extra, 1, Tv, Tt, clear);
+            timeline_point(st, "detect: aabbs");
             if (both) SB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));   // (the counters are cleared: the intersection pass may start)
             if (n0 + n1 > 0) {
                 k_tile_pairs_all<<<(n0 + n1 + 255) / 256, 256, 0, st>>>(d, Tv, Tt, Te, n0, n1, 0);
                 if (pt && ee) k_broad_all<0, 1><<<broad_grid((long long)n0 + n1), TILE, 0, st>>>(d);
                 else if (pt) k_broad_all<0, -1><<<broad_grid(n0), TILE, 0, st>>>(d);
                 else k_broad_all<1, -1><<<broad_grid(n1), TILE, 0, st>>>(d);
-                const int emit_mode = (mode == 3) ? 2 : (mode == 4 ? 0 : mode);   // 2 = lists only (no table matches mode 2 inside emit_*)
+                const int emit_mode = (mode == 3) ? 2 : (mode == 4 ? 0 : (mode == 5 ? 3 : mode));   // 2 = lists only (no table matches mode 2 inside emit_*), 3 = contact + friction tables
+                timeline_point(st, "detect: broad");
                 k_narrow_all<<<148 * 2, 128, 0, st>>>(d, enlargement * enlargement, emit_mode, C->stiffness, 1e-30, pt ? 1 : 0, ee ? 1 : 0);
+                timeline_point(st, "detect: narrow");
                 ctx->launches += 3;
             }
             ctx->launches += 1;
             clear = 0;   // (mode 3: the intersection pass below must not wipe what the proximity pass just counted)
         }
-        if (mode == 2 || mode == 3 || mode == 4) {
+        if (mode == 2 || mode == 3 || mode == 4 || mode == 5) {
             // The intersection pass has its own boxes, tile-pair list, candidate list and counters: next to a proximity pass it
             // runs on a side stream at the same time (both are chains of latency-bound kernels).
             const float extra = 0.0f + FLT_EPSILON;   // IntersectionDetection uses non-enlarged AABBs (tmcd/BroadPhaseET.cpp:38)
@@ -1121,7 +1166,9 @@ static int detect(sb_context* ctx, Contact* C, int mode, double enlargement)
                 k_broad_all<2, -1><<<broad_grid((long long)Te * Tt), TILE, 0, s2>>>(d0);
                 ctx->launches += 2;
             }
+            timeline_point(s2, "detect: et broad");
             k_narrow_et<<<148, 128, 0, s2>>>(d0);
+            timeline_point(s2, "detect: et narrow");
             ctx->launches++;
             if (both) {
                 SB_CUDA(ctx, cudaEventRecord(ctx->ev_join[0], s2));
@@ -1129,6 +1176,7 @@ static int detect(sb_context* ctx, Contact* C, int mode, double enlargement)
             }
         }
         SB_CUDA(ctx, cudaMemcpyAsync(C->h_counters, C->counters.p, 64 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (mode == 0 || mode == 4 || mode == 5) SB_CUDA(ctx, cudaMemcpyAsync(C->h_hash, C->hash.p, 2 * N_CONTACT_TABLES * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         SB_CUDA(ctx, cudaStreamSynchronize(st));
         SB_CUDA(ctx, cudaGetLastError());
         if (ctx->profile) for (int k = 0; k < 3; k++) { ctx->stage_calls[ST_TILE_PAIRS_PT + k] += C->h_counters[4 + k]; ctx->stage_calls[ST_CAND_PT + k] += C->h_counters[k]; }
@@ -1145,9 +1193,7 @@ static int detect(sb_context* ctx, Contact* C, int mode, double enlargement)
     }
     for (int l = 0; l < N_LISTS; l++) C->h_list_count[l] = C->h_counters[8 + l];
     // publish the table sizes to the potentials / friction arrays
-    const bool contact_tables = (mode == 0 || mode == 4);
-    const int t0 = contact_tables ? 0 : N_CONTACT_TABLES, t1 = contact_tables ? N_CONTACT_TABLES : N_TABLES;
-    if (mode == 0 || mode == 1 || mode == 4) {
+    auto publish = [&](int t0, int t1) {
         bool any = false;   // empty before and empty now: neither the connectivity nor the pattern changed
         for (int t = t0; t < t1; t++) any = any || C->h_counters[16 + t] != 0 || C->h_table_count[t] != 0 || ctx->potentials[C->pot[t]].n_elem != 0;
         for (int t = t0; t < t1; t++) {
@@ -1166,7 +1212,22 @@ static int detect(sb_context* ctx, Contact* C, int mode, double enlargement)
             ctx->dynamic_version++;
             ctx->have_pgh = false;
         }
+    };
+    if (mode == 0 || mode == 4 || mode == 5) {
+        static const bool no_reuse = std::getenv("SB_NO_TABLE_REUSE") != nullptr;   // diagnostic hook
+        bool same = C->cur_valid && !no_reuse;
+        for (int t = 0; t < N_CONTACT_TABLES && same; t++)
+            same = C->h_counters[16 + t] == C->h_table_count[t] && C->h_hash[2 * t] == C->cur_hash[2 * t] && C->h_hash[2 * t + 1] == C->cur_hash[2 * t + 1];
+        if (same) C->n_tables_same++;   // same rows as the current tables: keep them (and everything built on them)
+        else {
+            C->n_tables_changed++;
+            for (int t = 0; t < N_CONTACT_TABLES; t++) { std::swap(C->table[t].p, C->table_back[t].p); std::swap(C->table[t].cap, C->table_back[t].cap); }
+            for (int k = 0; k < 2 * N_CONTACT_TABLES; k++) C->cur_hash[k] = C->h_hash[k];
+            C->cur_valid = true;
+            publish(0, N_CONTACT_TABLES);
+        }
     }
+    if (mode == 1 || mode == 5) publish(N_CONTACT_TABLES, N_TABLES);
     return 0;
 }
 
@@ -1249,6 +1310,7 @@ int sb_contact_init(sb_context* ctx, const sb_contact_bindings* b)
     C->h_blacklist.assign(MAX_GROUPS * MAX_GROUPS, 0);
     C->h_mu.assign(MAX_GROUPS * MAX_GROUPS, 0.0);
     cudaMallocHost(&C->h_counters, 64 * sizeof(int));
+    cudaMallocHost(&C->h_hash, 2 * N_CONTACT_TABLES * sizeof(unsigned long long));
     C->a_thickness = new_array(ctx, "contact_thicknesses", 1);
     C->a_stiffness = new_array(ctx, "contact_stiffness", 1);
     C->a_rb_local = new_array(ctx, "rigidbody_local_vertices", 3);
@@ -1372,6 +1434,30 @@ int sb_contact_update_friction(sb_context* ctx)
     }
     if ((r = update_vertices(ctx, C, true))) return r;   // dt = 0 (EnergyFrictionalContact.cpp:543)
     return detect(ctx, C, 1, 2.0 * max_thickness(C));
+}
+// before_time_step of the contact model.  Friction tables are built from the positions at dt = 0
+// (EnergyFrictionalContact.cpp:531-773).  When the caller guarantees that every DoF array is zero at this point -- the
+// reference's own order: PointDynamics / RigidBodyDynamics zero v1 / w1 in their before_time_step callbacks, registered before
+// the contact model's -- the positions at dt = 0 ARE the positions of the initial Newton state, so the same detection also
+// yields the contact tables and the intersection count that sb_newton_solve asks for first (it then finds them cached).
+int sb_contact_begin_time_step(sb_context* ctx, int dofs_are_zero)
+{
+    Contact* C = ctx ? ctx->contact : nullptr;
+    if (!C) return fail(ctx, SB_ERR_STATE, "sb_contact_begin_time_step: call sb_contact_init first");
+    if (C->groups.empty()) return SB_OK;
+    if (!dofs_are_zero || C->external_vertices) return sb_contact_update_friction(ctx);
+    int r;
+    if (C->topology_dirty && (r = upload_topology(ctx, C))) return r;
+    if ((r = refresh_params(ctx, C))) return r;
+    if (!C->enable_friction)
+        for (int t = N_CONTACT_TABLES; t < N_TABLES; t++) ctx->potentials[C->pot[t]].n_elem = 0;
+    StageTimer timer(ctx, ST_INTERSECTIONS);
+    if ((r = update_vertices(ctx, C, true))) return r;
+    if ((r = detect(ctx, C, C->enable_friction ? 5 : 4, 2.0 * max_thickness(C)))) return r;
+    C->cached_intersections = C->h_list_count[6];
+    C->intersections_state = ctx->state_version;
+    C->contacts_state = ctx->state_version;
+    return SB_OK;
 }
 int sb_contact_count_intersections(sb_context* ctx, int* out_count)
 {

@@ -10,18 +10,140 @@ static double now_ms()
 {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
+// SB_TIMELINE=1: no synchronisation; every stage records a CUDA event pair on the context stream and host timestamps, and
+// sb_newton_solve prints the timeline of its last call (where the GPU idles between stages, how long the host takes to issue
+// a stage).  Diagnostic only.
+struct TimelineRec { int stage; double h0, h1; cudaEvent_t e0, e1; };
+static std::vector<TimelineRec> g_timeline;
+static std::vector<cudaEvent_t> g_event_pool;
+static const bool g_timeline_on = std::getenv("SB_TIMELINE") != nullptr;
+static cudaEvent_t pool_event()
+{
+    if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+bool timeline_enabled() { return g_timeline_on; }
+// a completion point on any stream ("everything issued so far on `st` is done at t"), labelled
+struct TimelinePoint { const char* label; cudaEvent_t e; double h; };
+static std::vector<TimelinePoint> g_points;
+static std::mutex g_points_mutex;   // (the helper thread records points too)
+void timeline_point(cudaStream_t st, const char* label)
+{
+    if (!g_timeline_on) return;
+    std::lock_guard<std::mutex> lk(g_points_mutex);
+    TimelinePoint p; p.label = label; p.e = pool_event(); p.h = now_ms();
+    cudaEventRecord(p.e, st);
+    g_points.push_back(p);
+}
+void timeline_mark(sb_context* ctx, int stage)   // a zero-length record (e.g. begin / end of the solve)
+{
+    if (!g_timeline_on) return;
+    TimelineRec r; r.stage = stage; r.h0 = r.h1 = now_ms(); r.e0 = pool_event(); r.e1 = nullptr;
+    cudaEventRecord(r.e0, ctx->stream);
+    g_timeline.push_back(r);
+}
+void timeline_dump(sb_context* ctx, const char* const* names)
+{
+    if (!g_timeline_on || g_timeline.empty()) return;
+    cudaStreamSynchronize(ctx->stream);
+    if (!names) {   // discard
+        for (TimelineRec& r : g_timeline) { g_event_pool.push_back(r.e0); if (r.e1) g_event_pool.push_back(r.e1); }
+        g_timeline.clear();
+        for (TimelinePoint& q : g_points) g_event_pool.push_back(q.e);
+        g_points.clear();
+        return;
+    }
+    cudaDeviceSynchronize();
+    for (TimelinePoint& q : g_points) {
+        float g = 0.f;
+        cudaEventElapsedTime(&g, g_timeline.front().e0, q.e);
+        fprintf(stderr, "TIMEPOINT %-44s issued %9.3f done %9.3f\n", q.label, q.h - g_timeline.front().h0, g);
+        g_event_pool.push_back(q.e);
+    }
+    g_points.clear();
+    const TimelineRec& base = g_timeline.front();
+    double prev_gpu_end = 0.0;
+    fprintf(stderr, "TIMELINE %-18s %9s %9s | %9s %9s %9s (ms; gpu gap = idle before the stage's first kernel)\n", "stage", "host_beg", "host_dur", "gpu_beg", "gpu_dur", "gpu_gap");
+    for (const TimelineRec& r : g_timeline) {
+        float g0 = 0.f, g1 = 0.f;
+        cudaEventElapsedTime(&g0, base.e0, r.e0);
+        if (r.e1) cudaEventElapsedTime(&g1, base.e0, r.e1); else g1 = g0;
+        fprintf(stderr, "TIMELINE %-18s %9.3f %9.3f | %9.3f %9.3f %9.3f\n", r.stage >= 0 ? names[r.stage] : "mark", r.h0 - base.h0, r.h1 - r.h0, g0, g1 - g0, g0 - prev_gpu_end);
+        prev_gpu_end = g1;
+    }
+    for (TimelineRec& r : g_timeline) { g_event_pool.push_back(r.e0); if (r.e1) g_event_pool.push_back(r.e1); }
+    g_timeline.clear();
+}
 StageTimer::StageTimer(sb_context* c, int s) : ctx(c), stage(s), t0(0.0)
 {
+    if (g_timeline_on) {
+        TimelineRec r; r.stage = s; r.h0 = now_ms(); r.h1 = 0.0; r.e0 = pool_event(); r.e1 = pool_event();
+        cudaEventRecord(r.e0, ctx->stream);
+        g_timeline.push_back(r);
+        t0 = (double)(g_timeline.size() - 1);
+        return;
+    }
     if (!ctx->profile) return;
     cudaStreamSynchronize(ctx->stream);
     t0 = now_ms();
 }
 StageTimer::~StageTimer()
 {
+    if (g_timeline_on) {
+        TimelineRec& r = g_timeline[(size_t)t0];
+        cudaEventRecord(r.e1, ctx->stream);
+        r.h1 = now_ms();
+        return;
+    }
     if (!ctx->profile) return;
     cudaStreamSynchronize(ctx->stream);
     ctx->stage_ms[stage] += now_ms() - t0;
     ctx->stage_calls[stage]++;
+}
+
+static const char* const g_stage_names[ST_COUNT] = {"contact_update", "intersections", "eval_pgh", "eval_p", "project_to_pd", "assembly_symbolic", "assembly_numeric", "pcg", "line_search_misc", "cg_iterations", "pcg_kernel_setup", "project_selected", "project_changed", "pcg_cycles_spmv", "pcg_cycles_barrier", "pcg_cycles_reduce", "pcg_cycles_vector",
+                                            "tile_pairs_pt", "tile_pairs_ee", "tile_pairs_et", "candidates_pt", "candidates_ee", "candidates_et", "project_sweeps", "pcg_cycles_window"};
+const char* const* stage_names() { return g_stage_names; }
+
+void Issuer::start(int dev)
+{
+    device = dev;
+    th = std::thread([this] {
+        cudaSetDevice(device);
+        std::unique_lock<std::mutex> lk(m);
+        while (true) {
+            cv.wait(lk, [this] { return quit || job; });
+            if (quit) return;
+            std::function<void()> f = std::move(job);
+            job = nullptr;
+            lk.unlock();
+            f();
+            state.store(0, std::memory_order_release);
+            lk.lock();
+        }
+    });
+}
+void Issuer::post(std::function<void()> f)
+{
+    wait();
+    state.store(1, std::memory_order_release);
+    { std::lock_guard<std::mutex> lk(m); job = std::move(f); }
+    cv.notify_one();
+}
+void Issuer::stop()
+{
+    wait();
+    { std::lock_guard<std::mutex> lk(m); quit = true; }
+    cv.notify_one();
+    if (th.joinable()) th.join();
+}
+
+// writers of device arrays are ordered behind asynchronous downloads still in flight (sb_array_download_async)
+void order_after_async_downloads(sb_context* ctx)
+{
+    if (!ctx->copy_dev_pending) return;
+    cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_done, 0);
+    ctx->copy_dev_pending = false;
 }
 
 int fail(sb_context* ctx, int code, const std::string& msg)
@@ -174,6 +296,117 @@ int refresh_slots(sb_context* ctx, Potential& p)
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// evaluation
+// ---------------------------------------------------------------------------------------------------
+// large potentials stay on the context stream; the small ones are spread over the side streams (fork / join by events)
+constexpr int SMALL_POTENTIAL = 100000;   // (everything but the volume elements of a large mesh: the per-node inertia terms overlap with them too)
+
+static EvalArgs make_args(sb_context* ctx, Potential& p)
+{
+    EvalArgs a;
+    a.slots = p.slots.p;
+    a.slots_host = p.slots_host.data();
+    a.conn = p.conn_ext ? p.conn_ext : p.conn.p;
+    a.conn_stride = p.conn_stride;
+    a.n_elem = p.n_elem;
+    for (int b = 0; b < MAX_BLOCKS; b++) a.blocks[b] = p.blocks[b];
+    a.grad = ctx->grad.p;
+    a.H = ctx->H.p + p.H_off;
+    a.rows = ctx->rows.p + p.rows_off;
+    a.E_elem = ctx->E_elem.p + p.E_off;
+    a.g_elem = nullptr;
+    return a;
+}
+
+// grow an element-output buffer; `keep` > 0: the first `keep` entries are already written by kernels in flight (the static
+// potentials of a pre-launched evaluation) and must survive -- rare (the buffers carry slack for the dynamic potentials)
+template<class T> static void grow_output(sb_context* ctx, DevBuf<T>& b, size_t n, size_t keep)
+{
+    if (n <= b.cap) return;
+    const size_t want = n + n / 16 + (1u << 20);
+    if (keep) { cudaDeviceSynchronize(); b.ensure_keep(want, keep, ctx->stream); }
+    else b.ensure(want);
+}
+
+// P+G+H, first half: everything that does not depend on the contact tables.  Lays out the STATIC potentials (their offsets
+// never depend on the dynamic ones, which follow them), clears gradient / projection flags and launches the static potentials'
+// kernels.  sb_newton_solve calls this right after a line-search step has been applied and BEFORE the collision detection of
+// the trial state: the volume elements' kernel (70 us at the 200k-tet scene) then runs while the host issues the detection,
+// instead of after the detection's synchronisation.  eval_internal picks the result up if the state has not changed since.
+static int pgh_static_part(sb_context* ctx)
+{
+    assembly_prefetch_drain(ctx);   // (a prefetched symbolic phase still reads the previous evaluation's block rows)
+    ctx->pgh_cache_ok = false;
+    ctx->have_pgh = false;
+    recompute_dof_offsets(ctx);
+    if (ctx->ndofs <= 0) return fail(ctx, SB_ERR_STATE, "sb_eval: no degrees of freedom");
+    if (ctx->ndofs % 3 != 0) return fail(ctx, SB_ERR_STATE, "sb_eval: ndofs must be divisible by 3");
+    size_t H_total = 0, rows_total = 0, E_total = 0, n_blocks = 0;
+    for (auto& p : ctx->potentials) {
+        if (p.dynamic) continue;
+        H_total = (H_total + 15) & ~(size_t)15;   // every potential's Hessian block starts 128 B aligned (bulk stores)
+        p.H_off = H_total; p.rows_off = rows_total; p.E_off = E_total;
+        const size_t n = p.k->n_dof;
+        H_total += (size_t)p.n_elem * n * n;
+        rows_total += (size_t)p.n_elem * p.k->nb;
+        E_total += (size_t)p.n_elem;
+        n_blocks += (size_t)p.n_elem * p.k->nb * p.k->nb;
+    }
+    ctx->st_H = H_total; ctx->st_rows = rows_total; ctx->st_E = E_total; ctx->st_blocks = n_blocks;
+    grow_output(ctx, ctx->E_elem, E_total + 1, 0);
+    grow_output(ctx, ctx->H, H_total + 1, 0);
+    grow_output(ctx, ctx->rows, rows_total + 1, 0);
+    grow_output(ctx, ctx->projected, E_total + 1, 0);
+    ctx->grad.ensure(ctx->ndofs);
+    SB_CUDA(ctx, cudaMemsetAsync(ctx->grad.p, 0, sizeof(double) * ctx->ndofs, ctx->stream));
+    SB_CUDA(ctx, cudaMemsetAsync(ctx->projected.p, 0, ctx->projected.cap, ctx->stream));   // (whole buffer: the dynamic element count is not known yet)
+    for (auto& p : ctx->potentials) {
+        if (p.dynamic || p.n_elem == 0) continue;
+        int r = refresh_slots(ctx, p);
+        if (r) return r;
+    }
+    // the big potentials first: they are the critical path of the evaluation.  (The fork event is recorded BEFORE them: the small
+    // potentials on the side streams wait for the memsets above, not for the volume kernel.)
+    ctx->st_side_mask = 0;
+    bool forked = false;
+    int next_side = 0;
+    for (auto& p : ctx->potentials)
+        if (!p.dynamic && p.n_elem > 0 && p.n_elem < SMALL_POTENTIAL && !forked) { SB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream)); forked = true; }
+    for (int pass = 0; pass < 2; pass++)
+        for (auto& p : ctx->potentials) {
+            if (p.dynamic || p.n_elem == 0) continue;
+            const bool big = p.n_elem >= SMALL_POTENTIAL;
+            if (big != (pass == 0)) continue;
+            cudaStream_t st = ctx->stream;
+            if (!big) {
+                const int k = next_side++ % sb_context::N_SIDE;
+                if (!(ctx->st_side_mask & (1u << k))) { SB_CUDA(ctx, cudaStreamWaitEvent(ctx->side[k], ctx->ev_fork, 0)); ctx->st_side_mask |= 1u << k; }
+                st = ctx->side[k];
+            }
+            p.k->launch_pgh(make_args(ctx, p), st);
+            ctx->launches++;
+            timeline_point(st, p.k->name);
+        }
+    SB_CUDA(ctx, cudaGetLastError());
+    ctx->st_next_side = next_side;
+    return 0;
+}
+int eval_prelaunch_static(sb_context* ctx)
+{
+    // Measured at the 200k-tet scene: 921 it/s with the pre-launch against 934 without (the dynamic potentials are then issued
+    // after the detection's synchronisation with no kernel to hide behind, instead of under the volume kernel) -- off unless
+    // SB_PRELAUNCH is set; kept for scenes whose detection is long compared with the volume kernel.
+    static const bool on = std::getenv("SB_PRELAUNCH") != nullptr;
+    if (!on) return 0;
+    StageTimer timer(ctx, ST_EVAL_PGH);
+    int r = pgh_static_part(ctx);
+    if (r) return r;
+    ctx->pre_valid = true;
+    ctx->pre_state = ctx->state_version; ctx->pre_static = ctx->static_version;
+    return 0;
+}
+
 int eval_internal(sb_context* ctx, int mode, double* out_E, double* out_grad_inf, bool sync_scalars)
 {
     if (mode != SB_EVAL_P && mode != SB_EVAL_PGH) return fail(ctx, SB_ERR_ARG, "sb_eval: unknown mode");
@@ -188,129 +421,149 @@ int eval_internal(sb_context* ctx, int mode, double* out_E, double* out_grad_inf
     StageTimer timer(ctx, mode == SB_EVAL_PGH ? ST_EVAL_PGH : ST_EVAL_P);
     static const bool eval_dump = std::getenv("SB_EVAL_DUMP") != nullptr;   // diagnostic: host time of the phases of every evaluation
     const double td0 = eval_dump ? now_ms() : 0.0;
-    if (mode == SB_EVAL_PGH) { assembly_prefetch_drain(ctx); ctx->pgh_cache_ok = false; }
-    const double td1 = eval_dump ? now_ms() : 0.0;   // (a prefetched symbolic phase still reads the previous evaluation's block rows)
-    recompute_dof_offsets(ctx);
-    if (ctx->ndofs <= 0) return fail(ctx, SB_ERR_STATE, "sb_eval: no degrees of freedom");
-    if (ctx->ndofs % 3 != 0) return fail(ctx, SB_ERR_STATE, "sb_eval: ndofs must be divisible by 3");
-
-    // layout of the shared element-output buffers
-    size_t H_total = 0, rows_total = 0, E_total = 0, n_blocks = 0;
-    for (int pi : layout_order(ctx)) {
-        Potential& p = ctx->potentials[pi];
-        H_total = (H_total + 15) & ~(size_t)15;   // every potential's Hessian block starts 128 B aligned (bulk stores)
-        p.H_off = H_total; p.rows_off = rows_total; p.E_off = E_total;
-        const size_t n = p.k->n_dof;
-        H_total += (size_t)p.n_elem * n * n;
-        rows_total += (size_t)p.n_elem * p.k->nb;
-        E_total += (size_t)p.n_elem;
-        n_blocks += (size_t)p.n_elem * p.k->nb * p.k->nb;
+    const bool pre = ctx->pre_valid && ctx->pre_state == ctx->state_version && ctx->pre_static == ctx->static_version;
+    if (ctx->pre_valid && !pre) {
+        // a pre-launched static part of another state (the trial was rejected before it was evaluated): its kernels are still
+        // writing the output buffers -- they are in stream order before anything launched below
+        ctx->have_pgh = false;
     }
-    ctx->E_elem.ensure(E_total + 1);
+    ctx->pre_valid = false;
+    double td1 = td0;
+
     if (mode == SB_EVAL_PGH) {
-        ctx->H.ensure(H_total + 1);
-        ctx->rows.ensure(rows_total + 1);
-        ctx->grad.ensure(ctx->ndofs);
-        ctx->projected.ensure(E_total + 1);
-        SB_CUDA(ctx, cudaMemsetAsync(ctx->grad.p, 0, sizeof(double) * ctx->ndofs, ctx->stream));
-        SB_CUDA(ctx, cudaMemsetAsync(ctx->projected.p, 0, E_total + 1, ctx->stream));
+        if (!pre) { int r = pgh_static_part(ctx); if (r) return r; }
+        td1 = eval_dump ? now_ms() : 0.0;
+        // ---- second half: the dynamic potentials (contact / friction tables), laid out behind the static ones ----
+        size_t H_total = ctx->st_H, rows_total = ctx->st_rows, E_total = ctx->st_E, n_blocks = ctx->st_blocks;
+        for (auto& p : ctx->potentials) {
+            if (!p.dynamic) continue;
+            H_total = (H_total + 15) & ~(size_t)15;
+            p.H_off = H_total; p.rows_off = rows_total; p.E_off = E_total;
+            const size_t n = p.k->n_dof;
+            H_total += (size_t)p.n_elem * n * n;
+            rows_total += (size_t)p.n_elem * p.k->nb;
+            E_total += (size_t)p.n_elem;
+            n_blocks += (size_t)p.n_elem * p.k->nb * p.k->nb;
+        }
+        if (E_total + 1 > ctx->projected.cap) {   // (the flags of the new tail must be cleared as well)
+            grow_output(ctx, ctx->projected, E_total + 1, ctx->st_E);
+            SB_CUDA(ctx, cudaMemsetAsync(ctx->projected.p + ctx->st_E, 0, ctx->projected.cap - ctx->st_E, ctx->stream));
+        }
+        grow_output(ctx, ctx->E_elem, E_total + 1, ctx->st_E);
+        grow_output(ctx, ctx->H, H_total + 1, ctx->st_H);
+        grow_output(ctx, ctx->rows, rows_total + 1, ctx->st_rows);
         ctx->n_hessians = E_total;
         ctx->n_blocks_total = n_blocks;
-        {   // blocks of the static potentials (numbered first)
-            size_t nsb = 0;
-            for (auto& p : ctx->potentials) if (!p.dynamic) nsb += (size_t)p.n_elem * p.k->nb * p.k->nb;
-            ctx->n_static_blocks = nsb;
-        }
+        ctx->n_static_blocks = ctx->st_blocks;
         ctx->n_rows_total = rows_total;
         ctx->H_total = H_total;
         ctx->n_projected = 0;
         ctx->eval_id++;
         projector_prepare(ctx);
-    }
-
-    for (auto& p : ctx->potentials) {
-        if (p.n_elem == 0) continue;
-        int r = refresh_slots(ctx, p);
-        if (r) return r;
-    }
-    // large potentials stay on the context stream; the small ones are spread over the side streams (fork / join by events)
-    constexpr int SMALL = 100000;   // (everything but the volume elements of a large mesh: the per-node inertia terms overlap with them too)
-    int n_small = 0;
-    for (auto& p : ctx->potentials) if (p.n_elem > 0 && p.n_elem < SMALL) n_small++;
-    const bool fork = n_small >= 2;
-    bool side_used[sb_context::N_SIDE] = {false, false, false, false};
-    if (fork) {
-        SB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
-    }
-    int next_side = 0;
-    // energy-only evaluation: every small potential goes into one multi-potential launch on a side stream
-    MultiPArgs M;
-    M.n = 0; M.pad = 0;
-    int multi_ctas = 0;
-    const bool use_multi = (mode == SB_EVAL_P) && n_small >= 2;
-    for (auto& p : ctx->potentials) {
-        if (p.n_elem == 0) continue;
-        if (use_multi && p.n_elem < SMALL && p.k->p_kind >= 0 && M.n < MULTI_P_MAX) {
-            MultiPItem& it = M.it[M.n++];
-            it.slots = p.slots.p; it.conn = p.conn_ext ? p.conn_ext : p.conn.p; it.E_elem = ctx->E_elem.p + p.E_off;
-            it.conn_stride = p.conn_stride; it.n_elem = p.n_elem; it.kind = p.k->p_kind; it.cta0 = multi_ctas;
-            multi_ctas += multi_p_ctas(p.k->p_kind, p.n_elem);
-            continue;
+        unsigned side_mask = ctx->st_side_mask;
+        int next_side = ctx->st_next_side;
+        bool forked = false;
+        unsigned dyn_mask = 0;
+        bool dyn_all_small = true;
+        for (auto& p : ctx->potentials) {
+            if (!p.dynamic || p.n_elem == 0) continue;
+            int r = refresh_slots(ctx, p);
+            if (r) return r;
+            cudaStream_t st = ctx->stream;
+            if (p.n_elem < SMALL_POTENTIAL) {
+                if (!forked) { SB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream)); forked = true; }   // (behind the detection that wrote the tables)
+                const int k = next_side++ % sb_context::N_SIDE;
+                if (!(dyn_mask & (1u << k))) { SB_CUDA(ctx, cudaStreamWaitEvent(ctx->side[k], ctx->ev_fork, 0)); dyn_mask |= 1u << k; }
+                st = ctx->side[k];
+            } else dyn_all_small = false;
+            p.k->launch_pgh(make_args(ctx, p), st);
+            ctx->launches++;
+            timeline_point(st, p.k->name);
         }
-        EvalArgs a;
-        a.slots = p.slots.p;
-        a.slots_host = p.slots_host.data();
-        a.conn = p.conn_ext ? p.conn_ext : p.conn.p;
-        a.conn_stride = p.conn_stride;
-        a.n_elem = p.n_elem;
-        for (int b = 0; b < MAX_BLOCKS; b++) a.blocks[b] = p.blocks[b];
-        a.grad = ctx->grad.p;
-        a.H = ctx->H.p + p.H_off;
-        a.rows = ctx->rows.p + p.rows_off;
-        a.E_elem = ctx->E_elem.p + p.E_off;
-        a.g_elem = nullptr;
-        cudaStream_t st = ctx->stream;
-        if (fork && p.n_elem < SMALL) {
+        // The symbolic phase of the coming assembly depends on the dynamic potentials' block rows only: the helper thread issues
+        // it (its own stream, behind these kernels) while this thread goes on with the reductions.
+        const bool prefetch = dyn_mask && dyn_all_small;
+        if (prefetch)
+            for (int k = 0; k < sb_context::N_SIDE; k++)
+                if (dyn_mask & (1u << k)) SB_CUDA(ctx, cudaEventRecord(ctx->ev_dyn[k], ctx->side[k]));
+        side_mask |= dyn_mask;
+        for (int k = 0; k < sb_context::N_SIDE; k++)
+            if (side_mask & (1u << k)) {
+                SB_CUDA(ctx, cudaEventRecord(ctx->ev_join[k], ctx->side[k]));
+                SB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[k], 0));
+            }
+        SB_CUDA(ctx, cudaGetLastError());
+        timeline_point(ctx->stream, "eval: joined");
+        reduce_sum_and_absmax(ctx, ctx->E_elem.p, E_total, ctx->grad.p, ctx->ndofs, ctx->d_scalars);
+        timeline_point(ctx->stream, "eval: reduced");
+        ctx->have_pgh = true;
+        if (sync_scalars) SB_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        // issued LAST: the ~20 launches of the symbolic phase take the host a while, and the reductions must already be queued
+        if (prefetch) assembly_prefetch_symbolic(ctx, dyn_mask);
+    } else {
+        // ---- energy only (line-search trials after a backtrack) ----
+        recompute_dof_offsets(ctx);
+        if (ctx->ndofs <= 0) return fail(ctx, SB_ERR_STATE, "sb_eval: no degrees of freedom");
+        size_t E_total = 0;
+        for (int pi : layout_order(ctx)) { Potential& p = ctx->potentials[pi]; p.E_off = E_total; E_total += (size_t)p.n_elem; }
+        // (a P evaluation overwrites the element energies only; the offsets of Hessians / rows of the last P+G+H stay valid)
+        grow_output(ctx, ctx->E_elem, E_total + 1, 0);
+        for (auto& p : ctx->potentials) {
+            if (p.n_elem == 0) continue;
+            int r = refresh_slots(ctx, p);
+            if (r) return r;
+        }
+        int n_small = 0;
+        for (auto& p : ctx->potentials) if (p.n_elem > 0 && p.n_elem < SMALL_POTENTIAL) n_small++;
+        const bool fork = n_small >= 2;
+        bool side_used[sb_context::N_SIDE] = {false, false, false, false};
+        if (fork) SB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+        int next_side = 0;
+        // every small potential goes into one multi-potential launch on a side stream
+        MultiPArgs M;
+        M.n = 0; M.pad = 0;
+        int multi_ctas = 0;
+        const bool use_multi = n_small >= 2;
+        for (auto& p : ctx->potentials) {
+            if (p.n_elem == 0) continue;
+            if (use_multi && p.n_elem < SMALL_POTENTIAL && p.k->p_kind >= 0 && M.n < MULTI_P_MAX) {
+                MultiPItem& it = M.it[M.n++];
+                it.slots = p.slots.p; it.conn = p.conn_ext ? p.conn_ext : p.conn.p; it.E_elem = ctx->E_elem.p + p.E_off;
+                it.conn_stride = p.conn_stride; it.n_elem = p.n_elem; it.kind = p.k->p_kind; it.cta0 = multi_ctas;
+                multi_ctas += multi_p_ctas(p.k->p_kind, p.n_elem);
+                continue;
+            }
+            cudaStream_t st = ctx->stream;
+            if (fork && p.n_elem < SMALL_POTENTIAL) {
+                const int k = next_side++ % sb_context::N_SIDE;
+                if (!side_used[k]) { SB_CUDA(ctx, cudaStreamWaitEvent(ctx->side[k], ctx->ev_fork, 0)); side_used[k] = true; }
+                st = ctx->side[k];
+            }
+            p.k->launch_p(make_args(ctx, p), st);
+            ctx->launches++;
+        }
+        if (M.n > 0) {
             const int k = next_side++ % sb_context::N_SIDE;
             if (!side_used[k]) { SB_CUDA(ctx, cudaStreamWaitEvent(ctx->side[k], ctx->ev_fork, 0)); side_used[k] = true; }
-            st = ctx->side[k];
+            launch_p_multi(M, multi_ctas, ctx->side[k]);
+            ctx->launches++;
         }
-        if (mode == SB_EVAL_PGH) p.k->launch_pgh(a, st);
-        else p.k->launch_p(a, st);
-        ctx->launches++;
-    }
-    if (M.n > 0) {
-        const int k = next_side++ % sb_context::N_SIDE;
-        if (!side_used[k]) { SB_CUDA(ctx, cudaStreamWaitEvent(ctx->side[k], ctx->ev_fork, 0)); side_used[k] = true; }
-        launch_p_multi(M, multi_ctas, ctx->side[k]);
-        ctx->launches++;
-    }
-    for (int k = 0; k < sb_context::N_SIDE; k++)
-        if (side_used[k]) {
-            SB_CUDA(ctx, cudaEventRecord(ctx->ev_join[k], ctx->side[k]));
-            SB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[k], 0));
-        }
-    SB_CUDA(ctx, cudaGetLastError());
-
-    if (mode == SB_EVAL_PGH) {
-        reduce_sum_and_absmax(ctx, ctx->E_elem.p, E_total, ctx->grad.p, ctx->ndofs, ctx->d_scalars);
-        ctx->have_pgh = true;
-    } else {
+        for (int k = 0; k < sb_context::N_SIDE; k++)
+            if (side_used[k]) {
+                SB_CUDA(ctx, cudaEventRecord(ctx->ev_join[k], ctx->side[k]));
+                SB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[k], 0));
+            }
+        SB_CUDA(ctx, cudaGetLastError());
         reduce_sum(ctx, ctx->E_elem.p, E_total, ctx->d_scalars + 0);
     }
-    if (sync_scalars) SB_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (sync_scalars && mode != SB_EVAL_PGH) SB_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     const double td2 = eval_dump ? now_ms() : 0.0;
-    // The pattern of the coming assembly, under this evaluation.  Issued LAST: its ~20 launches take the host longer than the
-    // volume kernel runs, and the reductions above must already be queued behind that kernel when it ends.
-    if (mode == SB_EVAL_PGH && fork) {
-        bool dyn_on_side = true;         // (the prefetch waits for the side streams only: every dynamic potential must be there)
-        for (auto& p : ctx->potentials) if (p.dynamic && p.n_elem >= SMALL) dyn_on_side = false;
-        if (dyn_on_side) assembly_prefetch_symbolic(ctx);
-    }
-    const double td3 = eval_dump ? now_ms() : 0.0;
+    const double td3 = td2;
+    if (!sync_scalars) ctx->issuer->wait();   // (the helper thread's job reads the potentials: it ends inside this call)
     if (sync_scalars) {
         SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        if (eval_dump) fprintf(stderr, "EVALDUMP mode=%d drain=%.1f issue=%.1f prefetch=%.1f sync=%.1f us\n", mode, 1e3 * (td1 - td0), 1e3 * (td2 - td1), 1e3 * (td3 - td2), 1e3 * (now_ms() - td3));
+        ctx->issuer->wait();
+        if (eval_dump) fprintf(stderr, "EVALDUMP mode=%d static=%.1f issue=%.1f prefetch=%.1f sync=%.1f us\n", mode, 1e3 * (td1 - td0), 1e3 * (td2 - td1), 1e3 * (td3 - td2), 1e3 * (now_ms() - td3));
         if (out_E) *out_E = ctx->h_scalars[0];
         if (out_grad_inf && mode == SB_EVAL_PGH) *out_grad_inf = ctx->h_scalars[1];
         if (mode == SB_EVAL_PGH) {
@@ -332,6 +585,11 @@ __global__ void k_axpy_set(double* __restrict__ dst, const double* __restrict__ 
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = base[i] + s * d[i];
+}
+__global__ void k_axpy(double* __restrict__ y, const double* __restrict__ x, double a, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] += a * x[i];
 }
 __global__ void k_fill(double* __restrict__ x, double v, int n)
 {
@@ -374,6 +632,11 @@ int sb_create(sb_context** out, int device, void* stream)
         if (cudaEventCreateWithFlags(&ctx->ev_join[k], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SB_ERR_CUDA; }
     }
     if (cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SB_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&ctx->sym_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SB_ERR_CUDA; }
+    for (int k = 0; k < sb_context::N_SIDE; k++)
+        if (cudaEventCreateWithFlags(&ctx->ev_dyn[k], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SB_ERR_CUDA; }
+    ctx->issuer = new Issuer();
+    ctx->issuer->start(device);
     if (cudaMallocHost(&ctx->h_scalars, 64 * sizeof(double)) != cudaSuccess) { delete ctx; return SB_ERR_CUDA; }
     if (cudaMalloc(&ctx->d_scalars, 64 * sizeof(double)) != cudaSuccess) { delete ctx; return SB_ERR_CUDA; }
     cudaMemset(ctx->d_scalars, 0, 64 * sizeof(double));
@@ -389,7 +652,9 @@ void sb_destroy(sb_context* ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->issuer) { ctx->issuer->stop(); delete ctx->issuer; ctx->issuer = nullptr; }
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->sym_stream) cudaStreamSynchronize(ctx->sym_stream);
     for (auto& r : ctx->host_regions) cudaHostUnregister(r.first);
     ctx->host_regions.clear();
     assembly_destroy(ctx);
@@ -408,6 +673,9 @@ void sb_destroy(sb_context* ctx)
         if (ctx->ev_join[k]) cudaEventDestroy(ctx->ev_join[k]);
     }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    for (int k = 0; k < sb_context::N_SIDE; k++) if (ctx->ev_dyn[k]) cudaEventDestroy(ctx->ev_dyn[k]);
+    if (ctx->sym_stream) cudaStreamDestroy(ctx->sym_stream);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); cudaEventDestroy(ctx->ev_copy_src); cudaEventDestroy(ctx->ev_copy_done); }
     if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
     if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -422,7 +690,7 @@ int sb_synchronize(sb_context* ctx)
     SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return SB_OK;
 }
-int64_t sb_launch_count(const sb_context* ctx) { return ctx ? ctx->launches : 0; }
+int64_t sb_launch_count(const sb_context* ctx) { return ctx ? ctx->launches.load() : 0; }
 
 int sb_profile_stages(sb_context* ctx, int enable)
 {
@@ -434,8 +702,7 @@ int sb_profile_stages(sb_context* ctx, int enable)
 const char* sb_profile_report(sb_context* ctx)
 {
     if (!ctx) return "";
-    static const char* names[ST_COUNT] = {"contact_update", "intersections", "eval_pgh", "eval_p", "project_to_pd", "assembly_symbolic", "assembly_numeric", "pcg", "line_search_misc", "cg_iterations", "pcg_kernel_setup", "project_selected", "project_changed", "pcg_cycles_spmv", "pcg_cycles_barrier", "pcg_cycles_reduce", "pcg_cycles_vector",
-                                            "tile_pairs_pt", "tile_pairs_ee", "tile_pairs_et", "candidates_pt", "candidates_ee", "candidates_et", "project_sweeps", "pcg_cycles_window"};
+    const char* const* names = g_stage_names;
     ctx->profile_report.clear();
     for (int i = 0; i < ST_COUNT; i++)
         ctx->profile_report += std::string(names[i]) + " " + std::to_string(ctx->stage_ms[i]) + " " + std::to_string(ctx->stage_calls[i]) + "\n";
@@ -463,6 +730,7 @@ int sb_array_upload(sb_context* ctx, int array, const double* host, int n_rows)
     int r = check_array(ctx, array, "sb_array_upload"); if (r) return r;
     if (n_rows < 0 || (n_rows > 0 && !host)) return fail(ctx, SB_ERR_ARG, "sb_array_upload: bad argument");
     Array& a = ctx->arrays[array];
+    order_after_async_downloads(ctx);
     a.d.ensure((size_t)std::max(n_rows, 1) * a.stride);
     a.n_rows = n_rows;
     ctx->state_version++;
@@ -486,6 +754,7 @@ int sb_array_fill(sb_context* ctx, int array, int n_rows, double value)
     int r = check_array(ctx, array, "sb_array_fill"); if (r) return r;
     if (n_rows < 0) return fail(ctx, SB_ERR_ARG, "sb_array_fill: bad argument");
     Array& a = ctx->arrays[array];
+    order_after_async_downloads(ctx);
     a.d.ensure((size_t)std::max(n_rows, 1) * a.stride);
     a.n_rows = n_rows;
     ctx->state_version++;
@@ -494,6 +763,65 @@ int sb_array_fill(sb_context* ctx, int array, int n_rows, double value)
         if (value == 0.0) SB_CUDA(ctx, cudaMemsetAsync(a.d.p, 0, sizeof(double) * (size_t)n, ctx->stream));
         else { k_fill<<<(n + 255) / 256, 256, 0, ctx->stream>>>(a.d.p, value, n); ctx->launches++; }
     }
+    return SB_OK;
+}
+// state roll of a time step on the device (replaces the host loops of PointDynamics::_on_time_step_accepted,
+// S/models/deformables/PointDynamics.cpp:64-78: x0 += dt v1, v0 = v1)
+int sb_array_axpy(sb_context* ctx, int y, int x, double alpha, int n_rows)
+{
+    int r = check_array(ctx, y, "sb_array_axpy"); if (r) return r;
+    r = check_array(ctx, x, "sb_array_axpy"); if (r) return r;
+    Array& ay = ctx->arrays[y]; Array& ax = ctx->arrays[x];
+    if (n_rows < 0 || ay.stride != ax.stride || n_rows > ay.n_rows || n_rows > ax.n_rows) return fail(ctx, SB_ERR_ARG, "sb_array_axpy: shapes do not match");
+    order_after_async_downloads(ctx);
+    ctx->state_version++;
+    const int n = n_rows * ay.stride;
+    if (n > 0) { k_axpy<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ay.d.p, ax.d.p, alpha, n); ctx->launches++; }
+    SB_CUDA(ctx, cudaGetLastError());
+    return SB_OK;
+}
+int sb_array_copy(sb_context* ctx, int dst, int src, int n_rows)
+{
+    int r = check_array(ctx, dst, "sb_array_copy"); if (r) return r;
+    r = check_array(ctx, src, "sb_array_copy"); if (r) return r;
+    Array& ad = ctx->arrays[dst]; Array& as = ctx->arrays[src];
+    if (n_rows < 0 || ad.stride != as.stride || n_rows > as.n_rows) return fail(ctx, SB_ERR_ARG, "sb_array_copy: shapes do not match");
+    order_after_async_downloads(ctx);
+    ad.d.ensure((size_t)std::max(n_rows, 1) * ad.stride);
+    ad.n_rows = n_rows;
+    ctx->state_version++;
+    if (n_rows > 0) SB_CUDA(ctx, cudaMemcpyAsync(ad.d.p, as.d.p, sizeof(double) * (size_t)n_rows * ad.stride, cudaMemcpyDeviceToDevice, ctx->stream));
+    return SB_OK;
+}
+// Asynchronous read-back into a REGISTERED (sb_host_register) host buffer: ordered after everything submitted so far, runs on
+// the library's copy stream beside whatever is submitted next, and is complete after sb_download_wait (or any synchronising
+// download).  Later calls that write arrays are ordered behind it on the device.
+int sb_array_download_async(sb_context* ctx, int array, double* host, int n_rows)
+{
+    int r = check_array(ctx, array, "sb_array_download_async"); if (r) return r;
+    Array& a = ctx->arrays[array];
+    if (n_rows < 0 || n_rows > a.n_rows || (n_rows > 0 && !host)) return fail(ctx, SB_ERR_ARG, "sb_array_download_async: bad argument");
+    bool ours = false;
+    for (auto& rg : ctx->host_regions) if ((const char*)host >= (const char*)rg.first && (const char*)host + sizeof(double) * (size_t)n_rows * a.stride <= (const char*)rg.first + rg.second) ours = true;
+    if (!ours) return fail(ctx, SB_ERR_ARG, "sb_array_download_async: the host buffer is not registered (sb_host_register)");
+    if (n_rows == 0) return SB_OK;
+    if (!ctx->copy_stream) {
+        SB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        SB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copy_src, cudaEventDisableTiming));
+        SB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copy_done, cudaEventDisableTiming));
+    }
+    SB_CUDA(ctx, cudaEventRecord(ctx->ev_copy_src, ctx->stream));
+    SB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy_src, 0));
+    SB_CUDA(ctx, cudaMemcpyAsync(host, a.d.p, sizeof(double) * (size_t)n_rows * a.stride, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    SB_CUDA(ctx, cudaEventRecord(ctx->ev_copy_done, ctx->copy_stream));
+    ctx->copy_dev_pending = true;
+    ctx->copy_host_pending = true;
+    return SB_OK;
+}
+int sb_download_wait(sb_context* ctx)
+{
+    if (!ctx) return SB_ERR_ARG;
+    if (ctx->copy_host_pending) { SB_CUDA(ctx, cudaEventSynchronize(ctx->ev_copy_done)); ctx->copy_host_pending = false; ctx->copy_dev_pending = false; }
     return SB_OK;
 }
 int sb_host_register(sb_context* ctx, void* host, uint64_t bytes)
@@ -564,6 +892,7 @@ int sb_dofs_get(sb_context* ctx, double* host_u)
 int sb_dofs_set(sb_context* ctx, const double* host_u)
 {
     if (!ctx || !host_u) return fail(ctx, SB_ERR_ARG, "sb_dofs_set: bad argument");
+    order_after_async_downloads(ctx);
     ctx->state_version++;
     recompute_dof_offsets(ctx);
     for (auto& s : ctx->dof_sets) {
@@ -775,6 +1104,7 @@ int sb_dofs_apply_step(sb_context* ctx, double step)
 {
     if (!ctx) return SB_ERR_ARG;
     if (!ctx->du.p || !ctx->dofs_saved.p) return fail(ctx, SB_ERR_STATE, "sb_dofs_apply_step: no saved DoFs / direction");
+    order_after_async_downloads(ctx);
     ctx->state_version++;
     for (auto& s : ctx->dof_sets) {
         Array& a = ctx->arrays[s.array];

@@ -1,6 +1,11 @@
 // Internal state of a stark_b200 context (not part of the C-ABI).
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <cstdint>
 #include <cstdio>
 #include <string>
@@ -61,7 +66,7 @@ void preload_eval_kernels();
 void preload_project_kernels();
 void projector_prepare(sb_context* ctx);
 void preload_assembly_kernels();
-void assembly_prefetch_symbolic(sb_context* ctx);   // assembly.cu: symbolic phase ahead of time on a side stream
+void assembly_prefetch_symbolic(sb_context* ctx, unsigned side_mask);   // assembly.cu: symbolic phase ahead of time, issued by the helper thread behind ev_dyn[k] of the side streams in the mask
 void assembly_prefetch_drain(sb_context* ctx);
 const std::vector<KernelInfo>& all_kernels();
 
@@ -139,6 +144,30 @@ struct StageTimer {
     ~StageTimer();
 };
 
+bool timeline_enabled();
+void timeline_mark(sb_context* ctx, int stage);
+void timeline_point(cudaStream_t st, const char* label);
+void timeline_dump(sb_context* ctx, const char* const* names);
+const char* const* stage_names();
+
+// A helper host thread per context: issues an independent chain of launches (the symbolic phase of the assembly: ~20 small
+// kernels on its own stream) while the calling thread keeps issuing the evaluation.  A Newton iteration at the 200k-tet scene
+// is bound by the HOST's launch rate, not by the kernels; two issuing threads halve that.  One job at a time; wait() is the
+// host-side join (the job's launches are then all enqueued; device-side ordering is by events as usual).
+struct Issuer {
+    std::thread th;
+    std::mutex m;
+    std::condition_variable cv;
+    std::function<void()> job;
+    std::atomic<int> state{0};   // 0 idle, 1 job posted / running
+    bool quit = false;
+    int device = 0;
+    void start(int dev);
+    void post(std::function<void()> f);
+    void wait() { while (state.load(std::memory_order_acquire) != 0) { /* the job is a few tens of microseconds of launches */ } }
+    void stop();
+};
+
 struct Assembly;   // assembly.cu
 struct Pcg;        // pcg.cu
 struct Contact;    // contact.cu
@@ -156,8 +185,15 @@ struct sb_context {
     cudaStream_t side[N_SIDE] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[N_SIDE] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;   // sb_newton_solve's timing events
+    cudaStream_t sym_stream = nullptr;              // the helper thread's stream (symbolic phase of the assembly)
+    cudaEvent_t ev_dyn[N_SIDE] = {nullptr, nullptr, nullptr, nullptr};   // "the dynamic potentials' kernels on this side stream are done"
+    sb::Issuer* issuer = nullptr;
+    // sb_array_download_async
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copy_src = nullptr, ev_copy_done = nullptr;
+    bool copy_dev_pending = false, copy_host_pending = false;
     std::string error;
-    int64_t launches = 0;
+    std::atomic<int64_t> launches{0};   // (kernels are also issued by the helper thread)
 
     std::vector<std::pair<void*, size_t>> host_regions;   // sb_host_register: pinned mirrors
     std::vector<sb::Array> arrays;
@@ -187,6 +223,12 @@ struct sb_context {
     bool pgh_cache_ok = false;
     uint64_t pgh_state = 0, pgh_dynamic = 0, pgh_static = 0;
     double pgh_E = 0.0, pgh_residual = 0.0;
+    // first half of a P+G+H evaluation (the static potentials) launched ahead of the collision detection (eval_prelaunch_static)
+    bool pre_valid = false;
+    uint64_t pre_state = 0, pre_static = 0;
+    size_t st_H = 0, st_rows = 0, st_E = 0, st_blocks = 0;   // totals of the static potentials in the element-output buffers
+    unsigned st_side_mask = 0;
+    int st_next_side = 0;
 
     bool profile = false;           // stage profiling on (adds a stream synchronisation at every stage boundary)
     double stage_ms[32] = {0};
@@ -205,6 +247,7 @@ struct sb_context {
 
 namespace sb {
 int fail(sb_context* ctx, int code, const std::string& msg);
+void order_after_async_downloads(sb_context* ctx);
 int check_cuda(sb_context* ctx, cudaError_t e, const char* what);
 #define SB_CUDA(ctx, call) do { int _r = sb::check_cuda((ctx), (call), #call); if (_r) return _r; } while (0)
 int recompute_dof_offsets(sb_context* ctx);
@@ -237,4 +280,5 @@ int contact_update_internal(sb_context* ctx);
 int contact_intersections_internal(sb_context* ctx, int* out_count);
 bool contact_active(sb_context* ctx);
 int eval_internal(sb_context* ctx, int mode, double* out_E, double* out_grad_inf, bool sync_scalars);
+int eval_prelaunch_static(sb_context* ctx);   // static potentials of the coming P+G+H evaluation, before the collision detection
 }  // namespace sb

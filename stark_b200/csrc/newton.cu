@@ -87,6 +87,11 @@ extern "C" int sb_newton_solve(sb_context* ctx, const sb_newton_settings* S, sb_
     if (!ctx->ev_t0) { cudaEventCreate(&ctx->ev_t0); cudaEventCreate(&ctx->ev_t1); }
     cudaEvent_t ev0 = ctx->ev_t0, ev1 = ctx->ev_t1;
     cudaEventRecord(ev0, ctx->stream);
+    timeline_mark(ctx, -1);
+    static const bool no_spec = std::getenv("SB_NO_SPECULATION") != nullptr;   // diagnostic hook
+    // the static potentials of the first evaluation do not depend on the contact tables: their kernels are launched before the
+    // collision detection of the initial state (eval_internal picks them up)
+    if (!no_spec && (rc = eval_prelaunch_static(ctx))) return rc;
     bool valid = true;
     if ((rc = state_valid(valid))) return rc;
     if (!valid) result = InvalidInitialState;
@@ -203,6 +208,9 @@ extern "C" int sb_newton_solve(sb_context* ctx, const sb_newton_settings* S, sb_
         // [max] no max_allowed_step callback is registered by STARK
         double step = 1.0;
         if ((rc = sb_dofs_apply_step(ctx, step))) return rc;
+        // The first Armijo trial is evaluated with gradient and Hessians (below); the volume elements of that evaluation do not
+        // depend on the contact tables, so their kernels go out now, ahead of the trial state's collision detection.
+        if (S->enable_armijo_backtracking && !no_spec && (rc = eval_prelaunch_static(ctx))) return rc;
         int ls_inv = 0;
         for (; ls_inv < S->max_backtracking_invalid_state_iterations; ++ls_inv) {
             if ((rc = state_valid(valid))) return rc;
@@ -222,7 +230,6 @@ extern "C" int sb_newton_solve(sb_context* ctx, const sb_newton_settings* S, sb_
                 // The first trial is almost always accepted, and the next iteration then evaluates energy, gradient and
                 // Hessians at this very state: evaluate them now (eval_internal hands the result out again) instead of the
                 // energy alone.  Later trials (after a backtrack) are energy-only.
-                static const bool no_spec = std::getenv("SB_NO_SPECULATION") != nullptr;   // diagnostic hook
                 if (k == 0 && !no_spec) { double res_unused = 0.0; if ((rc = eval_internal(ctx, SB_EVAL_PGH, &E1, &res_unused, true))) return rc; }
                 else if ((rc = eval_internal(ctx, SB_EVAL_P, &E1, nullptr, true))) return rc;
                 if (E1 < E_threshold) break;
@@ -246,5 +253,8 @@ extern "C" int sb_newton_solve(sb_context* ctx, const sb_newton_settings* S, sb_
     cudaEventElapsedTime(&ms, ev0, ev1);
     stats->gpu_ms = ms;
     stats->newton_iterations = it;
+    timeline_mark(ctx, -1);
+    static const char* tl = std::getenv("SB_TIMELINE");   // "1": every solve, "N": only solves with at least N iterations
+    if (tl && it >= std::atoi(tl)) timeline_dump(ctx, stage_names()); else if (tl) timeline_dump(ctx, nullptr);
     return SB_OK;
 }

@@ -163,10 +163,13 @@ __attribute__((visibility("default"))) void sbh_scene_totals(void* h, double* ou
     out[3] = (double)sim.h2d_bytes; out[4] = (double)sim.d2h_bytes; out[5] = (double)sb_launch_count(sim.context());
     out[6] = (double)sim.total_newton_iterations; out[7] = sim.total_solve_s;
 }
+// wait for the asynchronous read-backs of the last step (the host mirrors of x0 / v0 are then current)
+__attribute__((visibility("default"))) void sbh_scene_sync(void* h) { static_cast<Scene*>(h)->sim->sync_host(); }
 __attribute__((visibility("default"))) int sbh_scene_positions(void* h, double* x0, int n_nodes)
 {
     Simulation& sim = *static_cast<Scene*>(h)->sim;
     if (n_nodes != sim.dyn.size()) return -1;
+    sim.sync_host();
     std::memcpy(x0, sim.dyn.x0.data.data(), sizeof(double) * 3 * (size_t)n_nodes);
     return 0;
 }
@@ -182,6 +185,7 @@ __attribute__((visibility("default"))) int sbh_scene_potential(void* h, const ch
 // host copy of a bound array by its label (e.g. "shells.rest_angle"); returns the number of doubles, -1 if unknown
 __attribute__((visibility("default"))) int sbh_scene_array(void* h, const char* label, double* out, int cap)
 {
+    static_cast<Scene*>(h)->sim->sync_host();
     const DeviceArray* a = static_cast<Scene*>(h)->sim->find_array(label);
     if (!a) return -1;
     const int n = (int)a->data.size();

@@ -171,10 +171,12 @@ int PointDynamics::add(const std::vector<Vec3>& x)
 void PointDynamics::add_displacement(int set, const Vec3& d)
 {   // PointSetHandler::add_displacement(..., also_at_rest_pose = true)
     for (int i = 0; i < get_set_size(set); i++) { const int g = get_global_index(set, i); set3(x0, g, get3(x0, g) + d); set3(X, g, get3(X, g) + d); }
+    x0.device_current = false;
 }
 void PointDynamics::set_velocity(int set, const Vec3& v)
 {
     for (int i = 0; i < get_set_size(set); i++) set3(v0, get_global_index(set, i), v);
+    v0.device_current = false;
 }
 
 int EnergyLumpedInertia::add(PointDynamics& dyn, int set, const std::vector<std::array<int, 4>>& tets, double rho, double damp)
@@ -458,7 +460,13 @@ Simulation::Simulation(const Settings& s) : settings(s)
     const int r = sb_create(&ctx, s.device, s.stream);
     if (r != SB_OK) die("sb_create failed (no CUDA device? this library has no CPU fallback), status " + std::to_string(r));
 }
-Simulation::~Simulation() { sb_destroy(ctx); }
+Simulation::~Simulation()
+{
+    if (std::getenv("SB_HOST_DUMP") && phase_steps > 0)
+        std::fprintf(stderr, "[stark_b200 host] %lld steps: pre %.3f ms, solve %.3f ms, post %.3f ms, roll %.3f ms per step\n", phase_steps,
+                     1e3 * phase_s[0] / phase_steps, 1e3 * phase_s[1] / phase_steps, 1e3 * phase_s[2] / phase_steps, 1e3 * phase_s[3] / phase_steps);
+    sb_destroy(ctx);
+}
 
 void Simulation::check(int status, const char* what)
 {
@@ -473,6 +481,7 @@ void Simulation::reg(DeviceArray& a, const char* label, int stride)
 }
 void Simulation::upload(DeviceArray& a)
 {
+    if (a.device_current) return;   // rolled on the device: nothing to send
     if (!a.volatile_data) {
         if (a.has_shadow && a.shadow == a.data) return;   // the device already holds these values
         a.shadow = a.data;
@@ -480,6 +489,8 @@ void Simulation::upload(DeviceArray& a)
     }
     check(sb_array_upload(ctx, a.id, a.data.data(), a.rows()), "sb_array_upload");
     h2d_bytes += (long long)a.data.size() * 8;
+    // per-node accelerations / forces have no setter after initialisation in this layer: one upload, no 0.9 MB compare per step
+    if (&a == &dyn.a || &a == &dyn.f) a.device_current = true;
 }
 void Simulation::pin(DeviceArray& a)
 {   // large per-step arrays become pinned mirrors: their uploads are asynchronous DMA without a staging copy
@@ -491,6 +502,12 @@ void Simulation::download(DeviceArray& a)
 {
     check(sb_array_download(ctx, a.id, a.data.data(), a.rows()), "sb_array_download");
     d2h_bytes += (long long)a.data.size() * 8;
+}
+void Simulation::sync_host()
+{
+    if (!host_mirror_pending) return;
+    check(sb_download_wait(ctx), "sb_download_wait");
+    host_mirror_pending = false;
 }
 int Simulation::ndofs()
 {
@@ -744,7 +761,9 @@ bool Simulation::run_one_time_step()
     dt_arr.data[0] = dt;
     gravity_arr.data = {gravity[0], gravity[1], gravity[2]};
     check(sb_array_fill(ctx, dyn.v1.id, dyn.v1.rows(), 0.0), "sb_array_fill");   // v1 <- 0 on the device (no transfer)
-    for (DeviceArray* a : {&dyn.x0, &dyn.v0, &dyn.a, &dyn.f, &rb.v1, &rb.w1, &rb.t0, &rb.q0_, &rb.v0, &rb.w0, &rb.a, &rb.aa, &rb.force, &rb.torque, &dt_arr, &gravity_arr,
+    check(sb_array_fill(ctx, rb.v1.id, rb.v1.rows(), 0.0), "sb_array_fill");
+    check(sb_array_fill(ctx, rb.w1.id, rb.w1.rows(), 0.0), "sb_array_fill");
+    for (DeviceArray* a : {&dyn.x0, &dyn.v0, &dyn.a, &dyn.f, &rb.t0, &rb.q0_, &rb.v0, &rb.w0, &rb.a, &rb.aa, &rb.force, &rb.torque, &dt_arr, &gravity_arr,
                            &rb_inertia.J0_glob, &prescribed_positions.target_positions, &prescribed_positions.stiffness, &rb_constraints.global_points.target_glob,
                            &rb_constraints.global_points.stiffness, &rb_constraints.global_directions.target_d_glob, &rb_constraints.global_directions.stiffness,
                            &rb_constraints.global_directions.d_loc,   // (scripted fix constraints rotate the LOCAL lock directions)
@@ -753,7 +772,9 @@ bool Simulation::run_one_time_step()
     if (settings.newton.contact_enabled) {
         check(sb_contact_set_params(ctx, contact.contact_stiffness, contact.global_params.friction_stick_slide_threshold, contact.global_params.triangle_point_enabled,
                                     contact.global_params.edge_edge_enabled, contact.global_params.friction_enabled), "sb_contact_set_params");
-        check(sb_contact_update_friction(ctx), "sb_contact_update_friction");                 // EnergyFrictionalContact.cpp:531-773
+        // friction tables (EnergyFrictionalContact.cpp:531-773); v1 / w1 are zero here, so the same detection also serves the
+        // solve's initial validity test and first contact update
+        check(sb_contact_begin_time_step(ctx, 1), "sb_contact_begin_time_step");
     }
 
     // ---- Newton solve on the device ----
@@ -763,12 +784,17 @@ bool Simulation::run_one_time_step()
     sb_newton_stats st;
     const auto t_solve = clk::now();
     check(sb_newton_solve(ctx, &ns, &st), "sb_newton_solve");
-    download(dyn.v1); download(rb.v1); download(rb.w1);
+    const auto t_solved = clk::now();
+    // the rigid bodies (a handful) are rolled on the host; the deformable state stays on the device unless a converged-state
+    // callback needs it here (prescribed positions with a finite tolerance)
+    download(rb.v1); download(rb.w1);
+    const bool need_v1 = prescribed_positions.checks_tolerance();
+    if (need_v1) { sync_host(); download(dyn.v1); }
     int result = st.result;
     if (result == 0) {
         // is_converged_state_valid callbacks, short-circuiting like SolverCallbacks::_run_bool (solver_utils.h:55-62):
         // prescribed positions -> rigid body constraints -> contact
-        bool valid = prescribed_positions.is_converged_state_valid(dyn, dt);
+        bool valid = !need_v1 || prescribed_positions.is_converged_state_valid(dyn, dt);
         valid = valid && rb_constraints.adjust_stiffness(rb, dt, 1.0, rb_constraints.stiffness_hard_multiplier, false);
         if (valid && settings.newton.contact_enabled && contact.global_params.intersection_test_enabled) {
             int n = 0;
@@ -788,10 +814,22 @@ bool Simulation::run_one_time_step()
     total_newton_iterations += st.newton_iterations; total_evaluations += st.n_evaluations; total_cg_iterations += st.cg_iterations;
     total_solve_s += stats.solve_s;
 
+    const auto t_post = clk::now();
     bool keep_going = true;
     if (result == 0) {
         // ---- on_time_step_accepted (S/core/Stark.cpp:161-170) ----
-        for (int i = 0; i < dyn.size(); i++) { set3(dyn.x0, i, get3(dyn.x0, i) + dt * get3(dyn.v1, i)); set3(dyn.v0, i, get3(dyn.v1, i)); }
+        // PointDynamics.cpp:64-78 on the device: x0 += dt v1, v0 = v1; the host mirrors follow asynchronously (the copy runs under
+        // the next step's solve; sync_host() before any host access)
+        if (dyn.size() > 0) {
+            sync_host();   // (a previous read-back still writing the mirrors)
+            check(sb_array_axpy(ctx, dyn.x0.id, dyn.v1.id, dt, dyn.size()), "sb_array_axpy");
+            check(sb_array_copy(ctx, dyn.v0.id, dyn.v1.id, dyn.size()), "sb_array_copy");
+            dyn.x0.device_current = dyn.v0.device_current = true;
+            check(sb_array_download_async(ctx, dyn.x0.id, dyn.x0.data.data(), dyn.size()), "sb_array_download_async");
+            check(sb_array_download_async(ctx, dyn.v0.id, dyn.v0.data.data(), dyn.size()), "sb_array_download_async");
+            d2h_bytes += 2ll * (long long)dyn.x0.data.size() * 8;
+            host_mirror_pending = true;
+        }
         for (int b = 0; b < rb.get_n_bodies(); b++) {                                          // RigidBodyDynamics.cpp:149-166
             set3(rb.t0, b, get3(rb.t0, b) + dt * get3(rb.v1, b));
             rb.q0[b] = quat_time_integration(rb.q0[b], get3(rb.w1, b), dt);
@@ -813,7 +851,15 @@ bool Simulation::run_one_time_step()
             if (dt < settings.simulation.time_step_size_lower_bound) keep_going = false;
         }
     }
-    stats.runtime_s = std::chrono::duration<double>(clk::now() - t_begin).count();
+    const auto t_end = clk::now();
+    phase_s[0] += std::chrono::duration<double>(t_solve - t_begin).count(); phase_s[1] += std::chrono::duration<double>(t_solved - t_solve).count();
+    phase_s[2] += std::chrono::duration<double>(t_post - t_solved).count(); phase_s[3] += std::chrono::duration<double>(t_end - t_post).count();
+    phase_steps++;
+    static const char* hd = std::getenv("SB_HOST_DUMP");
+    if (hd && hd[0] == '2')
+        std::fprintf(stderr, "[stark_b200 host] step %d: pre %.3f solve %.3f (gpu %.3f) post %.3f roll %.3f ms, %d its\n", current_time_step, 1e3 * std::chrono::duration<double>(t_solve - t_begin).count(),
+                     1e3 * std::chrono::duration<double>(t_solved - t_solve).count(), st.gpu_ms, 1e3 * std::chrono::duration<double>(t_post - t_solved).count(), 1e3 * std::chrono::duration<double>(t_end - t_post).count(), st.newton_iterations);
+    stats.runtime_s = std::chrono::duration<double>(t_end - t_begin).count();
     return keep_going;
 }
 

@@ -50,6 +50,7 @@ struct DeviceArray {
     bool has_shadow = false;
     bool volatile_data = false;   // rewritten every step: no shadow bookkeeping, always uploaded
     bool pinned = false;          // registered as a pinned mirror (asynchronous uploads)
+    bool device_current = false;  // the device copy is the truth (rolled there at the end of a step); the host mirror follows asynchronously
     int stride = 1;
     int id = -1;
     std::string label;
@@ -134,6 +135,8 @@ public:
     std::vector<std::array<int, 2>> group_begin_end;
     int potential = -1;
     int add_inside_aabb(PointDynamics& dyn, int set, const Vec3& center, const Vec3& dim, double stiffness, double tolerance);
+    // does is_converged_state_valid have anything to test? (the default tolerance is infinite, S/models/types.h:56-57)
+    bool checks_tolerance() const { if (conn.empty()) return false; for (double t : tolerance) if (t < 1e300) return true; return false; }
     void set_transformation(int group, const Vec3& t, double angle_deg, const Vec3& axis);
     bool is_converged_state_valid(const PointDynamics& dyn, double dt);
 };
@@ -247,6 +250,10 @@ public:
     // totals over all steps taken so far
     long long total_newton_iterations = 0, total_evaluations = 0, total_cg_iterations = 0, h2d_bytes = 0, d2h_bytes = 0;
     double total_solve_s = 0.0;
+    bool host_mirror_pending = false;   // asynchronous read-backs of x0 / v0 in flight (sync_host waits for them)
+    void sync_host();
+    double phase_s[4] = {0, 0, 0, 0};   // host wall time: before the solve, sb_newton_solve, converged-state callbacks + downloads, state roll (SB_HOST_DUMP=1 prints them)
+    long long phase_steps = 0;
 
 private:
     sb_context* ctx = nullptr;

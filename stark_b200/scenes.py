@@ -28,6 +28,7 @@ def load():
         h.sbh_scene_potential.argtypes = [C.c_void_p, C.c_char_p]
         h.sbh_scene_array.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.c_int]
         h.sbh_scene_connectivity.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int32), C.c_int]
+        h.sbh_scene_sync.argtypes = [C.c_void_p]
         h.sbh_scene_context.restype = C.c_void_p
         h.sbh_scene_context.argtypes = [C.c_void_p]
         _host = h
@@ -54,6 +55,10 @@ class Scene:
         out = (C.c_double * 16)()
         self.lib.sbh_scene_step(self.h, out)
         return dict(zip(STEP_FIELDS, list(out)))
+
+    def sync(self):
+        """Wait for the asynchronous read-backs of the last step: the host mirrors of positions / velocities are then current."""
+        self.lib.sbh_scene_sync(self.h)
 
     def residuals(self):
         buf = (C.c_double * 64)()

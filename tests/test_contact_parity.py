@@ -103,7 +103,15 @@ def test_contact_tables_and_global_evaluation(fixture):
             continue
         out = ctx.element_output(ctx.contact_potential(p["name"]))
         ref = g[f"pot{i}_sol"]
-        o, ro = np.argsort(out[:, 0]), np.argsort(ref[:, 0])
         scale = np.abs(ref).max()
-        assert np.abs(out[o] - ref[ro]).max() <= 1e-8 * scale, p["name"]
+        # (rows are matched one to one by nearest row, not by sorting on the energy: symmetric pairs -- the same two vertices
+        #  found from both sides -- have equal energies and mirrored gradients)
+        assert out.shape == ref.shape, p["name"]
+        used = np.zeros(len(out), dtype=bool)
+        for r in ref:
+            dist = np.abs(out - r).max(axis=1)
+            dist[used] = np.inf
+            j = int(np.argmin(dist))
+            assert dist[j] <= 1e-8 * scale, (p["name"], dist[j] / scale)
+            used[j] = True
     ctx.close()

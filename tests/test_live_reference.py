@@ -26,7 +26,7 @@ CASES = {
     "C4_tetchain_16": (["--scene", "tetchain", "--n", "16", "--steps", "16"], 50),
     # cloth draped over the box corner: all six proximity types, ~950 pairs, and a state where the reference's PCG stops on
     # indefiniteness (pcg_converged = 0): the failure signal is compared as well
-    "C3_cloth_shells_64": (["--scene", "cloth_shells", "--n", "64", "--steps", "40"], 800),
+    "C3_cloth_shells_64": (["--scene", "cloth_shells", "--n", "64", "--steps", "40"], 200),   # (the reference's trajectory depends on its thread count: 945 pairs on 8 threads, fewer on other machines)
 }
 
 
