@@ -132,10 +132,19 @@ class Context:
             raise SBError(f"sb_create failed with status {r}: no usable CUDA device (this library has no CPU fallback)")
         self.h = h
 
+    @classmethod
+    def borrow(cls, handle):
+        """Wrap an sb_context owned by someone else (e.g. a host-layer scene): close() does not destroy it."""
+        self = cls.__new__(cls)
+        self.lib = load()
+        self.h = C.c_void_p(handle)
+        self._borrowed = True
+        return self
+
     def close(self):
-        if self.h:
+        if self.h and not getattr(self, "_borrowed", False):
             self.lib.sb_destroy(self.h)
-            self.h = None
+        self.h = None
 
     def __del__(self):
         try:

@@ -84,6 +84,24 @@ struct Assembly {
     size_t pf_n_src = 0;
     bool pf_failed = false;
     cudaEvent_t ev_sym = nullptr;
+    // SCATTER MODE.  When the contact tables change but every block their elements touch already exists in the pattern (contact
+    // that persists: pairs come and go inside the same neighbourhoods), nothing is sorted or merged: a kernel behind the
+    // dynamic potentials looks every dynamic source's block up in the current BCSR rows (k_dyn_locate_src, one binary search
+    // in a row), and the numeric phase adds the dynamic contributions through a small FP64 hash table keyed by the BCSR
+    // block (k_scatter_dynamic) which the segmented reduction then picks up.  Blocks of pairs that are gone stay in the
+    // pattern as explicit zeros until the next sort-based rebuild (sb_bcsr_get drops them: the reference drops zero blocks at
+    // end_insertion).  A source whose block is missing raises a flag that travels to the host with the evaluation's scalars,
+    // and the sort-based symbolic phase above runs as before.
+    bool scatter_mode = false;
+    DevBuf<uint32_t> d_final_of_src;   // per dynamic source: its BCSR block (both modes; the projection's dirty marking uses it)
+    DevBuf<uint8_t> has_dyn;           // per BCSR block: receives dynamic contributions in this numeric pass
+    DevBuf<int32_t> hkeys;             // hash table: BCSR block or -1
+    DevBuf<double> hacc;               // 9 FP64 accumulators per slot
+    size_t hcap = 0;                   // slots (power of two)
+    PotDesc* h_descs = nullptr;        // pinned staging of the dynamic potentials' descriptors
+    size_t loc_n = 0;                  // dynamic sources of the last k_dyn_locate_src
+    uint64_t loc_dynamic = 0;          // ... and the table version it looked at
+    long long n_scatter_hits = 0, n_scatter_misses = 0;
 };
 
 static Assembly* get(sb_context* ctx)
@@ -104,6 +122,9 @@ void assembly_destroy(sb_context* ctx)
     A->d_pos.release(); A->d_isnew.release(); A->d_newrank.release(); A->newpos.release(); A->s_final.release(); A->d_final.release();
     A->seg4.release(); A->blk_row.release(); A->rows.release(); A->cols.release(); A->vals.release(); A->temp.release();
     A->dirty.release(); A->long_blocks.release(); A->descs.release();
+    A->d_final_of_src.release(); A->has_dyn.release(); A->hkeys.release(); A->hacc.release();
+    if (A->h_descs) cudaFreeHost(A->h_descs);
+    if (std::getenv("SB_ASM_DUMP")) fprintf(stderr, "[stark_b200 assembly] contact-table changes absorbed without a symbolic phase: %lld, with a sort-based rebuild: %lld\n", A->n_scatter_hits, A->n_scatter_misses);
     if (A->d_counts) cudaFree(A->d_counts);
     if (A->h_counts) cudaFreeHost(A->h_counts);
     if (ctx->issuer) ctx->issuer->wait();
@@ -233,6 +254,80 @@ __global__ void k_dyn_final(const uint64_t* __restrict__ dkey, const uint32_t* _
     d_final[j] = f;
 }
 
+// sort-based build: per dynamic source, its BCSR block (the scatter mode's k_dyn_locate_src produces the same table)
+__global__ void k_src_final(const uint32_t* __restrict__ blk_of_src, const uint32_t* __restrict__ d_final, uint32_t* __restrict__ d_final_of_src, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) d_final_of_src[i] = d_final[blk_of_src[i]];
+}
+
+// Scatter mode, step 1 (behind the dynamic potentials' kernels of an evaluation): BCSR block of every dynamic source by a
+// binary search for its column inside its block row; a missing block raises *miss (a double: it rides with the evaluation's
+// scalars).  Also records where the source's 3x3 block lies in the element-Hessian store.
+__global__ void k_dyn_locate_src(const PotDesc* __restrict__ descs, int n_descs, size_t n_total, const int32_t* __restrict__ rows_all,
+                                 const unsigned long long* __restrict__ row_ptr, const int32_t* __restrict__ cols, int nbr,
+                                 uint32_t* __restrict__ d_final_of_src, uint32_t* __restrict__ src_off, uint8_t* __restrict__ src_pitch, double* __restrict__ miss)
+{
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_total) return;
+    int lo = 0, hi = n_descs - 1;   // last desc with blk_off <= g
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (descs[mid].blk_off <= g) lo = mid; else hi = mid - 1;
+    }
+    const PotDesc d = descs[lo];
+    const size_t t = g - d.blk_off;
+    const int nb2 = d.nb * d.nb;
+    const int e = (int)(t / nb2);
+    const int k = (int)(t - (size_t)e * nb2);
+    const int bi = k / d.nb, bj = k - bi * d.nb;
+    const int32_t* r = rows_all + d.rows_off + (size_t)e * d.nb;
+    const int n = 3 * d.nb;
+    src_off[g] = (uint32_t)(d.H_off + (size_t)e * n * n + (size_t)(3 * bi) * n + 3 * bj);
+    src_pitch[g] = (uint8_t)n;
+    const int row = r[bi], col = 3 * r[bj];
+    uint32_t f = 0xffffffffu;
+    if (row >= 0 && row < nbr) {
+        size_t a = row_ptr[row], b = row_ptr[row + 1];
+        while (a < b) {
+            const size_t mid = (a + b) >> 1;
+            if (cols[mid] < col) a = mid + 1; else b = mid;
+        }
+        if (a < row_ptr[row + 1] && cols[a] == col) f = (uint32_t)a;
+    }
+    d_final_of_src[g] = f;
+    if (f == 0xffffffffu) *miss = 1.0;
+}
+
+// Scatter mode, step 2 (numeric phase): every dynamic source adds its 3x3 block to the FP64 accumulators of its BCSR block in a
+// lock-free open-addressing table (9 threads per source).
+__device__ __forceinline__ uint32_t blk_hash(uint32_t f) { f *= 0x9E3779B1u; return f ^ (f >> 15); }
+__global__ void k_scatter_dynamic(const double* __restrict__ H, const uint32_t* __restrict__ d_final_of_src, const uint32_t* __restrict__ src_off,
+                                  const uint8_t* __restrict__ src_pitch, size_t n_src, int32_t* __restrict__ hkeys, double* __restrict__ hacc,
+                                  uint32_t hmask, uint8_t* __restrict__ has_dyn)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t g = t / 9;
+    if (g >= n_src) return;
+    const int k = (int)(t - g * 9);
+    const int r = k % 3, c = k / 3;
+    const uint32_t f = d_final_of_src[g];
+    uint32_t slot = blk_hash(f) & hmask;
+    while (true) {
+        const int32_t prev = atomicCAS(hkeys + slot, -1, (int32_t)f);
+        if (prev == -1 || prev == (int32_t)f) break;
+        slot = (slot + 1) & hmask;
+    }
+    if (k == 0) has_dyn[f] = 1;
+    atomicAdd(hacc + 9 * (size_t)slot + k, H[(size_t)src_off[g] + (size_t)r * src_pitch[g] + c]);
+}
+__device__ __forceinline__ double dyn_lookup(uint32_t f, int k, const int32_t* __restrict__ hkeys, const double* __restrict__ hacc, uint32_t hmask)
+{
+    uint32_t slot = blk_hash(f) & hmask;
+    while (hkeys[slot] != (int32_t)f) slot = (slot + 1) & hmask;   // (present: has_dyn[f] was set by the thread that inserted it)
+    return hacc[9 * (size_t)slot + k];
+}
+
 // rows[r] = first BCSR block whose block row is >= r (blocks are sorted by (row, col))
 __global__ void k_row_ptr(const int32_t* __restrict__ blk_row, unsigned long long* __restrict__ rows, int nbr, size_t nnzb)
 {
@@ -279,6 +374,9 @@ struct NumericArgs {
     uint8_t* dirty;
     const uint32_t* long_blocks; const int* n_long;
     size_t nnzb;
+    // scatter mode: the dynamic ranges of seg4 are stale; dynamic contributions come from the hash table
+    int scatter;
+    const uint8_t* has_dyn; const int32_t* hkeys; const double* hacc; uint32_t hmask;
 };
 
 // One CTA per long block: 32 strided partial sums per entry, then a fixed shared-memory tree (deterministic).
@@ -295,7 +393,8 @@ __global__ void __launch_bounds__(288) k_assemble_long(const NumericArgs a)
         const int4 g = a.seg4[b];
         double acc = 0.0;
         for (int s = g.x + lane; s < g.y; s += 32) acc += a.H[(size_t)a.s_off[s] + (size_t)r * a.s_pitch[s] + c];
-        for (int s = g.z + lane; s < g.w; s += 32) acc += a.H[(size_t)a.d_off[s] + (size_t)r * a.d_pitch[s] + c];
+        if (!a.scatter) { for (int s = g.z + lane; s < g.w; s += 32) acc += a.H[(size_t)a.d_off[s] + (size_t)r * a.d_pitch[s] + c]; }
+        else if (lane == 0 && a.has_dyn[b]) acc += dyn_lookup(b, k, a.hkeys, a.hacc, a.hmask);
         sm[lane][k] = acc;
         __syncthreads();
         for (int w = 16; w > 0; w >>= 1) {
@@ -331,7 +430,8 @@ __global__ void __launch_bounds__(288) k_assemble_numeric(const NumericArgs a)
         acc += v0; acc += v1; acc += v2; acc += v3;
     }
     for (; s < g.y; s++) acc += a.H[(size_t)a.s_off[s] + (size_t)r * a.s_pitch[s] + c];
-    for (s = g.z; s < g.w; s++) acc += a.H[(size_t)a.d_off[s] + (size_t)r * a.d_pitch[s] + c];
+    if (!a.scatter) { for (s = g.z; s < g.w; s++) acc += a.H[(size_t)a.d_off[s] + (size_t)r * a.d_pitch[s] + c]; }
+    else if (a.has_dyn[b]) acc += dyn_lookup((uint32_t)b, k, a.hkeys, a.hacc, a.hmask);
     a.vals[t] = (float)acc;
 }
 // the dirty flags are cleared by a separate pass (the nine threads of a block must all have seen the flag)
@@ -430,7 +530,9 @@ static int symbolic_phase_a(sb_context* ctx, Assembly* A, bool rebuild_static_in
     if (ndb > 0) {
         k_dyn_final<<<(unsigned)((ndb + 255) / 256), 256, 0, st>>>(A->D.blk_key.p, A->D.seg.p, ndb_dev, A->d_pos.p, A->d_isnew.p, A->d_newrank.p,
                                                                     A->s_final.p, A->d_final.p, A->seg4.p, A->blk_row.p, A->cols.p, A->key_shift);
-        ctx->launches++;
+        A->d_final_of_src.ensure(A->D.n + 1);
+        k_src_final<<<(unsigned)((A->D.n + 255) / 256), 256, 0, st>>>(A->D.blk_of_src.p, A->d_final.p, A->d_final_of_src.p, A->D.n);
+        ctx->launches += 2;
     }
     SB_CUDA(ctx, cudaMemcpyAsync(A->h_counts, A->d_counts, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
     return 0;
@@ -449,6 +551,7 @@ static int symbolic_phase_b(sb_context* ctx, Assembly* A)
     A->built_static = ctx->static_version;
     A->built_dynamic = ctx->dynamic_version;
     A->built_n_src = ctx->n_blocks_total;
+    A->scatter_mode = false;   // (seg4 carries this evaluation's dynamic source ranges)
     return 0;
 }
 static int build_symbolic(sb_context* ctx, Assembly* A, bool rebuild_static)
@@ -522,6 +625,62 @@ void assembly_prefetch_drain(sb_context* ctx)
     if (A && A->pf_pending) { ctx->issuer->wait(); cudaEventSynchronize(A->ev_sym); }
 }
 
+// Scatter mode, called by the P+G+H evaluation once the dynamic potentials' kernels are enqueued and joined into the context
+// stream: can the changed contact tables be absorbed by the current pattern?  Launches k_dyn_locate_src; its miss flag lands in
+// ctx->d_scalars[2] and travels to the host with the evaluation's scalars.  Returns true when the kernel was launched.
+bool assembly_locate_dynamic(sb_context* ctx)
+{
+    Assembly* A = ctx->assembly;
+    static const bool disabled = std::getenv("SB_NO_SCATTER") != nullptr;   // diagnostic hook
+    if (disabled || !A || !A->numeric_valid || A->pf_pending || ctx->n_blocks_total == 0) return false;
+    if (pattern_current(ctx, A) || static_part_stale(ctx, A)) return false;
+    if (A->nnzb == 0 || A->nnzb >= (1ull << 31)) return false;
+    {
+        int bits = 1;
+        while ((1ll << bits) < ctx->ndofs / 3 + 1) bits++;
+        if (bits != A->key_shift) return false;
+    }
+    // descriptors of the dynamic potentials (same numbering as the sort-based path: layout order, blk_off within the class)
+    if (!A->h_descs) cudaMallocHost(&A->h_descs, 128 * sizeof(PotDesc));
+    int nd = 0;
+    size_t blk_off = 0;
+    for (int pi : layout_order(ctx)) {
+        Potential& p = ctx->potentials[pi];
+        if (!p.dynamic || p.n_elem == 0) continue;
+        if (nd >= 128) return false;
+        PotDesc d;
+        d.H_off = p.H_off; d.rows_off = p.rows_off; d.blk_off = blk_off; d.n_elem = p.n_elem; d.nb = p.k->nb;
+        A->h_descs[nd++] = d;
+        blk_off += (size_t)p.n_elem * d.nb * d.nb;
+    }
+    const size_t n = blk_off;
+    cudaStream_t st = ctx->stream;
+    cudaMemsetAsync(ctx->d_scalars + 2, 0, sizeof(double), st);
+    A->loc_n = n;
+    A->loc_dynamic = ctx->dynamic_version;
+    if (n == 0) return true;   // no dynamic element left: the pattern trivially holds every block
+    if (ctx->H_total >= (1ull << 32)) return false;
+    A->descs.ensure(nd + 1);
+    A->D.src_off.ensure(n + 1); A->D.src_pitch.ensure(n + 1); A->d_final_of_src.ensure(n + 1);
+    cudaMemcpyAsync(A->descs.p, A->h_descs, nd * sizeof(PotDesc), cudaMemcpyHostToDevice, st);
+    k_dyn_locate_src<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(A->descs.p, nd, n, ctx->rows.p, A->rows.p, A->cols.p, A->nbr, A->d_final_of_src.p,
+                                                                   A->D.src_off.p, A->D.src_pitch.p, ctx->d_scalars + 2);
+    ctx->launches++;
+    return true;
+}
+// ... and the answer, once the evaluation's scalars are on the host
+void assembly_locate_result(sb_context* ctx, bool miss)
+{
+    Assembly* A = ctx->assembly;
+    if (!A || A->loc_dynamic != ctx->dynamic_version) return;
+    if (miss) { A->n_scatter_misses++; return; }   // (the sort-based symbolic phase runs at the next assembly)
+    A->n_scatter_hits++;
+    A->D.n = A->loc_n;
+    A->built_dynamic = ctx->dynamic_version;
+    A->built_n_src = ctx->n_blocks_total;
+    A->scatter_mode = true;
+}
+
 int assemble_internal(sb_context* ctx)
 {
     if (!ctx->have_pgh) return fail(ctx, SB_ERR_STATE, "sb_assemble: call sb_eval(SB_EVAL_PGH) first");
@@ -554,6 +713,26 @@ int assemble_internal(sb_context* ctx)
     NumericArgs a;
     a.H = ctx->H.p; a.seg4 = A->seg4.p; a.s_off = A->S.sorted_off.p; a.s_pitch = A->S.sorted_pitch.p; a.d_off = A->D.sorted_off.p; a.d_pitch = A->D.sorted_pitch.p;
     a.vals = A->vals.p; a.dirty = A->dirty.p; a.long_blocks = A->long_blocks.p; a.n_long = A->d_counts; a.nnzb = A->nnzb;
+    a.scatter = A->scatter_mode ? 1 : 0;
+    a.has_dyn = nullptr; a.hkeys = nullptr; a.hacc = nullptr; a.hmask = 0;
+    if (A->scatter_mode) {
+        // dynamic contributions of this pass: FP64 accumulators per touched BCSR block (all sources, every pass: a pass after a
+        // PD projection re-sums only dirty blocks, and those see the projected elements' new values)
+        const size_t n_src = A->D.n;
+        size_t cap = 1024;
+        while (cap < 2 * n_src) cap <<= 1;
+        A->hkeys.ensure(cap); A->hacc.ensure(9 * cap); A->has_dyn.ensure(A->nnzb + 1);
+        A->hcap = cap;
+        SB_CUDA(ctx, cudaMemsetAsync(A->has_dyn.p, 0, A->nnzb + 1, ctx->stream));
+        if (n_src > 0) {
+            SB_CUDA(ctx, cudaMemsetAsync(A->hkeys.p, 0xff, cap * sizeof(int32_t), ctx->stream));
+            SB_CUDA(ctx, cudaMemsetAsync(A->hacc.p, 0, 9 * cap * sizeof(double), ctx->stream));
+            k_scatter_dynamic<<<(unsigned)((9 * n_src + 287) / 288), 288, 0, ctx->stream>>>(ctx->H.p, A->d_final_of_src.p, A->D.src_off.p, A->D.src_pitch.p, n_src,
+                                                                                           A->hkeys.p, A->hacc.p, (uint32_t)(cap - 1), A->has_dyn.p);
+            ctx->launches++;
+        }
+        a.has_dyn = A->has_dyn.p; a.hkeys = A->hkeys.p; a.hacc = A->hacc.p; a.hmask = (uint32_t)(cap - 1);
+    }
     const size_t nt = 9 * A->nnzb;
     const unsigned grid = (unsigned)((nt + 287) / 288);
     // the few long blocks (a rigid body's diagonal: thousands of sources, one CTA each, latency-bound) are summed on a side
@@ -586,7 +765,7 @@ bool assembly_dirty_view(sb_context* ctx, DirtyView* v)
     if (!A || !pattern_current(ctx, A)) return false;
     v->n_static = (unsigned long long)A->S.n;
     v->s_blk_of_src = A->S.blk_of_src.p; v->s_final = A->s_final.p;
-    v->d_blk_of_src = A->D.blk_of_src.p; v->d_final = A->d_final.p;
+    v->d_final_of_src = A->d_final_of_src.p;
     v->dirty = A->dirty.p;
     return true;
 }
@@ -612,13 +791,36 @@ int sb_assemble(sb_context* ctx)
     return assemble_internal(ctx);
 }
 
+// Scatter mode keeps the blocks of contact pairs that are gone as explicit zeros until the next sort-based rebuild; the
+// reference drops zero blocks at end_insertion (BlockedSparseMatrix.h:782-895), so the matrix handed out is compacted: blocks
+// without a static source that received no dynamic contribution in the last numeric pass are left out.
+static int bcsr_kept_blocks(sb_context* ctx, Assembly* A, std::vector<uint32_t>& keep)
+{
+    keep.clear();
+    if (!A->scatter_mode) return 0;
+    std::vector<int4> seg(A->nnzb);
+    std::vector<uint8_t> dyn(A->nnzb);
+    SB_CUDA(ctx, cudaMemcpyAsync(seg.data(), A->seg4.p, sizeof(int4) * A->nnzb, cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(ctx, cudaMemcpyAsync(dyn.data(), A->has_dyn.p, A->nnzb, cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (size_t b = 0; b < A->nnzb; b++) if (seg[b].y > seg[b].x || dyn[b]) keep.push_back((uint32_t)b);
+    return 0;
+}
+
 int sb_bcsr_info(sb_context* ctx, int* n_block_rows, int64_t* nnzb)
 {
     if (!ctx) return SB_ERR_ARG;
     Assembly* A = ctx->assembly;
     if (!A || !A->numeric_valid) return fail(ctx, SB_ERR_STATE, "sb_bcsr_info: call sb_assemble first");
     if (n_block_rows) *n_block_rows = A->nbr;
-    if (nnzb) *nnzb = (int64_t)A->nnzb;
+    if (nnzb) {
+        *nnzb = (int64_t)A->nnzb;
+        if (A->scatter_mode) {
+            std::vector<uint32_t> keep;
+            int r = bcsr_kept_blocks(ctx, A, keep); if (r) return r;
+            *nnzb = (int64_t)keep.size();
+        }
+    }
     return SB_OK;
 }
 
@@ -627,10 +829,33 @@ int sb_bcsr_get(sb_context* ctx, int64_t* host_rows, int32_t* host_cols, float* 
     if (!ctx) return SB_ERR_ARG;
     Assembly* A = ctx->assembly;
     if (!A || !A->numeric_valid) return fail(ctx, SB_ERR_STATE, "sb_bcsr_get: call sb_assemble first");
-    if (host_rows) SB_CUDA(ctx, cudaMemcpyAsync(host_rows, A->rows.p, sizeof(int64_t) * (A->nbr + 1), cudaMemcpyDeviceToHost, ctx->stream));
-    if (host_cols) SB_CUDA(ctx, cudaMemcpyAsync(host_cols, A->cols.p, sizeof(int32_t) * A->nnzb, cudaMemcpyDeviceToHost, ctx->stream));
-    if (host_vals) SB_CUDA(ctx, cudaMemcpyAsync(host_vals, A->vals.p, sizeof(float) * 9 * A->nnzb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!A->scatter_mode) {
+        if (host_rows) SB_CUDA(ctx, cudaMemcpyAsync(host_rows, A->rows.p, sizeof(int64_t) * (A->nbr + 1), cudaMemcpyDeviceToHost, ctx->stream));
+        if (host_cols) SB_CUDA(ctx, cudaMemcpyAsync(host_cols, A->cols.p, sizeof(int32_t) * A->nnzb, cudaMemcpyDeviceToHost, ctx->stream));
+        if (host_vals) SB_CUDA(ctx, cudaMemcpyAsync(host_vals, A->vals.p, sizeof(float) * 9 * A->nnzb, cudaMemcpyDeviceToHost, ctx->stream));
+        SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return SB_OK;
+    }
+    std::vector<uint32_t> keep;
+    int r = bcsr_kept_blocks(ctx, A, keep); if (r) return r;
+    std::vector<int64_t> rows(A->nbr + 1);
+    std::vector<int32_t> cols(A->nnzb);
+    std::vector<float> vals(9 * A->nnzb);
+    SB_CUDA(ctx, cudaMemcpyAsync(rows.data(), A->rows.p, sizeof(int64_t) * (A->nbr + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(ctx, cudaMemcpyAsync(cols.data(), A->cols.p, sizeof(int32_t) * A->nnzb, cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(ctx, cudaMemcpyAsync(vals.data(), A->vals.p, sizeof(float) * 9 * A->nnzb, cudaMemcpyDeviceToHost, ctx->stream));
     SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    size_t k = 0;
+    int row = 0;
+    if (host_rows) host_rows[0] = 0;
+    for (size_t i = 0; i < keep.size(); i++) {
+        const uint32_t b = keep[i];
+        while (row < A->nbr && (int64_t)b >= rows[row + 1]) { row++; if (host_rows) host_rows[row] = (int64_t)k; }
+        if (host_cols) host_cols[k] = cols[b];
+        if (host_vals) for (int c = 0; c < 9; c++) host_vals[9 * k + c] = vals[9 * (size_t)b + c];
+        k++;
+    }
+    while (row < A->nbr) { row++; if (host_rows) host_rows[row] = (int64_t)k; }
     return SB_OK;
 }
 

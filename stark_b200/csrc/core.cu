@@ -494,12 +494,16 @@ int eval_internal(sb_context* ctx, int mode, double* out_E, double* out_grad_inf
             }
         SB_CUDA(ctx, cudaGetLastError());
         timeline_point(ctx->stream, "eval: joined");
+        // changed contact tables: do all their blocks exist in the assembled pattern?  (answer rides with the scalars below)
+        const bool located = sync_scalars && assembly_locate_dynamic(ctx);
         reduce_sum_and_absmax(ctx, ctx->E_elem.p, E_total, ctx->grad.p, ctx->ndofs, ctx->d_scalars);
         timeline_point(ctx->stream, "eval: reduced");
         ctx->have_pgh = true;
-        if (sync_scalars) SB_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (sync_scalars) SB_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->locate_pending = located;
         // issued LAST: the ~20 launches of the symbolic phase take the host a while, and the reductions must already be queued
-        if (prefetch) assembly_prefetch_symbolic(ctx, dyn_mask);
+        // (not when the scatter-mode lookup is under way: the symbolic phase is only needed if that reports a missing block)
+        if (prefetch && !located) assembly_prefetch_symbolic(ctx, dyn_mask);
     } else {
         // ---- energy only (line-search trials after a backtrack) ----
         recompute_dof_offsets(ctx);
@@ -566,6 +570,7 @@ int eval_internal(sb_context* ctx, int mode, double* out_E, double* out_grad_inf
         if (eval_dump) fprintf(stderr, "EVALDUMP mode=%d static=%.1f issue=%.1f prefetch=%.1f sync=%.1f us\n", mode, 1e3 * (td1 - td0), 1e3 * (td2 - td1), 1e3 * (td3 - td2), 1e3 * (now_ms() - td3));
         if (out_E) *out_E = ctx->h_scalars[0];
         if (out_grad_inf && mode == SB_EVAL_PGH) *out_grad_inf = ctx->h_scalars[1];
+        if (mode == SB_EVAL_PGH && ctx->locate_pending) { assembly_locate_result(ctx, ctx->h_scalars[2] != 0.0); ctx->locate_pending = false; }
         if (mode == SB_EVAL_PGH) {
             ctx->pgh_cache_ok = true;
             ctx->pgh_state = ctx->state_version; ctx->pgh_dynamic = ctx->dynamic_version; ctx->pgh_static = ctx->static_version;

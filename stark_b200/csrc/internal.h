@@ -68,6 +68,8 @@ void projector_prepare(sb_context* ctx);
 void preload_assembly_kernels();
 void assembly_prefetch_symbolic(sb_context* ctx, unsigned side_mask);   // assembly.cu: symbolic phase ahead of time, issued by the helper thread behind ev_dyn[k] of the side streams in the mask
 void assembly_prefetch_drain(sb_context* ctx);
+bool assembly_locate_dynamic(sb_context* ctx);              // assembly.cu, scatter mode: can the current pattern absorb the changed contact tables?
+void assembly_locate_result(sb_context* ctx, bool miss);
 const std::vector<KernelInfo>& all_kernels();
 
 template<class T> struct DevBuf {
@@ -224,6 +226,7 @@ struct sb_context {
     uint64_t pgh_state = 0, pgh_dynamic = 0, pgh_static = 0;
     double pgh_E = 0.0, pgh_residual = 0.0;
     // first half of a P+G+H evaluation (the static potentials) launched ahead of the collision detection (eval_prelaunch_static)
+    bool locate_pending = false;   // a scatter-mode pattern lookup rides with this evaluation's scalars
     bool pre_valid = false;
     uint64_t pre_state = 0, pre_static = 0;
     size_t st_H = 0, st_rows = 0, st_E = 0, st_blocks = 0;   // totals of the static potentials in the element-output buffers
@@ -269,7 +272,7 @@ int assemble_internal(sb_context* ctx);
 struct DirtyView {
     unsigned long long n_static;
     const uint32_t* s_blk_of_src; const uint32_t* s_final;
-    const uint32_t* d_blk_of_src; const uint32_t* d_final;
+    const uint32_t* d_final_of_src;   // per dynamic source: its BCSR block
     uint8_t* dirty;
 };
 bool assembly_dirty_view(sb_context* ctx, DirtyView* v);

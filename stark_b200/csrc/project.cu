@@ -335,7 +335,7 @@ __device__ void project_item(unsigned char* base, const ProjTable& T, int pi, un
                 const unsigned long long src0 = T.blk_off[pi] + (e - T.E_off[pi]) * (unsigned long long)(nb * nb);
                 for (int k = lane; k < nb * nb; k += G) {
                     const unsigned long long src = src0 + k;
-                    const uint32_t f = (src < dv.n_static) ? dv.s_final[dv.s_blk_of_src[src]] : dv.d_final[dv.d_blk_of_src[src - dv.n_static]];
+                    const uint32_t f = (src < dv.n_static) ? dv.s_final[dv.s_blk_of_src[src]] : dv.d_final_of_src[src - dv.n_static];
                     dv.dirty[f] = 1;
                 }
             }

@@ -245,3 +245,69 @@ def test_pcg_streaming_paths(limit):
     assert a["ok"] and b["ok"] and a["it"] == b["it"]
     da, db = np.array(a["du"]), np.array(b["du"])
     assert np.abs(da - db).max() <= 1e-12 * np.abs(da).max()
+
+
+@pytest.mark.gpu
+def test_assembly_absorbs_changed_contact_tables_without_a_symbolic_phase():
+    """Scatter mode of the assembly (assembly.cu): once the pattern holds the blocks of the contact neighbourhood, a detection that
+    changes the contact tables is absorbed without sorting -- every dynamic source is looked up in the BCSR rows and added through
+    an FP64 hash table.  After a run that has been through such steps, the matrix handed out by sb_bcsr_get must still be the
+    exact assembly of the element Hessians (pattern with explicit zero blocks of vanished pairs dropped; values one float ulp from
+    the float64-accumulated oracle), and the trajectory must equal the one of a run with SB_NO_SCATTER=1."""
+    import json, subprocess, textwrap
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = textwrap.dedent("""
+        import sys, json
+        sys.path.insert(0, %r); sys.path.insert(0, %r); sys.path.insert(0, %r)
+        import numpy as np
+        from stark_b200 import scenes, capi
+        import oracle
+        sc = scenes.Scene("tetdrop", n=6, vz=0.6)
+        log = []
+        for _ in range(14):
+            s = sc.step()
+            log.append([s["accepted"], s["newton_iterations"], s["result"], s["first_residual"]])
+        ctx = capi.Context.borrow(sc.lib.sbh_scene_context(sc.h))
+        ctx.eval("PGH"); ctx.assemble()
+        rows, cols, vals = ctx.bcsr()
+        Hs, erows = [], []
+        pot = 0
+        while True:
+            try:
+                n_in, n, ne = ctx.potential_info(pot)
+            except capi.SBError:
+                break
+            if ne > 0:
+                Hs += list(ctx.hessians(pot)); erows += [list(x) for x in ctx.block_rows(pot)]
+            pot += 1
+        rp, oc, ov = oracle.assemble_bcsr(Hs, erows, len(rows) - 1)
+        ok_pattern = bool(np.array_equal(rp, rows) and np.array_equal(oc, cols))
+        err = 1.0
+        if ok_pattern:
+            d = np.abs(ov.astype(np.float64) - vals.astype(np.float64)).reshape(-1, 9)
+            sc_ = np.abs(ov.astype(np.float64)).reshape(-1, 9).max(axis=1, keepdims=True) + 1e-30
+            err = float((d / sc_).max())
+        print(json.dumps({"log": log, "x": sc.positions()[::7].tolist(), "pattern": ok_pattern, "err": err}))
+    """) % (here, os.path.dirname(here), os.path.join(os.path.dirname(here), "oracle"))
+    out = []
+    for no_scatter in (False, True):
+        env = dict(os.environ, SB_ASM_DUMP="1")
+        env.pop("SB_NO_SCATTER", None)
+        if no_scatter:
+            env["SB_NO_SCATTER"] = "1"
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out.append((json.loads(r.stdout.strip().splitlines()[-1]), r.stderr))
+    (a, err_a), (b, err_b) = out
+    # the scatter path was really taken (and not in the control run)
+    import re
+    hits = int(re.search(r"without a symbolic phase: (\d+)", err_a).group(1))
+    assert hits > 0, err_a
+    assert int(re.search(r"without a symbolic phase: (\d+)", err_b).group(1)) == 0
+    for run in (a, b):
+        assert run["pattern"], "BCSR pattern differs from the assembly of the element Hessians"
+        assert run["err"] < 2e-7
+    for sa, sb in zip(a["log"], b["log"]):
+        assert sa[:3] == sb[:3], (sa, sb)
+        assert abs(sa[3] - sb[3]) <= 1e-4 * abs(sa[3]), (sa, sb)
+    assert np.abs(np.array(a["x"]) - np.array(b["x"])).max() <= 1e-6
