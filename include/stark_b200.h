@@ -105,6 +105,10 @@ enum sb_eval_mode { SB_EVAL_P = 0, SB_EVAL_PGH = 2 };
  * anything: gradient, element Hessians and block rows on the device are still that evaluation's.  (sb_newton_solve uses this:
  * the first line-search trial is evaluated with SB_EVAL_PGH and becomes the next iteration's evaluation when accepted.) */
 SB_API int sb_eval(sb_context* ctx, int mode, double* out_E, double* out_grad_inf);
+/* Optional hint: start the kernels of the next SB_EVAL_PGH evaluation that do not depend on the contact tables (volume / shell /
+ * inertia / joint potentials) NOW, at the current state.  A collision detection issued next (sb_contact_begin_time_step,
+ * sb_contact_update) then runs beside them; sb_eval / sb_newton_solve pick the result up if the state has not changed since. */
+SB_API int sb_eval_prelaunch(sb_context* ctx);
 SB_API int sb_grad_get(sb_context* ctx, double* host_grad);   /* flat, length ndofs */
 /* per-element output of one potential as the reference lays it out: [E | grad(n) | hess(n*n) row-major] per element */
 SB_API int sb_potential_get_element_output(sb_context* ctx, int potential, double* host_sol);

@@ -74,7 +74,7 @@ SYMBOLS = [
     "sb_array_create", "sb_array_upload", "sb_array_download", "sb_array_rows", "sb_array_fill", "sb_array_axpy", "sb_array_copy", "sb_array_download_async", "sb_download_wait", "sb_host_register", "sb_host_unregister",
     "sb_dof_add", "sb_dof_total", "sb_dofs_get", "sb_dofs_set",
     "sb_potential_create", "sb_potential_set_connectivity", "sb_potential_info", "sb_kernel_names",
-    "sb_eval", "sb_grad_get", "sb_potential_get_element_output", "sb_potential_get_block_rows", "sb_potential_get_hessians",
+    "sb_eval", "sb_eval_prelaunch", "sb_grad_get", "sb_potential_get_element_output", "sb_potential_get_block_rows", "sb_potential_get_hessians",
     "sb_project_to_pd", "sb_assemble", "sb_bcsr_info", "sb_bcsr_get",
     "sb_solve_pcg", "sb_solve_llt", "sb_du_get", "sb_dofs_save", "sb_dofs_apply_step", "sb_du_scale",
     "sb_contact_init", "sb_contact_add_mesh", "sb_contact_blacklist", "sb_contact_set_friction", "sb_contact_set_params",

@@ -93,6 +93,7 @@ struct Assembly {
     // end_insertion).  A source whose block is missing raises a flag that travels to the host with the evaluation's scalars,
     // and the sort-based symbolic phase above runs as before.
     bool scatter_mode = false;
+    int n_long_static = 0;             // static blocks with more than LONG_SEG sources
     DevBuf<uint32_t> d_final_of_src;   // per dynamic source: its BCSR block (both modes; the projection's dirty marking uses it)
     DevBuf<uint8_t> has_dyn;           // per BCSR block: receives dynamic contributions in this numeric pass
     DevBuf<int32_t> hkeys;             // hash table: BCSR block or -1
@@ -102,7 +103,12 @@ struct Assembly {
     size_t loc_n = 0;                  // dynamic sources of the last k_dyn_locate_src
     uint64_t loc_dynamic = 0;          // ... and the table version it looked at
     long long n_scatter_hits = 0, n_scatter_misses = 0;
+    cudaEvent_t ev_loc = nullptr, ev_scatter = nullptr;
+    bool scatter_in_flight = false;     // a speculative pass has been issued on the side stream and not yet been ordered before the context stream
+    uint64_t scatter_done_eval = 0;     // evaluation whose dynamic contributions already sit in the hash table (speculative pass)
 };
+
+static int scatter_pass(sb_context* ctx, Assembly* A, cudaStream_t st);
 
 static Assembly* get(sb_context* ctx)
 {
@@ -123,6 +129,7 @@ void assembly_destroy(sb_context* ctx)
     A->seg4.release(); A->blk_row.release(); A->rows.release(); A->cols.release(); A->vals.release(); A->temp.release();
     A->dirty.release(); A->long_blocks.release(); A->descs.release();
     A->d_final_of_src.release(); A->has_dyn.release(); A->hkeys.release(); A->hacc.release();
+    if (A->ev_loc) { cudaEventDestroy(A->ev_loc); cudaEventDestroy(A->ev_scatter); }
     if (A->h_descs) cudaFreeHost(A->h_descs);
     if (std::getenv("SB_ASM_DUMP")) fprintf(stderr, "[stark_b200 assembly] contact-table changes absorbed without a symbolic phase: %lld, with a sort-based rebuild: %lld\n", A->n_scatter_hits, A->n_scatter_misses);
     if (A->d_counts) cudaFree(A->d_counts);
@@ -302,24 +309,53 @@ __global__ void k_dyn_locate_src(const PotDesc* __restrict__ descs, int n_descs,
 // Scatter mode, step 2 (numeric phase): every dynamic source adds its 3x3 block to the FP64 accumulators of its BCSR block in a
 // lock-free open-addressing table (9 threads per source).
 __device__ __forceinline__ uint32_t blk_hash(uint32_t f) { f *= 0x9E3779B1u; return f ^ (f >> 15); }
-__global__ void k_scatter_dynamic(const double* __restrict__ H, const uint32_t* __restrict__ d_final_of_src, const uint32_t* __restrict__ src_off,
-                                  const uint8_t* __restrict__ src_pitch, size_t n_src, int32_t* __restrict__ hkeys, double* __restrict__ hacc,
-                                  uint32_t hmask, uint8_t* __restrict__ has_dyn)
+// A persistent grid; every CTA first combines the contributions of its sources per BCSR block in a small shared-memory table
+// (the rigid-body blocks receive a contribution from EVERY contact element: without this, thousands of FP64 atomics queue on
+// the same nine addresses), then flushes the combined blocks into the global table.
+constexpr int SC_SLOTS = 256;      // shared-memory slots per CTA (power of two); overflow goes straight to the global table
+constexpr int SC_THREADS = 288;    // 32 sources x 9 entries per pass
+__device__ __forceinline__ void scatter_global(uint32_t f, int k, double v, int32_t* __restrict__ hkeys, double* __restrict__ hacc, uint32_t hmask)
 {
-    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t g = t / 9;
-    if (g >= n_src) return;
-    const int k = (int)(t - g * 9);
-    const int r = k % 3, c = k / 3;
-    const uint32_t f = d_final_of_src[g];
     uint32_t slot = blk_hash(f) & hmask;
     while (true) {
         const int32_t prev = atomicCAS(hkeys + slot, -1, (int32_t)f);
         if (prev == -1 || prev == (int32_t)f) break;
         slot = (slot + 1) & hmask;
     }
-    if (k == 0) has_dyn[f] = 1;
-    atomicAdd(hacc + 9 * (size_t)slot + k, H[(size_t)src_off[g] + (size_t)r * src_pitch[g] + c]);
+    atomicAdd(hacc + 9 * (size_t)slot + k, v);
+}
+__global__ void __launch_bounds__(SC_THREADS) k_scatter_dynamic(const double* __restrict__ H, const uint32_t* __restrict__ d_final_of_src, const uint32_t* __restrict__ src_off,
+                                  const uint8_t* __restrict__ src_pitch, size_t n_src, int32_t* __restrict__ hkeys, double* __restrict__ hacc,
+                                  uint32_t hmask, uint8_t* __restrict__ has_dyn)
+{
+    __shared__ int32_t s_key[SC_SLOTS];
+    __shared__ double s_acc[SC_SLOTS][9];
+    for (int i = threadIdx.x; i < SC_SLOTS; i += SC_THREADS) s_key[i] = -1;
+    for (int i = threadIdx.x; i < SC_SLOTS * 9; i += SC_THREADS) (&s_acc[0][0])[i] = 0.0;
+    __syncthreads();
+    const int k = threadIdx.x % 9, lane_src = threadIdx.x / 9;
+    const int r = k % 3, c = k / 3;
+    for (size_t g = (size_t)blockIdx.x * 32 + lane_src; g < n_src; g += (size_t)gridDim.x * 32) {
+        const uint32_t f = d_final_of_src[g];
+        if (f == 0xffffffffu) continue;   // (a speculative pass behind a lookup that found a block missing: its result is discarded)
+        const double v = H[(size_t)src_off[g] + (size_t)r * src_pitch[g] + c];
+        if (k == 0) has_dyn[f] = 1;
+        uint32_t slot = blk_hash(f) & (SC_SLOTS - 1);
+        bool placed = false;
+        for (int probe = 0; probe < 8; probe++) {
+            const int32_t prev = atomicCAS(s_key + slot, -1, (int32_t)f);
+            if (prev == -1 || prev == (int32_t)f) { placed = true; break; }
+            slot = (slot + 1) & (SC_SLOTS - 1);
+        }
+        if (placed) atomicAdd(&s_acc[slot][k], v);
+        else scatter_global(f, k, v, hkeys, hacc, hmask);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < SC_SLOTS * 9; i += SC_THREADS) {
+        const int slot = i / 9, kk = i - 9 * slot;
+        const int32_t f = s_key[slot];
+        if (f >= 0) scatter_global((uint32_t)f, kk, s_acc[slot][kk], hkeys, hacc, hmask);
+    }
 }
 __device__ __forceinline__ double dyn_lookup(uint32_t f, int k, const int32_t* __restrict__ hkeys, const double* __restrict__ hacc, uint32_t hmask)
 {
@@ -365,6 +401,15 @@ __global__ void k_find_long(const int4* __restrict__ seg4, uint32_t* __restrict_
     }
 }
 
+// static blocks with more than LONG_SEG sources (counted once per static build: when there are none, scatter-mode passes do not
+// launch k_assemble_long at all)
+__global__ void k_count_long_static(const uint32_t* __restrict__ seg, const uint32_t* __restrict__ n_blocks_p, int* __restrict__ out)
+{
+    const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= *n_blocks_p) return;
+    if (seg[b + 1] - seg[b] > LONG_SEG) atomicAdd(out, 1);
+}
+
 struct NumericArgs {
     const double* H;
     const int4* seg4;
@@ -391,6 +436,7 @@ __global__ void __launch_bounds__(288) k_assemble_long(const NumericArgs a)
         const uint32_t b = a.long_blocks[i];
         if (ONLY_DIRTY && !a.dirty[b]) continue;   // uniform across the CTA
         const int4 g = a.seg4[b];
+        if (a.scatter && g.y - g.x <= LONG_SEG) continue;   // (long through its dynamic sources at the last rebuild only: the plain kernel sums it; uniform across the CTA)
         double acc = 0.0;
         for (int s = g.x + lane; s < g.y; s += 32) acc += a.H[(size_t)a.s_off[s] + (size_t)r * a.s_pitch[s] + c];
         if (!a.scatter) { for (int s = g.z + lane; s < g.w; s += 32) acc += a.H[(size_t)a.d_off[s] + (size_t)r * a.d_pitch[s] + c]; }
@@ -418,7 +464,7 @@ __global__ void __launch_bounds__(288) k_assemble_numeric(const NumericArgs a)
     const int k = (int)(t - b * 9);
     const int r = k % 3, c = k / 3;
     const int4 g = a.seg4[b];
-    if ((g.y - g.x) + (g.w - g.z) > LONG_SEG && long_rank_ok(b, a.long_blocks, a.n_long)) return;   // summed by k_assemble_long
+    if ((a.scatter ? (g.y - g.x) : (g.y - g.x) + (g.w - g.z)) > LONG_SEG && long_rank_ok(b, a.long_blocks, a.n_long)) return;   // summed by k_assemble_long
     double acc = 0.0;
     int s = g.x;
     for (; s + 4 <= g.y; s += 4) {
@@ -482,9 +528,14 @@ static int build_set(sb_context* ctx, Assembly* A, SourceSet& X, bool dynamic, c
     ctx->launches += 7;
     if (dynamic) { X.n_blocks = n; return 0; }   // upper bound; the exact count stays on the device (blk_of[n - 1])
     uint32_t nb32 = 0;
+    int n_long_static = 0;
+    SB_CUDA(ctx, cudaMemsetAsync(A->d_counts + 3, 0, sizeof(int), st));
+    k_count_long_static<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(X.seg.p, X.blk_of.p + (n - 1), A->d_counts + 3);
     SB_CUDA(ctx, cudaMemcpyAsync(&nb32, X.blk_of.p + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    SB_CUDA(ctx, cudaMemcpyAsync(&n_long_static, A->d_counts + 3, sizeof(int), cudaMemcpyDeviceToHost, st));
     SB_CUDA(ctx, cudaStreamSynchronize(st));
     X.n_blocks = nb32;
+    A->n_long_static = n_long_static;
     return 0;
 }
 
@@ -666,6 +717,20 @@ bool assembly_locate_dynamic(sb_context* ctx)
     k_dyn_locate_src<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(A->descs.p, nd, n, ctx->rows.p, A->rows.p, A->cols.p, A->nbr, A->d_final_of_src.p,
                                                                    A->D.src_off.p, A->D.src_pitch.p, ctx->d_scalars + 2);
     ctx->launches++;
+    // Speculatively, on a side stream: the numeric phase's scatter pass of this evaluation (valid if no block is missing, which
+    // is the common case; the host learns that with the evaluation's scalars).  It runs under the reductions and the sync.
+    if (!A->ev_loc) { cudaEventCreateWithFlags(&A->ev_loc, cudaEventDisableTiming); cudaEventCreateWithFlags(&A->ev_scatter, cudaEventDisableTiming); }
+    {
+        const size_t keep_n = A->D.n;
+        A->D.n = n;
+        cudaEventRecord(A->ev_loc, st);
+        cudaStreamWaitEvent(ctx->sym_stream, A->ev_loc, 0);
+        const int rs = scatter_pass(ctx, A, ctx->sym_stream);
+        cudaEventRecord(A->ev_scatter, ctx->sym_stream);
+        A->scatter_in_flight = true;
+        A->D.n = keep_n;
+        A->scatter_done_eval = rs ? 0 : ctx->eval_id;
+    }
     return true;
 }
 // ... and the answer, once the evaluation's scalars are on the host
@@ -673,12 +738,32 @@ void assembly_locate_result(sb_context* ctx, bool miss)
 {
     Assembly* A = ctx->assembly;
     if (!A || A->loc_dynamic != ctx->dynamic_version) return;
-    if (miss) { A->n_scatter_misses++; return; }   // (the sort-based symbolic phase runs at the next assembly)
+    if (miss) { A->n_scatter_misses++; A->scatter_done_eval = 0; return; }   // (the sort-based symbolic phase runs at the next assembly)
     A->n_scatter_hits++;
     A->D.n = A->loc_n;
     A->built_dynamic = ctx->dynamic_version;
     A->built_n_src = ctx->n_blocks_total;
     A->scatter_mode = true;
+}
+
+// dynamic contributions of one numeric pass into the FP64 hash table (all sources, every pass: a pass after a PD projection
+// re-sums only dirty blocks, and those see the projected elements' new values)
+static int scatter_pass(sb_context* ctx, Assembly* A, cudaStream_t st)
+{
+    const size_t n_src = A->D.n;
+    size_t cap = 1024;
+    while (cap < 2 * n_src) cap <<= 1;
+    A->hkeys.ensure(cap); A->hacc.ensure(9 * cap); A->has_dyn.ensure(A->nnzb + 1);
+    A->hcap = cap;
+    SB_CUDA(ctx, cudaMemsetAsync(A->has_dyn.p, 0, A->nnzb + 1, st));
+    if (n_src > 0) {
+        SB_CUDA(ctx, cudaMemsetAsync(A->hkeys.p, 0xff, cap * sizeof(int32_t), st));
+        SB_CUDA(ctx, cudaMemsetAsync(A->hacc.p, 0, 9 * cap * sizeof(double), st));
+        k_scatter_dynamic<<<(unsigned)std::min<size_t>((n_src + 31) / 32, 148 * 4), SC_THREADS, 0, st>>>(ctx->H.p, A->d_final_of_src.p, A->D.src_off.p, A->D.src_pitch.p, n_src,
+                                                                                                       A->hkeys.p, A->hacc.p, (uint32_t)(cap - 1), A->has_dyn.p);
+        ctx->launches++;
+    }
+    return 0;
 }
 
 int assemble_internal(sb_context* ctx)
@@ -687,6 +772,7 @@ int assemble_internal(sb_context* ctx)
     Assembly* A = get(ctx);
     if (ctx->n_blocks_total == 0) return fail(ctx, SB_ERR_STATE, "sb_assemble: no element Hessians");
     bool rebuilt = false;
+    if (A->scatter_in_flight) { SB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, A->ev_scatter, 0)); A->scatter_in_flight = false; }   // (it reads buffers a rebuild below rewrites)
     if (A->pf_pending) {
         ctx->issuer->wait();
         if (A->pf_failed) { cudaEventSynchronize(A->ev_sym); A->pf_pending = false; }   // (falls back to the in-place build below)
@@ -716,42 +802,42 @@ int assemble_internal(sb_context* ctx)
     a.scatter = A->scatter_mode ? 1 : 0;
     a.has_dyn = nullptr; a.hkeys = nullptr; a.hacc = nullptr; a.hmask = 0;
     if (A->scatter_mode) {
-        // dynamic contributions of this pass: FP64 accumulators per touched BCSR block (all sources, every pass: a pass after a
-        // PD projection re-sums only dirty blocks, and those see the projected elements' new values)
-        const size_t n_src = A->D.n;
-        size_t cap = 1024;
-        while (cap < 2 * n_src) cap <<= 1;
-        A->hkeys.ensure(cap); A->hacc.ensure(9 * cap); A->has_dyn.ensure(A->nnzb + 1);
-        A->hcap = cap;
-        SB_CUDA(ctx, cudaMemsetAsync(A->has_dyn.p, 0, A->nnzb + 1, ctx->stream));
-        if (n_src > 0) {
-            SB_CUDA(ctx, cudaMemsetAsync(A->hkeys.p, 0xff, cap * sizeof(int32_t), ctx->stream));
-            SB_CUDA(ctx, cudaMemsetAsync(A->hacc.p, 0, 9 * cap * sizeof(double), ctx->stream));
-            k_scatter_dynamic<<<(unsigned)((9 * n_src + 287) / 288), 288, 0, ctx->stream>>>(ctx->H.p, A->d_final_of_src.p, A->D.src_off.p, A->D.src_pitch.p, n_src,
-                                                                                           A->hkeys.p, A->hacc.p, (uint32_t)(cap - 1), A->has_dyn.p);
-            ctx->launches++;
+        if (A->scatter_done_eval == ctx->eval_id && ctx->n_projected == 0) {
+            // the evaluation already ran this pass on a side stream (behind its pattern lookup, under its reductions and its sync;
+            // ordered before the context stream above)
+        } else {
+            int rs = scatter_pass(ctx, A, ctx->stream);
+            if (rs) return rs;
         }
-        a.has_dyn = A->has_dyn.p; a.hkeys = A->hkeys.p; a.hacc = A->hacc.p; a.hmask = (uint32_t)(cap - 1);
+        A->scatter_done_eval = 0;
+        a.has_dyn = A->has_dyn.p; a.hkeys = A->hkeys.p; a.hacc = A->hacc.p; a.hmask = (uint32_t)(A->hcap - 1);
     }
     const size_t nt = 9 * A->nnzb;
     const unsigned grid = (unsigned)((nt + 287) / 288);
     // the few long blocks (a rigid body's diagonal: thousands of sources, one CTA each, latency-bound) are summed on a side
     // stream while the bulk kernel streams the element Hessians; the two write disjoint blocks
     cudaStream_t side = ctx->side[0];
-    SB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
-    SB_CUDA(ctx, cudaStreamWaitEvent(side, ctx->ev_fork, 0));
-    if (!rebuilt && A->numeric_valid && A->assembled_eval == ctx->eval_id) {
+    const bool with_long = !(A->scatter_mode && A->n_long_static == 0);   // (scatter mode: only statically long blocks are left to it)
+    if (with_long) {
+        SB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+        SB_CUDA(ctx, cudaStreamWaitEvent(side, ctx->ev_fork, 0));
+    }
+    const bool update = !rebuilt && A->numeric_valid && A->assembled_eval == ctx->eval_id;
+    if (update) {
         // same evaluation, same pattern: only PD-projected elements changed since the last pass
-        k_assemble_long<true><<<LONG_CTAS, 288, 0, side>>>(a);
+        if (with_long) k_assemble_long<true><<<LONG_CTAS, 288, 0, side>>>(a);
         k_assemble_numeric<true><<<grid, 288, 0, ctx->stream>>>(a);
     } else {
-        k_assemble_long<false><<<LONG_CTAS, 288, 0, side>>>(a);
+        if (with_long) k_assemble_long<false><<<LONG_CTAS, 288, 0, side>>>(a);
         k_assemble_numeric<false><<<grid, 288, 0, ctx->stream>>>(a);
     }
-    SB_CUDA(ctx, cudaEventRecord(ctx->ev_join[0], side));
-    SB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[0], 0));
-    k_clear_dirty<<<(unsigned)((A->nnzb + 255) / 256), 256, 0, ctx->stream>>>(A->dirty.p, A->nnzb);
-    ctx->launches += 3;
+    if (with_long) {
+        SB_CUDA(ctx, cudaEventRecord(ctx->ev_join[0], side));
+        SB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[0], 0));
+    }
+    // (the dirty flags are only ever set by a PD projection of this evaluation: nothing to clear after a full pass of a fresh one)
+    if (update || ctx->n_projected > 0) { SB_CUDA(ctx, cudaMemsetAsync(A->dirty.p, 0, A->nnzb + 1, ctx->stream)); }
+    ctx->launches += with_long ? 2 : 1;
     SB_CUDA(ctx, cudaGetLastError());
     A->assembled_eval = ctx->eval_id;
     A->numeric_valid = true;

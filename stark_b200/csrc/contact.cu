@@ -292,7 +292,13 @@ __global__ void k_morton(const float* __restrict__ bb, const int32_t* __restrict
         const float u = (0.5f * (bb[6 * i + c] + bb[6 * i + 3 + c]) - bounds[c]) / ext;
         q[c] = (uint32_t)fminf(fmaxf(u * 1024.0f, 0.0f), 1023.0f);
     }
-    code[i] = (spread3(q[2]) << 2) | (spread3(q[1]) << 1) | spread3(q[0]);
+    // A primitive much larger than its neighbours (a floor triangle among the elements of a fine mesh) would blow up the box of
+    // whatever tile its centre falls into, and that tile would then be tested against every other one: such primitives are
+    // sorted behind all others (bit 30) and share tiles among themselves.
+    float ext = 0.0f, scene = 0.0f;
+    for (int c = 0; c < 3; c++) { ext = fmaxf(ext, bb[6 * i + 3 + c] - bb[6 * i + c]); scene = fmaxf(scene, bounds[3 + c] - bounds[c]); }
+    const uint32_t big = (ext > 0.0625f * scene) ? 0x40000000u : 0u;
+    code[i] = big | (spread3(q[2]) << 2) | (spread3(q[1]) << 1) | spread3(q[0]);
     ids[i] = perm[i];
 }
 
@@ -353,7 +359,7 @@ __global__ void k_tile_pairs_all(Dev d, int Tv, int Tt, int Te, int n0, int n1, 
 }
 
 // all-pairs test inside the overlapping tile pairs (persistent CTAs, B tile staged in shared memory)
-constexpr int QCAP = 2048;
+constexpr int QCAP = 384;      // (a tile pair yields a dozen candidates on average; 4 KB of queue lets 32 CTAs share an SM)
 struct alignas(16) BroadSmem {
     float bb[TILE][8];       // (min xyz, max xyz, 2 pad: one 128-bit + one 64-bit shared load per box)
     int v[TILE][3];
@@ -361,9 +367,11 @@ struct alignas(16) BroadSmem {
     int id[TILE];
     int2 q[QCAP];
     int qn, qbase;
+    int slot[TILE];          // slot of every staged B primitive (the B tile is compacted, see broad_kind)
+    int nb;                  // staged B primitives
 };
 template<int KIND>
-__device__ void broad_kind(const Dev& d, BroadSmem& S)
+__device__ void broad_kind(const Dev& d, BroadSmem& S, int first_pair)
 {
     float (*s_bb)[8] = S.bb;
     int (*s_v)[3] = S.v;
@@ -372,6 +380,10 @@ __device__ void broad_kind(const Dev& d, BroadSmem& S)
     int2* s_q = S.q;
     int& s_qn = S.qn;
     int& s_qbase = S.qbase;
+    int* s_slot = S.slot;
+    int& s_nb = S.nb;
+    const float* tbA = (KIND == 0) ? d.tb_p : d.tb_e;
+    const float* tbB = (KIND == 1) ? d.tb_e : d.tb_t;
     const int nA = (KIND == 0) ? d.n_v : d.n_e;
     const int nB = (KIND == 1) ? d.n_e : d.n_t;
     const float* bbA = (KIND == 0) ? d.bb_p : d.bb_e;
@@ -382,37 +394,47 @@ __device__ void broad_kind(const Dev& d, BroadSmem& S)
     // (tens of thousands of same-address global atomics would serialise in L2 and dominate the kernel)
     int2* out = (KIND == 0) ? d.cand_pt : (KIND == 1 ? d.cand_ee : d.cand_et);
     const int n_pairs = min(d.counters[4 + KIND], d.tile_pair_cap[KIND]);
-    for (int pi = blockIdx.x; pi < n_pairs; pi += gridDim.x) {
+    for (int pi = first_pair; pi < n_pairs; pi += gridDim.x) {
         const int2 tp = d.tile_pairs[KIND][pi];
         const int a = tp.x * TILE + threadIdx.x;     // slot of A
         const int b0 = tp.y * TILE;                  // first slot of the B tile
         __syncthreads();   // previous pair done with the shared tile and queue
-        if (threadIdx.x == 0) s_qn = 0;
+        if (threadIdx.x == 0) { s_qn = 0; s_nb = 0; }
+        __syncthreads();
         {
+            // Two tiles that overlap usually share a boundary strip only: B primitives outside the box of tile A cannot overlap
+            // any A primitive and are not staged (and A primitives outside the box of tile B sit the pair out, below) -- the
+            // all-pairs loop runs over what is left.
             const int b = b0 + threadIdx.x;
             if (b < nB) {
-                for (int c = 0; c < 6; c++) s_bb[threadIdx.x][c] = bbB[6 * b + c];
-                const int pb = permB[b];
-                s_id[threadIdx.x] = pb;
-                if (KIND == 1) { s_v[threadIdx.x][0] = d.edge[2 * pb]; s_v[threadIdx.x][1] = d.edge[2 * pb + 1]; s_v[threadIdx.x][2] = -1; s_g[threadIdx.x] = d.e_group[pb]; }
-                else { s_v[threadIdx.x][0] = d.tri[3 * pb]; s_v[threadIdx.x][1] = d.tri[3 * pb + 1]; s_v[threadIdx.x][2] = d.tri[3 * pb + 2]; s_g[threadIdx.x] = d.t_group[pb]; }
+                float bx[6];
+                for (int c = 0; c < 6; c++) bx[c] = bbB[6 * b + c];
+                if (bb_overlap(bx, tbA + 6 * tp.x)) {
+                    const int k = atomicAdd(&s_nb, 1);
+                    for (int c = 0; c < 6; c++) s_bb[k][c] = bx[c];
+                    const int pb = permB[b];
+                    s_id[k] = pb;
+                    s_slot[k] = b;
+                    if (KIND == 1) { s_v[k][0] = d.edge[2 * pb]; s_v[k][1] = d.edge[2 * pb + 1]; s_v[k][2] = -1; s_g[k] = d.e_group[pb]; }
+                    else { s_v[k][0] = d.tri[3 * pb]; s_v[k][1] = d.tri[3 * pb + 1]; s_v[k][2] = d.tri[3 * pb + 2]; s_g[k] = d.t_group[pb]; }
+                }
             }
         }
         __syncthreads();
         {
             // (every thread walks the B tile, so that the warp can skip a box none of its lanes overlaps with one vote: with a
             //  hit rate of a few per thousand tests, everything after the box test is off the common path)
-            const bool act = a < nA;
-            const int aa = act ? a : 0;
+            const int aa = (a < nA) ? a : 0;
             float ba[6];
             for (int c = 0; c < 6; c++) ba[c] = bbA[6 * aa + c];
+            const bool act = a < nA && bb_overlap(ba, tbB + 6 * tp.y);
             const int pa = permA[aa];
             int va0, va1, ga;
             if (KIND == 0) { va0 = pa; va1 = -2; ga = d.v_group[pa]; }
             else { va0 = d.edge[2 * pa]; va1 = d.edge[2 * pa + 1]; ga = d.e_group[pa]; }
-            const int nb = min(TILE, nB - b0);
+            const int nb = __any_sync(0xffffffffu, act) ? s_nb : 0;   // (a warp with no A primitive inside tile B's box skips the pair)
             for (int j = 0; j < nb; j++) {
-                const int b = b0 + j;
+                const int b = s_slot[j];
                 const float4 blo = *reinterpret_cast<const float4*>(&s_bb[j][0]);   // min x, min y, min z, max x
                 const float2 bhi = *reinterpret_cast<const float2*>(&s_bb[j][4]);   // max y, max z
                 bool hit = act && !(ba[0] > blo.w || blo.x > ba[3] || ba[1] > bhi.x || blo.y > ba[4] || ba[2] > bhi.y || blo.z > ba[5]);
@@ -453,8 +475,15 @@ template<int K0, int K1>
 __global__ void __launch_bounds__(TILE) k_broad_all(Dev d)
 {
     __shared__ BroadSmem S;
-    broad_kind<K0>(d, S);
-    if (K1 >= 0) { __syncthreads(); broad_kind<(K1 >= 0 ? K1 : 0)>(d, S); }
+    broad_kind<K0>(d, S, blockIdx.x);
+    if (K1 >= 0) {
+        // the second kind's pairs start where the first kind's left off: the kernel is bound by the latency of ONE tile pair
+        // (dependent gathers, a few barriers), so what matters is that no CTA gets more pairs than ceil(total / grid)
+        const int n0 = min(d.counters[4 + K0], d.tile_pair_cap[K0]);
+        const int first = (int)((blockIdx.x + gridDim.x - (unsigned)(n0 % (int)gridDim.x)) % gridDim.x);
+        __syncthreads();
+        broad_kind<(K1 >= 0 ? K1 : 0)>(d, S, first);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -926,6 +955,8 @@ __global__ void __launch_bounds__(128) k_narrow_et(Dev d)
 // point-triangle and edge-edge narrow phases of one detection in one launch
 __global__ void __launch_bounds__(128) k_narrow_all(Dev d, double enl_sq, int mode, double stiffness, double parallel_tol, int do_pt, int do_ee)
 {
+    // (the tables' digests go to global memory with L2 reductions: a shared-memory stage was tried and is slower -- 64-bit shared
+    //  atomics are compare-and-swap loops, and every point-triangle row of a warp hits the same word)
     if (do_pt) narrow_pt(d, enl_sq, mode, stiffness);
     if (do_ee) narrow_ee(d, enl_sq, mode, stiffness, parallel_tol);
 }
@@ -1098,10 +1129,10 @@ static int reorder_primitives(sb_context* ctx, Contact* C)
         if (c.n == 0) continue;
         k_morton<<<(c.n + 255) / 256, 256, 0, st>>>(c.bb, c.perm->p, C->bounds.p, C->morton.p, C->perm_tmp.p, c.n);
         size_t tb = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, tb, C->morton.p, C->morton_tmp.p, C->perm_tmp.p, c.perm->p, c.n, 0, 30, st);
+        cub::DeviceRadixSort::SortPairs(nullptr, tb, C->morton.p, C->morton_tmp.p, C->perm_tmp.p, c.perm->p, c.n, 0, 31, st);
         C->sort_temp.ensure(tb + 16);
         tb = C->sort_temp.cap;
-        SB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(C->sort_temp.p, tb, C->morton.p, C->morton_tmp.p, C->perm_tmp.p, c.perm->p, c.n, 0, 30, st));
+        SB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(C->sort_temp.p, tb, C->morton.p, C->morton_tmp.p, C->perm_tmp.p, c.perm->p, c.n, 0, 31, st));
         ctx->launches += 5;
     }
     SB_CUDA(ctx, cudaGetLastError());
@@ -1129,7 +1160,7 @@ static int detect(sb_context* ctx, Contact* C, int mode, double enlargement)
         if (mode == 1 || mode == 5) clear |= bits(8, 6) | bits(16 + N_CONTACT_TABLES, N_FRICTION);
         if (mode == 2 || mode == 3 || mode == 4 || mode == 5) clear |= bits(8 + 6, 1);
         const int Tv = (d.n_v + TILE - 1) / TILE, Tt = (d.n_t + TILE - 1) / TILE, Te = (d.n_e + TILE - 1) / TILE;
-        auto broad_grid = [](long long n_tile_pairs) { return (int)std::max(1ll, std::min(n_tile_pairs, 148ll * 16)); };
+        auto broad_grid = [](long long n_tile_pairs) { return (int)std::max(1ll, std::min(n_tile_pairs, 148ll * 32)); };
         (void)nmax;
         if (mode != 2) {
             const float extra = (float)enlargement + FLT_EPSILON;

@@ -105,6 +105,8 @@ static const char* const g_stage_names[ST_COUNT] = {"contact_update", "intersect
                                             "tile_pairs_pt", "tile_pairs_ee", "tile_pairs_et", "candidates_pt", "candidates_ee", "candidates_et", "project_sweeps", "pcg_cycles_window"};
 const char* const* stage_names() { return g_stage_names; }
 
+int g_tet_grid_cap = 148 * 3;
+
 void Issuer::start(int dev)
 {
     device = dev;
@@ -334,9 +336,10 @@ template<class T> static void grow_output(sb_context* ctx, DevBuf<T>& b, size_t 
 // kernels.  sb_newton_solve calls this right after a line-search step has been applied and BEFORE the collision detection of
 // the trial state: the volume elements' kernel (70 us at the 200k-tet scene) then runs while the host issues the detection,
 // instead of after the detection's synchronisation.  eval_internal picks the result up if the state has not changed since.
-static int pgh_static_part(sb_context* ctx)
+static int pgh_static_part(sb_context* ctx, bool beside_detection)
 {
     assembly_prefetch_drain(ctx);   // (a prefetched symbolic phase still reads the previous evaluation's block rows)
+    if (ctx->bulk_pending) { SB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_bulk, 0)); ctx->bulk_pending = false; }   // (an abandoned pre-launch still writing the buffers)
     ctx->pgh_cache_ok = false;
     ctx->have_pgh = false;
     recompute_dof_offsets(ctx);
@@ -372,7 +375,12 @@ static int pgh_static_part(sb_context* ctx)
     bool forked = false;
     int next_side = 0;
     for (auto& p : ctx->potentials)
-        if (!p.dynamic && p.n_elem > 0 && p.n_elem < SMALL_POTENTIAL && !forked) { SB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream)); forked = true; }
+        if (!p.dynamic && p.n_elem > 0 && (beside_detection || p.n_elem < SMALL_POTENTIAL) && !forked) { SB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream)); forked = true; }
+    // pre-launched ahead of the collision detection: the big kernels go to their own low-priority stream with a grid that leaves
+    // room on every SM (2 instead of 3 CTAs of the volume kernel), so that the detection's kernels -- issued next on the context
+    // stream -- run BESIDE them instead of behind them
+    bool bulk_used = false;
+    g_tet_grid_cap = beside_detection ? 148 * 2 : 148 * 3;
     for (int pass = 0; pass < 2; pass++)
         for (auto& p : ctx->potentials) {
             if (p.dynamic || p.n_elem == 0) continue;
@@ -383,11 +391,16 @@ static int pgh_static_part(sb_context* ctx)
                 const int k = next_side++ % sb_context::N_SIDE;
                 if (!(ctx->st_side_mask & (1u << k))) { SB_CUDA(ctx, cudaStreamWaitEvent(ctx->side[k], ctx->ev_fork, 0)); ctx->st_side_mask |= 1u << k; }
                 st = ctx->side[k];
+            } else if (beside_detection) {
+                if (!bulk_used) { SB_CUDA(ctx, cudaStreamWaitEvent(ctx->bulk_stream, ctx->ev_fork, 0)); bulk_used = true; }
+                st = ctx->bulk_stream;
             }
             p.k->launch_pgh(make_args(ctx, p), st);
             ctx->launches++;
             timeline_point(st, p.k->name);
         }
+    g_tet_grid_cap = 148 * 3;
+    if (bulk_used) { SB_CUDA(ctx, cudaEventRecord(ctx->ev_bulk, ctx->bulk_stream)); ctx->bulk_pending = true; }
     SB_CUDA(ctx, cudaGetLastError());
     ctx->st_next_side = next_side;
     return 0;
@@ -397,10 +410,11 @@ int eval_prelaunch_static(sb_context* ctx)
     // Measured at the 200k-tet scene: 921 it/s with the pre-launch against 934 without (the dynamic potentials are then issued
     // after the detection's synchronisation with no kernel to hide behind, instead of under the volume kernel) -- off unless
     // SB_PRELAUNCH is set; kept for scenes whose detection is long compared with the volume kernel.
-    static const bool on = std::getenv("SB_PRELAUNCH") != nullptr;
-    if (!on) return 0;
+    static const bool off = std::getenv("SB_NO_PRELAUNCH") != nullptr;
+    if (off) return 0;
+    if (ctx->pre_valid && ctx->pre_state == ctx->state_version && ctx->pre_static == ctx->static_version) return 0;   // already under way for this state
     StageTimer timer(ctx, ST_EVAL_PGH);
-    int r = pgh_static_part(ctx);
+    int r = pgh_static_part(ctx, true);
     if (r) return r;
     ctx->pre_valid = true;
     ctx->pre_state = ctx->state_version; ctx->pre_static = ctx->static_version;
@@ -431,7 +445,7 @@ int eval_internal(sb_context* ctx, int mode, double* out_E, double* out_grad_inf
     double td1 = td0;
 
     if (mode == SB_EVAL_PGH) {
-        if (!pre) { int r = pgh_static_part(ctx); if (r) return r; }
+        if (!pre) { int r = pgh_static_part(ctx, false); if (r) return r; }
         td1 = eval_dump ? now_ms() : 0.0;
         // ---- second half: the dynamic potentials (contact / friction tables), laid out behind the static ones ----
         size_t H_total = ctx->st_H, rows_total = ctx->st_rows, E_total = ctx->st_E, n_blocks = ctx->st_blocks;
@@ -487,6 +501,7 @@ int eval_internal(sb_context* ctx, int mode, double* out_E, double* out_grad_inf
             for (int k = 0; k < sb_context::N_SIDE; k++)
                 if (dyn_mask & (1u << k)) SB_CUDA(ctx, cudaEventRecord(ctx->ev_dyn[k], ctx->side[k]));
         side_mask |= dyn_mask;
+        if (ctx->bulk_pending) { SB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_bulk, 0)); ctx->bulk_pending = false; }
         for (int k = 0; k < sb_context::N_SIDE; k++)
             if (side_mask & (1u << k)) {
                 SB_CUDA(ctx, cudaEventRecord(ctx->ev_join[k], ctx->side[k]));
@@ -633,13 +648,22 @@ int sb_create(sb_context** out, int device, void* stream)
         ctx->own_stream = true;
     }
     for (int k = 0; k < sb_context::N_SIDE; k++) {
-        if (cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SB_ERR_CUDA; }
+        // (high priority: when an SM slot frees up under a large kernel of the context stream, the small potentials' CTAs go first)
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        if (cudaStreamCreateWithPriority(&ctx->side[k], cudaStreamNonBlocking, std::getenv("SB_NO_PRIORITY") ? prio_lo : prio_hi) != cudaSuccess) { delete ctx; return SB_ERR_CUDA; }
         if (cudaEventCreateWithFlags(&ctx->ev_join[k], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SB_ERR_CUDA; }
     }
     if (cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SB_ERR_CUDA; }
     if (cudaStreamCreateWithFlags(&ctx->sym_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SB_ERR_CUDA; }
     for (int k = 0; k < sb_context::N_SIDE; k++)
         if (cudaEventCreateWithFlags(&ctx->ev_dyn[k], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SB_ERR_CUDA; }
+    {
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        if (cudaStreamCreateWithPriority(&ctx->bulk_stream, cudaStreamNonBlocking, prio_lo) != cudaSuccess) { delete ctx; return SB_ERR_CUDA; }
+        if (cudaEventCreateWithFlags(&ctx->ev_bulk, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SB_ERR_CUDA; }
+    }
     ctx->issuer = new Issuer();
     ctx->issuer->start(device);
     if (cudaMallocHost(&ctx->h_scalars, 64 * sizeof(double)) != cudaSuccess) { delete ctx; return SB_ERR_CUDA; }
@@ -680,6 +704,8 @@ void sb_destroy(sb_context* ctx)
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     for (int k = 0; k < sb_context::N_SIDE; k++) if (ctx->ev_dyn[k]) cudaEventDestroy(ctx->ev_dyn[k]);
     if (ctx->sym_stream) cudaStreamDestroy(ctx->sym_stream);
+    if (ctx->bulk_stream) { cudaStreamSynchronize(ctx->bulk_stream); cudaStreamDestroy(ctx->bulk_stream); }
+    if (ctx->ev_bulk) cudaEventDestroy(ctx->ev_bulk);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); cudaEventDestroy(ctx->ev_copy_src); cudaEventDestroy(ctx->ev_copy_done); }
     if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
     if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
@@ -1009,6 +1035,11 @@ int sb_eval(sb_context* ctx, int mode, double* out_E, double* out_grad_inf)
 {
     if (!ctx) return SB_ERR_ARG;
     return eval_internal(ctx, mode, out_E, out_grad_inf, true);
+}
+int sb_eval_prelaunch(sb_context* ctx)
+{
+    if (!ctx) return SB_ERR_ARG;
+    return eval_prelaunch_static(ctx);
 }
 int sb_grad_get(sb_context* ctx, double* host_grad)
 {

@@ -190,6 +190,9 @@ struct sb_context {
     cudaStream_t sym_stream = nullptr;              // the helper thread's stream (symbolic phase of the assembly)
     cudaEvent_t ev_dyn[N_SIDE] = {nullptr, nullptr, nullptr, nullptr};   // "the dynamic potentials' kernels on this side stream are done"
     sb::Issuer* issuer = nullptr;
+    cudaStream_t bulk_stream = nullptr;             // pre-launched volume kernels (low priority: they run beside the collision detection)
+    cudaEvent_t ev_bulk = nullptr;
+    bool bulk_pending = false;                      // ev_bulk has been recorded and not yet joined into the context stream
     // sb_array_download_async
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copy_src = nullptr, ev_copy_done = nullptr;
@@ -283,5 +286,6 @@ int contact_update_internal(sb_context* ctx);
 int contact_intersections_internal(sb_context* ctx, int* out_count);
 bool contact_active(sb_context* ctx);
 int eval_internal(sb_context* ctx, int mode, double* out_E, double* out_grad_inf, bool sync_scalars);
-int eval_prelaunch_static(sb_context* ctx);   // static potentials of the coming P+G+H evaluation, before the collision detection
+int eval_prelaunch_static(sb_context* ctx);
+extern int g_tet_grid_cap;   // persistent grid of the volume kernel (tet_analytic.cuh): 3 CTAs per SM alone, 2 when it shares the SMs with the detection   // static potentials of the coming P+G+H evaluation, before the collision detection
 }  // namespace sb

@@ -554,7 +554,9 @@ template<bool COMPLETE> static void launch_tet_analytic_pgh(const EvalArgs& a, c
     for (int i = 0; i < nin; i++) P.slot[i] = a.slots_host[i];
     const int n_tiles = (a.n_elem + TET_TILE - 1) / TET_TILE;
     const int ctas_needed = (n_tiles + TET_WARPS - 1) / TET_WARPS;
-    const int grid = ctas_needed < 148 * 3 ? ctas_needed : 148 * 3;   // persistent: 3 CTAs per SM
+    static const int env_cap = std::getenv("SB_TET_GRID") ? std::max(1, std::atoi(std::getenv("SB_TET_GRID"))) : 0;   // (experiment hook)
+    const int grid_cap = env_cap ? env_cap : g_tet_grid_cap;
+    const int grid = ctas_needed < grid_cap ? ctas_needed : grid_cap;   // persistent: 3 CTAs per SM (2 beside the collision detection)
     if (tet_layout_is_canonical(P.slot)) k_tet_analytic<COMPLETE, true><<<grid, TET_THREADS, TET_SMEM_BYTES, s>>>(P);
     else k_tet_analytic<COMPLETE, false><<<grid, TET_THREADS, TET_SMEM_BYTES, s>>>(P);
 }

@@ -773,7 +773,9 @@ bool Simulation::run_one_time_step()
         check(sb_contact_set_params(ctx, contact.contact_stiffness, contact.global_params.friction_stick_slide_threshold, contact.global_params.triangle_point_enabled,
                                     contact.global_params.edge_edge_enabled, contact.global_params.friction_enabled), "sb_contact_set_params");
         // friction tables (EnergyFrictionalContact.cpp:531-773); v1 / w1 are zero here, so the same detection also serves the
-        // solve's initial validity test and first contact update
+        // solve's initial validity test and first contact update -- and the volume elements of the first evaluation, which do not
+        // depend on it, are started first and run beside it
+        check(sb_eval_prelaunch(ctx), "sb_eval_prelaunch");
         check(sb_contact_begin_time_step(ctx, 1), "sb_contact_begin_time_step");
     }
 
