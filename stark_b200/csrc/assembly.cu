@@ -104,6 +104,7 @@ struct Assembly {
     uint64_t loc_dynamic = 0;          // ... and the table version it looked at
     long long n_scatter_hits = 0, n_scatter_misses = 0;
     cudaEvent_t ev_loc = nullptr, ev_scatter = nullptr;
+    bool miss_flag_dirty = true;        // ctx->d_scalars[2] must be cleared before the next lookup
     bool scatter_in_flight = false;     // a speculative pass has been issued on the side stream and not yet been ordered before the context stream
     uint64_t scatter_done_eval = 0;     // evaluation whose dynamic contributions already sit in the hash table (speculative pass)
 };
@@ -679,18 +680,21 @@ void assembly_prefetch_drain(sb_context* ctx)
 // Scatter mode, called by the P+G+H evaluation once the dynamic potentials' kernels are enqueued and joined into the context
 // stream: can the changed contact tables be absorbed by the current pattern?  Launches k_dyn_locate_src; its miss flag lands in
 // ctx->d_scalars[2] and travels to the host with the evaluation's scalars.  Returns true when the kernel was launched.
-bool assembly_locate_dynamic(sb_context* ctx)
+bool assembly_locate_possible(sb_context* ctx)
 {
     Assembly* A = ctx->assembly;
     static const bool disabled = std::getenv("SB_NO_SCATTER") != nullptr;   // diagnostic hook
     if (disabled || !A || !A->numeric_valid || A->pf_pending || ctx->n_blocks_total == 0) return false;
     if (pattern_current(ctx, A) || static_part_stale(ctx, A)) return false;
-    if (A->nnzb == 0 || A->nnzb >= (1ull << 31)) return false;
-    {
-        int bits = 1;
-        while ((1ll << bits) < ctx->ndofs / 3 + 1) bits++;
-        if (bits != A->key_shift) return false;
-    }
+    if (A->nnzb == 0 || A->nnzb >= (1ull << 31) || ctx->H_total >= (1ull << 32)) return false;
+    int bits = 1;
+    while ((1ll << bits) < ctx->ndofs / 3 + 1) bits++;
+    return bits == A->key_shift;
+}
+bool assembly_locate_dynamic(sb_context* ctx)
+{
+    Assembly* A = ctx->assembly;
+    if (!assembly_locate_possible(ctx)) return false;
     // descriptors of the dynamic potentials (same numbering as the sort-based path: layout order, blk_off within the class)
     if (!A->h_descs) cudaMallocHost(&A->h_descs, 128 * sizeof(PotDesc));
     int nd = 0;
@@ -706,7 +710,7 @@ bool assembly_locate_dynamic(sb_context* ctx)
     }
     const size_t n = blk_off;
     cudaStream_t st = ctx->stream;
-    cudaMemsetAsync(ctx->d_scalars + 2, 0, sizeof(double), st);
+    if (A->miss_flag_dirty) { cudaMemsetAsync(ctx->d_scalars + 2, 0, sizeof(double), st); A->miss_flag_dirty = false; }   // (only a lookup that missed leaves it set)
     A->loc_n = n;
     A->loc_dynamic = ctx->dynamic_version;
     if (n == 0) return true;   // no dynamic element left: the pattern trivially holds every block
@@ -717,17 +721,23 @@ bool assembly_locate_dynamic(sb_context* ctx)
     k_dyn_locate_src<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(A->descs.p, nd, n, ctx->rows.p, A->rows.p, A->cols.p, A->nbr, A->d_final_of_src.p,
                                                                    A->D.src_off.p, A->D.src_pitch.p, ctx->d_scalars + 2);
     ctx->launches++;
-    // Speculatively, on a side stream: the numeric phase's scatter pass of this evaluation (valid if no block is missing, which
-    // is the common case; the host learns that with the evaluation's scalars).  It runs under the reductions and the sync.
-    if (!A->ev_loc) { cudaEventCreateWithFlags(&A->ev_loc, cudaEventDisableTiming); cudaEventCreateWithFlags(&A->ev_scatter, cudaEventDisableTiming); }
+    // Speculatively, right behind the lookup: the numeric phase's scatter pass of this evaluation (valid if no block is missing,
+    // which is the common case; the host learns that with the evaluation's scalars).  On the context stream: this stretch of the
+    // evaluation is bound by the host's API calls, the GPU has time to spare, and a side stream would cost three more calls.
     {
+        static const bool on_main = std::getenv("SB_SCATTER_MAIN") != nullptr;   // (experiment hook)
         const size_t keep_n = A->D.n;
         A->D.n = n;
-        cudaEventRecord(A->ev_loc, st);
-        cudaStreamWaitEvent(ctx->sym_stream, A->ev_loc, 0);
-        const int rs = scatter_pass(ctx, A, ctx->sym_stream);
-        cudaEventRecord(A->ev_scatter, ctx->sym_stream);
-        A->scatter_in_flight = true;
+        int rs;
+        if (on_main) rs = scatter_pass(ctx, A, st);
+        else {
+            if (!A->ev_loc) { cudaEventCreateWithFlags(&A->ev_loc, cudaEventDisableTiming); cudaEventCreateWithFlags(&A->ev_scatter, cudaEventDisableTiming); }
+            cudaEventRecord(A->ev_loc, st);
+            cudaStreamWaitEvent(ctx->sym_stream, A->ev_loc, 0);
+            rs = scatter_pass(ctx, A, ctx->sym_stream);
+            cudaEventRecord(A->ev_scatter, ctx->sym_stream);
+            A->scatter_in_flight = true;
+        }
         A->D.n = keep_n;
         A->scatter_done_eval = rs ? 0 : ctx->eval_id;
     }
@@ -738,7 +748,7 @@ void assembly_locate_result(sb_context* ctx, bool miss)
 {
     Assembly* A = ctx->assembly;
     if (!A || A->loc_dynamic != ctx->dynamic_version) return;
-    if (miss) { A->n_scatter_misses++; A->scatter_done_eval = 0; return; }   // (the sort-based symbolic phase runs at the next assembly)
+    if (miss) { A->n_scatter_misses++; A->scatter_done_eval = 0; A->miss_flag_dirty = true; return; }   // (the sort-based symbolic phase runs at the next assembly)
     A->n_scatter_hits++;
     A->D.n = A->loc_n;
     A->built_dynamic = ctx->dynamic_version;
@@ -748,6 +758,19 @@ void assembly_locate_result(sb_context* ctx, bool miss)
 
 // dynamic contributions of one numeric pass into the FP64 hash table (all sources, every pass: a pass after a PD projection
 // re-sums only dirty blocks, and those see the projected elements' new values)
+__global__ void k_scatter_clear(uint8_t* __restrict__ has_dyn, size_t n_blocks, int32_t* __restrict__ hkeys, double* __restrict__ hacc, size_t cap)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // 16 flags, then (if in range) one key and its nine accumulators per thread
+    if (16 * i < n_blocks) {
+        if (16 * i + 16 <= n_blocks) *reinterpret_cast<uint4*>(has_dyn + 16 * i) = make_uint4(0, 0, 0, 0);
+        else for (size_t b = 16 * i; b < n_blocks; b++) has_dyn[b] = 0;
+    }
+    if (i < cap) {
+        hkeys[i] = -1;
+        for (int k = 0; k < 9; k++) hacc[9 * i + k] = 0.0;
+    }
+}
 static int scatter_pass(sb_context* ctx, Assembly* A, cudaStream_t st)
 {
     const size_t n_src = A->D.n;
@@ -755,10 +778,12 @@ static int scatter_pass(sb_context* ctx, Assembly* A, cudaStream_t st)
     while (cap < 2 * n_src) cap <<= 1;
     A->hkeys.ensure(cap); A->hacc.ensure(9 * cap); A->has_dyn.ensure(A->nnzb + 1);
     A->hcap = cap;
-    SB_CUDA(ctx, cudaMemsetAsync(A->has_dyn.p, 0, A->nnzb + 1, st));
+    {
+        const size_t n_clear = std::max((A->nnzb + 1 + 15) / 16, n_src > 0 ? cap : (size_t)0);
+        k_scatter_clear<<<(unsigned)((n_clear + 255) / 256), 256, 0, st>>>(A->has_dyn.p, A->nnzb + 1, A->hkeys.p, A->hacc.p, n_src > 0 ? cap : 0);
+        ctx->launches++;
+    }
     if (n_src > 0) {
-        SB_CUDA(ctx, cudaMemsetAsync(A->hkeys.p, 0xff, cap * sizeof(int32_t), st));
-        SB_CUDA(ctx, cudaMemsetAsync(A->hacc.p, 0, 9 * cap * sizeof(double), st));
         k_scatter_dynamic<<<(unsigned)std::min<size_t>((n_src + 31) / 32, 148 * 4), SC_THREADS, 0, st>>>(ctx->H.p, A->d_final_of_src.p, A->D.src_off.p, A->D.src_pitch.p, n_src,
                                                                                                        A->hkeys.p, A->hacc.p, (uint32_t)(cap - 1), A->has_dyn.p);
         ctx->launches++;

@@ -388,6 +388,7 @@ static int pgh_static_part(sb_context* ctx, bool beside_detection)
             if (big != (pass == 0)) continue;
             cudaStream_t st = ctx->stream;
             if (!big) {
+                // (measured: one side stream for the pre-launched small potentials -- fewer joins -- is slower than spreading them)
                 const int k = next_side++ % sb_context::N_SIDE;
                 if (!(ctx->st_side_mask & (1u << k))) { SB_CUDA(ctx, cudaStreamWaitEvent(ctx->side[k], ctx->ev_fork, 0)); ctx->st_side_mask |= 1u << k; }
                 st = ctx->side[k];
@@ -474,19 +475,37 @@ int eval_internal(sb_context* ctx, int mode, double* out_E, double* out_grad_inf
         ctx->n_projected = 0;
         ctx->eval_id++;
         projector_prepare(ctx);
+        const double te1 = eval_dump ? now_ms() : 0.0;
         unsigned side_mask = ctx->st_side_mask;
         int next_side = ctx->st_next_side;
         bool forked = false;
         unsigned dyn_mask = 0;
         bool dyn_all_small = true;
+        // the contact / friction tables go into ONE launch on the context stream (k_eval_pgh_multi); what is not eligible for
+        // it (24-DoF elements, very large tables) is launched on its own as before
+        static const bool no_multi = std::getenv("SB_NO_MULTI_PGH") != nullptr;   // diagnostic hook
+        MultiGArgs* MG = nullptr;
+        int mg_ctas = 0;
         for (auto& p : ctx->potentials) {
             if (!p.dynamic || p.n_elem == 0) continue;
             int r = refresh_slots(ctx, p);
             if (r) return r;
+            if (!no_multi && p.n_elem < SMALL_POTENTIAL && p.k->p_kind >= 0) {
+                const int ctas = multi_g_ctas(p.k->p_kind, p.n_elem);
+                if (ctas > 0 && (!MG || MG->n < MULTI_G_MAX)) {
+                    if (!MG) { MG = &ctx->multi_g; MG->n = 0; MG->pad = 0; }
+                    MG->kind[MG->n] = p.k->p_kind; MG->cta0[MG->n] = mg_ctas; MG->it[MG->n] = make_args(ctx, p);
+                    MG->n++;
+                    mg_ctas += ctas;
+                    continue;
+                }
+            }
             cudaStream_t st = ctx->stream;
             if (p.n_elem < SMALL_POTENTIAL) {
                 if (!forked) { SB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream)); forked = true; }   // (behind the detection that wrote the tables)
-                const int k = next_side++ % sb_context::N_SIDE;
+                // (two side streams for the contact / friction tables: this stretch of the evaluation is bound by the HOST's API
+                //  calls -- every further stream costs a wait, a record and a join -- not by these few-microsecond kernels)
+                const int k = next_side++ % 2;
                 if (!(dyn_mask & (1u << k))) { SB_CUDA(ctx, cudaStreamWaitEvent(ctx->side[k], ctx->ev_fork, 0)); dyn_mask |= 1u << k; }
                 st = ctx->side[k];
             } else dyn_all_small = false;
@@ -496,10 +515,23 @@ int eval_internal(sb_context* ctx, int mode, double* out_E, double* out_grad_inf
         }
         // The symbolic phase of the coming assembly depends on the dynamic potentials' block rows only: the helper thread issues
         // it (its own stream, behind these kernels) while this thread goes on with the reductions.
-        const bool prefetch = dyn_mask && dyn_all_small;
-        if (prefetch)
+        if (MG) {
+            launch_pgh_multi(*MG, mg_ctas, ctx->stream);
+            ctx->launches++;
+            timeline_point(ctx->stream, "contact / friction tables (one launch)");
+        }
+        const double te2 = eval_dump ? now_ms() : 0.0;
+        // (the sort-based symbolic phase is only prefetched when the scatter-mode lookup cannot run: first assembly, stale pattern)
+        const bool prefetch = (dyn_mask || MG) && dyn_all_small && !(sync_scalars && assembly_locate_possible(ctx));
+        unsigned pf_mask = dyn_mask;
+        if (prefetch) {
             for (int k = 0; k < sb_context::N_SIDE; k++)
                 if (dyn_mask & (1u << k)) SB_CUDA(ctx, cudaEventRecord(ctx->ev_dyn[k], ctx->side[k]));
+            if (MG) {   // (the multi-potential launch sits on the context stream: its event takes the slot of the last side stream, which the dynamic potentials never use)
+                SB_CUDA(ctx, cudaEventRecord(ctx->ev_dyn[sb_context::N_SIDE - 1], ctx->stream));
+                pf_mask |= 1u << (sb_context::N_SIDE - 1);
+            }
+        }
         side_mask |= dyn_mask;
         if (ctx->bulk_pending) { SB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_bulk, 0)); ctx->bulk_pending = false; }
         for (int k = 0; k < sb_context::N_SIDE; k++)
@@ -509,16 +541,19 @@ int eval_internal(sb_context* ctx, int mode, double* out_E, double* out_grad_inf
             }
         SB_CUDA(ctx, cudaGetLastError());
         timeline_point(ctx->stream, "eval: joined");
+        const double te3 = eval_dump ? now_ms() : 0.0;
         // changed contact tables: do all their blocks exist in the assembled pattern?  (answer rides with the scalars below)
         const bool located = sync_scalars && assembly_locate_dynamic(ctx);
+        const double te4 = eval_dump ? now_ms() : 0.0;
         reduce_sum_and_absmax(ctx, ctx->E_elem.p, E_total, ctx->grad.p, ctx->ndofs, ctx->d_scalars);
         timeline_point(ctx->stream, "eval: reduced");
+        if (eval_dump) fprintf(stderr, "EVALDUMP2 layout=%.1f dyn_launch=%.1f join=%.1f locate=%.1f reduce=%.1f us\n", 1e3 * (te1 - td1), 1e3 * (te2 - te1), 1e3 * (te3 - te2), 1e3 * (te4 - te3), 1e3 * (now_ms() - te4));
         ctx->have_pgh = true;
         if (sync_scalars) SB_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         ctx->locate_pending = located;
         // issued LAST: the ~20 launches of the symbolic phase take the host a while, and the reductions must already be queued
         // (not when the scatter-mode lookup is under way: the symbolic phase is only needed if that reports a missing block)
-        if (prefetch && !located) assembly_prefetch_symbolic(ctx, dyn_mask);
+        if (prefetch && !located) assembly_prefetch_symbolic(ctx, pf_mask);
     } else {
         // ---- energy only (line-search trials after a backtrack) ----
         recompute_dof_offsets(ctx);

@@ -29,16 +29,16 @@ __device__ __forceinline__ void pair_from_index(int p, int& i, int& j)
     j = p - r * (r + 1) / 2;
 }
 
-template<class Pot>
-__global__ void __launch_bounds__(Geo<Pot>::BLOCK) k_eval_pgh(const EvalArgs a)
+// body of the P+G+H evaluation of one CTA's elements; BLOCK threads take part (the kernel may have more), G = BLOCK / L elements
+template<class Pot, int BLOCK>
+__device__ __forceinline__ void eval_pgh_body(const EvalArgs& a, int cta, double* s_in)
 {
-    constexpr int N = Pot::N_DOF, L = Geo<Pot>::L, G = Geo<Pot>::G, NIN = Pot::N_IN, NB = Pot::NB, BLOCK = Geo<Pot>::BLOCK;
-    __shared__ double s_in[G * NIN];
+    constexpr int N = Pot::N_DOF, L = Geo<Pot>::L, G = BLOCK / L, NIN = Pot::N_IN, NB = Pot::NB;
     const int tid = threadIdx.x;
-    const int e_base = blockIdx.x * G;
+    const int e_base = cta * G;
 
     // cooperative gather of G elements' inputs
-    for (int idx = tid; idx < G * NIN; idx += BLOCK) {
+    for (int idx = tid; idx < G * NIN; idx += blockDim.x) {
         const int el = idx / NIN, slot = idx - el * NIN;
         const int e = e_base + el;
         if (e < a.n_elem) {
@@ -73,6 +73,12 @@ __global__ void __launch_bounds__(Geo<Pot>::BLOCK) k_eval_pgh(const EvalArgs a)
         a.rows[(size_t)e * NB + p] = b.dof_offset / 3 + ce[b.conn_col];
     }
     if (p == 0) a.E_elem[e] = r.v;
+}
+template<class Pot>
+__global__ void __launch_bounds__(Geo<Pot>::BLOCK) k_eval_pgh(const EvalArgs a)
+{
+    __shared__ double s_in[Geo<Pot>::G * Pot::N_IN];
+    eval_pgh_body<Pot, Geo<Pot>::BLOCK>(a, blockIdx.x, s_in);
 }
 
 // energy only (line-search evaluations): the same cooperative gather (all loads of a CTA's elements in flight together --
@@ -227,6 +233,63 @@ void launch_p_multi(const MultiPArgs& M, int total_ctas, cudaStream_t s)
     k_eval_p_multi<<<total_ctas, 128, 0, s>>>(M);
 }
 
+// ---- the contact and friction tables of one P+G+H evaluation in ONE launch ----
+// Seven to thirty-five potentials with a few hundred elements each: launched one by one (a launch, a fetch-table refresh and a
+// share of the fork / join events each) they cost the host ~5 us apiece in the stretch between the collision detection and the
+// evaluation's reductions, where nothing hides it.  Same scheme as k_eval_p_multi; potentials whose lane count exceeds the
+// block (24-DoF elements: 300 lanes) keep their own kernel.
+#define SB_TABLE_POTS(X) \
+    X(contact_d_d_pt_pp) X(contact_d_d_pt_pe) X(contact_d_d_pt_pt) X(contact_d_d_ee_pp) X(contact_d_d_ee_pe) X(contact_d_d_ee_ee) \
+    X(contact_rb_rb_pt_pp) X(contact_rb_rb_pt_pe) X(contact_rb_rb_pt_pt) X(contact_rb_rb_ee_pp) X(contact_rb_rb_ee_pe) X(contact_rb_rb_ee_ee) \
+    X(contact_rb_d_pt_pp) X(contact_rb_d_pt_pe) X(contact_rb_d_pt_pt) X(contact_rb_d_pt_ep) X(contact_rb_d_pt_tp) \
+    X(contact_rb_d_ee_pp) X(contact_rb_d_ee_pe) X(contact_rb_d_ee_ee) X(contact_rb_d_ee_ep) \
+    X(friction_d_d_pp) X(friction_d_d_pe) X(friction_d_d_pt) X(friction_d_d_ee) \
+    X(friction_rb_rb_pp) X(friction_rb_rb_pe) X(friction_rb_rb_pt) X(friction_rb_rb_ee) \
+    X(friction_rb_d_pp) X(friction_rb_d_pe) X(friction_rb_d_pt) X(friction_rb_d_ee) X(friction_rb_d_ep) X(friction_rb_d_tp)
+constexpr int MULTI_G_BLOCK = 256;
+template<class Pot> struct MultiGOk { static constexpr bool value = Geo<Pot>::L <= MULTI_G_BLOCK; };
+template<class Pot> constexpr int multi_g_smem() { return MultiGOk<Pot>::value ? (MULTI_G_BLOCK / Geo<Pot>::L) * Pot::N_IN : 0; }
+constexpr int multi_g_smem_max()
+{
+    int m = 0;
+#define X(S) m = multi_g_smem<sbpot::S>() > m ? multi_g_smem<sbpot::S>() : m;
+    SB_TABLE_POTS(X)
+#undef X
+    return m;
+}
+template<class Pot, bool OK = MultiGOk<Pot>::value> struct MultiGBody {
+    static __device__ __forceinline__ void run(const EvalArgs& a, int cta, double* s_in) { eval_pgh_body<Pot, MULTI_G_BLOCK>(a, cta, s_in); }
+};
+template<class Pot> struct MultiGBody<Pot, false> { static __device__ __forceinline__ void run(const EvalArgs&, int, double*) {} };
+__global__ void __launch_bounds__(MULTI_G_BLOCK) k_eval_pgh_multi(const __grid_constant__ MultiGArgs M)
+{
+    __shared__ double s_in[multi_g_smem_max()];
+    int i = 0;
+    while (i + 1 < M.n && (int)blockIdx.x >= M.cta0[i + 1]) i++;
+    const EvalArgs& a = M.it[i];
+    const int cta = blockIdx.x - M.cta0[i];
+    switch (M.kind[i]) {
+#define X(S) case PK_##S: MultiGBody<sbpot::S>::run(a, cta, s_in); break;
+    SB_TABLE_POTS(X)
+#undef X
+    default: break;
+    }
+}
+// CTAs an eligible potential needs in the multi-potential launch (0: not eligible)
+int multi_g_ctas(int p_kind, int n_elem)
+{
+    switch (p_kind) {
+#define X(S) case PK_##S: return MultiGOk<sbpot::S>::value ? (n_elem + (MULTI_G_BLOCK / Geo<sbpot::S>::L) - 1) / (MULTI_G_BLOCK / Geo<sbpot::S>::L) : 0;
+    SB_TABLE_POTS(X)
+#undef X
+    default: return 0;
+    }
+}
+void launch_pgh_multi(const MultiGArgs& M, int total_ctas, cudaStream_t s)
+{
+    k_eval_pgh_multi<<<total_ctas, MULTI_G_BLOCK, 0, s>>>(M);
+}
+
 }  // namespace sb
 #include "tet_analytic.cuh"
 namespace sb {
@@ -322,6 +385,7 @@ void preload_eval_kernels()
 #undef X
     cudaFuncAttributes fa;
     cudaFuncGetAttributes(&fa, k_eval_p_multi);
+    cudaFuncGetAttributes(&fa, k_eval_pgh_multi);
     cudaFuncGetAttributes(&fa, k_tet_analytic<true, true>); cudaFuncGetAttributes(&fa, k_tet_analytic<true, false>);
     cudaFuncGetAttributes(&fa, k_tet_analytic<false, true>); cudaFuncGetAttributes(&fa, k_tet_analytic<false, false>);
     cudaFuncGetAttributes(&fa, k_tet_energy<true, true>); cudaFuncGetAttributes(&fa, k_tet_energy<true, false>);

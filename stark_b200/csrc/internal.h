@@ -58,6 +58,11 @@ struct KernelInfo {
 struct MultiPItem { const FetchSlot* slots; const int32_t* conn; double* E_elem; int conn_stride, n_elem, kind, cta0; };
 constexpr int MULTI_P_MAX = 64;
 struct MultiPArgs { int n; int pad; MultiPItem it[MULTI_P_MAX]; };
+// one launch for the P+G+H evaluation of the contact / friction tables (eval.cu)
+constexpr int MULTI_G_MAX = 40;
+struct MultiGArgs { int n; int pad; int kind[MULTI_G_MAX]; int cta0[MULTI_G_MAX]; EvalArgs it[MULTI_G_MAX]; };
+int multi_g_ctas(int p_kind, int n_elem);
+void launch_pgh_multi(const MultiGArgs& M, int total_ctas, cudaStream_t s);
 int multi_p_ctas(int p_kind, int n_elem);
 void launch_p_multi(const MultiPArgs& M, int total_ctas, cudaStream_t s);
 const KernelInfo* find_kernel(const char* name);
@@ -68,6 +73,7 @@ void projector_prepare(sb_context* ctx);
 void preload_assembly_kernels();
 void assembly_prefetch_symbolic(sb_context* ctx, unsigned side_mask);   // assembly.cu: symbolic phase ahead of time, issued by the helper thread behind ev_dyn[k] of the side streams in the mask
 void assembly_prefetch_drain(sb_context* ctx);
+bool assembly_locate_possible(sb_context* ctx);
 bool assembly_locate_dynamic(sb_context* ctx);              // assembly.cu, scatter mode: can the current pattern absorb the changed contact tables?
 void assembly_locate_result(sb_context* ctx, bool miss);
 const std::vector<KernelInfo>& all_kernels();
@@ -229,6 +235,7 @@ struct sb_context {
     uint64_t pgh_state = 0, pgh_dynamic = 0, pgh_static = 0;
     double pgh_E = 0.0, pgh_residual = 0.0;
     // first half of a P+G+H evaluation (the static potentials) launched ahead of the collision detection (eval_prelaunch_static)
+    sb::MultiGArgs multi_g;        // staging of the multi-potential P+G+H launch (6 KB: not on the stack of every evaluation)
     bool locate_pending = false;   // a scatter-mode pattern lookup rides with this evaluation's scalars
     bool pre_valid = false;
     uint64_t pre_state = 0, pre_static = 0;
@@ -280,6 +287,7 @@ struct DirtyView {
 };
 bool assembly_dirty_view(sb_context* ctx, DirtyView* v);
 int project_internal(sb_context* ctx, double grad_threshold, double eps, int mirror, int64_t* out_n_projected, int64_t* out_n_hessians, int* out_all_projected);
+int project_selection_bounds(sb_context* ctx, double* out_m, double* out_gmin);   // project.cu: when does a falling PPN threshold select something new?
 int solve_pcg_internal(sb_context* ctx, double abs_tol, double rel_tol, int max_iter, int stop_on_indef, int* out_iterations, int* out_ok, double* out_du_dot_grad, double* out_du_inf);
 // contact hooks used by the Newton driver (contact.cu)
 int contact_update_internal(sb_context* ctx);

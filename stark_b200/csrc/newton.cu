@@ -123,6 +123,8 @@ extern "C" int sb_newton_solve(sb_context* ctx, const sb_newton_settings* S, sb_
         int64_t n_proj = 0, n_hess = 0;
         bool have_prev = false;      // a solve of this iteration's current matrix has already been made (and did not give a descent direction)
         int prev_ok = 0, prev_cg_it = 0;
+        bool have_bounds = false;    // bound_m / bound_gmin describe the current projection flags (see project_selection_bounds)
+        double bound_m = 0.0, bound_gmin = 0.0;
         while (!solved) {
             bool all_projected = false;
             const int64_t n_proj_before = n_proj;
@@ -146,7 +148,19 @@ extern "C" int sb_newton_solve(sb_context* ctx, const sb_newton_settings* S, sb_
             case PProgressive:
                 if (ppn_threshold > 0.0) {
                     if (ppn_threshold < 1e-12) ppn_threshold = 0.0;
-                    if ((rc = project_internal(ctx, ppn_threshold, S->projection_eps, S->project_to_pd_use_mirroring, &n_proj, &n_hess, &allp))) return rc;
+                    if (have_bounds && ppn_threshold > bound_m) {
+                        // a threshold that is still above every unprojected element's largest block gradient selects nothing: the
+                        // reference projects, assembles and solves again with an unchanged matrix; here the round is only counted
+                        allp = (ppn_threshold <= bound_gmin) ? 1 : 0;
+                    } else {
+                        if ((rc = project_internal(ctx, ppn_threshold, S->projection_eps, S->project_to_pd_use_mirroring, &n_proj, &n_hess, &allp))) return rc;
+                        if (n_proj != n_proj_before) have_bounds = false;
+                        else if (!have_bounds && ppn_threshold > 0.0 && assembled) {
+                            // nothing selected: find out how far the threshold has to fall (instead of one launch + sync per halving)
+                            if ((rc = project_selection_bounds(ctx, &bound_m, &bound_gmin))) return rc;
+                            have_bounds = true;
+                        }
+                    }
                     all_projected = (allp != 0); projected_now = true;
                 }
                 break;

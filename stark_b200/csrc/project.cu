@@ -75,6 +75,28 @@ __global__ void k_select(const ProjTable* __restrict__ Tp, const int32_t* __rest
     }
 }
 
+// How far does the PPN threshold have to fall before the selection changes?  m = max over not-yet-projected elements of the largest
+// |g_b|_inf of their blocks (a threshold above m selects nothing); g_min = min over all blocks of |g_b|_inf (at or below it every block
+// is active: "all projected").  Non-negative doubles compare like their bit patterns, so integer atomics do.
+__global__ void k_selection_bounds(const ProjTable* __restrict__ Tp, const int32_t* __restrict__ rows_all, const double* __restrict__ grad, const uint8_t* __restrict__ projected,
+                                   unsigned long long n_elem_total, int nbr, unsigned long long* __restrict__ out /* [0] m bits, [1] g_min bits */)
+{
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_elem_total && !projected[i]) {
+        const ProjTable& T = *Tp;
+        const int pi = find_pot(T, i);
+        const int nb = T.nb[pi];
+        const int32_t* r = rows_all + T.rows_off[pi] + (i - T.E_off[pi]) * nb;
+        double m = 0.0;
+        for (int b = 0; b < nb; b++) { const int row = r[b]; m = fmax(m, fmax(fabs(grad[3 * row]), fmax(fabs(grad[3 * row + 1]), fabs(grad[3 * row + 2])))); }
+        atomicMax(out, (unsigned long long)__double_as_longlong(m));
+    }
+    if (i < (unsigned long long)nbr) {
+        const double m = fmax(fabs(grad[3 * i]), fmax(fabs(grad[3 * i + 1]), fabs(grad[3 * i + 2])));
+        atomicMin(out + 1, (unsigned long long)__double_as_longlong(m));
+    }
+}
+
 // One GROUP of G lanes per selected element, 32 / G elements per warp, all groups of a warp in LOCKSTEP (one control flow per
 // warp: groups that are done or idle run on with identity rotations, so __syncwarp() stays legal and nothing serialises):
 //  0. TRANSLATION-INVARIANT potentials (strain, bending, deformable-deformable contact / friction / attachments: the energy
@@ -418,6 +440,8 @@ struct Projector {
     int* d_counts = nullptr;   // [0] n_list, [1] n_changed, [2] n_inactive
     int* h_counts = nullptr;
     size_t smem_configured = 0;
+    unsigned long long* d_bounds = nullptr;   // project_selection_bounds
+    unsigned long long* h_bounds = nullptr;
 };
 void projector_destroy(sb_context* ctx)
 {
@@ -427,6 +451,8 @@ void projector_destroy(sb_context* ctx)
     if (P->d_table) cudaFree(P->d_table);
     if (P->d_counts) cudaFree(P->d_counts);
     if (P->h_counts) cudaFreeHost(P->h_counts);
+    if (P->d_bounds) cudaFree(P->d_bounds);
+    if (P->h_bounds) cudaFreeHost(P->h_bounds);
     delete P;
     ctx->projector = nullptr;
 }
@@ -542,6 +568,37 @@ int project_internal(sb_context* ctx, double grad_threshold, double eps, int mir
     if (ctx->profile) { ctx->stage_calls[ST_PROJ_SELECTED] += P.h_counts[0]; ctx->stage_calls[ST_PROJ_CHANGED] += P.h_counts[1]; ctx->stage_calls[ST_PROJ_SWEEPS] += P.h_counts[3]; }
     if (out_n_projected) *out_n_projected = ctx->n_projected;
     if (out_all_projected) *out_all_projected = use_active ? (P.h_counts[2] == 0) : 1;
+    return 0;
+}
+
+// See k_selection_bounds.  Valid for the projection flags as they are now (call it right after a projection that selected nothing).
+// out_m < 0: every element is projected already.
+int project_selection_bounds(sb_context* ctx, double* out_m, double* out_gmin)
+{
+    Projector* Pp = ctx->projector;
+    if (!Pp || !Pp->table_valid || !ctx->have_pgh) return fail(ctx, SB_ERR_STATE, "project_selection_bounds: no projection has run on this evaluation");
+    Projector& P = *Pp;
+    cudaStream_t st = ctx->stream;
+    if (!P.d_bounds) { SB_CUDA(ctx, cudaMalloc(&P.d_bounds, 2 * sizeof(unsigned long long))); SB_CUDA(ctx, cudaMallocHost(&P.h_bounds, 2 * sizeof(unsigned long long))); }
+    P.h_bounds[0] = 0ull; P.h_bounds[1] = ~0ull;   // sentinels the kernel can only raise / lower (pinned: the copy is asynchronous)
+    SB_CUDA(ctx, cudaMemcpyAsync(P.d_bounds, P.h_bounds, 2 * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+    const unsigned long long n_elem = ctx->n_hessians;
+    const int nbr = ctx->ndofs / 3;
+    const unsigned long long n = std::max<unsigned long long>(n_elem, (unsigned long long)nbr);
+    // "no unprojected element" must be told apart from m == 0: count them through the sign of a separate launch-free trick --
+    // the kernel raises out[0] from 0 only for unprojected elements with m > 0; elements with a zero gradient cannot be told from
+    // none, and both mean the same for the caller (no positive threshold selects anything new)
+    k_selection_bounds<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P.d_table, ctx->rows.p, ctx->grad.p, ctx->projected.p, n_elem, nbr, P.d_bounds);
+    ctx->launches++;
+    SB_CUDA(ctx, cudaMemcpyAsync(P.h_bounds, P.d_bounds, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    SB_CUDA(ctx, cudaStreamSynchronize(st));
+    SB_CUDA(ctx, cudaGetLastError());
+    long long mb = (long long)P.h_bounds[0], gb = (long long)P.h_bounds[1];
+    double m, g;
+    std::memcpy(&m, &mb, sizeof(double)); std::memcpy(&g, &gb, sizeof(double));
+    if (P.h_bounds[1] == ~0ull) g = 0.0;
+    *out_m = m;
+    *out_gmin = g;
     return 0;
 }
 
