@@ -5,9 +5,9 @@ element evaluation, PD projection, assembly, linear solve and line search).
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 A "step" is one simulation time step (stark::Simulation::run_one_time_step): the Newton solve of that step is the hot
-path.  Workload at N = 1: BASELINE.json configs[1] -- 26^3 tet grid (210,912 tets, Soft_Rubber stable Neo-Hookean)
-dropped on a fixed rigid floor with IPC contact and friction.  For N > 1 every rank runs its own replica of the scene
-(the path does not shard below one scene at this size -- DESIGN.md "Multi-GPU") and `value` is the aggregate.
+path.  Workload at N = 1: BASELINE.json configs[1] (C2) -- 26^3 tet grid (210,912 tets, Soft_Rubber stable Neo-Hookean)
+dropped on a fixed rigid floor with IPC contact and friction; `--config C1|C3|C4|C5` runs the other BASELINE configurations
+(both arms).  For N > 1 every rank runs its own replica of the scene and `value` is the aggregate (DESIGN.md "Multi-GPU").
 
 Printed keys (one JSON line on rank 0):
   value   Newton iterations / s with the state resident in HBM: sum(iterations) / sum(device time of the solves, CUDA events)
@@ -28,21 +28,31 @@ sys.path.insert(0, ROOT)
 
 METRIC = "newton_iterations_per_second"
 UNIT = "Newton it/s"
-GRID_N = 26            # 26^3 hexahedra x 12 tets = 210,912 tets (BASELINE.json configs[1])
 TET_BYTES = 1632       # algorithmic bytes of one EnergyTetStrain element in PGH mode
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_tet_analytic launch at GRID_N = 26 from the `ncu --set full` capture
-# committed as profiles/r1_ncu_full_tet_assembly.csv (8.70 MB read + 199.07 MB written; gathers hit L2, the tail of the
-# Hessian stream is still in L2 when the kernel ends)
-TET_DRAM_TRAFFIC_NCU = 207.8e6
+
+# BASELINE.json configs (SURVEY.md section 8, table of concrete instantiations).  The driver's default is C2 (the configuration
+# the metric is quoted on); the others are run by hand (`--config C5`) and recorded under profiles/.
+CONFIGS = {
+    "C1": dict(scene="cloth", n=32, ny=-1, nz=-1, steps=40, warmup=5,
+               workload="C1 cloth: 32x32 Cotton_Fabric surface grid (triangle strain + flat bending) over a scripted fixed rigid box, IPC contact d=2mm, dt=10ms, PPN+BDPCG defaults"),
+    "C2": dict(scene="tetdrop", n=26, ny=-1, nz=-1, steps=30, warmup=5,
+               workload="C2 tetdrop: 26^3 Soft_Rubber tet grid (12 tets/hex) on a fixed rigid floor, IPC contact d=1mm k_min=1e8 mu=0.5, dt=10ms, PPN+BDPCG defaults"),
+    "C3": dict(scene="cloth_shells", n=256, ny=-1, nz=-1, steps=4, warmup=3,
+               workload="C3 cloth: 256x256 Cotton_Fabric grid with discrete-shell hinges over a scripted fixed rigid box, IPC contact d=2mm, friction mu=0.3, dt=10ms, PPN+BDPCG defaults"),
+    "C4": dict(scene="tetchain", n=16, ny=10, nz=-1, steps=20, warmup=5,
+               workload="C4 tetchain: 16^3 tet grid (49,152 tets, bottom face prescribed) under a chain of 10 hinged rigid boxes, IPC contact + friction mu=0.3, dt=10ms, PPN+BDPCG defaults"),
+    "C5": dict(scene="tetbar", n=22, ny=22, nz=172, steps=10, warmup=3,
+               workload="C5 tetbar: 22x22x172 Soft_Rubber tet bar (998,976 tets), end caps prescribed, one cap turning 90 deg/s, no contact, dt=10ms, PPN+BDPCG defaults"),
+}
 
 
-def workload_config(n_gpus, grid=GRID_N):
-    name = "C2 tetdrop" if grid == GRID_N else "tetdrop (reduced grid: NOT the benchmark configuration)"
-    return {"workload": f"{name}: {grid}^3 Soft_Rubber tet grid (12 tets/hex) on a fixed rigid floor, IPC contact d=1mm k_min=1e8 mu=0.5, dt=10ms, PPN+BDPCG defaults",
-            "tets": 12 * grid ** 3, "grid": grid, "dt": 0.01,
+def workload_config(n_gpus, name, cfg, grid=None):
+    n = grid if grid else cfg["n"]
+    reduced = grid is not None and grid != cfg["n"]
+    return {"workload": cfg["workload"] if not reduced else f"{cfg['scene']} at a reduced grid {n} (NOT the benchmark configuration)",
+            "name": name, "scene": cfg["scene"], "grid": n, "dt": 0.01,
             "parallelism": "single GPU" if n_gpus == 1 else f"{n_gpus} independent replicas (one scene per GPU)",
-            "l2_policy": ("working set per evaluation (~350 MB element outputs) exceeds the 126 MB L2" if grid == GRID_N
-                          else f"working set per evaluation ~{12 * grid ** 3 * 1632 / 1e6:.0f} MB")}
+            "l2_policy": "the element outputs written and read by every evaluation (1,152 B per tet / hinge) exceed the 126 MB L2 at the C2, C3 and C5 sizes; C1 and C4 are L2-resident (latency-bound scenes)"}
 
 
 class ClockSampler:
@@ -79,16 +89,23 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
-def reference_cmd(steps, warmup, grid=GRID_N):
+def reference_cmd(cfg, steps, warmup, grid=None, llt=False):
     driver = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
     codegen = f"/tmp/stark_ref_codegen_{os.getuid()}"   # JIT cache of the reference on THIS machine (its kernels use -march=native)
-    return driver, [driver, "--scene", "tetdrop", "--n", str(grid), "--bench", "--steps", str(steps), "--warmup", str(warmup), "--codegen", codegen,
-                    "--threads", str(os.cpu_count() or 1)]
+    cmd = [driver, "--scene", cfg["scene"], "--n", str(grid if grid else cfg["n"]), "--bench", "--steps", str(steps), "--warmup", str(warmup), "--codegen", codegen,
+           "--threads", str(os.cpu_count() or 1)]
+    if cfg["ny"] > 0:
+        cmd += ["--ny", str(cfg["ny"])]
+    if cfg["nz"] > 0:
+        cmd += ["--nz", str(cfg["nz"])]
+    if llt:
+        cmd += ["--llt"]
+    return driver, cmd
 
 
-def run_reference(steps, warmup, grid=GRID_N):
+def run_reference(cfg, steps, warmup, grid=None, llt=False):
     """The UNMODIFIED reference (oracle/_ref/ref_driver, built from /root/reference by oracle/Makefile.ref) on the host cores."""
-    driver, cmd = reference_cmd(steps, warmup, grid)
+    driver, cmd = reference_cmd(cfg, steps, warmup, grid, llt)
     if not os.path.exists(driver):
         return None
     env = dict(os.environ, CXX="/usr/bin/g++")
@@ -102,13 +119,19 @@ def run_reference(steps, warmup, grid=GRID_N):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="stark_b200")
-    ap.add_argument("--grid", type=int, default=GRID_N)
+    ap.add_argument("--config", default="C2", choices=sorted(CONFIGS), help="BASELINE.json configuration (default C2: the one the metric is quoted on)")
+    ap.add_argument("--grid", type=int, default=None, help="override the grid size (diagnostic: NOT the benchmark configuration)")
+    ap.add_argument("--llt", action="store_true", help="DirectLLT instead of the default BDPCG (both arms; reference: Eigen SimplicialLLT, ours: dense blocked Cholesky, <= 32k DoFs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--stage-steps", type=int, default=4, help="extra (untimed) steps run with stage profiling on after the timed region; 0 = off")
     args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    steps = args.steps if args.steps is not None else cfg["steps"]
+    warmup = max(args.warmup if args.warmup is not None else cfg["warmup"], 3)
+    grid = args.grid if args.grid else cfg["n"]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -117,21 +140,23 @@ def main():
         if rank != 0:
             return 0
         # the same window of time steps as the stark_b200 arm (same warm-up rule), bounded so that the run ends within minutes
-        ref_steps = max(1, min(args.steps, 200))
-        ref_warmup = max(args.warmup, 3)
-        r = run_reference(ref_steps, ref_warmup, args.grid)
+        ref_steps = max(1, min(steps, 200))
+        r = run_reference(cfg, ref_steps, warmup, args.grid, args.llt)
         if r is None:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_driver has not been built (oracle/Makefile.ref)"}))
             return 0
         v = r["newton_it_per_s"]
-        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": ref_steps, "warmup": ref_warmup,
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": ref_steps, "warmup": warmup,
                 "ms_per_step": 1e3 * r["wall_s"] / max(1, r["steps"]), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic", "config": workload_config(1, args.grid), "newton_iterations": r["newton_iterations"],
-                "cpu_baseline": {"value": v, "unit": UNIT, "cores": r["threads"], "kind": "reference", "sample": f"{ref_steps} time steps of the same scene after {ref_warmup} warm-up steps (unmodified reference, all host threads)"},
+                "data": "synthetic", "config": workload_config(1, args.config, cfg, args.grid), "newton_iterations": r["newton_iterations"],
+                "accepted_steps": r.get("accepted_steps"), "cg_iterations": r.get("cg_iterations"), "linear_solver": "DirectLLT" if args.llt else "BDPCG",
+                "cpu_baseline": {"value": v, "unit": UNIT, "cores": r["threads"], "kind": "reference",
+                                 "sample": f"{ref_steps} time steps of the same scene after {warmup} warm-up steps (unmodified reference, all host threads)"},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
 
+    import ctypes as C
     import torch
     import torch.distributed as dist
     from stark_b200 import capi, scenes
@@ -142,7 +167,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     stream = torch.cuda.Stream()
-    sc = scenes.Scene("tetdrop", n=args.grid, dt=0.01, drop=0.003, device=local_rank, stream=stream.cuda_stream)
+    sc = scenes.Scene(cfg["scene"], n=grid, ny=cfg["ny"], nz=cfg["nz"], dt=0.01, drop=0.003, device=local_rank, stream=stream.cuda_stream, llt=args.llt)
 
     def barrier():
         sbdist.barrier(torch.device("cuda", local_rank))
@@ -150,7 +175,7 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warmup):
         sc.step()
     t0 = sc.totals()
     barrier()
@@ -159,7 +184,7 @@ def main():
     wall0 = time.perf_counter()
     its = evals = cg = accepted = 0
     solve_gpu_ms = 0.0
-    for _ in range(args.steps):
+    for _ in range(steps):
         s = sc.step()
         its += int(s["newton_iterations"]); evals += int(s["evaluations"]); cg += int(s["cg_iterations"]); accepted += int(s["accepted"])
         solve_gpu_ms += s["solve_gpu_ms"]
@@ -179,40 +204,22 @@ def main():
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant kernel: EnergyTetStrain P+grad+Hessian element evaluation, timed alone (CUDA events) ----
-    ctx_handle = sc.lib.sbh_scene_context(sc.h)
-    roof = None
-    try:
-        import ctypes as C
-        lib = capi.load()
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else None
-        peak = peaks["hbm_gbs"] if peaks else 6650.0
-        E, g = C.c_double(), C.c_double()
-        lib.sb_eval(C.c_void_p(ctx_handle), 2, C.byref(E), C.byref(g))
-        pot = int(sc.lib.sbh_scene_potential(sc.h, b"EnergyTetStrain"))
-        ms = C.c_double()
-        lib.sb_profile_potential(C.c_void_p(ctx_handle), pot, 2, 3, C.byref(ms))       # warm-up
-        lib.sb_profile_potential(C.c_void_p(ctx_handle), pot, 2, 20, C.byref(ms))
-        n_tets = int(t1["tets"])
-        achieved = TET_BYTES * n_tets / (ms.value * 1e-3) / 1e9
-        roof = {"kernel": "EnergyTetStrain element evaluation (P + grad + dense 12x12 Hessian)", "bound": "hbm", "achieved": achieved, "peak": peak,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)", "unit": "GB/s", "frac": achieved / peak,
-                "traffic": TET_DRAM_TRAFFIC_NCU if args.grid == GRID_N else None, "traffic_source": "ncu --set full, profiles/r1_ncu_full_tet_assembly.csv", "launch_ms": ms.value, "algorithmic_bytes_per_launch": TET_BYTES * n_tets}
-    except Exception as e:   # the line must still print
-        roof = {"error": repr(e)}
+    ctx_handle = C.c_void_p(sc.lib.sbh_scene_context(sc.h))
+    lib = capi.load()
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else None
+    peak = peaks["hbm_gbs"] if peaks else 6650.0
+    peak_source = "MEASURED_PEAKS.json hbm_gbs (burst: kernels timed alone / inside their own launch)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
 
     # ---- per-stage breakdown (diagnostic, outside the timed region): extra steps with a stream sync at every stage boundary ----
     stages = None
     if args.stage_steps > 0:
         try:
-            import ctypes as C
-            lib = capi.load()
-            lib.sb_profile_stages(C.c_void_p(ctx_handle), 1)
+            lib.sb_profile_stages(ctx_handle, 1)
             it_s = 0
             for _ in range(args.stage_steps):
                 it_s += int(sc.step()["newton_iterations"])
-            rep = lib.sb_profile_report(C.c_void_p(ctx_handle)).decode()
-            lib.sb_profile_stages(C.c_void_p(ctx_handle), 0)
+            rep = lib.sb_profile_report(ctx_handle).decode()
+            lib.sb_profile_stages(ctx_handle, 0)
             stages = {"steps": args.stage_steps, "newton_iterations": it_s}
             for ln in rep.splitlines():
                 name, ms, calls = ln.split()
@@ -220,28 +227,69 @@ def main():
         except Exception as e:
             stages = {"error": repr(e)}
 
-    # ---- CPU baseline: the unmodified reference on this box's host cores, bounded sample ----
+    # ---- rooflines, both measured live in this run ----
+    # (1) element evaluation: the EnergyTetStrain P + grad + Hessian kernel timed alone with CUDA events on the context stream
+    # (2) the PCG kernel: in-kernel timers of the iteration loop (global timer, read in the kernel; stage steps above) over the
+    #     algorithmic bytes of one iteration (nnzb 40 + 8 (nbr + 1) + 156 ndofs)
+    kernels = []
+    try:
+        n_tets = int(t1["tets"])
+        if n_tets > 0 and not args.llt:
+            E, g = C.c_double(), C.c_double()
+            lib.sb_eval(ctx_handle, 2, C.byref(E), C.byref(g))
+            pot = int(sc.lib.sbh_scene_potential(sc.h, b"EnergyTetStrain"))
+            ms = C.c_double()
+            lib.sb_profile_potential(ctx_handle, pot, 2, 3, C.byref(ms))       # warm-up
+            lib.sb_profile_potential(ctx_handle, pot, 2, 20, C.byref(ms))
+            achieved = TET_BYTES * n_tets / (ms.value * 1e-3) / 1e9
+            kernels.append({"kernel": "k_tet_analytic: EnergyTetStrain element evaluation (P + grad + dense 12x12 Hessian)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                            "peak_source": peak_source, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                            "traffic_note": "dram__bytes of this kernel are not measurable inside a bench run; the ncu --set full capture of the same launch is profiles/r2_ncu_kernels.csv",
+                            "launch_ms": ms.value, "algorithmic_bytes_per_launch": TET_BYTES * n_tets,
+                            "how": "20 launches alone on the context stream between two CUDA events; working set per launch exceeds L2 at the C2 / C5 sizes"})
+    except Exception as e:   # the line must still print
+        kernels.append({"kernel": "k_tet_analytic", "error": repr(e)})
+    try:
+        if stages and "cg_iterations" in stages and stages["cg_iterations"]["calls"] > 0:
+            nbr, nnzb = C.c_int(), C.c_int64()
+            lib.sb_bcsr_info(ctx_handle, C.byref(nbr), C.byref(nnzb))
+            ndofs = int(t1["ndofs"])
+            bytes_it = 40 * nnzb.value + 8 * (nbr.value + 1) + 156 * ndofs
+            us_it = 1e3 * stages["cg_iterations"]["ms"] / stages["cg_iterations"]["calls"]
+            achieved = bytes_it / (us_it * 1e-6) / 1e9
+            kernels.append({"kernel": "k_pcg_solve: one block-Jacobi PCG iteration (SpMV from the resident / streamed 3x3-BCSR + vector phase + 2 grid barriers)", "bound": "hbm",
+                            "achieved": achieved, "peak": peak, "peak_source": peak_source, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                            "us_per_iteration": us_it, "algorithmic_bytes_per_iteration": bytes_it, "iterations_timed": stages["cg_iterations"]["calls"],
+                            "how": "the kernel's own %globaltimer around its iteration loop, summed over the stage-profiled steps (one launch per solve)"})
+    except Exception as e:
+        kernels.append({"kernel": "k_pcg_solve", "error": repr(e)})
+    roof = dict(kernels[0]) if kernels and "error" not in kernels[0] else {"error": "no roofline kernel in this configuration"}
+    roof["kernels"] = kernels
+
+    # ---- CPU baseline: the unmodified reference on this box's host cores, bounded sample of the same window ----
     cpu = None
     if not args.no_cpu_baseline and args.gpus == 1:
         try:
-            n_cpu = max(1, min(args.steps, 12))
-            r = run_reference(n_cpu, max(args.warmup, 3), args.grid)
+            n_cpu = max(1, min(steps, 12))
+            r = run_reference(cfg, n_cpu, warmup, args.grid, args.llt)
             if r is not None:
                 cpu = {"value": r["newton_it_per_s"], "unit": UNIT, "cores": r["threads"], "kind": "reference",
-                       "sample": f"{n_cpu} time steps of the same scene after {max(args.warmup, 3)} warm-up steps (unmodified reference, all host threads)",
-                       "newton_iterations": r["newton_iterations"], "wall_s": r["wall_s"]}
+                       "sample": f"the first {n_cpu} of the window's time steps after the same {warmup} warm-up steps (unmodified reference, all host threads; the full window is what `--impl reference` times)",
+                       "newton_iterations": r["newton_iterations"], "accepted_steps": r.get("accepted_steps"), "wall_s": r["wall_s"]}
         except Exception as e:
             cpu = {"error": repr(e)}
 
-    steps_total = args.steps
     line = {
-        "metric": METRIC, "value": its_all / (solve_gpu_ms * 1e-3), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": e2e_ms / steps_total, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.gpus, args.grid),
+        "metric": METRIC, "value": its_all / (solve_gpu_ms * 1e-3), "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": e2e_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus, args.config, cfg, args.grid),
+        "value_note": "Newton iterations / device time of the steps' Newton path (CUDA events on the context stream from the start-of-step collision detection to the end of the solve), state resident in HBM",
         "e2e": {"value": its_all / (e2e_ms * 1e-3), "unit": UNIT,
-                "h2d_bytes_per_step": (t1["h2d_bytes"] - t0["h2d_bytes"]) / steps_total, "d2h_bytes_per_step": (t1["d2h_bytes"] - t0["d2h_bytes"]) / steps_total},
+                "h2d_bytes_per_step": (t1["h2d_bytes"] - t0["h2d_bytes"]) / steps, "d2h_bytes_per_step": (t1["d2h_bytes"] - t0["d2h_bytes"]) / steps,
+                "note": "through stark_b200::Simulation::run_one_time_step: per-step uploads of whatever host state changed (scripted boundary data, rigid-body state), read-back of the new positions / velocities into the pinned host mirrors and of the rigid DoFs"},
         "gpu_launches": int(t1["launches"] - t0["launches"]),
-        "newton_iterations": its_all, "evaluations": evals_all, "cg_iterations": cg_all, "accepted_steps_rank0": accepted, "wall_s_rank0": wall_s,
+        "newton_iterations": its_all, "evaluations": evals_all, "cg_iterations": cg_all, "accepted_steps": accepted, "wall_s_rank0": wall_s,
+        "linear_solver": "DirectLLT" if args.llt else "BDPCG",
         "solve_gpu_ms_per_iteration": solve_gpu_ms / max(1.0, its_all / world),
         "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "stages": stages,
     }

@@ -235,6 +235,10 @@ typedef struct sb_newton_stats {
     double residuals[64];      /* residual of every evaluation (first 64) */
     double gpu_ms;             /* device time of the solve: CUDA events on the context stream around the whole call */
 } sb_newton_stats;
+/* Optional: start the device clock of the next sb_newton_solve NOW (stats.gpu_ms then also covers what is submitted between this
+ * call and the solve: the start-of-step collision detection, a pre-launched evaluation).  Without it the clock starts at the
+ * solve's entry. */
+SB_API int sb_newton_timer_begin(sb_context* ctx);
 SB_API void sb_newton_default_settings(sb_newton_settings* s);   /* STARK's defaults (S/core/Settings.cpp:40-54) */
 SB_API int sb_newton_solve(sb_context* ctx, const sb_newton_settings* settings, sb_newton_stats* stats);
 

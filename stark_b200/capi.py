@@ -80,7 +80,7 @@ SYMBOLS = [
     "sb_contact_init", "sb_contact_add_mesh", "sb_contact_blacklist", "sb_contact_set_friction", "sb_contact_set_params",
     "sb_contact_update", "sb_contact_update_friction", "sb_contact_begin_time_step", "sb_contact_count_intersections", "sb_contact_get_proximity",
     "sb_contact_get_vertices", "sb_contact_set_vertices", "sb_contact_detect", "sb_contact_potential",
-    "sb_newton_default_settings", "sb_newton_solve", "sb_profile_potential",
+    "sb_newton_timer_begin", "sb_newton_default_settings", "sb_newton_solve", "sb_profile_potential",
     "sb_profile_stages", "sb_profile_report",
 ]
 

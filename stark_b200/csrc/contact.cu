@@ -1208,7 +1208,7 @@ static int detect(sb_context* ctx, Contact* C, int mode, double enlargement)
         }
         SB_CUDA(ctx, cudaMemcpyAsync(C->h_counters, C->counters.p, 64 * sizeof(int), cudaMemcpyDeviceToHost, st));
         if (mode == 0 || mode == 4 || mode == 5) SB_CUDA(ctx, cudaMemcpyAsync(C->h_hash, C->hash.p, 2 * N_CONTACT_TABLES * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-        SB_CUDA(ctx, cudaStreamSynchronize(st));
+        SB_CUDA(ctx, hot_sync(ctx));
         SB_CUDA(ctx, cudaGetLastError());
         if (ctx->profile) for (int k = 0; k < 3; k++) { ctx->stage_calls[ST_TILE_PAIRS_PT + k] += C->h_counters[4 + k]; ctx->stage_calls[ST_CAND_PT + k] += C->h_counters[k]; }
         if (!C->h_counters[3]) break;

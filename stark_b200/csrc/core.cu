@@ -140,6 +140,19 @@ void Issuer::stop()
     if (th.joinable()) th.join();
 }
 
+// The hot path's host synchronisations (detection counts, evaluation scalars, projection counts, PCG result): SB_SPIN_SYNC=1
+// polls an event instead of calling cudaStreamSynchronize (which may block / yield depending on the context's scheduling flags)
+cudaError_t hot_sync(sb_context* ctx)
+{
+    static const bool spin = std::getenv("SB_SPIN_SYNC") != nullptr;
+    if (!spin) return cudaStreamSynchronize(ctx->stream);
+    if (!ctx->ev_sync) cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventDisableTiming);
+    cudaError_t e = cudaEventRecord(ctx->ev_sync, ctx->stream);
+    if (e != cudaSuccess) return e;
+    while ((e = cudaEventQuery(ctx->ev_sync)) == cudaErrorNotReady) {}
+    return e;
+}
+
 // writers of device arrays are ordered behind asynchronous downloads still in flight (sb_array_download_async)
 void order_after_async_downloads(sb_context* ctx)
 {
@@ -615,7 +628,7 @@ int eval_internal(sb_context* ctx, int mode, double* out_E, double* out_grad_inf
     const double td3 = td2;
     if (!sync_scalars) ctx->issuer->wait();   // (the helper thread's job reads the potentials: it ends inside this call)
     if (sync_scalars) {
-        SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        SB_CUDA(ctx, hot_sync(ctx));
         ctx->issuer->wait();
         if (eval_dump) fprintf(stderr, "EVALDUMP mode=%d static=%.1f issue=%.1f prefetch=%.1f sync=%.1f us\n", mode, 1e3 * (td1 - td0), 1e3 * (td2 - td1), 1e3 * (td3 - td2), 1e3 * (now_ms() - td3));
         if (out_E) *out_E = ctx->h_scalars[0];
@@ -744,6 +757,7 @@ void sb_destroy(sb_context* ctx)
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); cudaEventDestroy(ctx->ev_copy_src); cudaEventDestroy(ctx->ev_copy_done); }
     if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
     if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
+    if (ctx->ev_sync) cudaEventDestroy(ctx->ev_sync);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

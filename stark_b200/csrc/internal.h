@@ -193,6 +193,8 @@ struct sb_context {
     cudaStream_t side[N_SIDE] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[N_SIDE] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;   // sb_newton_solve's timing events
+    cudaEvent_t ev_sync = nullptr;                  // hot_sync
+    bool timer_started = false;                     // sb_newton_timer_begin has recorded ev_t0 for the coming solve
     cudaStream_t sym_stream = nullptr;              // the helper thread's stream (symbolic phase of the assembly)
     cudaEvent_t ev_dyn[N_SIDE] = {nullptr, nullptr, nullptr, nullptr};   // "the dynamic potentials' kernels on this side stream are done"
     sb::Issuer* issuer = nullptr;
@@ -261,6 +263,7 @@ struct sb_context {
 namespace sb {
 int fail(sb_context* ctx, int code, const std::string& msg);
 void order_after_async_downloads(sb_context* ctx);
+cudaError_t hot_sync(sb_context* ctx);
 int check_cuda(sb_context* ctx, cudaError_t e, const char* what);
 #define SB_CUDA(ctx, call) do { int _r = sb::check_cuda((ctx), (call), #call); if (_r) return _r; } while (0)
 int recompute_dof_offsets(sb_context* ctx);

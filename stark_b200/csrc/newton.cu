@@ -54,6 +54,15 @@ extern "C" void sb_newton_default_settings(sb_newton_settings* s)
     s->intersection_test_enabled = 1;
 }
 
+extern "C" int sb_newton_timer_begin(sb_context* ctx)
+{
+    if (!ctx) return SB_ERR_ARG;
+    if (!ctx->ev_t0) { cudaEventCreate(&ctx->ev_t0); cudaEventCreate(&ctx->ev_t1); }
+    SB_CUDA(ctx, cudaEventRecord(ctx->ev_t0, ctx->stream));
+    ctx->timer_started = true;
+    return SB_OK;
+}
+
 extern "C" int sb_newton_solve(sb_context* ctx, const sb_newton_settings* S, sb_newton_stats* stats)
 {
     if (!ctx || !S || !stats) return fail(ctx, SB_ERR_ARG, "sb_newton_solve: bad argument");
@@ -86,7 +95,8 @@ extern "C" int sb_newton_solve(sb_context* ctx, const sb_newton_settings* S, sb_
     stats->result = Running;
     if (!ctx->ev_t0) { cudaEventCreate(&ctx->ev_t0); cudaEventCreate(&ctx->ev_t1); }
     cudaEvent_t ev0 = ctx->ev_t0, ev1 = ctx->ev_t1;
-    cudaEventRecord(ev0, ctx->stream);
+    if (!ctx->timer_started) cudaEventRecord(ev0, ctx->stream);   // (sb_newton_timer_begin started the clock earlier)
+    ctx->timer_started = false;
     timeline_mark(ctx, -1);
     static const bool no_spec = std::getenv("SB_NO_SPECULATION") != nullptr;   // diagnostic hook
     // the static potentials of the first evaluation do not depend on the contact tables: their kernels are launched before the

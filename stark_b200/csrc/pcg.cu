@@ -966,7 +966,7 @@ int solve_pcg_internal(sb_context* ctx, double abs_tol, double rel_tol, int max_
     SB_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_pcg_solve, dim3(P->grid), dim3(PCG_THREADS), args, smem_launch, st));
     ctx->launches += 1;
     SB_CUDA(ctx, cudaMemcpyAsync(P->h_result, P->d_result, sizeof(PcgResult), cudaMemcpyDeviceToHost, st));
-    SB_CUDA(ctx, cudaStreamSynchronize(st));
+    SB_CUDA(ctx, hot_sync(ctx));
     SB_CUDA(ctx, cudaGetLastError());
     if (dump) {
         const int G = P->grid;

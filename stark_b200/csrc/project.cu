@@ -559,7 +559,7 @@ int project_internal(sb_context* ctx, double grad_threshold, double eps, int mir
     ctx->launches++;
     ctx->launches += 1;
     SB_CUDA(ctx, cudaMemcpyAsync(P.h_counts, P.d_counts, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    SB_CUDA(ctx, cudaStreamSynchronize(st));   // also protects the stack-resident table T
+    SB_CUDA(ctx, hot_sync(ctx));   // also protects the stack-resident table T
     SB_CUDA(ctx, cudaGetLastError());
     ctx->n_projected += P.h_counts[0];
     static const bool dump = std::getenv("SB_PROJ_DUMP") != nullptr;   // per-call diagnostics on stderr

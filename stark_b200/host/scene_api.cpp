@@ -133,6 +133,8 @@ __attribute__((visibility("default"))) void* sbh_scene_create(const char* name, 
     return sc;
 }
 __attribute__((visibility("default"))) void sbh_scene_destroy(void* h) { delete static_cast<Scene*>(h); }
+// settings.newton.linear_solver: 0 DirectLLT, 1 BDPCG (symx::LinearSolver, solver_utils.h)
+__attribute__((visibility("default"))) void sbh_scene_set_linear_solver(void* h, int kind) { static_cast<Scene*>(h)->sim->settings.newton.linear_solver = kind; }
 
 // out[0] keep_going, [1] accepted, [2] result, [3] newton its, [4] cg its, [5] evaluations, [6] dt, [7] runtime s, [8] solve s,
 // [9] first residual, [10] ls_inv, [11] ls_bt, [12] time, [13] ndofs, [14] contact stiffness, [15] device ms of the Newton solve

@@ -769,6 +769,7 @@ bool Simulation::run_one_time_step()
                            &rb_constraints.global_directions.d_loc,   // (scripted fix constraints rotate the LOCAL lock directions)
                            &rb_constraints.points.stiffness, &rb_constraints.directions.stiffness})
         upload(*a);
+    check(sb_newton_timer_begin(ctx), "sb_newton_timer_begin");   // (the step's device time covers the start-of-step detection and the pre-launched evaluation)
     if (settings.newton.contact_enabled) {
         check(sb_contact_set_params(ctx, contact.contact_stiffness, contact.global_params.friction_stick_slide_threshold, contact.global_params.triangle_point_enabled,
                                     contact.global_params.edge_edge_enabled, contact.global_params.friction_enabled), "sb_contact_set_params");

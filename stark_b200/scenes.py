@@ -29,6 +29,7 @@ def load():
         h.sbh_scene_array.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.c_int]
         h.sbh_scene_connectivity.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int32), C.c_int]
         h.sbh_scene_sync.argtypes = [C.c_void_p]
+        h.sbh_scene_set_linear_solver.argtypes = [C.c_void_p, C.c_int]
         h.sbh_scene_context.restype = C.c_void_p
         h.sbh_scene_context.argtypes = [C.c_void_p]
         _host = h
@@ -45,11 +46,13 @@ class Scene:
     'tetbar' (C5: prescribed twisted bar, no contact), 'tetchain' (C4: tet block + hinged chain of boxes), 'cloth' /
     'cloth_shells' (C1 / C3: n x n Cotton_Fabric grid over a scripted rigid box; flat-bending or discrete-shell hinges)."""
 
-    def __init__(self, name, n, ny=-1, nz=-1, dt=0.01, drop=0.003, vz=0.0, device=0, stream=None):
+    def __init__(self, name, n, ny=-1, nz=-1, dt=0.01, drop=0.003, vz=0.0, device=0, stream=None, llt=False):
         self.lib = load()
         self.h = self.lib.sbh_scene_create(name.encode(), n, ny, nz, dt, drop, vz, device, C.c_void_p(stream) if stream else None)
         if not self.h:
             raise capi.SBError(f"unknown scene {name}")
+        if llt:
+            self.lib.sbh_scene_set_linear_solver(self.h, 0)
 
     def step(self):
         out = (C.c_double * 16)()
