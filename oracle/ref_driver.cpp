@@ -86,6 +86,7 @@ struct Args
 	double vz = 0.0;     // initial downward speed (to reach contact quickly in small fixtures)
 	bool llt = false;
 	double inject = 1.0; // dump: injected DoF state v1 := inject * v0 + small deterministic noise
+	std::string trace = ""; // trace mode: one JSON line per time step (solver statistics + state) into this file
 };
 
 static Args parse(int argc, char** argv)
@@ -110,6 +111,7 @@ static Args parse(int argc, char** argv)
 		else if (s == "--verbose") a.verbose = true;
 		else if (s == "--llt") a.llt = true;
 		else if (s == "--inject") a.inject = std::stod(next());
+		else if (s == "--trace") a.trace = next();
 		else { std::cerr << "unknown arg " << s << "\n"; exit(2); }
 	}
 	return a;
@@ -801,6 +803,30 @@ int main(int argc, char** argv)
 		std::ofstream g(a.dump + "/next_step_stats.json");
 		g << "{\"newton_iterations\": " << stats.newton_iterations << ", \"cg_iterations\": " << stats.cg_iterations
 			<< ", \"ls_inv\": " << stats.ls_inv_iterations << ", \"ls_bt\": " << stats.ls_bt_iterations << "}\n";
+		return 0;
+	}
+
+	if (!a.trace.empty()) {
+		// trajectory trace: the same scene through two builds (the unmodified reference / the reference with the stark_b200
+		// NewtonsMethod linked in, integration/Makefile.shim) must agree step by step
+		std::ofstream f(a.trace);
+		f << std::setprecision(17);
+		for (int s = 0; s < a.steps; s++) {
+			const int step_before = st.current_time_step;
+			one_step(sim);
+			auto stats = st.newton->get_last_solve_stats();
+			auto& dyn = *sim.deformables->point_sets;
+			auto& rb = *sim.rigidbodies->rb;
+			double sx = 0.0, sx2 = 0.0, mx = 0.0;
+			for (int i = 0; i < dyn.size(); i++) for (int c = 0; c < 3; c++) { const double x = dyn.x0[i][c]; sx += x; sx2 += x * x; mx = std::max(mx, std::abs(x)); }
+			double rt = 0.0, rq = 0.0;
+			for (int i = 0; i < rb.get_n_bodies(); i++) { for (int c = 0; c < 3; c++) rt += (i + 1) * (c + 1) * rb.t0[i][c]; rq += (i + 1) * (rb.q0[i].w() + 2.0 * rb.q0[i].x() + 3.0 * rb.q0[i].y() + 4.0 * rb.q0[i].z()); }
+			f << "{\"step\": " << s << ", \"time\": " << st.current_time << ", \"accepted\": " << ((st.current_time_step > step_before) ? 1 : 0)
+				<< ", \"newton_iterations\": " << stats.newton_iterations << ", \"cg_iterations\": " << stats.cg_iterations
+				<< ", \"ls_inv\": " << stats.ls_inv_iterations << ", \"ls_bt\": " << stats.ls_bt_iterations
+				<< ", \"n_points\": " << dyn.size() << ", \"sum_x\": " << sx << ", \"sum_x2\": " << sx2 << ", \"max_abs_x\": " << mx
+				<< ", \"rigid_t\": " << rt << ", \"rigid_q\": " << rq << "}" << std::endl;
+		}
 		return 0;
 	}
 
