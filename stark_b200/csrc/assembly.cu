@@ -24,13 +24,6 @@
 
 namespace sb {
 
-struct PotDesc {
-    unsigned long long H_off;     // offset of the potential's element Hessians in ctx->H
-    unsigned long long rows_off;  // offset of its block rows in ctx->rows
-    unsigned long long blk_off;   // offset of its element blocks in the source numbering of its class (static / dynamic)
-    int n_elem, nb;
-};
-
 // one sorted-and-reduced class of sources (static or dynamic)
 struct SourceSet {
     size_t n = 0;                    // sources
@@ -101,6 +94,7 @@ struct Assembly {
     size_t hcap = 0;                   // slots (power of two)
     PotDesc* h_descs = nullptr;        // pinned staging of the dynamic potentials' descriptors
     size_t loc_n = 0;                  // dynamic sources of the last k_dyn_locate_src
+    size_t loc_cap = 0;                // fused path: sources the per-source arrays can hold
     uint64_t loc_dynamic = 0;          // ... and the table version it looked at
     long long n_scatter_hits = 0, n_scatter_misses = 0;
     cudaEvent_t ev_loc = nullptr, ev_scatter = nullptr;
@@ -110,6 +104,7 @@ struct Assembly {
 };
 
 static int scatter_pass(sb_context* ctx, Assembly* A, cudaStream_t st);
+__global__ void k_scatter_clear(uint8_t* __restrict__ has_dyn, size_t n_blocks, int32_t* __restrict__ hkeys, double* __restrict__ hacc, size_t cap);
 
 static Assembly* get(sb_context* ctx)
 {
@@ -272,12 +267,12 @@ __global__ void k_src_final(const uint32_t* __restrict__ blk_of_src, const uint3
 // Scatter mode, step 1 (behind the dynamic potentials' kernels of an evaluation): BCSR block of every dynamic source by a
 // binary search for its column inside its block row; a missing block raises *miss (a double: it rides with the evaluation's
 // scalars).  Also records where the source's 3x3 block lies in the element-Hessian store.
-__global__ void k_dyn_locate_src(const PotDesc* __restrict__ descs, int n_descs, size_t n_total, const int32_t* __restrict__ rows_all,
+__global__ void k_dyn_locate_src(const PotDesc* __restrict__ descs, int n_descs, size_t n_total, const DynTotals* __restrict__ tot, const int32_t* __restrict__ rows_all,
                                  const unsigned long long* __restrict__ row_ptr, const int32_t* __restrict__ cols, int nbr,
                                  uint32_t* __restrict__ d_final_of_src, uint32_t* __restrict__ src_off, uint8_t* __restrict__ src_pitch, double* __restrict__ miss)
 {
-    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n_total) return;
+    if (tot) { n_descs = tot->n_descs; n_total = tot->n_dyn_src; }   // (fused path: counts known on the device only)
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_total; g += (size_t)gridDim.x * blockDim.x) {
     int lo = 0, hi = n_descs - 1;   // last desc with blk_off <= g
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
@@ -305,6 +300,7 @@ __global__ void k_dyn_locate_src(const PotDesc* __restrict__ descs, int n_descs,
     }
     d_final_of_src[g] = f;
     if (f == 0xffffffffu) *miss = 1.0;
+  }
 }
 
 // Scatter mode, step 2 (numeric phase): every dynamic source adds its 3x3 block to the FP64 accumulators of its BCSR block in a
@@ -326,9 +322,10 @@ __device__ __forceinline__ void scatter_global(uint32_t f, int k, double v, int3
     atomicAdd(hacc + 9 * (size_t)slot + k, v);
 }
 __global__ void __launch_bounds__(SC_THREADS) k_scatter_dynamic(const double* __restrict__ H, const uint32_t* __restrict__ d_final_of_src, const uint32_t* __restrict__ src_off,
-                                  const uint8_t* __restrict__ src_pitch, size_t n_src, int32_t* __restrict__ hkeys, double* __restrict__ hacc,
+                                  const uint8_t* __restrict__ src_pitch, size_t n_src, const DynTotals* __restrict__ tot, int32_t* __restrict__ hkeys, double* __restrict__ hacc,
                                   uint32_t hmask, uint8_t* __restrict__ has_dyn)
 {
+    if (tot) { n_src = tot->n_dyn_src; if (2 * n_src > (size_t)hmask + 1) return; }   // (fused path; a table too small for the actual count: the host redoes the pass)
     __shared__ int32_t s_key[SC_SLOTS];
     __shared__ double s_acc[SC_SLOTS][9];
     for (int i = threadIdx.x; i < SC_SLOTS; i += SC_THREADS) s_key[i] = -1;
@@ -718,7 +715,7 @@ bool assembly_locate_dynamic(sb_context* ctx)
     A->descs.ensure(nd + 1);
     A->D.src_off.ensure(n + 1); A->D.src_pitch.ensure(n + 1); A->d_final_of_src.ensure(n + 1);
     cudaMemcpyAsync(A->descs.p, A->h_descs, nd * sizeof(PotDesc), cudaMemcpyHostToDevice, st);
-    k_dyn_locate_src<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(A->descs.p, nd, n, ctx->rows.p, A->rows.p, A->cols.p, A->nbr, A->d_final_of_src.p,
+    k_dyn_locate_src<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(A->descs.p, nd, n, nullptr, ctx->rows.p, A->rows.p, A->cols.p, A->nbr, A->d_final_of_src.p,
                                                                    A->D.src_off.p, A->D.src_pitch.p, ctx->d_scalars + 2);
     ctx->launches++;
     // Speculatively, right behind the lookup: the numeric phase's scatter pass of this evaluation (valid if no block is missing,
@@ -742,6 +739,72 @@ bool assembly_locate_dynamic(sb_context* ctx)
         A->scatter_done_eval = rs ? 0 : ctx->eval_id;
     }
     return true;
+}
+// ---- fused detection + evaluation: the same two steps with the sources' count and descriptors known on the device only ----
+bool assembly_locate_ready(sb_context* ctx)
+{
+    Assembly* A = ctx->assembly;
+    static const bool disabled = std::getenv("SB_NO_SCATTER") != nullptr;
+    if (disabled || !A || !A->numeric_valid || A->pf_pending || static_part_stale(ctx, A)) return false;
+    if (A->nnzb == 0 || A->nnzb >= (1ull << 31) || ctx->H.cap >= (1ull << 32)) return false;
+    int bits = 1;
+    while ((1ll << bits) < ctx->ndofs / 3 + 1) bits++;
+    return bits == A->key_shift;
+}
+PotDesc* assembly_descs_dev(sb_context* ctx, int n)
+{
+    Assembly* A = ctx->assembly;
+    A->descs.ensure(n + 1);
+    return A->descs.p;
+}
+size_t assembly_scatter_capacity(sb_context* ctx, size_t n_src_estimate)
+{
+    (void)ctx;
+    size_t cap = 1024;
+    while (cap < 2 * n_src_estimate) cap <<= 1;
+    return cap;
+}
+int assembly_locate_dynamic_dev(sb_context* ctx, const DynTotals* d_tot, size_t n_src_estimate)
+{
+    Assembly* A = ctx->assembly;
+    cudaStream_t st = ctx->stream;
+    if (A->miss_flag_dirty) { SB_CUDA(ctx, cudaMemsetAsync(ctx->d_scalars + 2, 0, sizeof(double), st)); A->miss_flag_dirty = false; }
+    const size_t n = std::max<size_t>(n_src_estimate, 1024);
+    A->D.src_off.ensure(n + 1); A->D.src_pitch.ensure(n + 1); A->d_final_of_src.ensure(n + 1);
+    A->loc_cap = std::min(std::min(A->D.src_off.cap, A->D.src_pitch.cap), A->d_final_of_src.cap);
+    k_dyn_locate_src<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(A->descs.p, 0, 0, d_tot, ctx->rows.p, A->rows.p, A->cols.p, A->nbr, A->d_final_of_src.p,
+                                                                                           A->D.src_off.p, A->D.src_pitch.p, ctx->d_scalars + 2);
+    ctx->launches++;
+    // speculative scatter pass on the side stream (capacity from the estimate; the kernel declines if the actual count does not fit)
+    if (!A->ev_loc) { cudaEventCreateWithFlags(&A->ev_loc, cudaEventDisableTiming); cudaEventCreateWithFlags(&A->ev_scatter, cudaEventDisableTiming); }
+    const size_t cap = assembly_scatter_capacity(ctx, n);
+    A->hkeys.ensure(cap); A->hacc.ensure(9 * cap); A->has_dyn.ensure(A->nnzb + 1);
+    A->hcap = cap;
+    SB_CUDA(ctx, cudaEventRecord(A->ev_loc, st));
+    SB_CUDA(ctx, cudaStreamWaitEvent(ctx->sym_stream, A->ev_loc, 0));
+    {
+        const size_t n_clear = std::max((A->nnzb + 1 + 15) / 16, cap);
+        k_scatter_clear<<<(unsigned)((n_clear + 255) / 256), 256, 0, ctx->sym_stream>>>(A->has_dyn.p, A->nnzb + 1, A->hkeys.p, A->hacc.p, cap);
+        k_scatter_dynamic<<<(unsigned)std::min<size_t>((n + 31) / 32, 148 * 4), SC_THREADS, 0, ctx->sym_stream>>>(ctx->H.p, A->d_final_of_src.p, A->D.src_off.p, A->D.src_pitch.p, 0, d_tot,
+                                                                                                               A->hkeys.p, A->hacc.p, (uint32_t)(cap - 1), A->has_dyn.p);
+        ctx->launches += 2;
+    }
+    SB_CUDA(ctx, cudaEventRecord(A->ev_scatter, ctx->sym_stream));
+    A->scatter_in_flight = true;
+    A->loc_dynamic = 0;   // (set by assembly_locate_result_dev: the table version is bumped when the tables are published)
+    return 0;
+}
+void assembly_locate_result_dev(sb_context* ctx, bool miss, size_t n_src, bool scatter_valid)
+{
+    Assembly* A = ctx->assembly;
+    A->scatter_done_eval = 0;
+    if (miss || n_src > A->loc_cap) { A->n_scatter_misses++; A->miss_flag_dirty = miss; return; }   // (sort-based symbolic phase at the next assembly)
+    A->n_scatter_hits++;
+    A->D.n = n_src;
+    A->built_dynamic = ctx->dynamic_version;
+    A->built_n_src = ctx->n_blocks_total;
+    A->scatter_mode = true;
+    if (scatter_valid && 2 * n_src <= A->hcap) A->scatter_done_eval = ctx->eval_id;
 }
 // ... and the answer, once the evaluation's scalars are on the host
 void assembly_locate_result(sb_context* ctx, bool miss)
@@ -784,7 +847,7 @@ static int scatter_pass(sb_context* ctx, Assembly* A, cudaStream_t st)
         ctx->launches++;
     }
     if (n_src > 0) {
-        k_scatter_dynamic<<<(unsigned)std::min<size_t>((n_src + 31) / 32, 148 * 4), SC_THREADS, 0, st>>>(ctx->H.p, A->d_final_of_src.p, A->D.src_off.p, A->D.src_pitch.p, n_src,
+        k_scatter_dynamic<<<(unsigned)std::min<size_t>((n_src + 31) / 32, 148 * 4), SC_THREADS, 0, st>>>(ctx->H.p, A->d_final_of_src.p, A->D.src_off.p, A->D.src_pitch.p, n_src, nullptr,
                                                                                                        A->hkeys.p, A->hacc.p, (uint32_t)(cap - 1), A->has_dyn.p);
         ctx->launches++;
     }

@@ -1142,86 +1142,96 @@ static int reorder_primitives(sb_context* ctx, Contact* C)
 
 // mode 0: proximity + contact tables; 1: proximity + friction tables; 2: intersections only; 3: proximity lists only + intersections;
 // 4: proximity + contact tables + intersections (a line-search trial: validity test and the tables of the evaluation that follows)
-static int detect(sb_context* ctx, Contact* C, int mode, double enlargement)
+// One detection = issue (all launches + the read-back of the counters, no synchronisation) -> [host sync] -> overflow check
+// (grow + run again) -> publish (table sizes to the potentials).  The three steps are separate so that sb_newton_solve can queue
+// the evaluation of the contact potentials BEHIND an issued detection and synchronise once for both (core.cu, fused path).
+// mode 0: proximity + contact tables; 1: proximity + friction tables; 2: intersections only; 3: proximity lists only + intersections;
+// 4: proximity + contact tables + intersections (a line-search trial: validity test and the tables of the evaluation that follows);
+// 5: 4 + friction tables (start of a time step)
+static int detect_issue(sb_context* ctx, Contact* C, int mode, double enlargement, bool defer_readback = false)
 {
     cudaStream_t st = ctx->stream;
-    if (C->reorder_countdown-- <= 0) { int r = reorder_primitives(ctx, C); if (r) return r; }
-    for (int attempt = 0; attempt < 8; attempt++) {
-        ensure_capacities(ctx, C);
-        Dev d = make_dev(ctx, C, mode == 0 || mode == 4 || mode == 5);   // (contact tables go to the back buffers, see Contact::table_back)
-        Dev d0 = d;   // the intersection pass's view: its own boxes
-        d0.bb_p = C->bb0_p.p; d0.bb_t = C->bb0_t.p; d0.bb_e = C->bb0_e.p; d0.tb_p = C->tb0_p.p; d0.tb_t = C->tb0_t.p; d0.tb_e = C->tb0_e.p;
-        const bool both = (mode == 3 || mode == 4 || mode == 5);
-        const int nmax = std::max(d.n_v, std::max(d.n_t, d.n_e));
-        // only the counters this mode rewrites are cleared (contact and friction tables live side by side): bit t = counters[t]
-        auto bits = [](int lo, int n) { unsigned long long m = 0; for (int t = lo; t < lo + n; t++) m |= 1ull << t; return m; };
-        unsigned long long clear = bits(0, 8);
-        if (mode == 0 || mode == 3 || mode == 4 || mode == 5) clear |= bits(8, 6) | bits(16, N_CONTACT_TABLES);
-        if (mode == 1 || mode == 5) clear |= bits(8, 6) | bits(16 + N_CONTACT_TABLES, N_FRICTION);
-        if (mode == 2 || mode == 3 || mode == 4 || mode == 5) clear |= bits(8 + 6, 1);
-        const int Tv = (d.n_v + TILE - 1) / TILE, Tt = (d.n_t + TILE - 1) / TILE, Te = (d.n_e + TILE - 1) / TILE;
-        auto broad_grid = [](long long n_tile_pairs) { return (int)std::max(1ll, std::min(n_tile_pairs, 148ll * 32)); };
-        (void)nmax;
-        if (mode != 2) {
-            const float extra = (float)enlargement + FLT_EPSILON;
-            const bool pt = C->enable_pt && d.n_t > 0 && d.n_v > 0, ee = C->enable_ee && d.n_e > 1;
-            const int n0 = pt ? Tv * Tt : 0, n1 = ee ? Te * Te : 0;
-            timeline_point(st, "detect: begin");
-            k_aabbs_tiles<<<Tv + Tt + Te, TILE, 0, st>>>(d, extra, 1, Tv, Tt, clear);
-            timeline_point(st, "detect: aabbs");
-            if (both) SB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));   // (the counters are cleared: the intersection pass may start)
-            if (n0 + n1 > 0) {
-                k_tile_pairs_all<<<(n0 + n1 + 255) / 256, 256, 0, st>>>(d, Tv, Tt, Te, n0, n1, 0);
-                if (pt && ee) k_broad_all<0, 1><<<broad_grid((long long)n0 + n1), TILE, 0, st>>>(d);
-                else if (pt) k_broad_all<0, -1><<<broad_grid(n0), TILE, 0, st>>>(d);
-                else k_broad_all<1, -1><<<broad_grid(n1), TILE, 0, st>>>(d);
-                const int emit_mode = (mode == 3) ? 2 : (mode == 4 ? 0 : (mode == 5 ? 3 : mode));   // 2 = lists only (no table matches mode 2 inside emit_*), 3 = contact + friction tables
-                timeline_point(st, "detect: broad");
-                k_narrow_all<<<148 * 2, 128, 0, st>>>(d, enlargement * enlargement, emit_mode, C->stiffness, 1e-30, pt ? 1 : 0, ee ? 1 : 0);
-                timeline_point(st, "detect: narrow");
-                ctx->launches += 3;
-            }
-            ctx->launches += 1;
-            clear = 0;   // (mode 3: the intersection pass below must not wipe what the proximity pass just counted)
+    ensure_capacities(ctx, C);
+    Dev d = make_dev(ctx, C, mode == 0 || mode == 4 || mode == 5);   // (contact tables go to the back buffers, see Contact::table_back)
+    Dev d0 = d;   // the intersection pass's view: its own boxes
+    d0.bb_p = C->bb0_p.p; d0.bb_t = C->bb0_t.p; d0.bb_e = C->bb0_e.p; d0.tb_p = C->tb0_p.p; d0.tb_t = C->tb0_t.p; d0.tb_e = C->tb0_e.p;
+    const bool both = (mode == 3 || mode == 4 || mode == 5);
+    const int nmax = std::max(d.n_v, std::max(d.n_t, d.n_e));
+    // only the counters this mode rewrites are cleared (contact and friction tables live side by side): bit t = counters[t]
+    auto bits = [](int lo, int n) { unsigned long long m = 0; for (int t = lo; t < lo + n; t++) m |= 1ull << t; return m; };
+    unsigned long long clear = bits(0, 8);
+    if (mode == 0 || mode == 3 || mode == 4 || mode == 5) clear |= bits(8, 6) | bits(16, N_CONTACT_TABLES);
+    if (mode == 1 || mode == 5) clear |= bits(8, 6) | bits(16 + N_CONTACT_TABLES, N_FRICTION);
+    if (mode == 2 || mode == 3 || mode == 4 || mode == 5) clear |= bits(8 + 6, 1);
+    const int Tv = (d.n_v + TILE - 1) / TILE, Tt = (d.n_t + TILE - 1) / TILE, Te = (d.n_e + TILE - 1) / TILE;
+    auto broad_grid = [](long long n_tile_pairs) { return (int)std::max(1ll, std::min(n_tile_pairs, 148ll * 32)); };
+    (void)nmax;
+    if (mode != 2) {
+        const float extra = (float)enlargement + FLT_EPSILON;
+        const bool pt = C->enable_pt && d.n_t > 0 && d.n_v > 0, ee = C->enable_ee && d.n_e > 1;
+        const int n0 = pt ? Tv * Tt : 0, n1 = ee ? Te * Te : 0;
+        timeline_point(st, "detect: begin");
+        k_aabbs_tiles<<<Tv + Tt + Te, TILE, 0, st>>>(d, extra, 1, Tv, Tt, clear);
+        timeline_point(st, "detect: aabbs");
+        if (both) SB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));   // (the counters are cleared: the intersection pass may start)
+        if (n0 + n1 > 0) {
+            k_tile_pairs_all<<<(n0 + n1 + 255) / 256, 256, 0, st>>>(d, Tv, Tt, Te, n0, n1, 0);
+            if (pt && ee) k_broad_all<0, 1><<<broad_grid((long long)n0 + n1), TILE, 0, st>>>(d);
+            else if (pt) k_broad_all<0, -1><<<broad_grid(n0), TILE, 0, st>>>(d);
+            else k_broad_all<1, -1><<<broad_grid(n1), TILE, 0, st>>>(d);
+            const int emit_mode = (mode == 3) ? 2 : (mode == 4 ? 0 : (mode == 5 ? 3 : mode));   // 2 = lists only (no table matches mode 2 inside emit_*), 3 = contact + friction tables
+            timeline_point(st, "detect: broad");
+            k_narrow_all<<<148 * 2, 128, 0, st>>>(d, enlargement * enlargement, emit_mode, C->stiffness, 1e-30, pt ? 1 : 0, ee ? 1 : 0);
+            timeline_point(st, "detect: narrow");
+            ctx->launches += 3;
         }
-        if (mode == 2 || mode == 3 || mode == 4 || mode == 5) {
-            // The intersection pass has its own boxes, tile-pair list, candidate list and counters: next to a proximity pass it
-            // runs on a side stream at the same time (both are chains of latency-bound kernels).
-            const float extra = 0.0f + FLT_EPSILON;   // IntersectionDetection uses non-enlarged AABBs (tmcd/BroadPhaseET.cpp:38)
-            cudaStream_t s2 = both ? ctx->side[0] : st;
-            if (both) SB_CUDA(ctx, cudaStreamWaitEvent(s2, ctx->ev_fork, 0));
-            k_aabbs_tiles<<<Tv + Tt + Te, TILE, 0, s2>>>(d0, extra, 0, Tv, Tt, clear);
-            ctx->launches++;
-            if (d.n_e > 0 && d.n_t > 0) {
-                k_tile_pairs_all<<<(Te * Tt + 255) / 256, 256, 0, s2>>>(d0, Tv, Tt, Te, 0, Te * Tt, 1);
-                k_broad_all<2, -1><<<broad_grid((long long)Te * Tt), TILE, 0, s2>>>(d0);
-                ctx->launches += 2;
-            }
-            timeline_point(s2, "detect: et broad");
-            k_narrow_et<<<148, 128, 0, s2>>>(d0);
-            timeline_point(s2, "detect: et narrow");
-            ctx->launches++;
-            if (both) {
-                SB_CUDA(ctx, cudaEventRecord(ctx->ev_join[0], s2));
-                SB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join[0], 0));
-            }
-        }
-        SB_CUDA(ctx, cudaMemcpyAsync(C->h_counters, C->counters.p, 64 * sizeof(int), cudaMemcpyDeviceToHost, st));
-        if (mode == 0 || mode == 4 || mode == 5) SB_CUDA(ctx, cudaMemcpyAsync(C->h_hash, C->hash.p, 2 * N_CONTACT_TABLES * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-        SB_CUDA(ctx, hot_sync(ctx));
-        SB_CUDA(ctx, cudaGetLastError());
-        if (ctx->profile) for (int k = 0; k < 3; k++) { ctx->stage_calls[ST_TILE_PAIRS_PT + k] += C->h_counters[4 + k]; ctx->stage_calls[ST_CAND_PT + k] += C->h_counters[k]; }
-        if (!C->h_counters[3]) break;
-        // overflow: grow whatever was too small and run again
-        const int mc = std::max(C->h_counters[0], std::max(C->h_counters[1], C->h_counters[2]));
-        if (mc > C->cand_cap) C->cand_cap = mc + mc / 2;
-        int ml = 0, mt = 0;
-        for (int l = 0; l < N_LISTS; l++) ml = std::max(ml, C->h_counters[8 + l]);
-        for (int t = 0; t < N_TABLES; t++) mt = std::max(mt, C->h_counters[16 + t]);
-        if (ml > C->list_cap) C->list_cap = ml + ml / 2;
-        if (mt > C->table_cap) C->table_cap = mt + mt / 2;
-        if (attempt == 7) return fail(ctx, SB_ERR_STATE, "contact detection: buffers keep overflowing");
+        ctx->launches += 1;
+        clear = 0;   // (mode 3: the intersection pass below must not wipe what the proximity pass just counted)
     }
+    if (mode == 2 || mode == 3 || mode == 4 || mode == 5) {
+        // The intersection pass has its own boxes, tile-pair list, candidate list and counters: next to a proximity pass it
+        // runs on a side stream at the same time (both are chains of latency-bound kernels).
+        const float extra = 0.0f + FLT_EPSILON;   // IntersectionDetection uses non-enlarged AABBs (tmcd/BroadPhaseET.cpp:38)
+        cudaStream_t s2 = both ? ctx->side[0] : st;
+        if (both) SB_CUDA(ctx, cudaStreamWaitEvent(s2, ctx->ev_fork, 0));
+        k_aabbs_tiles<<<Tv + Tt + Te, TILE, 0, s2>>>(d0, extra, 0, Tv, Tt, clear);
+        ctx->launches++;
+        if (d.n_e > 0 && d.n_t > 0) {
+            k_tile_pairs_all<<<(Te * Tt + 255) / 256, 256, 0, s2>>>(d0, Tv, Tt, Te, 0, Te * Tt, 1);
+            k_broad_all<2, -1><<<broad_grid((long long)Te * Tt), TILE, 0, s2>>>(d0);
+            ctx->launches += 2;
+        }
+        timeline_point(s2, "detect: et broad");
+        k_narrow_et<<<148, 128, 0, s2>>>(d0);
+        timeline_point(s2, "detect: et narrow");
+        ctx->launches++;
+        if (both) {
+            SB_CUDA(ctx, cudaEventRecord(ctx->ev_join[0], s2));
+            SB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join[0], 0));
+        }
+    }
+    if (defer_readback) return 0;   // (fused path: the counters travel to the host in one copy with the evaluation's results)
+    SB_CUDA(ctx, cudaMemcpyAsync(C->h_counters, C->counters.p, 64 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (mode == 0 || mode == 4 || mode == 5) SB_CUDA(ctx, cudaMemcpyAsync(C->h_hash, C->hash.p, 2 * N_CONTACT_TABLES * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+// after the synchronisation: true = something overflowed, capacities have been grown, the detection must run again
+static bool detect_overflowed(sb_context* ctx, Contact* C)
+{
+    if (ctx->profile) for (int k = 0; k < 3; k++) { ctx->stage_calls[ST_TILE_PAIRS_PT + k] += C->h_counters[4 + k]; ctx->stage_calls[ST_CAND_PT + k] += C->h_counters[k]; }
+    if (!C->h_counters[3]) return false;
+    const int mc = std::max(C->h_counters[0], std::max(C->h_counters[1], C->h_counters[2]));
+    if (mc > C->cand_cap) C->cand_cap = mc + mc / 2;
+    int ml = 0, mt = 0;
+    for (int l = 0; l < N_LISTS; l++) ml = std::max(ml, C->h_counters[8 + l]);
+    for (int t = 0; t < N_TABLES; t++) mt = std::max(mt, C->h_counters[16 + t]);
+    if (ml > C->list_cap) C->list_cap = ml + ml / 2;
+    if (mt > C->table_cap) C->table_cap = mt + mt / 2;
+    return true;
+}
+// force_swap: the new contact tables become the current ones even if they hold the same rows (something has already read them)
+static int detect_publish(sb_context* ctx, Contact* C, int mode, bool force_swap)
+{
     for (int l = 0; l < N_LISTS; l++) C->h_list_count[l] = C->h_counters[8 + l];
     // publish the table sizes to the potentials / friction arrays
     auto publish = [&](int t0, int t1) {
@@ -1246,7 +1256,7 @@ static int detect(sb_context* ctx, Contact* C, int mode, double enlargement)
     };
     if (mode == 0 || mode == 4 || mode == 5) {
         static const bool no_reuse = std::getenv("SB_NO_TABLE_REUSE") != nullptr;   // diagnostic hook
-        bool same = C->cur_valid && !no_reuse;
+        bool same = C->cur_valid && !no_reuse && !force_swap;
         for (int t = 0; t < N_CONTACT_TABLES && same; t++)
             same = C->h_counters[16 + t] == C->h_table_count[t] && C->h_hash[2 * t] == C->cur_hash[2 * t] && C->h_hash[2 * t + 1] == C->cur_hash[2 * t + 1];
         if (same) C->n_tables_same++;   // same rows as the current tables: keep them (and everything built on them)
@@ -1260,6 +1270,21 @@ static int detect(sb_context* ctx, Contact* C, int mode, double enlargement)
     }
     if (mode == 1 || mode == 5) publish(N_CONTACT_TABLES, N_TABLES);
     return 0;
+}
+
+
+static int detect(sb_context* ctx, Contact* C, int mode, double enlargement)
+{
+    if (C->reorder_countdown-- <= 0) { int r = reorder_primitives(ctx, C); if (r) return r; }
+    for (int attempt = 0; attempt < 8; attempt++) {
+        int r = detect_issue(ctx, C, mode, enlargement);
+        if (r) return r;
+        SB_CUDA(ctx, hot_sync(ctx));
+        SB_CUDA(ctx, cudaGetLastError());
+        if (!detect_overflowed(ctx, C)) break;
+        if (attempt == 7) return fail(ctx, SB_ERR_STATE, "contact detection: buffers keep overflowing");
+    }
+    return detect_publish(ctx, C, mode, false);
 }
 
 static double max_thickness(Contact* C)
@@ -1317,6 +1342,66 @@ int contact_intersections_internal(sb_context* ctx, int* out_count)
     C->cached_intersections = *out_count;
     C->intersections_state = ctx->state_version;
     if (with_tables) C->contacts_state = ctx->state_version;
+    return 0;
+}
+
+// ---- fused detection + evaluation (core.cu: eval_fused) ----
+// Can the detection of a trial state be issued without synchronising?  (internal vertex update, clean topology)
+bool contact_fusable(sb_context* ctx)
+{
+    Contact* C = ctx->contact;
+    // (friction switched off: the host zeroes the friction potentials while the device counters keep their last values)
+    return C && !C->groups.empty() && !C->external_vertices && !C->topology_dirty && C->reorder_countdown > 0 && C->enable_friction;
+}
+// vertex update + every launch of a mode-4 detection + the read-back of the counters, NO synchronisation
+int contact_fused_issue(sb_context* ctx)
+{
+    Contact* C = ctx->contact;
+    int r;
+    if ((r = refresh_params(ctx, C))) return r;
+    if ((r = update_vertices(ctx, C, false))) return r;
+    C->reorder_countdown--;
+    return detect_issue(ctx, C, 4, 2.0 * max_thickness(C), true);
+}
+// the detection's counters / table digests on the device, and their delivery to the host copies detect_* reads
+void contact_readback_sources(sb_context* ctx, const int** counters, const unsigned long long** hash)
+{
+    *counters = ctx->contact->counters.p;
+    *hash = ctx->contact->hash.p;
+}
+void contact_readback_deliver(sb_context* ctx, const int* counters, const unsigned long long* hash)
+{
+    std::memcpy(ctx->contact->h_counters, counters, 64 * sizeof(int));
+    std::memcpy(ctx->contact->h_hash, hash, 2 * N_CONTACT_TABLES * sizeof(unsigned long long));
+}
+int contact_n_digest_words() { return 2 * N_CONTACT_TABLES; }
+// where the issued detection writes the table of potential `pot` (contact tables: the back buffer), the table's counter on the
+// device, the common capacity; -1 if `pot` is not a contact / friction table
+int contact_issue_table(sb_context* ctx, int pot, const int32_t** conn, const int** count_dev, int* cap)
+{
+    Contact* C = ctx->contact;
+    for (int t = 0; t < N_TABLES; t++)
+        if (C->pot[t] == pot) {
+            *conn = (t < N_CONTACT_TABLES) ? C->table_back[t].p : C->table[t].p;
+            *count_dev = C->counters.p + 16 + t;
+            *cap = C->table_cap;
+            return t;
+        }
+    return -1;
+}
+// after the synchronisation: overflow -> *retry (capacities grown, nothing published); otherwise the tables are published (always
+// swapped in: the evaluation queued behind the detection has read the new buffers) and the caches are set
+int contact_fused_finish(sb_context* ctx, int* out_intersections, bool* retry)
+{
+    Contact* C = ctx->contact;
+    *retry = detect_overflowed(ctx, C);
+    if (*retry) return 0;
+    int r = detect_publish(ctx, C, 4, true);
+    if (r) return r;
+    *out_intersections = C->h_list_count[6];
+    C->cached_intersections = *out_intersections;
+    C->intersections_state = ctx->state_version;
+    C->contacts_state = ctx->state_version;
     return 0;
 }
 

@@ -209,9 +209,10 @@ __global__ void __launch_bounds__(512) k_reduce_stage2(const double* __restrict_
 }
 // energy sum and gradient inf-norm of one P+G+H evaluation in two launches instead of four (same trees, same results: the
 // first RED_BLOCKS blocks are the sum's, the others the maximum's)
-__global__ void __launch_bounds__(RED_THREADS) k_reduce_pair_stage1(const double* __restrict__ e, size_t ne, const double* __restrict__ g, size_t ng, double* __restrict__ partial)
+__global__ void __launch_bounds__(RED_THREADS) k_reduce_pair_stage1(const double* __restrict__ e, size_t ne, const unsigned long long* __restrict__ ne_dev, const double* __restrict__ g, size_t ng, double* __restrict__ partial)
 {
     __shared__ double s[RED_THREADS];
+    if (ne_dev) ne = (size_t)*ne_dev;   // (fused detection + evaluation: the element count is known on the device only)
     const bool mx = blockIdx.x >= RED_BLOCKS;
     const int b = mx ? blockIdx.x - RED_BLOCKS : blockIdx.x;
     const double* in = mx ? g : e;
@@ -241,10 +242,10 @@ __global__ void __launch_bounds__(512) k_reduce_pair_stage2(const double* __rest
     }
     if (threadIdx.x == 0) out[mx ? 1 : 0] = s[0];
 }
-static void reduce_sum_and_absmax(sb_context* ctx, const double* e, size_t ne, const double* g, size_t ng, double* d_out2)
+static void reduce_sum_and_absmax(sb_context* ctx, const double* e, size_t ne, const double* g, size_t ng, double* d_out2, const unsigned long long* ne_dev = nullptr)
 {
     ctx->scratch.ensure(1024);
-    k_reduce_pair_stage1<<<2 * RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(e, ne, g, ng, ctx->scratch.p);
+    k_reduce_pair_stage1<<<2 * RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(e, ne, ne_dev, g, ng, ctx->scratch.p);
     k_reduce_pair_stage2<<<2, 512, 0, ctx->stream>>>(ctx->scratch.p, d_out2);
     ctx->launches += 2;
 }
@@ -320,6 +321,7 @@ constexpr int SMALL_POTENTIAL = 100000;   // (everything but the volume elements
 static EvalArgs make_args(sb_context* ctx, Potential& p)
 {
     EvalArgs a;
+    a.dyn = nullptr;
     a.slots = p.slots.p;
     a.slots_host = p.slots_host.data();
     a.conn = p.conn_ext ? p.conn_ext : p.conn.p;
@@ -432,6 +434,209 @@ int eval_prelaunch_static(sb_context* ctx)
     if (r) return r;
     ctx->pre_valid = true;
     ctx->pre_state = ctx->state_version; ctx->pre_static = ctx->static_version;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Fused collision detection + P+G+H evaluation of a line-search trial state: ONE host synchronisation
+// ---------------------------------------------------------------------------------------------------
+// The plain path is detection -> sync (table sizes) -> contact / friction potentials -> reductions -> sync: between the two syncs
+// the GPU waits for the host to size and issue a dozen launches.  Here everything behind the detection is queued at once: a
+// one-thread kernel lays the tables' elements out on the device (same formulas as the host layout), the table potentials' kernels
+// (one multi-potential launch sized by the previous counts, grid-stride) read their element count and offsets from that layout, the
+// assembly's pattern lookup, the speculative scatter pass and the reductions take their counts from it too, and the host
+// synchronises once for the detection's counters, the layout totals and the evaluation's scalars.  Whatever does not fit the
+// assumptions (buffer overflow, a table whose potential is not in the multi-potential kernel, no assembled pattern yet) falls back
+// to the plain path, which redoes the work.
+struct DynMeta { int n; int table_nb[MULTI_G_MAX]; int table_ndof[MULTI_G_MAX]; const int* count[MULTI_G_MAX]; };
+__global__ void k_dyn_layout(const __grid_constant__ DynMeta M, int table_cap, unsigned long long st_H, unsigned long long st_rows, unsigned long long st_E,
+                             unsigned long long cap_H, unsigned long long cap_rows, unsigned long long cap_E,
+                             DynLayout* __restrict__ layout, PotDesc* __restrict__ descs, DynTotals* __restrict__ tot)
+{
+    __shared__ int s_n[MULTI_G_MAX];
+    if ((int)threadIdx.x < M.n) s_n[threadIdx.x] = min(*M.count[threadIdx.x], table_cap);   // (the counters' loads in parallel: 35 dependent round trips otherwise)
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    unsigned long long H = st_H, R = st_rows, E = st_E, blk = 0;
+    int nd = 0;
+    for (int d = 0; d < M.n; d++) {
+        const int n = s_n[d];
+        const unsigned long long nd2 = (unsigned long long)M.table_ndof[d] * M.table_ndof[d];
+        H = (H + 15ull) & ~15ull;
+        layout[d].n_elem = n; layout[d].pad = 0; layout[d].H_off = H; layout[d].rows_off = R; layout[d].E_off = E;
+        if (n > 0) {
+            PotDesc pd; pd.H_off = H; pd.rows_off = R; pd.blk_off = blk; pd.n_elem = n; pd.nb = M.table_nb[d];
+            descs[nd++] = pd;
+        }
+        H += (unsigned long long)n * nd2;
+        R += (unsigned long long)n * M.table_nb[d];
+        E += (unsigned long long)n;
+        blk += (unsigned long long)n * M.table_nb[d] * M.table_nb[d];
+    }
+    const bool overflow = H + 1 > cap_H || R + 1 > cap_rows || E + 1 > cap_E || H >= (1ull << 32);
+    if (overflow) { for (int d = 0; d < M.n; d++) layout[d].n_elem = 0; nd = 0; blk = 0; }
+    tot->E_total = overflow ? st_E : E; tot->H_total = H; tot->rows_total = R; tot->n_dyn_src = blk; tot->n_descs = nd; tot->overflow = overflow ? 1 : 0;
+}
+
+// counters (64 ints) | table digests | scalars (3 doubles) | layout totals -> one contiguous block, one device-to-host copy
+struct Mailbox { int counters[64]; unsigned long long hash[64]; double scalars[4]; DynTotals totals; };
+__global__ void k_pack_mailbox(const int* __restrict__ counters, const unsigned long long* __restrict__ hash, int n_hash, const double* __restrict__ scalars,
+                               const DynTotals* __restrict__ tot, Mailbox* __restrict__ out)
+{
+    const int t = threadIdx.x;
+    if (t < 64) out->counters[t] = counters[t];
+    if (t < n_hash) out->hash[t] = hash[t];
+    if (t < 3) out->scalars[t] = scalars[t];
+    if (t == 0) out->totals = *tot;
+}
+
+void eval_discard(sb_context* ctx)
+{
+    ctx->have_pgh = false; ctx->pgh_cache_ok = false; ctx->pre_valid = false;
+}
+
+int eval_fused(sb_context* ctx, int* out_intersections, double* out_E, double* out_res, bool* out_done)
+{
+    *out_done = false;
+    // Measured at the 200k-tet scene (tools/ab.py, medians of 3): 1105 it/s fused against 1107 plain -- the host-bound stretch
+    // behind the detection (~100 us) turns into ~95 us of queued GPU work (layout kernel, table kernels, lookup, reductions, the
+    // packed read-back), so nothing is gained there; kept behind SB_FUSED=1 for scenes with many populated tables, where the
+    // plain path's per-table host work grows and this one's does not.
+    static const bool on = std::getenv("SB_FUSED") != nullptr;
+    if (!on || ctx->profile || !contact_fusable(ctx) || !assembly_locate_ready(ctx)) return 0;
+    // the table potentials, in layout (= registration) order; all of them must have a body in the multi-potential kernel or be
+    // empty now AND after this detection (checked below)
+    std::vector<int> dyn;
+    for (int i = 0; i < (int)ctx->potentials.size(); i++) if (ctx->potentials[i].dynamic) dyn.push_back(i);
+    if (dyn.empty() || (int)dyn.size() > MULTI_G_MAX) return 0;
+    int rc;
+    if (!(ctx->pre_valid && ctx->pre_state == ctx->state_version && ctx->pre_static == ctx->static_version)) {
+        if ((rc = eval_prelaunch_static(ctx))) return rc;
+        if (!ctx->pre_valid) return 0;   // (pre-launch switched off)
+    }
+    StageTimer timer(ctx, ST_EVAL_PGH);
+    cudaStream_t st = ctx->stream;
+    if (!ctx->d_dyn_layout) {
+        SB_CUDA(ctx, cudaMalloc(&ctx->d_dyn_layout, MULTI_G_MAX * sizeof(DynLayout)));
+        SB_CUDA(ctx, cudaMalloc(&ctx->d_dyn_totals, sizeof(DynTotals)));
+        SB_CUDA(ctx, cudaMallocHost(&ctx->h_dyn_totals, sizeof(DynTotals)));
+        SB_CUDA(ctx, cudaMalloc(&ctx->d_mailbox, sizeof(Mailbox)));
+        SB_CUDA(ctx, cudaMallocHost(&ctx->h_mailbox, sizeof(Mailbox)));
+    }
+    // ---- detection: all launches, counters on their way to the host ----
+    if ((rc = contact_fused_issue(ctx))) return rc;
+    // ---- layout on the device ----
+    DynMeta M;
+    M.n = (int)dyn.size();
+    MultiGArgs& MG = ctx->multi_g;
+    MG.n = 0; MG.pad = 0;
+    int mg_ctas = 0, table_cap = 0;
+    size_t est_src = 0;
+    std::vector<int> ineligible;
+    std::vector<std::pair<int, EvalArgs>> own;
+    for (int d = 0; d < M.n; d++) {
+        Potential& p = ctx->potentials[dyn[d]];
+        const int32_t* conn = nullptr;
+        if (contact_issue_table(ctx, dyn[d], &conn, &M.count[d], &table_cap) < 0) { eval_discard(ctx); return 0; }   // (a dynamic potential that is not a contact table)
+        M.table_nb[d] = p.k->nb; M.table_ndof[d] = p.k->n_dof;
+        const int est = std::max(64, 2 * p.n_elem);
+        est_src += (size_t)est * p.k->nb * p.k->nb;
+        // Tables that held elements at the last detection get their own kernel (sized by twice that count, grid-stride); the
+        // others -- usually empty again -- share the multi-potential launch with one CTA each.  (All of them in the multi-potential
+        // kernel was measured: 49 us against ~10, its code is the sum of 35 differentiated energies and every CTA runs a different one.)
+        if ((rc = refresh_slots(ctx, p))) return rc;
+        EvalArgs a = make_args(ctx, p);
+        a.dyn = ctx->d_dyn_layout + d;
+        a.conn = conn;
+        a.H = ctx->H.p; a.rows = ctx->rows.p; a.E_elem = ctx->E_elem.p;
+        if (p.n_elem > 0) { a.n_elem = est; own.push_back(std::make_pair(dyn[d], a)); continue; }
+        const int ctas = (p.k->p_kind >= 0) ? multi_g_ctas(p.k->p_kind, 1) : 0;
+        if (ctas <= 0) { ineligible.push_back(dyn[d]); continue; }
+        MG.kind[MG.n] = p.k->p_kind; MG.cta0[MG.n] = mg_ctas; MG.it[MG.n] = a;
+        MG.n++;
+        mg_ctas += ctas;
+    }
+    PotDesc* d_descs = assembly_descs_dev(ctx, M.n);
+    k_dyn_layout<<<1, 64, 0, st>>>(M, table_cap, ctx->st_H, ctx->st_rows, ctx->st_E, ctx->H.cap, ctx->rows.cap, std::min(ctx->E_elem.cap, ctx->projected.cap),
+                                   ctx->d_dyn_layout, d_descs, ctx->d_dyn_totals);
+    // ---- the table potentials in one launch, reading that layout ----
+    timeline_point(st, "fused: layout");
+    unsigned own_mask = 0;
+    if (!own.empty()) {
+        SB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+        int k = 0;
+        for (auto& oa : own) {
+            const int sidx = k++ % sb_context::N_SIDE;
+            if (!(own_mask & (1u << sidx))) { SB_CUDA(ctx, cudaStreamWaitEvent(ctx->side[sidx], ctx->ev_fork, 0)); own_mask |= 1u << sidx; }
+            ctx->potentials[oa.first].k->launch_pgh(oa.second, ctx->side[sidx]);
+            ctx->launches++;
+        }
+    }
+    if (MG.n > 0) launch_pgh_multi(MG, mg_ctas, st);
+    timeline_point(st, "fused: table potentials");
+    ctx->launches += 2;
+    // ---- joins (static part on the side / bulk streams), pattern lookup + speculative scatter, reductions ----
+    if (ctx->bulk_pending) { SB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_bulk, 0)); ctx->bulk_pending = false; }
+    for (int k = 0; k < sb_context::N_SIDE; k++)
+        if ((ctx->st_side_mask | own_mask) & (1u << k)) {
+            SB_CUDA(ctx, cudaEventRecord(ctx->ev_join[k], ctx->side[k]));
+            SB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join[k], 0));
+        }
+    timeline_point(st, "fused: joined");
+    if ((rc = assembly_locate_dynamic_dev(ctx, ctx->d_dyn_totals, est_src))) return rc;
+    timeline_point(st, "fused: located");
+    reduce_sum_and_absmax(ctx, ctx->E_elem.p, 0, ctx->grad.p, ctx->ndofs, ctx->d_scalars, &ctx->d_dyn_totals->E_total);
+    timeline_point(st, "fused: reduced");
+    {   // everything the host needs, in one copy
+        const int* d_counters; const unsigned long long* d_hash;
+        contact_readback_sources(ctx, &d_counters, &d_hash);
+        k_pack_mailbox<<<1, 64, 0, st>>>(d_counters, d_hash, contact_n_digest_words(), ctx->d_scalars, ctx->d_dyn_totals, reinterpret_cast<Mailbox*>(ctx->d_mailbox));
+        ctx->launches++;
+        SB_CUDA(ctx, cudaMemcpyAsync(ctx->h_mailbox, ctx->d_mailbox, sizeof(Mailbox), cudaMemcpyDeviceToHost, st));
+    }
+    // ---- the one synchronisation ----
+    SB_CUDA(ctx, hot_sync(ctx));
+    SB_CUDA(ctx, cudaGetLastError());
+    {
+        const Mailbox& mb = *reinterpret_cast<const Mailbox*>(ctx->h_mailbox);
+        contact_readback_deliver(ctx, mb.counters, mb.hash);
+        for (int k = 0; k < 3; k++) ctx->h_scalars[k] = mb.scalars[k];
+        *ctx->h_dyn_totals = mb.totals;
+    }
+    bool retry = false;
+    if ((rc = contact_fused_finish(ctx, out_intersections, &retry))) return rc;
+    const DynTotals& T = *ctx->h_dyn_totals;
+    bool fallback = retry || T.overflow != 0;
+    for (int pi : ineligible) if (ctx->potentials[pi].n_elem > 0) fallback = true;
+    static const bool fdump = std::getenv("SB_FUSED_DUMP") != nullptr;
+    if (fdump) fprintf(stderr, "FUSED retry=%d overflow=%d fallback=%d n_int=%d miss=%g n_src=%llu est_src=%zu E_total=%llu\n", (int)retry, T.overflow, (int)fallback, *out_intersections, ctx->h_scalars[2], T.n_dyn_src, est_src, T.E_total);
+    if (fallback) { eval_discard(ctx); return 0; }   // (the plain path redoes detection / evaluation; the gradient already holds these tables' contributions, hence the full discard)
+    // ---- host copy of the layout (same formulas as k_dyn_layout and eval_internal) ----
+    size_t H_total = ctx->st_H, rows_total = ctx->st_rows, E_total = ctx->st_E, n_blocks = ctx->st_blocks;
+    for (int pi : dyn) {
+        Potential& p = ctx->potentials[pi];
+        H_total = (H_total + 15) & ~(size_t)15;
+        p.H_off = H_total; p.rows_off = rows_total; p.E_off = E_total;
+        const size_t n = p.k->n_dof;
+        H_total += (size_t)p.n_elem * n * n;
+        rows_total += (size_t)p.n_elem * p.k->nb;
+        E_total += (size_t)p.n_elem;
+        n_blocks += (size_t)p.n_elem * p.k->nb * p.k->nb;
+    }
+    if (E_total != T.E_total || H_total != T.H_total || rows_total != T.rows_total) { eval_discard(ctx); return fail(ctx, SB_ERR_STATE, "eval_fused: device and host layouts differ"); }
+    ctx->pre_valid = false;
+    ctx->n_hessians = E_total; ctx->n_blocks_total = n_blocks; ctx->n_static_blocks = ctx->st_blocks; ctx->n_rows_total = rows_total; ctx->H_total = H_total;
+    ctx->n_projected = 0;
+    ctx->eval_id++;
+    projector_prepare(ctx);
+    ctx->have_pgh = true;
+    assembly_locate_result_dev(ctx, ctx->h_scalars[2] != 0.0, (size_t)T.n_dyn_src, true);
+    ctx->pgh_cache_ok = true;
+    ctx->pgh_state = ctx->state_version; ctx->pgh_dynamic = ctx->dynamic_version; ctx->pgh_static = ctx->static_version;
+    ctx->pgh_E = ctx->h_scalars[0]; ctx->pgh_residual = ctx->h_scalars[1];
+    *out_E = ctx->h_scalars[0];
+    *out_res = ctx->h_scalars[1];
+    *out_done = true;
     return 0;
 }
 
@@ -1114,6 +1319,7 @@ int sb_potential_get_element_output(sb_context* ctx, int potential, double* host
     SB_CUDA(ctx, cudaMemsetAsync(grad_tmp.p, 0, sizeof(double) * ctx->ndofs, ctx->stream));
     r = refresh_slots(ctx, p); if (r) return r;
     EvalArgs a;
+    a.dyn = nullptr;
     a.slots = p.slots.p;
     a.slots_host = p.slots_host.data();
     a.conn = p.conn_ext ? p.conn_ext : p.conn.p;
@@ -1226,6 +1432,7 @@ extern "C" int sb_profile_potential(sb_context* ctx, int potential, int mode, in
     if (p.n_elem == 0) { *out_avg_ms = 0.0; return SB_OK; }
     r = refresh_slots(ctx, p); if (r) return r;
     EvalArgs a;
+    a.dyn = nullptr;
     a.slots = p.slots.p;
     a.slots_host = p.slots_host.data();
     a.conn = p.conn_ext ? p.conn_ext : p.conn.p;

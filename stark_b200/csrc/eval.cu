@@ -31,54 +31,60 @@ __device__ __forceinline__ void pair_from_index(int p, int& i, int& j)
 
 // body of the P+G+H evaluation of one CTA's elements; BLOCK threads take part (the kernel may have more), G = BLOCK / L elements
 template<class Pot, int BLOCK>
-__device__ __forceinline__ void eval_pgh_body(const EvalArgs& a, int cta, double* s_in)
+__device__ __forceinline__ void eval_pgh_body(const EvalArgs& a, int cta_first, int cta_stride, double* s_in)
 {
     constexpr int N = Pot::N_DOF, L = Geo<Pot>::L, G = BLOCK / L, NIN = Pot::N_IN, NB = Pot::NB;
     const int tid = threadIdx.x;
-    const int e_base = cta * G;
-
-    // cooperative gather of G elements' inputs
-    for (int idx = tid; idx < G * NIN; idx += blockDim.x) {
-        const int el = idx / NIN, slot = idx - el * NIN;
-        const int e = e_base + el;
-        if (e < a.n_elem) {
-            const FetchSlot fs = a.slots[slot];
-            const int row = (fs.conn_col >= 0) ? a.conn[(size_t)e * a.conn_stride + fs.conn_col] : 0;
-            s_in[idx] = fs.base[(size_t)row * fs.stride + fs.off];
+    // element count and output locations: launch arguments, or (fused detection + evaluation) the device-side layout
+    int n_elem = a.n_elem;
+    double* Hb = a.H; int32_t* rows_b = a.rows; double* Eb = a.E_elem;
+    if (a.dyn) { n_elem = a.dyn->n_elem; Hb = a.H + a.dyn->H_off; rows_b = a.rows + a.dyn->rows_off; Eb = a.E_elem + a.dyn->E_off; }
+    for (int cta = cta_first; cta * G < n_elem; cta += cta_stride) {   // (one trip unless the launch was sized by an estimate)
+        const int e_base = cta * G;
+        // cooperative gather of G elements' inputs
+        for (int idx = tid; idx < G * NIN; idx += blockDim.x) {
+            const int el = idx / NIN, slot = idx - el * NIN;
+            const int e = e_base + el;
+            if (e < n_elem) {
+                const FetchSlot fs = a.slots[slot];
+                const int row = (fs.conn_col >= 0) ? a.conn[(size_t)e * a.conn_stride + fs.conn_col] : 0;
+                s_in[idx] = fs.base[(size_t)row * fs.stride + fs.off];
+            }
         }
-    }
-    __syncthreads();
+        __syncthreads();
 
-    const int el = tid / L;
-    const int p = tid - el * L;
-    const int e = e_base + el;
-    if (el >= G || e >= a.n_elem) return;
+        const int el = tid / L;
+        const int p = tid - el * L;
+        const int e = e_base + el;
+        if (el < G && e < n_elem) {
+            sbad::Seed<sbad::D2> seed;
+            pair_from_index(p, seed.i, seed.j);
+            const sbad::D2 r = Pot::template energy<sbad::D2>(s_in + el * NIN, seed);
 
-    sbad::Seed<sbad::D2> seed;
-    pair_from_index(p, seed.i, seed.j);
-    const sbad::D2 r = Pot::template energy<sbad::D2>(s_in + el * NIN, seed);
-
-    const int i = seed.i, j = seed.j;
-    double* He = a.H + (size_t)e * N * N;
-    He[i * N + j] = r.h;
-    if (i != j) He[j * N + i] = r.h;
-    const int32_t* ce = a.conn + (size_t)e * a.conn_stride;
-    if (j == 0) {
-        const DofBlock b = a.blocks[i / 3];
-        atomicAdd(a.grad + b.dof_offset + 3 * ce[b.conn_col] + (i % 3), r.gi);
-        if (a.g_elem) a.g_elem[(size_t)e * N + i] = r.gi;
+            const int i = seed.i, j = seed.j;
+            double* He = Hb + (size_t)e * N * N;
+            He[i * N + j] = r.h;
+            if (i != j) He[j * N + i] = r.h;
+            const int32_t* ce = a.conn + (size_t)e * a.conn_stride;
+            if (j == 0) {
+                const DofBlock b = a.blocks[i / 3];
+                atomicAdd(a.grad + b.dof_offset + 3 * ce[b.conn_col] + (i % 3), r.gi);
+                if (a.g_elem) a.g_elem[(size_t)e * N + i] = r.gi;
+            }
+            if (p < NB) {
+                const DofBlock b = a.blocks[p];
+                rows_b[(size_t)e * NB + p] = b.dof_offset / 3 + ce[b.conn_col];
+            }
+            if (p == 0) Eb[e] = r.v;
+        }
+        __syncthreads();   // (the staged inputs are overwritten by the next trip)
     }
-    if (p < NB) {
-        const DofBlock b = a.blocks[p];
-        a.rows[(size_t)e * NB + p] = b.dof_offset / 3 + ce[b.conn_col];
-    }
-    if (p == 0) a.E_elem[e] = r.v;
 }
 template<class Pot>
 __global__ void __launch_bounds__(Geo<Pot>::BLOCK) k_eval_pgh(const EvalArgs a)
 {
     __shared__ double s_in[Geo<Pot>::G * Pot::N_IN];
-    eval_pgh_body<Pot, Geo<Pot>::BLOCK>(a, blockIdx.x, s_in);
+    eval_pgh_body<Pot, Geo<Pot>::BLOCK>(a, blockIdx.x, gridDim.x, s_in);
 }
 
 // energy only (line-search evaluations): the same cooperative gather (all loads of a CTA's elements in flight together --
@@ -258,9 +264,9 @@ constexpr int multi_g_smem_max()
     return m;
 }
 template<class Pot, bool OK = MultiGOk<Pot>::value> struct MultiGBody {
-    static __device__ __forceinline__ void run(const EvalArgs& a, int cta, double* s_in) { eval_pgh_body<Pot, MULTI_G_BLOCK>(a, cta, s_in); }
+    static __device__ __forceinline__ void run(const EvalArgs& a, int cta, int n_ctas, double* s_in) { eval_pgh_body<Pot, MULTI_G_BLOCK>(a, cta, n_ctas, s_in); }
 };
-template<class Pot> struct MultiGBody<Pot, false> { static __device__ __forceinline__ void run(const EvalArgs&, int, double*) {} };
+template<class Pot> struct MultiGBody<Pot, false> { static __device__ __forceinline__ void run(const EvalArgs&, int, int, double*) {} };
 __global__ void __launch_bounds__(MULTI_G_BLOCK) k_eval_pgh_multi(const __grid_constant__ MultiGArgs M)
 {
     __shared__ double s_in[multi_g_smem_max()];
@@ -268,8 +274,9 @@ __global__ void __launch_bounds__(MULTI_G_BLOCK) k_eval_pgh_multi(const __grid_c
     while (i + 1 < M.n && (int)blockIdx.x >= M.cta0[i + 1]) i++;
     const EvalArgs& a = M.it[i];
     const int cta = blockIdx.x - M.cta0[i];
+    const int n_ctas = ((i + 1 < M.n) ? M.cta0[i + 1] : (int)gridDim.x) - M.cta0[i];   // this potential's share of the grid
     switch (M.kind[i]) {
-#define X(S) case PK_##S: MultiGBody<sbpot::S>::run(a, cta, s_in); break;
+#define X(S) case PK_##S: MultiGBody<sbpot::S>::run(a, cta, n_ctas, s_in); break;
     SB_TABLE_POTS(X)
 #undef X
     default: break;

@@ -32,7 +32,30 @@ struct DofBlock {
     int32_t conn_col;    // connectivity column that indexes the set
 };
 
+// Element layout of the dynamic potentials computed ON THE DEVICE (fused detection + evaluation, core.cu): the contact / friction
+// tables' sizes are only on the device when their potentials' kernels are queued, so those kernels read their element count and
+// their offsets in the element-output buffers from here.
+struct DynLayout {
+    int32_t n_elem;
+    int32_t pad;
+    unsigned long long H_off, rows_off, E_off;   // offsets (in elements of the respective buffer) from the buffers' bases
+};
+// descriptor of one potential's element blocks for the assembly's key / lookup kernels (assembly.cu)
+struct PotDesc {
+    unsigned long long H_off;     // offset of the potential's element Hessians in ctx->H
+    unsigned long long rows_off;  // offset of its block rows in ctx->rows
+    unsigned long long blk_off;   // offset of its element blocks in the source numbering of its class (static / dynamic)
+    int n_elem, nb;
+};
+// totals written by the device-side layout kernel (read back with the evaluation's scalars)
+struct DynTotals {
+    unsigned long long E_total, H_total, rows_total, n_dyn_src;
+    int32_t n_descs;      // dynamic potentials with elements
+    int32_t overflow;     // the element-output buffers (or the scatter table) are too small for this layout: nothing was evaluated
+};
+
 struct EvalArgs {
+    const DynLayout* dyn;          // non-null: n_elem / H / rows / E_elem come from the device-side layout (H, rows, E_elem are then the buffers' bases)
     const FetchSlot* slots;
     const FetchSlot* slots_host;   // HOST copy of the same table (for launchers that pass it as a kernel parameter)
     const int32_t* conn;
@@ -237,6 +260,11 @@ struct sb_context {
     uint64_t pgh_state = 0, pgh_dynamic = 0, pgh_static = 0;
     double pgh_E = 0.0, pgh_residual = 0.0;
     // first half of a P+G+H evaluation (the static potentials) launched ahead of the collision detection (eval_prelaunch_static)
+    unsigned char* d_mailbox = nullptr;      // everything the host reads after a fused detection + evaluation, packed for ONE copy
+    unsigned char* h_mailbox = nullptr;
+    sb::DynLayout* d_dyn_layout = nullptr;   // fused detection + evaluation (core.cu: eval_fused)
+    sb::DynTotals* d_dyn_totals = nullptr;
+    sb::DynTotals* h_dyn_totals = nullptr;
     sb::MultiGArgs multi_g;        // staging of the multi-potential P+G+H launch (6 KB: not on the stack of every evaluation)
     bool locate_pending = false;   // a scatter-mode pattern lookup rides with this evaluation's scalars
     bool pre_valid = false;
@@ -293,6 +321,21 @@ int project_internal(sb_context* ctx, double grad_threshold, double eps, int mir
 int project_selection_bounds(sb_context* ctx, double* out_m, double* out_gmin);   // project.cu: when does a falling PPN threshold select something new?
 int solve_pcg_internal(sb_context* ctx, double abs_tol, double rel_tol, int max_iter, int stop_on_indef, int* out_iterations, int* out_ok, double* out_du_dot_grad, double* out_du_inf);
 // contact hooks used by the Newton driver (contact.cu)
+bool contact_fusable(sb_context* ctx);
+int contact_fused_issue(sb_context* ctx);
+int contact_issue_table(sb_context* ctx, int pot, const int32_t** conn, const int** count_dev, int* cap);
+int contact_fused_finish(sb_context* ctx, int* out_intersections, bool* retry);
+void contact_readback_sources(sb_context* ctx, const int** counters, const unsigned long long** hash);
+void contact_readback_deliver(sb_context* ctx, const int* counters, const unsigned long long* hash);
+int contact_n_digest_words();
+int eval_fused(sb_context* ctx, int* out_intersections, double* out_E, double* out_res, bool* out_done);   // core.cu
+void eval_discard(sb_context* ctx);
+// assembly.cu, fused path: lookup + speculative scatter with the dynamic sources' count / descriptors on the device
+bool assembly_locate_ready(sb_context* ctx);
+PotDesc* assembly_descs_dev(sb_context* ctx, int n);
+size_t assembly_scatter_capacity(sb_context* ctx, size_t n_src_estimate);
+int assembly_locate_dynamic_dev(sb_context* ctx, const DynTotals* d_tot, size_t n_src_estimate);
+void assembly_locate_result_dev(sb_context* ctx, bool miss, size_t n_src, bool scatter_valid);
 int contact_update_internal(sb_context* ctx);
 int contact_intersections_internal(sb_context* ctx, int* out_count);
 bool contact_active(sb_context* ctx);

@@ -235,9 +235,23 @@ extern "C" int sb_newton_solve(sb_context* ctx, const sb_newton_settings* S, sb_
         // The first Armijo trial is evaluated with gradient and Hessians (below); the volume elements of that evaluation do not
         // depend on the contact tables, so their kernels go out now, ahead of the trial state's collision detection.
         if (S->enable_armijo_backtracking && !no_spec && (rc = eval_prelaunch_static(ctx))) return rc;
+        // First trial: collision detection (validity + contact tables) and the evaluation with gradient and Hessians are queued
+        // together and synchronised once (eval_fused); anything it cannot handle goes the plain way below.
+        bool have_E1 = false;
+        double E1_fused = 0.0;
         int ls_inv = 0;
         for (; ls_inv < S->max_backtracking_invalid_state_iterations; ++ls_inv) {
-            if ((rc = state_valid(valid))) return rc;
+            bool fused = false;
+            if (ls_inv == 0 && contact && S->intersection_test_enabled && S->enable_armijo_backtracking && !no_spec) {
+                int n_int = 0;
+                double res_unused = 0.0;
+                if ((rc = eval_fused(ctx, &n_int, &E1_fused, &res_unused, &fused))) return rc;
+                if (fused) {
+                    valid = (n_int == 0);
+                    if (valid) have_E1 = true; else eval_discard(ctx);   // (an invalid state: the evaluation queued behind its detection is of no use)
+                }
+            }
+            if (!fused && (rc = state_valid(valid))) return rc;
             if (valid) break;
             step *= 0.5;
             if ((rc = sb_dofs_apply_step(ctx, step))) return rc;
@@ -254,7 +268,8 @@ extern "C" int sb_newton_solve(sb_context* ctx, const sb_newton_settings* S, sb_
                 // The first trial is almost always accepted, and the next iteration then evaluates energy, gradient and
                 // Hessians at this very state: evaluate them now (eval_internal hands the result out again) instead of the
                 // energy alone.  Later trials (after a backtrack) are energy-only.
-                if (k == 0 && !no_spec) { double res_unused = 0.0; if ((rc = eval_internal(ctx, SB_EVAL_PGH, &E1, &res_unused, true))) return rc; }
+                if (k == 0 && have_E1) E1 = E1_fused;   // (evaluated together with the detection above; eval_internal hands it out again to the next iteration)
+                else if (k == 0 && !no_spec) { double res_unused = 0.0; if ((rc = eval_internal(ctx, SB_EVAL_PGH, &E1, &res_unused, true))) return rc; }
                 else if ((rc = eval_internal(ctx, SB_EVAL_P, &E1, nullptr, true))) return rc;
                 if (E1 < E_threshold) break;
                 step *= 0.5;

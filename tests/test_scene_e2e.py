@@ -210,3 +210,37 @@ def test_contact_tables_growing_mid_step_keep_friction_tables():
         assert sa[:3] == sb[:3], (sa, sb)
         assert abs(sa[3] - sb[3]) <= 1e-4 * abs(sa[3]), (sa, sb)
     assert np.abs(np.array(a["x"]) - np.array(b["x"])).max() <= 1e-6
+
+
+@pytest.mark.gpu
+def test_fused_detection_and_evaluation_gives_the_same_trajectory():
+    """SB_FUSED=1: the first line-search trial's collision detection and P+G+H evaluation are queued together (device-side layout of
+    the contact tables' elements, one host synchronisation).  Same trajectory as the plain path."""
+    import os, subprocess, sys, textwrap
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = textwrap.dedent("""
+        import sys, json
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        from stark_b200 import scenes
+        sc = scenes.Scene("tetdrop", n=6, vz=0.25)
+        log = []
+        for _ in range(14):
+            s = sc.step()
+            log.append([s["accepted"], s["newton_iterations"], s["result"], s["first_residual"]])
+        print(json.dumps({"log": log, "x": sc.positions()[::7].tolist()}))
+    """) % (here, os.path.dirname(here))
+    out = []
+    for fused in (False, True):
+        env = dict(os.environ)
+        env.pop("SB_FUSED", None)
+        if fused:
+            env["SB_FUSED"] = "1"
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    a, b = out
+    assert sum(s[1] for s in a["log"]) > 14
+    for sa, sb in zip(a["log"], b["log"]):
+        assert sa[:3] == sb[:3], (sa, sb)
+        assert abs(sa[3] - sb[3]) <= 1e-4 * abs(sa[3]), (sa, sb)
+    assert np.abs(np.array(a["x"]) - np.array(b["x"])).max() <= 1e-6
