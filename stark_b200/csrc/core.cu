@@ -528,9 +528,9 @@ int eval_fused(sb_context* ctx, int* out_intersections, double* out_E, double* o
     // ---- layout on the device ----
     DynMeta M;
     M.n = (int)dyn.size();
-    MultiGArgs& MG = ctx->multi_g;
-    MG.n = 0; MG.pad = 0;
-    int mg_ctas = 0, table_cap = 0;
+    int fam_ctas[MULTI_G_FAMILIES] = {0, 0, 0, 0, 0, 0};
+    for (int f = 0; f < MULTI_G_FAMILIES; f++) { ctx->multi_g[f].n = 0; ctx->multi_g[f].pad = 0; }
+    int table_cap = 0;
     size_t est_src = 0;
     std::vector<int> ineligible;
     std::vector<std::pair<int, EvalArgs>> own;
@@ -552,9 +552,11 @@ int eval_fused(sb_context* ctx, int* out_intersections, double* out_E, double* o
         if (p.n_elem > 0) { a.n_elem = est; own.push_back(std::make_pair(dyn[d], a)); continue; }
         const int ctas = (p.k->p_kind >= 0) ? multi_g_ctas(p.k->p_kind, 1) : 0;
         if (ctas <= 0) { ineligible.push_back(dyn[d]); continue; }
-        MG.kind[MG.n] = p.k->p_kind; MG.cta0[MG.n] = mg_ctas; MG.it[MG.n] = a;
+        const int fam = multi_g_family(p.k->p_kind);
+        MultiGArgs& MG = ctx->multi_g[fam];
+        MG.kind[MG.n] = p.k->p_kind; MG.cta0[MG.n] = fam_ctas[fam]; MG.it[MG.n] = a;
         MG.n++;
-        mg_ctas += ctas;
+        fam_ctas[fam] += ctas;
     }
     PotDesc* d_descs = assembly_descs_dev(ctx, M.n);
     k_dyn_layout<<<1, 64, 0, st>>>(M, table_cap, ctx->st_H, ctx->st_rows, ctx->st_E, ctx->H.cap, ctx->rows.cap, std::min(ctx->E_elem.cap, ctx->projected.cap),
@@ -572,7 +574,7 @@ int eval_fused(sb_context* ctx, int* out_intersections, double* out_E, double* o
             ctx->launches++;
         }
     }
-    if (MG.n > 0) launch_pgh_multi(MG, mg_ctas, st);
+    for (int f = 0; f < MULTI_G_FAMILIES; f++) if (ctx->multi_g[f].n > 0) { launch_pgh_multi(f, ctx->multi_g[f], fam_ctas[f], st); ctx->launches++; }
     timeline_point(st, "fused: table potentials");
     ctx->launches += 2;
     // ---- joins (static part on the side / bulk streams), pattern lookup + speculative scatter, reductions ----
@@ -702,19 +704,22 @@ int eval_internal(sb_context* ctx, int mode, double* out_E, double* out_grad_inf
         // the contact / friction tables go into ONE launch on the context stream (k_eval_pgh_multi); what is not eligible for
         // it (24-DoF elements, very large tables) is launched on its own as before
         static const bool no_multi = std::getenv("SB_NO_MULTI_PGH") != nullptr;   // diagnostic hook
-        MultiGArgs* MG = nullptr;
-        int mg_ctas = 0;
+        bool MG = false;   // any table in a multi-potential launch
+        int fam_ctas[MULTI_G_FAMILIES] = {0, 0, 0, 0, 0, 0};
+        for (int f = 0; f < MULTI_G_FAMILIES; f++) { ctx->multi_g[f].n = 0; ctx->multi_g[f].pad = 0; }
         for (auto& p : ctx->potentials) {
             if (!p.dynamic || p.n_elem == 0) continue;
             int r = refresh_slots(ctx, p);
             if (r) return r;
             if (!no_multi && p.n_elem < SMALL_POTENTIAL && p.k->p_kind >= 0) {
                 const int ctas = multi_g_ctas(p.k->p_kind, p.n_elem);
-                if (ctas > 0 && (!MG || MG->n < MULTI_G_MAX)) {
-                    if (!MG) { MG = &ctx->multi_g; MG->n = 0; MG->pad = 0; }
-                    MG->kind[MG->n] = p.k->p_kind; MG->cta0[MG->n] = mg_ctas; MG->it[MG->n] = make_args(ctx, p);
-                    MG->n++;
-                    mg_ctas += ctas;
+                const int fam = multi_g_family(p.k->p_kind);
+                if (ctas > 0 && fam >= 0 && ctx->multi_g[fam].n < MULTI_G_MAX) {
+                    MultiGArgs& M = ctx->multi_g[fam];
+                    M.kind[M.n] = p.k->p_kind; M.cta0[M.n] = fam_ctas[fam]; M.it[M.n] = make_args(ctx, p);
+                    M.n++;
+                    fam_ctas[fam] += ctas;
+                    MG = true;
                     continue;
                 }
             }
@@ -734,9 +739,17 @@ int eval_internal(sb_context* ctx, int mode, double* out_E, double* out_grad_inf
         // The symbolic phase of the coming assembly depends on the dynamic potentials' block rows only: the helper thread issues
         // it (its own stream, behind these kernels) while this thread goes on with the reductions.
         if (MG) {
-            launch_pgh_multi(*MG, mg_ctas, ctx->stream);
-            ctx->launches++;
-            timeline_point(ctx->stream, "contact / friction tables (one launch)");
+            // one launch per family of tables with elements (contact d_d / rb_rb / rb_d, friction likewise), on the two side streams
+            int kf = 0;
+            for (int f = 0; f < MULTI_G_FAMILIES; f++) {
+                if (ctx->multi_g[f].n == 0) continue;
+                if (!forked) { SB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream)); forked = true; }
+                const int k = kf++ % 2;
+                if (!(dyn_mask & (1u << k))) { SB_CUDA(ctx, cudaStreamWaitEvent(ctx->side[k], ctx->ev_fork, 0)); dyn_mask |= 1u << k; }
+                launch_pgh_multi(f, ctx->multi_g[f], fam_ctas[f], ctx->side[k]);
+                ctx->launches++;
+            }
+            timeline_point(ctx->stream, "contact / friction tables (one launch per family)");
         }
         const double te2 = eval_dump ? now_ms() : 0.0;
         // (the sort-based symbolic phase is only prefetched when the scatter-mode lookup cannot run: first assembly, stale pattern)
@@ -745,10 +758,7 @@ int eval_internal(sb_context* ctx, int mode, double* out_E, double* out_grad_inf
         if (prefetch) {
             for (int k = 0; k < sb_context::N_SIDE; k++)
                 if (dyn_mask & (1u << k)) SB_CUDA(ctx, cudaEventRecord(ctx->ev_dyn[k], ctx->side[k]));
-            if (MG) {   // (the multi-potential launch sits on the context stream: its event takes the slot of the last side stream, which the dynamic potentials never use)
-                SB_CUDA(ctx, cudaEventRecord(ctx->ev_dyn[sb_context::N_SIDE - 1], ctx->stream));
-                pf_mask |= 1u << (sb_context::N_SIDE - 1);
-            }
+
         }
         side_mask |= dyn_mask;
         if (ctx->bulk_pending) { SB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_bulk, 0)); ctx->bulk_pending = false; }

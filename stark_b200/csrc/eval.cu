@@ -244,14 +244,16 @@ void launch_p_multi(const MultiPArgs& M, int total_ctas, cudaStream_t s)
 // share of the fork / join events each) they cost the host ~5 us apiece in the stretch between the collision detection and the
 // evaluation's reductions, where nothing hides it.  Same scheme as k_eval_p_multi; potentials whose lane count exceeds the
 // block (24-DoF elements: 300 lanes) keep their own kernel.
-#define SB_TABLE_POTS(X) \
-    X(contact_d_d_pt_pp) X(contact_d_d_pt_pe) X(contact_d_d_pt_pt) X(contact_d_d_ee_pp) X(contact_d_d_ee_pe) X(contact_d_d_ee_ee) \
-    X(contact_rb_rb_pt_pp) X(contact_rb_rb_pt_pe) X(contact_rb_rb_pt_pt) X(contact_rb_rb_ee_pp) X(contact_rb_rb_ee_pe) X(contact_rb_rb_ee_ee) \
-    X(contact_rb_d_pt_pp) X(contact_rb_d_pt_pe) X(contact_rb_d_pt_pt) X(contact_rb_d_pt_ep) X(contact_rb_d_pt_tp) \
-    X(contact_rb_d_ee_pp) X(contact_rb_d_ee_pe) X(contact_rb_d_ee_ee) X(contact_rb_d_ee_ep) \
-    X(friction_d_d_pp) X(friction_d_d_pe) X(friction_d_d_pt) X(friction_d_d_ee) \
-    X(friction_rb_rb_pp) X(friction_rb_rb_pe) X(friction_rb_rb_pt) X(friction_rb_rb_ee) \
-    X(friction_rb_d_pp) X(friction_rb_d_pe) X(friction_rb_d_pt) X(friction_rb_d_ee) X(friction_rb_d_ep) X(friction_rb_d_tp)
+// (six kernels, one per family of tables: ONE kernel holding all 35 differentiated energies needs 255 registers with spills and
+//  runs 33 us for a thousand elements -- every CTA executes a different stretch of a very large code; per family it is a third)
+#define SB_FAM_0(X) X(contact_d_d_pt_pp) X(contact_d_d_pt_pe) X(contact_d_d_pt_pt) X(contact_d_d_ee_pp) X(contact_d_d_ee_pe) X(contact_d_d_ee_ee)
+#define SB_FAM_1(X) X(contact_rb_rb_pt_pp) X(contact_rb_rb_pt_pe) X(contact_rb_rb_pt_pt) X(contact_rb_rb_ee_pp) X(contact_rb_rb_ee_pe) X(contact_rb_rb_ee_ee)
+#define SB_FAM_2(X) X(contact_rb_d_pt_pp) X(contact_rb_d_pt_pe) X(contact_rb_d_pt_pt) X(contact_rb_d_pt_ep) X(contact_rb_d_pt_tp) \
+                    X(contact_rb_d_ee_pp) X(contact_rb_d_ee_pe) X(contact_rb_d_ee_ee) X(contact_rb_d_ee_ep)
+#define SB_FAM_3(X) X(friction_d_d_pp) X(friction_d_d_pe) X(friction_d_d_pt) X(friction_d_d_ee)
+#define SB_FAM_4(X) X(friction_rb_rb_pp) X(friction_rb_rb_pe) X(friction_rb_rb_pt) X(friction_rb_rb_ee)
+#define SB_FAM_5(X) X(friction_rb_d_pp) X(friction_rb_d_pe) X(friction_rb_d_pt) X(friction_rb_d_ee) X(friction_rb_d_ep) X(friction_rb_d_tp)
+#define SB_TABLE_POTS(X) SB_FAM_0(X) SB_FAM_1(X) SB_FAM_2(X) SB_FAM_3(X) SB_FAM_4(X) SB_FAM_5(X)
 constexpr int MULTI_G_BLOCK = 256;
 template<class Pot> struct MultiGOk { static constexpr bool value = Geo<Pot>::L <= MULTI_G_BLOCK; };
 template<class Pot> constexpr int multi_g_smem() { return MultiGOk<Pot>::value ? (MULTI_G_BLOCK / Geo<Pot>::L) * Pot::N_IN : 0; }
@@ -267,21 +269,27 @@ template<class Pot, bool OK = MultiGOk<Pot>::value> struct MultiGBody {
     static __device__ __forceinline__ void run(const EvalArgs& a, int cta, int n_ctas, double* s_in) { eval_pgh_body<Pot, MULTI_G_BLOCK>(a, cta, n_ctas, s_in); }
 };
 template<class Pot> struct MultiGBody<Pot, false> { static __device__ __forceinline__ void run(const EvalArgs&, int, int, double*) {} };
-__global__ void __launch_bounds__(MULTI_G_BLOCK) k_eval_pgh_multi(const __grid_constant__ MultiGArgs M)
-{
-    __shared__ double s_in[multi_g_smem_max()];
-    int i = 0;
-    while (i + 1 < M.n && (int)blockIdx.x >= M.cta0[i + 1]) i++;
-    const EvalArgs& a = M.it[i];
-    const int cta = blockIdx.x - M.cta0[i];
-    const int n_ctas = ((i + 1 < M.n) ? M.cta0[i + 1] : (int)gridDim.x) - M.cta0[i];   // this potential's share of the grid
-    switch (M.kind[i]) {
-#define X(S) case PK_##S: MultiGBody<sbpot::S>::run(a, cta, n_ctas, s_in); break;
-    SB_TABLE_POTS(X)
-#undef X
-    default: break;
-    }
+#define SB_MULTI_G_KERNEL(FAM) \
+__global__ void __launch_bounds__(MULTI_G_BLOCK) k_eval_pgh_multi_##FAM(const __grid_constant__ MultiGArgs M) \
+{ \
+    __shared__ double s_in[multi_g_smem_max()]; \
+    int i = 0; \
+    while (i + 1 < M.n && (int)blockIdx.x >= M.cta0[i + 1]) i++; \
+    const EvalArgs& a = M.it[i]; \
+    const int cta = blockIdx.x - M.cta0[i]; \
+    const int n_ctas = ((i + 1 < M.n) ? M.cta0[i + 1] : (int)gridDim.x) - M.cta0[i];   /* this potential's share of the grid */ \
+    switch (M.kind[i]) { \
+    SB_FAM_##FAM(SB_MULTI_G_CASE) \
+    default: break; \
+    } \
 }
+#define SB_MULTI_G_CASE(S) case PK_##S: MultiGBody<sbpot::S>::run(a, cta, n_ctas, s_in); break;
+SB_MULTI_G_KERNEL(0)
+SB_MULTI_G_KERNEL(1)
+SB_MULTI_G_KERNEL(2)
+SB_MULTI_G_KERNEL(3)
+SB_MULTI_G_KERNEL(4)
+SB_MULTI_G_KERNEL(5)
 // CTAs an eligible potential needs in the multi-potential launch (0: not eligible)
 int multi_g_ctas(int p_kind, int n_elem)
 {
@@ -292,9 +300,40 @@ int multi_g_ctas(int p_kind, int n_elem)
     default: return 0;
     }
 }
-void launch_pgh_multi(const MultiGArgs& M, int total_ctas, cudaStream_t s)
+int multi_g_family(int p_kind)
 {
-    k_eval_pgh_multi<<<total_ctas, MULTI_G_BLOCK, 0, s>>>(M);
+    switch (p_kind) {
+#define X(S) case PK_##S: return 0;
+    SB_FAM_0(X)
+#undef X
+#define X(S) case PK_##S: return 1;
+    SB_FAM_1(X)
+#undef X
+#define X(S) case PK_##S: return 2;
+    SB_FAM_2(X)
+#undef X
+#define X(S) case PK_##S: return 3;
+    SB_FAM_3(X)
+#undef X
+#define X(S) case PK_##S: return 4;
+    SB_FAM_4(X)
+#undef X
+#define X(S) case PK_##S: return 5;
+    SB_FAM_5(X)
+#undef X
+    default: return -1;
+    }
+}
+void launch_pgh_multi(int family, const MultiGArgs& M, int total_ctas, cudaStream_t s)
+{
+    switch (family) {
+    case 0: k_eval_pgh_multi_0<<<total_ctas, MULTI_G_BLOCK, 0, s>>>(M); break;
+    case 1: k_eval_pgh_multi_1<<<total_ctas, MULTI_G_BLOCK, 0, s>>>(M); break;
+    case 2: k_eval_pgh_multi_2<<<total_ctas, MULTI_G_BLOCK, 0, s>>>(M); break;
+    case 3: k_eval_pgh_multi_3<<<total_ctas, MULTI_G_BLOCK, 0, s>>>(M); break;
+    case 4: k_eval_pgh_multi_4<<<total_ctas, MULTI_G_BLOCK, 0, s>>>(M); break;
+    default: k_eval_pgh_multi_5<<<total_ctas, MULTI_G_BLOCK, 0, s>>>(M); break;
+    }
 }
 
 }  // namespace sb
@@ -392,7 +431,8 @@ void preload_eval_kernels()
 #undef X
     cudaFuncAttributes fa;
     cudaFuncGetAttributes(&fa, k_eval_p_multi);
-    cudaFuncGetAttributes(&fa, k_eval_pgh_multi);
+    cudaFuncGetAttributes(&fa, k_eval_pgh_multi_0); cudaFuncGetAttributes(&fa, k_eval_pgh_multi_1); cudaFuncGetAttributes(&fa, k_eval_pgh_multi_2);
+    cudaFuncGetAttributes(&fa, k_eval_pgh_multi_3); cudaFuncGetAttributes(&fa, k_eval_pgh_multi_4); cudaFuncGetAttributes(&fa, k_eval_pgh_multi_5);
     cudaFuncGetAttributes(&fa, k_tet_analytic<true, true>); cudaFuncGetAttributes(&fa, k_tet_analytic<true, false>);
     cudaFuncGetAttributes(&fa, k_tet_analytic<false, true>); cudaFuncGetAttributes(&fa, k_tet_analytic<false, false>);
     cudaFuncGetAttributes(&fa, k_tet_energy<true, true>); cudaFuncGetAttributes(&fa, k_tet_energy<true, false>);

@@ -83,9 +83,11 @@ constexpr int MULTI_P_MAX = 64;
 struct MultiPArgs { int n; int pad; MultiPItem it[MULTI_P_MAX]; };
 // one launch for the P+G+H evaluation of the contact / friction tables (eval.cu)
 constexpr int MULTI_G_MAX = 40;
+constexpr int MULTI_G_FAMILIES = 6;   // contact d_d / rb_rb / rb_d, friction d_d / rb_rb / rb_d: one kernel each
 struct MultiGArgs { int n; int pad; int kind[MULTI_G_MAX]; int cta0[MULTI_G_MAX]; EvalArgs it[MULTI_G_MAX]; };
 int multi_g_ctas(int p_kind, int n_elem);
-void launch_pgh_multi(const MultiGArgs& M, int total_ctas, cudaStream_t s);
+int multi_g_family(int p_kind);
+void launch_pgh_multi(int family, const MultiGArgs& M, int total_ctas, cudaStream_t s);
 int multi_p_ctas(int p_kind, int n_elem);
 void launch_p_multi(const MultiPArgs& M, int total_ctas, cudaStream_t s);
 const KernelInfo* find_kernel(const char* name);
@@ -265,7 +267,7 @@ struct sb_context {
     sb::DynLayout* d_dyn_layout = nullptr;   // fused detection + evaluation (core.cu: eval_fused)
     sb::DynTotals* d_dyn_totals = nullptr;
     sb::DynTotals* h_dyn_totals = nullptr;
-    sb::MultiGArgs multi_g;        // staging of the multi-potential P+G+H launch (6 KB: not on the stack of every evaluation)
+    sb::MultiGArgs multi_g[sb::MULTI_G_FAMILIES];        // staging of the multi-potential P+G+H launch (6 KB: not on the stack of every evaluation)
     bool locate_pending = false;   // a scatter-mode pattern lookup rides with this evaluation's scalars
     bool pre_valid = false;
     uint64_t pre_state = 0, pre_static = 0;
