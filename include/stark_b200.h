@@ -134,10 +134,18 @@ SB_API int sb_bcsr_get(sb_context* ctx, int64_t* host_rows, int32_t* host_cols, 
  * Solves H du = -grad.  out_ok = 0 when p^T A p <= 0 was met (indefiniteness) or max_iterations was hit. */
 SB_API int sb_solve_pcg(sb_context* ctx, double abs_tol, double rel_tol, int max_iterations, int stop_on_indefiniteness,
                  int* out_iterations, int* out_ok, double* out_du_dot_grad, double* out_du_inf);
-/* DirectLLT branch of the same function (NewtonsMethod.cpp:395-418: to_triplets -> Eigen::SimplicialLLT): dense blocked
- * Cholesky in FP64 of the assembled matrix, n <= 32768 DoFs.  out_ok = 0 when the matrix is not positive definite
- * (Eigen's info() != Success). */
+/* DirectLLT branch of the same function (NewtonsMethod.cpp:395-418: to_triplets -> Eigen::SimplicialLLT): sparse FP64
+ * Cholesky of the assembled matrix -- reverse Cuthill-McKee ordering of the 3x3-block graph (dense rows last), factor stored
+ * as a row envelope of 64x64 tiles, tile POTRF / TRSM / SYRK on the device; ordering and envelope are cached while the
+ * pattern stays inside them.  The factor must fit SB_LLT_MAX_BYTES (environment, default 96 GiB) or the call fails with
+ * SB_ERR_STATE.  out_ok = 0 when the matrix is not positive definite (Eigen's info() != Success). */
 SB_API int sb_solve_llt(sb_context* ctx, int* out_ok, double* out_du_dot_grad, double* out_du_inf);
+/* diagnostics of the last sb_solve_llt: out5 = { tiles in the envelope, tile rows, factor bytes, orderings made so far,
+ * analyses made so far } */
+SB_API int sb_llt_stats(sb_context* ctx, double* out5);
+/* the fill-reducing ordering sb_solve_llt uses, on HOST arrays in sb_bcsr_get's layout (rows: nbr + 1 block offsets, cols:
+ * first scalar column of every block); out_perm[block row] = position in the elimination order.  Needs no GPU. */
+SB_API int sb_llt_order(int nbr, const unsigned long long* rows, const int32_t* cols, int32_t* out_perm);
 SB_API int sb_du_get(sb_context* ctx, double* host_du);
 
 /* ---- line search support ----------------------------------------------------------------------------------------------
@@ -214,7 +222,7 @@ typedef struct sb_newton_settings {
     double projection_eps;
     int32_t project_to_pd_use_mirroring, project_on_demand_countdown;
     double ppn_tightening_factor, ppn_release_factor;
-    int32_t linear_solver;     /* 0 DirectLLT (dense, n <= 32768), 1 BDPCG */
+    int32_t linear_solver;     /* 0 DirectLLT (sparse tile-envelope Cholesky), 1 BDPCG */
     int32_t cg_max_iterations;
     double cg_abs_tolerance, cg_rel_tolerance;
     int32_t cg_stop_on_indefiniteness;

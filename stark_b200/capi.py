@@ -76,7 +76,7 @@ SYMBOLS = [
     "sb_potential_create", "sb_potential_set_connectivity", "sb_potential_info", "sb_kernel_names",
     "sb_eval", "sb_eval_prelaunch", "sb_grad_get", "sb_potential_get_element_output", "sb_potential_get_block_rows", "sb_potential_get_hessians",
     "sb_project_to_pd", "sb_assemble", "sb_bcsr_info", "sb_bcsr_get",
-    "sb_solve_pcg", "sb_solve_llt", "sb_du_get", "sb_dofs_save", "sb_dofs_apply_step", "sb_du_scale",
+    "sb_solve_pcg", "sb_solve_llt", "sb_llt_stats", "sb_llt_order", "sb_du_get", "sb_dofs_save", "sb_dofs_apply_step", "sb_du_scale",
     "sb_contact_init", "sb_contact_add_mesh", "sb_contact_blacklist", "sb_contact_set_friction", "sb_contact_set_params",
     "sb_contact_update", "sb_contact_update_friction", "sb_contact_begin_time_step", "sb_contact_count_intersections", "sb_contact_get_proximity",
     "sb_contact_get_vertices", "sb_contact_set_vertices", "sb_contact_detect", "sb_contact_potential",
@@ -270,6 +270,11 @@ class Context:
         ok, dg, di = C.c_int(), C.c_double(), C.c_double()
         self._ck(self.lib.sb_solve_llt(self.h, C.byref(ok), C.byref(dg), C.byref(di)))
         return dict(ok=bool(ok.value), du_dot_grad=dg.value, du_inf=di.value)
+
+    def llt_stats(self):
+        o = (C.c_double * 5)()
+        self._ck(self.lib.sb_llt_stats(self.h, o))
+        return dict(tiles=int(o[0]), tile_rows=int(o[1]), factor_bytes=int(o[2]), orderings=int(o[3]), analyses=int(o[4]))
 
     def du(self):
         d = np.empty(self.ndofs(), dtype=np.float64)

@@ -1,4 +1,4 @@
-// Direct solve of the Newton system: dense blocked Cholesky (L L^T) in FP64.
+// Direct solve of the Newton system: sparse Cholesky (L L^T) in FP64 on a tile envelope.
 //
 // Replaces the DirectLLT branch of NewtonsMethod::_solve_linear_system (symx/solver/NewtonsMethod.cpp:395-418):
 // BlockedSparseMatrix::to_triplets (bsm/BlockedSparseMatrix.h:1365-1393) -> Eigen::SimplicialLLT (serial, re-analysed at
@@ -6,211 +6,455 @@
 // the Newton driver project more Hessians, exactly like `solver.info() != Eigen::Success`.
 //
 // The reference uses this path for its unit tests and small scenes (at 27 k DoFs it already needs 6.3 s per solve,
-// BASELINE.md section 2).  Here the float-stored BCSR matrix is expanded to a dense FP64 lower triangle and factorised
-// right-looking in 64 x 64 tiles: POTRF of the diagonal tile (one CTA), TRSM of the panel below it (one CTA per tile),
-// SYRK / GEMM update of the trailing tiles (one CTA per tile, 4 x 4 register blocking) -- n^3 / 3 FP64 flops on the
-// FP64 pipe (FP64 has no tcgen05 path).  Dense storage bounds the size: n <= 32,768 DoFs
-// (8.6 GB); larger systems are the block-Jacobi PCG's domain and are rejected with an error, never silently re-routed.
+// BASELINE.md section 2).  Here:
+//   * ordering (host, only when the pattern leaves the cached envelope): reverse Cuthill-McKee on the graph of 3x3 blocks
+//     from a pseudo-peripheral start; block rows far denser than the rest (a rigid body touched by hundreds of contacts)
+//     are taken out of the search and ordered last (an "arrowhead": they cost one full-width tile row each instead of
+//     widening the whole band);
+//   * storage: 64 x 64 FP64 tiles of the lower triangle, per tile row I the contiguous run of tiles F(I) .. I (row
+//     envelope; Cholesky fill stays inside it).  A mesh of n nodes with a separator of s nodes needs ~ n * 6 s doubles
+//     (C4, 27 k DoFs: 0.6 GB instead of 5.8 GB dense; C5, 524 k DoFs: ~25 GB -- HBM3e holds it);
+//   * numeric (device): right-looking over tile columns k: POTRF of the diagonal tile, TRSM of the tiles (I, k) of the rows
+//     whose envelope reaches column k (list built at analysis time), SYRK / GEMM update of the tile pairs of that list
+//     (one CTA per tile, 8 x 4 register blocking from transposed shared-memory panels).  FP64 throughout (the FP64 pipe: B200
+//     has no FP64 path through tcgen05, and its DMMA rate equals the DFMA rate);
+//   * triangular solves tile row by tile row with the same lists; du is returned in the caller's DoF order.
+// The analysis is cached: a matrix whose blocks all fall inside the cached envelope (the usual case from one Newton iteration
+// to the next, also when a few contact pairs changed) is factorised without any host work but one flag read-back.
 #include "internal.h"
 #include <algorithm>
+#include <cstdlib>
+#include <numeric>
 
 namespace sb {
 
 int bcsr_view(sb_context* ctx, int* nbr, size_t* nnzb, const unsigned long long** rows, const int32_t** cols, const float** vals);
 
 constexpr int NB = 64;                 // tile size
-constexpr int LLT_MAX_N = 32768;
+constexpr size_t TILE = (size_t)NB * NB;
 
 struct Direct {
-    DevBuf<double> A;                  // [np x np] row-major, lower triangle used
-    DevBuf<double> y;                  // [np] right-hand side / solution
-    int* d_fail = nullptr;
-    int* h_fail = nullptr;
+    // analysis (cached)
+    int nbr = 0, nt = 0;
+    bool have_order = false;
+    DevBuf<int32_t> perm;              // block row -> position in the elimination order
+    DevBuf<int32_t> F, F_new;          // first tile of every tile row (cached envelope / envelope of the current matrix)
+    DevBuf<unsigned long long> off;    // tile offset of every tile row's run
+    DevBuf<int32_t> act_ptr, act;      // per tile column k: the tile rows I > k with F(I) <= k (ascending)
+    std::vector<int32_t> h_F, h_act_ptr;
+    std::vector<int32_t> h_perm;
+    size_t n_tiles = 0, n_tiles_at_order = 0;
+    // numeric
+    DevBuf<double> T;                  // the tiles
+    DevBuf<double> W;                  // inverse of every diagonal tile's factor
+    DevBuf<double> z;                  // intermediate of the triangular solves
+    DevBuf<double> y;                  // [np] right-hand side / solution (elimination order)
+    int* d_flags = nullptr;            // [0] factorisation failed, [1] pattern outside the cached envelope
+    int* h_flags = nullptr;
     double* h_out = nullptr;           // du.grad, |du|_inf
+    // statistics of the last solve (sb_llt_stats)
+    double last_order_ms = 0, last_factor_ms = 0;
+    int64_t n_orderings = 0, n_analyses = 0;
 };
 void direct_destroy(sb_context* ctx)
 {
     Direct* D = ctx->direct;
     if (!D) return;
-    D->A.release(); D->y.release();
-    if (D->d_fail) cudaFree(D->d_fail);
-    if (D->h_fail) cudaFreeHost(D->h_fail);
+    D->perm.release(); D->F.release(); D->F_new.release(); D->off.release(); D->act_ptr.release(); D->act.release();
+    D->T.release(); D->W.release(); D->z.release(); D->y.release();
+    if (D->d_flags) cudaFree(D->d_flags);
+    if (D->h_flags) cudaFreeHost(D->h_flags);
     if (D->h_out) cudaFreeHost(D->h_out);
     delete D;
     ctx->direct = nullptr;
 }
 
-// A = dense(BCSR) on the lower triangle (i >= j); padding rows get a unit diagonal
-__global__ void k_dense_from_bcsr(const unsigned long long* __restrict__ rows, const int32_t* __restrict__ cols, const float* __restrict__ vals,
-                                  double* __restrict__ A, int nbr, int np)
+// ---------------------------------------------------------------- ordering (host)
+
+// Reverse Cuthill-McKee over the block graph; rows with more than `dense_deg` blocks are ordered last.
+static void rcm_order(int nbr, const std::vector<unsigned long long>& rows, const std::vector<int32_t>& cols, std::vector<int32_t>& perm)
+{
+    std::vector<int32_t> deg(nbr);
+    double avg = 0;
+    for (int i = 0; i < nbr; i++) { deg[i] = (int32_t)(rows[i + 1] - rows[i]); avg += deg[i]; }
+    avg /= std::max(nbr, 1);
+    const int dense_deg = std::max(96, (int)(8 * avg));
+    std::vector<uint8_t> state(nbr, 0);   // 0 unvisited, 1 visited, 2 dense (ordered last)
+    int n_dense = 0;
+    for (int i = 0; i < nbr; i++) if (deg[i] > dense_deg) { state[i] = 2; n_dense++; }
+    std::vector<int32_t> order; order.reserve(nbr);
+    std::vector<int32_t> level, next, nb;
+    std::vector<int32_t> mark(nbr, -1);
+    int stamp = 0;
+    // BFS from s over unvisited sparse rows without committing; returns the last level's minimum-degree node and the depth
+    auto probe = [&](int s, int& depth) {
+        stamp++;
+        level.assign(1, s); mark[s] = stamp; depth = 0;
+        int last_best = s;
+        while (!level.empty()) {
+            next.clear();
+            int best = level[0];
+            for (int v : level) {
+                if (deg[v] < deg[best]) best = v;
+                for (unsigned long long j = rows[v]; j < rows[v + 1]; j++) {
+                    const int w = cols[j] / 3;
+                    if (state[w] == 0 && mark[w] != stamp) { mark[w] = stamp; next.push_back(w); }
+                }
+            }
+            last_best = best;
+            depth++;
+            level.swap(next);
+        }
+        return last_best;
+    };
+    // seeds in ascending degree
+    std::vector<int32_t> seeds(nbr);
+    std::iota(seeds.begin(), seeds.end(), 0);
+    std::stable_sort(seeds.begin(), seeds.end(), [&](int a, int b) { return deg[a] < deg[b]; });
+    for (int s0 : seeds) {
+        if (state[s0] != 0) continue;
+        int s = s0, depth = 0, d2 = 0;
+        int e = probe(s, depth);
+        for (int it = 0; it < 3; it++) {
+            int e2 = probe(e, d2);
+            if (d2 <= depth) break;
+            s = e; e = e2; depth = d2;
+        }
+        // Cuthill-McKee from s
+        size_t head = order.size();
+        order.push_back(s); state[s] = 1;
+        while (head < order.size()) {
+            const int v = order[head++];
+            nb.clear();
+            for (unsigned long long j = rows[v]; j < rows[v + 1]; j++) {
+                const int w = cols[j] / 3;
+                if (state[w] == 0) { state[w] = 1; nb.push_back(w); }
+            }
+            std::sort(nb.begin(), nb.end(), [&](int a, int b) { return deg[a] != deg[b] ? deg[a] < deg[b] : a < b; });
+            order.insert(order.end(), nb.begin(), nb.end());
+        }
+    }
+    perm.assign(nbr, 0);
+    const int n_sparse = (int)order.size();
+    for (int p = 0; p < n_sparse; p++) perm[order[p]] = n_sparse - 1 - p;   // reversed
+    int q = n_sparse;
+    for (int i = 0; i < nbr; i++) if (state[i] == 2) perm[i] = q++;
+    (void)n_dense;
+}
+
+// ---------------------------------------------------------------- analysis kernels
+
+// F_new[I] = min tile column of the blocks of tile row I under the ordering (lower triangle of the symmetric matrix)
+__global__ void k_envelope(const unsigned long long* __restrict__ rows, const int32_t* __restrict__ cols, const int32_t* __restrict__ perm,
+                           int32_t* __restrict__ F_new, int nbr)
+{
+    const int br = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    if (br >= nbr) return;
+    const int pi = perm[br];
+    int lo = pi;
+    for (unsigned long long j = rows[br] + (threadIdx.x & 31); j < rows[br + 1]; j += 32) {
+        const int pj = perm[cols[j] / 3];
+        if (pj < lo) lo = pj;
+    }
+    for (int o = 16; o > 0; o >>= 1) lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    if ((threadIdx.x & 31) == 0) {
+        // scalar rows 3 pi .. 3 pi + 2 reach scalar column 3 lo: the block (also the diagonal one) may straddle two tile rows
+        const int tj = (3 * lo) / NB;
+        atomicMin(&F_new[(3 * pi) / NB], tj);
+        atomicMin(&F_new[(3 * pi + 2) / NB], tj);
+    }
+}
+__global__ void k_iota_tiles(int32_t* __restrict__ F, int nt)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nt) F[i] = i;
+}
+__global__ void k_envelope_inside(const int32_t* __restrict__ F_new, const int32_t* __restrict__ F, int nt, int* __restrict__ flags)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nt && F_new[i] < F[i]) flags[1] = 1;
+}
+
+// ---------------------------------------------------------------- numeric kernels
+
+__device__ __forceinline__ double* tile_ptr(double* T, const unsigned long long* __restrict__ off, const int32_t* __restrict__ F, int I, int J)
+{
+    return T + (off[I] + (unsigned long long)(J - F[I])) * TILE;
+}
+
+// scatter the BCSR blocks into the tiles (lower triangle in elimination order)
+__global__ void k_fill_tiles(const unsigned long long* __restrict__ rows, const int32_t* __restrict__ cols, const float* __restrict__ vals,
+                             const int32_t* __restrict__ perm, double* __restrict__ T, const unsigned long long* __restrict__ off,
+                             const int32_t* __restrict__ F, int nbr)
 {
     const int br = blockIdx.x;
     if (br >= nbr) return;
     const int g = threadIdx.x / 9, k = threadIdx.x % 9;   // 32 groups of nine threads, one BCSR block per group and trip
     const int r = k % 3, c = k / 3;                        // column-major inside the block
+    const int pi = perm[br];
     for (unsigned long long j = rows[br] + g; j < rows[br + 1]; j += 32) {
-        const int gi = 3 * br + r, gj = cols[j] + c;
-        if (gi >= gj) A[(size_t)gi * np + gj] = (double)vals[9 * j + k];
+        const int gi = 3 * pi + r, gj = 3 * perm[cols[j] / 3] + c;
+        if (gi >= gj) tile_ptr(T, off, F, gi / NB, gj / NB)[(gi % NB) * NB + (gj % NB)] = (double)vals[9 * j + k];
     }
 }
-__global__ void k_pad_diagonal(double* __restrict__ A, int n, int np)
+__global__ void k_pad_diagonal(double* __restrict__ T, const unsigned long long* __restrict__ off, const int32_t* __restrict__ F, int n, int np)
 {
     const int i = n + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < np) A[(size_t)i * np + i] = 1.0;
+    if (i < np) tile_ptr(T, off, F, i / NB, i / NB)[(i % NB) * NB + (i % NB)] = 1.0;
 }
 
-// Cholesky of the diagonal tile k (lower, in place); *fail = 1 on a non-positive pivot
-__global__ void __launch_bounds__(256) k_potrf_tile(double* __restrict__ A, int np, int k, int* __restrict__ fail)
-{
-    __shared__ double T[NB][NB + 1];
-    double* base = A + (size_t)(k * NB) * np + k * NB;
-    for (int t = threadIdx.x; t < NB * NB; t += 256) { const int i = t / NB, j = t % NB; T[i][j] = (j <= i) ? base[(size_t)i * np + j] : 0.0; }
-    __syncthreads();
-    for (int j = 0; j < NB; j++) {
-        const double d = T[j][j];
-        if (!(d > 0.0)) { if (threadIdx.x == 0) *fail = 1; return; }   // shared value: uniform exit
-        const double l = sqrt(d);
-        __syncthreads();
-        if (threadIdx.x == 0) T[j][j] = l;
-        for (int i = j + 1 + threadIdx.x; i < NB; i += 256) T[i][j] /= l;
-        __syncthreads();
-        // trailing update: T[i][c] -= T[i][j] * T[c][j] for j < c <= i
-        for (int t = threadIdx.x; t < NB * NB; t += 256) {
-            const int i = t / NB, c = t % NB;
-            if (c > j && c <= i) T[i][c] -= T[i][j] * T[c][j];
-        }
-        __syncthreads();
-    }
-    for (int t = threadIdx.x; t < NB * NB; t += 256) { const int i = t / NB, j = t % NB; if (j <= i) base[(size_t)i * np + j] = T[i][j]; }
-}
-
-// panel: A[i][k] <- A[i][k] L_kk^-T for every tile row i > k (one CTA per tile, one thread per tile row)
-__global__ void __launch_bounds__(NB) k_trsm_panel(double* __restrict__ A, int np, int k, const int* __restrict__ fail)
-{
-    if (*fail) return;
-    __shared__ double L[NB][NB + 1];
-    const int it = k + 1 + blockIdx.x;
-    const double* Lkk = A + (size_t)(k * NB) * np + k * NB;
-    for (int t = threadIdx.x; t < NB * NB; t += NB) { const int i = t / NB, j = t % NB; L[i][j] = Lkk[(size_t)i * np + j]; }
-    __syncthreads();
-    double* row = A + (size_t)(it * NB + threadIdx.x) * np + k * NB;
-    double x[NB];
-#pragma unroll
-    for (int j = 0; j < NB; j++) x[j] = row[j];
-#pragma unroll
-    for (int j = 0; j < NB; j++) {
-        double acc = x[j];
-#pragma unroll
-        for (int m = 0; m < j; m++) acc -= x[m] * L[j][m];
-        x[j] = acc / L[j][j];
-    }
-#pragma unroll
-    for (int j = 0; j < NB; j++) row[j] = x[j];
-}
-
-// trailing update: A[i][j] -= A[i][k] A[j][k]^T for k < j <= i (one CTA per tile; 16 x 16 threads, 4 x 4 outputs each)
-__global__ void __launch_bounds__(256) k_syrk_update(double* __restrict__ A, int np, int k, int nt, const int* __restrict__ fail)
-{
-    if (*fail) return;
-    // linear tile index -> (i, j) in the lower triangle of the trailing (nt - k - 1)^2 tile matrix
-    const int m = nt - k - 1;
-    int idx = blockIdx.x;
-    int ti = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
-    while ((ti + 1) * (ti + 2) / 2 <= idx) ti++;
-    while (ti * (ti + 1) / 2 > idx) ti--;
-    const int tj = idx - ti * (ti + 1) / 2;
-    if (ti >= m) return;
-    const int I = k + 1 + ti, J = k + 1 + tj;
-    constexpr int KH = NB / 2;   // the two 64 x 64 panels are streamed through shared memory in two K-halves (2 x 16.5 KB)
-    __shared__ double Pa[NB][KH + 1], Pb[NB][KH + 1];
-    const double* pa = A + (size_t)(I * NB) * np + k * NB;
-    const double* pb = A + (size_t)(J * NB) * np + k * NB;
-    const int tr = (threadIdx.x / 16) * 4, tc = (threadIdx.x % 16) * 4;
-    double acc[4][4] = {{0}};
-    for (int half = 0; half < 2; half++) {
-        __syncthreads();
-        for (int t = threadIdx.x; t < NB * KH; t += 256) {
-            const int r = t / KH, c = t % KH;
-            Pa[r][c] = pa[(size_t)r * np + half * KH + c];
-            Pb[r][c] = pb[(size_t)r * np + half * KH + c];
-        }
-        __syncthreads();
-        for (int q = 0; q < KH; q++) {
-            double a[4], b[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) { a[u] = Pa[tr + u][q]; b[u] = Pb[tc + u][q]; }
-#pragma unroll
-            for (int u = 0; u < 4; u++)
-#pragma unroll
-                for (int v = 0; v < 4; v++) acc[u][v] += a[u] * b[v];
-        }
-    }
-    double* out = A + (size_t)(I * NB) * np + J * NB;
-#pragma unroll
-    for (int u = 0; u < 4; u++)
-#pragma unroll
-        for (int v = 0; v < 4; v++)
-            if (I != J || tc + v <= tr + u) out[(size_t)(tr + u) * np + tc + v] -= acc[u][v];
-}
-
-// ---- triangular solves with one right-hand side ----
-// y_k <- L_kk^-1 y_k (forward) or L_kk^-T y_k (backward), one CTA
-__global__ void __launch_bounds__(NB) k_solve_diag(const double* __restrict__ A, double* __restrict__ y, int np, int k, int transposed)
+// Cholesky of the diagonal tile k and the inverse of its factor; flags[0] = 1 on a non-positive pivot.
+// One CTA of 256 threads.  Phase 1 (factor): the tile lives in registers, thread (ty, tx) of a 16 x 16 grid owns the 4 x 4
+// entries (ty + 16 a, tx + 16 b); step j: the owners of column j publish it through a double-buffered shared column (ONE
+// barrier per step), everybody scales by 1 / d (rsqrt(d)^2) and applies the rank-1 update to its registers.  Entries above
+// the diagonal carry garbage that never reaches a lower entry.  Phase 2 (inverse W = L^-1, needed as a GEMM operand by the
+// panel kernel and as a mat-vec operand by the triangular solves -- substitution would be a 2,016-long dependent chain per
+// row): column c of W by forward substitution in a 4-lane group, the column's entries in the lanes' registers (m = 4 s + q
+// in lane q), dot products split over the four lanes and closed with two shuffles.
+__global__ void __launch_bounds__(256) k_potrf_inv(double* __restrict__ T, const unsigned long long* __restrict__ off, const int32_t* __restrict__ F,
+                                                   double* __restrict__ Winv, int k, int* __restrict__ flags)
 {
     __shared__ double L[NB][NB + 1];
-    __shared__ double v[NB];
-    const double* Lkk = A + (size_t)(k * NB) * np + k * NB;
-    for (int t = threadIdx.x; t < NB * NB; t += NB) { const int i = t / NB, j = t % NB; L[i][j] = Lkk[(size_t)i * np + j]; }
-    v[threadIdx.x] = y[k * NB + threadIdx.x];
-    __syncthreads();
-    if (!transposed) {
-        for (int j = 0; j < NB; j++) {
-            if (threadIdx.x == j) v[j] /= L[j][j];
-            __syncthreads();
-            if (threadIdx.x > j) v[threadIdx.x] -= L[threadIdx.x][j] * v[j];
-            __syncthreads();
+    __shared__ double colbuf[2][NB];
+    __shared__ double invd[NB];
+    if (flags[0]) return;
+    double* base = tile_ptr(T, off, F, k, k);
+    const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+    double s[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int row = ty + 16 * a, col = tx + 16 * b;
+            s[a][b] = (col <= row) ? base[row * NB + col] : 0.0;
         }
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+        const int bj = j / 16, txj = j % 16;
+        double* cb = colbuf[j & 1];
+        if (tx == txj) {
+#pragma unroll
+            for (int a = 0; a < 4; a++) cb[ty + 16 * a] = s[a][bj];
+        }
+        __syncthreads();
+        const double d = cb[j];
+        if (!(d > 0.0)) { if (threadIdx.x == 0) flags[0] = 1; return; }   // shared value: uniform exit
+        const double rs = rsqrt(d);
+        const double rinv = rs * rs;
+        if (tx == txj) {
+#pragma unroll
+            for (int a = 0; a < 4; a++) { const int row = ty + 16 * a; L[row][j] = (row >= j) ? s[a][bj] * rs : 0.0; }
+            if (ty == 0) invd[j] = rs;
+        }
+        double ra[4], cbv[4];
+#pragma unroll
+        for (int a = 0; a < 4; a++) ra[a] = cb[ty + 16 * a];
+#pragma unroll
+        for (int b = 0; b < 4; b++) cbv[b] = cb[tx + 16 * b] * rinv;
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+            if (tx + 16 * b > j) {
+#pragma unroll
+                for (int a = 0; a < 4; a++) s[a][b] -= ra[a] * cbv[b];
+            }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < NB * NB; t += 256) { const int i = t / NB, j = t % NB; if (j <= i) base[t] = L[i][j]; }
+    // inverse: column c in the 4-lane group c
+    const int c = threadIdx.x / 4, q = threadIdx.x % 4;
+    double w[NB / 4];
+#pragma unroll
+    for (int u = 0; u < NB / 4; u++) w[u] = 0.0;
+#pragma unroll
+    for (int i = 0; i < NB; i++) {
+        double sum = 0.0;
+#pragma unroll
+        for (int u = 0; u < (i + 3) / 4; u++) {
+            const int m = 4 * u + q;
+            if (m < i) sum += L[i][m] * w[u];      // w[u] = 0 for m < c
+        }
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        const double val = (i < c) ? 0.0 : ((i == c) ? invd[i] : -sum * invd[i]);
+        if (q == i % 4) w[i / 4] = val;
+    }
+    double* W = Winv + (size_t)k * TILE;
+#pragma unroll
+    for (int u = 0; u < NB / 4; u++) W[(4 * u + q) * NB + c] = w[u];
+}
+
+// One kernel for the two tile products of the factorisation (one CTA of 128 threads per output tile; both operands are
+// transposed into shared memory ([q][row], pitch 66 doubles) so that a thread reads its 8 + 4 operands of one q with six
+// 128-bit loads and issues 32 DFMA on them):
+//   PANEL:  T(I, k) <- T(I, k) W_k^T            for the active rows I of column k   (the TRSM, as a product with L_kk^-1)
+//   UPDATE: T(I, J) -= T(I, k) T(J, k)^T        for the pairs J <= I of the active rows of column k   (SYRK / GEMM)
+constexpr int SP = NB + 2;
+template<bool PANEL>
+__global__ void __launch_bounds__(128) k_tile_product(double* __restrict__ T, const unsigned long long* __restrict__ off, const int32_t* __restrict__ F,
+                                                      const double* __restrict__ Winv, const int32_t* __restrict__ act, int m, int k, const int* __restrict__ flags)
+{
+    if (flags[0]) return;
+    extern __shared__ __align__(16) double sm[];
+    double* Pa = sm;                 // [NB][SP]
+    double* Pb = sm + NB * SP;
+    int I, J;
+    const double *pa, *pb;
+    if (PANEL) {
+        I = act[blockIdx.x]; J = k;
+        pa = tile_ptr(T, off, F, I, k);
+        pb = Winv + (size_t)k * TILE;
     } else {
-        for (int j = NB - 1; j >= 0; j--) {
-            if (threadIdx.x == j) v[j] /= L[j][j];
-            __syncthreads();
-            if (threadIdx.x < j) v[threadIdx.x] -= L[j][threadIdx.x] * v[j];
-            __syncthreads();
+        // linear index -> (a, b), b <= a, in the lower triangle of the m x m pair matrix
+        const int idx = blockIdx.x;
+        int a = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
+        while ((a + 1) * (a + 2) / 2 <= idx) a++;
+        while (a * (a + 1) / 2 > idx) a--;
+        const int b = idx - a * (a + 1) / 2;
+        if (a >= m) return;
+        I = act[a]; J = act[b];
+        pa = tile_ptr(T, off, F, I, k);
+        pb = tile_ptr(T, off, F, J, k);
+    }
+    {
+        // 16 loads in flight per thread and operand, then the transposing stores
+        double va[8], vb[8];
+#pragma unroll
+        for (int h = 0; h < 4; h++) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) { const int t = threadIdx.x + 128 * (8 * h + u); va[u] = pa[t]; vb[u] = pb[t]; }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int t = threadIdx.x + 128 * (8 * h + u);
+                const int r = t / NB, q = t % NB;
+                Pa[q * SP + r] = va[u];
+                Pb[q * SP + r] = vb[u];
+            }
         }
     }
-    y[k * NB + threadIdx.x] = v[threadIdx.x];
-}
-// forward: y_i -= A[i][k] y_k for tile rows i > k ; backward: y_i -= A[k][i]^T y_k for tile rows i < k
-__global__ void __launch_bounds__(NB) k_solve_update(const double* __restrict__ A, double* __restrict__ y, int np, int k, int transposed)
-{
-    __shared__ double yk[NB];
-    yk[threadIdx.x] = y[k * NB + threadIdx.x];
     __syncthreads();
-    double acc = 0.0;
-    if (!transposed) {
-        const int it = k + 1 + blockIdx.x;
-        const double* row = A + (size_t)(it * NB + threadIdx.x) * np + k * NB;
-        for (int j = 0; j < NB; j++) acc += row[j] * yk[j];
-        y[it * NB + threadIdx.x] -= acc;
-    } else {
-        const int it = blockIdx.x;   // < k
-        const double* col = A + (size_t)(k * NB) * np + it * NB + threadIdx.x;   // A[k*NB + j][it*NB + t]
-        for (int j = 0; j < NB; j++) acc += col[(size_t)j * np] * yk[j];
-        y[it * NB + threadIdx.x] -= acc;
+    const int tr = (threadIdx.x / 16) * 8, tc = (threadIdx.x % 16) * 4;
+    double acc[8][4];
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+#pragma unroll
+        for (int v = 0; v < 4; v++) acc[u][v] = 0.0;
+#pragma unroll 4
+    for (int q = 0; q < NB; q++) {
+        double av[8], bv[4];
+        const double2* ap = reinterpret_cast<const double2*>(Pa + q * SP + tr);
+        const double2* bp = reinterpret_cast<const double2*>(Pb + q * SP + tc);
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const double2 t2 = ap[u]; av[2 * u] = t2.x; av[2 * u + 1] = t2.y; }
+#pragma unroll
+        for (int u = 0; u < 2; u++) { const double2 t2 = bp[u]; bv[2 * u] = t2.x; bv[2 * u + 1] = t2.y; }
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+#pragma unroll
+            for (int v = 0; v < 4; v++) acc[u][v] += av[u] * bv[v];
+    }
+    double* out = tile_ptr(T, off, F, I, J);
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+        double* o = out + (tr + u) * NB + tc;
+        if (PANEL) {
+            *reinterpret_cast<double2*>(o) = make_double2(acc[u][0], acc[u][1]);
+            *reinterpret_cast<double2*>(o + 2) = make_double2(acc[u][2], acc[u][3]);
+        } else if (I != J) {
+            double2 o0 = *reinterpret_cast<double2*>(o), o1 = *reinterpret_cast<double2*>(o + 2);
+            o0.x -= acc[u][0]; o0.y -= acc[u][1]; o1.x -= acc[u][2]; o1.y -= acc[u][3];
+            *reinterpret_cast<double2*>(o) = o0; *reinterpret_cast<double2*>(o + 2) = o1;
+        } else {
+#pragma unroll
+            for (int v = 0; v < 4; v++) if (tc + v <= tr + u) o[v] -= acc[u][v];
+        }
     }
 }
 
-__global__ void k_rhs(const double* __restrict__ grad, double* __restrict__ y, int n, int np)
+// ---- triangular solves with one right-hand side, one launch per tile column ----
+// forward  (k ascending):  z_k = W_k y_k ;  y_I -= T(I, k) z_k for the active rows I of column k
+// backward (k descending): x_k = W_k^T z_k ; z_J -= T(k, J)^T x_k for J = F(k) .. k - 1
+// Every CTA (256 threads) recomputes the 64-vector of its column from the inverse diagonal factor (a mat-vec, no substitution
+// chain), CTA 0 stores it, and each CTA applies one tile.  `in` is only read at tile row k and updated at other rows; `out` is a
+// different array.
+template<bool BACKWARD>
+__global__ void __launch_bounds__(256) k_solve_step(const double* __restrict__ T, const unsigned long long* __restrict__ off, const int32_t* __restrict__ F,
+                                                    const double* __restrict__ Winv, const int32_t* __restrict__ act, double* __restrict__ in,
+                                                    double* __restrict__ out, int k)
+{
+    __shared__ double Ws[NB][NB + 1];
+    __shared__ double vin[NB], v[NB];
+    __shared__ double part[4][NB];
+    const double* W = Winv + (size_t)k * TILE;
+    {
+        double tmp[16];
+#pragma unroll
+        for (int u = 0; u < 16; u++) tmp[u] = W[threadIdx.x + 256 * u];
+#pragma unroll
+        for (int u = 0; u < 16; u++) { const int t = threadIdx.x + 256 * u; Ws[t / NB][t % NB] = tmp[u]; }
+    }
+    if (threadIdx.x < NB) vin[threadIdx.x] = in[k * NB + threadIdx.x];
+    // this CTA's tile, prefetched into registers while the mat-vec runs
+    const bool has_tile = BACKWARD ? (k - F[k] > 0) : (act != nullptr);
+    const double* tile = nullptr;
+    int target = 0;
+    if (has_tile) {
+        if (BACKWARD) { target = F[k] + blockIdx.x; tile = T + (off[k] + (unsigned long long)blockIdx.x) * TILE; }
+        else { target = act[blockIdx.x]; tile = T + (off[target] + (unsigned long long)(k - F[target])) * TILE; }
+    }
+    double tv[16];
+    if (has_tile) {
+#pragma unroll
+        for (int u = 0; u < 16; u++) tv[u] = tile[threadIdx.x + 256 * u];   // element (row 4 u + tid / 64, col tid % 64)
+    }
+    __syncthreads();
+    {
+        // v = W vin (forward) or W^T vin (backward): four threads per output entry
+        const int e = threadIdx.x / 4, q = threadIdx.x % 4;
+        double sum = 0.0;
+#pragma unroll
+        for (int u = 0; u < 16; u++) { const int j = 4 * u + q; sum += (BACKWARD ? Ws[j][e] : Ws[e][j]) * vin[j]; }
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        if (q == 0) { v[e] = sum; if (blockIdx.x == 0) out[k * NB + e] = sum; }
+    }
+    __syncthreads();
+    if (!has_tile) return;
+    const int col = threadIdx.x % NB, rq = threadIdx.x / NB;   // this thread holds tile rows 4 u + rq of column col
+    if (BACKWARD) {
+        // in_J[col] -= sum_j tile[j][col] v[j]
+        double sum = 0.0;
+#pragma unroll
+        for (int u = 0; u < 16; u++) sum += tv[u] * v[4 * u + rq];
+        part[rq][col] = sum;
+        __syncthreads();
+        if (threadIdx.x < NB) in[target * NB + threadIdx.x] -= part[0][threadIdx.x] + part[1][threadIdx.x] + part[2][threadIdx.x] + part[3][threadIdx.x];
+    } else {
+        // in_I[row] -= sum_c tile[row][c] v[c]: reduce every row over the 64 threads that hold its entries (two warps)
+        __shared__ double rowsum[NB][2];
+        const double vc = v[col];
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            double p = tv[u] * vc;
+            for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+            if ((threadIdx.x & 31) == 0) rowsum[4 * u + rq][(threadIdx.x >> 5) & 1] = p;
+        }
+        __syncthreads();
+        if (threadIdx.x < NB) in[target * NB + threadIdx.x] -= rowsum[threadIdx.x][0] + rowsum[threadIdx.x][1];
+    }
+}
+
+// y (elimination order) = -grad ; du = y back in DoF order
+__global__ void k_rhs(const double* __restrict__ grad, const int32_t* __restrict__ perm, double* __restrict__ y, int n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < np) y[i] = (i < n) ? -grad[i] : 0.0;
+    if (i < n) y[3 * perm[i / 3] + i % 3] = -grad[i];
 }
-__global__ void k_copy_n(double* __restrict__ dst, const double* __restrict__ src, int n)
+__global__ void k_unpermute(double* __restrict__ du, const double* __restrict__ y, const int32_t* __restrict__ perm, int n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[i] = src[i];
+    if (i < n) du[i] = y[3 * perm[i / 3] + i % 3];
 }
-// out[0] = du.grad, out[1] = |du|_inf (single CTA, fixed tree: the systems this path handles are small)
+// out[0] = du.grad, out[1] = |du|_inf (single CTA, fixed tree)
 __global__ void __launch_bounds__(1024) k_du_stats(const double* __restrict__ du, const double* __restrict__ grad, int n, double* __restrict__ out)
 {
     __shared__ double s0[32], s1[32];
@@ -226,6 +470,72 @@ __global__ void __launch_bounds__(1024) k_du_stats(const double* __restrict__ du
     }
 }
 
+// ---------------------------------------------------------------- host driver
+
+static size_t llt_max_bytes()
+{
+    const char* e = getenv("SB_LLT_MAX_BYTES");
+    if (e && *e) return (size_t)strtoull(e, nullptr, 10);
+    return (size_t)96 << 30;
+}
+
+// envelope of the current matrix under the current ordering -> F_new (device); flags[1] = it leaves the cached envelope
+static void envelope_of_current(sb_context* ctx, Direct& D, const unsigned long long* rows, const int32_t* cols, int nbr, int nt, bool compare)
+{
+    cudaStream_t st = ctx->stream;
+    k_iota_tiles<<<(nt + 255) / 256, 256, 0, st>>>(D.F_new.p, nt);
+    k_envelope<<<(nbr + 7) / 8, 256, 0, st>>>(rows, cols, D.perm.p, D.F_new.p, nbr);
+    if (compare) k_envelope_inside<<<(nt + 255) / 256, 256, 0, st>>>(D.F_new.p, D.F.p, nt, D.d_flags);
+    ctx->launches += compare ? 3 : 2;
+}
+
+// offsets and active lists from the envelope on the host; uploads them
+static int analyse(sb_context* ctx, Direct& D, int nt)
+{
+    cudaStream_t st = ctx->stream;
+    D.h_F.resize(nt);
+    SB_CUDA(ctx, cudaMemcpyAsync(D.h_F.data(), D.F_new.p, sizeof(int32_t) * nt, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(ctx, cudaStreamSynchronize(st));
+    std::vector<unsigned long long> off(nt + 1);
+    off[0] = 0;
+    for (int I = 0; I < nt; I++) off[I + 1] = off[I] + (unsigned long long)(I - D.h_F[I] + 1);
+    D.n_tiles = (size_t)off[nt];
+    // active rows of column k: the rows I > k with F(I) <= k
+    D.h_act_ptr.assign(nt + 1, 0);
+    for (int I = 0; I < nt; I++)
+        for (int k = D.h_F[I]; k < I; k++) D.h_act_ptr[k + 1]++;
+    for (int k = 0; k < nt; k++) D.h_act_ptr[k + 1] += D.h_act_ptr[k];
+    std::vector<int32_t> act((size_t)D.h_act_ptr[nt]);
+    {
+        std::vector<int32_t> fill(D.h_act_ptr.begin(), D.h_act_ptr.end() - 1);
+        for (int I = 0; I < nt; I++)   // ascending I: every column's list comes out sorted
+            for (int k = D.h_F[I]; k < I; k++) act[(size_t)fill[k]++] = I;
+    }
+    D.off.ensure(nt + 1); D.F.ensure(nt); D.act_ptr.ensure(nt + 1); D.act.ensure(std::max<size_t>(act.size(), 1));
+    SB_CUDA(ctx, cudaMemcpyAsync(D.off.p, off.data(), sizeof(unsigned long long) * (nt + 1), cudaMemcpyHostToDevice, st));
+    SB_CUDA(ctx, cudaMemcpyAsync(D.F.p, D.h_F.data(), sizeof(int32_t) * nt, cudaMemcpyHostToDevice, st));
+    if (!act.empty()) SB_CUDA(ctx, cudaMemcpyAsync(D.act.p, act.data(), sizeof(int32_t) * act.size(), cudaMemcpyHostToDevice, st));
+    SB_CUDA(ctx, cudaStreamSynchronize(st));   // the host vectors go out of scope
+    D.n_analyses++;
+    return 0;
+}
+
+static int reorder(sb_context* ctx, Direct& D, const unsigned long long* rows, const int32_t* cols, int nbr, size_t nnzb)
+{
+    cudaStream_t st = ctx->stream;
+    std::vector<unsigned long long> h_rows(nbr + 1);
+    std::vector<int32_t> h_cols(nnzb);
+    SB_CUDA(ctx, cudaMemcpyAsync(h_rows.data(), rows, sizeof(unsigned long long) * (nbr + 1), cudaMemcpyDeviceToHost, st));
+    if (nnzb) SB_CUDA(ctx, cudaMemcpyAsync(h_cols.data(), cols, sizeof(int32_t) * nnzb, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(ctx, cudaStreamSynchronize(st));
+    rcm_order(nbr, h_rows, h_cols, D.h_perm);
+    D.perm.ensure(nbr);
+    SB_CUDA(ctx, cudaMemcpyAsync(D.perm.p, D.h_perm.data(), sizeof(int32_t) * nbr, cudaMemcpyHostToDevice, st));
+    SB_CUDA(ctx, cudaStreamSynchronize(st));
+    D.n_orderings++;
+    return 0;
+}
+
 int solve_llt_internal(sb_context* ctx, int* out_ok, double* out_du_dot_grad, double* out_du_inf)
 {
     int nbr; size_t nnzb; const unsigned long long* rows; const int32_t* cols; const float* vals;
@@ -233,59 +543,111 @@ int solve_llt_internal(sb_context* ctx, int* out_ok, double* out_du_dot_grad, do
     if (r) return r;
     const int n = 3 * nbr;
     if (n != ctx->ndofs) return fail(ctx, SB_ERR_STATE, "sb_solve_llt: matrix and DoF vector sizes differ");
-    if (n > LLT_MAX_N) return fail(ctx, SB_ERR_STATE, "sb_solve_llt: the direct solver is dense (n <= 32768 DoFs); use the block-Jacobi PCG for larger systems");
     StageTimer timer(ctx, ST_PCG);
     if (!ctx->direct) {
         ctx->direct = new Direct();
-        cudaMalloc(&ctx->direct->d_fail, sizeof(int));
-        cudaMallocHost(&ctx->direct->h_fail, sizeof(int));
+        cudaMalloc(&ctx->direct->d_flags, 2 * sizeof(int));
+        cudaMallocHost(&ctx->direct->h_flags, 2 * sizeof(int));
         cudaMallocHost(&ctx->direct->h_out, 2 * sizeof(double));
+        cudaFuncSetAttribute(k_tile_product<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * NB * SP * sizeof(double)));
+        cudaFuncSetAttribute(k_tile_product<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * NB * SP * sizeof(double)));
     }
     Direct& D = *ctx->direct;
     cudaStream_t st = ctx->stream;
     const int nt = (n + NB - 1) / NB, np = nt * NB;
-    D.A.ensure((size_t)np * np);
-    D.y.ensure(np);
+    D.F_new.ensure(nt);
+    SB_CUDA(ctx, cudaMemsetAsync(D.d_flags, 0, 2 * sizeof(int), st));
+
+    // ---- analysis: reuse the cached ordering + envelope when the matrix fits inside
+    bool need_analysis = !D.have_order || D.nbr != nbr || D.nt != nt;
+    if (need_analysis) {
+        if ((r = reorder(ctx, D, rows, cols, nbr, nnzb))) return r;
+        envelope_of_current(ctx, D, rows, cols, nbr, nt, false);
+        if ((r = analyse(ctx, D, nt))) return r;
+        D.n_tiles_at_order = D.n_tiles;
+        D.have_order = true; D.nbr = nbr; D.nt = nt;
+    } else {
+        envelope_of_current(ctx, D, rows, cols, nbr, nt, true);
+        SB_CUDA(ctx, cudaMemcpyAsync(D.h_flags, D.d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        SB_CUDA(ctx, cudaStreamSynchronize(st));
+        if (D.h_flags[1]) {
+            // outside the cached envelope: new envelope under the old ordering; when that costs much more storage than the
+            // ordering was made for (contacts between far-apart nodes), order again
+            if ((r = analyse(ctx, D, nt))) return r;
+            if (D.n_tiles > D.n_tiles_at_order + D.n_tiles_at_order / 4 + 8) {
+                if ((r = reorder(ctx, D, rows, cols, nbr, nnzb))) return r;
+                envelope_of_current(ctx, D, rows, cols, nbr, nt, false);
+                if ((r = analyse(ctx, D, nt))) return r;
+                D.n_tiles_at_order = D.n_tiles;
+            }
+            SB_CUDA(ctx, cudaMemsetAsync(D.d_flags, 0, 2 * sizeof(int), st));
+        }
+    }
+    if (D.n_tiles * TILE * sizeof(double) > llt_max_bytes())
+        return fail(ctx, SB_ERR_STATE, "sb_solve_llt: the factor's tile envelope needs " + std::to_string((D.n_tiles * TILE * sizeof(double)) >> 20) +
+                                           " MiB (limit SB_LLT_MAX_BYTES); use the block-Jacobi PCG for this system");
+    D.T.ensure(D.n_tiles * TILE);
+    if (!D.T.p) return fail(ctx, SB_ERR_CUDA, "sb_solve_llt: out of device memory for the factor");
+    D.W.ensure((size_t)nt * TILE);
+    D.y.ensure(np); D.z.ensure(np);
     ctx->du.ensure(n);
-    SB_CUDA(ctx, cudaMemsetAsync(D.A.p, 0, sizeof(double) * (size_t)np * np, st));
-    SB_CUDA(ctx, cudaMemsetAsync(D.d_fail, 0, sizeof(int), st));
-    k_dense_from_bcsr<<<nbr, 288, 0, st>>>(rows, cols, vals, D.A.p, nbr, np);
-    if (np > n) k_pad_diagonal<<<(np - n + 63) / 64, 64, 0, st>>>(D.A.p, n, np);
+
+    // ---- numeric factorisation
+    static const bool dump = getenv("SB_LLT_DUMP") != nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+    if (dump) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventRecord(e0, st); }
+    SB_CUDA(ctx, cudaMemsetAsync(D.T.p, 0, sizeof(double) * D.n_tiles * TILE, st));
+    SB_CUDA(ctx, cudaMemsetAsync(D.y.p, 0, sizeof(double) * np, st));
+    k_fill_tiles<<<nbr, 288, 0, st>>>(rows, cols, vals, D.perm.p, D.T.p, D.off.p, D.F.p, nbr);
+    if (np > n) k_pad_diagonal<<<(np - n + 63) / 64, 64, 0, st>>>(D.T.p, D.off.p, D.F.p, n, np);
     ctx->launches += 2;
+    const size_t syrk_smem = 2 * NB * SP * sizeof(double);
     for (int k = 0; k < nt; k++) {
-        k_potrf_tile<<<1, 256, 0, st>>>(D.A.p, np, k, D.d_fail);
+        k_potrf_inv<<<1, 256, 0, st>>>(D.T.p, D.off.p, D.F.p, D.W.p, k, D.d_flags);
         ctx->launches++;
-        const int m = nt - k - 1;
+        const int m = D.h_act_ptr[k + 1] - D.h_act_ptr[k];
         if (m > 0) {
-            k_trsm_panel<<<m, NB, 0, st>>>(D.A.p, np, k, D.d_fail);
-            k_syrk_update<<<m * (m + 1) / 2, 256, 0, st>>>(D.A.p, np, k, nt, D.d_fail);
+            const int32_t* act = D.act.p + D.h_act_ptr[k];
+            k_tile_product<true><<<m, 128, syrk_smem, st>>>(D.T.p, D.off.p, D.F.p, D.W.p, act, m, k, D.d_flags);
+            k_tile_product<false><<<(unsigned)((size_t)m * (m + 1) / 2), 128, syrk_smem, st>>>(D.T.p, D.off.p, D.F.p, D.W.p, act, m, k, D.d_flags);
             ctx->launches += 2;
         }
     }
-    SB_CUDA(ctx, cudaMemcpyAsync(D.h_fail, D.d_fail, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SB_CUDA(ctx, cudaMemcpyAsync(D.h_flags, D.d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (dump) cudaEventRecord(e1, st);
+    // ---- triangular solves (queued behind the factorisation; their results are ignored when it failed)
+    k_rhs<<<(n + 255) / 256, 256, 0, st>>>(ctx->grad.p, D.perm.p, D.y.p, n);
+    for (int k = 0; k < nt; k++) {
+        const int m = D.h_act_ptr[k + 1] - D.h_act_ptr[k];
+        k_solve_step<false><<<std::max(m, 1), 256, 0, st>>>(D.T.p, D.off.p, D.F.p, D.W.p, m > 0 ? D.act.p + D.h_act_ptr[k] : nullptr, D.y.p, D.z.p, k);
+    }
+    for (int k = nt - 1; k >= 0; k--) {
+        const int m = k - D.h_F[k];
+        k_solve_step<true><<<std::max(m, 1), 256, 0, st>>>(D.T.p, D.off.p, D.F.p, D.W.p, nullptr, D.z.p, D.y.p, k);
+    }
+    k_unpermute<<<(n + 255) / 256, 256, 0, st>>>(ctx->du.p, D.y.p, D.perm.p, n);
+    k_du_stats<<<1, 1024, 0, st>>>(ctx->du.p, ctx->grad.p, n, ctx->d_scalars + 4);
+    ctx->launches += 2 * nt + 3;
+    SB_CUDA(ctx, cudaMemcpyAsync(D.h_out, ctx->d_scalars + 4, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (dump) cudaEventRecord(e2, st);
     SB_CUDA(ctx, cudaStreamSynchronize(st));
     SB_CUDA(ctx, cudaGetLastError());
-    if (*D.h_fail) {   // not positive definite: Eigen::SimplicialLLT::info() != Success
+    if (dump) {
+        float f = 0, s2 = 0;
+        cudaEventElapsedTime(&f, e0, e1); cudaEventElapsedTime(&s2, e1, e2);
+        size_t pairs = 0; int mmax = 0;
+        for (int k = 0; k < nt; k++) { const size_t m = D.h_act_ptr[k + 1] - D.h_act_ptr[k]; pairs += m * (m + 1) / 2; mmax = std::max(mmax, (int)m); }
+        fprintf(stderr, "LLT n %d tile rows %d tiles %zu (%.1f MiB) syrk tiles %zu (%.2f GFLOP) max active %d | factor %.3f ms solve %.3f ms ok %d | orderings %lld analyses %lld\n",
+                n, nt, D.n_tiles, D.n_tiles * TILE * 8.0 / 1048576.0, pairs, pairs * 2.0 * NB * NB * NB * 1e-9, mmax, f, s2, !D.h_flags[0],
+                (long long)D.n_orderings, (long long)D.n_analyses);
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    }
+    if (D.h_flags[0]) {   // not positive definite: Eigen::SimplicialLLT::info() != Success
         if (out_ok) *out_ok = 0;
         if (out_du_dot_grad) *out_du_dot_grad = 0.0;
         if (out_du_inf) *out_du_inf = 0.0;
         return 0;
     }
-    k_rhs<<<(np + 255) / 256, 256, 0, st>>>(ctx->grad.p, D.y.p, n, np);
-    for (int k = 0; k < nt; k++) {
-        k_solve_diag<<<1, NB, 0, st>>>(D.A.p, D.y.p, np, k, 0);
-        if (nt - k - 1 > 0) k_solve_update<<<nt - k - 1, NB, 0, st>>>(D.A.p, D.y.p, np, k, 0);
-    }
-    for (int k = nt - 1; k >= 0; k--) {
-        k_solve_diag<<<1, NB, 0, st>>>(D.A.p, D.y.p, np, k, 1);
-        if (k > 0) k_solve_update<<<k, NB, 0, st>>>(D.A.p, D.y.p, np, k, 1);
-    }
-    k_copy_n<<<(n + 255) / 256, 256, 0, st>>>(ctx->du.p, D.y.p, n);
-    k_du_stats<<<1, 1024, 0, st>>>(ctx->du.p, ctx->grad.p, n, ctx->d_scalars + 4);
-    ctx->launches += 4 * nt + 3;
-    SB_CUDA(ctx, cudaMemcpyAsync(D.h_out, ctx->d_scalars + 4, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    SB_CUDA(ctx, cudaStreamSynchronize(st));
-    SB_CUDA(ctx, cudaGetLastError());
     if (out_ok) *out_ok = 1;
     if (out_du_dot_grad) *out_du_dot_grad = D.h_out[0];
     if (out_du_inf) *out_du_inf = D.h_out[1];
@@ -301,4 +663,28 @@ extern "C" int sb_solve_llt(sb_context* ctx, int* out_ok, double* out_du_dot_gra
     if (!ctx) return SB_ERR_ARG;
     if (!ctx->have_pgh) return fail(ctx, SB_ERR_STATE, "sb_solve_llt: no gradient: call sb_eval(SB_EVAL_PGH) first");
     return solve_llt_internal(ctx, out_ok, out_du_dot_grad, out_du_inf);
+}
+
+// n_tiles, n_tile_rows, factor bytes, orderings made, analyses made (diagnostic; tests and bench.py)
+extern "C" int sb_llt_stats(sb_context* ctx, double* out5)
+{
+    if (!ctx || !out5) return SB_ERR_ARG;
+    for (int i = 0; i < 5; i++) out5[i] = 0.0;
+    if (!ctx->direct) return 0;
+    const Direct& D = *ctx->direct;
+    out5[0] = (double)D.n_tiles; out5[1] = (double)D.nt; out5[2] = (double)(D.n_tiles * TILE * sizeof(double));
+    out5[3] = (double)D.n_orderings; out5[4] = (double)D.n_analyses;
+    return 0;
+}
+
+// the ordering alone, on host arrays (no GPU involved): block rows / first scalar columns as sb_bcsr_get returns them
+extern "C" int sb_llt_order(int nbr, const unsigned long long* rows, const int32_t* cols, int32_t* out_perm)
+{
+    if (nbr < 0 || !rows || !out_perm || (rows[nbr] && !cols)) return SB_ERR_ARG;
+    std::vector<unsigned long long> r(rows, rows + nbr + 1);
+    std::vector<int32_t> c(cols, cols + rows[nbr]);
+    std::vector<int32_t> perm;
+    rcm_order(nbr, r, c, perm);
+    std::copy(perm.begin(), perm.end(), out_perm);
+    return 0;
 }

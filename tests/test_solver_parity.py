@@ -165,9 +165,9 @@ def _dense(rows, cols, vals):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("fixture", ["tetdrop_n3", "tetbar_n2", "cloth_n8", "attach_n6"])
+@pytest.mark.parametrize("fixture", ["tetdrop_n3", "tetdrop_n5", "tetbar_n2", "cloth_n8", "cloth_shells_n8", "attach_n6", "tetchain_n3", "boxes", "joints"])
 def test_direct_llt(fixture):
-    """DirectLLT branch (NewtonsMethod.cpp:395-418): the dense blocked Cholesky solves the assembled (float-stored) matrix
+    """DirectLLT branch (NewtonsMethod.cpp:395-418): the sparse tile-envelope Cholesky solves the assembled (float-stored) matrix
     like a FP64 direct solver does; an indefinite matrix is reported as a failed solve."""
     capi, ctx, g, handles = setup(fixture)
     ctx.eval("PGH")
@@ -185,6 +185,13 @@ def test_direct_llt(fixture):
     assert abs(out["du_dot_grad"] - du @ grad) <= 1e-12 * abs(du @ grad)
     assert out["du_inf"] == np.abs(du).max()
     assert out["du_dot_grad"] < 0
+    # a second factorisation of the same pattern reuses ordering + envelope (no host analysis) and gives the same result
+    st0 = ctx.llt_stats()
+    assert st0["orderings"] == 1 and st0["analyses"] == 1 and st0["tiles"] <= st0["tile_rows"] * (st0["tile_rows"] + 1) // 2
+    out2 = ctx.solve_llt()
+    st1 = ctx.llt_stats()
+    assert out2["ok"] and st1["orderings"] == 1 and st1["analyses"] == 1
+    assert np.array_equal(ctx.du(), du)
     ctx.close()
 
 
