@@ -250,6 +250,30 @@ SB_API int sb_newton_timer_begin(sb_context* ctx);
 SB_API void sb_newton_default_settings(sb_newton_settings* s);   /* STARK's defaults (S/core/Settings.cpp:40-54) */
 SB_API int sb_newton_solve(sb_context* ctx, const sb_newton_settings* settings, sb_newton_stats* stats);
 
+/* ---- multi-GPU: distributed linear solve over peer memory ---------------------------------------------------------------------
+ * replaces: nothing in the reference (it is single-process OpenMP); shards what SURVEY.md 8(e) names -- the SpMV
+ * (bsm/BlockedSparseMatrix.h:988-1138) and the PCG body (bsm/solve_pcg.h:174-222) -- over the GPUs of one NVSwitch domain.
+ * One process (or thread) per GPU, every rank drives the SAME scene (replicated state, evaluation and assembly); after
+ * sb_dist_init + sb_dist_connect every sb_solve_pcg / BDPCG solve of sb_newton_solve is ONE solve shared by all ranks: the
+ * persistent kernels of the ranks form one virtual grid, each keeps 1 / world of the matrix in shared memory, and the halo of
+ * u, the dot-product partials, the barrier and du cross GPUs through NVLink loads / stores issued inside the kernel on
+ * buffers mapped with CUDA IPC.  All ranks must issue the same sequence of solves; a rank that waits longer than
+ * SB_DIST_TIMEOUT_S (environment, default 30 s) at a barrier fails the solve with SB_ERR_CUDA instead of hanging.
+ * sb_dist_init allocates the rank's peer buffer (sized for max_dofs) and returns its cudaIpcMemHandle_t (64 bytes);
+ * sb_dist_connect takes the world x 64 bytes of all ranks' handles (gathered by the caller, e.g. torch.distributed). */
+SB_API int sb_dist_init(sb_context* ctx, int rank, int world, long long max_dofs, unsigned char* out_handle64);
+SB_API int sb_dist_connect(sb_context* ctx, const unsigned char* handles);
+/* ranks inside one process connect by pointer instead (bases[q] = sb_dist_local_base of rank q's context) */
+SB_API int sb_dist_connect_ptrs(sb_context* ctx, void* const* bases);
+SB_API void* sb_dist_local_base(sb_context* ctx);
+/* out3 = { barriers completed, distributed solves, bytes of the peer buffer } */
+SB_API int sb_dist_stats(sb_context* ctx, int* out_rank, int* out_world, double* out3);
+/* The row partition and the halo send lists of a distributed solve, on HOST arrays in sb_bcsr_get's layout (no GPU needed):
+ * out_bounds[world + 1] = first block row of every rank; out_needmask[nbr]: for the block rows `rank` owns, bit q is set when
+ * rank q's rows reference that column of u (the owner pushes the row to q every iteration).  grid = CTAs per rank. */
+SB_API int sb_dist_plan(int nbr, const unsigned long long* rows, const int32_t* cols, int world, int grid, int rank,
+                        int32_t* out_bounds, unsigned char* out_needmask);
+
 /* ---- measurement ----------------------------------------------------------------------------------------------------------
  * Launches the element kernel of ONE potential `reps` times on the current state (mode as sb_eval) and returns the average
  * launch duration measured with CUDA events on the context stream (bench.py roofline). */

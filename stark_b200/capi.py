@@ -82,6 +82,7 @@ SYMBOLS = [
     "sb_contact_get_vertices", "sb_contact_set_vertices", "sb_contact_detect", "sb_contact_potential",
     "sb_newton_timer_begin", "sb_newton_default_settings", "sb_newton_solve", "sb_profile_potential",
     "sb_profile_stages", "sb_profile_report",
+    "sb_dist_init", "sb_dist_connect", "sb_dist_connect_ptrs", "sb_dist_local_base", "sb_dist_stats", "sb_dist_plan",
 ]
 
 
@@ -97,6 +98,11 @@ def load():
     lib.sb_kernel_names.restype = C.c_char_p
     lib.sb_profile_report.restype = C.c_char_p
     lib.sb_get_stream.restype = C.c_void_p
+    lib.sb_dist_local_base.restype = C.c_void_p
+    lib.sb_dist_local_base.argtypes = [C.c_void_p]
+    lib.sb_dist_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_void_p]
+    lib.sb_dist_connect.argtypes = [C.c_void_p, C.c_void_p]
+    lib.sb_dist_connect_ptrs.argtypes = [C.c_void_p, C.c_void_p]
     lib.sb_launch_count.restype = C.c_int64
     lib.sb_destroy.restype = None
     lib.sb_newton_default_settings.restype = None

@@ -951,6 +951,7 @@ void sb_destroy(sb_context* ctx)
     ctx->host_regions.clear();
     assembly_destroy(ctx);
     pcg_destroy(ctx);
+    dist_destroy(ctx);
     contact_destroy(ctx);
     projector_destroy(ctx);
     direct_destroy(ctx);

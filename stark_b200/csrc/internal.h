@@ -203,6 +203,7 @@ struct Issuer {
 
 struct Assembly;   // assembly.cu
 struct Pcg;        // pcg.cu
+struct Dist;       // pcg.cu: peer-memory state of a distributed solve
 struct Contact;    // contact.cu
 struct Projector;  // project.cu
 struct Direct;     // direct.cu
@@ -288,6 +289,7 @@ struct sb_context {
     sb::Contact* contact = nullptr;
     sb::Projector* projector = nullptr;
     sb::Direct* direct = nullptr;
+    sb::Dist* dist = nullptr;
 };
 
 namespace sb {
@@ -308,6 +310,7 @@ void pcg_destroy(sb_context* ctx);
 void contact_destroy(sb_context* ctx);
 void projector_destroy(sb_context* ctx);
 void direct_destroy(sb_context* ctx);
+void dist_destroy(sb_context* ctx);
 int solve_llt_internal(sb_context* ctx, int* out_ok, double* out_du_dot_grad, double* out_du_inf);
 int assemble_internal(sb_context* ctx);
 // where the blocks of an element land in the assembled matrix: sources are numbered static-first; a static source maps

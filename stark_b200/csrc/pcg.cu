@@ -34,13 +34,15 @@
 #include <vector>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 namespace sb {
 
 int bcsr_view(sb_context* ctx, int* nbr, size_t* nnzb, const unsigned long long** rows, const int32_t** cols, const float** vals);
 
 constexpr int PCG_THREADS = 1024;     // one CTA per SM
-constexpr int PCG_MAX_BLOCKS = 1024;  // upper bound of the cooperative grid (partial-sum arrays)
+constexpr int PCG_MAX_BLOCKS = 1280;  // upper bound of the (virtual) cooperative grid: 8 ranks x 148 CTAs (partial-sum arrays)
+constexpr int DIST_MAX_WORLD = 8;     // ranks of one distributed solve (one NVSwitch domain)
 constexpr int LANES_PER_ROW = 4;      // lanes cooperating on one block row of the SpMV
 constexpr int LONG_ROW = 96;          // rows with more blocks (rigid bodies in contact with many nodes) are cut into segments
 constexpr int PCG_TILE_BLOCKS = 768;                // blocks per streamed tile (multiple of 4: 16-byte granularity of the bulk copies)
@@ -53,11 +55,35 @@ constexpr int MAX_LONG_ROWS = 32;     // per CTA; further long rows fall back to
 struct PcgResult {
     double du_dot_grad, du_inf, error, bb;
     int it;             // completed iterations
-    int done;           // 1 converged, 2 indefinite, 3 max iterations
+    int done;           // 1 converged, 2 indefinite, 3 max iterations, 4 aborted (a peer rank never arrived at a barrier)
     int found_indef;
     int pad;
     unsigned long long t_start, t_loaded, t_loop, t_end;   // %globaltimer (ns) of CTA 0: kernel entry, slices resident, first iteration, exit
     long long c_spmv, c_bar, c_red, c_vec, c_win;          // clock64 cycles of CTA 0 inside the loop (only when instrumented)
+    unsigned long long barriers;                           // grid barriers this solve executed (the distributed counter never resets)
+};
+
+// Distributed solve (one process per GPU, all ranks hold the same assembled matrix and right-hand side): the W x G CTAs of all
+// ranks form ONE virtual grid, CTA (rank, c) takes slice rank * G + c of the same row partition, so every rank keeps 1 / W of the
+// matrix in its shared memory.  What crosses GPUs goes through PEER MEMORY inside the persistent kernel (NVLink loads / stores
+// on buffers opened with CUDA IPC), no collective library and no kernel boundary:
+//   * u = M^-1 r: the owner stores a row into its own copy and into the copy of every rank whose rows reference that column
+//     (needmask, built per solve from the replicated pattern: the halo of a slab, plus rigid bodies / far contacts);
+//   * dot products: every CTA stores its partial into the partial arrays of ALL ranks; after the barrier every CTA of every rank
+//     re-reduces the same W x G values in the same order (identical scalars and decisions everywhere, as on one GPU);
+//   * barrier: one release-reduction on every rank's counter, acquire spin on the own one (flat: one NVLink hop);
+//   * du: every CTA stores its slice of the solution into every rank's copy.
+struct DistArgs {
+    int world, rank;
+    unsigned long long epoch_base;            // barriers completed by earlier solves (monotonic 64-bit counters, never reset)
+    unsigned long long timeout_ns;            // a barrier that waits longer aborts the solve (done = 4) instead of hanging the GPU
+    unsigned long long* bar[DIST_MAX_WORLD];  // every rank's barrier counter
+    double* part[DIST_MAX_WORLD];             // every rank's partial arrays (the set of this solve's parity)
+    double* u[DIST_MAX_WORLD];
+    double* u4[DIST_MAX_WORLD];
+    double* du[DIST_MAX_WORLD];
+    const unsigned char* needmask;            // [nbr] bit q: rank q reads this block row of u (own bit clear)
+    int* abort_flag;                          // local: set by the first CTA that timed out
 };
 
 struct PcgArgs {
@@ -81,6 +107,7 @@ struct PcgArgs {
     int force_stream;               // test hook: never keep the matrix slice resident
     int tiled;                      // experimental: stream through TMA-filled tile buffers (MODE 3) instead of ordinary loads
     long long* dbg;                 // [5 x grid + 2] per-CTA cycle counters (SB_PCG_DUMP diagnostics, else null)
+    DistArgs d;                     // world <= 1: single GPU
 };
 
 struct Pcg {
@@ -95,6 +122,46 @@ struct Pcg {
     unsigned smem_bytes = 0;
     unsigned smem_launch_last = 0;
 };
+// Peer-memory state of the distributed solve: ONE communication buffer per rank (cudaMalloc, exported with CUDA IPC), the same
+// layout on every rank: [barrier counter | 2 sets of partial sums | u | u4 | du].
+struct Dist {
+    int world = 1, rank = 0;
+    size_t max_dofs = 0;
+    unsigned char* base[DIST_MAX_WORLD] = {nullptr};   // base[rank] is the own buffer
+    bool opened[DIST_MAX_WORLD] = {false};              // peer mappings opened through IPC (closed at destroy)
+    bool connected = false;
+    size_t bytes = 0, off_part = 0, off_u = 0, off_u4 = 0, off_du = 0;
+    unsigned long long epoch_base = 0;                  // barriers completed so far (identical on every rank)
+    unsigned long long n_solves = 0;
+    DevBuf<unsigned char> needmask;
+    int* d_abort = nullptr;
+    int grid_override = 0;                              // test hook (SB_PCG_GRID): smaller grids so that two solves share one GPU
+};
+void dist_destroy(sb_context* ctx)
+{
+    Dist* D = ctx->dist;
+    if (!D) return;
+    for (int q = 0; q < D->world; q++)
+        if (q != D->rank && D->opened[q] && D->base[q]) cudaIpcCloseMemHandle(D->base[q]);
+    if (D->base[D->rank]) cudaFree(D->base[D->rank]);
+    if (D->d_abort) cudaFree(D->d_abort);
+    D->needmask.release();
+    delete D;
+    ctx->dist = nullptr;
+}
+
+// Row partition of the virtual grid on the host (the device computes the same bounds: row_lower_bound / ROW_COST below) and
+// the halo masks that follow from it; shared by sb_dist_plan (CPU tests) and nothing else on the product path.
+static int host_row_lower_bound(const unsigned long long* rows, int nbr, unsigned long long t)
+{
+    int lo = 0, hi = nbr;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (rows[mid] + 4ull * (unsigned long long)mid < t) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
 static Pcg* get(sb_context* ctx)
 {
     if (!ctx->pcg) {
@@ -203,30 +270,30 @@ __device__ __forceinline__ void block_sum2(double& a, double& b, double* s)
     }
     a = ta; b = tb;   // valid in thread 0
 }
-// every CTA sums the same gridDim.x partials of two arrays in the same order -> identical values everywhere
-__device__ __forceinline__ void all_partials2(const double* partA, const double* partB, double* s, double* bc, double& outA, double& outB)
+// every CTA sums the same n (= virtual grid size) partials of two arrays in the same order -> identical values everywhere
+__device__ __forceinline__ void all_partials2(const double* partA, const double* partB, int n, double* s, double* bc, double& outA, double& outB)
 {
     double a = 0.0, b = 0.0;
-    for (int i = threadIdx.x; i < gridDim.x; i += PCG_THREADS) { a += __ldcg(partA + i); b += __ldcg(partB + i); }
+    for (int i = threadIdx.x; i < n; i += PCG_THREADS) { a += __ldcg(partA + i); b += __ldcg(partB + i); }
     block_sum2(a, b, s);
     if (threadIdx.x == 0) { bc[0] = a; bc[1] = b; }
     __syncthreads();
     outA = bc[0]; outB = bc[1];
 }
-// every CTA sums the same gridDim.x partials in the same order -> identical value everywhere
-__device__ __forceinline__ double all_partials(const double* part, double* s, double* bc)
+// every CTA sums the same n partials in the same order -> identical value everywhere
+__device__ __forceinline__ double all_partials(const double* part, int n, double* s, double* bc)
 {
     double v = 0.0;
-    for (int i = threadIdx.x; i < gridDim.x; i += PCG_THREADS) v += __ldcg(part + i);
+    for (int i = threadIdx.x; i < n; i += PCG_THREADS) v += __ldcg(part + i);
     const double t = block_sum(v, s);
     if (threadIdx.x == 0) *bc = t;
     __syncthreads();
     return *bc;
 }
-__device__ __forceinline__ double all_partials_max(const double* part, double* s, double* bc)
+__device__ __forceinline__ double all_partials_max(const double* part, int n, double* s, double* bc)
 {
     double v = 0.0;
-    for (int i = threadIdx.x; i < gridDim.x; i += PCG_THREADS) v = fmax(v, __ldcg(part + i));
+    for (int i = threadIdx.x; i < n; i += PCG_THREADS) v = fmax(v, __ldcg(part + i));
     const double t = block_max(v, s);
     if (threadIdx.x == 0) *bc = t;
     __syncthreads();
@@ -243,7 +310,7 @@ __device__ __forceinline__ void apply_dinv(const float* d, double r0, double r1,
 // Row partition: a CTA's iteration costs about one unit per block (product) plus ROW_COST units per block row (vector
 // phase, row bookkeeping), so the rows are cut into slices of equal  blocks + ROW_COST * rows.  (Cutting by blocks alone gives
 // the slices of sparse rows -- hex-centre nodes: 9 blocks per row instead of 27 -- twice the rows and twice the vector phase.)
-constexpr unsigned long long ROW_COST = 4;
+constexpr unsigned long long ROW_COST = 4;   // (host_row_lower_bound above restates it)
 // first row r in [0, nbr] with rows[r] + ROW_COST * r >= t
 __device__ __forceinline__ int row_lower_bound(const unsigned long long* __restrict__ rows, int nbr, unsigned long long t)
 {
@@ -281,6 +348,37 @@ __device__ __forceinline__ unsigned long long global_ns()
     return t;
 }
 
+// ---- barrier over the CTAs of ALL ranks of a distributed solve ----
+// Everything this CTA stored into peer memory (u halo rows, partial sums, du) is ordered before its arrival by the CTA barrier
+// and the system-scope fence; the arrival is one release-reduction on every rank's counter (W NVLink stores, not waited for),
+// the wait an acquire spin on the OWN counter.  The counters are monotonic over the life of the context (a rank that is one
+// solve ahead may already be arriving at the next solve's first barrier).  A wait longer than the time-out, or an abort seen
+// on this GPU, ends the solve (done = 4) instead of hanging the device.
+__device__ __forceinline__ bool dist_barrier(const DistArgs& D, unsigned long long& epoch, int* s_abort)
+{
+    __syncthreads();
+    epoch++;
+    if (threadIdx.x == 0 && !*s_abort) {
+        __threadfence_system();
+        for (int q = 0; q < D.world; q++)
+            asm volatile("red.release.sys.global.add.u64 [%0], %1;" :: "l"(D.bar[q]), "l"(1ull) : "memory");
+        const unsigned long long target = (D.epoch_base + epoch) * (unsigned long long)(D.world * (int)gridDim.x);
+        unsigned long long v, t0 = 0;
+        unsigned spins = 0;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(D.bar[D.rank]) : "memory");
+            if (v >= target) break;
+            if ((++spins & 1023u) == 0u) {
+                const unsigned long long now = global_ns();
+                if (!t0) t0 = now;
+                if (now - t0 > D.timeout_ns || *(volatile int*)D.abort_flag) { *(volatile int*)D.abort_flag = 1; *s_abort = 1; break; }
+            }
+        }
+    }
+    __syncthreads();
+    return *s_abort != 0;
+}
+
 // The dynamic shared memory of the solver.  A CTA whose slices all fit (the normal case) runs the FAST instance of the solve
 // body, in which every slice pointer is derived from this symbol, so that the compiler emits shared-memory loads / stores
 // (LDS / STS); pointers that may be either shared or global are generic and every access pays the generic-address path of
@@ -299,6 +397,7 @@ struct PcgPlan {
     unsigned off_tile[2];                  // tile buffers (MODE 2)
     unsigned long long* tbar;              // their mbarriers
     unsigned long long t_start, t_loaded;
+    int* s_abort;
 };
 
 // MODE 1: every slice (row pointers, vectors, matrix, window) in shared memory.  MODE 2 (the matrix slice does not fit: 66 k-node
@@ -309,16 +408,30 @@ struct PcgPlan {
 // 5.0 us resident, 11.4 us MODE 2, 19.8 us MODE 3 -- one 30 KB bulk copy in flight per SM does not cover the copy latency;
 // it needs a deeper ring of smaller tiles before it can replace MODE 2.  MODE 0: anything may live in global memory (generic
 // pointers; million-tet slices, tiny budgets).
-template<int MODE>
+template<int MODE, bool DIST>
 __device__ __forceinline__ void pcg_body(const PcgArgs& A, const PcgPlan& P)
 {
     const int G = gridDim.x;
+    const int VG = DIST ? A.d.world * (int)gridDim.x : (int)gridDim.x;               // virtual grid: the CTAs of all ranks
+    const int vb = DIST ? A.d.rank * (int)gridDim.x + (int)blockIdx.x : (int)blockIdx.x;   // this CTA in it
     const int nbr = A.nbr;
     const int tid = threadIdx.x;
     unsigned epoch = 0;
-    double* part0 = A.part;
-    double* part1 = A.part + PCG_MAX_BLOCKS;
-    double* part2 = A.part + 2 * PCG_MAX_BLOCKS;
+    unsigned long long depoch = 0;
+    double* part0 = DIST ? A.d.part[A.d.rank] : A.part;
+    double* part1 = part0 + PCG_MAX_BLOCKS;
+    double* part2 = part0 + 2 * PCG_MAX_BLOCKS;
+    // this CTA's partial sum k: into the own array, or into the arrays of all ranks
+    auto put_part = [&](int k, double v) {
+        if (DIST) { for (int q = 0; q < A.d.world; q++) __stcg(A.d.part[q] + k * PCG_MAX_BLOCKS + vb, v); }
+        else __stcg(part0 + k * PCG_MAX_BLOCKS + vb, v);
+    };
+    // barrier over the virtual grid; true = the distributed solve was aborted
+    auto gbar = [&]() -> bool {
+        if (DIST) return dist_barrier(A.d, depoch, P.s_abort);
+        grid_barrier(A.barrier, epoch);
+        return false;
+    };
     double* s = P.s;
     double* bc2 = P.bc2;
     double& bc = bc2[0];
@@ -342,7 +455,7 @@ __device__ __forceinline__ void pcg_body(const PcgArgs& A, const PcgPlan& P)
     auto COL = [&](int j) -> int { return (MODE >= 2) ? __ldg(cols + j) : cols[j]; };
     auto VAL = [&](const float* q) -> float { return (MODE >= 2) ? __ldg(q) : *q; };
     double* uwin = (MODE != 0) ? reinterpret_cast<double*>(pcg_smem + P.off_win) : P.uwin;
-    (void)G; (void)nbr; (void)bc;
+    (void)G; (void)nbr; (void)bc; (void)VG; (void)depoch;
     auto is_swept = [&](int lr) {   // long AND listed (every listed row gets its own block reduction)
         if (rp[lr + 1] - rp[lr] <= LONG_ROW) return false;
         for (int k = 0; k < n_long; k++) if (s_long[k] == lr) return true;
@@ -351,6 +464,21 @@ __device__ __forceinline__ void pcg_body(const PcgArgs& A, const PcgPlan& P)
     double* ug = A.u + 3 * (size_t)r0;                           // own slice of the global u
     auto store_u4 = [&](int br, double z0, double z1, double z2) {   // padded copy for the far gathers
         asm volatile("st.global.cg.v4.f64 [%0], {%1, %2, %3, %4};" :: "l"(A.u4 + 4 * (size_t)br), "d"(z0), "d"(z1), "d"(z2), "d"(0.0) : "memory");
+    };
+    // publish u of own row lr: own copies (compact + padded) and, in a distributed solve, the copies of the ranks that read it
+    auto publish_u = [&](int lr, double z0, double z1, double z2) {
+        __stcg(ug + 3 * lr, z0); __stcg(ug + 3 * lr + 1, z1); __stcg(ug + 3 * lr + 2, z2);
+        store_u4(r0 + lr, z0, z1, z2);
+        if (DIST) {
+            unsigned m = A.d.needmask[r0 + lr];
+            while (m) {
+                const int q = __ffs(m) - 1;
+                m &= m - 1;
+                double* pu = A.d.u[q] + 3 * (size_t)(r0 + lr);
+                __stcg(pu, z0); __stcg(pu + 1, z1); __stcg(pu + 2, z2);
+                asm volatile("st.global.cg.v4.f64 [%0], {%1, %2, %3, %4};" :: "l"(A.d.u4[q] + 4 * (size_t)(r0 + lr)), "d"(z0), "d"(z1), "d"(z2), "d"(0.0) : "memory");
+            }
+        }
     };
     const double* uo_win = own_in_win ? uwin + 3 * (size_t)(r0 - w0) : nullptr;
     auto uo = [&](int i) -> double { return own_in_win ? uo_win[i] : __ldcg(ug + i); };   // own slice of u as this CTA reads it
@@ -602,17 +730,16 @@ __device__ __forceinline__ void pcg_body(const PcgArgs& A, const PcgPlan& P)
             apply_dinv(mi, g0, g1, g2, z0, z1, z2);
             for (int c = 0; c < 3; c++) { xg[3 * lr + c] = 0.0; ps[3 * lr + c] = 0.0; ss[3 * lr + c] = 0.0; }
             rs[3 * lr] = g0; rs[3 * lr + 1] = g1; rs[3 * lr + 2] = g2;
-            __stcg(ug + 3 * lr, z0); __stcg(ug + 3 * lr + 1, z1); __stcg(ug + 3 * lr + 2, z2);
-            store_u4(r0 + lr, z0, z1, z2);
+            publish_u(lr, z0, z1, z2);
             bb += g0 * g0 + g1 * g1 + g2 * g2;
             ru += g0 * z0 + g1 * z1 + g2 * z2;
         }
         block_sum2(bb, ru, s);
-        if (tid == 0) { __stcg(part0 + blockIdx.x, bb); __stcg(part1 + blockIdx.x, ru); }
+        if (tid == 0) { put_part(0, bb); put_part(1, ru); }
     }
-    grid_barrier(A.barrier, epoch);
+    const bool aborted0 = gbar();
     double bb, gamma;
-    all_partials2(part0, part1, s, bc2, bb, gamma);
+    all_partials2(part0, part1, VG, s, bc2, bb, gamma);
 
     int it = 0, done = 0, found_indef = 0;
     double error = 1.0;               // x0 = 0 -> r = b
@@ -620,6 +747,7 @@ __device__ __forceinline__ void pcg_body(const PcgArgs& A, const PcgPlan& P)
     if (bb < A.abs_tol * A.abs_tol) { done = 1; error = 0.0; }   // zero right-hand side
     else if (1.0 < A.abs_tol) done = 1;
     else if (A.max_iter <= 0) done = 3;
+    if (aborted0) done = 4;
 
     const unsigned long long t_loop = global_ns();
     long long c_spmv = 0, c_bar = 0, c_red = 0, c_vec = 0, c_win = 0, c_t = A.instrument ? clock64() : 0;
@@ -630,13 +758,14 @@ __device__ __forceinline__ void pcg_body(const PcgArgs& A, const PcgPlan& P)
         load_window();
         const double wu = product();
         const double t = block_sum(wu, s);
-        if (tid == 0) __stcg(part2 + blockIdx.x, t);
+        if (tid == 0) put_part(2, t);
         PCG_TICK(c_spmv);
-        grid_barrier(A.barrier, epoch);
+        const bool ab = gbar();
         PCG_TICK(c_bar);
-        const double delta = all_partials(part2, s, &bc);
+        const double delta = all_partials(part2, VG, s, &bc);
         PCG_TICK(c_red);
-        if (delta <= 0.0) {
+        if (ab) done = 4;
+        else if (delta <= 0.0) {
             found_indef = 1;
             if (A.stop_on_indef) { it = 1; done = 2; }   // x is returned as is (solve_pcg.h:183-192)
         }
@@ -658,20 +787,19 @@ __device__ __forceinline__ void pcg_body(const PcgArgs& A, const PcgPlan& P)
                     rs[3 * lr + c] = q[c];
                 }
                 apply_dinv(dinv + 9 * lr, q[0], q[1], q[2], z0, z1, z2);
-                __stcg(ug + 3 * lr, z0); __stcg(ug + 3 * lr + 1, z1); __stcg(ug + 3 * lr + 2, z2);
-                store_u4(r0 + lr, z0, z1, z2);
+                publish_u(lr, z0, z1, z2);
                 rr += q[0] * q[0] + q[1] * q[1] + q[2] * q[2];
                 ru += q[0] * z0 + q[1] * z1 + q[2] * z2;
             }
             block_sum2(rr, ru, s);
-            if (tid == 0) { __stcg(part0 + blockIdx.x, rr); __stcg(part1 + blockIdx.x, ru); }
+            if (tid == 0) { put_part(0, rr); put_part(1, ru); }
         }
         PCG_TICK(c_vec);
-        grid_barrier(A.barrier, epoch);
+        if (gbar()) { done = 4; break; }
         PCG_TICK(c_bar);
         issue_window();     // every slice of u is published: the window copy runs under the reduction below
         double rr, gamma_new;
-        all_partials2(part0, part1, s, bc2, rr, gamma_new);
+        all_partials2(part0, part1, VG, s, bc2, rr, gamma_new);
         error = sqrt(rr / bb);
         PCG_TICK(c_red);
         wait_window();      // (also on the way out: no copy may be in flight when the CTA leaves)
@@ -682,12 +810,12 @@ __device__ __forceinline__ void pcg_body(const PcgArgs& A, const PcgPlan& P)
         {
             const double wu = product();
             const double t = block_sum(wu, s);
-            if (tid == 0) __stcg(part2 + blockIdx.x, t);
+            if (tid == 0) put_part(2, t);
         }
         PCG_TICK(c_spmv);
-        grid_barrier(A.barrier, epoch);
+        if (gbar()) { done = 4; break; }
         PCG_TICK(c_bar);
-        const double delta = all_partials(part2, s, &bc);
+        const double delta = all_partials(part2, VG, s, &bc);
         PCG_TICK(c_red);
         beta = gamma_new / gamma;
         const double pAp = delta - beta * gamma_new / alpha;     // p^T A p of the coming iteration
@@ -706,36 +834,39 @@ __device__ __forceinline__ void pcg_body(const PcgArgs& A, const PcgPlan& P)
         for (int lr = tid; lr < nr; lr += PCG_THREADS) {
             for (int c = 0; c < 3; c++) {
                 const double v = xg[3 * lr + c];
-                A.du[3 * (size_t)(r0 + lr) + c] = v;
+                if (DIST) { for (int q = 0; q < A.d.world; q++) __stcg(A.d.du[q] + 3 * (size_t)(r0 + lr) + c, v); }
+                else A.du[3 * (size_t)(r0 + lr) + c] = v;
                 dg += v * A.grad[3 * (size_t)(r0 + lr) + c];
                 mx = fmax(mx, fabs(v));
             }
         }
         const double t0 = block_sum(dg, s);
         const double t1 = block_max(mx, s);
-        grid_barrier(A.barrier, epoch);   // CTAs that left the loop one reduction behind may still be reading the partial arrays
-        if (tid == 0) { __stcg(part0 + blockIdx.x, t0); __stcg(part1 + blockIdx.x, t1); }
+        if (gbar()) done = 4;   // CTAs that left the loop one reduction behind may still be reading the partial arrays
+        if (tid == 0) { put_part(0, t0); put_part(1, t1); }
     }
-    grid_barrier(A.barrier, epoch);
+    if (gbar()) done = 4;
     if (A.dbg && tid == 0) {
         const int G = gridDim.x;
         A.dbg[blockIdx.x] = c_spmv; A.dbg[G + blockIdx.x] = c_bar + c_red; A.dbg[2 * G + blockIdx.x] = c_vec; A.dbg[3 * G + blockIdx.x] = c_win;
         A.dbg[4 * G + blockIdx.x] = ((long long)nr << 32) | (unsigned)(rp[nr] - rp[0]);
     }
     if (blockIdx.x == 0) {
-        const double dg = all_partials(part0, s, &bc);
-        const double mx = all_partials_max(part1, s, &bc);
+        const double dg = all_partials(part0, VG, s, &bc);
+        const double mx = all_partials_max(part1, VG, s, &bc);
         if (tid == 0) {
             PcgResult R;
             R.du_dot_grad = dg; R.du_inf = mx; R.error = error; R.bb = bb;
             R.it = it; R.done = done; R.found_indef = found_indef; R.pad = 0;
             R.c_spmv = c_spmv; R.c_bar = c_bar; R.c_red = c_red; R.c_vec = c_vec; R.c_win = c_win;
             R.t_start = t_start; R.t_loaded = t_loaded; R.t_loop = t_loop; R.t_end = global_ns();
+            R.barriers = DIST ? depoch : (unsigned long long)epoch;
             *A.result = R;
         }
     }
 }
 
+template<bool DIST>
 __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_solve(const PcgArgs A)
 {
     unsigned char* const smem = pcg_smem;
@@ -749,8 +880,10 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_solve(const PcgArgs A)
     __shared__ int s_n_long;
     __shared__ __align__(8) unsigned long long s_mbar;
     __shared__ __align__(8) unsigned long long s_tbar[2];
+    __shared__ int s_abort;
     const unsigned long long t_start = global_ns();
-    const int G = gridDim.x;
+    const int G = DIST ? A.d.world * (int)gridDim.x : (int)gridDim.x;                      // virtual grid (all ranks)
+    const int vb = DIST ? A.d.rank * (int)gridDim.x + (int)blockIdx.x : (int)blockIdx.x;   // this CTA in it
     const int nbr = A.nbr;
     const int tid = threadIdx.x;
 
@@ -758,11 +891,12 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_solve(const PcgArgs A)
     if (tid < 64) {   // (warps 0 and 1: one boundary each)
         const unsigned long long cost = A.nnzb + ROW_COST * (unsigned long long)nbr;
         const int which = tid >> 5;
-        int r = row_lower_bound_warp(A.rows, nbr, (cost * (blockIdx.x + which)) / G);
-        if (which == 1 && blockIdx.x == G - 1) r = nbr;
+        int r = row_lower_bound_warp(A.rows, nbr, (cost * (unsigned long long)(vb + which)) / (unsigned long long)G);
+        if (which == 1 && vb == G - 1) r = nbr;
         if ((tid & 31) == 0) s_range[which] = r;
     }
     if (tid == 0) {
+        s_abort = 0;
         mbar_init(&s_mbar, 1);
         mbar_init(&s_tbar[0], 1);
         mbar_init(&s_tbar[1], 1);
@@ -882,11 +1016,36 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_solve(const PcgArgs A)
     P.rp = rp; P.rs = rs; P.ps = ps; P.ss = ss; P.ws = ws; P.dinv = dinv; P.cols = cols; P.vals = vals; P.uwin = uwin;
     P.s = s; P.bc2 = bc2; P.s_long = s_long; P.mbar = &s_mbar;
     P.t_start = t_start; P.t_loaded = global_ns();
-    P.b0 = b0; P.tbar = s_tbar;
-    if (rp_fit && vec_fit && mat_fit && own_in_win) pcg_body<1>(A, P);
-    else if (rp_fit && vec_fit && tile_fit && own_in_win) pcg_body<3>(A, P);
-    else if (rp_fit && vec_fit && own_in_win) pcg_body<2>(A, P);
-    else pcg_body<0>(A, P);
+    P.b0 = b0; P.tbar = s_tbar; P.s_abort = &s_abort;
+    if (rp_fit && vec_fit && mat_fit && own_in_win) pcg_body<1, DIST>(A, P);
+    else if (rp_fit && vec_fit && tile_fit && own_in_win) pcg_body<3, DIST>(A, P);
+    else if (rp_fit && vec_fit && own_in_win) pcg_body<2, DIST>(A, P);
+    else pcg_body<0, DIST>(A, P);
+}
+
+// needmask[c] |= 1 << q for every rank q != rank whose rows reference block column c, for the columns THIS rank owns (the
+// pattern is replicated, so every rank derives its send lists locally).  One warp per block row.
+__global__ void k_dist_needmask(const unsigned long long* __restrict__ rows, const int32_t* __restrict__ cols, int nbr, unsigned long long nnzb,
+                                int world, int rank, int grid, unsigned char* __restrict__ needmask)
+{
+    __shared__ int bound[DIST_MAX_WORLD + 1];
+    if (threadIdx.x <= world) {
+        const unsigned long long cost = nnzb + ROW_COST * (unsigned long long)nbr;
+        const int VG = world * grid;
+        bound[threadIdx.x] = (threadIdx.x == world) ? nbr : row_lower_bound(rows, nbr, (cost * (unsigned long long)(threadIdx.x * grid)) / (unsigned long long)VG);
+    }
+    __syncthreads();
+    const int lo = bound[rank], hi = bound[rank + 1];
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nbr; i += warps) {
+        if (i >= lo && i < hi) continue;   // own rows read own columns locally
+        int q = 0;
+        while (q + 1 < world && i >= bound[q + 1]) q++;
+        for (unsigned long long j = rows[i] + (threadIdx.x & 31); j < rows[i + 1]; j += 32) {
+            const int c = cols[j] / 3;
+            if (c >= lo && c < hi) atomicOr(reinterpret_cast<unsigned*>(needmask + (c & ~3)), (1u << q) << (8 * (c & 3)));
+        }
+    }
 }
 
 int solve_pcg_internal(sb_context* ctx, double abs_tol, double rel_tol, int max_iter, int stop_on_indef,
@@ -912,7 +1071,7 @@ int solve_pcg_internal(sb_context* ctx, double abs_tol, double rel_tol, int max_
         SB_CUDA(ctx, cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
         if (!coop) return fail(ctx, SB_ERR_CUDA, "sb_solve_pcg: the device does not support cooperative launches");
         cudaFuncAttributes fa;
-        SB_CUDA(ctx, cudaFuncGetAttributes(&fa, k_pcg_solve));
+        SB_CUDA(ctx, cudaFuncGetAttributes(&fa, k_pcg_solve<false>));
         P->smem_bytes = (unsigned)(smem_max - (int)fa.sharedSizeBytes - 1024);
         // test hook: SB_PCG_SMEM_LIMIT=<bytes> shrinks the budget so that small fixtures exercise the streaming (slices in global
         // memory) and partial-window paths that million-tet scenes take
@@ -920,10 +1079,16 @@ int solve_pcg_internal(sb_context* ctx, double abs_tol, double rel_tol, int max_
             const long v = std::atol(lim);
             if (v >= 1024 && (unsigned)v < P->smem_bytes) P->smem_bytes = (unsigned)v;
         }
-        SB_CUDA(ctx, cudaFuncSetAttribute(k_pcg_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem_bytes));
-        SB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pcg_solve, PCG_THREADS, P->smem_bytes));
+        SB_CUDA(ctx, cudaFuncSetAttribute(k_pcg_solve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem_bytes));
+        SB_CUDA(ctx, cudaFuncSetAttribute(k_pcg_solve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem_bytes));
+        SB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pcg_solve<false>, PCG_THREADS, P->smem_bytes));
         if (occ < 1) return fail(ctx, SB_ERR_CUDA, "sb_solve_pcg: the persistent kernel does not fit on an SM");
-        P->grid = std::min(sms, PCG_MAX_BLOCKS);
+        P->grid = std::min(sms, PCG_MAX_BLOCKS / DIST_MAX_WORLD);
+        // test hook: SB_PCG_GRID=<ctas> shrinks the grid (two distributed solves then fit on ONE GPU side by side)
+        if (const char* g = std::getenv("SB_PCG_GRID")) {
+            const int v = std::atoi(g);
+            if (v >= 1 && v < P->grid) P->grid = v;
+        }
     }
     PcgArgs A;
     A.rows = rows; A.cols = cols; A.vals = vals; A.grad = ctx->grad.p; A.dinv = P->dinv.p;
@@ -934,17 +1099,21 @@ int solve_pcg_internal(sb_context* ctx, double abs_tol, double rel_tol, int max_
     // full carve-out would leave no L1: every 4-byte load of a block would be its own L2 request (the SM's miss path takes ~2
     // cycles per request).  Such solves run with a smaller carve-out, so that the nine loads of a 36-byte block share one or two
     // L1 line fills.  (The experimental tiled mode needs no L1 and takes everything again.)
+    Dist* DS = (ctx->dist && ctx->dist->connected && ctx->dist->world > 1) ? ctx->dist : nullptr;
+    if (DS && (size_t)n > DS->max_dofs) return fail(ctx, SB_ERR_STATE, "sb_solve_pcg: the system has more DoFs than sb_dist_init reserved peer memory for");
+    const int vgrid = P->grid * (DS ? DS->world : 1);   // CTAs of all ranks
     unsigned smem_launch = P->smem_bytes;
     {
-        const double resident = 1.08 * (40.0 * (double)nnzb + 160.0 * (double)nbr) / P->grid;
-        const double rows_max = 1.6 * (double)nbr / P->grid;                               // (sparse-row slices hold more rows)
+        const double resident = 1.08 * (40.0 * (double)nnzb + 160.0 * (double)nbr) / vgrid;
+        const double rows_max = 1.6 * (double)nbr / vgrid;                                 // (sparse-row slices hold more rows)
         const double tiled = 140.0 * rows_max + 2.0 * PCG_TILE_BYTES + 24.0 * (rows_max + 2.0) + 64.0;
         static const bool tiled_on = std::getenv("SB_PCG_TILED") != nullptr;
         if (resident > (double)P->smem_bytes && (!tiled_on || tiled > (double)P->smem_bytes)) smem_launch = std::min(P->smem_bytes, PCG_STREAM_SMEM);
     }
     if (smem_launch != P->smem_launch_last) {
         const int pct = (int)std::min<long>(100, (100L * (smem_launch + 16 * 1024)) / (228 * 1024) + 1);
-        SB_CUDA(ctx, cudaFuncSetAttribute(k_pcg_solve, cudaFuncAttributePreferredSharedMemoryCarveout, smem_launch == P->smem_bytes ? (int)cudaSharedmemCarveoutMaxShared : pct));
+        SB_CUDA(ctx, cudaFuncSetAttribute(k_pcg_solve<false>, cudaFuncAttributePreferredSharedMemoryCarveout, smem_launch == P->smem_bytes ? (int)cudaSharedmemCarveoutMaxShared : pct));
+        SB_CUDA(ctx, cudaFuncSetAttribute(k_pcg_solve<true>, cudaFuncAttributePreferredSharedMemoryCarveout, smem_launch == P->smem_bytes ? (int)cudaSharedmemCarveoutMaxShared : pct));
         P->smem_launch_last = smem_launch;
     }
     A.nnzb = nnzb; A.smem_bytes = smem_launch; A.instrument = ctx->profile ? 1 : 0;
@@ -954,7 +1123,7 @@ int solve_pcg_internal(sb_context* ctx, double abs_tol, double rel_tol, int max_
     static const bool tiled_env = std::getenv("SB_PCG_TILED") != nullptr;
     A.tiled = tiled_env ? 1 : 0;
     A.nbr = nbr; A.abs_tol = abs_tol; A.rel_tol = rel_tol; A.max_iter = max_iter; A.stop_on_indef = stop_on_indef;
-    SB_CUDA(ctx, cudaMemsetAsync(P->d_barrier, 0, sizeof(unsigned), st));
+    SB_CUDA(ctx, cudaMemsetAsync(P->d_barrier, 0, sizeof(unsigned), st));   // (single-GPU barrier; the distributed counters are never reset)
     // SB_PCG_DUMP=1: per-CTA cycle counters of every solve on stderr (load-balance diagnostics)
     static const bool dump = std::getenv("SB_PCG_DUMP") != nullptr;
     static long long* d_dbg = nullptr;
@@ -962,12 +1131,41 @@ int solve_pcg_internal(sb_context* ctx, double abs_tol, double rel_tol, int max_
     if (dump) cudaMemsetAsync(d_dbg, 0, (5 * PCG_MAX_BLOCKS + 8) * sizeof(long long), st);
     A.dbg = dump ? d_dbg : nullptr;
     if (dump) A.instrument = 1;
+    A.d.world = 1; A.d.rank = 0;
+    if (DS) {
+        // distributed solve: every rank runs this same code on the same (replicated) matrix and right-hand side
+        DistArgs& d = A.d;
+        d.world = DS->world; d.rank = DS->rank; d.epoch_base = DS->epoch_base;
+        static const double timeout_s = std::getenv("SB_DIST_TIMEOUT_S") ? std::atof(std::getenv("SB_DIST_TIMEOUT_S")) : 30.0;
+        d.timeout_ns = (unsigned long long)(timeout_s * 1e9);
+        const size_t set = (size_t)(DS->n_solves & 1ull) * 3 * PCG_MAX_BLOCKS * sizeof(double);
+        for (int q = 0; q < DS->world; q++) {
+            d.bar[q] = reinterpret_cast<unsigned long long*>(DS->base[q]);
+            d.part[q] = reinterpret_cast<double*>(DS->base[q] + DS->off_part + set);
+            d.u[q] = reinterpret_cast<double*>(DS->base[q] + DS->off_u);
+            d.u4[q] = reinterpret_cast<double*>(DS->base[q] + DS->off_u4);
+            d.du[q] = reinterpret_cast<double*>(DS->base[q] + DS->off_du);
+        }
+        A.u = d.u[d.rank]; A.u4 = d.u4[d.rank]; A.du = nullptr;
+        DS->needmask.ensure((size_t)nbr + 8);
+        SB_CUDA(ctx, cudaMemsetAsync(DS->needmask.p, 0, (size_t)nbr + 8, st));
+        k_dist_needmask<<<296, 256, 0, st>>>(rows, cols, nbr, (unsigned long long)nnzb, DS->world, DS->rank, P->grid, DS->needmask.p);
+        d.needmask = DS->needmask.p; d.abort_flag = DS->d_abort;
+        ctx->launches += 1;
+    }
     void* args[] = {(void*)&A};
-    SB_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_pcg_solve, dim3(P->grid), dim3(PCG_THREADS), args, smem_launch, st));
+    SB_CUDA(ctx, cudaLaunchCooperativeKernel(DS ? (const void*)k_pcg_solve<true> : (const void*)k_pcg_solve<false>, dim3(P->grid), dim3(PCG_THREADS), args, smem_launch, st));
     ctx->launches += 1;
     SB_CUDA(ctx, cudaMemcpyAsync(P->h_result, P->d_result, sizeof(PcgResult), cudaMemcpyDeviceToHost, st));
+    if (DS) SB_CUDA(ctx, cudaMemcpyAsync(ctx->du.p, DS->base[DS->rank] + DS->off_du, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
     SB_CUDA(ctx, hot_sync(ctx));
     SB_CUDA(ctx, cudaGetLastError());
+    if (DS) {
+        DS->epoch_base += P->h_result->barriers;
+        DS->n_solves++;
+        if (P->h_result->done == 4)
+            return fail(ctx, SB_ERR_CUDA, "sb_solve_pcg: distributed solve aborted: a peer rank did not arrive at a barrier within SB_DIST_TIMEOUT_S (ranks out of step, or a peer failed)");
+    }
     if (dump) {
         const int G = P->grid;
         std::vector<long long> h(5 * (size_t)G + 8);
@@ -1005,4 +1203,113 @@ extern "C" int sb_solve_pcg(sb_context* ctx, double abs_tol, double rel_tol, int
     if (!ctx) return SB_ERR_ARG;
     if (!ctx->have_pgh) return fail(ctx, SB_ERR_STATE, "sb_solve_pcg: no gradient: call sb_eval(SB_EVAL_PGH) first");
     return solve_pcg_internal(ctx, abs_tol, rel_tol, max_iterations, stop_on_indefiniteness, out_iterations, out_ok, out_du_dot_grad, out_du_inf);
+}
+
+// ---- distributed solve: set-up over peer memory (include/stark_b200.h "multi-GPU") ----
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+extern "C" int sb_dist_init(sb_context* ctx, int rank, int world, long long max_dofs, unsigned char* out_handle64)
+{
+    if (!ctx || world < 1 || world > DIST_MAX_WORLD || rank < 0 || rank >= world || max_dofs < 3) return SB_ERR_ARG;
+    if (ctx->dist) return fail(ctx, SB_ERR_STATE, "sb_dist_init: already initialised");
+    Dist* D = new Dist();
+    D->world = world; D->rank = rank; D->max_dofs = (size_t)max_dofs;
+    const size_t nbr = ((size_t)max_dofs + 2) / 3;
+    D->off_part = 256;
+    D->off_u = align256(D->off_part + 2 * 3 * (size_t)PCG_MAX_BLOCKS * sizeof(double));
+    D->off_u4 = align256(D->off_u + sizeof(double) * ((size_t)max_dofs + 4));
+    D->off_du = align256(D->off_u4 + sizeof(double) * 4 * (nbr + 1));
+    D->bytes = align256(D->off_du + sizeof(double) * ((size_t)max_dofs + 4));
+    unsigned char* p = nullptr;
+    if (cudaMalloc(&p, D->bytes) != cudaSuccess || cudaMemset(p, 0, D->bytes) != cudaSuccess || cudaMalloc(&D->d_abort, sizeof(int)) != cudaSuccess ||
+        cudaMemset(D->d_abort, 0, sizeof(int)) != cudaSuccess) {
+        delete D;
+        return fail(ctx, SB_ERR_CUDA, "sb_dist_init: allocation of the peer buffer failed");
+    }
+    D->base[rank] = p;
+    if (out_handle64) {
+        cudaIpcMemHandle_t h;
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        if (cudaIpcGetMemHandle(&h, p) != cudaSuccess) { cudaGetLastError(); memset(out_handle64, 0, 64); }   // (single-process use connects by pointer)
+        else memcpy(out_handle64, &h, 64);
+    }
+    cudaDeviceSynchronize();
+    ctx->dist = D;
+    return 0;
+}
+
+// handles: world x 64 bytes (cudaIpcMemHandle_t of every rank, own entry ignored), gathered by the caller's process group
+extern "C" int sb_dist_connect(sb_context* ctx, const unsigned char* handles)
+{
+    if (!ctx || !handles) return SB_ERR_ARG;
+    Dist* D = ctx->dist;
+    if (!D) return fail(ctx, SB_ERR_STATE, "sb_dist_connect: call sb_dist_init first");
+    for (int q = 0; q < D->world; q++) {
+        if (q == D->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + 64 * (size_t)q, 64);
+        void* p = nullptr;
+        const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return fail(ctx, SB_ERR_CUDA, std::string("sb_dist_connect: cudaIpcOpenMemHandle failed for rank ") + std::to_string(q) + ": " + cudaGetErrorString(e));
+        D->base[q] = static_cast<unsigned char*>(p);
+        D->opened[q] = true;
+    }
+    D->connected = true;
+    return 0;
+}
+
+// the same with plain device pointers (ranks living in ONE process: tests on a single GPU, or threads driving several GPUs
+// with peer access enabled by the caller)
+extern "C" int sb_dist_connect_ptrs(sb_context* ctx, void* const* bases)
+{
+    if (!ctx || !bases) return SB_ERR_ARG;
+    Dist* D = ctx->dist;
+    if (!D) return fail(ctx, SB_ERR_STATE, "sb_dist_connect_ptrs: call sb_dist_init first");
+    for (int q = 0; q < D->world; q++)
+        if (q != D->rank) { if (!bases[q]) return SB_ERR_ARG; D->base[q] = static_cast<unsigned char*>(bases[q]); }
+    D->connected = true;
+    return 0;
+}
+
+extern "C" void* sb_dist_local_base(sb_context* ctx)
+{
+    return (ctx && ctx->dist) ? ctx->dist->base[ctx->dist->rank] : nullptr;
+}
+
+// out3 = { barriers completed, distributed solves, bytes of the peer buffer }
+extern "C" int sb_dist_stats(sb_context* ctx, int* out_rank, int* out_world, double* out3)
+{
+    if (!ctx) return SB_ERR_ARG;
+    const Dist* D = ctx->dist;
+    if (out_rank) *out_rank = D ? D->rank : 0;
+    if (out_world) *out_world = (D && D->connected) ? D->world : 1;
+    if (out3) { out3[0] = D ? (double)D->epoch_base : 0.0; out3[1] = D ? (double)D->n_solves : 0.0; out3[2] = D ? (double)D->bytes : 0.0; }
+    return 0;
+}
+
+// The partition and halo lists of a distributed solve on HOST arrays (no GPU): out_bounds[world + 1] = first block row of every
+// rank, out_needmask[nbr] = for the rows of `rank`: bit q set when rank q's rows reference that block column (what the owner pushes
+// to q every iteration); rows of other ranks get 0.  `grid` = CTAs per rank (148 on B200).
+extern "C" int sb_dist_plan(int nbr, const unsigned long long* rows, const int32_t* cols, int world, int grid, int rank, int32_t* out_bounds, unsigned char* out_needmask)
+{
+    if (nbr < 0 || !rows || world < 1 || world > DIST_MAX_WORLD || grid < 1 || rank < 0 || rank >= world || !out_bounds) return SB_ERR_ARG;
+    const unsigned long long nnzb = rows[nbr];
+    const unsigned long long cost = nnzb + 4ull * (unsigned long long)nbr;
+    const int VG = world * grid;
+    for (int q = 0; q <= world; q++)
+        out_bounds[q] = (q == world) ? nbr : host_row_lower_bound(rows, nbr, (cost * (unsigned long long)(q * grid)) / (unsigned long long)VG);
+    if (out_needmask) {
+        memset(out_needmask, 0, (size_t)nbr);
+        const int lo = out_bounds[rank], hi = out_bounds[rank + 1];
+        int q = 0;
+        for (int i = 0; i < nbr; i++) {
+            while (q + 1 < world && i >= out_bounds[q + 1]) q++;
+            if (i >= lo && i < hi) continue;
+            for (unsigned long long j = rows[i]; j < rows[i + 1]; j++) {
+                const int c = cols[j] / 3;
+                if (c >= lo && c < hi) out_needmask[c] |= (unsigned char)(1u << q);
+            }
+        }
+    }
+    return 0;
 }
