@@ -7,7 +7,10 @@ element evaluation, PD projection, assembly, linear solve and line search).
 A "step" is one simulation time step (stark::Simulation::run_one_time_step): the Newton solve of that step is the hot
 path.  Workload at N = 1: BASELINE.json configs[1] (C2) -- 26^3 tet grid (210,912 tets, Soft_Rubber stable Neo-Hookean)
 dropped on a fixed rigid floor with IPC contact and friction; `--config C1|C3|C4|C5` runs the other BASELINE configurations
-(both arms).  For N > 1 every rank runs its own replica of the scene and `value` is the aggregate (DESIGN.md "Multi-GPU").
+(both arms).  For N > 1 the N ranks work on ONE scene (strong scaling): every block-Jacobi PCG solve is shared by all ranks --
+row slabs of the matrix, each rank keeping 1/N of it in shared memory, halo / partial sums / barrier over NVLink peer memory
+inside the persistent kernel (DESIGN.md "Multi-GPU"); evaluation and assembly are replicated.  `--replicas` runs N independent
+scenes instead (weak scaling, no data-plane exchange).
 
 Printed keys (one JSON line on rank 0):
   value   Newton iterations / s with the state resident in HBM: sum(iterations) / sum(device time of the solves, CUDA events)
@@ -38,7 +41,7 @@ CONFIGS = {
     "C2": dict(scene="tetdrop", n=26, ny=-1, nz=-1, steps=30, warmup=5,
                workload="C2 tetdrop: 26^3 Soft_Rubber tet grid (12 tets/hex) on a fixed rigid floor, IPC contact d=1mm k_min=1e8 mu=0.5, dt=10ms, PPN+BDPCG defaults"),
     "C3": dict(scene="cloth_shells", n=256, ny=-1, nz=-1, steps=4, warmup=3,
-               workload="C3 cloth: 256x256 Cotton_Fabric grid with discrete-shell hinges over a scripted fixed rigid box, IPC contact d=2mm, friction mu=0.3, dt=10ms, PPN+BDPCG defaults"),
+               workload="C3 cloth: 256x256 Cotton_Fabric grid (0.4 m, edges 1.56 mm) with discrete-shell hinges over a scripted fixed rigid box, IPC contact d=0.47mm (0.3 edge lengths), friction mu=0.3, dt=10ms, PPN+BDPCG defaults"),
     "C4": dict(scene="tetchain", n=16, ny=10, nz=-1, steps=20, warmup=5,
                workload="C4 tetchain: 16^3 tet grid (49,152 tets, bottom face prescribed) under a chain of 10 hinged rigid boxes, IPC contact + friction mu=0.3, dt=10ms, PPN+BDPCG defaults"),
     "C5": dict(scene="tetbar", n=22, ny=22, nz=172, steps=10, warmup=3,
@@ -46,12 +49,20 @@ CONFIGS = {
 }
 
 
-def workload_config(n_gpus, name, cfg, grid=None):
+def workload_config(n_gpus, name, cfg, grid=None, replicas=False):
     n = grid if grid else cfg["n"]
     reduced = grid is not None and grid != cfg["n"]
+    if n_gpus == 1:
+        par = "single GPU"
+    elif replicas:
+        par = f"{n_gpus} independent replicas (one scene per GPU)"
+    else:
+        par = (f"slab decomposition of the linear solve over {n_gpus} GPUs: contiguous block-row ranges of the 3x3-BCSR per rank (1/{n_gpus} of the matrix in each "
+               "rank's shared memory), halo of u + dot-product partials + barrier as NVLink peer-memory stores inside the persistent PCG kernel; element "
+               "evaluation, projection and assembly replicated on every rank")
     return {"workload": cfg["workload"] if not reduced else f"{cfg['scene']} at a reduced grid {n} (NOT the benchmark configuration)",
             "name": name, "scene": cfg["scene"], "grid": n, "dt": 0.01,
-            "parallelism": "single GPU" if n_gpus == 1 else f"{n_gpus} independent replicas (one scene per GPU)",
+            "parallelism": par,
             "l2_policy": "the element outputs written and read by every evaluation (1,152 B per tet / hinge) exceed the 126 MB L2 at the C2, C3 and C5 sizes; C1 and C4 are L2-resident (latency-bound scenes)"}
 
 
@@ -126,6 +137,7 @@ def main():
     ap.add_argument("--grid", type=int, default=None, help="override the grid size (diagnostic: NOT the benchmark configuration)")
     ap.add_argument("--llt", action="store_true", help="DirectLLT instead of the default BDPCG (both arms; reference: Eigen SimplicialLLT, ours: dense blocked Cholesky, <= 32k DoFs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--replicas", action="store_true", help="N > 1: N independent scenes (weak scaling) instead of one scene with the distributed solve")
     ap.add_argument("--stage-steps", type=int, default=4, help="extra (untimed) steps run with stage profiling on after the timed region; 0 = off")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
@@ -165,9 +177,25 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the stark_b200 hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # (NCCL prints its version banner on stdout at the first collective: keep stdout for the one JSON line)
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+        finally:
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     stream = torch.cuda.Stream()
     sc = scenes.Scene(cfg["scene"], n=grid, ny=cfg["ny"], nz=cfg["nz"], dt=0.01, drop=0.003, device=local_rank, stream=stream.cuda_stream, llt=args.llt)
+    distributed = world > 1 and not args.replicas and not args.llt
+    if distributed:
+        # one scene, N ranks: every PCG solve from here on is shared by all ranks (peer buffers mapped through CUDA IPC).
+        # (the first step registers the scene's degrees of freedom; it is the first of the warm-up steps on every rank)
+        sc.step()
+        warmup_left = max(warmup - 1, 0)
+        sbdist.connect_solver(capi.load(), C.c_void_p(sc.lib.sbh_scene_context(sc.h)), int(sc.totals()["ndofs"]), device=torch.device("cuda", local_rank))
 
     def barrier():
         sbdist.barrier(torch.device("cuda", local_rank))
@@ -175,7 +203,7 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    for _ in range(warmup):
+    for _ in range(warmup_left if distributed else warmup):
         sc.step()
     t0 = sc.totals()
     barrier()
@@ -198,21 +226,14 @@ def main():
 
     # max over ranks of the timed regions, sum over ranks of the work
     (e2e_ms, solve_gpu_ms), (its_all, evals_all, cg_all) = sbdist.aggregate([e2e_ms, solve_gpu_ms], [float(its), float(evals), float(cg)], device="cuda")
-    if rank != 0:
-        if world > 1:
-            dist.barrier()   # rank 0 finishes its single-GPU diagnostics before the group is torn down
-            dist.destroy_process_group()
-        return 0
-
+    if distributed:   # ONE scene: the work is rank 0's, not the sum over the ranks that shared it
+        its_all, evals_all, cg_all = float(its), float(evals), float(cg)
     ctx_handle = C.c_void_p(sc.lib.sbh_scene_context(sc.h))
     lib = capi.load()
-    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else None
-    peak = peaks["hbm_gbs"] if peaks else 6650.0
-    peak_source = "MEASURED_PEAKS.json hbm_gbs (burst: kernels timed alone / inside their own launch)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-
     # ---- per-stage breakdown (diagnostic, outside the timed region): extra steps with a stream sync at every stage boundary ----
+    # (with the distributed solve every rank takes these steps: a solve needs all of them)
     stages = None
-    if args.stage_steps > 0:
+    if args.stage_steps > 0 and (rank == 0 or distributed):
         try:
             lib.sb_profile_stages(ctx_handle, 1)
             it_s = 0
@@ -226,6 +247,17 @@ def main():
                 stages[name] = {"ms": round(float(ms), 4), "calls": int(calls)}
         except Exception as e:
             stages = {"error": repr(e)}
+            if distributed:
+                raise
+    if rank != 0:
+        if world > 1:
+            dist.barrier()   # rank 0 finishes its single-GPU diagnostics before the group is torn down
+            dist.destroy_process_group()
+        return 0
+
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else None
+    peak = peaks["hbm_gbs"] if peaks else 6650.0
+    peak_source = "MEASURED_PEAKS.json hbm_gbs (burst: kernels timed alone / inside their own launch)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
 
     # ---- rooflines, both measured live in this run ----
     # (1) element evaluation: the EnergyTetStrain P + grad + Hessian kernel timed alone with CUDA events on the context stream
@@ -257,8 +289,9 @@ def main():
             bytes_it = 40 * nnzb.value + 8 * (nbr.value + 1) + 156 * ndofs
             us_it = 1e3 * stages["cg_iterations"]["ms"] / stages["cg_iterations"]["calls"]
             achieved = bytes_it / (us_it * 1e-6) / 1e9
+            peak_all = peak * (world if distributed else 1)   # a distributed iteration runs on all ranks' GPUs
             kernels.append({"kernel": "k_pcg_solve: one block-Jacobi PCG iteration (SpMV from the resident / streamed 3x3-BCSR + vector phase + 2 grid barriers)", "bound": "hbm",
-                            "achieved": achieved, "peak": peak, "peak_source": peak_source, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                            "achieved": achieved, "peak": peak_all, "peak_source": peak_source + (f" x {world} GPUs" if distributed else ""), "unit": "GB/s", "frac": achieved / peak_all, "traffic": None,
                             "us_per_iteration": us_it, "algorithmic_bytes_per_iteration": bytes_it, "iterations_timed": stages["cg_iterations"]["calls"],
                             "how": "the kernel's own %globaltimer around its iteration loop, summed over the stage-profiled steps (one launch per solve)"})
     except Exception as e:
@@ -281,8 +314,8 @@ def main():
 
     line = {
         "metric": METRIC, "value": its_all / (solve_gpu_ms * 1e-3), "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
-        "ms_per_step": e2e_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.gpus, args.config, cfg, args.grid),
+        "ms_per_step": e2e_ms / steps, "higher_is_better": True, "scaling": "strong" if distributed else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus, args.config, cfg, args.grid, args.replicas or args.llt),
         "value_note": "Newton iterations / device time of the steps' Newton path (CUDA events on the context stream from the start-of-step collision detection to the end of the solve), state resident in HBM",
         "e2e": {"value": its_all / (e2e_ms * 1e-3), "unit": UNIT,
                 "h2d_bytes_per_step": (t1["h2d_bytes"] - t0["h2d_bytes"]) / steps, "d2h_bytes_per_step": (t1["d2h_bytes"] - t0["d2h_bytes"]) / steps,
@@ -290,9 +323,15 @@ def main():
         "gpu_launches": int(t1["launches"] - t0["launches"]),
         "newton_iterations": its_all, "evaluations": evals_all, "cg_iterations": cg_all, "accepted_steps": accepted, "wall_s_rank0": wall_s,
         "linear_solver": "DirectLLT" if args.llt else "BDPCG",
-        "solve_gpu_ms_per_iteration": solve_gpu_ms / max(1.0, its_all / world),
+        "solve_gpu_ms_per_iteration": solve_gpu_ms / max(1.0, its_all if distributed else its_all / world),
         "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "stages": stages,
     }
+    if distributed:
+        st4 = (C.c_double * 4)()
+        lib.sb_dist_stats(ctx_handle, None, None, st4)
+        line["distributed"] = {"solves_shared_by_all_ranks": int(st4[1]), "solves_kept_local_by_policy": int(st4[3]), "cross_gpu_barriers": int(st4[0]),
+                               "peer_buffer_bytes": int(st4[2]), "policy": os.environ.get("SB_DIST_POLICY", "auto"),
+                               "note": "policy auto: a matrix resident in one GPU's shared memory is solved locally by every rank (identical results); larger systems are shared"}
     print(json.dumps(line))
     if world > 1:
         dist.barrier()

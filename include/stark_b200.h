@@ -266,8 +266,11 @@ SB_API int sb_dist_connect(sb_context* ctx, const unsigned char* handles);
 /* ranks inside one process connect by pointer instead (bases[q] = sb_dist_local_base of rank q's context) */
 SB_API int sb_dist_connect_ptrs(sb_context* ctx, void* const* bases);
 SB_API void* sb_dist_local_base(sb_context* ctx);
-/* out3 = { barriers completed, distributed solves, bytes of the peer buffer } */
-SB_API int sb_dist_stats(sb_context* ctx, int* out_rank, int* out_world, double* out3);
+/* out4 = { barriers completed, distributed solves, bytes of the peer buffer, solves the policy kept on the own GPU }.
+ * Policy (environment SB_DIST_POLICY = auto | always, default auto): a system whose matrix is resident in ONE GPU's shared memory
+ * is solved locally by every rank (its iteration is bound by grid-wide synchronisation, which costs more across NVLink than on
+ * chip); systems that do not fit are shared by all ranks.  All ranks decide alike (same pattern sizes). */
+SB_API int sb_dist_stats(sb_context* ctx, int* out_rank, int* out_world, double* out4);
 /* The row partition and the halo send lists of a distributed solve, on HOST arrays in sb_bcsr_get's layout (no GPU needed):
  * out_bounds[world + 1] = first block row of every rank; out_needmask[nbr]: for the block rows `rank` owns, bit q is set when
  * rank q's rows reference that column of u (the owner pushes the row to q every iteration).  grid = CTAs per rank. */

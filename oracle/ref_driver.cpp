@@ -199,7 +199,9 @@ static Scene scene_cloth(const Args& a, bool discrete_shells, double mu)
 	sc.sim = std::make_unique<stark::Simulation>(settings);
 	auto& sim = *sc.sim;
 	stark::EnergyFrictionalContact::GlobalParams cp;
-	cp.default_contact_thickness = 0.002;
+	// the contact thickness has to stay below the mesh spacing (0.4 m / n): 2 mm up to n = 64, 0.3 edge lengths on finer grids
+	// (at n = 256 the edges are 1.56 mm long: with 2 mm every neighbouring primitive pair would be in contact at rest)
+	cp.default_contact_thickness = (a.n > 64) ? 0.3 * 0.4 / a.n : 0.002;
 	sim.interactions->contact->set_global_params(cp);
 	auto material = stark::Surface::Params::Cotton_Fabric();
 	if (discrete_shells) material.bending.flat_rest_angle = false;

@@ -35,6 +35,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 
 namespace sb {
 
@@ -61,6 +62,7 @@ struct PcgResult {
     unsigned long long t_start, t_loaded, t_loop, t_end;   // %globaltimer (ns) of CTA 0: kernel entry, slices resident, first iteration, exit
     long long c_spmv, c_bar, c_red, c_vec, c_win;          // clock64 cycles of CTA 0 inside the loop (only when instrumented)
     unsigned long long barriers;                           // grid barriers this solve executed (the distributed counter never resets)
+    unsigned long long ll_uses;                            // flagged all-reduces this solve executed (their flags never repeat either)
 };
 
 // Distributed solve (one process per GPU, all ranks hold the same assembled matrix and right-hand side): the W x G CTAs of all
@@ -71,7 +73,12 @@ struct PcgResult {
 //     (needmask, built per solve from the replicated pattern: the halo of a slab, plus rigid bodies / far contacts);
 //   * dot products: every CTA stores its partial into the partial arrays of ALL ranks; after the barrier every CTA of every rank
 //     re-reduces the same W x G values in the same order (identical scalars and decisions everywhere, as on one GPU);
-//   * barrier: one release-reduction on every rank's counter, acquire spin on the own one (flat: one NVLink hop);
+//   * barrier after the vector phase (u and two partials published): one system fence, then one relaxed reduction on every rank's
+//     counter, acquire spin on the own one (flat: the fence's round trip + one NVLink hop);
+//   * all-reduce of w.u after the product: no fence and no counter -- every CTA stores ONE 16-byte flagged packet
+//     {lo, flag, hi, flag} (8-byte halves, each with its flag: the granularity NVLink stores are atomic at) into slot
+//     [virtual CTA] of every rank and then polls all W x G slots until they carry this use's flag: one NVLink hop, and the
+//     arrival of all packets is the barrier (every CTA has finished its product);
 //   * du: every CTA stores its slice of the solution into every rank's copy.
 struct DistArgs {
     int world, rank;
@@ -82,6 +89,8 @@ struct DistArgs {
     double* u[DIST_MAX_WORLD];
     double* u4[DIST_MAX_WORLD];
     double* du[DIST_MAX_WORLD];
+    uint4* ll[DIST_MAX_WORLD];                // every rank's packet slots [PCG_MAX_BLOCKS]
+    unsigned ll_base;                         // flags used by earlier solves
     const unsigned char* needmask;            // [nbr] bit q: rank q reads this block row of u (own bit clear)
     int* abort_flag;                          // local: set by the first CTA that timed out
 };
@@ -130,9 +139,10 @@ struct Dist {
     unsigned char* base[DIST_MAX_WORLD] = {nullptr};   // base[rank] is the own buffer
     bool opened[DIST_MAX_WORLD] = {false};              // peer mappings opened through IPC (closed at destroy)
     bool connected = false;
-    size_t bytes = 0, off_part = 0, off_u = 0, off_u4 = 0, off_du = 0;
+    size_t bytes = 0, off_part = 0, off_ll = 0, off_u = 0, off_u4 = 0, off_du = 0;
+    unsigned ll_base = 0;                               // flags of the flagged all-reduce used so far (identical on every rank)
     unsigned long long epoch_base = 0;                  // barriers completed so far (identical on every rank)
-    unsigned long long n_solves = 0;
+    unsigned long long n_solves = 0, n_local_solves = 0;   // distributed solves / solves the policy kept on the own GPU
     DevBuf<unsigned char> needmask;
     int* d_abort = nullptr;
     int grid_override = 0;                              // test hook (SB_PCG_GRID): smaller grids so that two solves share one GPU
@@ -307,6 +317,39 @@ __device__ __forceinline__ void apply_dinv(const float* d, double r0, double r1,
     z2 = (double)d[6] * r0 + (double)d[7] * r1 + (double)d[8] * r2;
 }
 
+// ---- flagged all-reduce (sum) over the virtual grid: see DistArgs ----
+__device__ __forceinline__ unsigned long long global_ns();
+__device__ __forceinline__ void ll_put(const DistArgs& D, int vb, double v, unsigned flag)
+{
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    const unsigned lo = (unsigned)b, hi = (unsigned)(b >> 32);
+    for (int q = 0; q < D.world; q++)
+        asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" :: "l"(D.ll[q] + vb), "r"(lo), "r"(flag), "r"(hi), "r"(flag) : "memory");
+}
+__device__ __forceinline__ double ll_all_sum(const DistArgs& D, int n, unsigned flag, double* s, double* bc, int* s_abort)
+{
+    const uint4* slots = D.ll[D.rank];
+    double a = 0.0;
+    for (int i = threadIdx.x; i < n; i += PCG_THREADS) {
+        unsigned x, f0, y, f1, spins = 0;
+        unsigned long long t0 = 0;
+        for (;;) {
+            asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x), "=r"(f0), "=r"(y), "=r"(f1) : "l"(slots + i) : "memory");
+            if (f0 == flag && f1 == flag) break;
+            if ((++spins & 1023u) == 0u) {
+                const unsigned long long now = global_ns();
+                if (!t0) t0 = now;
+                if (now - t0 > D.timeout_ns || *(volatile int*)D.abort_flag || *(volatile int*)s_abort) { *(volatile int*)D.abort_flag = 1; *(volatile int*)s_abort = 1; x = y = 0u; break; }
+            }
+        }
+        a += __longlong_as_double((long long)(((unsigned long long)y << 32) | x));
+    }
+    const double t = block_sum(a, s);
+    if (threadIdx.x == 0) *bc = t;
+    __syncthreads();
+    return *bc;
+}
+
 // Row partition: a CTA's iteration costs about one unit per block (product) plus ROW_COST units per block row (vector
 // phase, row bookkeeping), so the rows are cut into slices of equal  blocks + ROW_COST * rows.  (Cutting by blocks alone gives
 // the slices of sparse rows -- hex-centre nodes: 9 blocks per row instead of 27 -- twice the rows and twice the vector phase.)
@@ -359,9 +402,9 @@ __device__ __forceinline__ bool dist_barrier(const DistArgs& D, unsigned long lo
     __syncthreads();
     epoch++;
     if (threadIdx.x == 0 && !*s_abort) {
-        __threadfence_system();
+        __threadfence_system();   // (one fence for all W arrivals: a release per reduction would pay the round trip W times)
         for (int q = 0; q < D.world; q++)
-            asm volatile("red.release.sys.global.add.u64 [%0], %1;" :: "l"(D.bar[q]), "l"(1ull) : "memory");
+            asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" :: "l"(D.bar[q]), "l"(1ull) : "memory");
         const unsigned long long target = (D.epoch_base + epoch) * (unsigned long long)(D.world * (int)gridDim.x);
         unsigned long long v, t0 = 0;
         unsigned spins = 0;
@@ -418,6 +461,7 @@ __device__ __forceinline__ void pcg_body(const PcgArgs& A, const PcgPlan& P)
     const int tid = threadIdx.x;
     unsigned epoch = 0;
     unsigned long long depoch = 0;
+    unsigned ll_uses = 0;
     double* part0 = DIST ? A.d.part[A.d.rank] : A.part;
     double* part1 = part0 + PCG_MAX_BLOCKS;
     double* part2 = part0 + 2 * PCG_MAX_BLOCKS;
@@ -455,7 +499,7 @@ __device__ __forceinline__ void pcg_body(const PcgArgs& A, const PcgPlan& P)
     auto COL = [&](int j) -> int { return (MODE >= 2) ? __ldg(cols + j) : cols[j]; };
     auto VAL = [&](const float* q) -> float { return (MODE >= 2) ? __ldg(q) : *q; };
     double* uwin = (MODE != 0) ? reinterpret_cast<double*>(pcg_smem + P.off_win) : P.uwin;
-    (void)G; (void)nbr; (void)bc; (void)VG; (void)depoch;
+    (void)G; (void)nbr; (void)bc; (void)VG; (void)depoch; (void)ll_uses;
     auto is_swept = [&](int lr) {   // long AND listed (every listed row gets its own block reduction)
         if (rp[lr + 1] - rp[lr] <= LONG_ROW) return false;
         for (int k = 0; k < n_long; k++) if (s_long[k] == lr) return true;
@@ -758,11 +802,22 @@ __device__ __forceinline__ void pcg_body(const PcgArgs& A, const PcgPlan& P)
         load_window();
         const double wu = product();
         const double t = block_sum(wu, s);
-        if (tid == 0) put_part(2, t);
-        PCG_TICK(c_spmv);
-        const bool ab = gbar();
-        PCG_TICK(c_bar);
-        const double delta = all_partials(part2, VG, s, &bc);
+        bool ab;
+        double delta;
+        if (DIST) {
+            if (tid == 0) ll_put(A.d, vb, t, A.d.ll_base + (++ll_uses));
+            else ++ll_uses;
+            PCG_TICK(c_spmv);
+            delta = ll_all_sum(A.d, VG, A.d.ll_base + ll_uses, s, &bc, P.s_abort);
+            ab = *P.s_abort != 0;
+            PCG_TICK(c_bar);
+        } else {
+            if (tid == 0) put_part(2, t);
+            PCG_TICK(c_spmv);
+            ab = gbar();
+            PCG_TICK(c_bar);
+            delta = all_partials(part2, VG, s, &bc);
+        }
         PCG_TICK(c_red);
         if (ab) done = 4;
         else if (delta <= 0.0) {
@@ -810,12 +865,20 @@ __device__ __forceinline__ void pcg_body(const PcgArgs& A, const PcgPlan& P)
         {
             const double wu = product();
             const double t = block_sum(wu, s);
-            if (tid == 0) put_part(2, t);
+            if (DIST) { if (tid == 0) ll_put(A.d, vb, t, A.d.ll_base + (++ll_uses)); else ++ll_uses; }
+            else if (tid == 0) put_part(2, t);
         }
         PCG_TICK(c_spmv);
-        if (gbar()) { done = 4; break; }
-        PCG_TICK(c_bar);
-        const double delta = all_partials(part2, VG, s, &bc);
+        double delta;
+        if (DIST) {
+            delta = ll_all_sum(A.d, VG, A.d.ll_base + ll_uses, s, &bc, P.s_abort);
+            if (*P.s_abort) { done = 4; break; }
+            PCG_TICK(c_bar);
+        } else {
+            if (gbar()) { done = 4; break; }
+            PCG_TICK(c_bar);
+            delta = all_partials(part2, VG, s, &bc);
+        }
         PCG_TICK(c_red);
         beta = gamma_new / gamma;
         const double pAp = delta - beta * gamma_new / alpha;     // p^T A p of the coming iteration
@@ -861,6 +924,7 @@ __device__ __forceinline__ void pcg_body(const PcgArgs& A, const PcgPlan& P)
             R.c_spmv = c_spmv; R.c_bar = c_bar; R.c_red = c_red; R.c_vec = c_vec; R.c_win = c_win;
             R.t_start = t_start; R.t_loaded = t_loaded; R.t_loop = t_loop; R.t_end = global_ns();
             R.barriers = DIST ? depoch : (unsigned long long)epoch;
+            R.ll_uses = ll_uses;
             *A.result = R;
         }
     }
@@ -1100,6 +1164,15 @@ int solve_pcg_internal(sb_context* ctx, double abs_tol, double rel_tol, int max_
     // cycles per request).  Such solves run with a smaller carve-out, so that the nine loads of a 36-byte block share one or two
     // L1 line fills.  (The experimental tiled mode needs no L1 and takes everything again.)
     Dist* DS = (ctx->dist && ctx->dist->connected && ctx->dist->world > 1) ? ctx->dist : nullptr;
+    // Policy (SB_DIST_POLICY=auto|always, default auto): a matrix that is resident in ONE GPU's shared memory gains nothing from
+    // more GPUs -- its iteration is bound by grid-wide synchronisation, and a synchronisation across NVLink costs about four times
+    // an on-chip one -- so such solves stay local (every rank solves its own replica, results identical); systems that do not fit
+    // (million-tet bars, 66 k-node cloth) are shared by all ranks.  Every rank takes the same decision from the same pattern sizes.
+    if (DS) {
+        static const bool always = std::getenv("SB_DIST_POLICY") && std::string(std::getenv("SB_DIST_POLICY")) == "always";
+        const double resident1 = 1.08 * (40.0 * (double)nnzb + 160.0 * (double)nbr) / P->grid;
+        if (!always && resident1 <= (double)P->smem_bytes) { DS->n_local_solves++; DS = nullptr; }
+    }
     if (DS && (size_t)n > DS->max_dofs) return fail(ctx, SB_ERR_STATE, "sb_solve_pcg: the system has more DoFs than sb_dist_init reserved peer memory for");
     const int vgrid = P->grid * (DS ? DS->world : 1);   // CTAs of all ranks
     unsigned smem_launch = P->smem_bytes;
@@ -1145,7 +1218,9 @@ int solve_pcg_internal(sb_context* ctx, double abs_tol, double rel_tol, int max_
             d.u[q] = reinterpret_cast<double*>(DS->base[q] + DS->off_u);
             d.u4[q] = reinterpret_cast<double*>(DS->base[q] + DS->off_u4);
             d.du[q] = reinterpret_cast<double*>(DS->base[q] + DS->off_du);
+            d.ll[q] = reinterpret_cast<uint4*>(DS->base[q] + DS->off_ll);
         }
+        d.ll_base = DS->ll_base;
         A.u = d.u[d.rank]; A.u4 = d.u4[d.rank]; A.du = nullptr;
         DS->needmask.ensure((size_t)nbr + 8);
         SB_CUDA(ctx, cudaMemsetAsync(DS->needmask.p, 0, (size_t)nbr + 8, st));
@@ -1162,6 +1237,7 @@ int solve_pcg_internal(sb_context* ctx, double abs_tol, double rel_tol, int max_
     SB_CUDA(ctx, cudaGetLastError());
     if (DS) {
         DS->epoch_base += P->h_result->barriers;
+        DS->ll_base += (unsigned)P->h_result->ll_uses;
         DS->n_solves++;
         if (P->h_result->done == 4)
             return fail(ctx, SB_ERR_CUDA, "sb_solve_pcg: distributed solve aborted: a peer rank did not arrive at a barrier within SB_DIST_TIMEOUT_S (ranks out of step, or a peer failed)");
@@ -1216,7 +1292,8 @@ extern "C" int sb_dist_init(sb_context* ctx, int rank, int world, long long max_
     D->world = world; D->rank = rank; D->max_dofs = (size_t)max_dofs;
     const size_t nbr = ((size_t)max_dofs + 2) / 3;
     D->off_part = 256;
-    D->off_u = align256(D->off_part + 2 * 3 * (size_t)PCG_MAX_BLOCKS * sizeof(double));
+    D->off_ll = align256(D->off_part + 2 * 3 * (size_t)PCG_MAX_BLOCKS * sizeof(double));
+    D->off_u = align256(D->off_ll + (size_t)PCG_MAX_BLOCKS * sizeof(uint4));
     D->off_u4 = align256(D->off_u + sizeof(double) * ((size_t)max_dofs + 4));
     D->off_du = align256(D->off_u4 + sizeof(double) * 4 * (nbr + 1));
     D->bytes = align256(D->off_du + sizeof(double) * ((size_t)max_dofs + 4));
@@ -1276,14 +1353,14 @@ extern "C" void* sb_dist_local_base(sb_context* ctx)
     return (ctx && ctx->dist) ? ctx->dist->base[ctx->dist->rank] : nullptr;
 }
 
-// out3 = { barriers completed, distributed solves, bytes of the peer buffer }
+// out4 = { barriers completed, distributed solves, bytes of the peer buffer, solves kept local by the policy }
 extern "C" int sb_dist_stats(sb_context* ctx, int* out_rank, int* out_world, double* out3)
 {
     if (!ctx) return SB_ERR_ARG;
     const Dist* D = ctx->dist;
     if (out_rank) *out_rank = D ? D->rank : 0;
     if (out_world) *out_world = (D && D->connected) ? D->world : 1;
-    if (out3) { out3[0] = D ? (double)D->epoch_base : 0.0; out3[1] = D ? (double)D->n_solves : 0.0; out3[2] = D ? (double)D->bytes : 0.0; }
+    if (out3) { out3[0] = D ? (double)D->epoch_base : 0.0; out3[1] = D ? (double)D->n_solves : 0.0; out3[2] = D ? (double)D->bytes : 0.0; out3[3] = D ? (double)D->n_local_solves : 0.0; }
     return 0;
 }
 

@@ -47,7 +47,8 @@ void build_cloth(Scene& sc, int n, double dt, double drop, bool discrete_shells,
     sc.sim = std::make_unique<Simulation>(s);
     Simulation& sim = *sc.sim;
     EnergyFrictionalContact::GlobalParams cp;
-    cp.default_contact_thickness = 0.002;
+    // below the mesh spacing (0.4 m / n): 2 mm up to n = 64, 0.3 edge lengths on finer grids (same rule as oracle/ref_driver.cpp)
+    cp.default_contact_thickness = (n > 64) ? 0.3 * 0.4 / n : 0.002;
     sim.contact.set_global_params(cp);
     SurfaceParams material = SurfaceParams::Cotton_Fabric();
     if (discrete_shells) material.flat_rest_angle = false;

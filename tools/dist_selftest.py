@@ -27,6 +27,7 @@ args = ap.parse_args()
 if not args.multiprocess:
     os.environ.setdefault("SB_PCG_GRID", "16")           # W kernels of 16 CTAs share the GPU
     os.environ.setdefault("SB_DIST_TIMEOUT_S", "20")
+os.environ.setdefault("SB_DIST_POLICY", "always")        # the fixtures are tiny: the automatic policy would keep their solves local
 
 import numpy as np  # noqa: E402
 from golden_util import Golden, bind  # noqa: E402
@@ -113,7 +114,7 @@ err = float(np.abs(dus[-1][0] - du_ref).max() / np.abs(du_ref).max())
 its = [results[k][0]["iterations"] for k in range(args.solves)]
 ok = bool(identical and repeat and err < 1e-6 and all(results[k][r]["ok"] for k in range(args.solves) for r in range(W))
           and all(abs(i - ref["iterations"]) <= 2 for i in its))
-st = (C.c_double * 3)()
+st = (C.c_double * 4)()
 lib.sb_dist_stats(ctxs[0].h, None, None, st)
 print(json.dumps({"mode": "threads", "world": W, "fixture": args.fixture, "ref_iterations": ref["iterations"], "dist_iterations": its, "rel_err": err,
                   "identical_across_ranks": identical, "identical_across_solves": repeat, "barriers": st[0], "ok": ok}))
