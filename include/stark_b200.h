@@ -93,6 +93,28 @@ typedef struct sb_fetch {
 SB_API int sb_potential_create(sb_context* ctx, const char* kernel_name, int conn_stride, const sb_fetch* fetch, int n_fetch, int* out_potential);
 SB_API int sb_potential_set_connectivity(sb_context* ctx, int potential, const int32_t* conn, int n_elements);
 SB_API int sb_potential_info(sb_context* ctx, int potential, int* n_in, int* n_dofs, int* n_elements);
+/* User potentials (GlobalPotential::add_potential with an energy no built-in kernel covers, e.g. examples/main.cpp:666-690):
+ * replaces the reference's code generator + host-compiler JIT (symx/compile/Compilation.cpp:381-469 `_add_instructions_scalar`,
+ * one C statement per symx::core::Op of a Sequence -- compile/FixedBranchSequence.h:44-83 -- then g++ and dlopen) by CUDA source
+ * + NVRTC + a cubin cache ($SB_CACHE_DIR, default ~/.cache/stark_b200, keyed by a hash of the generated source).
+ * The caller differentiates the energy with symx itself (SecondOrderCompiledPotential.cpp:62-80: gradient, symmetric Hessian)
+ * and passes the operation sequences of [E] and of [E | grad(n) | hess(n x n, row-major)] with n = 3 n_blocks:
+ *   sb_op mirrors symx::core::Op: type = symx::ExprType value (symbol/Expr.h:12-44; Symbol = 5 means out[dst] = value a),
+ *   dst / a / b / cond = indices into [in[0 .. n_in) | temporaries], constant = value of a ConstantFloat; Branch ops use the
+ *   reference's encoding (cond == -2: end-if; a == 0: `if (value[cond] > 0) {`; a == 1: `} else {`).
+ * dof_block_slots[b] = in[] slot of the first of the three DoF symbols of block b (DoF-set order, then slot order, as
+ * SecondOrderCompiledPotential builds `dofs`).  Fails with SB_ERR_NO_KERNEL when NVRTC cannot be loaded. */
+typedef struct sb_op {
+    int32_t type, dst, a, b, cond, pad;
+    double constant;
+} sb_op;
+SB_API int sb_potential_create_user(sb_context* ctx, const char* name, int conn_stride, const sb_fetch* fetch, int n_fetch, int n_in, int n_blocks,
+                                    const int32_t* dof_block_slots, const sb_op* ops_p, int n_ops_p, const sb_op* ops_pgh, int n_ops_pgh, int* out_potential);
+/* the two halves of the above without a GPU: the generated CUDA source (out_length = its size; out_source may be NULL), and
+ * its compilation for sm_100a (NVRTC cross-compiles; out_log receives the compiler's messages on failure) */
+SB_API int sb_user_codegen(const char* name, int n_in, int n_blocks, const sb_op* ops_p, int n_ops_p, const sb_op* ops_pgh, int n_ops_pgh,
+                           char* out_source, long long capacity, long long* out_length);
+SB_API int sb_user_compile(const char* source, long long* out_cubin_bytes, int* out_was_cached, char* out_log, int log_capacity);
 /* names of all built-in kernels, '\n' separated */
 SB_API const char* sb_kernel_names(void);
 

@@ -11,8 +11,9 @@
 //   * constructor: walks GlobalPotential exactly as SecondOrderCompiledGlobal does (SecondOrderCompiledGlobal.cpp:9-70):
 //     DoF maps -> sb_dof_add in order; every potential's MappedWorkspace::maps -> one device array per distinct bound container
 //     (DataMap::id) and the potential's fetch table {array, connectivity_index, first_symbol_idx, stride}; the kernel is looked
-//     up by the potential's NAME (sb_potential_create).  A potential without a built-in kernel is a fatal error in the reference's
-//     style (print + exit(-1)) -- that is where a Sequence -> NVRTC back-end would plug in.
+//     up by the potential's NAME (sb_potential_create).  A potential without a built-in kernel (a user's add_potential) is
+//     differentiated here with symx's own symbolic engine and its operation sequences go to the library's Sequence -> CUDA -> NVRTC
+//     back-end (sb_potential_create_user).
 //   * solve(): the reference's control flow (NewtonsMethod.cpp:28-252, 254-371, 388-457, 459-641) on device-resident state, stage
 //     by stage through the C-ABI.  User / model callbacks run on the host exactly where the reference runs them; around them the
 //     DoFs are written back into the model's arrays (GlobalPotential::set_dofs) and every bound array / connectivity the callbacks
@@ -42,6 +43,9 @@
 #include "solver_utils.h"
 #undef private
 #include "NewtonsMethod.h"
+#include "../symbol/diff.h"            // gradient / symmetric Hessian of a user potential's energy (symx's own symbolic engine)
+#include "../symbol/utils.h"           // collect_scalars
+#include "../compile/Sequence.h"       // the operation sequence the reference's code generator would print
 #include <fmt/format.h>
 
 #include "stark_b200.h"
@@ -208,9 +212,37 @@ symx::NewtonsMethod::NewtonsMethod(spGlobalPotential global_potential, spContext
         PotRec r;
         r.pot = pot.get();
         r.conn_stride = mws->conn.stride;
-        const int status = sb_potential_create(gpu->ctx, pot->get_name().c_str(), r.conn_stride, fetch.data(), (int)fetch.size(), &r.handle);
-        if (status == SB_ERR_NO_KERNEL)
-            die("potential '" + pot->get_name() + "' has no GPU kernel in this build (a user potential: the Sequence -> CUDA back-end is not part of it)");
+        int status = sb_potential_create(gpu->ctx, pot->get_name().c_str(), r.conn_stride, fetch.data(), (int)fetch.size(), &r.handle);
+        if (status == SB_ERR_NO_KERNEL) {
+            // a user potential: differentiate it as SecondOrderCompiledPotential does (SecondOrderCompiledPotential.cpp:9-80) and hand
+            // the operation sequences of [E] and [E | grad | hess] to the library's Sequence -> CUDA -> NVRTC back-end
+            std::vector<Scalar> dofs;
+            std::vector<int32_t> block_slots;
+            for (const auto& dof_map : global_potential->get_dof_maps()) {
+                const std::vector<Scalar> set_dofs = mws->get_symbols(dof_map);
+                if (set_dofs.size() % 3 != 0) die("user potential '" + pot->get_name() + "': DoF symbols do not come in 3-vectors");
+                for (size_t k = 0; k < set_dofs.size(); k += 3) block_slots.push_back(set_dofs[k].get_symbol_idx());
+                dofs.insert(dofs.end(), set_dofs.begin(), set_dofs.end());
+            }
+            if (dofs.empty()) die("user potential '" + pot->get_name() + "' has no degrees of freedom");
+            const Scalar v = pot->get_expression();
+            DiffCache diff_cache;
+            const Vector g = gradient(v, dofs, diff_cache);
+            const Matrix h = gradient(g, dofs, /*symmetric=*/true, diff_cache);
+            Sequence seq_p({v});
+            Sequence seq_pgh(collect_scalars({{v}, g.values(), h.values()}));
+            auto to_ops = [](const Sequence& seq) {
+                std::vector<sb_op> ops(seq.ops.size());
+                for (size_t k = 0; k < seq.ops.size(); k++) {
+                    const core::Op& o = seq.ops[k];
+                    ops[k].type = (int32_t)o.type; ops[k].dst = o.dst; ops[k].a = o.a; ops[k].b = o.b; ops[k].cond = o.cond; ops[k].pad = 0; ops[k].constant = o.constant;
+                }
+                return ops;
+            };
+            const std::vector<sb_op> ops_p = to_ops(seq_p), ops_pgh = to_ops(seq_pgh);
+            status = sb_potential_create_user(gpu->ctx, pot->get_name().c_str(), r.conn_stride, fetch.data(), (int)fetch.size(), seq_pgh.get_n_inputs(),
+                                              (int)block_slots.size(), block_slots.data(), ops_p.data(), (int)ops_p.size(), ops_pgh.data(), (int)ops_pgh.size(), &r.handle);
+        }
         gpu->check(status, ("sb_potential_create(" + pot->get_name() + ")").c_str());
         gpu->pots.push_back(r);
     }

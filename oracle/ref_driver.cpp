@@ -87,6 +87,7 @@ struct Args
 	bool llt = false;
 	double inject = 1.0; // dump: injected DoF state v1 := inject * v0 + small deterministic noise
 	std::string trace = ""; // trace mode: one JSON line per time step (solver statistics + state) into this file
+	std::string ops = "";   // dump: name of a (user) potential whose symx operation sequences are dumped as well
 };
 
 static Args parse(int argc, char** argv)
@@ -97,6 +98,7 @@ static Args parse(int argc, char** argv)
 		auto next = [&]() { if (i + 1 >= argc) { std::cerr << "missing value for " << s << "\n"; exit(2); } return std::string(argv[++i]); };
 		if (s == "--scene") a.scene = next();
 		else if (s == "--n") a.n = std::stoi(next());
+		else if (s == "--ops") a.ops = next();
 		else if (s == "--ny") a.ny = std::stoi(next());
 		else if (s == "--nz") a.nz = std::stoi(next());
 		else if (s == "--steps") a.steps = std::stoi(next());
@@ -124,6 +126,7 @@ struct Scene
 {
 	std::unique_ptr<stark::Simulation> sim;
 	std::function<void()> per_step = nullptr;
+	std::shared_ptr<void> keep = nullptr;   // data a user potential's lambda binds by reference
 };
 
 static stark::Settings base_settings(const Args& a, const std::string& name)
@@ -167,6 +170,37 @@ static Scene scene_tetdrop(const Args& a)
 	floor.rigidbody.set_translation({ 0.0, 0.0, -0.05 });
 	sim.rigidbodies->add_constraint_fix(floor.rigidbody);
 	sim.interactions->contact->set_friction(floor.contact, H.contact, 0.5);
+	return sc;
+}
+
+// A USER potential (examples/main.cpp:666-690, EnergyMagneticAttraction): the tet drop scene plus an attraction -k / |x1 - m| of
+// every vertex to a fixed magnet, added through the public GlobalPotential::add_potential with a lambda -- no kernel of that
+// name exists on the GPU path, the drop-in has to generate one from the symbolic expression.
+struct MagnetData { Eigen::Vector3d center = { 0.3, 0.2, 2.5 }; double force = 40.0; symx::LabelledConnectivity<1> conn{ { "point" } }; };
+static Scene scene_magnet(const Args& a)
+{
+	Scene sc = scene_tetdrop(a);
+	auto& sim = *sc.sim;
+	auto data = std::make_shared<MagnetData>();
+	sc.keep = data;
+	stark::core::Stark& st = sim.get_stark();
+	stark::PointDynamics* dyn = sim.deformables->point_sets.get();
+	for (int i = 0; i < dyn->size(); i++) data->conn.push_back({ i });
+	MagnetData* d = data.get();
+	stark::core::Stark* pst = &st;
+	st.global_potential->add_potential("EnergyMagneticAttraction", d->conn,
+		[dyn, pst, d](symx::MappedWorkspace<double>& mws, symx::Element& elem)
+		{
+			symx::Vector v1 = mws.make_vector(dyn->v1.data, elem["point"]);
+			symx::Vector x0 = mws.make_vector(dyn->x0.data, elem["point"]);
+			symx::Scalar dt = mws.make_scalar(pst->dt);
+			symx::Scalar k = mws.make_scalar(d->force);
+			symx::Vector m = mws.make_vector(d->center);
+			symx::Vector x1 = stark::time_integration(x0, v1, dt);
+			symx::Vector r = x1 - m;
+			return -k / r.norm();
+		}
+	);
 	return sc;
 }
 
@@ -487,6 +521,7 @@ static Scene make_scene(const Args& a)
 	if (a.scene == "boxes") return scene_boxes(a);
 	if (a.scene == "attach") return scene_attach(a);
 	if (a.scene == "tetdrop") return scene_tetdrop(a);
+	if (a.scene == "magnet") return scene_magnet(a);
 	if (a.scene == "tetbar") return scene_tetbar(a);
 	if (a.scene == "cloth") return scene_cloth(a, false, 0.0);
 	if (a.scene == "cloth_shells") return scene_cloth(a, true, 0.3);
@@ -618,6 +653,32 @@ static void dump_iteration(const Args& a, stark::Simulation& sim)
 				}, cp.has_element_positive_condition);
 			D.bin("pot" + std::to_string(p) + "_sol", sol.data(), sol.size());
 			D.bin("pot" + std::to_string(p) + "_active", active.data(), active.size());
+		}
+		// user potentials: the operation sequences the reference's code generator prints (Compilation.cpp:381-469), as
+		// SecondOrderCompiledPotential.cpp:9-80 builds them -- input of the GPU path's Sequence -> CUDA back-end
+		if (pot.get_name() == a.ops) {
+			std::vector<symx::Scalar> dofs;
+			std::vector<int32_t> block_slots;
+			for (const auto& dof_map : gp->get_dof_maps()) {
+				const std::vector<symx::Scalar> set_dofs = mws->get_symbols(dof_map);
+				for (size_t k = 0; k < set_dofs.size(); k += 3) block_slots.push_back(set_dofs[k].get_symbol_idx());
+				dofs.insert(dofs.end(), set_dofs.begin(), set_dofs.end());
+			}
+			const symx::Scalar v = pot.get_expression();
+			symx::DiffCache diff_cache;
+			const symx::Vector g = symx::gradient(v, dofs, diff_cache);
+			const symx::Matrix h = symx::gradient(g, dofs, /*symmetric=*/true, diff_cache);
+			symx::Sequence seq_p({ v });
+			symx::Sequence seq_pgh(symx::collect_scalars({ { v }, g.values(), h.values() }));
+			auto dump_ops = [&](const symx::Sequence& seq, const std::string& tag) {
+				std::vector<int32_t> ints; std::vector<double> consts;
+				for (const auto& o : seq.ops) { ints.insert(ints.end(), { (int32_t)o.type, o.dst, o.a, o.b, o.cond }); consts.push_back(o.constant); }
+				D.bin("pot" + std::to_string(p) + "_ops_" + tag, ints.data(), ints.size());
+				D.bin("pot" + std::to_string(p) + "_opsc_" + tag, consts.data(), consts.size());
+			};
+			dump_ops(seq_p, "p"); dump_ops(seq_pgh, "pgh");
+			D.bin("pot" + std::to_string(p) + "_block_slots", block_slots.data(), block_slots.size());
+			pots_json << ", \"user_ops\": true, \"n_in\": " << seq_pgh.get_n_inputs();
 		}
 		pots_json << ", \"n_out\": " << n_out << "}";
 	}

@@ -21,6 +21,19 @@ class Fetch(C.Structure):
     _fields_ = [("array", C.c_int32), ("conn_col", C.c_int32), ("first_slot", C.c_int32), ("stride", C.c_int32)]
 
 
+class Op(C.Structure):
+    """sb_op: one operation of a symx sequence (include/stark_b200.h, user potentials)."""
+    _fields_ = [("type", C.c_int32), ("dst", C.c_int32), ("a", C.c_int32), ("b", C.c_int32), ("cond", C.c_int32), ("pad", C.c_int32), ("constant", C.c_double)]
+
+
+def ops_array(ints, consts):
+    """(n x 5 int32 [type, dst, a, b, cond], n float64 constants) -> ctypes array of sb_op."""
+    arr = (Op * len(ints))()
+    for i, (row, c) in enumerate(zip(ints, consts)):
+        arr[i] = Op(int(row[0]), int(row[1]), int(row[2]), int(row[3]), int(row[4]), 0, float(c))
+    return arr
+
+
 class ContactMesh(C.Structure):
     _fields_ = [
         ("physical_system", C.c_int32), ("rigid_body", C.c_int32), ("n_vertices", C.c_int32), ("n_triangles", C.c_int32),
@@ -83,6 +96,7 @@ SYMBOLS = [
     "sb_newton_timer_begin", "sb_newton_default_settings", "sb_newton_solve", "sb_profile_potential",
     "sb_profile_stages", "sb_profile_report",
     "sb_dist_init", "sb_dist_connect", "sb_dist_connect_ptrs", "sb_dist_local_base", "sb_dist_stats", "sb_dist_plan",
+    "sb_potential_create_user", "sb_user_codegen", "sb_user_compile",
 ]
 
 
@@ -207,6 +221,16 @@ class Context:
         arr = (Fetch * len(fetch))(*[Fetch(*map(int, f)) for f in fetch])
         out = C.c_int()
         self._ck(self.lib.sb_potential_create(self.h, name.encode(), int(conn_stride), arr, len(fetch), C.byref(out)))
+        return out.value
+
+    def potential_user(self, name, conn_stride, fetch, n_in, block_slots, ops_p, ops_pgh):
+        """A potential without a built-in kernel: its symx operation sequences go through the Sequence -> CUDA -> NVRTC back-end."""
+        arr = (Fetch * len(fetch))(*[Fetch(*map(int, f)) for f in fetch])
+        slots = (C.c_int32 * len(block_slots))(*[int(x) for x in block_slots])
+        p, pgh = ops_array(*ops_p), ops_array(*ops_pgh)
+        out = C.c_int()
+        self._ck(self.lib.sb_potential_create_user(self.h, name.encode(), int(conn_stride), arr, len(fetch), int(n_in), len(block_slots), slots,
+                                                   p, len(p), pgh, len(pgh), C.byref(out)))
         return out.value
 
     def set_connectivity(self, pot, conn):

@@ -333,6 +333,7 @@ static EvalArgs make_args(sb_context* ctx, Potential& p)
     a.rows = ctx->rows.p + p.rows_off;
     a.E_elem = ctx->E_elem.p + p.E_off;
     a.g_elem = nullptr;
+    a.user = p.k->user;
     return a;
 }
 
@@ -952,6 +953,7 @@ void sb_destroy(sb_context* ctx)
     assembly_destroy(ctx);
     pcg_destroy(ctx);
     dist_destroy(ctx);
+    user_kernels_destroy(ctx);
     contact_destroy(ctx);
     projector_destroy(ctx);
     direct_destroy(ctx);
@@ -1213,6 +1215,14 @@ int sb_potential_create(sb_context* ctx, const char* kernel_name, int conn_strid
     if (!ctx || !kernel_name || !fetch || n_fetch <= 0 || conn_stride <= 0) return fail(ctx, SB_ERR_ARG, "sb_potential_create: bad argument");
     const KernelInfo* k = find_kernel(kernel_name);
     if (!k) return fail(ctx, SB_ERR_NO_KERNEL, std::string("sb_potential_create: no kernel named '") + kernel_name + "'");
+    return sb::potential_create_with_kernel(ctx, k, kernel_name, conn_stride, fetch, n_fetch, out_potential);
+}
+}  // extern "C"
+
+// the checks and bookkeeping shared by built-in kernels and generated ones (user.cu)
+int sb::potential_create_with_kernel(sb_context* ctx, const KernelInfo* k, const char* kernel_name, int conn_stride, const sb_fetch* fetch, int n_fetch, int* out_potential)
+{
+    if (!ctx || !k || !kernel_name || !fetch || n_fetch <= 0 || conn_stride <= 0) return fail(ctx, SB_ERR_ARG, "sb_potential_create: bad argument");
     Potential p;
     p.k = k;
     p.name = kernel_name;
@@ -1263,6 +1273,8 @@ int sb_potential_create(sb_context* ctx, const char* kernel_name, int conn_strid
     ctx->static_version++;
     return SB_OK;
 }
+
+extern "C" {
 
 static int check_pot(sb_context* ctx, int pot, const char* where)
 {
@@ -1349,6 +1361,7 @@ int sb_potential_get_element_output(sb_context* ctx, int potential, double* host
     a.rows = rows_tmp.p;
     a.E_elem = E_tmp.p;
     a.g_elem = g_elem.p;
+    a.user = p.k->user;
     p.k->launch_pgh(a, ctx->stream);
     ctx->launches++;
     std::vector<double> E(p.n_elem), g((size_t)p.n_elem * n), H((size_t)p.n_elem * n * n);
@@ -1465,6 +1478,7 @@ extern "C" int sb_profile_potential(sb_context* ctx, int potential, int mode, in
     a.rows = rows_tmp.p;
     a.E_elem = E_tmp.p;
     a.g_elem = nullptr;
+    a.user = p.k->user;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0, ctx->stream);

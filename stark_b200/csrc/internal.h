@@ -67,6 +67,7 @@ struct EvalArgs {
     int32_t* rows;     // global block rows, NB per element
     double* E_elem;    // per-element energy
     double* g_elem;    // optional per-element gradient (n per element) for parity dumps, may be null
+    const void* user;  // generated kernel of a user potential (user.cu), else null
 };
 
 struct KernelInfo {
@@ -76,6 +77,7 @@ struct KernelInfo {
     void (*launch_pgh)(const EvalArgs&, cudaStream_t);
     void (*launch_p)(const EvalArgs&, cudaStream_t);
     int p_kind;     // index into the multi-potential energy kernel's dispatch (-1: own kernel only)
+    const void* user = nullptr;   // user.cu: the generated kernel behind launch_pgh / launch_p
 };
 // one launch for the energy-only evaluation of many small potentials (eval.cu)
 struct MultiPItem { const FetchSlot* slots; const int32_t* conn; double* E_elem; int conn_stride, n_elem, kind, cta0; };
@@ -290,6 +292,7 @@ struct sb_context {
     sb::Projector* projector = nullptr;
     sb::Direct* direct = nullptr;
     sb::Dist* dist = nullptr;
+    std::vector<void*> user_kernels;   // user.cu: generated kernels owned by this context
 };
 
 namespace sb {
@@ -311,6 +314,8 @@ void contact_destroy(sb_context* ctx);
 void projector_destroy(sb_context* ctx);
 void direct_destroy(sb_context* ctx);
 void dist_destroy(sb_context* ctx);
+void user_kernels_destroy(sb_context* ctx);
+int potential_create_with_kernel(sb_context* ctx, const KernelInfo* k, const char* kernel_name, int conn_stride, const sb_fetch* fetch, int n_fetch, int* out_potential);
 int solve_llt_internal(sb_context* ctx, int* out_ok, double* out_du_dot_grad, double* out_du_inf);
 int assemble_internal(sb_context* ctx);
 // where the blocks of an element land in the assembled matrix: sources are numbered static-first; a static source maps

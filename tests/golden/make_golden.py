@@ -39,6 +39,9 @@ FIXTURES = {
     "zoo_slide_n4": ["--scene", "zoo", "--n", "4", "--steps", "1"],
     # slider, distance, distance-limit, angle-limit and damped-spring rigid-body constraints, all violated
     "joints": ["--scene", "joints", "--n", "1", "--steps", "6"],
+    # a USER potential (examples/main.cpp:666-690 EnergyMagneticAttraction, added with a lambda through add_potential): besides
+    # the usual dump, the symx operation sequences of [E] and [E | grad | hess] the reference's code generator prints
+    "magnet_n2": ["--scene", "magnet", "--n", "2", "--steps", "3", "--ops", "EnergyMagneticAttraction"],
 }
 
 
@@ -62,6 +65,11 @@ def pack(d):
         out[f"pot{p}_conn"] = rd(d, f"pot{p}_conn", np.int32).reshape(pot["n_elements"], pot["conn_stride"])
         out[f"pot{p}_sol"] = rd(d, f"pot{p}_sol", np.float64).reshape(pot["n_elements"], pot["n_out"])
         out[f"pot{p}_active"] = rd(d, f"pot{p}_active", np.uint8)
+        if pot.get("user_ops"):
+            for tag in ("p", "pgh"):
+                out[f"pot{p}_ops_{tag}"] = rd(d, f"pot{p}_ops_{tag}", np.int32).reshape(-1, 5)
+                out[f"pot{p}_opsc_{tag}"] = rd(d, f"pot{p}_opsc_{tag}", np.float64)
+            out[f"pot{p}_block_slots"] = rd(d, f"pot{p}_block_slots", np.int32)
     out["bcsr_rows"] = rd(d, "bcsr_rows", np.uint64).astype(np.int64)
     out["bcsr_cols"] = rd(d, "bcsr_cols", np.int32)
     out["bcsr_vals"] = rd(d, "bcsr_vals", np.float32)

@@ -41,9 +41,16 @@ def bind(ctx, g, kernel_names, rename=None, skip=(), override=None, split_fetch=
     handles = {}
     for i, p in g.potentials():
         name = rename.get(p["name"], p["name"])
-        if name not in kernel_names or p["name"] in skip:
+        if (name not in kernel_names and not p.get("user_ops")) or p["name"] in skip:
             continue
         fetch = [(arrays[m["array"]], m["conn_idx"], m["first_symbol"], m["stride"]) for m in p["maps"]]
+        if p.get("user_ops"):
+            # a user potential: the operation sequences the reference produced for it go through the NVRTC back-end
+            h = ctx.potential_user(name, p["conn_stride"], fetch, p["n_in"], g[f"pot{i}_block_slots"],
+                                   (g[f"pot{i}_ops_p"], g[f"pot{i}_opsc_p"]), (g[f"pot{i}_ops_pgh"], g[f"pot{i}_opsc_pgh"]))
+            ctx.set_connectivity(h, g[f"pot{i}_conn"][g[f"pot{i}_active"].astype(bool)])
+            handles[i] = h
+            continue
         if split_fetch and split_fetch[0] == p["name"]:
             for k, m in enumerate(p["maps"]):
                 if m["first_symbol"] == split_fetch[1]:

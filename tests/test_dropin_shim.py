@@ -48,6 +48,7 @@ def trace(exe, args, steps):
     ("tetbar", ["--scene", "tetbar", "--n", "2", "--nz", "10"], 6),            # volume elements + scripted prescribed positions
     ("tetdrop", ["--scene", "tetdrop", "--n", "4", "--vz", "0.25"], 14),        # IPC contact + friction: the reference's host-side contact callbacks run around every evaluation
     ("cloth", ["--scene", "cloth", "--n", "8"], 14),                           # triangle strain + bending over a scripted rigid box
+    ("magnet", ["--scene", "magnet", "--n", "3", "--vz", "0.25"], 12),         # a USER potential (add_potential with a lambda): kernel generated from its symx sequence by NVRTC
 ])
 def test_scene_trajectories_match_the_unmodified_reference(scene, args, steps):
     ref = trace(need(REF_DRIVER), args, steps)

@@ -5,7 +5,7 @@ import pytest
 
 from golden_util import Golden, bind
 
-FIXTURES = ["tetdrop_n3", "tetdrop_n5", "tetbar_n2", "cloth_n8", "cloth_shells_n8", "boxes", "attach_n6", "tetchain_n3", "zoo_n4", "zoo_slide_n4", "joints"]
+FIXTURES = ["tetdrop_n3", "tetdrop_n5", "tetbar_n2", "cloth_n8", "cloth_shells_n8", "boxes", "attach_n6", "tetchain_n3", "zoo_n4", "zoo_slide_n4", "joints", "magnet_n2"]
 RTOL = 1e-10  # north_star: 1e-10 relative on gradient / residual
 
 

@@ -11,7 +11,7 @@ from golden_util import Golden, bind
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
 import oracle  # noqa: E402
 
-FIXTURES = ["tetdrop_n3", "tetdrop_n5", "tetbar_n2", "cloth_n8", "cloth_shells_n8", "boxes", "attach_n6", "tetchain_n3", "zoo_n4", "joints"]
+FIXTURES = ["tetdrop_n3", "tetdrop_n5", "tetbar_n2", "cloth_n8", "cloth_shells_n8", "boxes", "attach_n6", "tetchain_n3", "zoo_n4", "joints", "magnet_n2"]
 
 
 def setup(fixture):
