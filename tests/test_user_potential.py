@@ -128,7 +128,7 @@ def test_reference_sequences_of_a_user_potential_compile(tmp_path, monkeypatch):
     buf = C.create_string_buffer(n.value + 1)
     assert lib.sb_user_codegen(p["name"].encode(), p["n_in"], 1, ops_p, len(ops_p), ops_pgh, len(ops_pgh), buf, n.value + 1, None) == 0
     src = buf.value.decode()
-    assert src.count("out[") >= 13 + 1 + 13 and "sqrt(" in src
+    assert src.count("] = ") >= 13 + 1 and "sqrt(" in src
     size, cached = C.c_longlong(), C.c_int()
     log = C.create_string_buffer(4096)
     rc = lib.sb_user_compile(buf.value, C.byref(size), C.byref(cached), log, 4096)
