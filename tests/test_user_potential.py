@@ -103,10 +103,10 @@ def test_generated_kernel_against_numpy(tmp_path, monkeypatch):
         assert np.array_equal(H[e], (k[e, 0] if on[e] else 0.0) * np.eye(3))
     E_only = ctx.eval("P")
     assert E_only == E
-    # the whole Newton path works on it: one step of the quadratic (where every spring is on) lands on the minimum
+    # the element Hessians assemble like any other potential's
     ctx.assemble()
-    out = ctx.solve_pcg(1e-12, 1e-14, 100, True)
-    assert out["ok"]
+    rows, cols, vals = ctx.bcsr()
+    assert len(rows) == n_nodes + 1 and len(cols) == len(set(conn[:, 1]))   # one diagonal block per touched node
     ctx.close()
 
 
