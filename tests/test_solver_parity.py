@@ -81,6 +81,12 @@ def test_pcg(fixture):
     assert np.abs(du - x).max() <= (2e-7 if fixture == "joints" else 1e-7) * np.abs(x).max()
     if out["iterations"] == g.meta["pcg_iterations"]:
         assert np.abs(du - g["pcg_du"]).max() <= 1e-4 * np.abs(g["pcg_du"]).max()
+    if not ok:
+        # the indefiniteness signal (solve_pcg.h:183-192: p^T A p <= 0 stops the solve, x is returned as it is) -- magnet_n2: the
+        # attraction's Hessian is indefinite and nothing is projected here; same verdict at the same iteration as the reference
+        assert fixture == "magnet_n2" and out["iterations"] == g.meta["pcg_iterations"]
+        ctx.close()
+        return
     # contract of the inexact solve: residual below the forcing tolerance, descent direction
     r = oracle.bcsr_spmv(rows, cols, vals, du) + grad
     assert np.linalg.norm(r) / np.linalg.norm(grad) < max(g.meta["pcg_abs_tol"], g.meta["pcg_rel_tol"]) * 1.0000001
