@@ -36,6 +36,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <chrono>
 
 namespace sb {
 
@@ -63,6 +64,7 @@ struct PcgResult {
     long long c_spmv, c_bar, c_red, c_vec, c_win;          // clock64 cycles of CTA 0 inside the loop (only when instrumented)
     unsigned long long barriers;                           // grid barriers this solve executed (the distributed counter never resets)
     unsigned long long ll_uses;                            // flagged all-reduces this solve executed (their flags never repeat either)
+    unsigned long long seq;                                // written LAST (after a system fence): the host polls it in pinned memory
 };
 
 // Distributed solve (one process per GPU, all ranks hold the same assembled matrix and right-hand side): the W x G CTAs of all
@@ -105,7 +107,8 @@ struct PcgArgs {
     double* du;
     double* part;                   // 3 x PCG_MAX_BLOCKS partial sums
     int* rp_scratch;                // [nbr + grid + 1] local row pointers of slices whose row pointers do not fit in shared memory
-    unsigned* barrier;              // zeroed before the launch
+    unsigned* barrier;              // monotonic arrival counter of the single-GPU barrier (zeroed once, never reset)
+    unsigned barrier_base;          // its value when this solve starts
     PcgResult* result;
     int nbr;
     double abs_tol, rel_tol;
@@ -117,6 +120,7 @@ struct PcgArgs {
     int tiled;                      // experimental: stream through TMA-filled tile buffers (MODE 3) instead of ordinary loads
     long long* dbg;                 // [5 x grid + 2] per-CTA cycle counters (SB_PCG_DUMP diagnostics, else null)
     DistArgs d;                     // world <= 1: single GPU
+    unsigned long long seq;         // number of this solve (PcgResult::seq)
 };
 
 struct Pcg {
@@ -126,7 +130,10 @@ struct Pcg {
     DevBuf<int> rp_scratch;
     unsigned* d_barrier = nullptr;
     PcgResult* d_result = nullptr;
-    PcgResult* h_result = nullptr;
+    PcgResult* h_result = nullptr;   // pinned, written by the kernel directly
+    unsigned long long seq = 0;
+    unsigned barrier_base = 0;       // arrivals of the solves so far (mod 2^32)
+    int barrier_grid = 0;
     int grid = 0;
     unsigned smem_bytes = 0;
     unsigned smem_launch_last = 0;
@@ -194,19 +201,20 @@ void pcg_destroy(sb_context* ctx)
     ctx->pcg = nullptr;
 }
 
-// ---- grid-wide barrier: monotonic counter, epoch-th barrier completes when it reaches epoch * gridDim.x ----
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch)
+// ---- grid-wide barrier: monotonic counter (never reset: `base` = its value when the solve started, a multiple of gridDim.x),
+//      the epoch-th barrier of a solve completes when it reaches base + epoch * gridDim.x (wrap-safe comparison) ----
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned base, unsigned& epoch)
 {
     __syncthreads();
     epoch++;
     if (threadIdx.x == 0) {
         __threadfence();
         atomicAdd(counter, 1u);
-        const unsigned target = epoch * gridDim.x;
+        const unsigned target = base + epoch * gridDim.x;
         unsigned v;
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-        } while (v < target);
+        } while ((int)(v - target) < 0);
     }
     __syncthreads();
 }
@@ -473,7 +481,7 @@ __device__ __forceinline__ void pcg_body(const PcgArgs& A, const PcgPlan& P)
     // barrier over the virtual grid; true = the distributed solve was aborted
     auto gbar = [&]() -> bool {
         if (DIST) return dist_barrier(A.d, depoch, P.s_abort);
-        grid_barrier(A.barrier, epoch);
+        grid_barrier(A.barrier, A.barrier_base, epoch);
         return false;
     };
     double* s = P.s;
@@ -925,7 +933,12 @@ __device__ __forceinline__ void pcg_body(const PcgArgs& A, const PcgPlan& P)
             R.t_start = t_start; R.t_loaded = t_loaded; R.t_loop = t_loop; R.t_end = global_ns();
             R.barriers = DIST ? depoch : (unsigned long long)epoch;
             R.ll_uses = ll_uses;
+            R.seq = 0;
+            // the record goes straight into pinned host memory; its sequence number follows behind a system fence, so the host,
+            // which polls that word, never sees a half-written record (no copy node, no stream synchronisation on the way back)
             *A.result = R;
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned long long*>(&A.result->seq) = A.seq;
         }
     }
 }
@@ -1157,7 +1170,8 @@ int solve_pcg_internal(sb_context* ctx, double abs_tol, double rel_tol, int max_
     PcgArgs A;
     A.rows = rows; A.cols = cols; A.vals = vals; A.grad = ctx->grad.p; A.dinv = P->dinv.p;
     A.x = P->x.p; A.r = P->r.p; A.p = P->p.p; A.s = P->s.p; A.w = P->w.p; A.u = P->u.p; A.u4 = P->u4.p; A.du = ctx->du.p;
-    A.part = P->part.p; A.rp_scratch = P->rp_scratch.p; A.barrier = P->d_barrier; A.result = P->d_result;
+    A.part = P->part.p; A.rp_scratch = P->rp_scratch.p; A.barrier = P->d_barrier; A.result = P->h_result;   // (pinned host memory, UVA)
+    A.seq = ++P->seq;
     // Shared memory of this launch.  When the slices fit (per-CTA estimate; the rows are cut by cost, see ROW_COST) the kernel
     // takes everything and the matrix stays resident.  Otherwise the matrix is read with ordinary loads every iteration, and a
     // full carve-out would leave no L1: every 4-byte load of a block would be its own L2 request (the SM's miss path takes ~2
@@ -1196,7 +1210,11 @@ int solve_pcg_internal(sb_context* ctx, double abs_tol, double rel_tol, int max_
     static const bool tiled_env = std::getenv("SB_PCG_TILED") != nullptr;
     A.tiled = tiled_env ? 1 : 0;
     A.nbr = nbr; A.abs_tol = abs_tol; A.rel_tol = rel_tol; A.max_iter = max_iter; A.stop_on_indef = stop_on_indef;
-    SB_CUDA(ctx, cudaMemsetAsync(P->d_barrier, 0, sizeof(unsigned), st));   // (single-GPU barrier; the distributed counters are never reset)
+    if (P->barrier_grid != P->grid) {   // first solve (or a changed grid): start the counter at zero
+        SB_CUDA(ctx, cudaMemsetAsync(P->d_barrier, 0, sizeof(unsigned), st));
+        P->barrier_base = 0; P->barrier_grid = P->grid;
+    }
+    A.barrier_base = P->barrier_base;
     // SB_PCG_DUMP=1: per-CTA cycle counters of every solve on stderr (load-balance diagnostics)
     static const bool dump = std::getenv("SB_PCG_DUMP") != nullptr;
     static long long* d_dbg = nullptr;
@@ -1231,10 +1249,28 @@ int solve_pcg_internal(sb_context* ctx, double abs_tol, double rel_tol, int max_
     void* args[] = {(void*)&A};
     SB_CUDA(ctx, cudaLaunchCooperativeKernel(DS ? (const void*)k_pcg_solve<true> : (const void*)k_pcg_solve<false>, dim3(P->grid), dim3(PCG_THREADS), args, smem_launch, st));
     ctx->launches += 1;
-    SB_CUDA(ctx, cudaMemcpyAsync(P->h_result, P->d_result, sizeof(PcgResult), cudaMemcpyDeviceToHost, st));
     if (DS) SB_CUDA(ctx, cudaMemcpyAsync(ctx->du.p, DS->base[DS->rank] + DS->off_du, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
-    SB_CUDA(ctx, hot_sync(ctx));
-    SB_CUDA(ctx, cudaGetLastError());
+    {
+        // wait for the kernel's record: poll its sequence number in pinned memory for a while (the usual solve takes 0.1-0.4 ms
+        // and the round trip of a copy + stream synchronisation would leave the GPU idle for ~10 us), then block on the stream
+        static const bool no_poll = std::getenv("SB_PCG_NO_POLL") != nullptr;
+        volatile unsigned long long* seq = &P->h_result->seq;
+        bool seen = false;
+        if (!no_poll && !DS && !dump && !ctx->profile) {
+            const auto t0 = std::chrono::steady_clock::now();
+            for (unsigned spins = 0;; spins++) {
+                if (*seq == A.seq) { seen = true; break; }
+                if ((spins & 255u) == 255u && std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(2)) break;
+            }
+            std::atomic_thread_fence(std::memory_order_acquire);
+        }
+        if (!seen) {
+            SB_CUDA(ctx, hot_sync(ctx));
+            SB_CUDA(ctx, cudaGetLastError());
+            if (*seq != A.seq) { P->barrier_grid = 0; return fail(ctx, SB_ERR_CUDA, "sb_solve_pcg: the solve kernel ended without writing its result"); }
+        }
+    }
+    if (!DS) P->barrier_base += (unsigned)P->h_result->barriers * (unsigned)P->grid;
     if (DS) {
         DS->epoch_base += P->h_result->barriers;
         DS->ll_base += (unsigned)P->h_result->ll_uses;
