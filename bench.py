@@ -133,13 +133,17 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="stark_b200")
-    ap.add_argument("--config", default="C2", choices=sorted(CONFIGS), help="BASELINE.json configuration (default C2: the one the metric is quoted on)")
+    ap.add_argument("--config", default=None, choices=sorted(CONFIGS),
+                    help="BASELINE.json configuration; default: C2 at --gpus 1 (the 1xB200 configuration the metric is quoted on), C5 at --gpus N > 1 (the "
+                         "1M-tet bar BASELINE.json names for the 1/2/4/8-GPU sweep)")
     ap.add_argument("--grid", type=int, default=None, help="override the grid size (diagnostic: NOT the benchmark configuration)")
     ap.add_argument("--llt", action="store_true", help="DirectLLT instead of the default BDPCG (both arms; reference: Eigen SimplicialLLT, ours: dense blocked Cholesky, <= 32k DoFs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--replicas", action="store_true", help="N > 1: N independent scenes (weak scaling) instead of one scene with the distributed solve")
     ap.add_argument("--stage-steps", type=int, default=4, help="extra (untimed) steps run with stage profiling on after the timed region; 0 = off")
     args = ap.parse_args()
+    if args.config is None:
+        args.config = "C2" if args.gpus <= 1 else "C5"
     cfg = CONFIGS[args.config]
     steps = args.steps if args.steps is not None else cfg["steps"]
     warmup = max(args.warmup if args.warmup is not None else cfg["warmup"], 3)
@@ -160,7 +164,7 @@ def main():
         v = r["newton_it_per_s"]
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": ref_steps, "warmup": warmup,
                 "ms_per_step": 1e3 * r["wall_s"] / max(1, r["steps"]), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic", "config": workload_config(1, args.config, cfg, args.grid), "newton_iterations": r["newton_iterations"],
+                "data": "synthetic", "config": workload_config(args.gpus, args.config, cfg, args.grid, args.replicas or args.llt), "newton_iterations": r["newton_iterations"],
                 "accepted_steps": r.get("accepted_steps"), "cg_iterations": r.get("cg_iterations"), "linear_solver": "DirectLLT" if args.llt else "BDPCG",
                 "cpu_baseline": {"value": v, "unit": UNIT, "cores": r["threads"], "kind": "reference",
                                  "sample": f"{ref_steps} time steps of the same scene after {warmup} warm-up steps (unmodified reference, all host threads)"},
@@ -230,6 +234,21 @@ def main():
         its_all, evals_all, cg_all = float(its), float(evals), float(cg)
     ctx_handle = C.c_void_p(sc.lib.sbh_scene_context(sc.h))
     lib = capi.load()
+    # ---- the single-GPU rate of the SAME scene in the SAME run (outside the timed region): sharing switched off on every rank,
+    #      each rank then solves its own replica locally; rank 0's rate is the strong-scaling baseline of this line ----
+    single = None
+    if distributed:
+        lib.sb_dist_set_enabled(ctx_handle, 0)
+        n_single = max(2, min(steps, 6))
+        sc.step()   # (first local solve: kernel attributes of the local instance)
+        its1, ms1 = 0, 0.0
+        for _ in range(n_single):
+            s1 = sc.step()
+            its1 += int(s1["newton_iterations"]); ms1 += s1["solve_gpu_ms"]
+        lib.sb_dist_set_enabled(ctx_handle, 1)
+        barrier()
+        single = {"value": its1 / (ms1 * 1e-3) if ms1 > 0 else None, "unit": UNIT, "steps": n_single,
+                  "note": "same scene, same process, the steps right after the timed region with the sharing of solves switched off (every rank solves locally); device time as `value`"}
     # ---- per-stage breakdown (diagnostic, outside the timed region): extra steps with a stream sync at every stage boundary ----
     # (with the distributed solve every rank takes these steps: a solve needs all of them)
     stages = None
@@ -329,6 +348,7 @@ def main():
     if distributed:
         st4 = (C.c_double * 4)()
         lib.sb_dist_stats(ctx_handle, None, None, st4)
+        line["single_gpu_same_config"] = single
         line["distributed"] = {"solves_shared_by_all_ranks": int(st4[1]), "solves_kept_local_by_policy": int(st4[3]), "cross_gpu_barriers": int(st4[0]),
                                "peer_buffer_bytes": int(st4[2]), "policy": os.environ.get("SB_DIST_POLICY", "auto"),
                                "note": "policy auto: a matrix resident in one GPU's shared memory is solved locally by every rank (identical results); larger systems are shared"}

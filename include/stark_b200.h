@@ -288,6 +288,8 @@ SB_API int sb_dist_connect(sb_context* ctx, const unsigned char* handles);
 /* ranks inside one process connect by pointer instead (bases[q] = sb_dist_local_base of rank q's context) */
 SB_API int sb_dist_connect_ptrs(sb_context* ctx, void* const* bases);
 SB_API void* sb_dist_local_base(sb_context* ctx);
+/* sharing off / on again (every rank between the same two solves): off = each rank solves its own replica locally */
+SB_API int sb_dist_set_enabled(sb_context* ctx, int enabled);
 /* out4 = { barriers completed, distributed solves, bytes of the peer buffer, solves the policy kept on the own GPU }.
  * Policy (environment SB_DIST_POLICY = auto | always, default auto): a system whose matrix is resident in ONE GPU's shared memory
  * is solved locally by every rank (its iteration is bound by grid-wide synchronisation, which costs more across NVLink than on

@@ -95,7 +95,7 @@ SYMBOLS = [
     "sb_contact_get_vertices", "sb_contact_set_vertices", "sb_contact_detect", "sb_contact_potential",
     "sb_newton_timer_begin", "sb_newton_default_settings", "sb_newton_solve", "sb_profile_potential",
     "sb_profile_stages", "sb_profile_report",
-    "sb_dist_init", "sb_dist_connect", "sb_dist_connect_ptrs", "sb_dist_local_base", "sb_dist_stats", "sb_dist_plan",
+    "sb_dist_init", "sb_dist_connect", "sb_dist_connect_ptrs", "sb_dist_local_base", "sb_dist_stats", "sb_dist_plan", "sb_dist_set_enabled",
     "sb_potential_create_user", "sb_user_codegen", "sb_user_compile",
 ]
 

@@ -146,6 +146,7 @@ struct Dist {
     unsigned char* base[DIST_MAX_WORLD] = {nullptr};   // base[rank] is the own buffer
     bool opened[DIST_MAX_WORLD] = {false};              // peer mappings opened through IPC (closed at destroy)
     bool connected = false;
+    bool enabled = true;                                // sb_dist_set_enabled: off = every rank solves locally (same-run single-GPU baseline)
     size_t bytes = 0, off_part = 0, off_ll = 0, off_u = 0, off_u4 = 0, off_du = 0;
     unsigned ll_base = 0;                               // flags of the flagged all-reduce used so far (identical on every rank)
     unsigned long long epoch_base = 0;                  // barriers completed so far (identical on every rank)
@@ -1177,7 +1178,7 @@ int solve_pcg_internal(sb_context* ctx, double abs_tol, double rel_tol, int max_
     // full carve-out would leave no L1: every 4-byte load of a block would be its own L2 request (the SM's miss path takes ~2
     // cycles per request).  Such solves run with a smaller carve-out, so that the nine loads of a 36-byte block share one or two
     // L1 line fills.  (The experimental tiled mode needs no L1 and takes everything again.)
-    Dist* DS = (ctx->dist && ctx->dist->connected && ctx->dist->world > 1) ? ctx->dist : nullptr;
+    Dist* DS = (ctx->dist && ctx->dist->connected && ctx->dist->enabled && ctx->dist->world > 1) ? ctx->dist : nullptr;
     // Policy (SB_DIST_POLICY=auto|always, default auto): a matrix that is resident in ONE GPU's shared memory gains nothing from
     // more GPUs -- its iteration is bound by grid-wide synchronisation, and a synchronisation across NVLink costs about four times
     // an on-chip one -- so such solves stay local (every rank solves its own replica, results identical); systems that do not fit
@@ -1381,6 +1382,16 @@ extern "C" int sb_dist_connect_ptrs(sb_context* ctx, void* const* bases)
     for (int q = 0; q < D->world; q++)
         if (q != D->rank) { if (!bases[q]) return SB_ERR_ARG; D->base[q] = static_cast<unsigned char*>(bases[q]); }
     D->connected = true;
+    return 0;
+}
+
+// switch the sharing of solves off / on again (all ranks must do it between the same two solves): with it off every rank solves
+// its own replica, which is how bench.py measures the single-GPU rate of the same scene in the same run
+extern "C" int sb_dist_set_enabled(sb_context* ctx, int enabled)
+{
+    if (!ctx) return SB_ERR_ARG;
+    if (!ctx->dist) return fail(ctx, SB_ERR_STATE, "sb_dist_set_enabled: call sb_dist_init first");
+    ctx->dist->enabled = enabled != 0;
     return 0;
 }
 
