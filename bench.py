@@ -196,10 +196,10 @@ def main():
     distributed = world > 1 and not args.replicas and not args.llt
     if distributed:
         # one scene, N ranks: every PCG solve from here on is shared by all ranks (peer buffers mapped through CUDA IPC).
-        # (the first step registers the scene's degrees of freedom; it is the first of the warm-up steps on every rank)
-        sc.step()
-        warmup_left = max(warmup - 1, 0)
-        sbdist.connect_solver(capi.load(), C.c_void_p(sc.lib.sbh_scene_context(sc.h)), int(sc.totals()["ndofs"]), device=torch.device("cuda", local_rank))
+        # Connected BEFORE the first step, so that the replicas never differ (rank 0's gradient / energy are everybody's from the
+        # first evaluation on); the scene registers its degrees of freedom at its first step: nodes + up to 1,024 rigid bodies
+        warmup_left = warmup
+        sbdist.connect_solver(capi.load(), C.c_void_p(sc.lib.sbh_scene_context(sc.h)), 3 * int(sc.totals()["nodes"]) + 6 * 1024, device=torch.device("cuda", local_rank))
 
     def barrier():
         sbdist.barrier(torch.device("cuda", local_rank))
@@ -234,21 +234,6 @@ def main():
         its_all, evals_all, cg_all = float(its), float(evals), float(cg)
     ctx_handle = C.c_void_p(sc.lib.sbh_scene_context(sc.h))
     lib = capi.load()
-    # ---- the single-GPU rate of the SAME scene in the SAME run (outside the timed region): sharing switched off on every rank,
-    #      each rank then solves its own replica locally; rank 0's rate is the strong-scaling baseline of this line ----
-    single = None
-    if distributed:
-        lib.sb_dist_set_enabled(ctx_handle, 0)
-        n_single = max(2, min(steps, 6))
-        sc.step()   # (first local solve: kernel attributes of the local instance)
-        its1, ms1 = 0, 0.0
-        for _ in range(n_single):
-            s1 = sc.step()
-            its1 += int(s1["newton_iterations"]); ms1 += s1["solve_gpu_ms"]
-        lib.sb_dist_set_enabled(ctx_handle, 1)
-        barrier()
-        single = {"value": its1 / (ms1 * 1e-3) if ms1 > 0 else None, "unit": UNIT, "steps": n_single,
-                  "note": "same scene, same process, the steps right after the timed region with the sharing of solves switched off (every rank solves locally); device time as `value`"}
     # ---- per-stage breakdown (diagnostic, outside the timed region): extra steps with a stream sync at every stage boundary ----
     # (with the distributed solve every rank takes these steps: a solve needs all of them)
     stages = None
@@ -268,6 +253,21 @@ def main():
             stages = {"error": repr(e)}
             if distributed:
                 raise
+    # ---- the single-GPU rate of the SAME scene in the SAME run (outside the timed region): sharing switched off on every rank,
+    #      each rank then solves its own replica locally; rank 0's rate is the strong-scaling baseline of this line.  Last thing
+    #      that steps the scene: the replicas are no longer kept identical once the sharing is off ----
+    single = None
+    if distributed:
+        lib.sb_dist_set_enabled(ctx_handle, 0)
+        n_single = max(2, min(steps, 6))
+        sc.step()   # (first local solve: kernel attributes of the local instance)
+        its1, ms1 = 0, 0.0
+        for _ in range(n_single):
+            s1 = sc.step()
+            its1 += int(s1["newton_iterations"]); ms1 += s1["solve_gpu_ms"]
+        barrier()   # (the sharing stays off: nothing after this point needs the other ranks)
+        single = {"value": its1 / (ms1 * 1e-3) if ms1 > 0 else None, "unit": UNIT, "steps": n_single,
+                  "note": "same scene, same process, the steps right after the timed region with the sharing of solves switched off (every rank solves locally); device time as `value`"}
     if rank != 0:
         if world > 1:
             dist.barrier()   # rank 0 finishes its single-GPU diagnostics before the group is torn down

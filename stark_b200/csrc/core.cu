@@ -775,6 +775,8 @@ int eval_internal(sb_context* ctx, int mode, double* out_E, double* out_grad_inf
         const bool located = sync_scalars && assembly_locate_dynamic(ctx);
         const double te4 = eval_dump ? now_ms() : 0.0;
         reduce_sum_and_absmax(ctx, ctx->E_elem.p, E_total, ctx->grad.p, ctx->ndofs, ctx->d_scalars);
+        // several GPUs on one scene: rank 0's gradient, energy and residual are everybody's (the replicas stay bitwise identical)
+        { const int rb = dist_bcast_from_root(ctx, ctx->grad.p, ctx->ndofs, ctx->d_scalars, 2); if (rb) return rb; }
         timeline_point(ctx->stream, "eval: reduced");
         if (eval_dump) fprintf(stderr, "EVALDUMP2 layout=%.1f dyn_launch=%.1f join=%.1f locate=%.1f reduce=%.1f us\n", 1e3 * (te1 - td1), 1e3 * (te2 - te1), 1e3 * (te3 - te2), 1e3 * (te4 - te3), 1e3 * (now_ms() - te4));
         ctx->have_pgh = true;
@@ -838,6 +840,7 @@ int eval_internal(sb_context* ctx, int mode, double* out_E, double* out_grad_inf
             }
         SB_CUDA(ctx, cudaGetLastError());
         reduce_sum(ctx, ctx->E_elem.p, E_total, ctx->d_scalars + 0);
+        { const int rb = dist_bcast_from_root(ctx, nullptr, 0, ctx->d_scalars, 1); if (rb) return rb; }
     }
     if (sync_scalars && mode != SB_EVAL_PGH) SB_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     const double td2 = eval_dump ? now_ms() : 0.0;
@@ -845,6 +848,7 @@ int eval_internal(sb_context* ctx, int mode, double* out_E, double* out_grad_inf
     if (!sync_scalars) ctx->issuer->wait();   // (the helper thread's job reads the potentials: it ends inside this call)
     if (sync_scalars) {
         SB_CUDA(ctx, hot_sync(ctx));
+        if (dist_aborted(ctx)) return fail(ctx, SB_ERR_CUDA, "sb_eval: a peer rank did not deliver its broadcast within SB_DIST_TIMEOUT_S (ranks out of step, or a peer failed)");
         ctx->issuer->wait();
         if (eval_dump) fprintf(stderr, "EVALDUMP mode=%d static=%.1f issue=%.1f prefetch=%.1f sync=%.1f us\n", mode, 1e3 * (td1 - td0), 1e3 * (td2 - td1), 1e3 * (td3 - td2), 1e3 * (now_ms() - td3));
         if (out_E) *out_E = ctx->h_scalars[0];

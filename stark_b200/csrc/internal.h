@@ -315,6 +315,8 @@ void projector_destroy(sb_context* ctx);
 void direct_destroy(sb_context* ctx);
 void dist_destroy(sb_context* ctx);
 void user_kernels_destroy(sb_context* ctx);
+bool dist_aborted(sb_context* ctx);
+int dist_bcast_from_root(sb_context* ctx, double* vec, int n, double* scal, int n_scal);   // pcg.cu: rank 0's values replace every rank's (no-op without peers)
 int potential_create_with_kernel(sb_context* ctx, const KernelInfo* k, const char* kernel_name, int conn_stride, const sb_fetch* fetch, int n_fetch, int* out_potential);
 int solve_llt_internal(sb_context* ctx, int* out_ok, double* out_du_dot_grad, double* out_du_inf);
 int assemble_internal(sb_context* ctx);

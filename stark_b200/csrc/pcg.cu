@@ -147,12 +147,13 @@ struct Dist {
     bool opened[DIST_MAX_WORLD] = {false};              // peer mappings opened through IPC (closed at destroy)
     bool connected = false;
     bool enabled = true;                                // sb_dist_set_enabled: off = every rank solves locally (same-run single-GPU baseline)
-    size_t bytes = 0, off_part = 0, off_ll = 0, off_u = 0, off_u4 = 0, off_du = 0;
+    size_t bytes = 0, off_part = 0, off_ll = 0, off_u = 0, off_u4 = 0, off_du = 0, off_bcast = 0;
+    unsigned long long n_bcasts = 0;                    // broadcasts from rank 0 so far (identical on every rank)
     unsigned ll_base = 0;                               // flags of the flagged all-reduce used so far (identical on every rank)
     unsigned long long epoch_base = 0;                  // barriers completed so far (identical on every rank)
     unsigned long long n_solves = 0, n_local_solves = 0;   // distributed solves / solves the policy kept on the own GPU
     DevBuf<unsigned char> needmask;
-    int* d_abort = nullptr;
+    int* d_abort = nullptr;                             // pinned host memory (the kernels write it, the host reads it after its synchronisations)
     int grid_override = 0;                              // test hook (SB_PCG_GRID): smaller grids so that two solves share one GPU
 };
 void dist_destroy(sb_context* ctx)
@@ -162,7 +163,7 @@ void dist_destroy(sb_context* ctx)
     for (int q = 0; q < D->world; q++)
         if (q != D->rank && D->opened[q] && D->base[q]) cudaIpcCloseMemHandle(D->base[q]);
     if (D->base[D->rank]) cudaFree(D->base[D->rank]);
-    if (D->d_abort) cudaFree(D->d_abort);
+    if (D->d_abort) cudaFreeHost(D->d_abort);
     D->needmask.release();
     delete D;
     ctx->dist = nullptr;
@@ -1126,6 +1127,106 @@ __global__ void k_dist_needmask(const unsigned long long* __restrict__ rows, con
     }
 }
 
+// ---- rank 0 is authoritative: broadcast of a vector + a few scalars from rank 0 to every rank, in stream order ----
+// Every rank drives the same scene, but FP64 atomics (gradient scatter, contact tables filled in arrival order) make the last bits
+// of the gradient and of the energy differ from rank to rank; left alone, the replicas drift apart (measurably within tens of
+// time steps on the cloth scenes) and sooner or later take different decisions -- a different number of shared solves is a
+// dead-lock.  So after every evaluation all ranks adopt rank 0's gradient, energy and residual (and, after a solve the policy kept
+// local, rank 0's du): the replicas stay bitwise identical.  Two buffers alternate; rank 0 waits for the acknowledgements of
+// broadcast k - 2 before it overwrites that buffer.
+constexpr int BCAST_CTAS = 32;
+struct BcastArgs {
+    int world, n, n_scal;
+    unsigned long long k;                      // number of this broadcast (1, 2, ...)
+    unsigned long long timeout_ns;
+    double* buf[DIST_MAX_WORLD];               // this broadcast's buffer on every rank: [vector | scalars]
+    unsigned long long* arrive[DIST_MAX_WORLD];
+    unsigned long long* ack_root;              // on rank 0
+    unsigned long long* done_local;
+    int* abort_flag;
+};
+__device__ __forceinline__ bool spin_until(const unsigned long long* p, unsigned long long target, unsigned long long timeout_ns, int* abort_flag)
+{
+    unsigned long long v, t0 = 0;
+    unsigned spins = 0;
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+        if (v >= target) return true;
+        if ((++spins & 1023u) == 0u) {
+            const unsigned long long now = global_ns();
+            if (!t0) t0 = now;
+            if (now - t0 > timeout_ns || *(volatile int*)abort_flag) { *(volatile int*)abort_flag = 1; return false; }
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_bcast_root(const double* __restrict__ vec, const double* __restrict__ scal, const BcastArgs a)
+{
+    __shared__ int ok;
+    if (threadIdx.x == 0) ok = spin_until(a.ack_root, a.k >= 2 ? (a.k - 2) * (unsigned long long)(a.world - 1) : 0ull, a.timeout_ns, a.abort_flag) ? 1 : 0;
+    __syncthreads();
+    if (ok) {
+        for (int q = 1; q < a.world; q++) {
+            for (int i = blockIdx.x * 256 + threadIdx.x; i < a.n; i += gridDim.x * 256) __stcg(a.buf[q] + i, vec[i]);
+            if (blockIdx.x == 0 && threadIdx.x < a.n_scal) __stcg(a.buf[q] + a.n + threadIdx.x, scal[threadIdx.x]);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && ok) {
+        __threadfence_system();
+        for (int q = 1; q < a.world; q++) asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" :: "l"(a.arrive[q]), "l"(1ull) : "memory");
+    }
+}
+__global__ void __launch_bounds__(256) k_bcast_peer(double* __restrict__ vec, double* __restrict__ scal, int rank, const BcastArgs a)
+{
+    __shared__ int ok;
+    if (threadIdx.x == 0) ok = spin_until(a.arrive[rank], a.k * (unsigned long long)gridDim.x, a.timeout_ns, a.abort_flag) ? 1 : 0;
+    __syncthreads();
+    if (ok) {
+        const double* src = a.buf[rank];
+        for (int i = blockIdx.x * 256 + threadIdx.x; i < a.n; i += gridDim.x * 256) vec[i] = __ldcg(src + i);
+        if (blockIdx.x == 0 && threadIdx.x < a.n_scal) scal[threadIdx.x] = __ldcg(src + a.n + threadIdx.x);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && ok) {
+        __threadfence();
+        const unsigned long long done = atomicAdd(a.done_local, 1ull) + 1ull;
+        if (done == a.k * (unsigned long long)gridDim.x) {   // the last CTA of this rank: the buffer may be reused
+            __threadfence_system();
+            asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" :: "l"(a.ack_root), "l"(1ull) : "memory");
+        }
+    }
+}
+
+// a peer did not show up in time (set by any kernel that waits on another GPU): everything received since is void
+bool dist_aborted(sb_context* ctx)
+{
+    return ctx->dist && ctx->dist->d_abort && *(volatile int*)ctx->dist->d_abort != 0;
+}
+
+// vec[0 .. n) and scal[0 .. n_scal) of rank 0 replace those of every other rank (queued on the context stream; n may be 0)
+int dist_bcast_from_root(sb_context* ctx, double* vec, int n, double* scal, int n_scal)
+{
+    Dist* D = ctx->dist;
+    if (!D || !D->connected || !D->enabled || D->world <= 1) return 0;
+    if ((size_t)n > D->max_dofs || n_scal > 8) return fail(ctx, SB_ERR_STATE, "distributed broadcast: vector longer than the peer buffer");
+    BcastArgs a;
+    a.world = D->world; a.n = n; a.n_scal = n_scal; a.k = ++D->n_bcasts;
+    static const double timeout_s = std::getenv("SB_DIST_TIMEOUT_S") ? std::atof(std::getenv("SB_DIST_TIMEOUT_S")) : 30.0;
+    a.timeout_ns = (unsigned long long)(timeout_s * 1e9);
+    const size_t half = sizeof(double) * (D->max_dofs + 8);
+    for (int q = 0; q < D->world; q++) {
+        a.buf[q] = reinterpret_cast<double*>(D->base[q] + D->off_bcast + (a.k & 1ull) * half);
+        a.arrive[q] = reinterpret_cast<unsigned long long*>(D->base[q] + 64);
+    }
+    a.ack_root = reinterpret_cast<unsigned long long*>(D->base[0] + 128);
+    a.done_local = reinterpret_cast<unsigned long long*>(D->base[D->rank] + 192);
+    a.abort_flag = D->d_abort;
+    if (D->rank == 0) k_bcast_root<<<BCAST_CTAS, 256, 0, ctx->stream>>>(vec, scal, a);
+    else k_bcast_peer<<<BCAST_CTAS, 256, 0, ctx->stream>>>(vec, scal, D->rank, a);
+    ctx->launches++;
+    return 0;
+}
+
 int solve_pcg_internal(sb_context* ctx, double abs_tol, double rel_tol, int max_iter, int stop_on_indef,
                        int* out_iterations, int* out_ok, double* out_du_dot_grad, double* out_du_inf)
 {
@@ -1179,6 +1280,7 @@ int solve_pcg_internal(sb_context* ctx, double abs_tol, double rel_tol, int max_
     // cycles per request).  Such solves run with a smaller carve-out, so that the nine loads of a 36-byte block share one or two
     // L1 line fills.  (The experimental tiled mode needs no L1 and takes everything again.)
     Dist* DS = (ctx->dist && ctx->dist->connected && ctx->dist->enabled && ctx->dist->world > 1) ? ctx->dist : nullptr;
+    bool kept_local = false;   // connected, but this solve stays on the own GPU: every rank then adopts rank 0's du
     // Policy (SB_DIST_POLICY=auto|always, default auto): a matrix that is resident in ONE GPU's shared memory gains nothing from
     // more GPUs -- its iteration is bound by grid-wide synchronisation, and a synchronisation across NVLink costs about four times
     // an on-chip one -- so such solves stay local (every rank solves its own replica, results identical); systems that do not fit
@@ -1186,7 +1288,7 @@ int solve_pcg_internal(sb_context* ctx, double abs_tol, double rel_tol, int max_
     if (DS) {
         static const bool always = std::getenv("SB_DIST_POLICY") && std::string(std::getenv("SB_DIST_POLICY")) == "always";
         const double resident1 = 1.08 * (40.0 * (double)nnzb + 160.0 * (double)nbr) / P->grid;
-        if (!always && resident1 <= (double)P->smem_bytes) { DS->n_local_solves++; DS = nullptr; }
+        if (!always && resident1 <= (double)P->smem_bytes) { DS->n_local_solves++; DS = nullptr; kept_local = true; }
     }
     if (DS && (size_t)n > DS->max_dofs) return fail(ctx, SB_ERR_STATE, "sb_solve_pcg: the system has more DoFs than sb_dist_init reserved peer memory for");
     const int vgrid = P->grid * (DS ? DS->world : 1);   // CTAs of all ranks
@@ -1246,11 +1348,20 @@ int solve_pcg_internal(sb_context* ctx, double abs_tol, double rel_tol, int max_
         k_dist_needmask<<<296, 256, 0, st>>>(rows, cols, nbr, (unsigned long long)nnzb, DS->world, DS->rank, P->grid, DS->needmask.p);
         d.needmask = DS->needmask.p; d.abort_flag = DS->d_abort;
         ctx->launches += 1;
+        // SB_DIST_TRACE=1: one line per shared solve and rank (the ranks' traces must be identical: the first difference names the
+        // host decision that went out of step)
+        static const bool trace = std::getenv("SB_DIST_TRACE") != nullptr;
+        if (trace) {
+            unsigned long long tb; memcpy(&tb, &abs_tol, 8);
+            fprintf(stderr, "DISTTRACE rank %d solve %llu nbr %d nnzb %zu abs_tol %016llx max_iter %d epoch %llu ll %u state %llu eval %llu\n", DS->rank, DS->n_solves, nbr, nnzb, tb,
+                    max_iter, DS->epoch_base, DS->ll_base, (unsigned long long)ctx->state_version, (unsigned long long)ctx->eval_id);
+        }
     }
     void* args[] = {(void*)&A};
     SB_CUDA(ctx, cudaLaunchCooperativeKernel(DS ? (const void*)k_pcg_solve<true> : (const void*)k_pcg_solve<false>, dim3(P->grid), dim3(PCG_THREADS), args, smem_launch, st));
     ctx->launches += 1;
     if (DS) SB_CUDA(ctx, cudaMemcpyAsync(ctx->du.p, DS->base[DS->rank] + DS->off_du, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+    if (kept_local) { const int rb = dist_bcast_from_root(ctx, ctx->du.p, n, nullptr, 0); if (rb) return rb; }
     {
         // wait for the kernel's record: poll its sequence number in pinned memory for a while (the usual solve takes 0.1-0.4 ms
         // and the round trip of a copy + stream synchronisation would leave the GPU idle for ~10 us), then block on the stream
@@ -1333,13 +1444,14 @@ extern "C" int sb_dist_init(sb_context* ctx, int rank, int world, long long max_
     D->off_u = align256(D->off_ll + (size_t)PCG_MAX_BLOCKS * sizeof(uint4));
     D->off_u4 = align256(D->off_u + sizeof(double) * ((size_t)max_dofs + 4));
     D->off_du = align256(D->off_u4 + sizeof(double) * 4 * (nbr + 1));
-    D->bytes = align256(D->off_du + sizeof(double) * ((size_t)max_dofs + 4));
+    D->off_bcast = align256(D->off_du + sizeof(double) * ((size_t)max_dofs + 4));
+    D->bytes = align256(D->off_bcast + 2 * sizeof(double) * ((size_t)max_dofs + 8));
     unsigned char* p = nullptr;
-    if (cudaMalloc(&p, D->bytes) != cudaSuccess || cudaMemset(p, 0, D->bytes) != cudaSuccess || cudaMalloc(&D->d_abort, sizeof(int)) != cudaSuccess ||
-        cudaMemset(D->d_abort, 0, sizeof(int)) != cudaSuccess) {
+    if (cudaMalloc(&p, D->bytes) != cudaSuccess || cudaMemset(p, 0, D->bytes) != cudaSuccess || cudaMallocHost(&D->d_abort, sizeof(int)) != cudaSuccess) {
         delete D;
         return fail(ctx, SB_ERR_CUDA, "sb_dist_init: allocation of the peer buffer failed");
     }
+    *D->d_abort = 0;
     D->base[rank] = p;
     if (out_handle64) {
         cudaIpcMemHandle_t h;
