@@ -279,8 +279,11 @@ SB_API int sb_newton_solve(sb_context* ctx, const sb_newton_settings* settings, 
  * sb_dist_init + sb_dist_connect every sb_solve_pcg / BDPCG solve of sb_newton_solve is ONE solve shared by all ranks: the
  * persistent kernels of the ranks form one virtual grid, each keeps 1 / world of the matrix in shared memory, and the halo of
  * u, the dot-product partials, the barrier and du cross GPUs through NVLink loads / stores issued inside the kernel on
- * buffers mapped with CUDA IPC.  All ranks must issue the same sequence of solves; a rank that waits longer than
- * SB_DIST_TIMEOUT_S (environment, default 30 s) at a barrier fails the solve with SB_ERR_CUDA instead of hanging.
+ * buffers mapped with CUDA IPC.  All ranks must issue the same sequence of solves: to that end every sb_eval of a connected
+ * context ends with rank 0's gradient, energy and residual replacing every rank's (FP64 atomics make their last bits differ
+ * between replicas, and replicas that drift apart end up taking different decisions), so connect before the first evaluation.
+ * A rank that waits longer than SB_DIST_TIMEOUT_S (environment, default 30 s) for its peers fails with SB_ERR_CUDA instead of
+ * hanging.
  * sb_dist_init allocates the rank's peer buffer (sized for max_dofs) and returns its cudaIpcMemHandle_t (64 bytes);
  * sb_dist_connect takes the world x 64 bytes of all ranks' handles (gathered by the caller, e.g. torch.distributed). */
 SB_API int sb_dist_init(sb_context* ctx, int rank, int world, long long max_dofs, unsigned char* out_handle64);
