@@ -1134,7 +1134,7 @@ __global__ void k_dist_needmask(const unsigned long long* __restrict__ rows, con
 // dead-lock.  So after every evaluation all ranks adopt rank 0's gradient, energy and residual (and, after a solve the policy kept
 // local, rank 0's du): the replicas stay bitwise identical.  Two buffers alternate; rank 0 waits for the acknowledgements of
 // broadcast k - 2 before it overwrites that buffer.
-constexpr int BCAST_CTAS = 32;
+constexpr int BCAST_CTAS = 128;   // (enough CTAs to keep rank 0's NVLink egress busy: it stores the vector W - 1 times)
 struct BcastArgs {
     int world, n, n_scal;
     unsigned long long k;                      // number of this broadcast (1, 2, ...)
