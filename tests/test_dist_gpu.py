@@ -30,6 +30,7 @@ def test_distributed_pcg_matches_single_gpu(world, fixture):
     summed over a different partition), bit-identical on every rank and from solve to solve."""
     r = _run(world, fixture)
     assert r["identical_across_ranks"] and r["identical_across_solves"] and r["rel_err"] < 1e-6
+    assert r["rank0_gradient_everywhere"]   # an evaluation on connected contexts ends with rank 0's gradient and energy on every rank
 
 
 @pytest.mark.gpu

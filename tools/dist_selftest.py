@@ -108,14 +108,35 @@ for k in range(args.solves):
     if errors or any(t.is_alive() for t in th):
         print(json.dumps({"mode": "threads", "ok": False, "errors": errors, "hung": any(t.is_alive() for t in th)}))
         os._exit(1)
+# an evaluation on connected contexts ends with rank 0's gradient / energy on every rank (dist_bcast_from_root): perturb the
+# ranks' states differently in the last bits first, so that their own gradients differ
+grads, energies = [None] * W, [None] * W
+for r, c in enumerate(ctxs):
+    u = c.dofs_get()
+    c.dofs_set(u * (1.0 + r * 2.0 ** -50))
+def eval_work(r):
+    try:
+        energies[r], _ = ctxs[r].eval("PGH")
+        grads[r] = ctxs[r].grad()
+    except Exception as e:   # noqa: BLE001
+        errors.append(repr(e))
+th = [threading.Thread(target=eval_work, args=(r,)) for r in range(W)]
+for t in th:
+    t.start()
+for t in th:
+    t.join(120)
+if errors or any(t.is_alive() for t in th):
+    print(json.dumps({"mode": "threads", "ok": False, "errors": errors, "hung": any(t.is_alive() for t in th)}))
+    os._exit(1)
+bcast_ok = all(np.array_equal(grads[0], grads[r]) and energies[0] == energies[r] for r in range(W))
 identical = all(np.array_equal(dus[k][0], dus[k][r]) for k in range(args.solves) for r in range(W))
 repeat = all(np.array_equal(dus[0][0], dus[k][0]) for k in range(args.solves))
 err = float(np.abs(dus[-1][0] - du_ref).max() / np.abs(du_ref).max())
 its = [results[k][0]["iterations"] for k in range(args.solves)]
-ok = bool(identical and repeat and err < 1e-6 and all(results[k][r]["ok"] for k in range(args.solves) for r in range(W))
+ok = bool(identical and repeat and bcast_ok and err < 1e-6 and all(results[k][r]["ok"] for k in range(args.solves) for r in range(W))
           and all(abs(i - ref["iterations"]) <= 2 for i in its))
 st = (C.c_double * 4)()
 lib.sb_dist_stats(ctxs[0].h, None, None, st)
 print(json.dumps({"mode": "threads", "world": W, "fixture": args.fixture, "ref_iterations": ref["iterations"], "dist_iterations": its, "rel_err": err,
-                  "identical_across_ranks": identical, "identical_across_solves": repeat, "barriers": st[0], "ok": ok}))
+                  "identical_across_ranks": identical, "identical_across_solves": repeat, "rank0_gradient_everywhere": bcast_ok, "barriers": st[0], "ok": ok}))
 sys.exit(0 if ok else 1)
