@@ -43,3 +43,17 @@ def test_reference_arm_is_silent_on_other_ranks():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "2", "--warmup", "3", "--grid", "3"],
                          capture_output=True, text=True, timeout=120, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+@pytest.mark.timeout(600)
+def test_default_configuration_follows_the_gpu_count():
+    """`--gpus 1` runs C2 (the 1xB200 configuration the metric is quoted on), `--gpus N > 1` the 1M-tet bar BASELINE.json names for
+    the 1/2/4/8-GPU sweep (one scene shared by the ranks); both arms pick the same one."""
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_driver")):
+        pytest.skip("oracle/_ref/ref_driver not built (no /root/reference here)")
+    env = dict(os.environ, RANK="0", WORLD_SIZE="2", LOCAL_RANK="0")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "2", "--warmup", "3", "--grid", "2"],
+                         capture_output=True, text=True, timeout=580, env=env)
+    assert out.returncode == 0, out.stderr[-1500:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["config"]["name"] == "C5" and line["n_gpus"] == 2 and "slab decomposition" in line["config"]["parallelism"]
