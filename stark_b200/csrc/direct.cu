@@ -41,7 +41,7 @@ struct Direct {
     DevBuf<int32_t> F, F_new;          // first tile of every tile row (cached envelope / envelope of the current matrix)
     DevBuf<unsigned long long> off;    // tile offset of every tile row's run
     DevBuf<int32_t> act_ptr, act;      // per tile column k: the tile rows I > k with F(I) <= k (ascending)
-    std::vector<int32_t> h_F, h_act_ptr;
+    std::vector<int32_t> h_F, h_act_ptr, h_act;
     std::vector<int32_t> h_perm;
     size_t n_tiles = 0, n_tiles_at_order = 0;
     // numeric
@@ -370,6 +370,113 @@ __global__ void __launch_bounds__(128) k_tile_product(double* __restrict__ T, co
     }
 }
 
+// The same two products on the FP64 TENSOR path: mma.sync m8n8k4 (DMMA).  One CTA of 128 threads per output tile, each warp a
+// 32 x 32 quadrant = 4 x 4 fragments of 8 x 8; both operands stay row-major in shared memory (pitch 68 doubles: the fragment
+// loads of a warp -- 8 rows x 4 consecutive doubles -- then need the minimum two wavefronts), because C = A B^T takes its A
+// fragment as A[r0 + lane / 4][q0 + lane % 4] and its B fragment (col-major 4 x 8) as B[c0 + lane / 4][q0 + lane % 4]: the same
+// access.  Per 4-wide k step a warp issues 8 fragment loads and 16 DMMA (256 FMA each) instead of 64 x 4 DFMA per lane: 8 x fewer
+// issue slots for the same flops, which is what the latency-bound DFMA version (FP64 pipe 22 % active) was short of.
+constexpr int MP = NB + 4;
+__device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+// MODE 0 (panel):    T(I, k) <- T(I, k) W_k^T                                   I = act[blockIdx.x]
+// MODE 1 (narrow):   T(I, J) -= T(I, k) T(J, k)^T                               I = act[blockIdx.x] >= J = act[blockIdx.y]  (J inside the column block)
+// MODE 2 (trailing): T(I, J) -= sum_{kk = k .. k_end - 1} T(I, kk) T(J, kk)^T    pairs J <= I of act, one pass over the output tile for the
+//                    whole column block (a tile row whose envelope starts after kk has no tile there and contributes nothing)
+template<int MODE>
+__global__ void __launch_bounds__(128) k_tile_product_mma(double* __restrict__ T, const unsigned long long* __restrict__ off, const int32_t* __restrict__ F,
+                                                          const double* __restrict__ Winv, const int32_t* __restrict__ act, int m, int k, int k_end,
+                                                          const int* __restrict__ flags)
+{
+    if (flags[0]) return;
+    extern __shared__ __align__(16) double sm[];
+    double* Pa = sm;                 // [NB][MP] row-major
+    double* Pb = sm + NB * MP;
+    int I, J;
+    if (MODE == 0) { I = act[blockIdx.x]; J = k; }
+    else if (MODE == 1) {
+        if (blockIdx.x < blockIdx.y) return;
+        I = act[blockIdx.x]; J = act[blockIdx.y];
+    } else {
+        const int idx = blockIdx.x;
+        int a = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
+        while ((a + 1) * (a + 2) / 2 <= idx) a++;
+        while (a * (a + 1) / 2 > idx) a--;
+        const int b = idx - a * (a + 1) / 2;
+        if (a >= m) return;
+        I = act[a]; J = act[b];
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wr = (warp >> 1) * 32, wc = (warp & 1) * 32;     // this warp's quadrant
+    const int fr = lane >> 2, fq = lane & 3;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+    const int FI = F[I], FJ = (MODE == 0) ? 0 : F[J];
+    bool first = true;
+    for (int kk = k; kk < ((MODE == 2) ? k_end : k + 1); kk++) {
+        if (MODE == 2 && (FI > kk || FJ > kk)) continue;       // (uniform in the CTA)
+        const double* pa = T + (off[I] + (unsigned long long)(kk - FI)) * TILE;
+        const double* pb = (MODE == 0) ? Winv + (size_t)kk * TILE : T + (off[J] + (unsigned long long)(kk - FJ)) * TILE;
+        if (!first) __syncthreads();                           // the previous column's fragments have been read
+        first = false;
+        {
+            // 2 x 8 x 16-byte loads in flight per thread, then the stores (rows keep their order: no transposition)
+            const double2* ga = reinterpret_cast<const double2*>(pa);
+            const double2* gb = reinterpret_cast<const double2*>(pb);
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                double2 va[8], vb[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) { const int t = threadIdx.x + 128 * (8 * h + u); va[u] = ga[t]; vb[u] = gb[t]; }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int t = threadIdx.x + 128 * (8 * h + u);      // pair index: row t / 32, columns 2 (t % 32), +1
+                    const int r = t / (NB / 2), q = 2 * (t % (NB / 2));
+                    *reinterpret_cast<double2*>(Pa + r * MP + q) = va[u];
+                    *reinterpret_cast<double2*>(Pb + r * MP + q) = vb[u];
+                }
+            }
+        }
+        __syncthreads();
+        const double* arow = Pa + (wr + fr) * MP + fq;
+        const double* brow = Pb + (wc + fr) * MP + fq;
+#pragma unroll 4
+        for (int q0 = 0; q0 < NB; q0 += 4) {
+            double af[4], bf[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) { af[i] = arow[i * 8 * MP + q0]; bf[i] = brow[i * 8 * MP + q0]; }
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+    }
+    if (first) return;                                         // no column of the block reaches this pair
+    // fragment (i, j): rows wr + 8 i + lane / 4, columns wc + 8 j + 2 (lane % 4), + 1
+    double* out = T + (off[I] + (unsigned long long)(J - FI)) * TILE;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int r = wr + 8 * i + fr, c = wc + 8 * j + 2 * fq;
+            double* o = out + r * NB + c;
+            if (MODE == 0) *reinterpret_cast<double2*>(o) = make_double2(acc[i][j][0], acc[i][j][1]);
+            else if (I != J) {
+                double2 v = *reinterpret_cast<double2*>(o);
+                v.x -= acc[i][j][0]; v.y -= acc[i][j][1];
+                *reinterpret_cast<double2*>(o) = v;
+            } else {
+                if (c <= r) o[0] -= acc[i][j][0];
+                if (c + 1 <= r) o[1] -= acc[i][j][1];
+            }
+        }
+}
+
 // ---- triangular solves with one right-hand side, one launch per tile column ----
 // forward  (k ascending):  z_k = W_k y_k ;  y_I -= T(I, k) z_k for the active rows I of column k
 // backward (k descending): x_k = W_k^T z_k ; z_J -= T(k, J)^T x_k for J = F(k) .. k - 1
@@ -511,6 +618,7 @@ static int analyse(sb_context* ctx, Direct& D, int nt)
         for (int I = 0; I < nt; I++)   // ascending I: every column's list comes out sorted
             for (int k = D.h_F[I]; k < I; k++) act[(size_t)fill[k]++] = I;
     }
+    D.h_act = act;
     D.off.ensure(nt + 1); D.F.ensure(nt); D.act_ptr.ensure(nt + 1); D.act.ensure(std::max<size_t>(act.size(), 1));
     SB_CUDA(ctx, cudaMemcpyAsync(D.off.p, off.data(), sizeof(unsigned long long) * (nt + 1), cudaMemcpyHostToDevice, st));
     SB_CUDA(ctx, cudaMemcpyAsync(D.F.p, D.h_F.data(), sizeof(int32_t) * nt, cudaMemcpyHostToDevice, st));
@@ -551,6 +659,9 @@ int solve_llt_internal(sb_context* ctx, int* out_ok, double* out_du_dot_grad, do
         cudaMallocHost(&ctx->direct->h_out, 2 * sizeof(double));
         cudaFuncSetAttribute(k_tile_product<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * NB * SP * sizeof(double)));
         cudaFuncSetAttribute(k_tile_product<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * NB * SP * sizeof(double)));
+        cudaFuncSetAttribute(k_tile_product_mma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * NB * MP * sizeof(double)));
+        cudaFuncSetAttribute(k_tile_product_mma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * NB * MP * sizeof(double)));
+        cudaFuncSetAttribute(k_tile_product_mma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * NB * MP * sizeof(double)));
     }
     Direct& D = *ctx->direct;
     cudaStream_t st = ctx->stream;
@@ -601,7 +712,38 @@ int solve_llt_internal(sb_context* ctx, int* out_ok, double* out_du_dot_grad, do
     k_fill_tiles<<<nbr, 288, 0, st>>>(rows, cols, vals, D.perm.p, D.T.p, D.off.p, D.F.p, nbr);
     if (np > n) k_pad_diagonal<<<(np - n + 63) / 64, 64, 0, st>>>(D.T.p, D.off.p, D.F.p, n, np);
     ctx->launches += 2;
-    const size_t syrk_smem = 2 * NB * SP * sizeof(double);
+    const size_t syrk_smem = 2 * NB * SP * sizeof(double), mma_smem = 2 * NB * MP * sizeof(double);
+    static const bool use_mma = getenv("SB_LLT_NO_MMA") == nullptr;   // (A/B hook: the DFMA version of the tile products)
+    if (use_mma) {
+        // blocked right-looking: inside a block of `pw` tile columns every column updates only the block's own columns (narrow
+        // update), and the tiles to the right of the block are read and written ONCE per block for all its columns (trailing
+        // update) -- at the million-tet bar the active window (180 MB of tiles) does not fit the L2, and one pass per column made
+        // the factorisation HBM-bound
+        static const int pw = std::max(1, getenv("SB_LLT_PANEL") ? atoi(getenv("SB_LLT_PANEL")) : 4);
+        for (int k0 = 0; k0 < nt; k0 += pw) {
+            const int k1 = std::min(k0 + pw, nt);
+            for (int j = k0; j < k1; j++) {
+                k_potrf_inv<<<1, 256, 0, st>>>(D.T.p, D.off.p, D.F.p, D.W.p, j, D.d_flags);
+                ctx->launches++;
+                const int m = D.h_act_ptr[j + 1] - D.h_act_ptr[j];
+                if (m <= 0) continue;
+                const int32_t* act = D.act.p + D.h_act_ptr[j];
+                k_tile_product_mma<0><<<m, 128, mma_smem, st>>>(D.T.p, D.off.p, D.F.p, D.W.p, act, m, j, j + 1, D.d_flags);
+                ctx->launches++;
+                int nb = 0;   // active rows of column j that are columns of this block (the list is ascending)
+                while (nb < m && D.h_act[(size_t)D.h_act_ptr[j] + nb] < k1) nb++;
+                if (nb > 0) {
+                    k_tile_product_mma<1><<<dim3(m, nb), 128, mma_smem, st>>>(D.T.p, D.off.p, D.F.p, D.W.p, act, m, j, j + 1, D.d_flags);
+                    ctx->launches++;
+                }
+            }
+            const int mt = D.h_act_ptr[k1] - D.h_act_ptr[k1 - 1];
+            if (mt > 0) {
+                k_tile_product_mma<2><<<(unsigned)((size_t)mt * (mt + 1) / 2), 128, mma_smem, st>>>(D.T.p, D.off.p, D.F.p, D.W.p, D.act.p + D.h_act_ptr[k1 - 1], mt, k0, k1, D.d_flags);
+                ctx->launches++;
+            }
+        }
+    } else
     for (int k = 0; k < nt; k++) {
         k_potrf_inv<<<1, 256, 0, st>>>(D.T.p, D.off.p, D.F.p, D.W.p, k, D.d_flags);
         ctx->launches++;
