@@ -89,6 +89,7 @@ struct Assembly {
     int n_long_static = 0;             // static blocks with more than LONG_SEG sources
     DevBuf<uint32_t> d_final_of_src;   // per dynamic source: its BCSR block (both modes; the projection's dirty marking uses it)
     DevBuf<uint8_t> has_dyn;           // per BCSR block: receives dynamic contributions in this numeric pass
+    DevBuf<unsigned long long> own_range;   // several GPUs: the block range of this rank's rows
     DevBuf<int32_t> hkeys;             // hash table: BCSR block or -1
     DevBuf<double> hacc;               // 9 FP64 accumulators per slot
     size_t hcap = 0;                   // slots (power of two)
@@ -122,7 +123,7 @@ void assembly_destroy(sb_context* ctx)
     if (!A) return;
     A->S.release(); A->D.release();
     A->d_pos.release(); A->d_isnew.release(); A->d_newrank.release(); A->newpos.release(); A->s_final.release(); A->d_final.release();
-    A->seg4.release(); A->blk_row.release(); A->rows.release(); A->cols.release(); A->vals.release(); A->temp.release();
+    A->seg4.release(); A->blk_row.release(); A->rows.release(); A->own_range.release(); A->cols.release(); A->vals.release(); A->temp.release();
     A->dirty.release(); A->long_blocks.release(); A->descs.release();
     A->d_final_of_src.release(); A->has_dyn.release(); A->hkeys.release(); A->hacc.release();
     if (A->ev_loc) { cudaEventDestroy(A->ev_loc); cudaEventDestroy(A->ev_scatter); }
@@ -420,6 +421,8 @@ struct NumericArgs {
     // scatter mode: the dynamic ranges of seg4 are stale; dynamic contributions come from the hash table
     int scatter;
     const uint8_t* has_dyn; const int32_t* hkeys; const double* hacc; uint32_t hmask;
+    // several GPUs sharing the solve: only the blocks [own_range[0], own_range[1]) of this rank's rows are summed (null: all)
+    const unsigned long long* own_range;
 };
 
 // One CTA per long block: 32 strided partial sums per entry, then a fixed shared-memory tree (deterministic).
@@ -433,6 +436,7 @@ __global__ void __launch_bounds__(288) k_assemble_long(const NumericArgs a)
     for (int i = blockIdx.x; i < total; i += gridDim.x) {
         const uint32_t b = a.long_blocks[i];
         if (ONLY_DIRTY && !a.dirty[b]) continue;   // uniform across the CTA
+        if (a.own_range && (b < a.own_range[0] || b >= a.own_range[1])) continue;
         const int4 g = a.seg4[b];
         if (a.scatter && g.y - g.x <= LONG_SEG) continue;   // (long through its dynamic sources at the last rebuild only: the plain kernel sums it; uniform across the CTA)
         double acc = 0.0;
@@ -459,6 +463,7 @@ __global__ void __launch_bounds__(288) k_assemble_numeric(const NumericArgs a)
     const size_t b = t / 9;
     if (b >= a.nnzb) return;
     if (ONLY_DIRTY && !a.dirty[b]) return;
+    if (a.own_range && (b < a.own_range[0] || b >= a.own_range[1])) return;
     const int k = (int)(t - b * 9);
     const int r = k % 3, c = k / 3;
     const int4 g = a.seg4[b];
@@ -889,6 +894,11 @@ int assemble_internal(sb_context* ctx)
     a.vals = A->vals.p; a.dirty = A->dirty.p; a.long_blocks = A->long_blocks.p; a.n_long = A->d_counts; a.nnzb = A->nnzb;
     a.scatter = A->scatter_mode ? 1 : 0;
     a.has_dyn = nullptr; a.hkeys = nullptr; a.hacc = nullptr; a.hmask = 0;
+    a.own_range = nullptr;
+    if (ctx->assemble_own_rows) {
+        A->own_range.ensure(2);
+        if (dist_own_rows_only(ctx, A->rows.p, A->nbr, A->nnzb, A->own_range.p)) a.own_range = A->own_range.p;
+    }
     if (A->scatter_mode) {
         if (A->scatter_done_eval == ctx->eval_id && ctx->n_projected == 0) {
             // the evaluation already ran this pass on a side stream (behind its pattern lookup, under its reductions and its sync;

@@ -293,6 +293,7 @@ struct sb_context {
     sb::Direct* direct = nullptr;
     sb::Dist* dist = nullptr;
     std::vector<void*> user_kernels;   // user.cu: generated kernels owned by this context
+    bool assemble_own_rows = false;    // set by the Newton driver around its assemblies: a shared PCG solve follows, other ranks' rows are not needed
 };
 
 namespace sb {
@@ -316,6 +317,7 @@ void direct_destroy(sb_context* ctx);
 void dist_destroy(sb_context* ctx);
 void user_kernels_destroy(sb_context* ctx);
 bool dist_aborted(sb_context* ctx);
+bool dist_own_rows_only(sb_context* ctx, const unsigned long long* rows, int nbr, size_t nnzb, unsigned long long* d_range2);   // pcg.cu
 int dist_bcast_from_root(sb_context* ctx, double* vec, int n, double* scal, int n_scal);   // pcg.cu: rank 0's values replace every rank's (no-op without peers)
 int potential_create_with_kernel(sb_context* ctx, const KernelInfo* k, const char* kernel_name, int conn_stride, const sb_fetch* fetch, int n_fetch, int* out_potential);
 int solve_llt_internal(sb_context* ctx, int* out_ok, double* out_du_dot_grad, double* out_du_inf);

@@ -185,7 +185,10 @@ extern "C" int sb_newton_solve(sb_context* ctx, const sb_newton_settings* S, sb_
                 ok = prev_ok; cg_it = prev_cg_it;
             } else {
                 if (!assembled || projected_now) {
-                    if ((rc = assemble_internal(ctx))) return rc;
+                    ctx->assemble_own_rows = (S->linear_solver == 1);   // (several GPUs: a shared PCG solve only reads this rank's rows)
+                    rc = assemble_internal(ctx);
+                    ctx->assemble_own_rows = false;
+                    if (rc) return rc;
                     assembled = true;
                 }
                 // _solve_linear_system (NewtonsMethod.cpp:420-451): forcing sequence

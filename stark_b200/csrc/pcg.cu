@@ -1127,6 +1127,35 @@ __global__ void k_dist_needmask(const unsigned long long* __restrict__ rows, con
     }
 }
 
+// The BCSR blocks of this rank's rows: {rows[bound[rank]], rows[bound[rank + 1]]} (same partition rule as the solve).  A rank whose
+// next solve is shared only ever reads its own rows of the matrix, so the numeric assembly can skip the others (assembly.cu).
+__global__ void k_dist_own_blocks(const unsigned long long* __restrict__ rows, int nbr, unsigned long long nnzb, int world, int rank, int grid,
+                                  unsigned long long* __restrict__ out2)
+{
+    if (threadIdx.x < 2) {
+        const unsigned long long cost = nnzb + ROW_COST * (unsigned long long)nbr;
+        const int q = rank + (int)threadIdx.x;
+        const int r = (q == world) ? nbr : row_lower_bound(rows, nbr, (cost * (unsigned long long)(q * grid)) / (unsigned long long)(world * grid));
+        out2[threadIdx.x] = rows[r];
+    }
+}
+// Will the solve that follows an assembly of this pattern be shared by all ranks?  If so, queue the computation of this rank's block
+// range into d_range2 and return true (the caller then assembles only that range).
+bool dist_own_rows_only(sb_context* ctx, const unsigned long long* rows, int nbr, size_t nnzb, unsigned long long* d_range2)
+{
+    Dist* D = ctx->dist;
+    Pcg* P = ctx->pcg;
+    if (!D || !D->connected || !D->enabled || D->world <= 1 || !P || P->grid == 0) return false;
+    static const bool off = std::getenv("SB_DIST_FULL_ASSEMBLY") != nullptr;   // diagnostic hook
+    if (off) return false;
+    static const bool always = std::getenv("SB_DIST_POLICY") && std::string(std::getenv("SB_DIST_POLICY")) == "always";
+    const double resident1 = 1.08 * (40.0 * (double)nnzb + 160.0 * (double)nbr) / P->grid;
+    if (!always && resident1 <= (double)P->smem_bytes) return false;           // the policy keeps this solve local: it needs the whole matrix
+    k_dist_own_blocks<<<1, 32, 0, ctx->stream>>>(rows, nbr, (unsigned long long)nnzb, D->world, D->rank, P->grid, d_range2);
+    ctx->launches++;
+    return true;
+}
+
 // ---- rank 0 is authoritative: broadcast of a vector + a few scalars from rank 0 to every rank, in stream order ----
 // Every rank drives the same scene, but FP64 atomics (gradient scatter, contact tables filled in arrival order) make the last bits
 // of the gradient and of the energy differ from rank to rank; left alone, the replicas drift apart (measurably within tens of
