@@ -9,7 +9,9 @@ path.  Workload at N = 1: BASELINE.json configs[1] (C2) -- 26^3 tet grid (210,91
 dropped on a fixed rigid floor with IPC contact and friction; `--config C1|C3|C4|C5` runs the other BASELINE configurations
 (both arms).  For N > 1 the N ranks work on ONE scene (strong scaling): every block-Jacobi PCG solve is shared by all ranks --
 row slabs of the matrix, each rank keeping 1/N of it in shared memory, halo / partial sums / barrier over NVLink peer memory
-inside the persistent kernel (DESIGN.md "Multi-GPU"); evaluation and assembly are replicated.  `--replicas` runs N independent
+inside the persistent kernel (DESIGN.md "Multi-GPU"); each rank assembles only its own rows, element evaluation and projection are
+replicated with rank 0's gradient / energy broadcast to every rank.  The default configuration at N > 1 is C5 (the 1M-tet bar
+BASELINE.json names for the 1/2/4/8-GPU sweep); the line carries the same run's single-GPU rate.  `--replicas` runs N independent
 scenes instead (weak scaling, no data-plane exchange).
 
 Printed keys (one JSON line on rank 0):
@@ -58,8 +60,8 @@ def workload_config(n_gpus, name, cfg, grid=None, replicas=False):
         par = f"{n_gpus} independent replicas (one scene per GPU)"
     else:
         par = (f"slab decomposition of the linear solve over {n_gpus} GPUs: contiguous block-row ranges of the 3x3-BCSR per rank (1/{n_gpus} of the matrix in each "
-               "rank's shared memory), halo of u + dot-product partials + barrier as NVLink peer-memory stores inside the persistent PCG kernel; element "
-               "evaluation, projection and assembly replicated on every rank")
+               "rank's shared memory), halo of u + dot-product partials + barrier as NVLink peer-memory stores inside the persistent PCG kernel; each rank "
+               "assembles only its own rows; element evaluation and projection replicated on every rank (rank 0's gradient / energy broadcast)")
     return {"workload": cfg["workload"] if not reduced else f"{cfg['scene']} at a reduced grid {n} (NOT the benchmark configuration)",
             "name": name, "scene": cfg["scene"], "grid": n, "dt": 0.01,
             "parallelism": par,
@@ -137,7 +139,7 @@ def main():
                     help="BASELINE.json configuration; default: C2 at --gpus 1 (the 1xB200 configuration the metric is quoted on), C5 at --gpus N > 1 (the "
                          "1M-tet bar BASELINE.json names for the 1/2/4/8-GPU sweep)")
     ap.add_argument("--grid", type=int, default=None, help="override the grid size (diagnostic: NOT the benchmark configuration)")
-    ap.add_argument("--llt", action="store_true", help="DirectLLT instead of the default BDPCG (both arms; reference: Eigen SimplicialLLT, ours: dense blocked Cholesky, <= 32k DoFs)")
+    ap.add_argument("--llt", action="store_true", help="DirectLLT instead of the default BDPCG (both arms; reference: Eigen SimplicialLLT, ours: sparse tile-envelope Cholesky with DMMA tile products)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--replicas", action="store_true", help="N > 1: N independent scenes (weak scaling) instead of one scene with the distributed solve")
     ap.add_argument("--stage-steps", type=int, default=4, help="extra (untimed) steps run with stage profiling on after the timed region; 0 = off")
