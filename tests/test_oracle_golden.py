@@ -115,3 +115,32 @@ def test_oracle_projection_matches_reference(fixture):
         assert errs[k] <= 1e-9, (r, errs)
         n_changed += by_rows[r][k][1]
     assert n_changed > 0
+
+
+def test_oracle_sequence_interpreter_matches_reference():
+    """The operation sequences the reference produced for a user potential (examples/main.cpp:666-690 EnergyMagneticAttraction,
+    fixture magnet_n2), run through the oracle's interpreter on the gathered inputs, reproduce the outputs of the reference's own
+    JIT-compiled code: pins the meaning of the sb_op encoding the GPU back-end (stark_b200/csrc/user.cu) translates."""
+    g = Golden("magnet_n2")
+    i, p = next((i, p) for i, p in g.potentials() if p.get("user_ops"))
+    arrays = {k: g[f"array{k}"] for k in range(len(g.meta["arrays"]))}
+    maps = [(m["array"], m["conn_idx"], m["first_symbol"], m["stride"]) for m in p["maps"]]
+    conn = g[f"pot{i}_conn"][g[f"pot{i}_active"].astype(bool)]
+    X = oracle.gather_inputs(p["n_in"], conn, maps, arrays)
+    ref = g[f"pot{i}_sol"][g[f"pot{i}_active"].astype(bool)]
+    out = oracle.evaluate_sequence(g[f"pot{i}_ops_pgh"], g[f"pot{i}_opsc_pgh"], X, p["n_out"])
+    assert out.shape == ref.shape
+    assert np.abs(out - ref).max() <= 1e-12 * np.abs(ref).max()
+    E_only = oracle.evaluate_sequence(g[f"pot{i}_ops_p"], g[f"pot{i}_opsc_p"], X, 1)
+    assert np.abs(E_only[:, 0] - ref[:, 0]).max() <= 1e-13 * np.abs(ref[:, 0]).max()
+
+
+def test_oracle_sequence_interpreter_branches():
+    """if / else / end-if of the reference's branch encoding: E = k/2 |x|^2 where k > 0, else 0 (hand-written sequence)."""
+    ADD, MUL, CONST, OUT, BRANCH = 6, 8, 4, 5, 2
+    ops = [(MUL, 2, 0, 0, 0), (CONST, 3, -1, -1, 0), (MUL, 4, 3, 1, 0), (MUL, 5, 4, 2, 0), (CONST, 6, -1, -1, 0),
+           (BRANCH, -1, 0, -1, 1), (OUT, 0, 5, -1, 0), (BRANCH, -1, 1, -1, 1), (OUT, 0, 6, -1, 0), (BRANCH, -1, -1, -1, -2)]
+    consts = [0, 0.5, 0, 0, 0.0, 0, 0, 0, 0, 0]
+    X = np.array([[2.0, 3.0], [2.0, -1.0], [0.5, 0.0]])
+    out = oracle.evaluate_sequence(np.array(ops), np.array(consts), X, 1)
+    assert np.array_equal(out[:, 0], [6.0, 0.0, 0.0])

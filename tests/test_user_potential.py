@@ -135,3 +135,42 @@ def test_reference_sequences_of_a_user_potential_compile(tmp_path, monkeypatch):
     if rc == -4:
         pytest.skip("NVRTC is not installed here")
     assert rc == 0 and size.value > 1000, log.value.decode()
+
+
+def test_generated_statements_evaluate_like_the_reference_on_the_host(tmp_path):
+    """The statement list the generator prints for the reference's own sequences (magnet_n2) is plain C: compiled with gcc and run
+    on the fixture's gathered inputs it reproduces the per-element [E | grad | hess] of the reference's JIT-compiled code --
+    a check of the generator's text itself that needs no GPU."""
+    import re
+    import subprocess
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import oracle
+    from golden_util import Golden
+    g = Golden("magnet_n2")
+    i, p = next((i, p) for i, p in g.potentials() if p.get("user_ops"))
+    lib = capi.load()
+    ops_p = capi.ops_array(g[f"pot{i}_ops_p"], g[f"pot{i}_opsc_p"])
+    ops_pgh = capi.ops_array(g[f"pot{i}_ops_pgh"], g[f"pot{i}_opsc_pgh"])
+    n = C.c_longlong()
+    assert lib.sb_user_codegen(p["name"].encode(), p["n_in"], 1, ops_p, len(ops_p), ops_pgh, len(ops_pgh), None, 0, C.byref(n)) == 0
+    buf = C.create_string_buffer(n.value + 1)
+    assert lib.sb_user_codegen(p["name"].encode(), p["n_in"], 1, ops_p, len(ops_p), ops_pgh, len(ops_pgh), buf, n.value + 1, None) == 0
+    src = buf.value.decode()
+    m = re.search(r"void f_pgh\(const double\* __restrict__ in, double\* __restrict__ out\)\n\{\n(.*?)\n\}\n__device__", src, re.S)
+    assert m, "f_pgh not found in the generated source"
+    c_file = tmp_path / "f_pgh.c"
+    c_file.write_text("#include <math.h>\n#define SB_INF INFINITY\nvoid f_pgh(const double* in, double* out)\n{\n" + m.group(1) + "\n}\n")
+    so = tmp_path / "f_pgh.so"
+    subprocess.run(["gcc", "-O1", "-ffp-contract=off", "-shared", "-fPIC", str(c_file), "-o", str(so), "-lm"], check=True)
+    f = C.CDLL(str(so)).f_pgh
+    arrays = {k: g[f"array{k}"] for k in range(len(g.meta["arrays"]))}
+    maps = [(mm["array"], mm["conn_idx"], mm["first_symbol"], mm["stride"]) for mm in p["maps"]]
+    conn = g[f"pot{i}_conn"][g[f"pot{i}_active"].astype(bool)]
+    X = np.ascontiguousarray(oracle.gather_inputs(p["n_in"], conn, maps, arrays))
+    ref = g[f"pot{i}_sol"][g[f"pot{i}_active"].astype(bool)]
+    out = np.zeros_like(ref)
+    for e in range(X.shape[0]):
+        f(X[e].ctypes.data_as(C.POINTER(C.c_double)), out[e].ctypes.data_as(C.POINTER(C.c_double)))
+    assert np.abs(out - ref).max() <= 1e-12 * np.abs(ref).max()
