@@ -38,3 +38,11 @@ def test_distributed_pcg_streaming_slices():
     """The same with a shared-memory budget too small for the slices (the path of million-tet scenes on few GPUs)."""
     r = _run(2, "tetdrop_n5", {"SB_PCG_SMEM_LIMIT": "4096"})
     assert r["identical_across_ranks"]
+
+
+@pytest.mark.gpu
+def test_policy_keeps_resident_solves_local_and_adopts_rank0_du():
+    """SB_DIST_POLICY=auto: a matrix that is resident in one GPU's shared memory is solved locally by every rank (no cross-GPU
+    barrier is executed), and every rank then adopts rank 0's du (dist_bcast_from_root), so the replicas stay identical."""
+    r = _run(2, "tetdrop_n5", {"SB_DIST_POLICY": "auto"})
+    assert r["barriers"] == 0 and r["identical_across_ranks"] and r["rank0_gradient_everywhere"]
