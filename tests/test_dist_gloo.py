@@ -165,3 +165,121 @@ def test_plan_partition_matches_virtual_grid_rule():
         assert bounds[w] == 100
         if w == 1:
             assert not mask.any()
+
+
+# ---- the whole distributed solve in numpy over gloo: Chronopoulos-Gear PCG, row slabs, halo pushes, shared partials ----
+
+def _cg_worker(rank, world_size, port, out):
+    """What the DIST instances of k_pcg_solve do (stark_b200/csrc/pcg.cu), restated per rank: every rank owns the rows
+    [bounds[rank], bounds[rank + 1]) of the replicated matrix, keeps x, r, p, s, w only for them, pushes the rows of u = M^-1 r its
+    peer reads (needmask) before every product, and all ranks sum the same per-rank partials in the same order."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    from stark_b200 import dist as sbdist
+    nbr = 180
+    rows, cols, blocks = _band_matrix(nbr, 5, seed=11)
+    vals = np.stack([b.T.reshape(9) for b in blocks]).astype(np.float32).reshape(-1)   # BCSR: float, column-major blocks
+    rows_i = rows.astype(np.int64)
+    b = np.random.default_rng(3).standard_normal(3 * nbr)
+    bounds, mask = sbdist.plan(rows, cols, world_size, 7, rank)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    peer = 1 - rank
+    send_rows = np.nonzero(mask & (1 << peer))[0]
+    n_send = torch.tensor([len(send_rows)], dtype=torch.int64)
+    counts = [torch.zeros(1, dtype=torch.int64) for _ in range(world_size)]
+    dist.all_gather(counts, n_send)
+    recv_rows_t = torch.zeros(int(counts[peer].item()), dtype=torch.int64)
+    if rank == 0:
+        dist.send(torch.tensor(send_rows, dtype=torch.int64), dst=1); dist.recv(recv_rows_t, src=1)
+    else:
+        dist.recv(recv_rows_t, src=0); dist.send(torch.tensor(send_rows, dtype=torch.int64), dst=0)
+    recv_rows = recv_rows_t.numpy()
+    dinv = oracle.block_jacobi(rows_i, cols, vals).astype(np.float64).reshape(-1, 3, 3)
+
+    def own(v):
+        return v[3 * lo:3 * hi]
+
+    def prec_own(r_own):
+        return np.einsum("kij,kj->ki", dinv[lo:hi], r_own.reshape(-1, 3)).reshape(-1)
+
+    def exchange(u_full):
+        """halo push: my rows the peer reads -> its copy of u; its rows I read -> mine (NaN everywhere else stays NaN)"""
+        payload = torch.tensor(u_full.reshape(-1, 3)[send_rows].ravel(), dtype=torch.float64)
+        got = torch.zeros(3 * len(recv_rows), dtype=torch.float64)
+        if rank == 0:
+            dist.send(payload, dst=1); dist.recv(got, src=1)
+        else:
+            dist.recv(got, src=0); dist.send(payload, dst=0)
+        u_full.reshape(-1, 3)[recv_rows] = got.numpy().reshape(-1, 3)
+
+    def allsum(*partials):
+        t = torch.tensor(list(partials), dtype=torch.float64)
+        parts = [torch.zeros_like(t) for _ in range(world_size)]
+        dist.all_gather(parts, t)
+        return [sum(p[k].item() for p in parts) for k in range(len(partials))]     # rank order: identical everywhere
+
+    blocks64 = vals.reshape(-1, 3, 3).transpose(0, 2, 1).astype(np.float64)   # the float-stored blocks, row-major
+
+    def spmv_own(u_full):
+        return _spmv_rows(rows_i, cols, blocks64, u_full, lo, hi)
+
+    abs_tol, rel_tol, max_iter = 1e-10, 1e-12, 500
+    x = np.zeros(3 * (hi - lo)); r = own(b).copy(); p = np.zeros_like(x); s = np.zeros_like(x)
+    u_full = np.full(3 * nbr, np.nan)
+    u_full[3 * lo:3 * hi] = prec_own(r)
+    bb, gamma = allsum(float(r @ r), float(r @ own(u_full)))
+    exchange(u_full)
+    w = spmv_own(u_full)
+    assert np.all(np.isfinite(w))                     # the halo lists cover every column the own rows read
+    (delta,) = allsum(float(w @ own(u_full)))
+    alpha, beta, it, ok = gamma / delta, 0.0, 0, False
+    while it < max_iter:
+        it += 1
+        u_own = own(u_full).copy()
+        p = u_own + beta * p
+        s = w + beta * s
+        x += alpha * p
+        r -= alpha * s
+        u_full[:] = np.nan
+        u_full[3 * lo:3 * hi] = prec_own(r)
+        rr, gamma_new = allsum(float(r @ r), float(r @ own(u_full)))
+        if np.sqrt(rr / bb) < abs_tol or np.sqrt(rr / bb) < rel_tol:
+            ok = True
+            break
+        exchange(u_full)
+        w = spmv_own(u_full)
+        (delta,) = allsum(float(w @ own(u_full)))
+        beta = gamma_new / gamma
+        pAp = delta - beta * gamma_new / alpha
+        gamma = gamma_new
+        assert pAp > 0.0
+        alpha = gamma / pAp
+    # du: every rank's slice to everybody
+    mine = torch.zeros(3 * nbr, dtype=torch.float64)
+    mine[3 * lo:3 * hi] = torch.tensor(x)
+    dist.all_reduce(mine)
+    out[rank] = (it, ok, mine.numpy().tolist())
+    dist.destroy_process_group()
+
+
+def test_two_rank_distributed_pcg_over_gloo_matches_the_oracle():
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_cg_worker, args=(2, port, out), nprocs=2, join=True)
+    it0, ok0, x0 = out[0]
+    it1, ok1, x1 = out[1]
+    assert ok0 and ok1 and it0 == it1 and x0 == x1            # same decisions, bit-identical solution on both ranks
+    rows, cols, blocks = _band_matrix(180, 5, seed=11)
+    vals = np.stack([b.T.reshape(9) for b in blocks]).astype(np.float32).reshape(-1)
+    b = np.random.default_rng(3).standard_normal(540)
+    x_ref, it_ref, ok_ref = oracle.solve_pcg(rows.astype(np.int64), cols, vals, b, 1e-10, 1e-12, 500)
+    assert ok_ref and abs(it_ref - it0) <= 1                  # Chronopoulos-Gear = textbook PCG in exact arithmetic
+    assert np.abs(np.array(x0) - x_ref).max() <= 1e-8 * np.abs(x_ref).max()
