@@ -283,3 +283,30 @@ def test_two_rank_distributed_pcg_over_gloo_matches_the_oracle():
     x_ref, it_ref, ok_ref = oracle.solve_pcg(rows.astype(np.int64), cols, vals, b, 1e-10, 1e-12, 500)
     assert ok_ref and abs(it_ref - it0) <= 1                  # Chronopoulos-Gear = textbook PCG in exact arithmetic
     assert np.abs(np.array(x0) - x_ref).max() <= 1e-8 * np.abs(x_ref).max()
+
+
+def test_plan_send_lists_are_consistent_for_eight_ranks():
+    """For every pair of ranks: what r pushes to q (needmask of r, bit q) is exactly the set of columns in r's rows that q's rows
+    reference -- checked in one process on a band matrix with a dense row, for the 8-rank partition of one NVSwitch domain."""
+    import numpy as np
+    from stark_b200 import dist as sbdist
+    nbr, W, grid = 400, 8, 3
+    rows, cols, _ = _band_matrix(nbr, 7, seed=5)
+    plans = [sbdist.plan(rows, cols, W, grid, r) for r in range(W)]
+    bounds = plans[0][0]
+    assert all(np.array_equal(bounds, p[0]) for p in plans) and bounds[0] == 0 and bounds[W] == nbr and np.all(np.diff(bounds) > 0)
+    owner = np.searchsorted(bounds, np.arange(nbr), side="right") - 1
+    for r in range(W):
+        mask = plans[r][1]
+        assert not np.any(mask[owner != r]) and not np.any(mask & (1 << r))
+        for q in range(W):
+            if q == r:
+                continue
+            need = set()
+            for i in range(int(bounds[q]), int(bounds[q + 1])):
+                for c in cols[int(rows[i]):int(rows[i + 1])] // 3:
+                    if owner[c] == r:
+                        need.add(int(c))
+            assert need == set(np.nonzero(mask & (1 << q))[0].tolist()), (r, q)
+    # the dense last row (a rigid body) makes the last rank read rows of every other rank
+    assert all(np.any(plans[r][1] & (1 << (W - 1))) for r in range(W - 1))

@@ -91,3 +91,39 @@ def test_disconnected_components_and_empty():
     perm = _order(2 * n, rows2, cols2)
     assert sorted(perm.tolist()) == list(range(2 * n))
     assert _order(0, np.zeros(1, dtype=np.uint64), np.zeros(0, dtype=np.int32)).size == 0
+
+
+def test_cholesky_fill_stays_inside_the_tile_row_envelope():
+    """The factor of sb_solve_llt is stored as a row envelope of 64 x 64 tiles (per tile row the run F(I) .. I, F from the
+    pattern of the permuted matrix): on a fixture's real pattern -- tet block under hinged rigid boxes, i.e. with dense rigid-body
+    rows -- the dense numpy Cholesky factor of the permuted matrix has no entry outside that envelope, and the envelope is much
+    smaller than the dense lower triangle."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from golden_util import Golden
+    NB = 64
+    for name, max_fraction in (("tetbar_n2", 0.9), ("tetchain_n3", 0.95), ("tetdrop_n5", 0.9)):
+        g = Golden(name)
+        rows, cols, vals = g["bcsr_rows"].astype(np.uint64), g["bcsr_cols"].astype(np.int32), g["bcsr_vals"].astype(np.float64)
+        nbr = len(rows) - 1
+        perm = _order(nbr, rows, cols)
+        n = 3 * nbr
+        A = np.zeros((n, n))
+        blocks = vals.reshape(-1, 3, 3).transpose(0, 2, 1)
+        for i in range(nbr):
+            for j in range(int(rows[i]), int(rows[i + 1])):
+                c = int(cols[j]) // 3
+                A[3 * perm[i]:3 * perm[i] + 3, 3 * perm[c]:3 * perm[c] + 3] = blocks[j]
+        A = np.tril(A) + np.tril(A, -1).T
+        pattern = A != 0.0
+        A = A + (np.abs(A).sum(axis=1).max() + 1.0) * np.eye(n)           # diagonally dominant: positive definite, same pattern
+        L = np.linalg.cholesky(A)
+        nt = (n + NB - 1) // NB
+        F = np.arange(nt)
+        ii, jj = np.nonzero(np.tril(pattern))
+        np.minimum.at(F, ii // NB, jj // NB)
+        li, lj = np.nonzero(np.abs(L) > 1e-13 * np.abs(L).max())
+        assert np.all(lj // NB >= F[li // NB]), name
+        tiles = int(np.sum(np.arange(nt) - F + 1))
+        assert tiles <= max_fraction * nt * (nt + 1) // 2 or nt <= 3, (name, tiles, nt)
